@@ -1,0 +1,346 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the loudness hot path (BASELINE.json).
+
+Metric: PCM Gsamples/s for the fused K-weight + gate + true-peak measurement,
+whole job over N GPUs.  Workload at every N: BASELINE.json configs[1], a
+synthetic 12-track 44.1 kHz stereo 16-bit album per GPU (album mode: per-track
+and album results), generated on the device.  One "step" = one complete
+measurement of the rank's album: sweep, FP64 fix-up, gating, range, peaks,
+and the read-back of the per-track / per-album scalars.
+
+  value     whole-job Gsamples/s with the PCM already resident in HBM
+  e2e       the same album through the drop-in C ABI (ebur128_init /
+            add_frames_short / queries, driven like scan.c) from pinned HOST
+            buffers, copies inside the timed region
+  roofline  the sweep kernel's algorithmic bytes (2 B per S16 sample, read
+            once) / its mean launch time (CUDA events on the launching
+            stream) against the measured HBM copy bandwidth
+  cpu_baseline  the CPU oracle (restatement of the reference's libebur128
+            path) on one host core over a bounded sample of the same album
+
+`--impl reference` times the reference's CPU path instead (the oracle port:
+libebur128 itself is not in /root/reference), on all host cores, one worker
+per track like bin/rgbpm2.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pcm_gsamples_per_s_kweight_gate_truepeak"
+UNIT = "Gsamples/s"
+WORKLOAD = "cfg2: 12-track 44.1 kHz stereo S16 album per GPU, album mode (-a -k quantities)"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_album(device, rank: int):
+    """cfg2 on `device`: list of (int16 tensor [frames, 2], rate)."""
+    from loudgain_b200 import synth
+    specs = synth.config2_specs(12)
+    for s in specs:
+        s.seed += 1000 * rank            # every rank scans a different album
+    return [(synth.programme_s16(s, device=device), s.rate) for s in specs]
+
+
+# ------------------------------------------------------------------ CPU arms
+
+def _oracle_scan(lib, pcm_list, rate_list, chunk=1024, threads=1):
+    """scan.c's sequence on the oracle; returns seconds."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(i):
+        st = lib.init(pcm_list[i].shape[1], rate_list[i])
+        st.add_frames(pcm_list[i], chunk)
+        r = (st.loudness_global(), st.loudness_range(), max(st.true_peaks()))
+        return st, r
+
+    t0 = time.perf_counter()
+    if threads > 1:
+        with ThreadPoolExecutor(threads) as ex:       # ctypes drops the GIL inside the C calls
+            done = list(ex.map(one, range(len(pcm_list))))
+    else:
+        done = [one(i) for i in range(len(pcm_list))]
+    states = [d[0] for d in done]
+    lib.loudness_global_multiple(states)
+    lib.loudness_range_multiple(states)
+    dt = time.perf_counter() - t0
+    for st in states:
+        st.destroy()
+    return dt
+
+
+def reference_arm(args):
+    """The reference's CPU path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from loudgain_b200 import synth
+    from oracle import load_oracle
+    lib = load_oracle()
+    cores = os.cpu_count() or 1
+    seconds = 60.0
+    specs = synth.config2_specs(12)
+    pcm, rates = [], []
+    for s in specs:
+        s.seconds = min(s.seconds, seconds)
+        pcm.append(synth.programme_s16(s).numpy())
+        rates.append(s.rate)
+    samples = sum(p.size for p in pcm)
+    threads = min(cores, len(pcm))
+    for _ in range(args.warmup):
+        _oracle_scan(lib, pcm[:threads], rates[:threads], threads=threads)
+    times = [_oracle_scan(lib, pcm, rates, threads=threads) for _ in range(args.steps)]
+    total = sum(times)
+    value = samples * args.steps / total / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"first {seconds:.0f} s of each of the 12 tracks",
+                   "feed": "ebur128_add_frames_short, 1024-frame calls (scan.c:448)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"first {seconds:.0f} s of each of the 12 album tracks per step; "
+                                   "one worker thread per track (rgbpm2 model)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "host_cores": cores,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(album_host, rates):
+    """One core, bounded sample (about 10-20 s of CPU work)."""
+    from oracle import load_oracle
+    lib = load_oracle()
+    budget = 120_000_000            # samples: ~12 s at ~10 Msamples/s
+    pcm, rr, n = [], [], 0
+    for p, r in zip(album_host, rates):
+        if n >= budget:
+            break
+        take = min(p.shape[0], (budget - n) // p.shape[1])
+        pcm.append(p[:take]); rr.append(r); n += take * p.shape[1]
+    dt = _oracle_scan(lib, pcm, rr, threads=1)
+    return {"value": n / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{len(pcm)} tracks / {n} samples of the same album, 1024-frame calls, "
+                      "single thread (loudgain is single-threaded)"}
+
+
+# ------------------------------------------------------------------- GPU arm
+
+class HostTrack(C.Structure):
+    _fields_ = [("pcm", C.c_void_p), ("frames", C.c_uint64), ("channels", C.c_uint32),
+                ("samplerate", C.c_uint32), ("format", C.c_uint32)]
+
+
+class ScanResult(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "track_gain", "track_peak", "track_loudness", "track_loudness_range", "album_gain",
+        "album_peak", "album_loudness", "album_loudness_range", "loudness_reference")]
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from loudgain_b200 import build, engine
+
+    build()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    album = make_album(dev, rank)
+    albums = [0] * len(album)
+    stream = torch.cuda.current_stream()
+    batch = engine.Batch(album, albums, stream)
+    L = engine._bind()
+    L.lgb_batch_enable_timing.argtypes = [C.c_void_p, C.c_int]
+    L.lgb_batch_sweep_ms.argtypes = [C.c_void_p]
+    L.lgb_batch_sweep_ms.restype = C.c_double
+    samples = batch.total_samples
+    pcm_bytes = sum(t.numel() * t.element_size() for t, _ in album)
+
+    def merged_album():
+        """Album over ALL ranks' tracks: all-gather the block lists over NCCL,
+        then run the gating / range kernel over the union on every rank."""
+        if world == 1:
+            return None
+        return engine.merge_album_across_ranks(batch, range(len(album)), dist, world)
+
+    def step():
+        batch.run()
+        res = batch.fetch()
+        return res, merged_album()
+
+    # ---- resident-PCM throughput
+    for _ in range(args.warmup):
+        step()
+    L.lgb_batch_enable_timing(batch._h, 1)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record(stream)
+        for _ in range(args.steps):
+            (tres, ares), merged = step()
+        e1.record(stream)
+        barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    sweep_ms = L.lgb_batch_sweep_ms(batch._h)
+    L.lgb_batch_enable_timing(batch._h, 0)
+    value = samples * world * args.steps / (ms_total * 1e-3) / 1e9
+
+    # ---- end to end through the drop-in ABI from pinned host memory
+    host = [t.cpu().pin_memory() for t, _ in album]
+    arr = (HostTrack * len(host))()
+    for i, (h, (_, rate)) in enumerate(zip(host, album)):
+        arr[i] = HostTrack(h.data_ptr(), h.shape[0], h.shape[1], rate, 0)
+    out = (ScanResult * len(host))()
+    L.lgb_scan_host.argtypes = [C.POINTER(HostTrack), C.c_size_t, C.c_size_t, C.c_int, C.c_double,
+                                C.POINTER(ScanResult)]
+    chunk = 4096
+    os.environ.setdefault("LOUDGAIN_B200_DEVICE", str(local))
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(min(args.warmup, 2)):
+        assert L.lgb_scan_host(arr, len(host), chunk, 1, 0.0, out) == 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        assert L.lgb_scan_host(arr, len(host), chunk, 1, 0.0, out) == 0
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = samples * world * e2e_steps / float(dt.item()) / 1e9
+    d2h = (len(host) + 1) * 64 + 2 * 4 * sum(h.shape[1] for h in host)
+
+    # ---- consistency: both paths measured the same album
+    for i in range(len(host)):
+        assert abs(out[i].track_loudness - tres[i].loudness) < 1e-9, "e2e and resident paths disagree"
+    assert abs(out[0].album_loudness - ares[0].loudness) < 1e-9
+
+    if rank == 0:
+        hbm, src = _peaks()
+        achieved = samples * 2 / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None
+        cpu = cpu_baseline_leg([h.numpy() for h in host], [r for _, r in album])
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "samples_per_gpu": samples,
+                       "pcm_bytes_per_gpu": pcm_bytes,
+                       "l2_policy": "input (508 MB per GPU) is larger than L2 (126 MB); no flush",
+                       "sharding": "by track; album block lists all-gathered over NCCL" if world > 1
+                                   else "single GPU",
+                       "e2e_feed": f"ebur128_add_frames_short, {chunk}-frame calls, pinned host PCM"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                         "frac": achieved / hbm if achieved else None, "traffic": None,
+                         "kernel": "sweep_kernel<S16,4x>", "kernel_ms": sweep_ms,
+                         "peak_source": src,
+                         "algorithmic_bytes": "2 B per S16 sample, read once (SURVEY 8d)"},
+            "cpu_baseline": cpu,
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pcm_bytes,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": batch.kernel_launches * args.steps,
+            "album_loudness": ares[0].loudness, "album_range": ares[0].range,
+            "merged_album_loudness": merged.loudness if merged else None,
+            "host_cores": os.cpu_count(),
+        }
+        print(json.dumps(line), flush=True)
+    batch.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,126 @@
+/*
+ * ebur128_b200.h -- batch extension of the B200 loudness library.
+ *
+ * The ebur128_* functions of ebur128.h are the drop-in surface that
+ * /root/reference/src/scan.c binds to.  This header adds what the reference
+ * API cannot express: measuring many tracks whose PCM is ALREADY resident in
+ * HBM in one pass (album and library scans), which is
+ * also what the ebur128_* layer itself calls at query time.  Plain C ABI: raw
+ * device pointers and sizes, no CUDA or torch types in the signatures.
+ *
+ * One batch = a set of tracks + the queries over them: one per track
+ * (ebur128_loudness_global / _range / peaks, scan.c:294-307) and one per
+ * album (ebur128_loudness_global_multiple / _range_multiple, scan.c:383-391).
+ */
+#ifndef EBUR128_B200_H_
+#define EBUR128_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGB_FORMAT_S16 0u      /* what scan.c:414 feeds: interleaved int16 */
+#define LGB_FORMAT_F32 1u      /* ebur128_add_frames_float layout */
+#define LGB_NO_ALBUM 0xffffffffu
+
+typedef struct lgb_batch lgb_batch;
+
+typedef struct {
+  const void* pcm;             /* DEVICE pointer, interleaved [frames][channels], 16-byte aligned */
+  uint64_t frames;
+  uint32_t channels;           /* 1..64 */
+  uint32_t samplerate;
+  uint32_t format;             /* LGB_FORMAT_* */
+  uint32_t album;              /* album index < nalbums, or LGB_NO_ALBUM */
+  const uint8_t* weight_class; /* optional HOST array [channels]: 0 unused, 1 -> 1.0,
+                                  2 -> 1.41, 3 -> 2.0; NULL = default channel map */
+} lgb_track;
+
+typedef struct {
+  double loudness;             /* LUFS; -HUGE_VAL if nothing passed the gates */
+  double range;                /* LU */
+  double rel_threshold;        /* relative gate, as block energy */
+  double sum_abs, sum_rel;     /* block-energy sums behind the two gates */
+  uint64_t n_abs, n_rel;       /* block counts behind the two gates */
+  uint64_t n_shortterm;        /* short-term blocks above the absolute gate */
+} lgb_result;
+
+/* Last error message of the calling thread ("" if none). */
+const char* lgb_last_error(void);
+
+/* Plans a batch on the current CUDA device and allocates its workspace.
+ * `cuda_stream` is a cudaStream_t (NULL = default stream).  NULL on failure. */
+lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t ntracks, uint32_t nalbums,
+                            void* cuda_stream);
+
+/* Enqueues the whole measurement (sweep, fix-up, gating, range) on the
+ * batch's stream.  Asynchronous; 0 on success. */
+int lgb_batch_run(lgb_batch* b);
+
+/* Waits for the stream and copies results to the host.  Any pointer may be
+ * NULL.  Peaks are linear amplitudes laid out track after track, one value
+ * per channel; true_peaks already folds in the sample peak, as
+ * ebur128_true_peak does. */
+int lgb_batch_fetch(lgb_batch* b, lgb_result* track_results, lgb_result* album_results,
+                    double* sample_peaks, double* true_peaks);
+
+/* Plan facts. */
+uint64_t lgb_batch_total_samples(const lgb_batch* b);   /* frames*channels over all tracks */
+uint64_t lgb_batch_peak_count(const lgb_batch* b);      /* sum of channels */
+uint32_t lgb_batch_kernel_launches(const lgb_batch* b); /* kernels one run launches */
+uint32_t lgb_batch_sweep_launches(const lgb_batch* b);  /* of which sweep kernels */
+
+/* Device views for diagnostics and multi-GPU merges (valid after run + sync):
+ * kind 0 = 400 ms gating blocks, 1 = 3 s short-term blocks, 2 = 100 ms slot
+ * energies of `track`.  Returns the element count and stores the DEVICE
+ * pointer (doubles). */
+uint64_t lgb_batch_blocks(const lgb_batch* b, size_t track, int kind, const double** dev_ptr);
+
+/* Kernel timing for benchmarks: when enabled, every run brackets its sweep
+ * launches with CUDA events on the batch's stream; fetch accumulates them.
+ * lgb_batch_sweep_ms returns the mean sweep time per run in milliseconds over
+ * the runs fetched since timing was (re-)enabled, 0 if none. */
+void lgb_batch_enable_timing(lgb_batch* b, int on);
+double lgb_batch_sweep_ms(const lgb_batch* b);
+
+void lgb_batch_destroy(lgb_batch* b);
+
+/* Gated loudness + range over the union of `n` block lists that live in
+ * device memory (e.g. lists all-gathered from other GPUs over NCCL).
+ * z[i] / st[i] are DEVICE pointers to doubles.  Synchronous.  0 on success. */
+int lgb_query_lists(const double* const* z, const uint32_t* nz, const double* const* st,
+                    const uint32_t* nst, size_t n, void* cuda_stream, lgb_result* out);
+
+/* ---- scan.c-shaped host driver -------------------------------------------
+ * Replays the reference scanner's call sequence against the ebur128_* ABI of
+ * this library for PCM held in HOST memory: scan_file's per-frame
+ * ebur128_add_frames_short loop (scan.c:225-256,448), scan_get_track_result
+ * (scan.c:275-330) and scan_set_album_result (scan.c:380-405), including the
+ * reference's habit of re-querying the album once per track. */
+typedef struct {
+  const void* pcm;            /* HOST pointer, interleaved */
+  uint64_t frames;
+  uint32_t channels;
+  uint32_t samplerate;
+  uint32_t format;            /* LGB_FORMAT_* */
+} lgb_host_track;
+
+typedef struct {              /* mirrors scan_result (scan.h:35-53) */
+  double track_gain, track_peak, track_loudness, track_loudness_range;
+  double album_gain, album_peak, album_loudness, album_loudness_range;
+  double loudness_reference;
+} lgb_scan_result;
+
+/* chunk_frames: frames per ebur128_add_frames call (a decoded AVFrame is
+ * about 1k-4k frames); 0 = one call per track.  0 on success. */
+int lgb_scan_host(const lgb_host_track* tracks, size_t ntracks, size_t chunk_frames,
+                  int do_album, double pre_gain, lgb_scan_result* out);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* EBUR128_B200_H_ */

@@ -1,0 +1,279 @@
+// lg_batch.cu -- host layer of the batch API (include/ebur128_b200.h): plan
+// upload, workspace, launch sequencing on one CUDA stream, result fetch.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ebur128_b200.h"
+#include "lg_batch.h"
+#include "lg_kernels.h"
+#include "lg_plan.h"
+
+namespace lg {
+
+static thread_local std::string g_error;
+
+void set_error(const char* what, cudaError_t e) {
+  g_error = std::string(what) + ": " + cudaGetErrorString(e);
+}
+void set_error(const char* what) { g_error = what; }
+
+template <class T>
+static bool upload(const std::vector<T>& v, T** dev, cudaStream_t s) {
+  *dev = nullptr;
+  const size_t bytes = (v.empty() ? 1 : v.size()) * sizeof(T);
+  cudaError_t e = cudaMalloc((void**) dev, bytes);
+  if (e != cudaSuccess) { set_error("cudaMalloc", e); return false; }
+  if (!v.empty()) {
+    e = cudaMemcpyAsync(*dev, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) { set_error("cudaMemcpyAsync(H2D tables)", e); return false; }
+  }
+  return true;
+}
+
+template <class T>
+static bool dalloc(T** dev, uint64_t n) {
+  *dev = nullptr;
+  cudaError_t e = cudaMalloc((void**) dev, (n ? n : 1) * sizeof(T));
+  if (e != cudaSuccess) { set_error("cudaMalloc", e); return false; }
+  return true;
+}
+
+int query_lists_sync(const BlockList* lists, size_t n, cudaStream_t stream, QueryResult* out) {
+  std::vector<BlockList> hl(lists, lists + n);
+  std::vector<uint32_t> hm(n);
+  for (size_t i = 0; i < n; ++i) hm[i] = (uint32_t) i;
+  std::vector<Query> hq(1, Query{0, (uint32_t) n});
+  BlockList* dl = nullptr; uint32_t* dm = nullptr; Query* dq = nullptr; QueryResult* dr = nullptr;
+  bool ok = upload(hl, &dl, stream) && upload(hm, &dm, stream) && upload(hq, &dq, stream) &&
+            dalloc(&dr, 1);
+  if (ok) {
+    cudaError_t e = launch_queries(dl, dq, dm, 1, pow(10.0, (-70.0 + 0.691) / 10.0), dr, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dr, sizeof(QueryResult), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { set_error("query_lists_sync", e); ok = false; }
+  }
+  cudaFree(dl); cudaFree(dm); cudaFree(dq); cudaFree(dr);
+  return ok ? 0 : 1;
+}
+
+}  // namespace lg
+
+using namespace lg;
+
+struct lgb_batch {
+  Plan plan;
+  cudaStream_t stream = nullptr;
+  // device tables
+  Track* d_tracks = nullptr;
+  CoefSet* d_coefs = nullptr;
+  float* d_basis = nullptr;
+  WarpWork* d_work = nullptr;
+  Query* d_queries = nullptr;
+  uint32_t* d_members = nullptr;
+  BlockList* d_lists = nullptr;
+  ChunkRec* d_recs = nullptr;
+  uint32_t* d_peaks = nullptr;
+  double* d_echunk = nullptr;
+  double* d_eslot = nullptr;
+  double* d_zblock = nullptr;
+  double* d_zst = nullptr;
+  QueryResult* d_results = nullptr;
+  // pinned host mirrors
+  QueryResult* h_results = nullptr;
+  uint32_t* h_peaks = nullptr;
+  double abs_gate = 0.0;
+  uint32_t launches = 0, sweep_launches = 0;
+  // optional sweep timing
+  bool timing = false, timed_run_pending = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double sweep_ms_total = 0.0;
+  uint64_t sweep_runs = 0;
+
+  DeviceTables tables() const {
+    DeviceTables t;
+    t.tracks = d_tracks; t.coefs = d_coefs; t.basis = d_basis; t.work = d_work;
+    t.queries = d_queries; t.members = d_members; t.lists = d_lists; t.recs = d_recs; t.peaks = d_peaks;
+    t.echunk = d_echunk; t.eslot = d_eslot; t.zblock = d_zblock; t.zst = d_zst;
+    t.results = d_results;
+    return t;
+  }
+};
+
+extern "C" LG_EXPORT const char* lgb_last_error(void) { return g_error.c_str(); }
+
+extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t ntracks, uint32_t nalbums,
+                                       void* cuda_stream) {
+  g_error.clear();
+  std::vector<TrackIn> in(ntracks);
+  for (size_t i = 0; i < ntracks; ++i) {
+    const lgb_track& t = tracks[i];
+    if (t.channels == 0 || t.channels > (uint32_t) kMaxChannels || t.samplerate < 16 ||
+        t.format > LGB_FORMAT_F32 || (t.frames && !t.pcm) ||
+        (t.album != LGB_NO_ALBUM && t.album >= nalbums)) {
+      set_error("lgb_batch_create: invalid track descriptor");
+      return nullptr;
+    }
+    in[i] = TrackIn{t.pcm, t.frames, t.channels, t.samplerate, t.format, t.album, t.weight_class};
+  }
+  lgb_batch* b = new lgb_batch();
+  b->stream = (cudaStream_t) cuda_stream;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // Two full waves of resident threads when the audio is long enough.
+  build_plan(in.data(), ntracks, nalbums, (uint64_t) sms * 2048u, b->plan);
+  const Plan& p = b->plan;
+  b->abs_gate = pow(10.0, (-70.0 + 0.691) / 10.0);
+  bool ok = upload(p.tracks, &b->d_tracks, b->stream) && upload(p.coefs, &b->d_coefs, b->stream) &&
+            upload(p.basis, &b->d_basis, b->stream) && upload(p.work, &b->d_work, b->stream) &&
+            upload(p.queries, &b->d_queries, b->stream) &&
+            upload(p.members, &b->d_members, b->stream) && dalloc(&b->d_recs, p.total_recs) &&
+            dalloc(&b->d_peaks, 2 * p.total_peaks) && dalloc(&b->d_echunk, p.total_recs) &&
+            dalloc(&b->d_eslot, p.total_slots) && dalloc(&b->d_zblock, p.total_blocks) &&
+            dalloc(&b->d_zst, p.total_st) && dalloc(&b->d_results, (uint64_t) p.queries.size());
+  if (ok) {
+    std::vector<BlockList> lists(p.tracks.size());
+    for (size_t i = 0; i < p.tracks.size(); ++i) {
+      const Track& tr = p.tracks[i];
+      lists[i] = BlockList{b->d_zblock + tr.block_base, b->d_zst + tr.st_base, tr.nblocks, tr.nst};
+    }
+    ok = upload(lists, &b->d_lists, b->stream);
+  }
+  if (ok) {
+    cudaError_t e = cudaMallocHost((void**) &b->h_results,
+                                   (p.queries.empty() ? 1 : p.queries.size()) * sizeof(QueryResult));
+    if (e == cudaSuccess)
+      e = cudaMallocHost((void**) &b->h_peaks, (p.total_peaks ? 2 * p.total_peaks : 1) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);   // tables are in place
+    if (e != cudaSuccess) { set_error("lgb_batch_create", e); ok = false; }
+  }
+  if (!ok) { lgb_batch_destroy(b); return nullptr; }
+  b->sweep_launches = (uint32_t) p.groups.size();
+  b->launches = b->sweep_launches + (p.total_recs ? 1 : 0) + (p.total_slots ? 1 : 0) +
+                ((p.total_blocks + p.total_st) ? 1 : 0) + (p.queries.empty() ? 0 : 1);
+  return b;
+}
+
+extern "C" LG_EXPORT int lgb_batch_run(lgb_batch* b) {
+  const Plan& p = b->plan;
+  const DeviceTables t = b->tables();
+  cudaError_t e = cudaMemsetAsync(b->d_peaks, 0, (p.total_peaks ? 2 * p.total_peaks : 1) * sizeof(uint32_t),
+                                  b->stream);
+  if (e != cudaSuccess) { set_error("cudaMemsetAsync(peaks)", e); return 1; }
+  if (b->timing) cudaEventRecord(b->ev0, b->stream);
+  for (const SweepGroup& g : p.groups) {
+    e = launch_sweep(t, g.format, g.tpf, g.first_warp, g.nwarps, b->stream);
+    if (e != cudaSuccess) { set_error("launch_sweep", e); return 1; }
+  }
+  if (b->timing) { cudaEventRecord(b->ev1, b->stream); b->timed_run_pending = true; }
+  PostSizes z{(uint32_t) p.tracks.size(), p.total_recs, p.total_slots, p.total_blocks, p.total_st};
+  e = launch_post(t, z, b->stream);
+  if (e != cudaSuccess) { set_error("launch_post", e); return 1; }
+  e = launch_queries(t.lists, t.queries, t.members, (uint32_t) p.queries.size(), b->abs_gate,
+                     t.results, b->stream);
+  if (e != cudaSuccess) { set_error("launch_queries", e); return 1; }
+  return 0;
+}
+
+static void to_result(const QueryResult& q, lgb_result& r) {
+  r.loudness = q.loudness; r.range = q.range; r.rel_threshold = q.rel_thr;
+  r.sum_abs = q.sum1; r.sum_rel = q.sum2; r.n_abs = q.n1; r.n_rel = q.n2; r.n_shortterm = q.nst;
+}
+
+extern "C" LG_EXPORT int lgb_batch_fetch(lgb_batch* b, lgb_result* track_results, lgb_result* album_results,
+                               double* sample_peaks, double* true_peaks) {
+  const Plan& p = b->plan;
+  cudaError_t e = cudaSuccess;
+  if (!p.queries.empty())
+    e = cudaMemcpyAsync(b->h_results, b->d_results, p.queries.size() * sizeof(QueryResult),
+                        cudaMemcpyDeviceToHost, b->stream);
+  if (e == cudaSuccess && p.total_peaks)
+    e = cudaMemcpyAsync(b->h_peaks, b->d_peaks, 2 * p.total_peaks * sizeof(uint32_t),
+                        cudaMemcpyDeviceToHost, b->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+  if (e != cudaSuccess) { set_error("lgb_batch_fetch", e); return 1; }
+  if (b->timed_run_pending) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, b->ev0, b->ev1) == cudaSuccess) {
+      b->sweep_ms_total += ms;
+      ++b->sweep_runs;
+    }
+    b->timed_run_pending = false;
+  }
+  const size_t nt = p.tracks.size();
+  if (track_results) for (size_t i = 0; i < nt; ++i) to_result(b->h_results[i], track_results[i]);
+  if (album_results) for (uint32_t a = 0; a < p.nalbums; ++a) to_result(b->h_results[nt + a], album_results[a]);
+  if (sample_peaks || true_peaks) {
+    for (size_t i = 0; i < nt; ++i) {
+      const Track& tr = p.tracks[i];
+      const double scale = tr.format == FMT_S16 ? 32768.0 : 1.0;
+      for (uint32_t c = 0; c < tr.channels; ++c) {
+        float sp, tp;
+        memcpy(&sp, &b->h_peaks[2 * (tr.peak_base + c)], 4);
+        memcpy(&tp, &b->h_peaks[2 * (tr.peak_base + c) + 1], 4);
+        const double s = (double) sp / scale, t = (double) tp / scale;
+        if (sample_peaks) sample_peaks[tr.peak_base + c] = s;
+        if (true_peaks) true_peaks[tr.peak_base + c] = t > s ? t : s;
+      }
+    }
+  }
+  return 0;
+}
+
+extern "C" LG_EXPORT uint64_t lgb_batch_total_samples(const lgb_batch* b) { return b->plan.total_samples; }
+extern "C" LG_EXPORT uint64_t lgb_batch_peak_count(const lgb_batch* b) { return b->plan.total_peaks; }
+extern "C" LG_EXPORT uint32_t lgb_batch_kernel_launches(const lgb_batch* b) { return b->launches; }
+extern "C" LG_EXPORT uint32_t lgb_batch_sweep_launches(const lgb_batch* b) { return b->sweep_launches; }
+
+extern "C" LG_EXPORT uint64_t lgb_batch_blocks(const lgb_batch* b, size_t track, int kind,
+                                     const double** dev_ptr) {
+  if (track >= b->plan.tracks.size()) { if (dev_ptr) *dev_ptr = nullptr; return 0; }
+  const Track& tr = b->plan.tracks[track];
+  const double* p = kind == 0 ? b->d_zblock + tr.block_base
+                  : kind == 1 ? b->d_zst + tr.st_base : b->d_eslot + tr.slot_base;
+  if (dev_ptr) *dev_ptr = p;
+  return kind == 0 ? tr.nblocks : kind == 1 ? tr.nst : tr.nslots;
+}
+
+extern "C" LG_EXPORT void lgb_batch_enable_timing(lgb_batch* b, int on) {
+  if (on && !b->ev0) {
+    cudaEventCreate(&b->ev0);
+    cudaEventCreate(&b->ev1);
+  }
+  b->timing = on != 0;
+  b->timed_run_pending = false;
+  b->sweep_ms_total = 0.0;
+  b->sweep_runs = 0;
+}
+
+extern "C" LG_EXPORT double lgb_batch_sweep_ms(const lgb_batch* b) {
+  return b->sweep_runs ? b->sweep_ms_total / (double) b->sweep_runs : 0.0;
+}
+
+extern "C" LG_EXPORT int lgb_query_lists(const double* const* z, const uint32_t* nz,
+                                         const double* const* st, const uint32_t* nst, size_t n,
+                                         void* cuda_stream, lgb_result* out) {
+  std::vector<BlockList> lists(n);
+  for (size_t i = 0; i < n; ++i) lists[i] = BlockList{z[i], st[i], nz[i], nst[i]};
+  QueryResult q;
+  if (query_lists_sync(lists.data(), n, (cudaStream_t) cuda_stream, &q)) return 1;
+  to_result(q, *out);
+  return 0;
+}
+
+extern "C" LG_EXPORT void lgb_batch_destroy(lgb_batch* b) {
+  if (!b) return;
+  if (b->ev0) { cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); }
+  cudaFree(b->d_tracks); cudaFree(b->d_coefs); cudaFree(b->d_basis); cudaFree(b->d_work);
+  cudaFree(b->d_queries); cudaFree(b->d_members); cudaFree(b->d_lists); cudaFree(b->d_recs); cudaFree(b->d_peaks);
+  cudaFree(b->d_echunk); cudaFree(b->d_eslot); cudaFree(b->d_zblock); cudaFree(b->d_zst);
+  cudaFree(b->d_results);
+  if (b->h_results) cudaFreeHost(b->h_results);
+  if (b->h_peaks) cudaFreeHost(b->h_peaks);
+  delete b;
+}

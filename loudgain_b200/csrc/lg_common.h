@@ -1,0 +1,113 @@
+// lg_common.h -- plain-old-data shared by the host planner and the sm_100a
+// kernels of the loudness sweep (the ebur128_add_frames_* path that
+// /root/reference/src/scan.c:448 drives, plus the query-time reductions of
+// scan.c:294-307,383-391).
+#pragma once
+
+#include <stdint.h>
+
+// Per-thread math is written once: device code under nvcc, plain inline host
+// code when a C++ compiler builds the test-only emulation (tests/emu).
+#if defined(__CUDACC__)
+#define LG_HD __device__ __forceinline__
+#else
+#define LG_HD inline
+#endif
+
+namespace lg {
+
+// Sample formats the sweep reads straight from HBM.
+enum Format : uint32_t { FMT_S16 = 0, FMT_F32 = 1 };
+
+// Frames the sweep advances per unrolled iteration (= tap count of a 4x
+// true-peak phase, so that window slides by exactly one phase length).
+constexpr int kIter = 12;
+// Longest per-phase tap count (49-tap prototype / factor 2, zero taps dropped).
+constexpr int kMaxTaps = 24;
+
+constexpr int kMaxChannels = 64;
+
+// One K-weighting coefficient set: a (sample rate, chunk length, warm-up,
+// input scale) combination.  Floats feed the sweep, doubles the fix-up.
+struct CoefSet {
+  // --- sweep, FP32.  High-pass in "leaky double integrator" form
+  //   t = x - e2*w2 ; d = c*d1 + t ; w = w1 + d ; yh = d - d1
+  // (algebraically w[n] = x[n] - a1 w[n-1] - a2 w[n-2], yh = w - 2w1 + w2)
+  // followed by the shelf  v = yh - p1 v1 - p2 v2 ; y = v + q1 v1 + q2 v2.
+  float c, e2, p1, p2, q1, q2;
+  int32_t s100;     // frames per 100 ms = (rate+5)/10
+  int32_t k;        // chunks per 100 ms slot (k divides s100)
+  int32_t L;        // frames per chunk = s100 / k
+  int32_t W;        // warm-up frames run before each chunk (multiple of kIter)
+  int32_t tpf;      // true-peak oversampling factor: 4, 2 or 0 (none)
+  int32_t horner;   // number of previous chunks the state carry looks back
+  // --- fix-up, FP64
+  double M[4];      // one-frame transition of the high-pass state (d1, w2)
+  double ML[4];     // M^L
+  double MinvW[4];  // M^-W
+  double Gaa, Gab, Gbb;  // sum over the chunk of alpha^2, alpha*beta, beta^2
+  double gain;      // (shelf b0 / input full scale)^2: raw energy -> K-weighted
+  uint64_t basis_off;    // offset (in float2) of this set's alpha/beta table
+};
+
+// One audio track resident in HBM as interleaved PCM [frames][channels].
+struct Track {
+  const void* pcm;     // device pointer to frame 0
+  uint64_t frames;
+  uint32_t channels;
+  uint32_t format;     // Format
+  uint32_t coef;       // index into the CoefSet table
+  uint32_t nslots;     // complete 100 ms slots
+  uint32_t nchunks;    // chunks incl. the tail after the last complete slot
+  uint32_t nblocks;    // 400 ms gating blocks
+  uint32_t nst;        // 3 s short-term blocks
+  uint32_t album;      // album (query group) index
+  uint64_t rec_base;   // first chunk record (index = rec_base + chunk*channels + ch)
+  uint64_t slot_base;  // first slot energy
+  uint64_t block_base; // first gating block
+  uint64_t st_base;    // first short-term block
+  uint64_t peak_base;  // first per-channel peak cell
+  // BS.1770 channel weight class: 0 unused, 1 -> 1.0, 2 -> 1.41, 3 -> 2.0
+  uint8_t wclass[kMaxChannels];
+};
+
+// What the sweep leaves behind for one (chunk, channel).
+struct ChunkRec {
+  double e0;        // sum y^2 over the chunk, filter started from zero state
+  float xa, xb;     // sum y*alpha, sum y*beta (cross terms of the correction)
+  float pd, pw;     // high-pass state (d1, w2) at the chunk's first frame
+  float qd, qw;     // ... and after its last frame
+};
+static_assert(sizeof(ChunkRec) == 32, "ChunkRec is written as two 16-byte stores");
+
+// Where one track's block energies live (device pointers).
+struct BlockList {
+  const double* z;    // 400 ms gating block energies
+  const double* st;   // 3 s short-term block energies
+  uint32_t nz, nst;
+};
+
+// A query: integrated loudness + range over the union of member block lists.
+struct Query {
+  uint32_t first;   // index of the first member in the member list
+  uint32_t count;   // number of members
+};
+
+struct QueryResult {
+  double loudness;  // LUFS, -inf if nothing passed the gates
+  double range;     // LU
+  double rel_thr;   // relative gate energy (diagnostic)
+  double sum1;      // sum of abs-gated block energies
+  double sum2;      // sum of rel-gated block energies
+  uint64_t n1;      // abs-gated block count
+  uint64_t n2;      // rel-gated block count
+  uint64_t nst;     // abs-gated short-term block count
+};
+
+// Work descriptor: one warp of the sweep.
+struct WarpWork {
+  uint32_t track;
+  uint32_t first_chunk;
+};
+
+}  // namespace lg

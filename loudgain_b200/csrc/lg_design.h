@@ -1,0 +1,193 @@
+// lg_design.h -- host-side (double precision) derivation of everything the
+// sweep and the fix-up need for one sample rate: K-weighting coefficients in
+// the sweep's FP32-friendly form, the high-pass state-transition powers, the
+// alpha/beta correction basis and its Gram sums.
+//
+// The filter being realised is the K-weighting of SURVEY.md A.3 (what the
+// reference path applies inside ebur128_add_frames_short, scan.c:448): a
+// +4 dB shelf at 1681.97 Hz cascaded with a 38.1 Hz high-pass.  It is
+// re-factored here, not transcribed: the high-pass runs as a leaky double
+// integrator so that its near-unit-circle poles survive FP32, and its
+// dependence on the state at the chunk start is removed afterwards by a
+// linear correction (see lg_post.cuh).
+#pragma once
+
+#include <cmath>
+#include <vector>
+
+#include "lg_common.h"
+
+namespace lg {
+
+struct KDesign {
+  double sb[3], sa[3];   // shelf numerator / denominator (sa[0] = 1)
+  double ha[3];          // high-pass denominator (numerator is 1,-2,1)
+  double e1, e2, c;      // e1 = 2 + ha1, e2 = 1 + ha1 + ha2, c = 1 - e1
+  double shelf_pole_radius, hp_pole_radius;
+};
+
+inline KDesign k_design(unsigned long rate) {
+  const double kPi = 3.14159265358979323846;
+  KDesign k;
+  {
+    const double f0 = 1681.974450955533, G = 3.999843853973347, Q = 0.7071752369554196;
+    const double K = std::tan(kPi * f0 / (double) rate);
+    const double Vh = std::pow(10.0, G / 20.0), Vb = std::pow(Vh, 0.4996667741545416);
+    const double den = 1.0 + K / Q + K * K;
+    k.sb[0] = (Vh + Vb * K / Q + K * K) / den;
+    k.sb[1] = 2.0 * (K * K - Vh) / den;
+    k.sb[2] = (Vh - Vb * K / Q + K * K) / den;
+    k.sa[0] = 1.0;
+    k.sa[1] = 2.0 * (K * K - 1.0) / den;
+    k.sa[2] = (1.0 - K / Q + K * K) / den;
+  }
+  {
+    const double f0 = 38.13547087602444, Q = 0.5003270373238773;
+    const double K = std::tan(kPi * f0 / (double) rate);
+    const double den = 1.0 + K / Q + K * K;
+    k.ha[0] = 1.0;
+    k.ha[1] = 2.0 * (K * K - 1.0) / den;
+    k.ha[2] = (1.0 - K / Q + K * K) / den;
+    // 2 + ha1 and 1 + ha1 + ha2 without cancellation:
+    k.e1 = (2.0 * K / Q + 4.0 * K * K) / den;
+    k.e2 = 4.0 * K * K / den;
+    k.c = 1.0 - k.e1;
+  }
+  auto radius = [](const double a[3]) {
+    const double disc = a[1] * a[1] - 4.0 * a[2];
+    if (disc < 0) return std::sqrt(a[2]);
+    const double r1 = std::fabs((-a[1] + std::sqrt(disc)) / 2.0);
+    const double r2 = std::fabs((-a[1] - std::sqrt(disc)) / 2.0);
+    return r1 > r2 ? r1 : r2;
+  };
+  k.shelf_pole_radius = radius(k.sa);
+  k.hp_pole_radius = radius(k.ha);
+  return k;
+}
+
+inline void mat2_mul(const double a[4], const double b[4], double out[4]) {
+  double r[4] = {a[0] * b[0] + a[1] * b[2], a[0] * b[1] + a[1] * b[3],
+                 a[2] * b[0] + a[3] * b[2], a[2] * b[1] + a[3] * b[3]};
+  for (int i = 0; i < 4; ++i) out[i] = r[i];
+}
+
+inline void mat2_pow(const double m[4], unsigned long n, double out[4]) {
+  double base[4] = {m[0], m[1], m[2], m[3]};
+  double acc[4] = {1, 0, 0, 1};
+  while (n) {
+    if (n & 1) mat2_mul(acc, base, acc);
+    mat2_mul(base, base, base);
+    n >>= 1;
+  }
+  for (int i = 0; i < 4; ++i) out[i] = acc[i];
+}
+
+// Warm-up length: long enough for the shelf's own (unknown) start state to
+// decay below 1e-5 and to prime the true-peak window; multiple of kIter.
+inline int warmup_frames(const KDesign& k) {
+  int w = (int) std::ceil(std::log(1e-5) / std::log(k.shelf_pole_radius));
+  if (w < kMaxTaps) w = kMaxTaps;
+  return ((w + kIter - 1) / kIter) * kIter;
+}
+
+inline int true_peak_factor(unsigned long rate) {
+  return rate < 96000 ? 4 : (rate < 192000 ? 2 : 0);
+}
+
+// Fills `cs` for (rate, chunks-per-slot k, input full scale) and appends the
+// alpha/beta basis (float2 per frame of warm-up + chunk) to `basis`.
+inline void make_coefset(unsigned long rate, int k, double full_scale, CoefSet& cs,
+                         std::vector<float>& basis) {
+  const KDesign d = k_design(rate);
+  cs.s100 = (int32_t) ((rate + 5) / 10);
+  cs.k = k;
+  cs.L = cs.s100 / k;
+  cs.W = warmup_frames(d);
+  cs.tpf = true_peak_factor(rate);
+  cs.c = (float) d.c;
+  cs.e2 = (float) d.e2;
+  cs.p1 = (float) d.sa[1];
+  cs.p2 = (float) d.sa[2];
+  cs.q1 = (float) (d.sb[1] / d.sb[0]);
+  cs.q2 = (float) (d.sb[2] / d.sb[0]);
+  cs.gain = (d.sb[0] / full_scale) * (d.sb[0] / full_scale);
+  cs.M[0] = d.c; cs.M[1] = -d.e2; cs.M[2] = 1.0; cs.M[3] = 1.0;
+  mat2_pow(cs.M, (unsigned long) cs.L, cs.ML);
+  {
+    const double det = cs.M[0] * cs.M[3] - cs.M[1] * cs.M[2];
+    const double inv[4] = {cs.M[3] / det, -cs.M[1] / det, -cs.M[2] / det, cs.M[0] / det};
+    mat2_pow(inv, (unsigned long) cs.W, cs.MinvW);
+  }
+  {
+    int h = (int) std::ceil(std::log(1e-18) / ((double) cs.L * std::log(d.hp_pole_radius))) + 1;
+    cs.horner = h < 2 ? 2 : h;
+  }
+  // Basis: K-weighted output at frame f for zero input and high-pass start
+  // state (d1, w2) = (1, 0) -> alpha, (0, 1) -> beta; shelf starts at rest.
+  const int n = cs.W + cs.L;
+  cs.basis_off = basis.size() / 2;
+  basis.resize(basis.size() + 2 * (size_t) n);
+  float* tab = basis.data() + 2 * cs.basis_off;
+  const double q1 = d.sb[1] / d.sb[0], q2 = d.sb[2] / d.sb[0];
+  double g[3] = {0, 0, 0};
+  for (int which = 0; which < 2; ++which) {
+    double d1 = which == 0 ? 1.0 : 0.0, w2 = which == 0 ? 0.0 : 1.0;
+    double w1 = w2 + d1, v1 = 0, v2 = 0;
+    for (int f = 0; f < n; ++f) {
+      const double dn = d.c * d1 - d.e2 * w2;
+      const double wn = w1 + dn;
+      const double yh = dn - d1;
+      const double v = yh - d.sa[1] * v1 - d.sa[2] * v2;
+      const double y = v + q1 * v1 + q2 * v2;
+      tab[2 * f + which] = (float) y;
+      w2 = w1; w1 = wn; d1 = dn; v2 = v1; v1 = v;
+    }
+  }
+  // Gram sums use the float-rounded table the sweep actually multiplies by.
+  for (int f = cs.W; f < n; ++f) {
+    const double a = tab[2 * f], b = tab[2 * f + 1];
+    g[0] += a * a; g[1] += a * b; g[2] += b * b;
+  }
+  cs.Gaa = g[0]; cs.Gab = g[1]; cs.Gbb = g[2];
+}
+
+// Largest divisor k of s100 whose chunk length s100/k is still >= min_len.
+inline int pick_chunks_per_slot(int s100, int min_len) {
+  int best = 1;
+  for (int k = 1; k <= s100; ++k) {
+    if (s100 % k) continue;
+    if (s100 / k < min_len) break;
+    best = k;
+  }
+  return best;
+}
+
+// BS.1770 channel weights of the default map: 4 ch ->
+// L R Ls Rs; 5 ch -> L R C Ls Rs; otherwise L R C (unused) Ls Rs, rest unused.
+// Emitted as weight classes (lg_common.h Track::wclass): 1 -> 1.0, 2 -> 1.41.
+inline void default_weight_classes(unsigned channels, uint8_t* w) {
+  for (unsigned i = 0; i < channels; ++i) w[i] = 0;
+  if (channels == 4) {
+    w[0] = w[1] = 1; w[2] = w[3] = 2;
+  } else if (channels == 5) {
+    w[0] = w[1] = w[2] = 1; w[3] = w[4] = 2;
+  } else {
+    static const uint8_t six[6] = {1, 1, 1, 0, 2, 2};
+    for (unsigned i = 0; i < channels && i < 6; ++i) w[i] = six[i];
+  }
+}
+
+// Weight class of an explicit channel role (enum channel of ebur128.h), for
+// states whose map was changed with ebur128_set_channel.
+inline uint8_t weight_class_of_role(int role) {
+  switch (role) {
+    case 0: return 0;                       // UNUSED
+    case 4: case 5:                         // Mp110 / Mm110 (surrounds)
+    case 9: case 10: case 11: case 12:      // Mp060 Mm060 Mp090 Mm090
+      return 2;
+    case 6: return 3;                       // DUAL_MONO
+    default: return 1;
+  }
+}
+
+}  // namespace lg

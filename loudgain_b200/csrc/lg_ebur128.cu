@@ -1,0 +1,536 @@
+// lg_ebur128.cu -- the drop-in ebur128_* C ABI (include/ebur128.h) over the
+// B200 batch engine.
+//
+// Call pattern being served (/root/reference/src/scan.c):
+//   ebur128_init per file (:203-207); ebur128_add_frames_short per decoded
+//   frame with a buffer the caller frees right away (:448-456); after ALL
+//   files are scanned, per-track queries (:294-307) and per-album queries
+//   (:383-391), the latter repeated once per track; ebur128_destroy (:102).
+//
+// So add_frames only stages: host memcpy into a pinned double buffer, then
+// cudaMemcpyAsync into the state's device PCM.  The first query measures every
+// state that has unmeasured audio in ONE batch (sweep + fix-up + gating on the
+// GPU); later queries read cached scalars, and *_multiple queries run only the
+// small gating/range kernel over block lists that are already in HBM.
+//
+// There is no CPU measurement path: without a usable CUDA device ebur128_init
+// fails (NULL) with a message on stderr.
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "../../include/ebur128.h"
+#include "../../include/ebur128_b200.h"
+#include "lg_batch.h"
+#include "lg_design.h"
+
+namespace {
+
+constexpr size_t kStageBytes = 8u << 20;   // each of the two pinned staging buffers
+
+struct BatchHolder {
+  lgb_batch* b = nullptr;
+  ~BatchHolder() { if (b) lgb_batch_destroy(b); }
+};
+
+// One run of audio with fixed (rate, channels, sample format).
+struct Segment {
+  unsigned channels = 0;
+  unsigned long rate = 0;
+  uint32_t format = LGB_FORMAT_S16;
+  char* d_pcm = nullptr;
+  size_t cap = 0, fill = 0;       // bytes
+  uint64_t frames = 0;
+  uint8_t wclass[lg::kMaxChannels] = {0};
+  // measurement cache
+  bool measured = false;
+  std::shared_ptr<BatchHolder> batch;
+  size_t track = 0;
+  lgb_result res{};
+  std::vector<double> sp, tp;
+};
+
+struct Context {
+  std::mutex mu;
+  bool ready = false, failed = false;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<ebur128_state*> live;
+  // cache of the last *_multiple query (loudgain repeats it per track)
+  std::vector<std::pair<const void*, size_t>> multi_key;
+  lg::QueryResult multi_res{};
+  bool multi_valid = false;
+};
+
+Context g_ctx;
+
+bool ctx_init() {
+  if (g_ctx.ready) return cudaSetDevice(g_ctx.device) == cudaSuccess;
+  if (g_ctx.failed) return false;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    fprintf(stderr, "libebur128 (B200): no usable CUDA device (%s); this library has no CPU path\n",
+            e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    g_ctx.failed = true;
+    return false;
+  }
+  const char* env = getenv("LOUDGAIN_B200_DEVICE");
+  g_ctx.device = env ? atoi(env) : 0;
+  if (g_ctx.device < 0 || g_ctx.device >= n) g_ctx.device = 0;
+  e = cudaSetDevice(g_ctx.device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "libebur128 (B200): CUDA initialisation failed: %s\n", cudaGetErrorString(e));
+    g_ctx.failed = true;
+    return false;
+  }
+  g_ctx.ready = true;
+  return true;
+}
+
+}  // namespace
+
+struct ebur128_state_internal {
+  std::vector<Segment> segs;
+  int chmap[lg::kMaxChannels];
+  char* stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  bool ev_armed[2] = {false, false};
+  int cur = 0;
+  size_t stage_fill = 0;
+  unsigned long window_ms = 400, history_ms = ULONG_MAX;
+  std::vector<float> convert;   // host scratch for int / double input
+};
+
+namespace {
+
+void default_map(int* map, unsigned channels) {
+  static const int six[6] = {EBUR128_LEFT, EBUR128_RIGHT, EBUR128_CENTER, EBUR128_UNUSED,
+                             EBUR128_LEFT_SURROUND, EBUR128_RIGHT_SURROUND};
+  if (channels == 4) {
+    map[0] = EBUR128_LEFT; map[1] = EBUR128_RIGHT;
+    map[2] = EBUR128_LEFT_SURROUND; map[3] = EBUR128_RIGHT_SURROUND;
+  } else if (channels == 5) {
+    map[0] = EBUR128_LEFT; map[1] = EBUR128_RIGHT; map[2] = EBUR128_CENTER;
+    map[3] = EBUR128_LEFT_SURROUND; map[4] = EBUR128_RIGHT_SURROUND;
+  } else {
+    for (unsigned i = 0; i < channels; ++i) map[i] = i < 6 ? six[i] : EBUR128_UNUSED;
+  }
+}
+
+void sync_weights(ebur128_state* st) {
+  Segment& s = st->d->segs.back();
+  for (unsigned c = 0; c < st->channels; ++c) s.wclass[c] = lg::weight_class_of_role(st->d->chmap[c]);
+}
+
+void open_segment(ebur128_state* st, uint32_t format) {
+  Segment s;
+  s.channels = st->channels;
+  s.rate = st->samplerate;
+  s.format = format;
+  st->d->segs.push_back(std::move(s));
+  sync_weights(st);
+}
+
+size_t sample_bytes(uint32_t format) { return format == LGB_FORMAT_S16 ? 2 : 4; }
+
+void invalidate(Segment& s) {
+  s.measured = false;
+  s.batch.reset();
+  g_ctx.multi_valid = false;
+}
+
+// Pushes the filled part of the current staging buffer to the device.
+bool flush_stage(ebur128_state* st) {
+  ebur128_state_internal* d = st->d;
+  if (!d->stage_fill) return true;
+  Segment& s = d->segs.back();
+  const size_t need = s.fill + d->stage_fill;
+  if (need > s.cap) {
+    size_t ncap = std::max<size_t>(std::max<size_t>(s.cap * 2, need), 4u << 20);
+    char* np = nullptr;
+    if (cudaMallocAsync((void**) &np, ncap, g_ctx.stream) != cudaSuccess) return false;
+    if (s.fill &&
+        cudaMemcpyAsync(np, s.d_pcm, s.fill, cudaMemcpyDeviceToDevice, g_ctx.stream) != cudaSuccess)
+      return false;
+    if (s.d_pcm) cudaFreeAsync(s.d_pcm, g_ctx.stream);
+    s.d_pcm = np;
+    s.cap = ncap;
+  }
+  const int cur = d->cur;
+  if (cudaMemcpyAsync(s.d_pcm + s.fill, d->stage[cur], d->stage_fill, cudaMemcpyHostToDevice,
+                      g_ctx.stream) != cudaSuccess)
+    return false;
+  cudaEventRecord(d->ev[cur], g_ctx.stream);
+  d->ev_armed[cur] = true;
+  s.fill += d->stage_fill;
+  d->stage_fill = 0;
+  d->cur = cur ^ 1;
+  // The other buffer may still be in flight from two flushes ago.
+  if (d->ev_armed[d->cur]) {
+    if (cudaEventSynchronize(d->ev[d->cur]) != cudaSuccess) return false;
+    d->ev_armed[d->cur] = false;
+  }
+  return true;
+}
+
+// Copies `bytes` of caller PCM through the pinned double buffer.
+bool stage_bytes(ebur128_state* st, const char* src, size_t bytes) {
+  ebur128_state_internal* d = st->d;
+  while (bytes) {
+    const size_t n = std::min(bytes, kStageBytes - d->stage_fill);
+    memcpy(d->stage[d->cur] + d->stage_fill, src, n);
+    d->stage_fill += n;
+    src += n;
+    bytes -= n;
+    if (d->stage_fill == kStageBytes && !flush_stage(st)) return false;
+  }
+  return true;
+}
+
+int add_frames(ebur128_state* st, const void* src, size_t frames, uint32_t format) {
+  if (!st || !st->d) return EBUR128_ERROR_NOMEM;
+  if (!frames) return EBUR128_SUCCESS;
+  std::lock_guard<std::mutex> lock(g_ctx.mu);
+  if (!ctx_init()) return EBUR128_ERROR_NOMEM;
+  ebur128_state_internal* d = st->d;
+  Segment* s = &d->segs.back();
+  if (s->frames == 0 && d->stage_fill == 0) s->format = format;
+  if (s->format != format) {
+    // A caller mixing sample types on one state: start a float run is not
+    // expressible without re-filtering, so keep one format per state.
+    fprintf(stderr, "libebur128 (B200): mixing sample formats on one state is not supported\n");
+    return EBUR128_ERROR_INVALID_MODE;
+  }
+  invalidate(*s);
+  const size_t bytes = frames * st->channels * sample_bytes(format);
+  if (!stage_bytes(st, (const char*) src, bytes)) return EBUR128_ERROR_NOMEM;
+  s->frames += frames;
+  return EBUR128_SUCCESS;
+}
+
+// Measures every live state that has audio the GPU has not looked at yet, in
+// one batch.
+bool measure_pending() {
+  std::vector<Segment*> todo;
+  for (ebur128_state* st : g_ctx.live) {
+    if (st->d->stage_fill && !flush_stage(st)) return false;
+    for (Segment& s : st->d->segs)
+      if (!s.measured) todo.push_back(&s);
+  }
+  if (todo.empty()) return true;
+  std::vector<lgb_track> tracks(todo.size());
+  for (size_t i = 0; i < todo.size(); ++i) {
+    Segment& s = *todo[i];
+    tracks[i] = lgb_track{s.d_pcm, s.frames, s.channels, (uint32_t) s.rate, s.format,
+                          LGB_NO_ALBUM, s.wclass};
+  }
+  auto holder = std::make_shared<BatchHolder>();
+  holder->b = lgb_batch_create(tracks.data(), tracks.size(), 0, g_ctx.stream);
+  if (!holder->b) {
+    fprintf(stderr, "libebur128 (B200): %s\n", lgb_last_error());
+    return false;
+  }
+  std::vector<lgb_result> res(todo.size());
+  std::vector<double> sp(lgb_batch_peak_count(holder->b)), tp(sp.size());
+  if (lgb_batch_run(holder->b) || lgb_batch_fetch(holder->b, res.data(), nullptr, sp.data(), tp.data())) {
+    fprintf(stderr, "libebur128 (B200): %s\n", lgb_last_error());
+    return false;
+  }
+  size_t off = 0;
+  for (size_t i = 0; i < todo.size(); ++i) {
+    Segment& s = *todo[i];
+    s.measured = true;
+    s.batch = holder;
+    s.track = i;
+    s.res = res[i];
+    s.sp.assign(sp.begin() + off, sp.begin() + off + s.channels);
+    s.tp.assign(tp.begin() + off, tp.begin() + off + s.channels);
+    off += s.channels;
+  }
+  return true;
+}
+
+// Gated loudness + range over the union of the given states' block lists.
+int query_union(ebur128_state** sts, size_t n, lg::QueryResult* out) {
+  if (!measure_pending()) return EBUR128_ERROR_NOMEM;
+  std::vector<lg::BlockList> lists;
+  std::vector<std::pair<const void*, size_t>> key;
+  for (size_t i = 0; i < n; ++i) {
+    if (!sts[i]) continue;
+    for (Segment& s : sts[i]->d->segs) {
+      lg::BlockList bl;
+      const double* p = nullptr;
+      bl.nz = (uint32_t) lgb_batch_blocks(s.batch->b, s.track, 0, &p); bl.z = p;
+      bl.nst = (uint32_t) lgb_batch_blocks(s.batch->b, s.track, 1, &p); bl.st = p;
+      lists.push_back(bl);
+      key.emplace_back((const void*) s.batch->b, s.track);
+    }
+  }
+  if (g_ctx.multi_valid && key == g_ctx.multi_key) { *out = g_ctx.multi_res; return EBUR128_SUCCESS; }
+  if (lg::query_lists_sync(lists.data(), lists.size(), g_ctx.stream, out)) {
+    fprintf(stderr, "libebur128 (B200): %s\n", lgb_last_error());
+    return EBUR128_ERROR_NOMEM;
+  }
+  g_ctx.multi_key = key;
+  g_ctx.multi_res = *out;
+  g_ctx.multi_valid = true;
+  return EBUR128_SUCCESS;
+}
+
+int state_query(ebur128_state* st, lg::QueryResult* out) {
+  if (st->d->segs.size() == 1) {
+    if (!measure_pending()) return EBUR128_ERROR_NOMEM;
+    const lgb_result& r = st->d->segs[0].res;
+    out->loudness = r.loudness; out->range = r.range; out->rel_thr = r.rel_threshold;
+    out->sum1 = r.sum_abs; out->sum2 = r.sum_rel; out->n1 = r.n_abs; out->n2 = r.n_rel;
+    out->nst = r.n_shortterm;
+    return EBUR128_SUCCESS;
+  }
+  return query_union(&st, 1, out);
+}
+
+bool has_mode(const ebur128_state* st, int bits) { return (st->mode & bits) == bits; }
+
+int peak_query(ebur128_state* st, unsigned ch, double* out, bool true_peak) {
+  if (!has_mode(st, true_peak ? EBUR128_MODE_TRUE_PEAK : EBUR128_MODE_SAMPLE_PEAK))
+    return EBUR128_ERROR_INVALID_MODE;
+  if (ch >= st->channels) return EBUR128_ERROR_INVALID_CHANNEL_INDEX;
+  std::lock_guard<std::mutex> lock(g_ctx.mu);
+  if (!ctx_init() || !measure_pending()) return EBUR128_ERROR_NOMEM;
+  double m = 0.0;
+  // Peaks survive a parameter change only while the channel count is kept.
+  for (auto it = st->d->segs.rbegin(); it != st->d->segs.rend(); ++it) {
+    if (it->channels != st->channels) break;
+    m = std::max(m, true_peak ? it->tp[ch] : it->sp[ch]);
+  }
+  *out = m;
+  return EBUR128_SUCCESS;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ the ABI
+
+extern "C" LG_EXPORT void ebur128_get_version(int* major, int* minor, int* patch) {
+  *major = EBUR128_VERSION_MAJOR;
+  *minor = EBUR128_VERSION_MINOR;
+  *patch = EBUR128_VERSION_PATCH;
+}
+
+extern "C" LG_EXPORT ebur128_state* ebur128_init(unsigned int channels, unsigned long samplerate, int mode) {
+  if (channels == 0 || channels > (unsigned) lg::kMaxChannels || samplerate < 16 ||
+      samplerate > 2822400)
+    return NULL;
+  if (!(mode & EBUR128_MODE_M)) return NULL;
+  std::lock_guard<std::mutex> lock(g_ctx.mu);
+  if (!ctx_init()) return NULL;
+  ebur128_state* st = (ebur128_state*) calloc(1, sizeof(ebur128_state));
+  if (!st) return NULL;
+  st->d = new (std::nothrow) ebur128_state_internal();
+  if (!st->d) { free(st); return NULL; }
+  st->mode = mode;
+  st->channels = channels;
+  st->samplerate = samplerate;
+  st->d->window_ms = has_mode(st, EBUR128_MODE_S) ? 3000 : 400;
+  default_map(st->d->chmap, channels);
+  bool ok = true;
+  for (int i = 0; i < 2 && ok; ++i) {
+    ok = cudaMallocHost((void**) &st->d->stage[i], kStageBytes) == cudaSuccess &&
+         cudaEventCreateWithFlags(&st->d->ev[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ok) {
+    fprintf(stderr, "libebur128 (B200): cannot allocate pinned staging buffers\n");
+    for (int i = 0; i < 2; ++i) {
+      if (st->d->stage[i]) cudaFreeHost(st->d->stage[i]);
+      if (st->d->ev[i]) cudaEventDestroy(st->d->ev[i]);
+    }
+    delete st->d;
+    free(st);
+    return NULL;
+  }
+  open_segment(st, LGB_FORMAT_S16);
+  g_ctx.live.push_back(st);
+  return st;
+}
+
+extern "C" LG_EXPORT void ebur128_destroy(ebur128_state** stp) {
+  if (!stp || !*stp) return;
+  ebur128_state* st = *stp;
+  std::lock_guard<std::mutex> lock(g_ctx.mu);
+  if (g_ctx.ready) cudaSetDevice(g_ctx.device);
+  g_ctx.live.erase(std::remove(g_ctx.live.begin(), g_ctx.live.end(), st), g_ctx.live.end());
+  g_ctx.multi_valid = false;
+  if (st->d) {
+    if (g_ctx.ready) cudaStreamSynchronize(g_ctx.stream);
+    for (Segment& s : st->d->segs) {
+      if (s.d_pcm) cudaFreeAsync(s.d_pcm, g_ctx.stream);
+      s.batch.reset();
+    }
+    for (int i = 0; i < 2; ++i) {
+      if (st->d->stage[i]) cudaFreeHost(st->d->stage[i]);
+      if (st->d->ev[i]) cudaEventDestroy(st->d->ev[i]);
+    }
+    delete st->d;
+  }
+  free(st);
+  *stp = NULL;
+}
+
+extern "C" LG_EXPORT int ebur128_set_channel(ebur128_state* st, unsigned int ch, int value) {
+  if (ch >= st->channels) return EBUR128_ERROR_INVALID_CHANNEL_INDEX;
+  if (value == EBUR128_DUAL_MONO && (st->channels != 1 || ch != 0)) {
+    fprintf(stderr, "EBUR128_DUAL_MONO only works with mono files!\n");
+    return EBUR128_ERROR_INVALID_CHANNEL_INDEX;
+  }
+  std::lock_guard<std::mutex> lock(g_ctx.mu);
+  st->d->chmap[ch] = value;
+  sync_weights(st);
+  invalidate(st->d->segs.back());
+  return EBUR128_SUCCESS;
+}
+
+extern "C" LG_EXPORT int ebur128_change_parameters(ebur128_state* st, unsigned int channels,
+                                         unsigned long samplerate) {
+  if (channels == 0 || channels > (unsigned) lg::kMaxChannels || samplerate < 16 ||
+      samplerate > 2822400)
+    return EBUR128_ERROR_NOMEM;
+  if (channels == st->channels && samplerate == st->samplerate) return EBUR128_ERROR_NO_CHANGE;
+  std::lock_guard<std::mutex> lock(g_ctx.mu);
+  if (!ctx_init()) return EBUR128_ERROR_NOMEM;
+  if (!flush_stage(st)) return EBUR128_ERROR_NOMEM;
+  const bool map_reset = channels != st->channels;
+  st->channels = channels;
+  st->samplerate = samplerate;
+  if (map_reset) default_map(st->d->chmap, channels);
+  // Filter, block schedule and interpolator restart; stored blocks are kept:
+  // exactly a new track whose blocks join the same union.
+  const uint32_t fmt = st->d->segs.back().format;
+  if (st->d->segs.back().frames == 0) st->d->segs.pop_back();
+  open_segment(st, fmt);
+  g_ctx.multi_valid = false;
+  return EBUR128_SUCCESS;
+}
+
+extern "C" LG_EXPORT int ebur128_set_max_window(ebur128_state* st, unsigned long window) {
+  if (has_mode(st, EBUR128_MODE_S) && window < 3000) window = 3000;
+  else if (has_mode(st, EBUR128_MODE_M) && window < 400) window = 400;
+  if (window == st->d->window_ms) return EBUR128_ERROR_NO_CHANGE;
+  st->d->window_ms = window;
+  return EBUR128_SUCCESS;
+}
+
+extern "C" LG_EXPORT int ebur128_set_max_history(ebur128_state* st, unsigned long history) {
+  if (has_mode(st, EBUR128_MODE_LRA) && history < 3000) history = 3000;
+  else if (has_mode(st, EBUR128_MODE_M) && history < 400) history = 400;
+  if (history == st->d->history_ms) return EBUR128_ERROR_NO_CHANGE;
+  st->d->history_ms = history;
+  return EBUR128_SUCCESS;
+}
+
+extern "C" LG_EXPORT int ebur128_add_frames_short(ebur128_state* st, const short* src, size_t frames) {
+  return add_frames(st, src, frames, LGB_FORMAT_S16);
+}
+
+extern "C" LG_EXPORT int ebur128_add_frames_float(ebur128_state* st, const float* src, size_t frames) {
+  return add_frames(st, src, frames, LGB_FORMAT_F32);
+}
+
+// int and double input are narrowed to float on the host (format shim only;
+// all measurement stays on the GPU).
+extern "C" LG_EXPORT int ebur128_add_frames_int(ebur128_state* st, const int* src, size_t frames) {
+  if (!st || !st->d) return EBUR128_ERROR_NOMEM;
+  std::vector<float>& v = st->d->convert;
+  const size_t n = frames * st->channels;
+  v.resize(n);
+  for (size_t i = 0; i < n; ++i) v[i] = (float) ((double) src[i] / 2147483648.0);
+  return add_frames(st, v.data(), frames, LGB_FORMAT_F32);
+}
+
+extern "C" LG_EXPORT int ebur128_add_frames_double(ebur128_state* st, const double* src, size_t frames) {
+  if (!st || !st->d) return EBUR128_ERROR_NOMEM;
+  std::vector<float>& v = st->d->convert;
+  const size_t n = frames * st->channels;
+  v.resize(n);
+  for (size_t i = 0; i < n; ++i) v[i] = (float) src[i];
+  return add_frames(st, v.data(), frames, LGB_FORMAT_F32);
+}
+
+extern "C" LG_EXPORT int ebur128_loudness_global(ebur128_state* st, double* out) {
+  if (!has_mode(st, EBUR128_MODE_I)) return EBUR128_ERROR_INVALID_MODE;
+  std::lock_guard<std::mutex> lock(g_ctx.mu);
+  if (!ctx_init()) return EBUR128_ERROR_NOMEM;
+  lg::QueryResult r;
+  const int rc = state_query(st, &r);
+  if (rc == EBUR128_SUCCESS) *out = r.loudness;
+  return rc;
+}
+
+extern "C" LG_EXPORT int ebur128_loudness_global_multiple(ebur128_state** sts, size_t size, double* out) {
+  for (size_t i = 0; i < size; ++i)
+    if (sts[i] && !has_mode(sts[i], EBUR128_MODE_I)) return EBUR128_ERROR_INVALID_MODE;
+  std::lock_guard<std::mutex> lock(g_ctx.mu);
+  if (!ctx_init()) return EBUR128_ERROR_NOMEM;
+  lg::QueryResult r;
+  const int rc = query_union(sts, size, &r);
+  if (rc == EBUR128_SUCCESS) *out = r.loudness;
+  return rc;
+}
+
+extern "C" LG_EXPORT int ebur128_loudness_range(ebur128_state* st, double* out) {
+  if (!has_mode(st, EBUR128_MODE_LRA)) return EBUR128_ERROR_INVALID_MODE;
+  std::lock_guard<std::mutex> lock(g_ctx.mu);
+  if (!ctx_init()) return EBUR128_ERROR_NOMEM;
+  lg::QueryResult r;
+  const int rc = state_query(st, &r);
+  if (rc == EBUR128_SUCCESS) *out = r.range;
+  return rc;
+}
+
+extern "C" LG_EXPORT int ebur128_loudness_range_multiple(ebur128_state** sts, size_t size, double* out) {
+  for (size_t i = 0; i < size; ++i)
+    if (sts[i] && !has_mode(sts[i], EBUR128_MODE_LRA)) return EBUR128_ERROR_INVALID_MODE;
+  std::lock_guard<std::mutex> lock(g_ctx.mu);
+  if (!ctx_init()) return EBUR128_ERROR_NOMEM;
+  lg::QueryResult r;
+  const int rc = query_union(sts, size, &r);
+  if (rc == EBUR128_SUCCESS) *out = r.range;
+  return rc;
+}
+
+extern "C" LG_EXPORT int ebur128_relative_threshold(ebur128_state* st, double* out) {
+  if (!has_mode(st, EBUR128_MODE_I)) return EBUR128_ERROR_INVALID_MODE;
+  std::lock_guard<std::mutex> lock(g_ctx.mu);
+  if (!ctx_init()) return EBUR128_ERROR_NOMEM;
+  lg::QueryResult r;
+  const int rc = state_query(st, &r);
+  if (rc != EBUR128_SUCCESS) return rc;
+  *out = r.n1 ? 10.0 * log10(r.rel_thr) - 0.691 : -70.0;
+  return EBUR128_SUCCESS;
+}
+
+extern "C" LG_EXPORT int ebur128_sample_peak(ebur128_state* st, unsigned int ch, double* out) {
+  return peak_query(st, ch, out, false);
+}
+
+extern "C" LG_EXPORT int ebur128_true_peak(ebur128_state* st, unsigned int ch, double* out) {
+  return peak_query(st, ch, out, true);
+}
+
+// The sliding-window queries (momentary / short-term / arbitrary window) and
+// the per-call "prev" peaks are live-metering features that loudgain never
+// uses; they are not on the B200 path yet.
+extern "C" LG_EXPORT int ebur128_loudness_momentary(ebur128_state*, double*) { return EBUR128_ERROR_INVALID_MODE; }
+extern "C" LG_EXPORT int ebur128_loudness_shortterm(ebur128_state*, double*) { return EBUR128_ERROR_INVALID_MODE; }
+extern "C" LG_EXPORT int ebur128_loudness_window(ebur128_state*, unsigned long, double*) { return EBUR128_ERROR_INVALID_MODE; }
+extern "C" LG_EXPORT int ebur128_prev_sample_peak(ebur128_state*, unsigned int, double*) { return EBUR128_ERROR_INVALID_MODE; }
+extern "C" LG_EXPORT int ebur128_prev_true_peak(ebur128_state*, unsigned int, double*) { return EBUR128_ERROR_INVALID_MODE; }

@@ -1,0 +1,45 @@
+// lg_kernels.h -- launch interface between the host layer (lg_batch.cu) and
+// the kernels (lg_kernels.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lg_common.h"
+
+namespace lg {
+
+constexpr int kSweepThreads = 128;
+
+// Device-resident tables of one batch.
+struct DeviceTables {
+  const Track* tracks;
+  const CoefSet* coefs;
+  const float* basis;
+  const WarpWork* work;
+  const Query* queries;
+  const uint32_t* members;
+  const BlockList* lists; // [ntracks]
+  ChunkRec* recs;       // [total_recs]
+  uint32_t* peaks;      // [total_peaks][2]: sample peak, true peak (float bits)
+  double* echunk;       // [total_recs] corrected chunk energies
+  double* eslot;        // [total_slots]
+  double* zblock;       // [total_blocks]
+  double* zst;          // [total_st]
+  QueryResult* results; // [nqueries]
+};
+
+struct PostSizes {
+  uint32_t ntracks;
+  uint64_t total_recs, total_slots, total_blocks, total_st;
+};
+
+cudaError_t launch_sweep(const DeviceTables& t, uint32_t format, int tpf, uint32_t first_warp,
+                         uint32_t nwarps, cudaStream_t stream);
+cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t stream);
+// Gated loudness + range for `nqueries` queries; all pointers are device memory.
+cudaError_t launch_queries(const BlockList* lists, const Query* queries, const uint32_t* members,
+                           uint32_t nqueries, double abs_gate, QueryResult* results,
+                           cudaStream_t stream);
+
+}  // namespace lg

@@ -1,0 +1,141 @@
+// lg_plan.h -- host-side planner: turns a list of tracks (interleaved PCM
+// already in HBM) into the tables the kernels consume: coefficient sets, track
+// descriptors with their record/slot/block offsets, the warp work list of the
+// sweep and the query (track / album) member lists.
+//
+// Host-only, no CUDA calls: lg_batch.cu uploads the result, tests/emu runs it
+// on the CPU.
+#pragma once
+
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "lg_common.h"
+#include "lg_design.h"
+
+namespace lg {
+
+struct TrackIn {
+  const void* pcm;
+  uint64_t frames;
+  uint32_t channels;
+  uint32_t samplerate;
+  uint32_t format;          // Format
+  uint32_t album;           // album index, or kNoAlbum
+  const uint8_t* wclass;    // optional explicit weight classes [channels]
+};
+
+constexpr uint32_t kNoAlbum = 0xffffffffu;
+
+// Sweep launch group: all warps that run the same kernel instantiation.
+struct SweepGroup {
+  uint32_t format;
+  int32_t tpf;
+  uint32_t first_warp;   // into Plan::work
+  uint32_t nwarps;
+};
+
+struct Plan {
+  std::vector<CoefSet> coefs;
+  std::vector<float> basis;          // float2 per entry
+  std::vector<Track> tracks;
+  std::vector<WarpWork> work;
+  std::vector<SweepGroup> groups;
+  std::vector<Query> queries;        // [ntracks] track queries, then [nalbums]
+  std::vector<uint32_t> members;     // track indices referenced by queries
+  uint64_t total_recs = 0, total_slots = 0, total_blocks = 0, total_st = 0,
+           total_peaks = 0;
+  uint64_t total_samples = 0;        // frames * channels over all tracks
+  uint32_t nalbums = 0;
+};
+
+inline int pairs_per_chunk(uint32_t channels) { return (int) ((channels + 1) / 2); }
+
+// target_tasks: how many (chunk, channel-pair) tasks the sweep should expose
+// at least, if the audio is long enough (a few per resident thread).
+inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, uint64_t target_tasks,
+                       Plan& p) {
+  p = Plan();
+  p.nalbums = nalbums;
+  // -- chunk length from the total amount of work
+  uint64_t pair_frames = 0;
+  for (size_t i = 0; i < n; ++i)
+    pair_frames += in[i].frames * (uint64_t) pairs_per_chunk(in[i].channels);
+  uint64_t want_len = target_tasks ? pair_frames / target_tasks : 0;
+
+  std::map<std::tuple<uint32_t, int, uint32_t>, uint32_t> coef_index;
+  p.tracks.resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    const TrackIn& t = in[i];
+    Track& tr = p.tracks[i];
+    tr = Track();
+    tr.pcm = t.pcm;
+    tr.frames = t.frames;
+    tr.channels = t.channels;
+    tr.format = t.format;
+    tr.album = t.album;
+    if (t.wclass) for (uint32_t c = 0; c < t.channels; ++c) tr.wclass[c] = t.wclass[c];
+    else default_weight_classes(t.channels, tr.wclass);
+    const int s100 = (int) ((t.samplerate + 5) / 10);
+    const KDesign kd = k_design(t.samplerate);
+    const int W = warmup_frames(kd);
+    int min_len = 4 * W;
+    if ((uint64_t) min_len < want_len) min_len = (int) (want_len > (uint64_t) s100 ? s100 : want_len);
+    const int k = pick_chunks_per_slot(s100, min_len);
+    const auto key = std::make_tuple(t.samplerate, k, t.format);
+    auto it = coef_index.find(key);
+    if (it == coef_index.end()) {
+      CoefSet cs;
+      make_coefset(t.samplerate, k, t.format == FMT_S16 ? 32768.0 : 1.0, cs, p.basis);
+      it = coef_index.emplace(key, (uint32_t) p.coefs.size()).first;
+      p.coefs.push_back(cs);
+    }
+    tr.coef = it->second;
+    const CoefSet& cs = p.coefs[tr.coef];
+    tr.nslots = (uint32_t) (t.frames / (uint64_t) s100);
+    tr.nchunks = (uint32_t) ((t.frames + cs.L - 1) / (uint64_t) cs.L);
+    tr.nblocks = tr.nslots >= 4 ? tr.nslots - 3 : 0;
+    tr.nst = tr.nslots >= 30 ? (tr.nslots - 30) / 10 + 1 : 0;
+    tr.rec_base = p.total_recs;
+    tr.slot_base = p.total_slots;
+    tr.block_base = p.total_blocks;
+    tr.st_base = p.total_st;
+    tr.peak_base = p.total_peaks;
+    p.total_recs += (uint64_t) tr.nchunks * tr.channels;
+    p.total_slots += tr.nslots;
+    p.total_blocks += tr.nblocks;
+    p.total_st += tr.nst;
+    p.total_peaks += tr.channels;
+    p.total_samples += t.frames * t.channels;
+  }
+  // -- sweep work list, grouped by kernel instantiation (format, tp factor)
+  for (uint32_t fmt = 0; fmt < 2; ++fmt) {
+    for (int tpf : {4, 2, 0}) {
+      SweepGroup g{fmt, tpf, (uint32_t) p.work.size(), 0};
+      for (size_t i = 0; i < n; ++i) {
+        const Track& tr = p.tracks[i];
+        if (tr.format != fmt || p.coefs[tr.coef].tpf != tpf) continue;
+        const uint32_t cpw = 32u / (uint32_t) pairs_per_chunk(tr.channels);
+        for (uint32_t c = 0; c < tr.nchunks; c += cpw)
+          p.work.push_back(WarpWork{(uint32_t) i, c});
+      }
+      g.nwarps = (uint32_t) p.work.size() - g.first_warp;
+      if (g.nwarps) p.groups.push_back(g);
+    }
+  }
+  // -- queries: one per track, then one per album
+  p.queries.resize(n + nalbums);
+  for (size_t i = 0; i < n; ++i) {
+    p.queries[i] = Query{(uint32_t) p.members.size(), 1};
+    p.members.push_back((uint32_t) i);
+  }
+  for (uint32_t a = 0; a < nalbums; ++a) {
+    Query q{(uint32_t) p.members.size(), 0};
+    for (size_t i = 0; i < n; ++i)
+      if (in[i].album == a) { p.members.push_back((uint32_t) i); ++q.count; }
+    p.queries[n + a] = q;
+  }
+}
+
+}  // namespace lg

@@ -1,0 +1,80 @@
+// lg_post.cuh -- FP64 post-processing of the sweep's chunk records:
+//   * carry of the high-pass state across chunk boundaries by composing the
+//     chunk transition matrix M^L (a short look-back suffices: |lambda|^L < 1),
+//   * exact energy correction of each zero-started chunk,
+//   * 100 ms slot energies, 400 ms gating blocks, 3 s short-term blocks
+//     (block schedule of SURVEY.md A.2: block b covers slots b..b+3, short-term
+//     block j covers slots 10j..10j+29).
+// Per-item functions are host/device so tests/emu can run them on the CPU.
+#pragma once
+
+#include "lg_common.h"
+
+namespace lg {
+
+LG_HD void mat2_vec(const double m[4], double x, double y, double& ox, double& oy) {
+  ox = m[0] * x + m[1] * y;
+  oy = m[2] * x + m[3] * y;
+}
+
+// True K-weighted energy (still unscaled) of chunk j of one channel.
+// recs points at the channel's record of chunk 0; consecutive chunks are
+// `stride` records apart.
+LG_HD double chunk_true_energy(const CoefSet& cs, const ChunkRec* recs, long long stride,
+                               long long j) {
+  // T = true high-pass state at the first frame of chunk j.
+  double td = 0.0, tw = 0.0;
+  long long i = j - cs.horner;
+  if (i < 0) i = 0;
+  for (; i < j; ++i) {
+    const ChunkRec& r = recs[i * stride];
+    // zero-state response of chunk i: R = Q - M^L P, then T <- R + M^L T
+    double mx, my;
+    mat2_vec(cs.ML, td - (double) r.pd, tw - (double) r.pw, mx, my);
+    td = (double) r.qd + mx;
+    tw = (double) r.qw + my;
+  }
+  const ChunkRec& r = recs[j * stride];
+  // State the zero-started run was missing at its own first (warm-up) frame.
+  double ad, aw;
+  mat2_vec(cs.MinvW, td - (double) r.pd, tw - (double) r.pw, ad, aw);
+  return r.e0 + 2.0 * ((double) r.xa * ad + (double) r.xb * aw) +
+         cs.Gaa * ad * ad + 2.0 * cs.Gab * ad * aw + cs.Gbb * aw * aw;
+}
+
+LG_HD double weight_of(uint8_t wclass) {
+  return wclass == 1 ? 1.0 : (wclass == 2 ? 1.41 : (wclass == 3 ? 2.0 : 0.0));
+}
+
+// Weighted, scaled energy (sum over frames, not yet the mean) of one slot.
+LG_HD double slot_energy(const Track& tr, const CoefSet& cs, const double* echunk,
+                         uint32_t slot) {
+  double total = 0.0;
+  for (uint32_t c = 0; c < tr.channels; ++c) {
+    const double w = weight_of(tr.wclass[c]);
+    if (w == 0.0) continue;
+    double s = 0.0;
+    const uint64_t base = tr.rec_base + (uint64_t) slot * cs.k * tr.channels + c;
+    for (int i = 0; i < cs.k; ++i) s += echunk[base + (uint64_t) i * tr.channels];
+    total += w * s;
+  }
+  return total * cs.gain;
+}
+
+LG_HD double gating_block(const double* eslot, const CoefSet& cs, uint32_t b) {
+  const double s = (eslot[b] + eslot[b + 1]) + (eslot[b + 2] + eslot[b + 3]);
+  return s / (4.0 * (double) cs.s100);
+}
+
+LG_HD double shortterm_block(const double* eslot, const CoefSet& cs, uint32_t j) {
+  double s = 0.0;
+  for (int i = 0; i < 30; ++i) s += eslot[10u * j + i];
+  return s / (30.0 * (double) cs.s100);
+}
+
+// 10^((-70 + 0.691)/10): absolute gate as block energy.
+LG_HD double abs_gate_energy() { return 1.1724653045822964e-07; }
+
+LG_HD double energy_to_lufs(double e) { return 10.0 * log10(e) - 0.691; }
+
+}  // namespace lg

@@ -1,0 +1,272 @@
+"""Batch measurement over PCM that is already resident in HBM
+(include/ebur128_b200.h).  torch is used for device memory and streams only.
+
+This is the path album / library scans take: all tracks of a
+batch go through ONE fused sweep launch per kernel variant, then the FP64
+fix-up and the gating / range reductions, all on the GPU; the host receives a
+few scalars per track and per album -- the same quantities the reference
+scanner reads back through ebur128_loudness_global[_multiple],
+ebur128_loudness_range[_multiple] and ebur128_true_peak
+(/root/reference/src/scan.c:294-307,383-391).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Sequence
+
+import numpy as np
+
+from . import load_library
+
+NO_ALBUM = 0xFFFFFFFF
+FORMAT_S16, FORMAT_F32 = 0, 1
+
+
+class _Track(C.Structure):
+    _fields_ = [("pcm", C.c_void_p), ("frames", C.c_uint64), ("channels", C.c_uint32),
+                ("samplerate", C.c_uint32), ("format", C.c_uint32), ("album", C.c_uint32),
+                ("weight_class", C.c_void_p)]
+
+
+class _Result(C.Structure):
+    _fields_ = [("loudness", C.c_double), ("range", C.c_double), ("rel_threshold", C.c_double),
+                ("sum_abs", C.c_double), ("sum_rel", C.c_double), ("n_abs", C.c_uint64),
+                ("n_rel", C.c_uint64), ("n_shortterm", C.c_uint64)]
+
+
+@dataclass
+class Measurement:
+    loudness: float
+    range: float
+    rel_threshold: float = 0.0
+    sum_abs: float = 0.0
+    sum_rel: float = 0.0
+    n_abs: int = 0
+    n_rel: int = 0
+    n_shortterm: int = 0
+    sample_peak: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    true_peak: np.ndarray = field(default_factory=lambda: np.zeros(0))
+
+
+_lib = None
+
+
+def _bind():
+    global _lib
+    if _lib is not None:
+        return _lib
+    L = load_library().lib
+    L.lgb_last_error.restype = C.c_char_p
+    L.lgb_batch_create.argtypes = [C.POINTER(_Track), C.c_size_t, C.c_uint32, C.c_void_p]
+    L.lgb_batch_create.restype = C.c_void_p
+    L.lgb_batch_run.argtypes = [C.c_void_p]
+    L.lgb_batch_fetch.argtypes = [C.c_void_p, C.POINTER(_Result), C.POINTER(_Result),
+                                  C.c_void_p, C.c_void_p]
+    L.lgb_batch_total_samples.argtypes = [C.c_void_p]
+    L.lgb_batch_total_samples.restype = C.c_uint64
+    L.lgb_batch_peak_count.argtypes = [C.c_void_p]
+    L.lgb_batch_peak_count.restype = C.c_uint64
+    L.lgb_batch_kernel_launches.argtypes = [C.c_void_p]
+    L.lgb_batch_kernel_launches.restype = C.c_uint32
+    L.lgb_batch_sweep_launches.argtypes = [C.c_void_p]
+    L.lgb_batch_sweep_launches.restype = C.c_uint32
+    L.lgb_batch_blocks.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
+    L.lgb_batch_blocks.restype = C.c_uint64
+    L.lgb_batch_destroy.argtypes = [C.c_void_p]
+    L.lgb_batch_destroy.restype = None
+    _lib = L
+    return L
+
+
+def _err(L) -> str:
+    return (L.lgb_last_error() or b"").decode()
+
+
+class Batch:
+    """A planned measurement of `tracks` = [(cuda tensor [frames, channels] of
+    int16 or float32, sample rate)], optionally grouped into albums."""
+
+    def __init__(self, tracks: Sequence, albums: Sequence[int] | None = None, stream=None):
+        import torch
+
+        L = _bind()
+        self._L = L
+        self._keep = []
+        n = len(tracks)
+        arr = (_Track * max(n, 1))()
+        nalb = 0
+        self.channels = []
+        for i, (pcm, rate) in enumerate(tracks):
+            if not pcm.is_cuda:
+                raise ValueError("Batch needs CUDA tensors (PCM resident in HBM)")
+            if pcm.dim() == 1:
+                pcm = pcm.view(-1, 1)
+            pcm = pcm.contiguous()
+            fmt = {torch.int16: FORMAT_S16, torch.float32: FORMAT_F32}[pcm.dtype]
+            alb = NO_ALBUM if albums is None else int(albums[i])
+            if alb != NO_ALBUM:
+                nalb = max(nalb, alb + 1)
+            self._keep.append(pcm)
+            self.channels.append(pcm.shape[1])
+            arr[i] = _Track(pcm.data_ptr(), pcm.shape[0], pcm.shape[1], int(rate), fmt, alb, None)
+        self.ntracks, self.nalbums = n, nalb
+        self.stream = stream if stream is not None else torch.cuda.current_stream()
+        self._h = L.lgb_batch_create(arr, n, nalb, C.c_void_p(self.stream.cuda_stream))
+        if not self._h:
+            raise RuntimeError("lgb_batch_create failed: " + _err(L))
+
+    @property
+    def total_samples(self) -> int:
+        return self._L.lgb_batch_total_samples(self._h)
+
+    @property
+    def kernel_launches(self) -> int:
+        return self._L.lgb_batch_kernel_launches(self._h)
+
+    @property
+    def sweep_launches(self) -> int:
+        return self._L.lgb_batch_sweep_launches(self._h)
+
+    def run(self) -> None:
+        """Enqueue the whole measurement on the batch's stream (asynchronous)."""
+        if self._L.lgb_batch_run(self._h):
+            raise RuntimeError("lgb_batch_run failed: " + _err(self._L))
+
+    def fetch(self) -> tuple[list[Measurement], list[Measurement]]:
+        """Wait and read back per-track and per-album results."""
+        L = self._L
+        tres = (_Result * max(self.ntracks, 1))()
+        ares = (_Result * max(self.nalbums, 1))()
+        npk = L.lgb_batch_peak_count(self._h)
+        sp = np.zeros(max(npk, 1))
+        tp = np.zeros(max(npk, 1))
+        if L.lgb_batch_fetch(self._h, tres, ares, sp.ctypes.data_as(C.c_void_p),
+                             tp.ctypes.data_as(C.c_void_p)):
+            raise RuntimeError("lgb_batch_fetch failed: " + _err(L))
+
+        def conv(r, s=None, t=None):
+            m = Measurement(r.loudness, r.range, r.rel_threshold, r.sum_abs, r.sum_rel,
+                            r.n_abs, r.n_rel, r.n_shortterm)
+            if s is not None:
+                m.sample_peak, m.true_peak = s, t
+            return m
+
+        out_t, off = [], 0
+        for i in range(self.ntracks):
+            ch = self.channels[i]
+            out_t.append(conv(tres[i], sp[off:off + ch].copy(), tp[off:off + ch].copy()))
+            off += ch
+        return out_t, [conv(ares[a]) for a in range(self.nalbums)]
+
+    def blocks(self, track: int, kind: int = 0) -> np.ndarray:
+        """Block energies of one track, copied to the host (0 = 400 ms gating
+        blocks, 1 = 3 s short-term blocks, 2 = 100 ms slots).  Diagnostic."""
+        import torch
+
+        p = C.c_void_p()
+        n = self._L.lgb_batch_blocks(self._h, track, kind, C.byref(p))
+        if not n:
+            return np.zeros(0)
+        out = torch.empty(n, dtype=torch.float64, device="cuda")
+        self.stream.synchronize()
+        err = torch.cuda.cudart().cudaMemcpy(out.data_ptr(), p.value, n * 8, 3)
+        assert int(err) == 0
+        return out.cpu().numpy()
+
+    def close(self) -> None:
+        if self._h:
+            self._L.lgb_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def measure(tracks, albums=None, stream=None):
+    """One-shot convenience: plan, run, fetch."""
+    b = Batch(tracks, albums, stream)
+    try:
+        b.run()
+        return b.fetch()
+    finally:
+        b.close()
+
+
+# ---------------------------------------------------------------- multi-GPU
+
+class _DeviceView:
+    """Zero-copy torch view of library-owned device memory."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False),
+                                         "version": 3, "strides": None}
+
+
+def device_blocks(batch: Batch, track: int, kind: int):
+    """Block energies of one track as a CUDA tensor view (no copy)."""
+    import torch
+
+    p = C.c_void_p()
+    n = batch._L.lgb_batch_blocks(batch._h, track, kind, C.byref(p))
+    if not n:
+        return torch.zeros(0, dtype=torch.float64, device="cuda")
+    return torch.as_tensor(_DeviceView(p.value, n), device="cuda")
+
+
+def gather_block_lists(dist, local: "torch.Tensor", world: int, group=None):
+    """All-gathers variable-length float64 lists (one per rank) and returns
+    them as a list of tensors.  Works on any backend / device (NCCL on GPUs,
+    gloo on CPU in tests): sizes first, then one padded all_gather."""
+    import torch
+
+    n = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    width = max(max(sizes), 1)
+    padded = torch.zeros(width, dtype=torch.float64, device=local.device)
+    padded[:local.numel()] = local
+    out = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(out, padded, group=group)
+    return [o[:s] for o, s in zip(out, sizes)]
+
+
+def query_lists(z_lists, st_lists, stream=None) -> Measurement:
+    """Gated loudness + range over the union of device-resident block lists
+    (lgb_query_lists)."""
+    import torch
+
+    L = _bind()
+    L.lgb_query_lists.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_uint32),
+                                  C.POINTER(C.c_void_p), C.POINTER(C.c_uint32), C.c_size_t,
+                                  C.c_void_p, C.POINTER(_Result)]
+    n = len(z_lists)
+    zp = (C.c_void_p * n)(*[t.data_ptr() if t.numel() else None for t in z_lists])
+    sp = (C.c_void_p * n)(*[t.data_ptr() if t.numel() else None for t in st_lists])
+    zn = (C.c_uint32 * n)(*[t.numel() for t in z_lists])
+    sn = (C.c_uint32 * n)(*[t.numel() for t in st_lists])
+    stream = stream if stream is not None else torch.cuda.current_stream()
+    r = _Result()
+    if L.lgb_query_lists(zp, zn, sp, sn, n, C.c_void_p(stream.cuda_stream), C.byref(r)):
+        raise RuntimeError("lgb_query_lists failed: " + _err(L))
+    return Measurement(r.loudness, r.range, r.rel_threshold, r.sum_abs, r.sum_rel, r.n_abs,
+                       r.n_rel, r.n_shortterm)
+
+
+def merge_album_across_ranks(batch: Batch, tracks, dist, world: int) -> Measurement:
+    """Album result over tracks that are sharded across ranks:
+    every rank contributes the block lists of its local `tracks`; the lists
+    are all-gathered over NCCL and the gating / range kernel runs over the
+    union.  Exact: same block energies as a single-GPU album query."""
+    import torch
+
+    batch.stream.synchronize()
+    z = torch.cat([device_blocks(batch, t, 0) for t in tracks])
+    st = torch.cat([device_blocks(batch, t, 1) for t in tracks])
+    zs = gather_block_lists(dist, z, world)
+    sts = gather_block_lists(dist, st, world)
+    return query_lists(zs, sts, batch.stream)

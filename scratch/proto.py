@@ -1,0 +1,75 @@
+import numpy as np, scipy.signal as sg, sys
+from oracle import load_oracle, kfilter_coeffs, tp_phase
+f32=np.float32
+def design(rate):
+    f0=1681.974450955533; G=3.999843853973347; Q=0.7071752369554196
+    K=np.tan(np.pi*f0/rate); Vh=10**(G/20); Vb=Vh**0.4996667741545416
+    D=1+K/Q+K*K
+    pb=np.array([(Vh+Vb*K/Q+K*K)/D, 2*(K*K-Vh)/D, (Vh-Vb*K/Q+K*K)/D]); pa=np.array([1,2*(K*K-1)/D,(1-K/Q+K*K)/D])
+    f0=38.13547087602444; Q=0.5003270373238773; K=np.tan(np.pi*f0/rate); D=1+K/Q+K*K
+    e1=(2*K/Q+4*K*K)/D; e2=4*K*K/D
+    return dict(pb=pb,pa=pa,e1=e1,e2=e2,c=1-e1,ra=np.array([1,2*(K*K-1)/D,(1-K/Q+K*K)/D]))
+def basis(cf,n):
+    # double: response y[f] to initial HP state (d1,w2) with zero input
+    out=[]
+    for s in ((1.0,0.0),(0.0,1.0)):
+        d1,w2=s; w1=w2+d1; v1=v2=0.0; y=np.zeros(n)
+        for f in range(n):
+            t=-cf['e2']*w2; d=cf['c']*d1+t; w=w1+d; yh=d-d1
+            v=yh-cf['pa'][1]*v1-cf['pa'][2]*v2
+            y[f]=v+cf['q1']*v1+cf['q2']*v2
+            w2,w1,d1,v2,v1=w1,w,d,v1,v
+        out.append(y)
+    return out
+def run(rate=44100,secs=20,k=10,W=72,dc=0.0,seed=1,bass=False):
+    cf=design(rate); cf['q1']=cf['pb'][1]/cf['pb'][0]; cf['q2']=cf['pb'][2]/cf['pb'][0]
+    s100=(rate+5)//10; L=s100//k; assert L*k==s100
+    rng=np.random.default_rng(seed); n=rate*secs
+    t=np.arange(n)/rate
+    if bass: x=0.5*np.sin(2*np.pi*41*t)+0.01*rng.standard_normal(n)
+    else:
+        x=sg.lfilter([1],[1,-0.95],rng.standard_normal(n)); x/=np.abs(x).max(); x*=0.5*(1+0.8*np.sin(2*np.pi*0.13*t))
+    x=x+dc
+    pcm=np.clip(np.round(x*32767),-32768,32767).astype(np.int16)
+    # reference double
+    b=np.convolve(cf['pb'],[1,-2,1]); a=np.convolve(cf['pa'],cf['ra'])
+    yref=sg.lfilter(b,a,pcm.astype(np.float64)/32768)
+    nslots=n//s100; eref=(yref[:nslots*s100]**2).reshape(nslots,s100).sum(1)
+    # chunked fp32
+    nch=nslots*k; N=W+L
+    starts=np.arange(nch)*L-W
+    xp=np.concatenate([np.zeros(W,dtype=np.int16),pcm]).astype(f32)  # index shift W
+    idx=starts[:,None]+W+np.arange(N)[None,:]
+    X=xp[idx]  # [nch,N] float32
+    al,be=basis(cf,N); al32=al.astype(f32); be32=be.astype(f32)
+    e2=f32(cf['e2']); c=f32(cf['c']); p1=f32(cf['pa'][1]); p2=f32(cf['pa'][2]); q1=f32(cf['q1']); q2=f32(cf['q2'])
+    z=np.zeros(nch,f32); d1=z.copy(); w1=z.copy(); w2=z.copy(); v1=z.copy(); v2=z.copy()
+    E=np.zeros(nch,np.float64); Ep=z.copy(); Xa=z.copy(); Xb=z.copy()
+    def fma(a,b,c_): return (a.astype(np.float64)*np.float64(b)+c_.astype(np.float64)).astype(f32)
+    for f in range(N):
+        if f==W: P=(d1.copy(),w2.copy())
+        xx=X[:,f]
+        tt=fma(w2,-e2,xx); d=fma(d1,c,tt); w=w1+d; yh=d-d1
+        u=fma(v2,-p2,yh); v=fma(v1,-p1,u)
+        y=fma(v2,q2,fma(v1,q1,v))
+        if f>=W:
+            Ep=fma(y,1,0*y) if False else (y.astype(np.float64)*y+Ep).astype(f32)
+            Xa=(y.astype(np.float64)*al32[f]+Xa).astype(f32); Xb=(y.astype(np.float64)*be32[f]+Xb).astype(f32)
+            if (f-W)%64==63: E+=Ep; Ep=z.copy()
+        w2,w1,d1,v2,v1=w1,w,d,v1,v
+    E+=Ep; Q=(d1.copy(),w2.copy())
+    # fixup in double
+    M=np.array([[cf['c'],-cf['e2']],[1.0,1.0]]); ML=np.linalg.matrix_power(M,L); MinvW=np.linalg.matrix_power(np.linalg.inv(M),W)
+    Gaa=(al[W:]**2).sum(); Gab=(al[W:]*be[W:]).sum(); Gbb=(be[W:]**2).sum()
+    T=np.zeros(2); Et=np.zeros(nch)
+    for j in range(nch):
+        Pj=np.array([P[0][j],P[1][j]],dtype=np.float64); Qj=np.array([Q[0][j],Q[1][j]],dtype=np.float64)
+        tau=MinvW@(T-Pj)
+        Et[j]=E[j]+2*(Xa[j]*tau[0]+Xb[j]*tau[1])+Gaa*tau[0]**2+2*Gab*tau[0]*tau[1]+Gbb*tau[1]**2
+        T=(Qj-ML@Pj)+ML@T
+    g=(cf['pb'][0]/32768)**2
+    eslot=Et.reshape(nslots,k).sum(1)*g
+    rel=(eslot-eref)/eref
+    print(f"rate={rate} k={k} W={W} dc={dc} bass={bass}: max|rel|={np.abs(rel).max():.3e} rms={np.sqrt((rel**2).mean()):.3e} E0/Et max ratio={np.max(E/np.maximum(Et,1e-30)):.2f} total rel={(eslot.sum()-eref.sum())/eref.sum():.3e}")
+if __name__=="__main__":
+    run(); run(k=1); run(dc=0.05); run(bass=True); run(rate=48000); run(rate=96000,W=144,secs=10); run(W=48)

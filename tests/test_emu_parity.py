@@ -1,0 +1,152 @@
+"""CPU check of the kernel MATH before any GPU time is spent.
+
+tests/emu compiles the per-thread device functions of loudgain_b200/csrc
+(lg_sweep.cuh, lg_post.cuh, lg_plan.h) for the host -- explicit fmaf, so bit
+for bit what the GPU computes -- and runs them sequentially.  These tests
+compare that against the oracle.  This emulation is test infrastructure; the
+product library contains no CPU path (see tests/test_abi.py).
+"""
+import numpy as np
+import pytest
+
+from loudgain_b200 import synth
+from tests import cases
+from tests.helpers import (GOAL_LU, NO_ALBUM, TOL_TP_REL, emu_measure, lu_diff, oracle_measure,
+                           rel_diff)
+
+ABS_GATE = 10 ** ((-70 + 0.691) / 10)
+
+
+def _check(o, e, goal=GOAL_LU):
+    assert lu_diff(e["loudness"], o["loudness"]) <= goal
+    assert lu_diff(e["range"], o["range"]) <= goal
+    np.testing.assert_array_equal(e["sample_peak"], o["sample_peak"])   # bit-exact
+    assert rel_diff(e["true_peak"], o["true_peak"]) <= TOL_TP_REL
+
+
+@pytest.mark.parametrize("target_tasks", [0, 500, 20])
+def test_programme_stereo_s16(oracle, target_tasks):
+    """cfg1 shape (44.1 kHz stereo S16), three chunk lengths."""
+    spec = synth.config1_spec(35.0)
+    pcm = synth.programme_s16(spec).numpy()
+    o = oracle_measure(oracle, [(pcm, spec.rate)])["tracks"][0]
+    e = emu_measure([(pcm, spec.rate)], target_tasks=target_tasks)
+    _check(o, e["tracks"][0])
+    got = e["blocks"][e["blocks"] >= ABS_GATE]
+    assert len(got) == len(o["blocks"])
+    assert rel_diff(got, o["blocks"]) < 2e-5
+    got = e["st"][e["st"] >= ABS_GATE]
+    assert len(got) == len(o["st"]) and rel_diff(got, o["st"]) < 2e-5
+
+
+@pytest.mark.parametrize("rate,channels,fmt", [
+    (48000, 2, "s16"), (48000, 2, "f32"), (44100, 1, "s16"), (22050, 2, "s16"),
+    (32000, 1, "f32"), (96000, 6, "s16"), (88200, 2, "s16"), (192000, 2, "s16"),
+    (48000, 5, "s16"), (48000, 4, "f32"), (44100, 3, "s16"), (11025, 2, "s16"),
+])
+def test_rates_channels_formats(oracle, rate, channels, fmt):
+    spec = synth.TrackSpec(seed=rate + channels, rate=rate, channels=channels, seconds=8.0,
+                           lfe_channel=3 if channels == 6 else None, surround_db=1.5)
+    x = synth.programme_float(spec)
+    pcm = synth.quantise_s16(x).numpy() if fmt == "s16" else x.numpy()
+    o = oracle_measure(oracle, [(pcm, rate)])["tracks"][0]
+    e = emu_measure([(pcm, rate)])["tracks"][0]
+    _check(o, e)
+
+
+def test_album_union(oracle):
+    """cfg2 shape, scaled down: per-track and album results."""
+    specs = synth.config2_specs(ntracks=4, scale=0.06)
+    tracks = [(synth.programme_s16(s).numpy(), s.rate) for s in specs]
+    albums = [0, 0, 0, 0]
+    o = oracle_measure(oracle, tracks, albums)
+    e = emu_measure(tracks, albums)
+    for ot, et in zip(o["tracks"], e["tracks"]):
+        _check(ot, et)
+    assert lu_diff(e["albums"][0]["loudness"], o["albums"][0]["loudness"]) <= GOAL_LU
+    assert lu_diff(e["albums"][0]["range"], o["albums"][0]["range"]) <= GOAL_LU
+
+
+def test_mixed_rate_album_and_loose_track(oracle):
+    rng = np.random.default_rng(3)
+    a = (rng.standard_normal((48000 * 5, 2)) * 2000).astype(np.int16)
+    b = (rng.standard_normal((96000 * 4, 1)) * 0.05).astype(np.float32)
+    c = (rng.standard_normal((44100 * 6, 2)) * 6000).astype(np.int16)
+    tracks = [(a, 48000), (b, 96000), (c, 44100)]
+    albums = [0, 0, NO_ALBUM]
+    o = oracle_measure(oracle, tracks, albums)
+    e = emu_measure(tracks, albums)
+    for ot, et in zip(o["tracks"], e["tracks"]):
+        _check(ot, et)
+    assert lu_diff(e["albums"][0]["loudness"], o["albums"][0]["loudness"]) <= GOAL_LU
+
+
+@pytest.mark.parametrize("frames", [0, 1, 11, 73, 4409, 4410, 17639, 17640, 17641, 132299, 132300])
+def test_ragged_lengths(oracle, frames):
+    """Empty, sub-block, exactly-one-block and exactly-3-s inputs."""
+    rng = np.random.default_rng(frames)
+    pcm = (rng.standard_normal((frames, 2)) * 5000).astype(np.int16)
+    o = oracle_measure(oracle, [(pcm, 44100)])["tracks"][0]
+    e = emu_measure([(pcm, 44100)])["tracks"][0]
+    _check(o, e)
+    assert e["n_abs"] == len(o["blocks"]) and e["n_st"] == len(o["st"])
+
+
+def test_dc_offset_and_bass(oracle):
+    """Zero-start chunks see a large high-pass transient; the correction must
+    cancel it (DC offset) and carry slow state exactly (41 Hz tone)."""
+    rate = 44100
+    t = np.arange(rate * 10) / rate
+    rng = np.random.default_rng(9)
+    dc = 0.05 + 0.003 * rng.standard_normal(len(t))
+    bass = 0.4 * np.sin(2 * np.pi * 41.0 * t) + 0.001 * rng.standard_normal(len(t))
+    for sig in (dc, bass):
+        pcm = cases.to_s16(np.stack([sig, -sig], axis=1))
+        o = oracle_measure(oracle, [(pcm, rate)])["tracks"][0]
+        e = emu_measure([(pcm, rate)])["tracks"][0]
+        _check(o, e)
+
+
+def test_full_scale_square_and_impulses(oracle):
+    rate = 48000
+    n = rate * 5
+    sq = np.where((np.arange(n) // 37) % 2 == 0, 32767, -32768).astype(np.int16)
+    imp = np.zeros(n, dtype=np.int16)
+    imp[::1000] = 32767
+    imp[500::1000] = -32768
+    pcm = np.stack([sq, imp], axis=1)
+    o = oracle_measure(oracle, [(pcm, rate)])["tracks"][0]
+    e = emu_measure([(pcm, rate)])["tracks"][0]
+    _check(o, e)
+    assert e["true_peak"][0] > 1.2      # inter-sample overs of a clipped square
+
+
+def test_ebu_cases_through_emulation(oracle):
+    for name, (pcm, rate, want, tol) in cases.loudness_cases().items():
+        e = emu_measure([(pcm, rate)])["tracks"][0]
+        assert abs(e["loudness"] - want) <= tol, name
+    for name, (pcm, rate, want, tol) in cases.range_cases().items():
+        e = emu_measure([(pcm, rate)])["tracks"][0]
+        assert abs(e["range"] - want) <= tol, name
+    for name, (pcm, rate, want, up, down) in cases.true_peak_cases().items():
+        e = emu_measure([(pcm, rate)])["tracks"][0]
+        db = 20 * np.log10(e["true_peak"].max())
+        assert want - down <= db <= want + up, name
+
+
+@pytest.mark.parametrize("rate", [44100, 96000])
+def test_true_peak_at_every_chunk_offset(oracle, rate):
+    """An inter-sample over placed at each offset inside a chunk (and across
+    chunk and warm-up boundaries) must be seen with full history."""
+    L = emu_measure([(np.zeros((rate, 1), dtype=np.int16), rate)])["chunk_len"][0]
+    base = 20 * L
+    for off in list(range(0, 30)) + [L // 2, L - 13, L - 12, L - 2, L - 1]:
+        pcm = np.zeros((40 * L, 1), dtype=np.int16)
+        k = base + off
+        pcm[k - 1:k + 1, 0] = 30000           # two equal samples: peak lies between them
+        pcm[k - 3:k - 1, 0] = -9000
+        pcm[k + 1:k + 3, 0] = -9000
+        o = oracle_measure(oracle, [(pcm, rate)])["tracks"][0]
+        e = emu_measure([(pcm, rate)])["tracks"][0]
+        assert o["true_peak"][0] > o["sample_peak"][0] * 1.05
+        assert rel_diff(e["true_peak"], o["true_peak"]) <= TOL_TP_REL, off
