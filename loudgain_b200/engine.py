@@ -162,17 +162,8 @@ class Batch:
     def blocks(self, track: int, kind: int = 0) -> np.ndarray:
         """Block energies of one track, copied to the host (0 = 400 ms gating
         blocks, 1 = 3 s short-term blocks, 2 = 100 ms slots).  Diagnostic."""
-        import torch
-
-        p = C.c_void_p()
-        n = self._L.lgb_batch_blocks(self._h, track, kind, C.byref(p))
-        if not n:
-            return np.zeros(0)
-        out = torch.empty(n, dtype=torch.float64, device="cuda")
         self.stream.synchronize()
-        err = torch.cuda.cudart().cudaMemcpy(out.data_ptr(), p.value, n * 8, 3)
-        assert int(err) == 0
-        return out.cpu().numpy()
+        return device_blocks(self, track, kind).cpu().numpy().copy()
 
     def close(self) -> None:
         if self._h:

@@ -219,9 +219,10 @@ def test_true_peak_at_chunk_offsets(product, oracle):
         assert rel_diff(g["true_peak"], o["true_peak"]) <= TOL_TP_REL, off
 
 
-def test_gpu_matches_host_emulation_bitwise(product):
-    """The host compile of the device math (tests/emu) predicts the GPU's
-    block energies exactly -- so CPU-side emulation tests are meaningful."""
+def test_gpu_matches_host_emulation(product):
+    """The host compile of the device math (tests/emu) predicts the GPU: the
+    FP32 sweep bit for bit (true peaks identical), the FP64 post-processing to
+    rounding (nvcc contracts a*b+c into DFMA, the host build does not)."""
     import torch
     from loudgain_b200 import engine
     from tests.helpers import emu_measure
@@ -235,5 +236,6 @@ def test_gpu_matches_host_emulation_bitwise(product):
     # same chunk length as the GPU plan: ask the emulation for the same task target
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     e = emu_measure([(pcm, spec.rate)], target_tasks=sms * 2048)
-    np.testing.assert_array_equal(z, e["blocks"])
+    np.testing.assert_allclose(z, e["blocks"], rtol=1e-13)
     np.testing.assert_array_equal(tres[0].true_peak, e["tracks"][0]["true_peak"])
+    np.testing.assert_array_equal(tres[0].sample_peak, e["tracks"][0]["sample_peak"])
