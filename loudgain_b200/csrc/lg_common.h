@@ -10,8 +10,10 @@
 // code when a C++ compiler builds the test-only emulation (tests/emu).
 #if defined(__CUDACC__)
 #define LG_HD __device__ __forceinline__
+#define LG_BOTH __host__ __device__ __forceinline__   // also used by the host planner
 #else
 #define LG_HD inline
+#define LG_BOTH inline
 #endif
 
 namespace lg {
@@ -22,8 +24,16 @@ enum Format : uint32_t { FMT_S16 = 0, FMT_F32 = 1 };
 // Frames the sweep advances per unrolled iteration (= tap count of a 4x
 // true-peak phase, so that window slides by exactly one phase length).
 constexpr int kIter = 12;
+// A staging stage = kItersPerStage iterations.  24 frames of any even-sized
+// frame are a whole number of 16-byte units, which is what cp.async moves.
+constexpr int kItersPerStage = 2;
+constexpr int kStageFrames = kIter * kItersPerStage;
+constexpr int kRing = 3;            // cp.async ring depth (stages in flight + 1)
 // Longest per-phase tap count (49-tap prototype / factor 2, zero taps dropped).
 constexpr int kMaxTaps = 24;
+// A lane starts on a 16-byte boundary of the track, i.e. on a multiple of
+// 16 / gcd(16, frame bytes) frames: at most 8 (mono / odd-channel S16).
+constexpr int kMaxAlign = 8;
 
 constexpr int kMaxChannels = 64;
 
@@ -41,27 +51,32 @@ struct CoefSet {
   int32_t W;        // warm-up frames run before each chunk (multiple of kIter)
   int32_t tpf;      // true-peak oversampling factor: 4, 2 or 0 (none)
   int32_t horner;   // number of previous chunks the state carry looks back
+  int32_t ntab;     // entries in the basis / Gram tables (even)
+  int32_t pad_;
   // --- fix-up, FP64
-  double M[4];      // one-frame transition of the high-pass state (d1, w2)
-  double ML[4];     // M^L
-  double MinvW[4];  // M^-W
-  double Gaa, Gab, Gbb;  // sum over the chunk of alpha^2, alpha*beta, beta^2
+  double ML[4];                   // M^L, M = one-frame transition of (d1, w2)
+  double MinvWo[kMaxAlign][4];    // M^-(W+o), o = lane alignment offset
   double gain;      // (shelf b0 / input full scale)^2: raw energy -> K-weighted
-  uint64_t basis_off;    // offset (in float2) of this set's alpha/beta table
+  uint64_t basis_off;   // offset (in float2) of this set's alpha/beta table
+  uint64_t gram_off;    // offset (in triples of doubles) of its prefix Gram table
 };
 
 // One audio track resident in HBM as interleaved PCM [frames][channels].
 struct Track {
-  const void* pcm;     // device pointer to frame 0
+  const void* pcm;     // device pointer to frame 0 (16-byte aligned)
   uint64_t frames;
   uint32_t channels;
   uint32_t format;     // Format
   uint32_t coef;       // index into the CoefSet table
+  uint32_t fb;         // bytes per frame
+  uint32_t aq;         // lane alignment quantum in frames (16 / gcd(16, fb))
+  uint32_t niters;     // sweep iterations per chunk (uniform over the track)
   uint32_t nslots;     // complete 100 ms slots
   uint32_t nchunks;    // chunks incl. the tail after the last complete slot
   uint32_t nblocks;    // 400 ms gating blocks
   uint32_t nst;        // 3 s short-term blocks
   uint32_t album;      // album (query group) index
+  uint32_t pad_;
   uint64_t rec_base;   // first chunk record (index = rec_base + chunk*channels + ch)
   uint64_t slot_base;  // first slot energy
   uint64_t block_base; // first gating block
@@ -104,10 +119,46 @@ struct QueryResult {
   uint64_t nst;     // abs-gated short-term block count
 };
 
-// Work descriptor: one warp of the sweep.
+// Work descriptor: one warp of the sweep = up to 32/ceil(C/2) consecutive
+// chunks of one track.
 struct WarpWork {
   uint32_t track;
   uint32_t first_chunk;
+  int32_t lmin_valid;   // shortest valid chunk length among the warp's chunks
+  uint32_t interior;    // 1: every byte the warp stages lies inside the track
 };
+
+// ---- lane geometry ---------------------------------------------------------
+// Chunk j covers track frames [j*L, j*L + L).  Its lane starts filtering from
+// zero state at frame a = align_down(j*L - W, aq), so that every staged row
+// begins on a 16-byte boundary; o = (j*L - W) - a is the lane's offset.
+// Lane-local frame f is track frame a + f; energy is accumulated over
+// [W + o, W + o + L).
+struct LaneGeom {
+  long long a;     // track frame of lane-local frame 0 (may be negative)
+  int o;           // 0 <= o < aq
+  int l_valid;     // frames of the chunk that exist in the track (0..L)
+};
+
+LG_BOTH LaneGeom lane_geometry(long long frames, int L, int W, int aq, long long chunk) {
+  LaneGeom g;
+  const long long b = chunk * (long long) L;
+  const long long s = b - W;
+  g.a = s & ~(long long) (aq - 1);     // aq is a power of two: floor, also for s < 0
+  g.o = (int) (s - g.a);
+  const long long left = frames - b;
+  g.l_valid = left <= 0 ? 0 : (left < L ? (int) left : L);
+  return g;
+}
+
+// How an iteration [f0, f0 + kIter) is run, uniformly for all lanes of a warp.
+enum IterKind : int { ITER_WARM = 0, ITER_FAST = 1, ITER_MASKED = 2 };
+
+LG_BOTH int iter_kind(int f0, int W, int aq, int L, int lmin_valid) {
+  if (f0 + kIter <= W) return ITER_WARM;       // before every lane's chunk
+  const int lfast = lmin_valid < L ? lmin_valid : L;
+  if (f0 >= W + aq - 1 && f0 + kIter <= W + lfast) return ITER_FAST;
+  return ITER_MASKED;
+}
 
 }  // namespace lg

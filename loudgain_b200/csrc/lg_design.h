@@ -94,11 +94,14 @@ inline int true_peak_factor(unsigned long rate) {
   return rate < 96000 ? 4 : (rate < 192000 ? 2 : 0);
 }
 
-// Fills `cs` for (rate, chunks-per-slot k, input full scale) and appends the
-// alpha/beta basis (float2 per frame of warm-up + chunk) to `basis`.
+// Fills `cs` for (rate, chunks-per-slot k, input full scale); appends the
+// alpha/beta basis (float2 per lane-local frame) to `basis` and the prefix
+// Gram sums (3 doubles per frame: sum alpha^2, alpha*beta, beta^2 over
+// frames < f) to `gram`.
 inline void make_coefset(unsigned long rate, int k, double full_scale, CoefSet& cs,
-                         std::vector<float>& basis) {
+                         std::vector<float>& basis, std::vector<double>& gram) {
   const KDesign d = k_design(rate);
+  cs = CoefSet();
   cs.s100 = (int32_t) ((rate + 5) / 10);
   cs.k = k;
   cs.L = cs.s100 / k;
@@ -111,25 +114,27 @@ inline void make_coefset(unsigned long rate, int k, double full_scale, CoefSet& 
   cs.q1 = (float) (d.sb[1] / d.sb[0]);
   cs.q2 = (float) (d.sb[2] / d.sb[0]);
   cs.gain = (d.sb[0] / full_scale) * (d.sb[0] / full_scale);
-  cs.M[0] = d.c; cs.M[1] = -d.e2; cs.M[2] = 1.0; cs.M[3] = 1.0;
-  mat2_pow(cs.M, (unsigned long) cs.L, cs.ML);
+  const double M[4] = {d.c, -d.e2, 1.0, 1.0};   // (d1, w2) -> one frame later
+  mat2_pow(M, (unsigned long) cs.L, cs.ML);
   {
-    const double det = cs.M[0] * cs.M[3] - cs.M[1] * cs.M[2];
-    const double inv[4] = {cs.M[3] / det, -cs.M[1] / det, -cs.M[2] / det, cs.M[0] / det};
-    mat2_pow(inv, (unsigned long) cs.W, cs.MinvW);
+    const double det = M[0] * M[3] - M[1] * M[2];
+    const double inv[4] = {M[3] / det, -M[1] / det, -M[2] / det, M[0] / det};
+    for (int o = 0; o < kMaxAlign; ++o) mat2_pow(inv, (unsigned long) (cs.W + o), cs.MinvWo[o]);
   }
   {
     int h = (int) std::ceil(std::log(1e-18) / ((double) cs.L * std::log(d.hp_pole_radius))) + 1;
     cs.horner = h < 2 ? 2 : h;
   }
-  // Basis: K-weighted output at frame f for zero input and high-pass start
-  // state (d1, w2) = (1, 0) -> alpha, (0, 1) -> beta; shelf starts at rest.
-  const int n = cs.W + cs.L;
+  // Basis: K-weighted output at lane-local frame f for zero input and
+  // high-pass start state (d1, w2) = (1, 0) -> alpha, (0, 1) -> beta; the
+  // shelf starts at rest.  Long enough for any lane offset plus one stage.
+  int n = cs.W + cs.L + kMaxAlign + kStageFrames;
+  n += n & 1;
+  cs.ntab = n;
   cs.basis_off = basis.size() / 2;
   basis.resize(basis.size() + 2 * (size_t) n);
   float* tab = basis.data() + 2 * cs.basis_off;
   const double q1 = d.sb[1] / d.sb[0], q2 = d.sb[2] / d.sb[0];
-  double g[3] = {0, 0, 0};
   for (int which = 0; which < 2; ++which) {
     double d1 = which == 0 ? 1.0 : 0.0, w2 = which == 0 ? 0.0 : 1.0;
     double w1 = w2 + d1, v1 = 0, v2 = 0;
@@ -143,13 +148,23 @@ inline void make_coefset(unsigned long rate, int k, double full_scale, CoefSet& 
       w2 = w1; w1 = wn; d1 = dn; v2 = v1; v1 = v;
     }
   }
-  // Gram sums use the float-rounded table the sweep actually multiplies by.
-  for (int f = cs.W; f < n; ++f) {
+  // Prefix Gram sums of the float-rounded table the sweep multiplies by.
+  cs.gram_off = gram.size() / 3;
+  gram.resize(gram.size() + 3 * (size_t) (n + 1));
+  double* pg = gram.data() + 3 * cs.gram_off;
+  pg[0] = pg[1] = pg[2] = 0.0;
+  for (int f = 0; f < n; ++f) {
     const double a = tab[2 * f], b = tab[2 * f + 1];
-    g[0] += a * a; g[1] += a * b; g[2] += b * b;
+    pg[3 * (f + 1) + 0] = pg[3 * f + 0] + a * a;
+    pg[3 * (f + 1) + 1] = pg[3 * f + 1] + a * b;
+    pg[3 * (f + 1) + 2] = pg[3 * f + 2] + b * b;
   }
-  cs.Gaa = g[0]; cs.Gab = g[1]; cs.Gbb = g[2];
 }
+
+inline uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }
+
+// Frames between consecutive 16-byte-aligned frame boundaries.
+inline uint32_t align_quantum(uint32_t frame_bytes) { return 16u / gcd_u32(16u, frame_bytes); }
 
 // Largest divisor k of s100 whose chunk length s100/k is still >= min_len.
 inline int pick_chunks_per_slot(int s100, int min_len) {

@@ -21,48 +21,207 @@
 namespace lg {
 
 // ------------------------------------------------------------------ sweep
+//
+// One warp = up to 32/ceil(C/2) consecutive chunks of one track; one lane =
+// one (chunk, channel pair).  The warp is autonomous (no CTA barrier): it
+// streams its rows HBM -> shared memory with 16-byte cp.async copies laid out
+// so that consecutive lanes fetch consecutive units of one row (coalesced),
+// three stages of 24 frames deep, and each lane then reads its own row with
+// conflict-free 128-bit shared loads (row stride is an odd number of units).
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Raw samples of one iteration of the lane's row, from shared memory.
+// rowp -> first frame of the iteration.
+template <int FMT>
+__device__ __forceinline__ void smem_load_iter(const unsigned char* rowp, uint32_t fb, bool stereo,
+                                               int nch, float x[2][kIter]) {
+  if (stereo) {
+    if (FMT == FMT_S16) {
+      const uint4* p = reinterpret_cast<const uint4*>(rowp);
+#pragma unroll
+      for (int u = 0; u < kIter / 4; ++u) {
+        const uint4 v = p[u];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          x[0][4 * u + j] = (float) (short) (w[j] & 0xffffu);
+          x[1][4 * u + j] = (float) (short) (w[j] >> 16);
+        }
+      }
+    } else {
+      const float4* p = reinterpret_cast<const float4*>(rowp);
+#pragma unroll
+      for (int u = 0; u < kIter / 2; ++u) {
+        const float4 v = p[u];
+        x[0][2 * u] = v.x; x[1][2 * u] = v.y;
+        x[0][2 * u + 1] = v.z; x[1][2 * u + 1] = v.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kIter; ++i) {
+      if (FMT == FMT_S16) {
+        const short* q = reinterpret_cast<const short*>(rowp + i * fb);
+        x[0][i] = (float) q[0];
+        x[1][i] = nch > 1 ? (float) q[1] : 0.0f;
+      } else {
+        const float* q = reinterpret_cast<const float*>(rowp + i * fb);
+        x[0][i] = q[0];
+        x[1][i] = nch > 1 ? q[1] : 0.0f;
+      }
+    }
+  }
+}
+
+template <int FMT> struct CopyTraits { static constexpr int kMax = FMT == FMT_S16 ? 6 : 12; };
 
 template <int FMT, int TPF>
 __global__ void __launch_bounds__(kSweepThreads)
 sweep_kernel(const Track* __restrict__ tracks, const CoefSet* __restrict__ coefs,
              const float* __restrict__ basis, const WarpWork* __restrict__ work,
-             uint32_t nwarps, ChunkRec* __restrict__ recs, uint32_t* __restrict__ peaks) {
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+             uint32_t nwarps, uint32_t warp_smem, ChunkRec* __restrict__ recs,
+             uint32_t* __restrict__ peaks) {
+  extern __shared__ __align__(16) unsigned char smem_all[];
+  const uint32_t wic = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31u;
-  if (warp >= nwarps) return;
+  const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + wic;
+  if (warp >= nwarps) return;                  // whole warps leave; no CTA barrier below
+  unsigned char* sm = smem_all + wic * warp_smem;
+  const uint32_t sm_addr = (uint32_t) __cvta_generic_to_shared(sm);
+
   const WarpWork ww = work[warp];
   const Track& tr = tracks[ww.track];
   const CoefSet& cs = coefs[tr.coef];
-  const uint32_t C = tr.channels;
+  const KCoef kc = load_kcoef(cs);
+  const int W = cs.W, L = cs.L;
+  const uint32_t C = tr.channels, fb = tr.fb, aq = tr.aq, niters = tr.niters;
+  const long long frames = (long long) tr.frames;
+  const unsigned char* pcm = reinterpret_cast<const unsigned char*>(tr.pcm);
+  const float* ab_tab = basis + 2 * cs.basis_off;
+
   const uint32_t ppc = (C + 1u) >> 1;
   const uint32_t cpw = 32u / ppc;
   const uint32_t slot = lane / ppc;
   const uint32_t pair = lane - slot * ppc;
   const uint32_t chunk = ww.first_chunk + slot;
-  const bool active = slot < cpw && chunk < tr.nchunks;
-
-  ChanOut out[2];
-  out[0].sp = out[0].tp = out[1].sp = out[1].tp = 0.0f;
+  const bool compute = slot < cpw;
+  const bool active = compute && chunk < tr.nchunks;
   const int ch0 = (int) (pair * 2u);
   const int nch = (ch0 + 1 < (int) C) ? 2 : 1;
+  const bool stereo = C == 2;
+
+  // ---- staging geometry
+  const uint32_t stage_row_bytes = kStageFrames * fb;          // multiple of 16
+  const uint32_t units = stage_row_bytes >> 4;
+  const uint32_t row_stride = (units | 1u) << 4;               // odd unit count: no bank conflicts
+  const uint32_t stage_bytes = cpw * row_stride;
+  const uint32_t ncopies = cpw * units;
+  const LaneGeom g0 = lane_geometry(frames, L, W, (int) aq, ww.first_chunk);
+  const long long warp_byte0 = g0.a * (long long) fb;          // may be negative
+  const long long track_bytes = frames * (long long) fb;
+  constexpr int KMAX = CopyTraits<FMT>::kMax;
+  int32_t soff[KMAX];      // source byte offset of copy k at stage 0, relative to warp_byte0
+  uint32_t doff[KMAX];     // destination byte offset inside a stage buffer
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const uint32_t idx = lane + 32u * k;
+    const uint32_t row = idx / units;
+    const uint32_t unit = idx - row * units;
+    const LaneGeom gr = lane_geometry(frames, L, W, (int) aq, ww.first_chunk + row);
+    soff[k] = (int32_t) ((gr.a - g0.a) * (long long) fb) + (int32_t) (unit << 4);
+    doff[k] = idx < ncopies ? row * row_stride + (unit << 4) : 0xffffffffu;
+  }
+  const bool interior = ww.interior != 0;
+
+  auto prefetch = [&](uint32_t stage) {
+    const uint32_t dst0 = sm_addr + (stage % kRing) * stage_bytes;
+    const long long adv = (long long) stage * stage_row_bytes;
+    if (interior) {
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        if (doff[k] != 0xffffffffu) cp_async16(dst0 + doff[k], pcm + (warp_byte0 + adv + soff[k]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (doff[k] == 0xffffffffu) continue;
+        const long long g = warp_byte0 + adv + soff[k];
+        long long ok = g < 0 ? 0 : track_bytes - g;
+        ok = ok < 0 ? 0 : (ok > 16 ? 16 : ok);
+        cp_async16_zfill(dst0 + doff[k], pcm + (ok ? g : 0), (uint32_t) ok);
+      }
+    }
+  };
+
+  // ---- lane state
+  LaneGeom geo = lane_geometry(frames, L, W, (int) aq, chunk);
+  LaneCtx<TPF> c;
+  lane_init(c, W, L, geo);
+  const unsigned char* my_row = sm + slot * row_stride + (uint32_t) ch0 * (FMT == FMT_S16 ? 2u : 4u);
+
+  const uint32_t nstages = (niters + kItersPerStage - 1) / kItersPerStage;
+  prefetch(0);
+  cp_async_commit();
+  if (nstages > 1) prefetch(1);
+  cp_async_commit();
+
+  for (uint32_t s = 0; s < nstages; ++s) {
+    cp_async_wait<1>();          // this lane's copies of stage s have landed
+    __syncwarp();                // ... everyone's have, and stage s-1 is fully consumed
+    if (s + 2 < nstages) prefetch(s + 2);
+    cp_async_commit();
+    if (compute) {
+      const unsigned char* buf = my_row + (s % kRing) * stage_bytes;
+#pragma unroll 1
+      for (int it = 0; it < kItersPerStage; ++it) {
+        const uint32_t iter = s * kItersPerStage + it;
+        if (iter >= niters) break;
+        const int f0 = (int) iter * kIter;
+        float x[2][kIter];
+        smem_load_iter<FMT>(buf + it * kIter * fb, fb, stereo, nch, x);
+        const int kind = iter_kind(f0, W, (int) aq, L, ww.lmin_valid);
+        if (kind == ITER_WARM) {
+          if (C == 1) iter_warm<TPF, 1>(c, kc, x); else iter_warm<TPF, 2>(c, kc, x);
+        } else {
+          float ab[2 * kIter];
+          const float4* abp = reinterpret_cast<const float4*>(ab_tab + 2 * f0);
+#pragma unroll
+          for (int i = 0; i < kIter / 2; ++i) {
+            const float4 v = __ldg(abp + i);
+            ab[4 * i] = v.x; ab[4 * i + 1] = v.y; ab[4 * i + 2] = v.z; ab[4 * i + 3] = v.w;
+          }
+          if (kind == ITER_FAST) {
+            if (C == 1) iter_fast<TPF, 1>(c, kc, x, ab, f0); else iter_fast<TPF, 2>(c, kc, x, ab, f0);
+          } else {
+            if (C == 1) iter_masked<TPF, 1>(c, kc, x, ab, f0); else iter_masked<TPF, 2>(c, kc, x, ab, f0);
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
   if (active) {
-    GlobalSource<FMT> src;
-    src.pcm = tr.pcm;
-    src.frames = (long long) tr.frames;
-    src.origin = (long long) chunk * cs.L - cs.W;
-    src.channels = (int) C;
-    src.ch0 = ch0;
-    src.nch = nch;
-    const long long left = (long long) tr.frames - (long long) chunk * cs.L;
-    const int L_valid = left < cs.L ? (int) left : cs.L;
-    sweep_chunk<TPF>(cs, basis + 2 * cs.basis_off, src, cs.L, L_valid, out);
     ChunkRec* r = recs + tr.rec_base + (uint64_t) chunk * C + ch0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       if (h < nch) {
         ChunkRec v;
-        v.e0 = out[h].e0; v.xa = out[h].xa; v.xb = out[h].xb;
-        v.pd = out[h].pd; v.pw = out[h].pw; v.qd = out[h].qd; v.qw = out[h].qw;
+        v.e0 = c.e0[h]; v.xa = c.xa[h]; v.xb = c.xb[h];
+        v.pd = c.pd[h]; v.pw = c.pw[h]; v.qd = c.qd[h]; v.qw = c.qw[h];
         r[h] = v;
       }
     }
@@ -70,10 +229,10 @@ sweep_kernel(const Track* __restrict__ tracks, const CoefSet* __restrict__ coefs
   // Peaks: non-negative floats order like their bit patterns.  Reduce over
   // the lanes of the warp that hold the same channel pair, one atomic each.
   const unsigned peers = __match_any_sync(0xffffffffu, active ? pair : 0xffffu);
-  uint32_t v[4] = {__float_as_uint(out[0].sp), __float_as_uint(out[0].tp),
-                   __float_as_uint(out[1].sp), __float_as_uint(out[1].tp)};
+  uint32_t v[4] = {__float_as_uint(c.sp[0]), __float_as_uint(c.tp[0]),
+                   __float_as_uint(c.sp[1]), __float_as_uint(c.tp[1])};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = __reduce_max_sync(peers, v[i]);
+  for (int i = 0; i < 4; ++i) v[i] = __reduce_max_sync(peers, active ? v[i] : 0u);
   if (active && lane == (uint32_t) (__ffs(peers) - 1)) {
     uint32_t* pk = peaks + 2 * (tr.peak_base + ch0);
     atomicMax(pk + 0, v[0]);
@@ -87,25 +246,33 @@ sweep_kernel(const Track* __restrict__ tracks, const CoefSet* __restrict__ coefs
 
 template <int FMT, int TPF>
 static cudaError_t launch_sweep_t(const DeviceTables& t, uint32_t first_warp, uint32_t nwarps,
-                                  cudaStream_t stream) {
+                                  uint32_t warp_smem, cudaStream_t stream) {
   const uint32_t wpb = kSweepThreads / 32;
   const uint32_t blocks = (nwarps + wpb - 1) / wpb;
-  sweep_kernel<FMT, TPF><<<blocks, kSweepThreads, 0, stream>>>(
-      t.tracks, t.coefs, t.basis, t.work + first_warp, nwarps, t.recs, t.peaks);
+  const size_t smem = (size_t) warp_smem * wpb;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<FMT, TPF>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  sweep_kernel<FMT, TPF><<<blocks, kSweepThreads, smem, stream>>>(
+      t.tracks, t.coefs, t.basis, t.work + first_warp, nwarps, warp_smem, t.recs, t.peaks);
   return cudaGetLastError();
 }
 
 cudaError_t launch_sweep(const DeviceTables& t, uint32_t format, int tpf, uint32_t first_warp,
-                         uint32_t nwarps, cudaStream_t stream) {
+                         uint32_t nwarps, uint32_t warp_smem, cudaStream_t stream) {
   if (nwarps == 0) return cudaSuccess;
   if (format == FMT_S16) {
-    if (tpf == 4) return launch_sweep_t<FMT_S16, 4>(t, first_warp, nwarps, stream);
-    if (tpf == 2) return launch_sweep_t<FMT_S16, 2>(t, first_warp, nwarps, stream);
-    return launch_sweep_t<FMT_S16, 0>(t, first_warp, nwarps, stream);
+    if (tpf == 4) return launch_sweep_t<FMT_S16, 4>(t, first_warp, nwarps, warp_smem, stream);
+    if (tpf == 2) return launch_sweep_t<FMT_S16, 2>(t, first_warp, nwarps, warp_smem, stream);
+    return launch_sweep_t<FMT_S16, 0>(t, first_warp, nwarps, warp_smem, stream);
   }
-  if (tpf == 4) return launch_sweep_t<FMT_F32, 4>(t, first_warp, nwarps, stream);
-  if (tpf == 2) return launch_sweep_t<FMT_F32, 2>(t, first_warp, nwarps, stream);
-  return launch_sweep_t<FMT_F32, 0>(t, first_warp, nwarps, stream);
+  if (tpf == 4) return launch_sweep_t<FMT_F32, 4>(t, first_warp, nwarps, warp_smem, stream);
+  if (tpf == 2) return launch_sweep_t<FMT_F32, 2>(t, first_warp, nwarps, warp_smem, stream);
+  return launch_sweep_t<FMT_F32, 0>(t, first_warp, nwarps, warp_smem, stream);
 }
 
 // --------------------------------------------------------- post-processing
@@ -125,8 +292,9 @@ __device__ uint32_t find_track(const Track* tracks, uint32_t ntracks, uint64_t i
 
 __global__ void __launch_bounds__(256)
 fixup_kernel(const Track* __restrict__ tracks, uint32_t ntracks,
-             const CoefSet* __restrict__ coefs, const ChunkRec* __restrict__ recs,
-             uint64_t total_recs, double* __restrict__ echunk) {
+             const CoefSet* __restrict__ coefs, const double* __restrict__ gram,
+             const ChunkRec* __restrict__ recs, uint64_t total_recs,
+             double* __restrict__ echunk) {
   const uint64_t r = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= total_recs) return;
   const uint32_t ti = find_track(tracks, ntracks, r, [](const Track& t) { return t.rec_base; });
@@ -136,7 +304,9 @@ fixup_kernel(const Track* __restrict__ tracks, uint32_t ntracks,
   const uint64_t chunk = local / tr.channels;
   const uint32_t ch = (uint32_t) (local - chunk * tr.channels);
   if (chunk >= (uint64_t) tr.nslots * cs.k) return;   // tail chunks carry peaks only
-  echunk[r] = chunk_true_energy(cs, recs + tr.rec_base + ch, tr.channels, (long long) chunk);
+  const LaneGeom geo = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, (long long) chunk);
+  echunk[r] = chunk_true_energy(cs, gram + 3 * cs.gram_off, recs + tr.rec_base + ch, tr.channels,
+                                (long long) chunk, geo.o);
 }
 
 __global__ void __launch_bounds__(256)
@@ -323,8 +493,8 @@ query_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ quer
 cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t stream) {
   if (z.total_recs) {
     const unsigned blocks = (unsigned) ((z.total_recs + 255) / 256);
-    fixup_kernel<<<blocks, 256, 0, stream>>>(t.tracks, z.ntracks, t.coefs, t.recs, z.total_recs,
-                                            t.echunk);
+    fixup_kernel<<<blocks, 256, 0, stream>>>(t.tracks, z.ntracks, t.coefs, t.gram, t.recs,
+                                            z.total_recs, t.echunk);
   }
   if (z.total_slots) {
     const unsigned blocks = (unsigned) ((z.total_slots + 255) / 256);

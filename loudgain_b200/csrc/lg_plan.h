@@ -34,11 +34,13 @@ struct SweepGroup {
   int32_t tpf;
   uint32_t first_warp;   // into Plan::work
   uint32_t nwarps;
+  uint32_t warp_smem;    // staging bytes per warp (max over the group's tracks)
 };
 
 struct Plan {
   std::vector<CoefSet> coefs;
   std::vector<float> basis;          // float2 per entry
+  std::vector<double> gram;          // 3 doubles per entry
   std::vector<Track> tracks;
   std::vector<WarpWork> work;
   std::vector<SweepGroup> groups;
@@ -87,12 +89,15 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, uint64_t t
     auto it = coef_index.find(key);
     if (it == coef_index.end()) {
       CoefSet cs;
-      make_coefset(t.samplerate, k, t.format == FMT_S16 ? 32768.0 : 1.0, cs, p.basis);
+      make_coefset(t.samplerate, k, t.format == FMT_S16 ? 32768.0 : 1.0, cs, p.basis, p.gram);
       it = coef_index.emplace(key, (uint32_t) p.coefs.size()).first;
       p.coefs.push_back(cs);
     }
     tr.coef = it->second;
     const CoefSet& cs = p.coefs[tr.coef];
+    tr.fb = t.channels * (t.format == FMT_S16 ? 2u : 4u);
+    tr.aq = align_quantum(tr.fb);
+    tr.niters = (uint32_t) ((cs.W + (int) tr.aq - 1 + cs.L + kIter - 1) / kIter);
     tr.nslots = (uint32_t) (t.frames / (uint64_t) s100);
     tr.nchunks = (uint32_t) ((t.frames + cs.L - 1) / (uint64_t) cs.L);
     tr.nblocks = tr.nslots >= 4 ? tr.nslots - 3 : 0;
@@ -112,13 +117,30 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, uint64_t t
   // -- sweep work list, grouped by kernel instantiation (format, tp factor)
   for (uint32_t fmt = 0; fmt < 2; ++fmt) {
     for (int tpf : {4, 2, 0}) {
-      SweepGroup g{fmt, tpf, (uint32_t) p.work.size(), 0};
+      SweepGroup g{fmt, tpf, (uint32_t) p.work.size(), 0, 0};
       for (size_t i = 0; i < n; ++i) {
         const Track& tr = p.tracks[i];
         if (tr.format != fmt || p.coefs[tr.coef].tpf != tpf) continue;
+        const CoefSet& cs = p.coefs[tr.coef];
         const uint32_t cpw = 32u / (uint32_t) pairs_per_chunk(tr.channels);
-        for (uint32_t c = 0; c < tr.nchunks; c += cpw)
-          p.work.push_back(WarpWork{(uint32_t) i, c});
+        {
+          const uint32_t units = (kStageFrames * tr.fb) >> 4;
+          const uint32_t need = kRing * cpw * ((units | 1u) << 4);
+          if (need > g.warp_smem) g.warp_smem = need;
+        }
+        const long long stage_frames = (long long) ((tr.niters + kItersPerStage - 1) / kItersPerStage) * kStageFrames;
+        for (uint32_t c = 0; c < tr.nchunks; c += cpw) {
+          const uint32_t last = c + cpw - 1;
+          const LaneGeom g0 = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, c);
+          const LaneGeom g1 = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, last);
+          int lmin = cs.L;
+          if (last >= tr.nchunks - 1) {
+            const LaneGeom gl = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, tr.nchunks - 1);
+            lmin = gl.l_valid;
+          }
+          const bool interior = g0.a >= 0 && g1.a + stage_frames <= (long long) tr.frames;
+          p.work.push_back(WarpWork{(uint32_t) i, c, lmin, interior ? 1u : 0u});
+        }
       }
       g.nwarps = (uint32_t) p.work.size() - g.first_warp;
       if (g.nwarps) p.groups.push_back(g);

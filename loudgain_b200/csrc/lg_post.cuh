@@ -19,9 +19,10 @@ LG_HD void mat2_vec(const double m[4], double x, double y, double& ox, double& o
 
 // True K-weighted energy (still unscaled) of chunk j of one channel.
 // recs points at the channel's record of chunk 0; consecutive chunks are
-// `stride` records apart.
-LG_HD double chunk_true_energy(const CoefSet& cs, const ChunkRec* recs, long long stride,
-                               long long j) {
+// `stride` records apart.  `gram` is the coefficient set's prefix Gram table,
+// `o` the lane's alignment offset (lg_common.h, lane_geometry).
+LG_HD double chunk_true_energy(const CoefSet& cs, const double* gram, const ChunkRec* recs,
+                               long long stride, long long j, int o) {
   // T = true high-pass state at the first frame of chunk j.
   double td = 0.0, tw = 0.0;
   long long i = j - cs.horner;
@@ -35,11 +36,15 @@ LG_HD double chunk_true_energy(const CoefSet& cs, const ChunkRec* recs, long lon
     tw = (double) r.qw + my;
   }
   const ChunkRec& r = recs[j * stride];
-  // State the zero-started run was missing at its own first (warm-up) frame.
+  // State the zero-started run was missing at its own first (warm-up) frame,
+  // W + o frames before the chunk.
   double ad, aw;
-  mat2_vec(cs.MinvW, td - (double) r.pd, tw - (double) r.pw, ad, aw);
+  mat2_vec(cs.MinvWo[o], td - (double) r.pd, tw - (double) r.pw, ad, aw);
+  const double* g0 = gram + 3 * (long long) (cs.W + o);
+  const double* g1 = g0 + 3 * (long long) cs.L;
+  const double gaa = g1[0] - g0[0], gab = g1[1] - g0[1], gbb = g1[2] - g0[2];
   return r.e0 + 2.0 * ((double) r.xa * ad + (double) r.xb * aw) +
-         cs.Gaa * ad * ad + 2.0 * cs.Gab * ad * aw + cs.Gbb * aw * aw;
+         gaa * ad * ad + 2.0 * gab * ad * aw + gbb * aw * aw;
 }
 
 LG_HD double weight_of(uint8_t wclass) {

@@ -1,6 +1,6 @@
-// lg_sweep.cuh -- the per-(chunk, channel-pair) body of the fused sweep:
-// K-weighting + slot energy + sample peak + polyphase true peak over one time
-// chunk of one track, started from zero filter state `W` frames early.
+// lg_sweep.cuh -- the per-lane body of the fused sweep: K-weighting + chunk
+// energy + sample peak + polyphase true peak over one time chunk of one
+// channel pair, started from zero filter state before the chunk.
 //
 // This is the B200 re-design of what the reference path does serially inside
 // ebur128_add_frames_short (/root/reference/src/scan.c:448; behaviour per
@@ -11,6 +11,10 @@
 // (sum y*alpha, sum y*beta) and snapshots its own high-pass state at the
 // chunk's first and last frame; lg_post.cuh composes the transition matrices
 // across chunks and applies the exact energy correction in FP64.
+//
+// A lane works in iterations of kIter frames, handed to it as raw samples
+// x[channel][frame]; how an iteration is run (warm-up / fast / masked) is
+// decided uniformly per warp by iter_kind() in lg_common.h.
 //
 // All arithmetic here is explicit fmaf/add on floats so that the host
 // compile used by tests/emu reproduces the device bit for bit.
@@ -23,53 +27,10 @@
 
 namespace lg {
 
-// ----- sample access -------------------------------------------------------
-// A Source hands out the raw (unscaled) sample pair of lane-local frame f;
-// frames outside the track read as zero (the reference starts from a zeroed
-// delay line and filter state).
-template <int FMT>
-struct GlobalSource {
-  const void* pcm;     // frame 0 of the track
-  long long frames;    // track length
-  long long origin;    // track frame of lane-local frame 0 (may be negative)
-  int channels;
-  int ch0;             // first channel of the pair
-  int nch;             // 1 or 2 live channels in the pair
-
-  LG_HD void get(int f, float& a, float& b) const {
-    const long long t = origin + f;
-    a = 0.0f; b = 0.0f;
-    if (t < 0 || t >= frames) return;
-    if (FMT == FMT_S16) {
-      const short* p = (const short*) pcm + t * channels + ch0;
-#if defined(__CUDA_ARCH__)
-      a = (float) __ldg(p);
-      if (nch > 1) b = (float) __ldg(p + 1);
-#else
-      a = (float) p[0];
-      if (nch > 1) b = (float) p[1];
-#endif
-    } else {
-      const float* p = (const float*) pcm + t * channels + ch0;
-#if defined(__CUDA_ARCH__)
-      a = __ldg(p);
-      if (nch > 1) b = __ldg(p + 1);
-#else
-      a = p[0];
-      if (nch > 1) b = p[1];
-#endif
-    }
-  }
-};
-
-LG_HD void basis_at(const float* basis, int f, float& al, float& be) {
-#if defined(__CUDA_ARCH__)
-  const float2 t = __ldg((const float2*) basis + f);
-  al = t.x; be = t.y;
-#else
-  al = basis[2 * f]; be = basis[2 * f + 1];
-#endif
-}
+template <int TPF> struct TpTraits;
+template <> struct TpTraits<4> { static constexpr int kTaps = 12; };
+template <> struct TpTraits<2> { static constexpr int kTaps = 24; };
+template <> struct TpTraits<0> { static constexpr int kTaps = 0; };
 
 // ----- filter state of one channel ----------------------------------------
 struct KState {
@@ -77,24 +38,30 @@ struct KState {
   float v1, v2;       // shelf
 };
 
+// The sweep's view of a coefficient set (registers / uniform registers).
+struct KCoef {
+  float c, ne2, np1, np2, q1, q2;
+};
+
+LG_HD KCoef load_kcoef(const CoefSet& cs) {
+  KCoef k;
+  k.c = cs.c; k.ne2 = -cs.e2; k.np1 = -cs.p1; k.np2 = -cs.p2; k.q1 = cs.q1; k.q2 = cs.q2;
+  return k;
+}
+
 // One frame of K-weighting.  Returns the (unnormalised) K-weighted sample.
-LG_HD float k_step(KState& s, float x, const CoefSet& cs) {
-  const float t = fmaf(-cs.e2, s.w2, x);
-  const float d = fmaf(cs.c, s.d1, t);
+LG_HD float k_step(KState& s, float x, const KCoef& k) {
+  const float t = fmaf(k.ne2, s.w2, x);
+  const float d = fmaf(k.c, s.d1, t);
   const float w = s.w1 + d;
   const float yh = d - s.d1;
-  const float u = fmaf(-cs.p2, s.v2, yh);
-  const float v = fmaf(-cs.p1, s.v1, u);
-  const float y = fmaf(cs.q2, s.v2, fmaf(cs.q1, s.v1, v));
+  const float u = fmaf(k.np2, s.v2, yh);
+  const float v = fmaf(k.np1, s.v1, u);
+  const float y = fmaf(k.q2, s.v2, fmaf(k.q1, s.v1, v));
   s.w2 = s.w1; s.w1 = w; s.d1 = d;
   s.v2 = s.v1; s.v1 = v;
   return y;
 }
-
-template <int TPF> struct TpTraits;
-template <> struct TpTraits<4> { static constexpr int kTaps = 12, kPhases = 3; };
-template <> struct TpTraits<2> { static constexpr int kTaps = 24, kPhases = 1; };
-template <> struct TpTraits<0> { static constexpr int kTaps = 0, kPhases = 0; };
 
 // max |phase outputs| for the newest frame at win[idx]; taps ascending = newest
 // sample first, the order the reference accumulates in.
@@ -118,144 +85,147 @@ LG_HD float tp_frame(const float* win, int idx) {
   return m;
 }
 
-// Result of one chunk for one channel, before it is written out.
-struct ChanOut {
-  double e0;
-  float xa, xb;
-  float pd, pw, qd, qw;
-  float sp, tp;
+// Everything one lane carries through its chunk, for up to two channels.
+template <int TPF>
+struct LaneCtx {
+  static constexpr int NT = TpTraits<TPF>::kTaps;
+  static constexpr int WIN = NT + kIter;
+  KState st[2];
+  float win[2][WIN > 0 ? WIN : 1];   // [0, NT) history, [NT, WIN) this iteration
+  float sp[2], tp[2];                // raw-unit sample / true peak
+  float xa[2], xb[2];
+  double e0[2];
+  float pd[2], pw[2], qd[2], qw[2];  // state snapshots
+  int f_lo, f_hi, f_tp;              // energy range, true-peak limit (lane-local)
 };
 
-// Processes one chunk for a pair of channels.
-//   L_energy : frames over which energy is accumulated (cs.L)
-//   L_valid  : frames of the chunk that exist in the track (<= L_energy);
-//              true-peak outputs beyond it are discarded.
-template <int TPF, class Source>
-LG_HD void sweep_chunk(const CoefSet& cs, const float* basis, const Source& src,
-                       int L_energy, int L_valid, ChanOut out[2]) {
-  constexpr int NT = TpTraits<TPF>::kTaps;
-  constexpr int WIN = NT + kIter;
-  KState st[2];
-  float win[2][WIN > 0 ? WIN : 1];
-  float sp[2] = {0.0f, 0.0f}, tp[2] = {0.0f, 0.0f};
-  float xa[2] = {0.0f, 0.0f}, xb[2] = {0.0f, 0.0f};
-  double e0[2] = {0.0, 0.0};
+template <int TPF>
+LG_HD void lane_init(LaneCtx<TPF>& c, int W, int L, const LaneGeom& g) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    st[h].d1 = st[h].w1 = st[h].w2 = st[h].v1 = st[h].v2 = 0.0f;
+    c.st[h].d1 = c.st[h].w1 = c.st[h].w2 = c.st[h].v1 = c.st[h].v2 = 0.0f;
 #pragma unroll
-    for (int i = 0; i < WIN; ++i) win[h][i] = 0.0f;
+    for (int i = 0; i < LaneCtx<TPF>::WIN; ++i) c.win[h][i] = 0.0f;
+    c.sp[h] = c.tp[h] = c.xa[h] = c.xb[h] = 0.0f;
+    c.e0[h] = 0.0;
+    c.pd[h] = c.pw[h] = c.qd[h] = c.qw[h] = 0.0f;
   }
+  c.f_lo = W + g.o;
+  c.f_hi = c.f_lo + L;
+  c.f_tp = c.f_lo + g.l_valid;
+}
 
-  const int W = cs.W;
-  // ---- warm-up: state only, keeps the true-peak window primed
-  for (int f0 = 0; f0 < W; f0 += kIter) {
-    float x[2][kIter];
+template <int TPF>
+LG_HD void win_push(LaneCtx<TPF>& c, int h, const float* x) {
+  constexpr int NT = LaneCtx<TPF>::NT;
+  if (NT > 0) {
 #pragma unroll
-    for (int i = 0; i < kIter; ++i) src.get(f0 + i, x[0][i], x[1][i]);
+    for (int i = 0; i < kIter; ++i) c.win[h][NT + i] = x[i];
+  }
+}
+
+template <int TPF>
+LG_HD void win_slide(LaneCtx<TPF>& c, int h) {
+  constexpr int NT = LaneCtx<TPF>::NT;
+  if (NT > 0) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int i = 0; i < NT; ++i) c.win[h][i] = c.win[h][i + kIter];
+  }
+}
+
+// Warm-up iteration: filter state and true-peak history only.
+template <int TPF, int NCH>
+LG_HD void iter_warm(LaneCtx<TPF>& c, const KCoef& k, const float x[2][kIter]) {
 #pragma unroll
-      for (int i = 0; i < kIter; ++i) (void) k_step(st[h], x[h][i], cs);
-      if (NT > 0) {
-        // same slide as the main loop: newest frames enter at the top, then
-        // the window moves down so that win[0..NT) is the history
+  for (int h = 0; h < NCH; ++h) {
 #pragma unroll
-        for (int i = 0; i < kIter; ++i) win[h][NT + i] = x[h][i];
+    for (int i = 0; i < kIter; ++i) (void) k_step(c.st[h], x[h][i], k);
+    win_push(c, h, x[h]);
+    win_slide(c, h);
+    // state before the first chunk frame of a lane with offset 0; lanes with
+    // a larger offset overwrite it in their first masked iteration
+    c.pd[h] = c.st[h].d1; c.pw[h] = c.st[h].w2;
+  }
+}
+
+// Fast iteration: all kIter frames lie inside every lane's chunk.
+// ab = alpha/beta of frames f0.. as float2 pairs.
+template <int TPF, int NCH>
+LG_HD void iter_fast(LaneCtx<TPF>& c, const KCoef& k, const float x[2][kIter],
+                     const float* ab, int f0) {
+  constexpr int NT = LaneCtx<TPF>::NT;
 #pragma unroll
-        for (int i = 0; i < NT; ++i) win[h][i] = win[h][i + kIter];
-      }
+  for (int h = 0; h < NCH; ++h) {
+    float e = 0.0f, sa = 0.0f, sb = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kIter; ++i) {
+      const float y = k_step(c.st[h], x[h][i], k);
+      e = fmaf(y, y, e);
+      sa = fmaf(y, ab[2 * i], sa);
+      sb = fmaf(y, ab[2 * i + 1], sb);
+      c.sp[h] = fmaxf(c.sp[h], fabsf(x[h][i]));
     }
+    c.e0[h] += (double) e;
+    c.xa[h] += sa;
+    c.xb[h] += sb;
+    if (NT > 0) {
+      win_push(c, h, x[h]);
+#pragma unroll
+      for (int i = 0; i < kIter; ++i) c.tp[h] = fmaxf(c.tp[h], tp_frame<TPF>(c.win[h], NT + i));
+      win_slide(c, h);
+    }
+    if (f0 + kIter == c.f_hi) { c.qd[h] = c.st[h].d1; c.qw[h] = c.st[h].w2; }
   }
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    out[h].pd = st[h].d1; out[h].pw = st[h].w2;
-    out[h].qd = st[h].d1; out[h].qw = st[h].w2;
-  }
+}
 
-  const int f_hi = W + L_energy;
-  const int f_tp = W + L_valid;
-  const int f_end = L_valid < L_energy ? f_tp : f_hi;   // partial chunks stop early
-  const int n_full = (L_valid < L_energy ? L_valid : L_energy) / kIter;
-
-  // ---- main iterations: every frame is inside the chunk
-  int f0 = W;
-  for (int it = 0; it < n_full; ++it, f0 += kIter) {
-    float x[2][kIter];
+// Masked iteration: frames are tested one by one against the lane's ranges;
+// also takes the state snapshots at the chunk's first and last frame.
+template <int TPF, int NCH>
+LG_HD void iter_masked(LaneCtx<TPF>& c, const KCoef& k, const float x[2][kIter],
+                       const float* ab, int f0) {
+  constexpr int NT = LaneCtx<TPF>::NT;
 #pragma unroll
-    for (int i = 0; i < kIter; ++i) src.get(f0 + i, x[0][i], x[1][i]);
-    float al[kIter], be[kIter];
+  for (int h = 0; h < NCH; ++h) {
+    float e = 0.0f, sa = 0.0f, sb = 0.0f;
+    win_push(c, h, x[h]);
 #pragma unroll
-    for (int i = 0; i < kIter; ++i) basis_at(basis, f0 + i, al[i], be[i]);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      float e = 0.0f, sa = 0.0f, sb = 0.0f;
-#pragma unroll
-      for (int i = 0; i < kIter; ++i) {
-        const float y = k_step(st[h], x[h][i], cs);
+    for (int i = 0; i < kIter; ++i) {
+      const int f = f0 + i;
+      if (f == c.f_lo) { c.pd[h] = c.st[h].d1; c.pw[h] = c.st[h].w2; }
+      const float y = k_step(c.st[h], x[h][i], k);
+      if (f >= c.f_lo && f < c.f_hi) {
         e = fmaf(y, y, e);
-        sa = fmaf(y, al[i], sa);
-        sb = fmaf(y, be[i], sb);
-        sp[h] = fmaxf(sp[h], fabsf(x[h][i]));
+        sa = fmaf(y, ab[2 * i], sa);
+        sb = fmaf(y, ab[2 * i + 1], sb);
       }
-      e0[h] += (double) e;
-      xa[h] += sa;
-      xb[h] += sb;
-      if (NT > 0) {
-#pragma unroll
-        for (int i = 0; i < kIter; ++i) win[h][NT + i] = x[h][i];
-#pragma unroll
-        for (int i = 0; i < kIter; ++i) tp[h] = fmaxf(tp[h], tp_frame<TPF>(win[h], NT + i));
-#pragma unroll
-        for (int i = 0; i < NT; ++i) win[h][i] = win[h][i + kIter];
+      if (f + 1 == c.f_hi) { c.qd[h] = c.st[h].d1; c.qw[h] = c.st[h].w2; }
+      if (f >= c.f_lo && f < c.f_tp) {
+        c.sp[h] = fmaxf(c.sp[h], fabsf(x[h][i]));
+        if (NT > 0) c.tp[h] = fmaxf(c.tp[h], tp_frame<TPF>(c.win[h], NT + i));
       }
     }
+    c.e0[h] += (double) e;
+    c.xa[h] += sa;
+    c.xb[h] += sb;
+    win_slide(c, h);
   }
-#pragma unroll
-  for (int h = 0; h < 2; ++h) { out[h].qd = st[h].d1; out[h].qw = st[h].w2; }
+}
 
-  // ---- tail iterations: frames are masked one by one
-  for (; f0 < f_end; f0 += kIter) {
-    float x[2][kIter];
-#pragma unroll
-    for (int i = 0; i < kIter; ++i) src.get(f0 + i, x[0][i], x[1][i]);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      float e = 0.0f, sa = 0.0f, sb = 0.0f;
-      if (NT > 0) {
-#pragma unroll
-        for (int i = 0; i < kIter; ++i) win[h][NT + i] = x[h][i];
-      }
-#pragma unroll
-      for (int i = 0; i < kIter; ++i) {
-        const int f = f0 + i;
-        const float y = k_step(st[h], x[h][i], cs);
-        if (f < f_hi) {
-          float al, be;
-          basis_at(basis, f, al, be);
-          e = fmaf(y, y, e);
-          sa = fmaf(y, al, sa);
-          sb = fmaf(y, be, sb);
-        }
-        if (f + 1 == f_hi) { out[h].qd = st[h].d1; out[h].qw = st[h].w2; }
-        if (f < f_tp) {
-          sp[h] = fmaxf(sp[h], fabsf(x[h][i]));
-          if (NT > 0) tp[h] = fmaxf(tp[h], tp_frame<TPF>(win[h], NT + i));
-        }
-      }
-      e0[h] += (double) e;
-      xa[h] += sa;
-      xb[h] += sb;
-      if (NT > 0) {
-#pragma unroll
-        for (int i = 0; i < NT; ++i) win[h][i] = win[h][i + kIter];
-      }
+// ----- host-side sample access (tests/emu) ----------------------------------
+// Raw samples of lane-local frames [f0, f0 + kIter) of a channel pair; frames
+// outside the track read as zero, exactly what the device's zero-filling
+// cp.async stages.
+template <int FMT>
+inline void host_load_iter(const void* pcm, long long frames, int channels, long long a, int f0,
+                           int ch0, int nch, float x[2][kIter]) {
+  for (int i = 0; i < kIter; ++i) {
+    const long long t = a + f0 + i;
+    x[0][i] = 0.0f; x[1][i] = 0.0f;
+    if (t < 0 || t >= frames) continue;
+    for (int h = 0; h < nch; ++h) {
+      if (FMT == FMT_S16) x[h][i] = (float) ((const short*) pcm)[t * channels + ch0 + h];
+      else x[h][i] = ((const float*) pcm)[t * channels + ch0 + h];
     }
-  }
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    out[h].e0 = e0[h]; out[h].xa = xa[h]; out[h].xb = xb[h];
-    out[h].sp = sp[h]; out[h].tp = tp[h];
   }
 }
 

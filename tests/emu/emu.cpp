@@ -27,27 +27,40 @@ static void run_group(const Plan& p, const SweepGroup& g, std::vector<ChunkRec>&
     const WarpWork ww = p.work[g.first_warp + w];
     const Track& tr = p.tracks[ww.track];
     const CoefSet& cs = p.coefs[tr.coef];
+    const KCoef k = load_kcoef(cs);
+    const float* basis = p.basis.data() + 2 * cs.basis_off;
     const uint32_t C = tr.channels, ppc = (C + 1) / 2, cpw = 32 / ppc;
     for (uint32_t lane = 0; lane < 32; ++lane) {
       const uint32_t slot = lane / ppc, pair = lane - slot * ppc, chunk = ww.first_chunk + slot;
       if (!(slot < cpw && chunk < tr.nchunks)) continue;
       const int ch0 = (int) pair * 2, nch = (ch0 + 1 < (int) C) ? 2 : 1;
-      GlobalSource<FMT> src;
-      src.pcm = tr.pcm; src.frames = (long long) tr.frames;
-      src.origin = (long long) chunk * cs.L - cs.W;
-      src.channels = (int) C; src.ch0 = ch0; src.nch = nch;
-      const long long left = (long long) tr.frames - (long long) chunk * cs.L;
-      const int L_valid = left < cs.L ? (int) left : cs.L;
-      ChanOut out[2];
-      sweep_chunk<TPF>(cs, p.basis.data() + 2 * cs.basis_off, src, cs.L, L_valid, out);
+      const LaneGeom geo = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, chunk);
+      LaneCtx<TPF> c;
+      lane_init(c, cs.W, cs.L, geo);
+      for (uint32_t it = 0; it < tr.niters; ++it) {
+        const int f0 = (int) it * kIter;
+        float x[2][kIter];
+        host_load_iter<FMT>(tr.pcm, (long long) tr.frames, (int) C, geo.a, f0, ch0, nch, x);
+        const int kind = iter_kind(f0, cs.W, (int) tr.aq, cs.L, ww.lmin_valid);
+        const float* ab = basis + 2 * f0;
+        if (C == 1) {
+          if (kind == ITER_WARM) iter_warm<TPF, 1>(c, k, x);
+          else if (kind == ITER_FAST) iter_fast<TPF, 1>(c, k, x, ab, f0);
+          else iter_masked<TPF, 1>(c, k, x, ab, f0);
+        } else {
+          if (kind == ITER_WARM) iter_warm<TPF, 2>(c, k, x);
+          else if (kind == ITER_FAST) iter_fast<TPF, 2>(c, k, x, ab, f0);
+          else iter_masked<TPF, 2>(c, k, x, ab, f0);
+        }
+      }
       for (int h = 0; h < nch; ++h) {
         ChunkRec& r = recs[tr.rec_base + (uint64_t) chunk * C + ch0 + h];
-        r.e0 = out[h].e0; r.xa = out[h].xa; r.xb = out[h].xb;
-        r.pd = out[h].pd; r.pw = out[h].pw; r.qd = out[h].qd; r.qw = out[h].qw;
+        r.e0 = c.e0[h]; r.xa = c.xa[h]; r.xb = c.xb[h];
+        r.pd = c.pd[h]; r.pw = c.pw[h]; r.qd = c.qd[h]; r.qw = c.qw[h];
         float& sp = peaks[2 * (tr.peak_base + ch0 + h)];
         float& tp = peaks[2 * (tr.peak_base + ch0 + h) + 1];
-        sp = std::max(sp, out[h].sp);
-        tp = std::max(tp, out[h].tp);
+        sp = std::max(sp, c.sp[h]);
+        tp = std::max(tp, c.tp[h]);
       }
     }
   }
@@ -135,10 +148,13 @@ extern "C" int emu_measure(const lgb_track* tracks, size_t ntracks, uint32_t nal
     const Track& tr = p.tracks[ti];
     const CoefSet& cs = p.coefs[tr.coef];
     if (chunk_len_out) chunk_len_out[ti] = cs.L;
-    for (uint64_t chunk = 0; chunk < (uint64_t) tr.nslots * cs.k; ++chunk)
+    for (uint64_t chunk = 0; chunk < (uint64_t) tr.nslots * cs.k; ++chunk) {
+      const LaneGeom geo = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, (long long) chunk);
       for (uint32_t ch = 0; ch < tr.channels; ++ch)
         echunk[tr.rec_base + chunk * tr.channels + ch] =
-            chunk_true_energy(cs, recs.data() + tr.rec_base + ch, tr.channels, (long long) chunk);
+            chunk_true_energy(cs, p.gram.data() + 3 * cs.gram_off, recs.data() + tr.rec_base + ch,
+                              tr.channels, (long long) chunk, geo.o);
+    }
     for (uint32_t s = 0; s < tr.nslots; ++s)
       eslot[tr.slot_base + s] = slot_energy(tr, cs, echunk.data(), s);
     for (uint32_t b = 0; b < tr.nblocks; ++b)
