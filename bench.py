@@ -266,6 +266,17 @@ def gpu_arm(args):
     L.lgb_batch_enable_timing(batch._h, 0)
     value = samples * world * args.steps / (ms_total * 1e-3) / 1e9
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "value": value, "ms_per_step": ms_total / args.steps,
+                              "sweep_ms": sweep_ms,
+                              "sweep_gsamples": samples / (sweep_ms * 1e-3) / 1e9 if sweep_ms else None}),
+                  flush=True)
+        batch.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- end to end through the drop-in ABI from pinned host memory
     host = [t.cpu().pin_memory() for t, _ in album]
     arr = (HostTrack * len(host))()
@@ -335,6 +346,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--quick", action="store_true",
+                    help="tuning runs: skip the CPU baseline and the end-to-end leg")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -14,7 +14,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libebur128.so")
+# LG_LIB_SUFFIX / LG_NVCC_EXTRA build tuning variants next to the product library
+_SUFFIX = os.environ.get("LG_LIB_SUFFIX", "")
+LIB_PATH = os.path.join(LIB_DIR, f"libebur128{'_' + _SUFFIX if _SUFFIX else ''}.so")
 SOURCES = ("lg_kernels.cu", "lg_batch.cu", "lg_ebur128.cu", "lg_scan.cu")
 
 NVCC_FLAGS = [
@@ -49,8 +51,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     objs = []
     for src in SOURCES:
-        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(LIB_DIR, src.replace(".cu", f"{_SUFFIX}.o"))
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("LG_NVCC_EXTRA", "").split(), "-c",
+               os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)

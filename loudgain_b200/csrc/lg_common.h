@@ -119,14 +119,17 @@ struct QueryResult {
   uint64_t nst;     // abs-gated short-term block count
 };
 
-// Work descriptor: one warp of the sweep = up to 32/ceil(C/2) consecutive
-// chunks of one track.
+// Work descriptor: one warp of the sweep = up to 32/min(C,32) consecutive
+// chunks of one track, for channels [ch_base, ch_base + 32).
 struct WarpWork {
   uint32_t track;
   uint32_t first_chunk;
   int32_t lmin_valid;   // shortest valid chunk length among the warp's chunks
-  uint32_t interior;    // 1: every byte the warp stages lies inside the track
+  uint16_t interior;    // 1: every byte the warp stages lies inside the track
+  uint16_t ch_base;     // first channel this warp handles (0 unless C > 32)
 };
+
+LG_BOTH uint32_t chunks_per_warp(uint32_t channels) { return 32u / (channels < 32u ? channels : 32u); }
 
 // ---- lane geometry ---------------------------------------------------------
 // Chunk j covers track frames [j*L, j*L + L).  Its lane starts filtering from

@@ -22,12 +22,23 @@ namespace lg {
 
 // ------------------------------------------------------------------ sweep
 //
-// One warp = up to 32/ceil(C/2) consecutive chunks of one track; one lane =
-// one (chunk, channel pair).  The warp is autonomous (no CTA barrier): it
-// streams its rows HBM -> shared memory with 16-byte cp.async copies laid out
-// so that consecutive lanes fetch consecutive units of one row (coalesced),
-// three stages of 24 frames deep, and each lane then reads its own row with
-// conflict-free 128-bit shared loads (row stride is an odd number of units).
+// One warp = up to 32/min(C,32) consecutive chunks of one track; one lane =
+// one (chunk, channel).  The warp is autonomous (no CTA barrier):
+//
+//  * it streams its rows HBM -> shared memory with 16-byte cp.async copies laid
+//    out so that consecutive lanes fetch consecutive units of one row
+//    (coalesced), kRing stages of 24 frames deep; rows start on 16-byte
+//    boundaries of the track and the row stride is an odd number of units, so
+//    128-bit shared loads of different rows do not collide;
+//  * every lane filters its channel (FP32) and accumulates energy and the
+//    correction cross terms;
+//  * true peak: a 12-frame window is evaluated only if ||c||_1 * max|x| over
+//    the window exceeds what the channel's peak is already known to reach
+//    (own maximum so far, the warp's, and the track-wide value other warps
+//    have published).  Such candidate windows are copied into a per-warp
+//    queue and evaluated 32 at a time, one window per lane, so the FIR runs
+//    dense instead of divergent.  The maximum is identical to evaluating
+//    every window (see lg_sweep.cuh).
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -44,57 +55,76 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// Raw samples of one iteration of the lane's row, from shared memory.
-// rowp -> first frame of the iteration.
+// Raw samples of one iteration of the lane's channel, from shared memory.
+// rowp -> first frame of the iteration in the lane's row.
 template <int FMT>
 __device__ __forceinline__ void smem_load_iter(const unsigned char* rowp, uint32_t fb, bool stereo,
-                                               int nch, float x[2][kIter]) {
-  if (stereo) {
-    if (FMT == FMT_S16) {
-      const uint4* p = reinterpret_cast<const uint4*>(rowp);
+                                               uint32_t ch, float* x) {
+  if (FMT == FMT_S16 && stereo) {
+    const uint4* p = reinterpret_cast<const uint4*>(rowp);
+    const uint32_t sh = ch << 4;
 #pragma unroll
-      for (int u = 0; u < kIter / 4; ++u) {
-        const uint4 v = p[u];
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          x[0][4 * u + j] = (float) (short) (w[j] & 0xffffu);
-          x[1][4 * u + j] = (float) (short) (w[j] >> 16);
-        }
-      }
-    } else {
-      const float4* p = reinterpret_cast<const float4*>(rowp);
-#pragma unroll
-      for (int u = 0; u < kIter / 2; ++u) {
-        const float4 v = p[u];
-        x[0][2 * u] = v.x; x[1][2 * u] = v.y;
-        x[0][2 * u + 1] = v.z; x[1][2 * u + 1] = v.w;
-      }
+    for (int u = 0; u < kIter / 4; ++u) {
+      const uint4 v = p[u];
+      x[4 * u + 0] = (float) (short) (v.x >> sh);
+      x[4 * u + 1] = (float) (short) (v.y >> sh);
+      x[4 * u + 2] = (float) (short) (v.z >> sh);
+      x[4 * u + 3] = (float) (short) (v.w >> sh);
     }
+  } else if (FMT == FMT_S16) {
+    const unsigned char* q = rowp + ch * 2u;
+#pragma unroll
+    for (int i = 0; i < kIter; ++i) x[i] = (float) *reinterpret_cast<const short*>(q + i * fb);
   } else {
+    const unsigned char* q = rowp + ch * 4u;
 #pragma unroll
-    for (int i = 0; i < kIter; ++i) {
-      if (FMT == FMT_S16) {
-        const short* q = reinterpret_cast<const short*>(rowp + i * fb);
-        x[0][i] = (float) q[0];
-        x[1][i] = nch > 1 ? (float) q[1] : 0.0f;
-      } else {
-        const float* q = reinterpret_cast<const float*>(rowp + i * fb);
-        x[0][i] = q[0];
-        x[1][i] = nch > 1 ? q[1] : 0.0f;
-      }
-    }
+    for (int i = 0; i < kIter; ++i) x[i] = *reinterpret_cast<const float*>(q + i * fb);
   }
 }
 
+#ifndef LG_SWEEP_MINBLOCKS
+#define LG_SWEEP_MINBLOCKS 3
+#endif
+
 template <int FMT> struct CopyTraits { static constexpr int kMax = FMT == FMT_S16 ? 6 : 12; };
 
+constexpr uint32_t kQueue = 64;     // candidate windows a warp can hold
+
+template <int TPF>
+__device__ __forceinline__ constexpr uint32_t queue_entry_bytes() {
+  // window floats + one meta word, rounded up to an odd number of 16-byte units
+  return ((((TpTraits<TPF>::kTaps + kIter) * 4u + 4u + 15u) >> 4) | 1u) << 4;
+}
+
+// Evaluates up to 32 queued windows, one per lane.
+template <int TPF>
+__device__ __forceinline__ void flush_round(const unsigned char* queue, uint32_t head, uint32_t n,
+                                            uint32_t lane, uint32_t* tpq) {
+  constexpr int NT = TpTraits<TPF>::kTaps;
+  constexpr uint32_t EB = queue_entry_bytes<TPF>();
+  __syncwarp();                                   // entries written by other lanes are visible
+  if (lane < n) {
+    const unsigned char* e = queue + ((head + lane) & (kQueue - 1)) * EB;
+    float win[NT + kIter];
+    const float4* p = reinterpret_cast<const float4*>(e);
+#pragma unroll
+    for (int i = 0; i < (NT + kIter) / 4; ++i) {
+      const float4 v = p[i];
+      win[4 * i] = v.x; win[4 * i + 1] = v.y; win[4 * i + 2] = v.z; win[4 * i + 3] = v.w;
+    }
+    const uint32_t slot = *reinterpret_cast<const uint32_t*>(e + (NT + kIter) * 4);
+    atomicMax(tpq + slot, __float_as_uint(tp_window<TPF>(win)));
+  }
+  __syncwarp();
+}
+
 template <int FMT, int TPF>
-__global__ void __launch_bounds__(kSweepThreads)
+__global__ void __launch_bounds__(kSweepThreads, LG_SWEEP_MINBLOCKS)
 sweep_kernel(const Track* __restrict__ tracks, const CoefSet* __restrict__ coefs,
              const float* __restrict__ basis, const WarpWork* __restrict__ work,
              uint32_t nwarps, uint32_t warp_smem, ChunkRec* __restrict__ recs,
-             uint32_t* __restrict__ peaks) {
+             uint32_t* peaks) {
+  constexpr int NT = TpTraits<TPF>::kTaps;
   extern __shared__ __align__(16) unsigned char smem_all[];
   const uint32_t wic = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31u;
@@ -113,15 +143,14 @@ sweep_kernel(const Track* __restrict__ tracks, const CoefSet* __restrict__ coefs
   const unsigned char* pcm = reinterpret_cast<const unsigned char*>(tr.pcm);
   const float* ab_tab = basis + 2 * cs.basis_off;
 
-  const uint32_t ppc = (C + 1u) >> 1;
-  const uint32_t cpw = 32u / ppc;
-  const uint32_t slot = lane / ppc;
-  const uint32_t pair = lane - slot * ppc;
+  const uint32_t lpc = C < 32u ? C : 32u;      // lanes per chunk
+  const uint32_t cpw = 32u / lpc;              // chunks per warp
+  const uint32_t slot = lane / lpc;
+  const uint32_t chl = lane - slot * lpc;      // channel within the warp's group
+  const uint32_t ch = ww.ch_base + chl;
   const uint32_t chunk = ww.first_chunk + slot;
-  const bool compute = slot < cpw;
+  const bool compute = slot < cpw && ch < C;
   const bool active = compute && chunk < tr.nchunks;
-  const int ch0 = (int) (pair * 2u);
-  const int nch = (ch0 + 1 < (int) C) ? 2 : 1;
   const bool stereo = C == 2;
 
   // ---- staging geometry
@@ -166,11 +195,29 @@ sweep_kernel(const Track* __restrict__ tracks, const CoefSet* __restrict__ coefs
     }
   };
 
+  // ---- candidate queue and per-channel true-peak cells of this warp
+  constexpr uint32_t EB = queue_entry_bytes<TPF>();
+  unsigned char* queue = sm + kRing * stage_bytes;
+  uint32_t* tpq = reinterpret_cast<uint32_t*>(queue + (NT > 0 ? kQueue * EB : 0));
+  tpq[lane] = 0u;
+  uint32_t q_head = 0, q_tail = 0;
+  // Frames at or beyond this lane-local index may lie past the end of the
+  // track for some lane of the warp: true peak is then masked frame by frame.
+  const LaneGeom glast = lane_geometry(frames, L, W, (int) aq, ww.first_chunk + cpw - 1);
+  const long long tp_safe_ll = frames - glast.a;
+  const int tp_safe = tp_safe_ll > 0x3fffffff ? 0x3fffffff : (int) tp_safe_ll;
+
   // ---- lane state
-  LaneGeom geo = lane_geometry(frames, L, W, (int) aq, chunk);
+  const LaneGeom geo = lane_geometry(frames, L, W, (int) aq, chunk);
   LaneCtx<TPF> c;
   lane_init(c, W, L, geo);
-  const unsigned char* my_row = sm + slot * row_stride + (uint32_t) ch0 * (FMT == FMT_S16 ? 2u : 4u);
+  const unsigned char* my_row = sm + slot * row_stride;
+  uint32_t* my_peak = peaks + 2 * (tr.peak_base + (compute ? ch : 0u));
+  const unsigned peers = __match_any_sync(0xffffffffu, compute ? chl : 0xffffu);
+  const bool leader = compute && lane == (uint32_t) (__ffs(peers) - 1);
+  float thr = 0.0f;        // the channel's peak is known to reach at least this (raw units)
+  float published = 0.0f;
+  const float gain = tp_gain_bound<TPF>();
 
   const uint32_t nstages = (niters + kItersPerStage - 1) / kItersPerStage;
   prefetch(0);
@@ -183,18 +230,22 @@ sweep_kernel(const Track* __restrict__ tracks, const CoefSet* __restrict__ coefs
     __syncwarp();                // ... everyone's have, and stage s-1 is fully consumed
     if (s + 2 < nstages) prefetch(s + 2);
     cp_async_commit();
-    if (compute) {
-      const unsigned char* buf = my_row + (s % kRing) * stage_bytes;
+    // what other warps have published for this channel so far
+    uint2 seen = make_uint2(0u, 0u);
+    if (NT > 0 && compute) seen = __ldcg(reinterpret_cast<const uint2*>(my_peak));
+    const unsigned char* buf = my_row + (s % kRing) * stage_bytes;
 #pragma unroll 1
-      for (int it = 0; it < kItersPerStage; ++it) {
-        const uint32_t iter = s * kItersPerStage + it;
-        if (iter >= niters) break;
-        const int f0 = (int) iter * kIter;
-        float x[2][kIter];
-        smem_load_iter<FMT>(buf + it * kIter * fb, fb, stereo, nch, x);
-        const int kind = iter_kind(f0, W, (int) aq, L, ww.lmin_valid);
+    for (int it = 0; it < kItersPerStage; ++it) {
+      const uint32_t iter = s * kItersPerStage + it;
+      if (iter >= niters) break;
+      const int f0 = (int) iter * kIter;
+      const int kind = iter_kind(f0, W, (int) aq, L, ww.lmin_valid);
+      float x[kIter];
+      bool cand = false;
+      if (compute) {
+        smem_load_iter<FMT>(buf + it * kIter * fb, fb, stereo, ch, x);
         if (kind == ITER_WARM) {
-          if (C == 1) iter_warm<TPF, 1>(c, kc, x); else iter_warm<TPF, 2>(c, kc, x);
+          iter_warm<TPF>(c, kc, x);
         } else {
           float ab[2 * kIter];
           const float4* abp = reinterpret_cast<const float4*>(ab_tab + 2 * f0);
@@ -203,44 +254,84 @@ sweep_kernel(const Track* __restrict__ tracks, const CoefSet* __restrict__ coefs
             const float4 v = __ldg(abp + i);
             ab[4 * i] = v.x; ab[4 * i + 1] = v.y; ab[4 * i + 2] = v.z; ab[4 * i + 3] = v.w;
           }
+          float m;
+          bool safe = true;
           if (kind == ITER_FAST) {
-            if (C == 1) iter_fast<TPF, 1>(c, kc, x, ab, f0); else iter_fast<TPF, 2>(c, kc, x, ab, f0);
+            m = iter_fast_energy<TPF>(c, kc, x, ab, f0);
           } else {
-            if (C == 1) iter_masked<TPF, 1>(c, kc, x, ab, f0); else iter_masked<TPF, 2>(c, kc, x, ab, f0);
+            iter_masked_energy<TPF>(c, kc, x, ab, f0);
+            m = max_abs12(x);
+            safe = f0 + kIter <= tp_safe;
+            if (safe) c.sp = fmaxf(c.sp, m);
+            else iter_peaks_masked<TPF>(c, x, f0);      // track end: frame by frame
+          }
+          if (NT > 0) {
+            cand = safe && gain * fmaxf(c.mprev, m) > fmaxf(thr, c.sp);
+            c.mprev = m;
           }
         }
+      }
+      if (NT > 0 && kind != ITER_WARM) {
+        const unsigned mask = __ballot_sync(0xffffffffu, cand);
+        if (mask) {
+          if (cand) {
+            const uint32_t pos = (q_tail + __popc(mask & ((1u << lane) - 1u))) & (kQueue - 1);
+            float4* e = reinterpret_cast<float4*>(queue + pos * EB);
+#pragma unroll
+            for (int i = 0; i < NT / 4; ++i)
+              e[i] = make_float4(c.hist[4 * i], c.hist[4 * i + 1], c.hist[4 * i + 2], c.hist[4 * i + 3]);
+#pragma unroll
+            for (int i = 0; i < kIter / 4; ++i)
+              e[NT / 4 + i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+            *reinterpret_cast<uint32_t*>(e + (NT + kIter) / 4) = chl;
+          }
+          q_tail += __popc(mask);
+          if (q_tail - q_head >= 32u) {
+            flush_round<TPF>(queue, q_head, 32u, lane, tpq);
+            q_head += 32u;
+            thr = fmaxf(thr, __uint_as_float(tpq[chl]));
+          }
+        }
+        if (compute) hist_advance(c, x);
+      }
+    }
+    if (NT > 0 && compute) {
+      // raise the bound with what other warps know; publish what this warp knows
+      thr = fmaxf(thr, __uint_as_float(seen.x > seen.y ? seen.x : seen.y));
+      const float mine = fmaxf(fmaxf(c.sp, c.tp), __uint_as_float(tpq[chl]));
+      if (mine > thr) thr = mine;
+      if (mine > published && mine > __uint_as_float(seen.x > seen.y ? seen.x : seen.y)) {
+        // goes into the true-peak cell: the reported true peak is the max of
+        // both cells anyway (ebur128_true_peak folds the sample peak in)
+        atomicMax(my_peak + 1, __float_as_uint(mine));
+        published = mine;
       }
     }
   }
   cp_async_wait<0>();
-
-  if (active) {
-    ChunkRec* r = recs + tr.rec_base + (uint64_t) chunk * C + ch0;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (h < nch) {
-        ChunkRec v;
-        v.e0 = c.e0[h]; v.xa = c.xa[h]; v.xb = c.xb[h];
-        v.pd = c.pd[h]; v.pw = c.pw[h]; v.qd = c.qd[h]; v.qw = c.qw[h];
-        r[h] = v;
-      }
+  if (NT > 0) {
+    while (q_tail != q_head) {
+      const uint32_t n = q_tail - q_head < 32u ? q_tail - q_head : 32u;
+      flush_round<TPF>(queue, q_head, n, lane, tpq);
+      q_head += n;
     }
   }
+  __syncwarp();
+
+  if (active) {
+    ChunkRec v;
+    v.e0 = c.e0; v.xa = c.xa; v.xb = c.xb;
+    v.pd = c.pd; v.pw = c.pw; v.qd = c.qd; v.qw = c.qw;
+    recs[tr.rec_base + (uint64_t) chunk * C + ch] = v;
+  }
   // Peaks: non-negative floats order like their bit patterns.  Reduce over
-  // the lanes of the warp that hold the same channel pair, one atomic each.
-  const unsigned peers = __match_any_sync(0xffffffffu, active ? pair : 0xffffu);
-  uint32_t v[4] = {__float_as_uint(c.sp[0]), __float_as_uint(c.tp[0]),
-                   __float_as_uint(c.sp[1]), __float_as_uint(c.tp[1])};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = __reduce_max_sync(peers, active ? v[i] : 0u);
-  if (active && lane == (uint32_t) (__ffs(peers) - 1)) {
-    uint32_t* pk = peaks + 2 * (tr.peak_base + ch0);
-    atomicMax(pk + 0, v[0]);
-    atomicMax(pk + 1, v[1]);
-    if (nch > 1) {
-      atomicMax(pk + 2, v[2]);
-      atomicMax(pk + 3, v[3]);
-    }
+  // the lanes of the warp that hold the same channel, one atomic each.
+  uint32_t spb = __reduce_max_sync(peers, active ? __float_as_uint(c.sp) : 0u);
+  uint32_t tpb = __reduce_max_sync(peers, active ? __float_as_uint(c.tp) : 0u);
+  if (leader) {
+    if (NT > 0) { const uint32_t q = tpq[chl]; tpb = tpb > q ? tpb : q; }
+    atomicMax(my_peak + 0, spb);
+    atomicMax(my_peak + 1, tpb);
   }
 }
 

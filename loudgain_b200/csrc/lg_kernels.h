@@ -35,16 +35,10 @@ struct PostSizes {
   uint64_t total_recs, total_slots, total_blocks, total_st;
 };
 
-// warp_smem: bytes of shared memory each warp needs for its staging ring.
+// warp_smem: shared memory per warp (lg_plan.h, sweep_warp_smem_host).
 cudaError_t launch_sweep(const DeviceTables& t, uint32_t format, int tpf, uint32_t first_warp,
                          uint32_t nwarps, uint32_t warp_smem, cudaStream_t stream);
 
-// Staging bytes one warp needs for a track with `channels` channels of `fb`-byte frames.
-inline uint32_t sweep_warp_smem(uint32_t channels, uint32_t fb) {
-  const uint32_t ppc = (channels + 1u) / 2u, cpw = 32u / ppc;
-  const uint32_t units = (kStageFrames * fb) >> 4;
-  return kRing * cpw * ((units | 1u) << 4);
-}
 cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t stream);
 // Gated loudness + range for `nqueries` queries; all pointers are device memory.
 cudaError_t launch_queries(const BlockList* lists, const Query* queries, const uint32_t* members,

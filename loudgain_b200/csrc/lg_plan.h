@@ -52,19 +52,29 @@ struct Plan {
   uint32_t nalbums = 0;
 };
 
-inline int pairs_per_chunk(uint32_t channels) { return (int) ((channels + 1) / 2); }
-
-// target_tasks: how many (chunk, channel-pair) tasks the sweep should expose
+// target_tasks: how many (chunk, channel) tasks the sweep should expose
 // at least, if the audio is long enough (a few per resident thread).
+// Mirror of sweep_warp_smem() in lg_kernels.cu (kept in the planner so that the
+// host emulation does not need the CUDA translation unit).
+inline uint32_t sweep_warp_smem_host(uint32_t channels, uint32_t fb, int tpf) {
+  const uint32_t cpw = chunks_per_warp(channels);
+  const uint32_t units = (kStageFrames * fb) >> 4;
+  uint32_t bytes = kRing * cpw * ((units | 1u) << 4);
+  if (tpf) {
+    const uint32_t nt = tpf == 4 ? 12u : 24u;
+    bytes += 64u * (((((nt + kIter) * 4u + 4u + 15u) >> 4) | 1u) << 4);
+  }
+  return bytes + 32u * 4u;
+}
+
 inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, uint64_t target_tasks,
                        Plan& p) {
   p = Plan();
   p.nalbums = nalbums;
   // -- chunk length from the total amount of work
-  uint64_t pair_frames = 0;
-  for (size_t i = 0; i < n; ++i)
-    pair_frames += in[i].frames * (uint64_t) pairs_per_chunk(in[i].channels);
-  uint64_t want_len = target_tasks ? pair_frames / target_tasks : 0;
+  uint64_t samples = 0;
+  for (size_t i = 0; i < n; ++i) samples += in[i].frames * (uint64_t) in[i].channels;
+  uint64_t want_len = target_tasks ? samples / target_tasks : 0;
 
   std::map<std::tuple<uint32_t, int, uint32_t>, uint32_t> coef_index;
   p.tracks.resize(n);
@@ -122,24 +132,27 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, uint64_t t
         const Track& tr = p.tracks[i];
         if (tr.format != fmt || p.coefs[tr.coef].tpf != tpf) continue;
         const CoefSet& cs = p.coefs[tr.coef];
-        const uint32_t cpw = 32u / (uint32_t) pairs_per_chunk(tr.channels);
+        const uint32_t cpw = chunks_per_warp(tr.channels);
         {
-          const uint32_t units = (kStageFrames * tr.fb) >> 4;
-          const uint32_t need = kRing * cpw * ((units | 1u) << 4);
+          const uint32_t need = sweep_warp_smem_host(tr.channels, tr.fb, tpf);
           if (need > g.warp_smem) g.warp_smem = need;
         }
-        const long long stage_frames = (long long) ((tr.niters + kItersPerStage - 1) / kItersPerStage) * kStageFrames;
+        const long long stage_frames =
+            (long long) ((tr.niters + kItersPerStage - 1) / kItersPerStage) * kStageFrames;
         for (uint32_t c = 0; c < tr.nchunks; c += cpw) {
           const uint32_t last = c + cpw - 1;
           const LaneGeom g0 = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, c);
           const LaneGeom g1 = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, last);
           int lmin = cs.L;
           if (last >= tr.nchunks - 1) {
-            const LaneGeom gl = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, tr.nchunks - 1);
+            const LaneGeom gl = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq,
+                                              tr.nchunks - 1);
             lmin = gl.l_valid;
           }
           const bool interior = g0.a >= 0 && g1.a + stage_frames <= (long long) tr.frames;
-          p.work.push_back(WarpWork{(uint32_t) i, c, lmin, interior ? 1u : 0u});
+          for (uint32_t cb = 0; cb < tr.channels; cb += 32)
+            p.work.push_back(WarpWork{(uint32_t) i, c, lmin, (uint16_t) (interior ? 1 : 0),
+                                      (uint16_t) cb});
         }
       }
       g.nwarps = (uint32_t) p.work.size() - g.first_warp;

@@ -1,20 +1,30 @@
 // lg_sweep.cuh -- the per-lane body of the fused sweep: K-weighting + chunk
-// energy + sample peak + polyphase true peak over one time chunk of one
-// channel pair, started from zero filter state before the chunk.
+// energy + sample peak + polyphase true peak over one time chunk of ONE
+// channel, started from zero filter state before the chunk.
 //
 // This is the B200 re-design of what the reference path does serially inside
 // ebur128_add_frames_short (/root/reference/src/scan.c:448; behaviour per
 // SURVEY.md A.2-A.5).  Time is cut into chunks of L = s100/k frames; every
-// chunk is filtered independently, so a single stream spreads over all SMs.
-// What a zero start state gets wrong is linear in the true high-pass state at
-// the chunk start, so the sweep also accumulates the two cross terms
-// (sum y*alpha, sum y*beta) and snapshots its own high-pass state at the
-// chunk's first and last frame; lg_post.cuh composes the transition matrices
-// across chunks and applies the exact energy correction in FP64.
+// (chunk, channel) is filtered independently by one lane, so a single stream
+// spreads over all SMs.  What a zero start state gets wrong is linear in the
+// true high-pass state at the chunk start, so the sweep also accumulates the
+// two cross terms (sum y*alpha, sum y*beta) and snapshots its own high-pass
+// state at the chunk's first and last frame; lg_post.cuh composes the
+// transition matrices across chunks and applies the exact energy correction
+// in FP64.
+//
+// True peak: the maximum over all polyphase outputs.  An output can never
+// exceed ||c||_1 * max|x| over the taps' window, so a window whose bound is
+// not above a value the channel's peak is already known to reach cannot move
+// the maximum and need not be evaluated.  The device kernel uses that to
+// defer only the "candidate" windows to a dense evaluation pass; this file
+// provides the window evaluation itself (tp_window) and the exhaustive
+// per-frame form used at chunk edges and by the host emulation.  Both give
+// the same maximum, bit for bit.
 //
 // A lane works in iterations of kIter frames, handed to it as raw samples
-// x[channel][frame]; how an iteration is run (warm-up / fast / masked) is
-// decided uniformly per warp by iter_kind() in lg_common.h.
+// x[frame]; how an iteration is run (warm-up / fast / masked) is decided
+// uniformly per warp by iter_kind() in lg_common.h.
 //
 // All arithmetic here is explicit fmaf/add on floats so that the host
 // compile used by tests/emu reproduces the device bit for bit.
@@ -31,6 +41,10 @@ template <int TPF> struct TpTraits;
 template <> struct TpTraits<4> { static constexpr int kTaps = 12; };
 template <> struct TpTraits<2> { static constexpr int kTaps = 24; };
 template <> struct TpTraits<0> { static constexpr int kTaps = 0; };
+
+// Upper bounds of the phases' tap L1 norms (1.8642 for 4x, 2.3068 for 2x),
+// inflated to cover FP32 rounding of the evaluation.
+template <int TPF> LG_HD float tp_gain_bound() { return TPF == 4 ? 1.8645f : 2.3072f; }
 
 // ----- filter state of one channel ----------------------------------------
 struct KState {
@@ -85,147 +99,176 @@ LG_HD float tp_frame(const float* win, int idx) {
   return m;
 }
 
-// Everything one lane carries through its chunk, for up to two channels.
+// max |phase outputs| over the kIter newest frames of a window
+// win[0, NT) = history, win[NT, NT + kIter) = the iteration's frames.
+template <int TPF>
+LG_HD float tp_window(const float* win) {
+  constexpr int NT = TpTraits<TPF>::kTaps;
+  float m = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kIter; ++i) m = fmaxf(m, tp_frame<TPF>(win, NT + i));
+  return m;
+}
+
+// Everything one lane carries through its chunk.
 template <int TPF>
 struct LaneCtx {
   static constexpr int NT = TpTraits<TPF>::kTaps;
-  static constexpr int WIN = NT + kIter;
-  KState st[2];
-  float win[2][WIN > 0 ? WIN : 1];   // [0, NT) history, [NT, WIN) this iteration
-  float sp[2], tp[2];                // raw-unit sample / true peak
-  float xa[2], xb[2];
-  double e0[2];
-  float pd[2], pw[2], qd[2], qw[2];  // state snapshots
-  int f_lo, f_hi, f_tp;              // energy range, true-peak limit (lane-local)
+  KState st;
+  float hist[NT > 0 ? NT : 1];   // the NT frames before the current iteration
+  float mprev;                   // max |x| over the previous iteration
+  float sp, tp;                  // raw-unit sample / true peak
+  float xa, xb;
+  double e0;
+  float pd, pw, qd, qw;          // state snapshots
+  int f_lo, f_hi, f_tp;          // energy range, true-peak limit (lane-local)
 };
 
 template <int TPF>
 LG_HD void lane_init(LaneCtx<TPF>& c, int W, int L, const LaneGeom& g) {
+  c.st.d1 = c.st.w1 = c.st.w2 = c.st.v1 = c.st.v2 = 0.0f;
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    c.st[h].d1 = c.st[h].w1 = c.st[h].w2 = c.st[h].v1 = c.st[h].v2 = 0.0f;
-#pragma unroll
-    for (int i = 0; i < LaneCtx<TPF>::WIN; ++i) c.win[h][i] = 0.0f;
-    c.sp[h] = c.tp[h] = c.xa[h] = c.xb[h] = 0.0f;
-    c.e0[h] = 0.0;
-    c.pd[h] = c.pw[h] = c.qd[h] = c.qw[h] = 0.0f;
-  }
+  for (int i = 0; i < (LaneCtx<TPF>::NT > 0 ? LaneCtx<TPF>::NT : 1); ++i) c.hist[i] = 0.0f;
+  c.mprev = 0.0f;
+  c.sp = c.tp = c.xa = c.xb = 0.0f;
+  c.e0 = 0.0;
+  c.pd = c.pw = c.qd = c.qw = 0.0f;
   c.f_lo = W + g.o;
   c.f_hi = c.f_lo + L;
   c.f_tp = c.f_lo + g.l_valid;
 }
 
+// hist <- last NT frames of (hist, x)
 template <int TPF>
-LG_HD void win_push(LaneCtx<TPF>& c, int h, const float* x) {
+LG_HD void hist_advance(LaneCtx<TPF>& c, const float* x) {
   constexpr int NT = LaneCtx<TPF>::NT;
+  if (NT > kIter) {
+#pragma unroll
+    for (int i = 0; i < NT - kIter; ++i) c.hist[i] = c.hist[i + kIter];
+  }
   if (NT > 0) {
 #pragma unroll
-    for (int i = 0; i < kIter; ++i) c.win[h][NT + i] = x[i];
+    for (int i = 0; i < kIter; ++i) c.hist[NT - kIter + i] = x[i];
   }
 }
 
-template <int TPF>
-LG_HD void win_slide(LaneCtx<TPF>& c, int h) {
-  constexpr int NT = LaneCtx<TPF>::NT;
-  if (NT > 0) {
+LG_HD float max_abs12(const float* x) {
+  float m = 0.0f;
 #pragma unroll
-    for (int i = 0; i < NT; ++i) c.win[h][i] = c.win[h][i + kIter];
-  }
+  for (int i = 0; i < kIter; i += 2) m = fmaxf(m, fmaxf(fabsf(x[i]), fabsf(x[i + 1])));
+  return m;
 }
 
 // Warm-up iteration: filter state and true-peak history only.
-template <int TPF, int NCH>
-LG_HD void iter_warm(LaneCtx<TPF>& c, const KCoef& k, const float x[2][kIter]) {
+template <int TPF>
+LG_HD void iter_warm(LaneCtx<TPF>& c, const KCoef& k, const float* x) {
 #pragma unroll
-  for (int h = 0; h < NCH; ++h) {
-#pragma unroll
-    for (int i = 0; i < kIter; ++i) (void) k_step(c.st[h], x[h][i], k);
-    win_push(c, h, x[h]);
-    win_slide(c, h);
-    // state before the first chunk frame of a lane with offset 0; lanes with
-    // a larger offset overwrite it in their first masked iteration
-    c.pd[h] = c.st[h].d1; c.pw[h] = c.st[h].w2;
-  }
+  for (int i = 0; i < kIter; ++i) (void) k_step(c.st, x[i], k);
+  hist_advance(c, x);
+  c.mprev = max_abs12(x);
+  // state before the first chunk frame of a lane with offset 0; lanes with a
+  // larger offset overwrite it in their first masked iteration
+  c.pd = c.st.d1; c.pw = c.st.w2;
 }
 
-// Fast iteration: all kIter frames lie inside every lane's chunk.
-// ab = alpha/beta of frames f0.. as float2 pairs.
-template <int TPF, int NCH>
-LG_HD void iter_fast(LaneCtx<TPF>& c, const KCoef& k, const float x[2][kIter],
-                     const float* ab, int f0) {
-  constexpr int NT = LaneCtx<TPF>::NT;
+// Filter + energy part of a fast iteration (all kIter frames lie inside the
+// lane's chunk).  ab = alpha/beta of frames f0.. as float2 pairs.  Returns
+// max |x| of the iteration; the caller owns the true-peak part.
+template <int TPF>
+LG_HD float iter_fast_energy(LaneCtx<TPF>& c, const KCoef& k, const float* x, const float* ab,
+                             int f0) {
+  float e = 0.0f, sa = 0.0f, sb = 0.0f;
 #pragma unroll
-  for (int h = 0; h < NCH; ++h) {
-    float e = 0.0f, sa = 0.0f, sb = 0.0f;
+  for (int i = 0; i < kIter; ++i) {
+    const float y = k_step(c.st, x[i], k);
+    e = fmaf(y, y, e);
+    sa = fmaf(y, ab[2 * i], sa);
+    sb = fmaf(y, ab[2 * i + 1], sb);
+  }
+  c.e0 += (double) e;
+  c.xa += sa;
+  c.xb += sb;
+  if (f0 + kIter == c.f_hi) { c.qd = c.st.d1; c.qw = c.st.w2; }
+  const float m = max_abs12(x);
+  c.sp = fmaxf(c.sp, m);
+  return m;
+}
+
+// Filter + energy part of a masked iteration: frames are tested one by one
+// against the lane's energy range; takes the state snapshots.  Does NOT touch
+// the peaks.
+template <int TPF>
+LG_HD void iter_masked_energy(LaneCtx<TPF>& c, const KCoef& k, const float* x, const float* ab,
+                              int f0) {
+  float e = 0.0f, sa = 0.0f, sb = 0.0f;
 #pragma unroll
-    for (int i = 0; i < kIter; ++i) {
-      const float y = k_step(c.st[h], x[h][i], k);
+  for (int i = 0; i < kIter; ++i) {
+    const int f = f0 + i;
+    if (f == c.f_lo) { c.pd = c.st.d1; c.pw = c.st.w2; }
+    const float y = k_step(c.st, x[i], k);
+    if (f >= c.f_lo && f < c.f_hi) {
       e = fmaf(y, y, e);
       sa = fmaf(y, ab[2 * i], sa);
       sb = fmaf(y, ab[2 * i + 1], sb);
-      c.sp[h] = fmaxf(c.sp[h], fabsf(x[h][i]));
     }
-    c.e0[h] += (double) e;
-    c.xa[h] += sa;
-    c.xb[h] += sb;
-    if (NT > 0) {
-      win_push(c, h, x[h]);
+    if (f + 1 == c.f_hi) { c.qd = c.st.d1; c.qw = c.st.w2; }
+  }
+  c.e0 += (double) e;
+  c.xa += sa;
+  c.xb += sb;
+}
+
+// Peaks of an iteration, frame by frame, limited to the lane's own chunk
+// frames that exist in the track: [f_lo, f_tp).  Exhaustive form.
+template <int TPF>
+LG_HD void iter_peaks_masked(LaneCtx<TPF>& c, const float* x, int f0) {
+  constexpr int NT = LaneCtx<TPF>::NT;
+  float win[NT + kIter];
 #pragma unroll
-      for (int i = 0; i < kIter; ++i) c.tp[h] = fmaxf(c.tp[h], tp_frame<TPF>(c.win[h], NT + i));
-      win_slide(c, h);
+  for (int i = 0; i < NT; ++i) win[i] = c.hist[i];
+#pragma unroll
+  for (int i = 0; i < kIter; ++i) win[NT + i] = x[i];
+#pragma unroll
+  for (int i = 0; i < kIter; ++i) {
+    const int f = f0 + i;
+    if (f >= c.f_lo && f < c.f_tp) {
+      c.sp = fmaxf(c.sp, fabsf(x[i]));
+      if (NT > 0) c.tp = fmaxf(c.tp, tp_frame<TPF>(win, NT + i));
     }
-    if (f0 + kIter == c.f_hi) { c.qd[h] = c.st[h].d1; c.qw[h] = c.st[h].w2; }
   }
 }
 
-// Masked iteration: frames are tested one by one against the lane's ranges;
-// also takes the state snapshots at the chunk's first and last frame.
-template <int TPF, int NCH>
-LG_HD void iter_masked(LaneCtx<TPF>& c, const KCoef& k, const float x[2][kIter],
-                       const float* ab, int f0) {
+// Peaks of an iteration whose frames all exist in the track.  Exhaustive form
+// (host emulation; the device defers this to the candidate queue).  Frames
+// outside [f_lo, f_hi) belong to a neighbouring chunk of the same channel, so
+// including them cannot change the channel's maximum.
+template <int TPF>
+LG_HD void iter_peaks_all(LaneCtx<TPF>& c, const float* x) {
   constexpr int NT = LaneCtx<TPF>::NT;
+  c.sp = fmaxf(c.sp, max_abs12(x));
+  if (NT > 0) {
+    float win[NT + kIter];
 #pragma unroll
-  for (int h = 0; h < NCH; ++h) {
-    float e = 0.0f, sa = 0.0f, sb = 0.0f;
-    win_push(c, h, x[h]);
+    for (int i = 0; i < NT; ++i) win[i] = c.hist[i];
 #pragma unroll
-    for (int i = 0; i < kIter; ++i) {
-      const int f = f0 + i;
-      if (f == c.f_lo) { c.pd[h] = c.st[h].d1; c.pw[h] = c.st[h].w2; }
-      const float y = k_step(c.st[h], x[h][i], k);
-      if (f >= c.f_lo && f < c.f_hi) {
-        e = fmaf(y, y, e);
-        sa = fmaf(y, ab[2 * i], sa);
-        sb = fmaf(y, ab[2 * i + 1], sb);
-      }
-      if (f + 1 == c.f_hi) { c.qd[h] = c.st[h].d1; c.qw[h] = c.st[h].w2; }
-      if (f >= c.f_lo && f < c.f_tp) {
-        c.sp[h] = fmaxf(c.sp[h], fabsf(x[h][i]));
-        if (NT > 0) c.tp[h] = fmaxf(c.tp[h], tp_frame<TPF>(c.win[h], NT + i));
-      }
-    }
-    c.e0[h] += (double) e;
-    c.xa[h] += sa;
-    c.xb[h] += sb;
-    win_slide(c, h);
+    for (int i = 0; i < kIter; ++i) win[NT + i] = x[i];
+    c.tp = fmaxf(c.tp, tp_window<TPF>(win));
   }
 }
 
 // ----- host-side sample access (tests/emu) ----------------------------------
-// Raw samples of lane-local frames [f0, f0 + kIter) of a channel pair; frames
+// Raw samples of lane-local frames [f0, f0 + kIter) of one channel; frames
 // outside the track read as zero, exactly what the device's zero-filling
 // cp.async stages.
 template <int FMT>
 inline void host_load_iter(const void* pcm, long long frames, int channels, long long a, int f0,
-                           int ch0, int nch, float x[2][kIter]) {
+                           int ch, float* x) {
   for (int i = 0; i < kIter; ++i) {
     const long long t = a + f0 + i;
-    x[0][i] = 0.0f; x[1][i] = 0.0f;
+    x[i] = 0.0f;
     if (t < 0 || t >= frames) continue;
-    for (int h = 0; h < nch; ++h) {
-      if (FMT == FMT_S16) x[h][i] = (float) ((const short*) pcm)[t * channels + ch0 + h];
-      else x[h][i] = ((const float*) pcm)[t * channels + ch0 + h];
-    }
+    if (FMT == FMT_S16) x[i] = (float) ((const short*) pcm)[t * channels + ch];
+    else x[i] = ((const float*) pcm)[t * channels + ch];
   }
 }
 

@@ -29,39 +29,44 @@ static void run_group(const Plan& p, const SweepGroup& g, std::vector<ChunkRec>&
     const CoefSet& cs = p.coefs[tr.coef];
     const KCoef k = load_kcoef(cs);
     const float* basis = p.basis.data() + 2 * cs.basis_off;
-    const uint32_t C = tr.channels, ppc = (C + 1) / 2, cpw = 32 / ppc;
+    const uint32_t C = tr.channels, lpc = C < 32 ? C : 32, cpw = 32 / lpc;
+    const LaneGeom glast = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq,
+                                         ww.first_chunk + cpw - 1);
+    const long long tp_safe = (long long) tr.frames - glast.a;
     for (uint32_t lane = 0; lane < 32; ++lane) {
-      const uint32_t slot = lane / ppc, pair = lane - slot * ppc, chunk = ww.first_chunk + slot;
-      if (!(slot < cpw && chunk < tr.nchunks)) continue;
-      const int ch0 = (int) pair * 2, nch = (ch0 + 1 < (int) C) ? 2 : 1;
+      const uint32_t slot = lane / lpc, chl = lane - slot * lpc, ch = ww.ch_base + chl;
+      const uint32_t chunk = ww.first_chunk + slot;
+      if (!(slot < cpw && ch < C && chunk < tr.nchunks)) continue;
       const LaneGeom geo = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, chunk);
       LaneCtx<TPF> c;
       lane_init(c, cs.W, cs.L, geo);
       for (uint32_t it = 0; it < tr.niters; ++it) {
         const int f0 = (int) it * kIter;
-        float x[2][kIter];
-        host_load_iter<FMT>(tr.pcm, (long long) tr.frames, (int) C, geo.a, f0, ch0, nch, x);
+        float x[kIter];
+        host_load_iter<FMT>(tr.pcm, (long long) tr.frames, (int) C, geo.a, f0, (int) ch, x);
         const int kind = iter_kind(f0, cs.W, (int) tr.aq, cs.L, ww.lmin_valid);
         const float* ab = basis + 2 * f0;
-        if (C == 1) {
-          if (kind == ITER_WARM) iter_warm<TPF, 1>(c, k, x);
-          else if (kind == ITER_FAST) iter_fast<TPF, 1>(c, k, x, ab, f0);
-          else iter_masked<TPF, 1>(c, k, x, ab, f0);
-        } else {
-          if (kind == ITER_WARM) iter_warm<TPF, 2>(c, k, x);
-          else if (kind == ITER_FAST) iter_fast<TPF, 2>(c, k, x, ab, f0);
-          else iter_masked<TPF, 2>(c, k, x, ab, f0);
+        if (kind == ITER_WARM) {
+          iter_warm<TPF>(c, k, x);
+          continue;
         }
+        if (kind == ITER_FAST) {
+          (void) iter_fast_energy<TPF>(c, k, x, ab, f0);
+          iter_peaks_all<TPF>(c, x);        // the device defers this to its candidate queue
+        } else {
+          iter_masked_energy<TPF>(c, k, x, ab, f0);
+          if ((long long) f0 + kIter <= tp_safe) iter_peaks_all<TPF>(c, x);
+          else iter_peaks_masked<TPF>(c, x, f0);
+        }
+        hist_advance(c, x);
       }
-      for (int h = 0; h < nch; ++h) {
-        ChunkRec& r = recs[tr.rec_base + (uint64_t) chunk * C + ch0 + h];
-        r.e0 = c.e0[h]; r.xa = c.xa[h]; r.xb = c.xb[h];
-        r.pd = c.pd[h]; r.pw = c.pw[h]; r.qd = c.qd[h]; r.qw = c.qw[h];
-        float& sp = peaks[2 * (tr.peak_base + ch0 + h)];
-        float& tp = peaks[2 * (tr.peak_base + ch0 + h) + 1];
-        sp = std::max(sp, c.sp[h]);
-        tp = std::max(tp, c.tp[h]);
-      }
+      ChunkRec& r = recs[tr.rec_base + (uint64_t) chunk * C + ch];
+      r.e0 = c.e0; r.xa = c.xa; r.xb = c.xb;
+      r.pd = c.pd; r.pw = c.pw; r.qd = c.qd; r.qw = c.qw;
+      float& sp = peaks[2 * (tr.peak_base + ch)];
+      float& tp = peaks[2 * (tr.peak_base + ch) + 1];
+      sp = std::max(sp, c.sp);
+      tp = std::max(tp, c.tp);
     }
   }
 }
