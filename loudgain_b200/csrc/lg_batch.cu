@@ -71,8 +71,6 @@ struct lgb_batch {
   // device tables
   Track* d_tracks = nullptr;
   CoefSet* d_coefs = nullptr;
-  float* d_basis = nullptr;
-  double* d_gram = nullptr;
   WarpWork* d_work = nullptr;
   Query* d_queries = nullptr;
   uint32_t* d_members = nullptr;
@@ -97,7 +95,7 @@ struct lgb_batch {
 
   DeviceTables tables() const {
     DeviceTables t;
-    t.tracks = d_tracks; t.coefs = d_coefs; t.basis = d_basis; t.gram = d_gram; t.work = d_work;
+    t.tracks = d_tracks; t.coefs = d_coefs; t.work = d_work;
     t.queries = d_queries; t.members = d_members; t.lists = d_lists; t.recs = d_recs; t.peaks = d_peaks;
     t.echunk = d_echunk; t.eslot = d_eslot; t.zblock = d_zblock; t.zst = d_zst;
     t.results = d_results;
@@ -131,7 +129,6 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
   const Plan& p = b->plan;
   b->abs_gate = pow(10.0, (-70.0 + 0.691) / 10.0);
   bool ok = upload(p.tracks, &b->d_tracks, b->stream) && upload(p.coefs, &b->d_coefs, b->stream) &&
-            upload(p.basis, &b->d_basis, b->stream) && upload(p.gram, &b->d_gram, b->stream) &&
             upload(p.work, &b->d_work, b->stream) &&
             upload(p.queries, &b->d_queries, b->stream) &&
             upload(p.members, &b->d_members, b->stream) && dalloc(&b->d_recs, p.total_recs) &&
@@ -169,7 +166,9 @@ extern "C" LG_EXPORT int lgb_batch_run(lgb_batch* b) {
   if (e != cudaSuccess) { set_error("cudaMemsetAsync(peaks)", e); return 1; }
   if (b->timing) cudaEventRecord(b->ev0, b->stream);
   for (const SweepGroup& g : p.groups) {
-    e = launch_sweep(t, g.format, g.tpf, g.first_warp, g.nwarps, g.warp_smem, b->stream);
+    SweepParams sp = g.params;
+    sp.tracks = t.tracks; sp.work = t.work + g.first_warp; sp.recs = t.recs; sp.peaks = t.peaks;
+    e = launch_sweep(sp, g.format, g.tpf, g.kmax, b->stream);
     if (e != cudaSuccess) { set_error("launch_sweep", e); return 1; }
   }
   if (b->timing) { cudaEventRecord(b->ev1, b->stream); b->timed_run_pending = true; }
@@ -271,7 +270,7 @@ extern "C" LG_EXPORT int lgb_query_lists(const double* const* z, const uint32_t*
 extern "C" LG_EXPORT void lgb_batch_destroy(lgb_batch* b) {
   if (!b) return;
   if (b->ev0) { cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); }
-  cudaFree(b->d_tracks); cudaFree(b->d_coefs); cudaFree(b->d_basis); cudaFree(b->d_gram); cudaFree(b->d_work);
+  cudaFree(b->d_tracks); cudaFree(b->d_coefs); cudaFree(b->d_work);
   cudaFree(b->d_queries); cudaFree(b->d_members); cudaFree(b->d_lists); cudaFree(b->d_recs); cudaFree(b->d_peaks);
   cudaFree(b->d_echunk); cudaFree(b->d_eslot); cudaFree(b->d_zblock); cudaFree(b->d_zst);
   cudaFree(b->d_results);

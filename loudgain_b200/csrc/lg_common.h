@@ -37,6 +37,8 @@ constexpr int kMaxAlign = 8;
 
 constexpr int kMaxChannels = 64;
 
+struct cplx { double re, im; };
+
 // One K-weighting coefficient set: a (sample rate, chunk length, warm-up,
 // input scale) combination.  Floats feed the sweep, doubles the fix-up.
 struct CoefSet {
@@ -45,21 +47,29 @@ struct CoefSet {
   // (algebraically w[n] = x[n] - a1 w[n-1] - a2 w[n-2], yh = w - 2w1 + w2)
   // followed by the shelf  v = yh - p1 v1 - p2 v2 ; y = v + q1 v1 + q2 v2.
   float c, e2, p1, p2, q1, q2;
+  // lambda = the high-pass pole (Im > 0).  The response of the K-weighted
+  // output to a high-pass start state is, after the warm-up, Re(A lambda^f);
+  // the sweep accumulates Xi = sum y[f] lambda^f with these constants.
+  float lam_re[kIter], lam_im[kIter];   // lambda^i, i = 0..kIter-1
+  float rot_re, rot_im;                 // lambda^-kIter
   int32_t s100;     // frames per 100 ms = (rate+5)/10
   int32_t k;        // chunks per 100 ms slot (k divides s100)
   int32_t L;        // frames per chunk = s100 / k
   int32_t W;        // warm-up frames run before each chunk (multiple of kIter)
   int32_t tpf;      // true-peak oversampling factor: 4, 2 or 0 (none)
   int32_t horner;   // number of previous chunks the state carry looks back
-  int32_t ntab;     // entries in the basis / Gram tables (even)
-  int32_t pad_;
   // --- fix-up, FP64
   double ML[4];                   // M^L, M = one-frame transition of (d1, w2)
   double MinvWo[kMaxAlign][4];    // M^-(W+o), o = lane alignment offset
+  cplx Ad, Aw;                    // A = tau_d * Ad + tau_w * Aw for start state tau
+  cplx xi_scale[4];               // lambda^((niters-1)*kIter) for aq = 1, 2, 4, 8
+  double S1o[kMaxAlign];          // sum over the chunk of |lambda|^(2f), per offset o
+  cplx S2o[kMaxAlign];            // sum over the chunk of lambda^(2f), per offset o
   double gain;      // (shelf b0 / input full scale)^2: raw energy -> K-weighted
-  uint64_t basis_off;   // offset (in float2) of this set's alpha/beta table
-  uint64_t gram_off;    // offset (in triples of doubles) of its prefix Gram table
 };
+
+// Sweep iterations per chunk for a lane alignment quantum aq.
+LG_BOTH int sweep_iters(int W, int L, int aq) { return (W + aq - 1 + L + kIter - 1) / kIter; }
 
 // One audio track resident in HBM as interleaved PCM [frames][channels].
 struct Track {
@@ -89,7 +99,7 @@ struct Track {
 // What the sweep leaves behind for one (chunk, channel).
 struct ChunkRec {
   double e0;        // sum y^2 over the chunk, filter started from zero state
-  float xa, xb;     // sum y*alpha, sum y*beta (cross terms of the correction)
+  float yr, yi;     // sum y[f] lambda^f, scaled by lambda^-(start of last iteration)
   float pd, pw;     // high-pass state (d1, w2) at the chunk's first frame
   float qd, qw;     // ... and after its last frame
 };
@@ -130,6 +140,26 @@ struct WarpWork {
 };
 
 LG_BOTH uint32_t chunks_per_warp(uint32_t channels) { return 32u / (channels < 32u ? channels : 32u); }
+
+// Everything that is uniform over one sweep launch (one format, coefficient
+// set and channel count).  Passed by value as the kernel parameter, so the
+// filter constants reach the FMAs straight from the constant bank.
+struct SweepParams {
+  float c, ne2, np1, np2, q1, q2;
+  float lam_re[kIter], lam_im[kIter];
+  float rot_re, rot_im;
+  float tp_bound;          // ||taps||_1 bound used for true-peak screening
+  int32_t W, L, niters, aq;
+  uint32_t channels, fb;
+  uint32_t lpc;            // lanes per chunk = min(channels, 32)
+  uint32_t cpw;            // chunks per warp
+  uint32_t stage_row_bytes, units, row_stride, stage_bytes, ncopies;
+  uint32_t warp_smem, nwarps;
+  const Track* tracks;
+  const WarpWork* work;
+  ChunkRec* recs;
+  uint32_t* peaks;
+};
 
 // ---- lane geometry ---------------------------------------------------------
 // Chunk j covers track frames [j*L, j*L + L).  Its lane starts filtering from

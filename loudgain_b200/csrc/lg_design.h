@@ -94,12 +94,22 @@ inline int true_peak_factor(unsigned long rate) {
   return rate < 96000 ? 4 : (rate < 192000 ? 2 : 0);
 }
 
-// Fills `cs` for (rate, chunks-per-slot k, input full scale); appends the
-// alpha/beta basis (float2 per lane-local frame) to `basis` and the prefix
-// Gram sums (3 doubles per frame: sum alpha^2, alpha*beta, beta^2 over
-// frames < f) to `gram`.
-inline void make_coefset(unsigned long rate, int k, double full_scale, CoefSet& cs,
-                         std::vector<float>& basis, std::vector<double>& gram) {
+inline cplx c_mul(cplx a, cplx b) { return cplx{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+inline cplx c_div(cplx a, cplx b) {
+  const double d = b.re * b.re + b.im * b.im;
+  return cplx{(a.re * b.re + a.im * b.im) / d, (a.im * b.re - a.re * b.im) / d};
+}
+inline cplx c_add(cplx a, cplx b) { return cplx{a.re + b.re, a.im + b.im}; }
+inline cplx c_sub(cplx a, cplx b) { return cplx{a.re - b.re, a.im - b.im}; }
+inline cplx c_pow(cplx a, long n) {      // integer power, n may be negative
+  if (n < 0) { a = c_div(cplx{1, 0}, a); n = -n; }
+  cplx r{1, 0};
+  while (n) { if (n & 1) r = c_mul(r, a); a = c_mul(a, a); n >>= 1; }
+  return r;
+}
+
+// Fills `cs` for (rate, chunks-per-slot k, input full scale).
+inline void make_coefset(unsigned long rate, int k, double full_scale, CoefSet& cs) {
   const KDesign d = k_design(rate);
   cs = CoefSet();
   cs.s100 = (int32_t) ((rate + 5) / 10);
@@ -111,8 +121,9 @@ inline void make_coefset(unsigned long rate, int k, double full_scale, CoefSet& 
   cs.e2 = (float) d.e2;
   cs.p1 = (float) d.sa[1];
   cs.p2 = (float) d.sa[2];
-  cs.q1 = (float) (d.sb[1] / d.sb[0]);
-  cs.q2 = (float) (d.sb[2] / d.sb[0]);
+  const double q1 = d.sb[1] / d.sb[0], q2 = d.sb[2] / d.sb[0];
+  cs.q1 = (float) q1;
+  cs.q2 = (float) q2;
   cs.gain = (d.sb[0] / full_scale) * (d.sb[0] / full_scale);
   const double M[4] = {d.c, -d.e2, 1.0, 1.0};   // (d1, w2) -> one frame later
   mat2_pow(M, (unsigned long) cs.L, cs.ML);
@@ -125,39 +136,52 @@ inline void make_coefset(unsigned long rate, int k, double full_scale, CoefSet& 
     int h = (int) std::ceil(std::log(1e-18) / ((double) cs.L * std::log(d.hp_pole_radius))) + 1;
     cs.horner = h < 2 ? 2 : h;
   }
-  // Basis: K-weighted output at lane-local frame f for zero input and
-  // high-pass start state (d1, w2) = (1, 0) -> alpha, (0, 1) -> beta; the
-  // shelf starts at rest.  Long enough for any lane offset plus one stage.
-  int n = cs.W + cs.L + kMaxAlign + kStageFrames;
-  n += n & 1;
-  cs.ntab = n;
-  cs.basis_off = basis.size() / 2;
-  basis.resize(basis.size() + 2 * (size_t) n);
-  float* tab = basis.data() + 2 * cs.basis_off;
-  const double q1 = d.sb[1] / d.sb[0], q2 = d.sb[2] / d.sb[0];
-  for (int which = 0; which < 2; ++which) {
-    double d1 = which == 0 ? 1.0 : 0.0, w2 = which == 0 ? 0.0 : 1.0;
-    double w1 = w2 + d1, v1 = 0, v2 = 0;
-    for (int f = 0; f < n; ++f) {
-      const double dn = d.c * d1 - d.e2 * w2;
-      const double wn = w1 + dn;
-      const double yh = dn - d1;
-      const double v = yh - d.sa[1] * v1 - d.sa[2] * v2;
-      const double y = v + q1 * v1 + q2 * v2;
-      tab[2 * f + which] = (float) y;
-      w2 = w1; w1 = wn; d1 = dn; v2 = v1; v1 = v;
-    }
+  // lambda: eigenvalue of M with Im > 0 (the high-pass poles are complex for
+  // every supported rate: Q = 0.5003 > 0.5).
+  const double tr = 1.0 + d.c, dt = d.c + d.e2, disc = tr * tr - 4.0 * dt;
+  const cplx lam = disc < 0 ? cplx{tr / 2.0, std::sqrt(-disc) / 2.0}
+                            : cplx{(tr + std::sqrt(disc)) / 2.0, 0.0};
+  for (int i = 0; i < kIter; ++i) {
+    const cplx p = c_pow(lam, i);
+    cs.lam_re[i] = (float) p.re;
+    cs.lam_im[i] = (float) p.im;
   }
-  // Prefix Gram sums of the float-rounded table the sweep multiplies by.
-  cs.gram_off = gram.size() / 3;
-  gram.resize(gram.size() + 3 * (size_t) (n + 1));
-  double* pg = gram.data() + 3 * cs.gram_off;
-  pg[0] = pg[1] = pg[2] = 0.0;
-  for (int f = 0; f < n; ++f) {
-    const double a = tab[2 * f], b = tab[2 * f + 1];
-    pg[3 * (f + 1) + 0] = pg[3 * f + 0] + a * a;
-    pg[3 * (f + 1) + 1] = pg[3 * f + 1] + a * b;
-    pg[3 * (f + 1) + 2] = pg[3 * f + 2] + b * b;
+  {
+    const cplx r = c_pow(lam, -kIter);
+    cs.rot_re = (float) r.re;
+    cs.rot_im = (float) r.im;
+  }
+  // Response of the K-weighted output to a start state tau = (d1, w2) at
+  // lane-local frame 0, once the shelf has settled: Re(A lambda^f) with
+  //   tau = a v + conj(a v),  v = (lambda - 1, 1),
+  //   A = 2 a (lambda - 1)^2 Hs(lambda),  Hs = shelf transfer function.
+  {
+    const cplx one{1, 0};
+    const cplx lm1 = c_sub(lam, one);
+    const cplx il = c_div(one, lam), il2 = c_mul(il, il);
+    const cplx num = c_add(one, c_add(c_mul(cplx{q1, 0}, il), c_mul(cplx{q2, 0}, il2)));
+    const cplx den = c_add(one, c_add(c_mul(cplx{d.sa[1], 0}, il), c_mul(cplx{d.sa[2], 0}, il2)));
+    const cplx g = c_mul(c_mul(cplx{2, 0}, c_mul(lm1, lm1)), c_div(num, den));
+    // a = p + iq with p = tau_w / 2, q = (tau_w x - tau_d) / (2 y), lambda - 1 = x + iy
+    const double x = lm1.re, y = lm1.im;
+    const cplx a_d{0.0, -1.0 / (2.0 * y)};          // d a / d tau_d
+    const cplx a_w{0.5, x / (2.0 * y)};             // d a / d tau_w
+    cs.Ad = c_mul(g, a_d);
+    cs.Aw = c_mul(g, a_w);
+  }
+  for (int j = 0; j < 4; ++j) {
+    const int aq = 1 << j;
+    cs.xi_scale[j] = c_pow(lam, (long) (sweep_iters(cs.W, cs.L, aq) - 1) * kIter);
+  }
+  {
+    const double r2 = lam.re * lam.re + lam.im * lam.im;
+    const cplx l2 = c_mul(lam, lam);
+    for (int o = 0; o < kMaxAlign; ++o) {
+      const long f0 = cs.W + o;
+      cs.S1o[o] = std::pow(r2, (double) f0) * (1.0 - std::pow(r2, (double) cs.L)) / (1.0 - r2);
+      const cplx top = c_mul(c_pow(l2, f0), c_sub(cplx{1, 0}, c_pow(l2, cs.L)));
+      cs.S2o[o] = c_div(top, c_sub(cplx{1, 0}, l2));
+    }
   }
 }
 

@@ -83,15 +83,13 @@ __device__ __forceinline__ void smem_load_iter(const unsigned char* rowp, uint32
 }
 
 #ifndef LG_SWEEP_MINBLOCKS
-#define LG_SWEEP_MINBLOCKS 3
+#define LG_SWEEP_MINBLOCKS 4
 #endif
-
-template <int FMT> struct CopyTraits { static constexpr int kMax = FMT == FMT_S16 ? 6 : 12; };
 
 constexpr uint32_t kQueue = 64;     // candidate windows a warp can hold
 
 template <int TPF>
-__device__ __forceinline__ constexpr uint32_t queue_entry_bytes() {
+__host__ __device__ constexpr uint32_t queue_entry_bytes() {
   // window floats + one meta word, rounded up to an odd number of 16-byte units
   return ((((TpTraits<TPF>::kTaps + kIter) * 4u + 4u + 15u) >> 4) | 1u) << 4;
 }
@@ -118,67 +116,96 @@ __device__ __forceinline__ void flush_round(const unsigned char* queue, uint32_t
   __syncwarp();
 }
 
-template <int FMT, int TPF>
+// Peaks of a track-end iteration, frame by frame.  Rare (last warp of a
+// track), so it is kept out of line to keep the hot loop small; everything
+// goes in and out by value so that the lane state stays in registers.
+template <int TPF>
+struct SlowPeakArgs {
+  float win[TpTraits<TPF>::kTaps + kIter];
+  int f0, f_lo, f_tp;
+  float sp, tp;
+};
+
+template <int TPF>
+__device__ __noinline__ float2 peaks_masked_slow(const SlowPeakArgs<TPF> a) {
+  constexpr int NT = TpTraits<TPF>::kTaps;
+  float sp = a.sp, tp = a.tp;
+#pragma unroll 1
+  for (int i = 0; i < kIter; ++i) {
+    const int f = a.f0 + i;
+    if (f >= a.f_lo && f < a.f_tp) {
+      sp = fmaxf(sp, fabsf(a.win[NT + i]));
+      if (NT > 0) {
+        // same arithmetic as tp_frame, with a run-time window position
+        float m = 0.0f;
+        if (TPF == 4) {
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int t = 0; t < 12; ++t) acc = fmaf(a.win[NT + i - t], kTp4f[p][t], acc);
+            m = fmaxf(m, fabsf(acc));
+          }
+        } else {
+          float acc = 0.0f;
+#pragma unroll
+          for (int t = 0; t < 24; ++t) acc = fmaf(a.win[NT + i - t], kTp2f[0][t], acc);
+          m = fabsf(acc);
+        }
+        tp = fmaxf(tp, m);
+      }
+    }
+  }
+  return make_float2(sp, tp);
+}
+
+template <int FMT, int TPF, int KMAX>
 __global__ void __launch_bounds__(kSweepThreads, LG_SWEEP_MINBLOCKS)
-sweep_kernel(const Track* __restrict__ tracks, const CoefSet* __restrict__ coefs,
-             const float* __restrict__ basis, const WarpWork* __restrict__ work,
-             uint32_t nwarps, uint32_t warp_smem, ChunkRec* __restrict__ recs,
-             uint32_t* peaks) {
+sweep_kernel(const __grid_constant__ SweepParams P) {
   constexpr int NT = TpTraits<TPF>::kTaps;
   extern __shared__ __align__(16) unsigned char smem_all[];
   const uint32_t wic = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + wic;
-  if (warp >= nwarps) return;                  // whole warps leave; no CTA barrier below
-  unsigned char* sm = smem_all + wic * warp_smem;
+  if (warp >= P.nwarps) return;                // whole warps leave; no CTA barrier below
+  unsigned char* sm = smem_all + wic * P.warp_smem;
   const uint32_t sm_addr = (uint32_t) __cvta_generic_to_shared(sm);
 
-  const WarpWork ww = work[warp];
-  const Track& tr = tracks[ww.track];
-  const CoefSet& cs = coefs[tr.coef];
-  const KCoef kc = load_kcoef(cs);
-  const int W = cs.W, L = cs.L;
-  const uint32_t C = tr.channels, fb = tr.fb, aq = tr.aq, niters = tr.niters;
+  const WarpWork ww = P.work[warp];
+  const Track& tr = P.tracks[ww.track];
+  const int W = P.W, L = P.L;
+  const uint32_t C = P.channels, fb = P.fb;
   const long long frames = (long long) tr.frames;
   const unsigned char* pcm = reinterpret_cast<const unsigned char*>(tr.pcm);
-  const float* ab_tab = basis + 2 * cs.basis_off;
 
-  const uint32_t lpc = C < 32u ? C : 32u;      // lanes per chunk
-  const uint32_t cpw = 32u / lpc;              // chunks per warp
-  const uint32_t slot = lane / lpc;
-  const uint32_t chl = lane - slot * lpc;      // channel within the warp's group
+  const uint32_t slot = lane / P.lpc;
+  const uint32_t chl = lane - slot * P.lpc;    // channel within the warp's group
   const uint32_t ch = ww.ch_base + chl;
   const uint32_t chunk = ww.first_chunk + slot;
-  const bool compute = slot < cpw && ch < C;
+  const bool compute = slot < P.cpw && ch < C;
   const bool active = compute && chunk < tr.nchunks;
   const bool stereo = C == 2;
 
-  // ---- staging geometry
-  const uint32_t stage_row_bytes = kStageFrames * fb;          // multiple of 16
-  const uint32_t units = stage_row_bytes >> 4;
-  const uint32_t row_stride = (units | 1u) << 4;               // odd unit count: no bank conflicts
-  const uint32_t stage_bytes = cpw * row_stride;
-  const uint32_t ncopies = cpw * units;
-  const LaneGeom g0 = lane_geometry(frames, L, W, (int) aq, ww.first_chunk);
+  // ---- staging: copy k of this lane moves unit (idx % units) of row (idx / units)
+  const LaneGeom g0 = lane_geometry(frames, L, W, P.aq, ww.first_chunk);
   const long long warp_byte0 = g0.a * (long long) fb;          // may be negative
   const long long track_bytes = frames * (long long) fb;
-  constexpr int KMAX = CopyTraits<FMT>::kMax;
-  int32_t soff[KMAX];      // source byte offset of copy k at stage 0, relative to warp_byte0
+  int32_t soff[KMAX];      // source byte offset at stage 0, relative to warp_byte0
   uint32_t doff[KMAX];     // destination byte offset inside a stage buffer
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
     const uint32_t idx = lane + 32u * k;
-    const uint32_t row = idx / units;
-    const uint32_t unit = idx - row * units;
-    const LaneGeom gr = lane_geometry(frames, L, W, (int) aq, ww.first_chunk + row);
+    const uint32_t row = idx / P.units;
+    const uint32_t unit = idx - row * P.units;
+    const LaneGeom gr = lane_geometry(frames, L, W, P.aq, ww.first_chunk + row);
     soff[k] = (int32_t) ((gr.a - g0.a) * (long long) fb) + (int32_t) (unit << 4);
-    doff[k] = idx < ncopies ? row * row_stride + (unit << 4) : 0xffffffffu;
+    doff[k] = idx < P.ncopies ? row * P.row_stride + (unit << 4) : 0xffffffffu;
   }
   const bool interior = ww.interior != 0;
 
   auto prefetch = [&](uint32_t stage) {
-    const uint32_t dst0 = sm_addr + (stage % kRing) * stage_bytes;
-    const long long adv = (long long) stage * stage_row_bytes;
+    const uint32_t dst0 = sm_addr + (stage % kRing) * P.stage_bytes;
+    const long long adv = (long long) stage * P.stage_row_bytes;
     if (interior) {
 #pragma unroll
       for (int k = 0; k < KMAX; ++k)
@@ -197,28 +224,28 @@ sweep_kernel(const Track* __restrict__ tracks, const CoefSet* __restrict__ coefs
 
   // ---- candidate queue and per-channel true-peak cells of this warp
   constexpr uint32_t EB = queue_entry_bytes<TPF>();
-  unsigned char* queue = sm + kRing * stage_bytes;
+  unsigned char* queue = sm + kRing * P.stage_bytes;
   uint32_t* tpq = reinterpret_cast<uint32_t*>(queue + (NT > 0 ? kQueue * EB : 0));
   tpq[lane] = 0u;
   uint32_t q_head = 0, q_tail = 0;
   // Frames at or beyond this lane-local index may lie past the end of the
   // track for some lane of the warp: true peak is then masked frame by frame.
-  const LaneGeom glast = lane_geometry(frames, L, W, (int) aq, ww.first_chunk + cpw - 1);
+  const LaneGeom glast = lane_geometry(frames, L, W, P.aq, ww.first_chunk + P.cpw - 1);
   const long long tp_safe_ll = frames - glast.a;
   const int tp_safe = tp_safe_ll > 0x3fffffff ? 0x3fffffff : (int) tp_safe_ll;
 
   // ---- lane state
-  const LaneGeom geo = lane_geometry(frames, L, W, (int) aq, chunk);
+  const LaneGeom geo = lane_geometry(frames, L, W, P.aq, chunk);
   LaneCtx<TPF> c;
   lane_init(c, W, L, geo);
-  const unsigned char* my_row = sm + slot * row_stride;
-  uint32_t* my_peak = peaks + 2 * (tr.peak_base + (compute ? ch : 0u));
+  const unsigned char* my_row = sm + slot * P.row_stride;
+  uint32_t* my_peak = P.peaks + 2 * (tr.peak_base + (compute ? ch : 0u));
   const unsigned peers = __match_any_sync(0xffffffffu, compute ? chl : 0xffffu);
   const bool leader = compute && lane == (uint32_t) (__ffs(peers) - 1);
   float thr = 0.0f;        // the channel's peak is known to reach at least this (raw units)
   float published = 0.0f;
-  const float gain = tp_gain_bound<TPF>();
 
+  const uint32_t niters = (uint32_t) P.niters;
   const uint32_t nstages = (niters + kItersPerStage - 1) / kItersPerStage;
   prefetch(0);
   cp_async_commit();
@@ -233,40 +260,42 @@ sweep_kernel(const Track* __restrict__ tracks, const CoefSet* __restrict__ coefs
     // what other warps have published for this channel so far
     uint2 seen = make_uint2(0u, 0u);
     if (NT > 0 && compute) seen = __ldcg(reinterpret_cast<const uint2*>(my_peak));
-    const unsigned char* buf = my_row + (s % kRing) * stage_bytes;
+    const unsigned char* buf = my_row + (s % kRing) * P.stage_bytes;
 #pragma unroll 1
     for (int it = 0; it < kItersPerStage; ++it) {
       const uint32_t iter = s * kItersPerStage + it;
       if (iter >= niters) break;
       const int f0 = (int) iter * kIter;
-      const int kind = iter_kind(f0, W, (int) aq, L, ww.lmin_valid);
+      const int kind = iter_kind(f0, W, P.aq, L, ww.lmin_valid);
       float x[kIter];
       bool cand = false;
       if (compute) {
         smem_load_iter<FMT>(buf + it * kIter * fb, fb, stereo, ch, x);
         if (kind == ITER_WARM) {
-          iter_warm<TPF>(c, kc, x);
+          iter_warm<TPF>(c, P, x);
         } else {
-          float ab[2 * kIter];
-          const float4* abp = reinterpret_cast<const float4*>(ab_tab + 2 * f0);
-#pragma unroll
-          for (int i = 0; i < kIter / 2; ++i) {
-            const float4 v = __ldg(abp + i);
-            ab[4 * i] = v.x; ab[4 * i + 1] = v.y; ab[4 * i + 2] = v.z; ab[4 * i + 3] = v.w;
-          }
           float m;
           bool safe = true;
           if (kind == ITER_FAST) {
-            m = iter_fast_energy<TPF>(c, kc, x, ab, f0);
+            m = iter_fast_energy<TPF>(c, P, x, f0);
           } else {
-            iter_masked_energy<TPF>(c, kc, x, ab, f0);
+            iter_masked_energy<TPF>(c, P, x, f0);
             m = max_abs12(x);
             safe = f0 + kIter <= tp_safe;
             if (safe) c.sp = fmaxf(c.sp, m);
-            else iter_peaks_masked<TPF>(c, x, f0);      // track end: frame by frame
+            else {                                       // track end: frame by frame
+              SlowPeakArgs<TPF> a;
+#pragma unroll
+              for (int i = 0; i < NT; ++i) a.win[i] = c.hist[i];
+#pragma unroll
+              for (int i = 0; i < kIter; ++i) a.win[NT + i] = x[i];
+              a.f0 = f0; a.f_lo = c.f_lo; a.f_tp = c.f_tp; a.sp = c.sp; a.tp = c.tp;
+              const float2 r = peaks_masked_slow<TPF>(a);
+              c.sp = r.x; c.tp = r.y;
+            }
           }
           if (NT > 0) {
-            cand = safe && gain * fmaxf(c.mprev, m) > fmaxf(thr, c.sp);
+            cand = safe && P.tp_bound * fmaxf(c.mprev, m) > fmaxf(thr, c.sp);
             c.mprev = m;
           }
         }
@@ -297,10 +326,10 @@ sweep_kernel(const Track* __restrict__ tracks, const CoefSet* __restrict__ coefs
     }
     if (NT > 0 && compute) {
       // raise the bound with what other warps know; publish what this warp knows
-      thr = fmaxf(thr, __uint_as_float(seen.x > seen.y ? seen.x : seen.y));
+      const float theirs = __uint_as_float(seen.x > seen.y ? seen.x : seen.y);
       const float mine = fmaxf(fmaxf(c.sp, c.tp), __uint_as_float(tpq[chl]));
-      if (mine > thr) thr = mine;
-      if (mine > published && mine > __uint_as_float(seen.x > seen.y ? seen.x : seen.y)) {
+      thr = fmaxf(thr, fmaxf(theirs, mine));
+      if (mine > published && mine > theirs) {
         // goes into the true-peak cell: the reported true peak is the max of
         // both cells anyway (ebur128_true_peak folds the sample peak in)
         atomicMax(my_peak + 1, __float_as_uint(mine));
@@ -320,9 +349,9 @@ sweep_kernel(const Track* __restrict__ tracks, const CoefSet* __restrict__ coefs
 
   if (active) {
     ChunkRec v;
-    v.e0 = c.e0; v.xa = c.xa; v.xb = c.xb;
+    v.e0 = c.e0; v.yr = c.yr; v.yi = c.yi;
     v.pd = c.pd; v.pw = c.pw; v.qd = c.qd; v.qw = c.qw;
-    recs[tr.rec_base + (uint64_t) chunk * C + ch] = v;
+    P.recs[tr.rec_base + (uint64_t) chunk * C + ch] = v;
   }
   // Peaks: non-negative floats order like their bit patterns.  Reduce over
   // the lanes of the warp that hold the same channel, one atomic each.
@@ -335,35 +364,43 @@ sweep_kernel(const Track* __restrict__ tracks, const CoefSet* __restrict__ coefs
   }
 }
 
-template <int FMT, int TPF>
-static cudaError_t launch_sweep_t(const DeviceTables& t, uint32_t first_warp, uint32_t nwarps,
-                                  uint32_t warp_smem, cudaStream_t stream) {
+template <int FMT, int TPF, int KMAX>
+static cudaError_t launch_sweep_k(const SweepParams& p, cudaStream_t stream) {
   const uint32_t wpb = kSweepThreads / 32;
-  const uint32_t blocks = (nwarps + wpb - 1) / wpb;
-  const size_t smem = (size_t) warp_smem * wpb;
+  const uint32_t blocks = (p.nwarps + wpb - 1) / wpb;
+  const size_t smem = (size_t) p.warp_smem * wpb;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<FMT, TPF>,
+    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<FMT, TPF, KMAX>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(sweep_kernel<FMT, TPF, KMAX>,
+                               cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  sweep_kernel<FMT, TPF><<<blocks, kSweepThreads, smem, stream>>>(
-      t.tracks, t.coefs, t.basis, t.work + first_warp, nwarps, warp_smem, t.recs, t.peaks);
+  sweep_kernel<FMT, TPF, KMAX><<<blocks, kSweepThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
-cudaError_t launch_sweep(const DeviceTables& t, uint32_t format, int tpf, uint32_t first_warp,
-                         uint32_t nwarps, uint32_t warp_smem, cudaStream_t stream) {
-  if (nwarps == 0) return cudaSuccess;
+template <int FMT, int TPF>
+static cudaError_t launch_sweep_t(const SweepParams& p, uint32_t kmax, cudaStream_t stream) {
+  if (kmax <= 3) return launch_sweep_k<FMT, TPF, 3>(p, stream);
+  if (kmax <= 6) return launch_sweep_k<FMT, TPF, 6>(p, stream);
+  return launch_sweep_k<FMT, TPF, 12>(p, stream);
+}
+
+cudaError_t launch_sweep(const SweepParams& p, uint32_t format, int tpf, uint32_t kmax,
+                         cudaStream_t stream) {
+  if (p.nwarps == 0) return cudaSuccess;
   if (format == FMT_S16) {
-    if (tpf == 4) return launch_sweep_t<FMT_S16, 4>(t, first_warp, nwarps, warp_smem, stream);
-    if (tpf == 2) return launch_sweep_t<FMT_S16, 2>(t, first_warp, nwarps, warp_smem, stream);
-    return launch_sweep_t<FMT_S16, 0>(t, first_warp, nwarps, warp_smem, stream);
+    if (tpf == 4) return launch_sweep_t<FMT_S16, 4>(p, kmax, stream);
+    if (tpf == 2) return launch_sweep_t<FMT_S16, 2>(p, kmax, stream);
+    return launch_sweep_t<FMT_S16, 0>(p, kmax, stream);
   }
-  if (tpf == 4) return launch_sweep_t<FMT_F32, 4>(t, first_warp, nwarps, warp_smem, stream);
-  if (tpf == 2) return launch_sweep_t<FMT_F32, 2>(t, first_warp, nwarps, warp_smem, stream);
-  return launch_sweep_t<FMT_F32, 0>(t, first_warp, nwarps, warp_smem, stream);
+  if (tpf == 4) return launch_sweep_t<FMT_F32, 4>(p, kmax, stream);
+  if (tpf == 2) return launch_sweep_t<FMT_F32, 2>(p, kmax, stream);
+  return launch_sweep_t<FMT_F32, 0>(p, kmax, stream);
 }
 
 // --------------------------------------------------------- post-processing
@@ -383,9 +420,8 @@ __device__ uint32_t find_track(const Track* tracks, uint32_t ntracks, uint64_t i
 
 __global__ void __launch_bounds__(256)
 fixup_kernel(const Track* __restrict__ tracks, uint32_t ntracks,
-             const CoefSet* __restrict__ coefs, const double* __restrict__ gram,
-             const ChunkRec* __restrict__ recs, uint64_t total_recs,
-             double* __restrict__ echunk) {
+             const CoefSet* __restrict__ coefs, const ChunkRec* __restrict__ recs,
+             uint64_t total_recs, double* __restrict__ echunk) {
   const uint64_t r = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= total_recs) return;
   const uint32_t ti = find_track(tracks, ntracks, r, [](const Track& t) { return t.rec_base; });
@@ -396,8 +432,8 @@ fixup_kernel(const Track* __restrict__ tracks, uint32_t ntracks,
   const uint32_t ch = (uint32_t) (local - chunk * tr.channels);
   if (chunk >= (uint64_t) tr.nslots * cs.k) return;   // tail chunks carry peaks only
   const LaneGeom geo = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, (long long) chunk);
-  echunk[r] = chunk_true_energy(cs, gram + 3 * cs.gram_off, recs + tr.rec_base + ch, tr.channels,
-                                (long long) chunk, geo.o);
+  echunk[r] = chunk_true_energy(cs, recs + tr.rec_base + ch, tr.channels, (long long) chunk,
+                                geo.o, 31 - __clz((int) tr.aq));
 }
 
 __global__ void __launch_bounds__(256)
@@ -584,8 +620,8 @@ query_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ quer
 cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t stream) {
   if (z.total_recs) {
     const unsigned blocks = (unsigned) ((z.total_recs + 255) / 256);
-    fixup_kernel<<<blocks, 256, 0, stream>>>(t.tracks, z.ntracks, t.coefs, t.gram, t.recs,
-                                            z.total_recs, t.echunk);
+    fixup_kernel<<<blocks, 256, 0, stream>>>(t.tracks, z.ntracks, t.coefs, t.recs, z.total_recs,
+                                            t.echunk);
   }
   if (z.total_slots) {
     const unsigned blocks = (unsigned) ((z.total_slots + 255) / 256);

@@ -15,8 +15,6 @@ constexpr int kSweepThreads = 128;
 struct DeviceTables {
   const Track* tracks;
   const CoefSet* coefs;
-  const float* basis;
-  const double* gram;
   const WarpWork* work;
   const Query* queries;
   const uint32_t* members;
@@ -35,10 +33,9 @@ struct PostSizes {
   uint64_t total_recs, total_slots, total_blocks, total_st;
 };
 
-// warp_smem: shared memory per warp (lg_plan.h, sweep_warp_smem_host).
-cudaError_t launch_sweep(const DeviceTables& t, uint32_t format, int tpf, uint32_t first_warp,
-                         uint32_t nwarps, uint32_t warp_smem, cudaStream_t stream);
-
+// One sweep launch; `p` carries the group's constants and device pointers.
+cudaError_t launch_sweep(const SweepParams& p, uint32_t format, int tpf, uint32_t kmax,
+                         cudaStream_t stream);
 cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t stream);
 // Gated loudness + range for `nqueries` queries; all pointers are device memory.
 cudaError_t launch_queries(const BlockList* lists, const Query* queries, const uint32_t* members,

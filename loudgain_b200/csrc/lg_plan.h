@@ -13,6 +13,7 @@
 
 #include "lg_common.h"
 #include "lg_design.h"
+#include "lg_sweep.cuh"
 
 namespace lg {
 
@@ -28,19 +29,22 @@ struct TrackIn {
 
 constexpr uint32_t kNoAlbum = 0xffffffffu;
 
-// Sweep launch group: all warps that run the same kernel instantiation.
+// Sweep launch group: all warps that run one kernel launch = one (format,
+// coefficient set, channel count); everything uniform over the launch lives in
+// `params` (device pointers are filled in by lg_batch.cu).
 struct SweepGroup {
   uint32_t format;
   int32_t tpf;
+  uint32_t coef;
+  uint32_t channels;
   uint32_t first_warp;   // into Plan::work
   uint32_t nwarps;
-  uint32_t warp_smem;    // staging bytes per warp (max over the group's tracks)
+  uint32_t kmax;         // cp.async copies per lane and stage, rounded to 3 / 6 / 12
+  SweepParams params;
 };
 
 struct Plan {
   std::vector<CoefSet> coefs;
-  std::vector<float> basis;          // float2 per entry
-  std::vector<double> gram;          // 3 doubles per entry
   std::vector<Track> tracks;
   std::vector<WarpWork> work;
   std::vector<SweepGroup> groups;
@@ -52,10 +56,8 @@ struct Plan {
   uint32_t nalbums = 0;
 };
 
-// target_tasks: how many (chunk, channel) tasks the sweep should expose
-// at least, if the audio is long enough (a few per resident thread).
-// Mirror of sweep_warp_smem() in lg_kernels.cu (kept in the planner so that the
-// host emulation does not need the CUDA translation unit).
+// Shared memory one warp of the sweep needs: staging ring, candidate queue,
+// per-channel true-peak cells.
 inline uint32_t sweep_warp_smem_host(uint32_t channels, uint32_t fb, int tpf) {
   const uint32_t cpw = chunks_per_warp(channels);
   const uint32_t units = (kStageFrames * fb) >> 4;
@@ -99,7 +101,7 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, uint64_t t
     auto it = coef_index.find(key);
     if (it == coef_index.end()) {
       CoefSet cs;
-      make_coefset(t.samplerate, k, t.format == FMT_S16 ? 32768.0 : 1.0, cs, p.basis, p.gram);
+      make_coefset(t.samplerate, k, t.format == FMT_S16 ? 32768.0 : 1.0, cs);
       it = coef_index.emplace(key, (uint32_t) p.coefs.size()).first;
       p.coefs.push_back(cs);
     }
@@ -107,7 +109,7 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, uint64_t t
     const CoefSet& cs = p.coefs[tr.coef];
     tr.fb = t.channels * (t.format == FMT_S16 ? 2u : 4u);
     tr.aq = align_quantum(tr.fb);
-    tr.niters = (uint32_t) ((cs.W + (int) tr.aq - 1 + cs.L + kIter - 1) / kIter);
+    tr.niters = (uint32_t) sweep_iters(cs.W, cs.L, (int) tr.aq);
     tr.nslots = (uint32_t) (t.frames / (uint64_t) s100);
     tr.nchunks = (uint32_t) ((t.frames + cs.L - 1) / (uint64_t) cs.L);
     tr.nblocks = tr.nslots >= 4 ? tr.nslots - 3 : 0;
@@ -124,40 +126,55 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, uint64_t t
     p.total_peaks += tr.channels;
     p.total_samples += t.frames * t.channels;
   }
-  // -- sweep work list, grouped by kernel instantiation (format, tp factor)
-  for (uint32_t fmt = 0; fmt < 2; ++fmt) {
-    for (int tpf : {4, 2, 0}) {
-      SweepGroup g{fmt, tpf, (uint32_t) p.work.size(), 0, 0};
-      for (size_t i = 0; i < n; ++i) {
-        const Track& tr = p.tracks[i];
-        if (tr.format != fmt || p.coefs[tr.coef].tpf != tpf) continue;
-        const CoefSet& cs = p.coefs[tr.coef];
-        const uint32_t cpw = chunks_per_warp(tr.channels);
-        {
-          const uint32_t need = sweep_warp_smem_host(tr.channels, tr.fb, tpf);
-          if (need > g.warp_smem) g.warp_smem = need;
+  // -- sweep work list, one launch group per (format, coefficient set, channels)
+  std::map<std::tuple<uint32_t, uint32_t, uint32_t>, std::vector<uint32_t>> by_group;
+  for (size_t i = 0; i < n; ++i)
+    by_group[std::make_tuple(p.tracks[i].format, p.tracks[i].coef, p.tracks[i].channels)]
+        .push_back((uint32_t) i);
+  for (const auto& kv : by_group) {
+    const Track& t0 = p.tracks[kv.second[0]];
+    const CoefSet& cs = p.coefs[t0.coef];
+    SweepGroup g;
+    g.format = t0.format; g.tpf = cs.tpf; g.coef = t0.coef; g.channels = t0.channels;
+    g.first_warp = (uint32_t) p.work.size();
+    SweepParams& sp = g.params;
+    sp = SweepParams();
+    fill_kcoef(cs, sp);
+    sp.tp_bound = cs.tpf == 4 ? 1.8645f : 2.3072f;   // > ||taps||_1 (1.8642 / 2.3068)
+    sp.W = cs.W; sp.L = cs.L; sp.niters = (int32_t) t0.niters; sp.aq = (int32_t) t0.aq;
+    sp.channels = t0.channels; sp.fb = t0.fb;
+    sp.lpc = t0.channels < 32u ? t0.channels : 32u;
+    sp.cpw = chunks_per_warp(t0.channels);
+    sp.stage_row_bytes = kStageFrames * t0.fb;
+    sp.units = sp.stage_row_bytes >> 4;
+    sp.row_stride = (sp.units | 1u) << 4;
+    sp.stage_bytes = sp.cpw * sp.row_stride;
+    sp.ncopies = sp.cpw * sp.units;
+    sp.warp_smem = sweep_warp_smem_host(t0.channels, t0.fb, cs.tpf);
+    const uint32_t k = (sp.ncopies + 31u) / 32u;
+    g.kmax = k <= 3 ? 3 : (k <= 6 ? 6 : 12);
+    const long long stage_frames =
+        (long long) ((t0.niters + kItersPerStage - 1) / kItersPerStage) * kStageFrames;
+    for (uint32_t i : kv.second) {
+      const Track& tr = p.tracks[i];
+      for (uint32_t c = 0; c < tr.nchunks; c += sp.cpw) {
+        const uint32_t last = c + sp.cpw - 1;
+        const LaneGeom g0 = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, c);
+        const LaneGeom g1 = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, last);
+        int lmin = cs.L;
+        if (last >= tr.nchunks - 1) {
+          const LaneGeom gl = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq,
+                                            tr.nchunks - 1);
+          lmin = gl.l_valid;
         }
-        const long long stage_frames =
-            (long long) ((tr.niters + kItersPerStage - 1) / kItersPerStage) * kStageFrames;
-        for (uint32_t c = 0; c < tr.nchunks; c += cpw) {
-          const uint32_t last = c + cpw - 1;
-          const LaneGeom g0 = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, c);
-          const LaneGeom g1 = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, last);
-          int lmin = cs.L;
-          if (last >= tr.nchunks - 1) {
-            const LaneGeom gl = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq,
-                                              tr.nchunks - 1);
-            lmin = gl.l_valid;
-          }
-          const bool interior = g0.a >= 0 && g1.a + stage_frames <= (long long) tr.frames;
-          for (uint32_t cb = 0; cb < tr.channels; cb += 32)
-            p.work.push_back(WarpWork{(uint32_t) i, c, lmin, (uint16_t) (interior ? 1 : 0),
-                                      (uint16_t) cb});
-        }
+        const bool interior = g0.a >= 0 && g1.a + stage_frames <= (long long) tr.frames;
+        for (uint32_t cb = 0; cb < tr.channels; cb += 32)
+          p.work.push_back(WarpWork{i, c, lmin, (uint16_t) (interior ? 1 : 0), (uint16_t) cb});
       }
-      g.nwarps = (uint32_t) p.work.size() - g.first_warp;
-      if (g.nwarps) p.groups.push_back(g);
     }
+    g.nwarps = (uint32_t) p.work.size() - g.first_warp;
+    sp.nwarps = g.nwarps;
+    if (g.nwarps) p.groups.push_back(g);
   }
   // -- queries: one per track, then one per album
   p.queries.resize(n + nalbums);

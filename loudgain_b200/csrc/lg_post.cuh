@@ -19,10 +19,10 @@ LG_HD void mat2_vec(const double m[4], double x, double y, double& ox, double& o
 
 // True K-weighted energy (still unscaled) of chunk j of one channel.
 // recs points at the channel's record of chunk 0; consecutive chunks are
-// `stride` records apart.  `gram` is the coefficient set's prefix Gram table,
-// `o` the lane's alignment offset (lg_common.h, lane_geometry).
-LG_HD double chunk_true_energy(const CoefSet& cs, const double* gram, const ChunkRec* recs,
-                               long long stride, long long j, int o) {
+// `stride` records apart.  `o` is the lane's alignment offset and `aq_log2`
+// the track's alignment class (lg_common.h, lane_geometry).
+LG_HD double chunk_true_energy(const CoefSet& cs, const ChunkRec* recs, long long stride,
+                               long long j, int o, int aq_log2) {
   // T = true high-pass state at the first frame of chunk j.
   double td = 0.0, tw = 0.0;
   long long i = j - cs.horner;
@@ -37,14 +37,19 @@ LG_HD double chunk_true_energy(const CoefSet& cs, const double* gram, const Chun
   }
   const ChunkRec& r = recs[j * stride];
   // State the zero-started run was missing at its own first (warm-up) frame,
-  // W + o frames before the chunk.
+  // W + o frames before the chunk ...
   double ad, aw;
   mat2_vec(cs.MinvWo[o], td - (double) r.pd, tw - (double) r.pw, ad, aw);
-  const double* g0 = gram + 3 * (long long) (cs.W + o);
-  const double* g1 = g0 + 3 * (long long) cs.L;
-  const double gaa = g1[0] - g0[0], gab = g1[1] - g0[1], gbb = g1[2] - g0[2];
-  return r.e0 + 2.0 * ((double) r.xa * ad + (double) r.xb * aw) +
-         gaa * ad * ad + 2.0 * gab * ad * aw + gbb * aw * aw;
+  // ... whose response in the output is Re(A lambda^f) over the chunk.
+  const double Are = ad * cs.Ad.re + aw * cs.Aw.re, Aim = ad * cs.Ad.im + aw * cs.Aw.im;
+  const cplx sc = cs.xi_scale[aq_log2];
+  const double xr = (double) r.yr * sc.re - (double) r.yi * sc.im;
+  const double xi = (double) r.yr * sc.im + (double) r.yi * sc.re;
+  const double cross = Are * xr - Aim * xi;                     // Re(A Xi)
+  const double a2r = Are * Are - Aim * Aim, a2i = 2.0 * Are * Aim;
+  const double quad = 0.5 * (Are * Are + Aim * Aim) * cs.S1o[o] +
+                      0.5 * (a2r * cs.S2o[o].re - a2i * cs.S2o[o].im);
+  return r.e0 + 2.0 * cross + quad;
 }
 
 LG_HD double weight_of(uint8_t wclass) {

@@ -52,15 +52,15 @@ struct KState {
   float v1, v2;       // shelf
 };
 
-// The sweep's view of a coefficient set (registers / uniform registers).
-struct KCoef {
-  float c, ne2, np1, np2, q1, q2;
-};
+// The sweep reads its filter constants from a SweepParams (kernel parameter /
+// constant bank on the device).
+typedef SweepParams KCoef;
 
-LG_HD KCoef load_kcoef(const CoefSet& cs) {
-  KCoef k;
+// Host-side: the filter part of a SweepParams from a coefficient set.
+inline void fill_kcoef(const CoefSet& cs, SweepParams& k) {
   k.c = cs.c; k.ne2 = -cs.e2; k.np1 = -cs.p1; k.np2 = -cs.p2; k.q1 = cs.q1; k.q2 = cs.q2;
-  return k;
+  for (int i = 0; i < kIter; ++i) { k.lam_re[i] = cs.lam_re[i]; k.lam_im[i] = cs.lam_im[i]; }
+  k.rot_re = cs.rot_re; k.rot_im = cs.rot_im;
 }
 
 // One frame of K-weighting.  Returns the (unnormalised) K-weighted sample.
@@ -118,7 +118,7 @@ struct LaneCtx {
   float hist[NT > 0 ? NT : 1];   // the NT frames before the current iteration
   float mprev;                   // max |x| over the previous iteration
   float sp, tp;                  // raw-unit sample / true peak
-  float xa, xb;
+  float yr, yi;                  // running sum y[f] lambda^(f - f0 of this iteration)
   double e0;
   float pd, pw, qd, qw;          // state snapshots
   int f_lo, f_hi, f_tp;          // energy range, true-peak limit (lane-local)
@@ -130,7 +130,7 @@ LG_HD void lane_init(LaneCtx<TPF>& c, int W, int L, const LaneGeom& g) {
 #pragma unroll
   for (int i = 0; i < (LaneCtx<TPF>::NT > 0 ? LaneCtx<TPF>::NT : 1); ++i) c.hist[i] = 0.0f;
   c.mprev = 0.0f;
-  c.sp = c.tp = c.xa = c.xb = 0.0f;
+  c.sp = c.tp = c.yr = c.yi = 0.0f;
   c.e0 = 0.0;
   c.pd = c.pw = c.qd = c.qw = 0.0f;
   c.f_lo = W + g.o;
@@ -171,23 +171,31 @@ LG_HD void iter_warm(LaneCtx<TPF>& c, const KCoef& k, const float* x) {
   c.pd = c.st.d1; c.pw = c.st.w2;
 }
 
-// Filter + energy part of a fast iteration (all kIter frames lie inside the
-// lane's chunk).  ab = alpha/beta of frames f0.. as float2 pairs.  Returns
-// max |x| of the iteration; the caller owns the true-peak part.
+// Y <- Y * lambda^-kIter + S: keeps Y = sum y[f] lambda^(f - f0) relative to
+// the current iteration's first frame, so the constants lambda^i stay O(1).
 template <int TPF>
-LG_HD float iter_fast_energy(LaneCtx<TPF>& c, const KCoef& k, const float* x, const float* ab,
-                             int f0) {
-  float e = 0.0f, sa = 0.0f, sb = 0.0f;
+LG_HD void mode_accumulate(LaneCtx<TPF>& c, const KCoef& k, float sr, float si) {
+  const float nr = fmaf(c.yr, k.rot_re, fmaf(-c.yi, k.rot_im, sr));
+  const float ni = fmaf(c.yr, k.rot_im, fmaf(c.yi, k.rot_re, si));
+  c.yr = nr;
+  c.yi = ni;
+}
+
+// Filter + energy part of a fast iteration (all kIter frames lie inside the
+// lane's chunk).  Returns max |x| of the iteration; the caller owns the
+// true-peak part.
+template <int TPF>
+LG_HD float iter_fast_energy(LaneCtx<TPF>& c, const KCoef& k, const float* x, int f0) {
+  float e = 0.0f, sr = 0.0f, si = 0.0f;
 #pragma unroll
   for (int i = 0; i < kIter; ++i) {
     const float y = k_step(c.st, x[i], k);
     e = fmaf(y, y, e);
-    sa = fmaf(y, ab[2 * i], sa);
-    sb = fmaf(y, ab[2 * i + 1], sb);
+    sr = fmaf(y, k.lam_re[i], sr);
+    si = fmaf(y, k.lam_im[i], si);
   }
   c.e0 += (double) e;
-  c.xa += sa;
-  c.xb += sb;
+  mode_accumulate(c, k, sr, si);
   if (f0 + kIter == c.f_hi) { c.qd = c.st.d1; c.qw = c.st.w2; }
   const float m = max_abs12(x);
   c.sp = fmaxf(c.sp, m);
@@ -198,9 +206,8 @@ LG_HD float iter_fast_energy(LaneCtx<TPF>& c, const KCoef& k, const float* x, co
 // against the lane's energy range; takes the state snapshots.  Does NOT touch
 // the peaks.
 template <int TPF>
-LG_HD void iter_masked_energy(LaneCtx<TPF>& c, const KCoef& k, const float* x, const float* ab,
-                              int f0) {
-  float e = 0.0f, sa = 0.0f, sb = 0.0f;
+LG_HD void iter_masked_energy(LaneCtx<TPF>& c, const KCoef& k, const float* x, int f0) {
+  float e = 0.0f, sr = 0.0f, si = 0.0f;
 #pragma unroll
   for (int i = 0; i < kIter; ++i) {
     const int f = f0 + i;
@@ -208,14 +215,13 @@ LG_HD void iter_masked_energy(LaneCtx<TPF>& c, const KCoef& k, const float* x, c
     const float y = k_step(c.st, x[i], k);
     if (f >= c.f_lo && f < c.f_hi) {
       e = fmaf(y, y, e);
-      sa = fmaf(y, ab[2 * i], sa);
-      sb = fmaf(y, ab[2 * i + 1], sb);
+      sr = fmaf(y, k.lam_re[i], sr);
+      si = fmaf(y, k.lam_im[i], si);
     }
     if (f + 1 == c.f_hi) { c.qd = c.st.d1; c.qw = c.st.w2; }
   }
   c.e0 += (double) e;
-  c.xa += sa;
-  c.xb += sb;
+  mode_accumulate(c, k, sr, si);
 }
 
 // Peaks of an iteration, frame by frame, limited to the lane's own chunk

@@ -23,13 +23,12 @@ using namespace lg;
 template <int FMT, int TPF>
 static void run_group(const Plan& p, const SweepGroup& g, std::vector<ChunkRec>& recs,
                       std::vector<float>& peaks) {
+  const SweepParams& k = g.params;
   for (uint32_t w = 0; w < g.nwarps; ++w) {
     const WarpWork ww = p.work[g.first_warp + w];
     const Track& tr = p.tracks[ww.track];
     const CoefSet& cs = p.coefs[tr.coef];
-    const KCoef k = load_kcoef(cs);
-    const float* basis = p.basis.data() + 2 * cs.basis_off;
-    const uint32_t C = tr.channels, lpc = C < 32 ? C : 32, cpw = 32 / lpc;
+    const uint32_t C = tr.channels, lpc = k.lpc, cpw = k.cpw;
     const LaneGeom glast = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq,
                                          ww.first_chunk + cpw - 1);
     const long long tp_safe = (long long) tr.frames - glast.a;
@@ -45,23 +44,22 @@ static void run_group(const Plan& p, const SweepGroup& g, std::vector<ChunkRec>&
         float x[kIter];
         host_load_iter<FMT>(tr.pcm, (long long) tr.frames, (int) C, geo.a, f0, (int) ch, x);
         const int kind = iter_kind(f0, cs.W, (int) tr.aq, cs.L, ww.lmin_valid);
-        const float* ab = basis + 2 * f0;
         if (kind == ITER_WARM) {
           iter_warm<TPF>(c, k, x);
           continue;
         }
         if (kind == ITER_FAST) {
-          (void) iter_fast_energy<TPF>(c, k, x, ab, f0);
+          (void) iter_fast_energy<TPF>(c, k, x, f0);
           iter_peaks_all<TPF>(c, x);        // the device defers this to its candidate queue
         } else {
-          iter_masked_energy<TPF>(c, k, x, ab, f0);
+          iter_masked_energy<TPF>(c, k, x, f0);
           if ((long long) f0 + kIter <= tp_safe) iter_peaks_all<TPF>(c, x);
           else iter_peaks_masked<TPF>(c, x, f0);
         }
         hist_advance(c, x);
       }
       ChunkRec& r = recs[tr.rec_base + (uint64_t) chunk * C + ch];
-      r.e0 = c.e0; r.xa = c.xa; r.xb = c.xb;
+      r.e0 = c.e0; r.yr = c.yr; r.yi = c.yi;
       r.pd = c.pd; r.pw = c.pw; r.qd = c.qd; r.qw = c.qw;
       float& sp = peaks[2 * (tr.peak_base + ch)];
       float& tp = peaks[2 * (tr.peak_base + ch) + 1];
@@ -70,6 +68,8 @@ static void run_group(const Plan& p, const SweepGroup& g, std::vector<ChunkRec>&
     }
   }
 }
+
+static int log2u(uint32_t v) { int r = 0; while (v > 1) { v >>= 1; ++r; } return r; }
 
 static void run_query(const Plan& p, const Query& q, const std::vector<double>& zblock,
                       const std::vector<double>& zst, double abs_gate, lgb_result& r) {
@@ -157,8 +157,8 @@ extern "C" int emu_measure(const lgb_track* tracks, size_t ntracks, uint32_t nal
       const LaneGeom geo = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, (long long) chunk);
       for (uint32_t ch = 0; ch < tr.channels; ++ch)
         echunk[tr.rec_base + chunk * tr.channels + ch] =
-            chunk_true_energy(cs, p.gram.data() + 3 * cs.gram_off, recs.data() + tr.rec_base + ch,
-                              tr.channels, (long long) chunk, geo.o);
+            chunk_true_energy(cs, recs.data() + tr.rec_base + ch, tr.channels, (long long) chunk,
+                              geo.o, log2u(tr.aq));
     }
     for (uint32_t s = 0; s < tr.nslots; ++s)
       eslot[tr.slot_base + s] = slot_energy(tr, cs, echunk.data(), s);
