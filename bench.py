@@ -98,12 +98,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_album(device, rank: int):
+def make_album(device, rank: int, fmt: str = "s16"):
     """cfg2 on `device`: list of (int16 tensor [frames, 2], rate)."""
     from loudgain_b200 import synth
     specs = synth.config2_specs(12)
     for s in specs:
         s.seed += 1000 * rank            # every rank scans a different album
+    if fmt == "f32":                     # tuning only: the float API's layout
+        return [(synth.programme_float(s, device=device), s.rate) for s in specs]
     return [(synth.programme_s16(s, device=device), s.rate) for s in specs]
 
 
@@ -223,7 +225,7 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    album = make_album(dev, rank)
+    album = make_album(dev, rank, args.format)
     albums = [0] * len(album)
     stream = torch.cuda.current_stream()
     batch = engine.Batch(album, albums, stream)
@@ -346,6 +348,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--format", default="s16", choices=["s16", "f32"],
+                    help="PCM sample format of the synthetic album (f32: tuning only)")
     ap.add_argument("--quick", action="store_true",
                     help="tuning runs: skip the CPU baseline and the end-to-end leg")
     args = ap.parse_args()

@@ -86,7 +86,7 @@ __device__ __forceinline__ void smem_load_iter(const unsigned char* rowp, uint32
 #define LG_SWEEP_MINBLOCKS 4
 #endif
 
-constexpr uint32_t kQueue = 64;     // candidate windows a warp can hold
+constexpr uint32_t kQueue = 32;     // candidate windows a warp can hold (one dense round)
 
 template <int TPF>
 __host__ __device__ constexpr uint32_t queue_entry_bytes() {
@@ -94,15 +94,15 @@ __host__ __device__ constexpr uint32_t queue_entry_bytes() {
   return ((((TpTraits<TPF>::kTaps + kIter) * 4u + 4u + 15u) >> 4) | 1u) << 4;
 }
 
-// Evaluates up to 32 queued windows, one per lane.
+// Evaluates the n <= 32 queued windows, one per lane.
 template <int TPF>
-__device__ __forceinline__ void flush_round(const unsigned char* queue, uint32_t head, uint32_t n,
-                                            uint32_t lane, uint32_t* tpq) {
+__device__ __forceinline__ void flush_round(const unsigned char* queue, uint32_t n, uint32_t lane,
+                                            uint32_t* tpq) {
   constexpr int NT = TpTraits<TPF>::kTaps;
   constexpr uint32_t EB = queue_entry_bytes<TPF>();
   __syncwarp();                                   // entries written by other lanes are visible
   if (lane < n) {
-    const unsigned char* e = queue + ((head + lane) & (kQueue - 1)) * EB;
+    const unsigned char* e = queue + lane * EB;
     float win[NT + kIter];
     const float4* p = reinterpret_cast<const float4*>(e);
 #pragma unroll
@@ -227,7 +227,7 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
   unsigned char* queue = sm + kRing * P.stage_bytes;
   uint32_t* tpq = reinterpret_cast<uint32_t*>(queue + (NT > 0 ? kQueue * EB : 0));
   tpq[lane] = 0u;
-  uint32_t q_head = 0, q_tail = 0;
+  uint32_t q_count = 0;
   // Frames at or beyond this lane-local index may lie past the end of the
   // track for some lane of the warp: true peak is then masked frame by frame.
   const LaneGeom glast = lane_geometry(frames, L, W, P.aq, ww.first_chunk + P.cpw - 1);
@@ -244,9 +244,39 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
   const bool leader = compute && lane == (uint32_t) (__ffs(peers) - 1);
   float thr = 0.0f;        // the channel's peak is known to reach at least this (raw units)
   float published = 0.0f;
+  uint2 seen = make_uint2(0u, 0u);   // what other warps had published, as of the last poll
+
+  // Queues the window (hist, x) of every lane that has `cand` set; evaluates
+  // the queue first if it cannot take them all.
+  auto enqueue = [&](bool cand, const float* hist, const float* x) {
+    const unsigned mask = __ballot_sync(0xffffffffu, cand);
+    if (mask == 0u) return;
+    const uint32_t npush = __popc(mask);
+    if (q_count + npush > kQueue) {
+      flush_round<TPF>(queue, q_count, lane, tpq);
+      q_count = 0;
+      thr = fmaxf(thr, __uint_as_float(tpq[chl]));
+    }
+    if (cand) {
+      const uint32_t pos = q_count + __popc(mask & ((1u << lane) - 1u));
+      float4* e = reinterpret_cast<float4*>(queue + pos * EB);
+#pragma unroll
+      for (int i = 0; i < NT / 4; ++i)
+        e[i] = make_float4(hist[4 * i], hist[4 * i + 1], hist[4 * i + 2], hist[4 * i + 3]);
+#pragma unroll
+      for (int i = 0; i < kIter / 4; ++i)
+        e[NT / 4 + i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+      *reinterpret_cast<uint32_t*>(e + (NT + kIter) / 4) = chl;
+    }
+    q_count += npush;
+  };
 
   const uint32_t niters = (uint32_t) P.niters;
   const uint32_t nstages = (niters + kItersPerStage - 1) / kItersPerStage;
+  // Stages whose two iterations are both "fast" for every lane of the warp.
+  const int lfast = ww.lmin_valid < L ? ww.lmin_valid : L;
+  const uint32_t fast_lo = (uint32_t) ((W + P.aq - 1 + kStageFrames - 1) / kStageFrames);
+  const uint32_t fast_hi = (uint32_t) ((W + lfast) / kStageFrames);     // exclusive
   prefetch(0);
   cp_async_commit();
   if (nstages > 1) prefetch(1);
@@ -257,78 +287,98 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
     __syncwarp();                // ... everyone's have, and stage s-1 is fully consumed
     if (s + 2 < nstages) prefetch(s + 2);
     cp_async_commit();
-    // what other warps have published for this channel so far
-    uint2 seen = make_uint2(0u, 0u);
-    if (NT > 0 && compute) seen = __ldcg(reinterpret_cast<const uint2*>(my_peak));
+    // What other warps have published for this channel.  Polled sparingly (the
+    // cells are hot) and only folded into the bound at the next poll, so the
+    // L2 round trip is off the critical path.
+    if (NT > 0 && compute && (s & 7u) == 0u) {
+      thr = fmaxf(thr, __uint_as_float(seen.x > seen.y ? seen.x : seen.y));
+      seen = __ldcg(reinterpret_cast<const uint2*>(my_peak));
+    }
     const unsigned char* buf = my_row + (s % kRing) * P.stage_bytes;
-#pragma unroll 1
-    for (int it = 0; it < kItersPerStage; ++it) {
-      const uint32_t iter = s * kItersPerStage + it;
-      if (iter >= niters) break;
-      const int f0 = (int) iter * kIter;
-      const int kind = iter_kind(f0, W, P.aq, L, ww.lmin_valid);
-      float x[kIter];
-      bool cand = false;
+    if (s >= fast_lo && s < fast_hi && tp_safe >= (int) ((s + 1) * kStageFrames)) {
+      // ---- both iterations fast: straight-line code, loads first
+      const int f0 = (int) (s * kStageFrames);
+      float x0[kIter], x1[kIter];
+      bool c0 = false, c1 = false;
+      float h1[NT > 0 ? NT : 1];      // history of the second iteration
       if (compute) {
-        smem_load_iter<FMT>(buf + it * kIter * fb, fb, stereo, ch, x);
-        if (kind == ITER_WARM) {
-          iter_warm<TPF>(c, P, x);
-        } else {
-          float m;
-          bool safe = true;
-          if (kind == ITER_FAST) {
-            m = iter_fast_energy<TPF>(c, P, x, f0);
+        smem_load_iter<FMT>(buf, fb, stereo, ch, x0);
+        smem_load_iter<FMT>(buf + kIter * fb, fb, stereo, ch, x1);
+        const float m0 = iter_fast_energy<TPF>(c, P, x0, f0);
+        const float m1 = iter_fast_energy<TPF>(c, P, x1, f0 + kIter);
+        if (NT > 0) {
+          const float floor_ = fmaxf(thr, c.sp);
+          c0 = P.tp_bound * fmaxf(c.mprev, m0) > floor_;
+          c1 = P.tp_bound * fmaxf(m0, m1) > floor_;
+          c.mprev = m1;
+#pragma unroll
+          for (int i = 0; i < NT - kIter; ++i) h1[i] = c.hist[i + kIter];
+#pragma unroll
+          for (int i = 0; i < kIter; ++i) h1[NT - kIter + i] = x0[i];
+        }
+      }
+      if (NT > 0) {
+        enqueue(c0, c.hist, x0);
+        enqueue(c1, h1, x1);
+        if (compute) {
+          // hist <- last NT frames of (h1, x1)
+#pragma unroll
+          for (int i = 0; i < NT - kIter; ++i) c.hist[i] = h1[i + kIter];
+#pragma unroll
+          for (int i = 0; i < kIter; ++i) c.hist[NT - kIter + i] = x1[i];
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int it = 0; it < kItersPerStage; ++it) {
+        const uint32_t iter = s * kItersPerStage + it;
+        if (iter >= niters) break;
+        const int f0 = (int) iter * kIter;
+        const int kind = iter_kind(f0, W, P.aq, L, ww.lmin_valid);
+        float x[kIter];
+        bool cand = false;
+        if (compute) {
+          smem_load_iter<FMT>(buf + it * kIter * fb, fb, stereo, ch, x);
+          if (kind == ITER_WARM) {
+            iter_warm<TPF>(c, P, x);
           } else {
-            iter_masked_energy<TPF>(c, P, x, f0);
-            m = max_abs12(x);
-            safe = f0 + kIter <= tp_safe;
-            if (safe) c.sp = fmaxf(c.sp, m);
-            else {                                       // track end: frame by frame
-              SlowPeakArgs<TPF> a;
+            float m;
+            bool safe = true;
+            if (kind == ITER_FAST) {
+              m = iter_fast_energy<TPF>(c, P, x, f0);
+            } else {
+              iter_masked_energy<TPF>(c, P, x, f0);
+              m = max_abs12(x);
+              safe = f0 + kIter <= tp_safe;
+              if (safe) c.sp = fmaxf(c.sp, m);
+              else {                                       // track end: frame by frame
+                SlowPeakArgs<TPF> a;
 #pragma unroll
-              for (int i = 0; i < NT; ++i) a.win[i] = c.hist[i];
+                for (int i = 0; i < NT; ++i) a.win[i] = c.hist[i];
 #pragma unroll
-              for (int i = 0; i < kIter; ++i) a.win[NT + i] = x[i];
-              a.f0 = f0; a.f_lo = c.f_lo; a.f_tp = c.f_tp; a.sp = c.sp; a.tp = c.tp;
-              const float2 r = peaks_masked_slow<TPF>(a);
-              c.sp = r.x; c.tp = r.y;
+                for (int i = 0; i < kIter; ++i) a.win[NT + i] = x[i];
+                a.f0 = f0; a.f_lo = c.f_lo; a.f_tp = c.f_tp; a.sp = c.sp; a.tp = c.tp;
+                const float2 r = peaks_masked_slow<TPF>(a);
+                c.sp = r.x; c.tp = r.y;
+              }
+            }
+            if (NT > 0) {
+              cand = safe && P.tp_bound * fmaxf(c.mprev, m) > fmaxf(thr, c.sp);
+              c.mprev = m;
             }
           }
-          if (NT > 0) {
-            cand = safe && P.tp_bound * fmaxf(c.mprev, m) > fmaxf(thr, c.sp);
-            c.mprev = m;
-          }
         }
-      }
-      if (NT > 0 && kind != ITER_WARM) {
-        const unsigned mask = __ballot_sync(0xffffffffu, cand);
-        if (mask) {
-          if (cand) {
-            const uint32_t pos = (q_tail + __popc(mask & ((1u << lane) - 1u))) & (kQueue - 1);
-            float4* e = reinterpret_cast<float4*>(queue + pos * EB);
-#pragma unroll
-            for (int i = 0; i < NT / 4; ++i)
-              e[i] = make_float4(c.hist[4 * i], c.hist[4 * i + 1], c.hist[4 * i + 2], c.hist[4 * i + 3]);
-#pragma unroll
-            for (int i = 0; i < kIter / 4; ++i)
-              e[NT / 4 + i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-            *reinterpret_cast<uint32_t*>(e + (NT + kIter) / 4) = chl;
-          }
-          q_tail += __popc(mask);
-          if (q_tail - q_head >= 32u) {
-            flush_round<TPF>(queue, q_head, 32u, lane, tpq);
-            q_head += 32u;
-            thr = fmaxf(thr, __uint_as_float(tpq[chl]));
-          }
+        if (NT > 0 && kind != ITER_WARM) {
+          enqueue(cand, c.hist, x);
+          if (compute) hist_advance(c, x);
         }
-        if (compute) hist_advance(c, x);
       }
     }
-    if (NT > 0 && compute) {
-      // raise the bound with what other warps know; publish what this warp knows
+    if (NT > 0 && compute && (s & 7u) == 7u) {
+      // publish what this warp knows, if it is news
       const float theirs = __uint_as_float(seen.x > seen.y ? seen.x : seen.y);
       const float mine = fmaxf(fmaxf(c.sp, c.tp), __uint_as_float(tpq[chl]));
-      thr = fmaxf(thr, fmaxf(theirs, mine));
+      thr = fmaxf(thr, mine);
       if (mine > published && mine > theirs) {
         // goes into the true-peak cell: the reported true peak is the max of
         // both cells anyway (ebur128_true_peak folds the sample peak in)
@@ -338,13 +388,7 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
     }
   }
   cp_async_wait<0>();
-  if (NT > 0) {
-    while (q_tail != q_head) {
-      const uint32_t n = q_tail - q_head < 32u ? q_tail - q_head : 32u;
-      flush_round<TPF>(queue, q_head, n, lane, tpq);
-      q_head += n;
-    }
-  }
+  if (NT > 0 && q_count) flush_round<TPF>(queue, q_count, lane, tpq);
   __syncwarp();
 
   if (active) {

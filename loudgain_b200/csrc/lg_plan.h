@@ -64,7 +64,7 @@ inline uint32_t sweep_warp_smem_host(uint32_t channels, uint32_t fb, int tpf) {
   uint32_t bytes = kRing * cpw * ((units | 1u) << 4);
   if (tpf) {
     const uint32_t nt = tpf == 4 ? 12u : 24u;
-    bytes += 64u * (((((nt + kIter) * 4u + 4u + 15u) >> 4) | 1u) << 4);
+    bytes += 32u * (((((nt + kIter) * 4u + 4u + 15u) >> 4) | 1u) << 4);   // candidate queue
   }
   return bytes + 32u * 4u;
 }
