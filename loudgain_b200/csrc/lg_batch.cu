@@ -22,12 +22,14 @@ void set_error(const char* what, cudaError_t e) {
 }
 void set_error(const char* what) { g_error = what; }
 
+// Device memory comes from the stream-ordered pool: batches are created and
+// destroyed per album on the drop-in path, and pool allocations are cheap.
 template <class T>
 static bool upload(const std::vector<T>& v, T** dev, cudaStream_t s) {
   *dev = nullptr;
   const size_t bytes = (v.empty() ? 1 : v.size()) * sizeof(T);
-  cudaError_t e = cudaMalloc((void**) dev, bytes);
-  if (e != cudaSuccess) { set_error("cudaMalloc", e); return false; }
+  cudaError_t e = cudaMallocAsync((void**) dev, bytes, s);
+  if (e != cudaSuccess) { set_error("cudaMallocAsync", e); return false; }
   if (!v.empty()) {
     e = cudaMemcpyAsync(*dev, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) { set_error("cudaMemcpyAsync(H2D tables)", e); return false; }
@@ -36,10 +38,10 @@ static bool upload(const std::vector<T>& v, T** dev, cudaStream_t s) {
 }
 
 template <class T>
-static bool dalloc(T** dev, uint64_t n) {
+static bool dalloc(T** dev, uint64_t n, cudaStream_t s) {
   *dev = nullptr;
-  cudaError_t e = cudaMalloc((void**) dev, (n ? n : 1) * sizeof(T));
-  if (e != cudaSuccess) { set_error("cudaMalloc", e); return false; }
+  cudaError_t e = cudaMallocAsync((void**) dev, (n ? n : 1) * sizeof(T), s);
+  if (e != cudaSuccess) { set_error("cudaMallocAsync", e); return false; }
   return true;
 }
 
@@ -50,14 +52,15 @@ int query_lists_sync(const BlockList* lists, size_t n, cudaStream_t stream, Quer
   std::vector<Query> hq(1, Query{0, (uint32_t) n});
   BlockList* dl = nullptr; uint32_t* dm = nullptr; Query* dq = nullptr; QueryResult* dr = nullptr;
   bool ok = upload(hl, &dl, stream) && upload(hm, &dm, stream) && upload(hq, &dq, stream) &&
-            dalloc(&dr, 1);
+            dalloc(&dr, 1, stream);
   if (ok) {
     cudaError_t e = launch_queries(dl, dq, dm, 1, pow(10.0, (-70.0 + 0.691) / 10.0), dr, stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, dr, sizeof(QueryResult), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) { set_error("query_lists_sync", e); ok = false; }
   }
-  cudaFree(dl); cudaFree(dm); cudaFree(dq); cudaFree(dr);
+  cudaFreeAsync(dl, stream); cudaFreeAsync(dm, stream); cudaFreeAsync(dq, stream);
+  cudaFreeAsync(dr, stream);
   return ok ? 0 : 1;
 }
 
@@ -82,9 +85,9 @@ struct lgb_batch {
   double* d_zblock = nullptr;
   double* d_zst = nullptr;
   QueryResult* d_results = nullptr;
-  // pinned host mirrors
-  QueryResult* h_results = nullptr;
-  uint32_t* h_peaks = nullptr;
+  // host mirrors of the (tiny) results
+  std::vector<QueryResult> h_results;
+  std::vector<uint32_t> h_peaks;
   double abs_gate = 0.0;
   uint32_t launches = 0, sweep_launches = 0;
   // optional sweep timing
@@ -131,10 +134,14 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
   bool ok = upload(p.tracks, &b->d_tracks, b->stream) && upload(p.coefs, &b->d_coefs, b->stream) &&
             upload(p.work, &b->d_work, b->stream) &&
             upload(p.queries, &b->d_queries, b->stream) &&
-            upload(p.members, &b->d_members, b->stream) && dalloc(&b->d_recs, p.total_recs) &&
-            dalloc(&b->d_peaks, 2 * p.total_peaks) && dalloc(&b->d_echunk, p.total_recs) &&
-            dalloc(&b->d_eslot, p.total_slots) && dalloc(&b->d_zblock, p.total_blocks) &&
-            dalloc(&b->d_zst, p.total_st) && dalloc(&b->d_results, (uint64_t) p.queries.size());
+            upload(p.members, &b->d_members, b->stream) &&
+            dalloc(&b->d_recs, p.total_recs, b->stream) &&
+            dalloc(&b->d_peaks, 2 * p.total_peaks, b->stream) &&
+            dalloc(&b->d_echunk, p.total_recs, b->stream) &&
+            dalloc(&b->d_eslot, p.total_slots, b->stream) &&
+            dalloc(&b->d_zblock, p.total_blocks, b->stream) &&
+            dalloc(&b->d_zst, p.total_st, b->stream) &&
+            dalloc(&b->d_results, (uint64_t) p.queries.size(), b->stream);
   if (ok) {
     std::vector<BlockList> lists(p.tracks.size());
     for (size_t i = 0; i < p.tracks.size(); ++i) {
@@ -144,11 +151,11 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
     ok = upload(lists, &b->d_lists, b->stream);
   }
   if (ok) {
-    cudaError_t e = cudaMallocHost((void**) &b->h_results,
-                                   (p.queries.empty() ? 1 : p.queries.size()) * sizeof(QueryResult));
-    if (e == cudaSuccess)
-      e = cudaMallocHost((void**) &b->h_peaks, (p.total_peaks ? 2 * p.total_peaks : 1) * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);   // tables are in place
+    b->h_results.resize(p.queries.empty() ? 1 : p.queries.size());
+    b->h_peaks.resize(p.total_peaks ? 2 * p.total_peaks : 1);
+    // the table uploads read host vectors that die with this call's scope
+    // only in `lists`; the plan's own vectors live as long as the batch
+    const cudaError_t e = cudaStreamSynchronize(b->stream);
     if (e != cudaSuccess) { set_error("lgb_batch_create", e); ok = false; }
   }
   if (!ok) { lgb_batch_destroy(b); return nullptr; }
@@ -191,10 +198,10 @@ extern "C" LG_EXPORT int lgb_batch_fetch(lgb_batch* b, lgb_result* track_results
   const Plan& p = b->plan;
   cudaError_t e = cudaSuccess;
   if (!p.queries.empty())
-    e = cudaMemcpyAsync(b->h_results, b->d_results, p.queries.size() * sizeof(QueryResult),
+    e = cudaMemcpyAsync(b->h_results.data(), b->d_results, p.queries.size() * sizeof(QueryResult),
                         cudaMemcpyDeviceToHost, b->stream);
   if (e == cudaSuccess && p.total_peaks)
-    e = cudaMemcpyAsync(b->h_peaks, b->d_peaks, 2 * p.total_peaks * sizeof(uint32_t),
+    e = cudaMemcpyAsync(b->h_peaks.data(), b->d_peaks, 2 * p.total_peaks * sizeof(uint32_t),
                         cudaMemcpyDeviceToHost, b->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
   if (e != cudaSuccess) { set_error("lgb_batch_fetch", e); return 1; }
@@ -270,11 +277,9 @@ extern "C" LG_EXPORT int lgb_query_lists(const double* const* z, const uint32_t*
 extern "C" LG_EXPORT void lgb_batch_destroy(lgb_batch* b) {
   if (!b) return;
   if (b->ev0) { cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); }
-  cudaFree(b->d_tracks); cudaFree(b->d_coefs); cudaFree(b->d_work);
-  cudaFree(b->d_queries); cudaFree(b->d_members); cudaFree(b->d_lists); cudaFree(b->d_recs); cudaFree(b->d_peaks);
-  cudaFree(b->d_echunk); cudaFree(b->d_eslot); cudaFree(b->d_zblock); cudaFree(b->d_zst);
-  cudaFree(b->d_results);
-  if (b->h_results) cudaFreeHost(b->h_results);
-  if (b->h_peaks) cudaFreeHost(b->h_peaks);
+  void* const mem[] = {b->d_tracks, b->d_coefs, b->d_work, b->d_queries, b->d_members, b->d_lists,
+                       b->d_recs, b->d_peaks, b->d_echunk, b->d_eslot, b->d_zblock, b->d_zst,
+                       b->d_results};
+  for (void* m : mem) if (m) cudaFreeAsync(m, b->stream);
   delete b;
 }

@@ -34,7 +34,8 @@
 
 namespace {
 
-constexpr size_t kStageBytes = 8u << 20;   // each of the two pinned staging buffers
+constexpr size_t kStageBytes = 8u << 20;   // each pinned staging buffer
+constexpr int kStageSlots = 4;             // ring of staging buffers, shared by all states
 
 struct BatchHolder {
   lgb_batch* b = nullptr;
@@ -58,11 +59,23 @@ struct Segment {
   std::vector<double> sp, tp;
 };
 
+// One pinned staging buffer.  A state owns a slot while it is filling it; a
+// flushed slot stays "in flight" until its H2D copy has completed.
+struct StageSlot {
+  char* buf = nullptr;
+  cudaEvent_t ev = nullptr;
+  bool in_flight = false;
+  ebur128_state* owner = nullptr;
+  size_t fill = 0;
+};
+
 struct Context {
   std::mutex mu;
   bool ready = false, failed = false;
   int device = 0;
   cudaStream_t stream = nullptr;
+  StageSlot slots[kStageSlots];
+  int next_slot = 0;
   std::vector<ebur128_state*> live;
   // cache of the last *_multiple query (loudgain repeats it per track)
   std::vector<std::pair<const void*, size_t>> multi_key;
@@ -72,8 +85,16 @@ struct Context {
 
 Context g_ctx;
 
+// Makes the library's device current (only needed before CUDA calls, i.e. when
+// a staging buffer is flushed or something is measured -- not per add_frames).
+bool ctx_device() {
+  int cur = -1;
+  if (cudaGetDevice(&cur) == cudaSuccess && cur == g_ctx.device) return true;
+  return cudaSetDevice(g_ctx.device) == cudaSuccess;
+}
+
 bool ctx_init() {
-  if (g_ctx.ready) return cudaSetDevice(g_ctx.device) == cudaSuccess;
+  if (g_ctx.ready) return ctx_device();
   if (g_ctx.failed) return false;
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -88,6 +109,18 @@ bool ctx_init() {
   if (g_ctx.device < 0 || g_ctx.device >= n) g_ctx.device = 0;
   e = cudaSetDevice(g_ctx.device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking);
+  for (int i = 0; i < kStageSlots && e == cudaSuccess; ++i) {
+    e = cudaMallocHost((void**) &g_ctx.slots[i].buf, kStageBytes);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_ctx.slots[i].ev, cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) {
+    // keep freed device memory in the stream-ordered pool: states come and go
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, g_ctx.device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   if (e != cudaSuccess) {
     fprintf(stderr, "libebur128 (B200): CUDA initialisation failed: %s\n", cudaGetErrorString(e));
     g_ctx.failed = true;
@@ -102,11 +135,7 @@ bool ctx_init() {
 struct ebur128_state_internal {
   std::vector<Segment> segs;
   int chmap[lg::kMaxChannels];
-  char* stage[2] = {nullptr, nullptr};
-  cudaEvent_t ev[2] = {nullptr, nullptr};
-  bool ev_armed[2] = {false, false};
-  int cur = 0;
-  size_t stage_fill = 0;
+  int slot = -1;                // staging slot this state is filling, or -1
   unsigned long window_ms = 400, history_ms = ULONG_MAX;
   std::vector<float> convert;   // host scratch for int / double input
 };
@@ -149,14 +178,20 @@ void invalidate(Segment& s) {
   g_ctx.multi_valid = false;
 }
 
-// Pushes the filled part of the current staging buffer to the device.
+// Pushes the filled part of the state's staging slot to the device and gives
+// the slot back to the ring.
 bool flush_stage(ebur128_state* st) {
   ebur128_state_internal* d = st->d;
-  if (!d->stage_fill) return true;
+  if (d->slot < 0) return true;
+  StageSlot& sl = g_ctx.slots[d->slot];
+  d->slot = -1;
+  sl.owner = nullptr;
+  if (!sl.fill) return true;
+  if (!ctx_device()) return false;
   Segment& s = d->segs.back();
-  const size_t need = s.fill + d->stage_fill;
+  const size_t need = s.fill + sl.fill;
   if (need > s.cap) {
-    size_t ncap = std::max<size_t>(std::max<size_t>(s.cap * 2, need), 4u << 20);
+    size_t ncap = std::max<size_t>(std::max<size_t>(s.cap * 2, need), 32u << 20);
     char* np = nullptr;
     if (cudaMallocAsync((void**) &np, ncap, g_ctx.stream) != cudaSuccess) return false;
     if (s.fill &&
@@ -166,33 +201,45 @@ bool flush_stage(ebur128_state* st) {
     s.d_pcm = np;
     s.cap = ncap;
   }
-  const int cur = d->cur;
-  if (cudaMemcpyAsync(s.d_pcm + s.fill, d->stage[cur], d->stage_fill, cudaMemcpyHostToDevice,
-                      g_ctx.stream) != cudaSuccess)
+  if (cudaMemcpyAsync(s.d_pcm + s.fill, sl.buf, sl.fill, cudaMemcpyHostToDevice, g_ctx.stream) !=
+      cudaSuccess)
     return false;
-  cudaEventRecord(d->ev[cur], g_ctx.stream);
-  d->ev_armed[cur] = true;
-  s.fill += d->stage_fill;
-  d->stage_fill = 0;
-  d->cur = cur ^ 1;
-  // The other buffer may still be in flight from two flushes ago.
-  if (d->ev_armed[d->cur]) {
-    if (cudaEventSynchronize(d->ev[d->cur]) != cudaSuccess) return false;
-    d->ev_armed[d->cur] = false;
-  }
+  cudaEventRecord(sl.ev, g_ctx.stream);
+  sl.in_flight = true;
+  s.fill += sl.fill;
+  sl.fill = 0;
   return true;
 }
 
-// Copies `bytes` of caller PCM through the pinned double buffer.
+// Finds a staging slot for `st`: the next one in the ring, waiting for its
+// copy if it is still in flight, or taking it from a state that left it
+// partly filled (that state's bytes are flushed first).
+bool acquire_slot(ebur128_state* st) {
+  StageSlot& sl = g_ctx.slots[g_ctx.next_slot];
+  if (sl.owner && !flush_stage(sl.owner)) return false;
+  if (sl.in_flight) {
+    if (!ctx_device() || cudaEventSynchronize(sl.ev) != cudaSuccess) return false;
+    sl.in_flight = false;
+  }
+  sl.owner = st;
+  sl.fill = 0;
+  st->d->slot = g_ctx.next_slot;
+  g_ctx.next_slot = (g_ctx.next_slot + 1) % kStageSlots;
+  return true;
+}
+
+// Copies `bytes` of caller PCM through the pinned staging ring.
 bool stage_bytes(ebur128_state* st, const char* src, size_t bytes) {
   ebur128_state_internal* d = st->d;
   while (bytes) {
-    const size_t n = std::min(bytes, kStageBytes - d->stage_fill);
-    memcpy(d->stage[d->cur] + d->stage_fill, src, n);
-    d->stage_fill += n;
+    if (d->slot < 0 && !acquire_slot(st)) return false;
+    StageSlot& sl = g_ctx.slots[d->slot];
+    const size_t n = std::min(bytes, kStageBytes - sl.fill);
+    memcpy(sl.buf + sl.fill, src, n);
+    sl.fill += n;
     src += n;
     bytes -= n;
-    if (d->stage_fill == kStageBytes && !flush_stage(st)) return false;
+    if (sl.fill == kStageBytes && !flush_stage(st)) return false;
   }
   return true;
 }
@@ -201,17 +248,17 @@ int add_frames(ebur128_state* st, const void* src, size_t frames, uint32_t forma
   if (!st || !st->d) return EBUR128_ERROR_NOMEM;
   if (!frames) return EBUR128_SUCCESS;
   std::lock_guard<std::mutex> lock(g_ctx.mu);
-  if (!ctx_init()) return EBUR128_ERROR_NOMEM;
+  if (!g_ctx.ready) return EBUR128_ERROR_NOMEM;
   ebur128_state_internal* d = st->d;
   Segment* s = &d->segs.back();
-  if (s->frames == 0 && d->stage_fill == 0) s->format = format;
+  if (s->frames == 0) s->format = format;
   if (s->format != format) {
-    // A caller mixing sample types on one state: start a float run is not
-    // expressible without re-filtering, so keep one format per state.
+    // Mixing sample types on one state is not supported: the PCM of a state
+    // is kept in one format in HBM.
     fprintf(stderr, "libebur128 (B200): mixing sample formats on one state is not supported\n");
     return EBUR128_ERROR_INVALID_MODE;
   }
-  invalidate(*s);
+  if (s->measured) invalidate(*s);
   const size_t bytes = frames * st->channels * sample_bytes(format);
   if (!stage_bytes(st, (const char*) src, bytes)) return EBUR128_ERROR_NOMEM;
   s->frames += frames;
@@ -223,7 +270,7 @@ int add_frames(ebur128_state* st, const void* src, size_t frames, uint32_t forma
 bool measure_pending() {
   std::vector<Segment*> todo;
   for (ebur128_state* st : g_ctx.live) {
-    if (st->d->stage_fill && !flush_stage(st)) return false;
+    if (!flush_stage(st)) return false;
     for (Segment& s : st->d->segs)
       if (!s.measured) todo.push_back(&s);
   }
@@ -343,21 +390,6 @@ extern "C" LG_EXPORT ebur128_state* ebur128_init(unsigned int channels, unsigned
   st->samplerate = samplerate;
   st->d->window_ms = has_mode(st, EBUR128_MODE_S) ? 3000 : 400;
   default_map(st->d->chmap, channels);
-  bool ok = true;
-  for (int i = 0; i < 2 && ok; ++i) {
-    ok = cudaMallocHost((void**) &st->d->stage[i], kStageBytes) == cudaSuccess &&
-         cudaEventCreateWithFlags(&st->d->ev[i], cudaEventDisableTiming) == cudaSuccess;
-  }
-  if (!ok) {
-    fprintf(stderr, "libebur128 (B200): cannot allocate pinned staging buffers\n");
-    for (int i = 0; i < 2; ++i) {
-      if (st->d->stage[i]) cudaFreeHost(st->d->stage[i]);
-      if (st->d->ev[i]) cudaEventDestroy(st->d->ev[i]);
-    }
-    delete st->d;
-    free(st);
-    return NULL;
-  }
   open_segment(st, LGB_FORMAT_S16);
   g_ctx.live.push_back(st);
   return st;
@@ -367,18 +399,18 @@ extern "C" LG_EXPORT void ebur128_destroy(ebur128_state** stp) {
   if (!stp || !*stp) return;
   ebur128_state* st = *stp;
   std::lock_guard<std::mutex> lock(g_ctx.mu);
-  if (g_ctx.ready) cudaSetDevice(g_ctx.device);
+  if (g_ctx.ready) ctx_device();
   g_ctx.live.erase(std::remove(g_ctx.live.begin(), g_ctx.live.end(), st), g_ctx.live.end());
   g_ctx.multi_valid = false;
   if (st->d) {
-    if (g_ctx.ready) cudaStreamSynchronize(g_ctx.stream);
+    if (st->d->slot >= 0) {           // drop bytes that were staged but never flushed
+      g_ctx.slots[st->d->slot].owner = nullptr;
+      g_ctx.slots[st->d->slot].fill = 0;
+    }
     for (Segment& s : st->d->segs) {
+      // stream-ordered: anything still reading the PCM was enqueued before
       if (s.d_pcm) cudaFreeAsync(s.d_pcm, g_ctx.stream);
       s.batch.reset();
-    }
-    for (int i = 0; i < 2; ++i) {
-      if (st->d->stage[i]) cudaFreeHost(st->d->stage[i]);
-      if (st->d->ev[i]) cudaEventDestroy(st->d->ev[i]);
     }
     delete st->d;
   }
