@@ -236,17 +236,16 @@ def gpu_arm(args):
     samples = batch.total_samples
     pcm_bytes = sum(t.numel() * t.element_size() for t, _ in album)
 
-    def merged_album():
-        """Album over ALL ranks' tracks: all-gather the block lists over NCCL,
-        then run the gating / range kernel over the union on every rank."""
-        if world == 1:
-            return None
-        return engine.merge_album_across_ranks(batch, range(len(album)), dist, world)
+    # Album over ALL ranks' tracks: all-gather the block lists over NCCL, then
+    # run the gating / range kernel over the union on every rank.
+    merge = engine.AlbumMerge(batch, range(len(album)), dist, world) if world > 1 else None
 
     def step():
         batch.run()
+        if merge is not None:
+            merge.run()                  # same stream: ordered after the batch's kernels
         res = batch.fetch()
-        return res, merged_album()
+        return res, (merge.fetch() if merge is not None else None)
 
     # ---- resident-PCM throughput
     for _ in range(args.warmup):
@@ -337,6 +336,8 @@ def gpu_arm(args):
             "host_cores": os.cpu_count(),
         }
         print(json.dumps(line), flush=True)
+    if merge is not None:
+        merge.close()
     batch.close()
     if world > 1:
         dist.destroy_process_group()

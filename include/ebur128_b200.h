@@ -94,6 +94,18 @@ void lgb_batch_destroy(lgb_batch* b);
 int lgb_query_lists(const double* const* z, const uint32_t* nz, const double* const* st,
                     const uint32_t* nst, size_t n, void* cuda_stream, lgb_result* out);
 
+/* Persistent form of lgb_query_lists for a fixed set of device buffers (a
+ * pre-allocated all-gather target that is refilled every step): tables are
+ * uploaded once, lgb_listquery_run only launches the kernel and an async
+ * read-back on the stream, lgb_listquery_fetch waits for it. */
+typedef struct lgb_listquery lgb_listquery;
+lgb_listquery* lgb_listquery_create(const double* const* z, const uint32_t* nz,
+                                    const double* const* st, const uint32_t* nst, size_t n,
+                                    void* cuda_stream);
+int lgb_listquery_run(lgb_listquery* q);
+int lgb_listquery_fetch(lgb_listquery* q, lgb_result* out);
+void lgb_listquery_destroy(lgb_listquery* q);
+
 /* ---- scan.c-shaped host driver -------------------------------------------
  * Replays the reference scanner's call sequence against the ebur128_* ABI of
  * this library for PCM held in HOST memory: scan_file's per-frame

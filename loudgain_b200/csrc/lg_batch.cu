@@ -68,6 +68,11 @@ int query_lists_sync(const BlockList* lists, size_t n, cudaStream_t stream, Quer
 
 using namespace lg;
 
+static void to_result(const QueryResult& q, lgb_result& r) {
+  r.loudness = q.loudness; r.range = q.range; r.rel_threshold = q.rel_thr;
+  r.sum_abs = q.sum1; r.sum_rel = q.sum2; r.n_abs = q.n1; r.n_rel = q.n2; r.n_shortterm = q.nst;
+}
+
 struct lgb_batch {
   Plan plan;
   cudaStream_t stream = nullptr;
@@ -188,10 +193,6 @@ extern "C" LG_EXPORT int lgb_batch_run(lgb_batch* b) {
   return 0;
 }
 
-static void to_result(const QueryResult& q, lgb_result& r) {
-  r.loudness = q.loudness; r.range = q.range; r.rel_threshold = q.rel_thr;
-  r.sum_abs = q.sum1; r.sum_rel = q.sum2; r.n_abs = q.n1; r.n_rel = q.n2; r.n_shortterm = q.nst;
-}
 
 extern "C" LG_EXPORT int lgb_batch_fetch(lgb_batch* b, lgb_result* track_results, lgb_result* album_results,
                                double* sample_peaks, double* true_peaks) {
@@ -272,6 +273,63 @@ extern "C" LG_EXPORT int lgb_query_lists(const double* const* z, const uint32_t*
   if (query_lists_sync(lists.data(), n, (cudaStream_t) cuda_stream, &q)) return 1;
   to_result(q, *out);
   return 0;
+}
+
+struct lgb_listquery {
+  cudaStream_t stream = nullptr;
+  BlockList* d_lists = nullptr;
+  uint32_t* d_members = nullptr;
+  Query* d_query = nullptr;
+  QueryResult* d_result = nullptr;
+  QueryResult* h_result = nullptr;   // pinned
+  double abs_gate = 0.0;
+};
+
+extern "C" LG_EXPORT lgb_listquery* lgb_listquery_create(const double* const* z, const uint32_t* nz,
+                                                         const double* const* st,
+                                                         const uint32_t* nst, size_t n,
+                                                         void* cuda_stream) {
+  lgb_listquery* q = new lgb_listquery();
+  q->stream = (cudaStream_t) cuda_stream;
+  q->abs_gate = pow(10.0, (-70.0 + 0.691) / 10.0);
+  std::vector<BlockList> hl(n);
+  std::vector<uint32_t> hm(n);
+  for (size_t i = 0; i < n; ++i) { hl[i] = BlockList{z[i], st[i], nz[i], nst[i]}; hm[i] = (uint32_t) i; }
+  std::vector<Query> hq(1, Query{0, (uint32_t) n});
+  bool ok = upload(hl, &q->d_lists, q->stream) && upload(hm, &q->d_members, q->stream) &&
+            upload(hq, &q->d_query, q->stream) && dalloc(&q->d_result, 1, q->stream);
+  if (ok) {
+    cudaError_t e = cudaMallocHost((void**) &q->h_result, sizeof(QueryResult));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(q->stream);
+    if (e != cudaSuccess) { set_error("lgb_listquery_create", e); ok = false; }
+  }
+  if (!ok) { lgb_listquery_destroy(q); return nullptr; }
+  return q;
+}
+
+extern "C" LG_EXPORT int lgb_listquery_run(lgb_listquery* q) {
+  cudaError_t e = launch_queries(q->d_lists, q->d_query, q->d_members, 1, q->abs_gate, q->d_result,
+                                 q->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(q->h_result, q->d_result, sizeof(QueryResult), cudaMemcpyDeviceToHost,
+                        q->stream);
+  if (e != cudaSuccess) { set_error("lgb_listquery_run", e); return 1; }
+  return 0;
+}
+
+extern "C" LG_EXPORT int lgb_listquery_fetch(lgb_listquery* q, lgb_result* out) {
+  const cudaError_t e = cudaStreamSynchronize(q->stream);
+  if (e != cudaSuccess) { set_error("lgb_listquery_fetch", e); return 1; }
+  to_result(*q->h_result, *out);
+  return 0;
+}
+
+extern "C" LG_EXPORT void lgb_listquery_destroy(lgb_listquery* q) {
+  if (!q) return;
+  void* const mem[] = {q->d_lists, q->d_members, q->d_query, q->d_result};
+  for (void* m : mem) if (m) cudaFreeAsync(m, q->stream);
+  if (q->h_result) cudaFreeHost(q->h_result);
+  delete q;
 }
 
 extern "C" LG_EXPORT void lgb_batch_destroy(lgb_batch* b) {

@@ -248,16 +248,90 @@ def query_lists(z_lists, st_lists, stream=None) -> Measurement:
                        r.n_rel, r.n_shortterm)
 
 
-def merge_album_across_ranks(batch: Batch, tracks, dist, world: int) -> Measurement:
-    """Album result over tracks that are sharded across ranks:
-    every rank contributes the block lists of its local `tracks`; the lists
-    are all-gathered over NCCL and the gating / range kernel runs over the
-    union.  Exact: same block energies as a single-GPU album query."""
-    import torch
+class AlbumMerge:
+    """Album result over tracks that are sharded across ranks.
 
-    batch.stream.synchronize()
-    z = torch.cat([device_blocks(batch, t, 0) for t in tracks])
-    st = torch.cat([device_blocks(batch, t, 1) for t in tracks])
-    zs = gather_block_lists(dist, z, world)
-    sts = gather_block_lists(dist, st, world)
-    return query_lists(zs, sts, batch.stream)
+    Every rank contributes the block lists (400 ms gating blocks and 3 s
+    short-term blocks) of its local `tracks`; per step they are packed into one
+    buffer, all-gathered over NCCL into a pre-allocated [world, width] tensor,
+    and the library's gating / range kernel runs over the union on every rank
+    (lgb_listquery_*).  Exact: the same block energies a single-GPU album query
+    would see.  Sizes are exchanged once, at construction.
+    """
+
+    def __init__(self, batch: Batch, tracks, dist, world: int, group=None):
+        import torch
+
+        self.batch, self.dist, self.world, self.group = batch, dist, world, group
+        self.tracks = list(tracks)
+        batch.stream.synchronize()
+        self.z_views = [device_blocks(batch, t, 0) for t in self.tracks]
+        self.st_views = [device_blocks(batch, t, 1) for t in self.tracks]
+        nz = sum(v.numel() for v in self.z_views)
+        nst = sum(v.numel() for v in self.st_views)
+        dev = self.z_views[0].device if self.z_views else torch.device("cuda")
+        mine = torch.tensor([nz, nst], dtype=torch.int64, device=dev)
+        sizes = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(sizes, mine, group=group)
+        self.sizes = [(int(s[0].item()), int(s[1].item())) for s in sizes]
+        self.width = max(max(a + b for a, b in self.sizes), 1)
+        self.send = torch.zeros(self.width, dtype=torch.float64, device=dev)
+        self.recv = torch.zeros(world * self.width, dtype=torch.float64, device=dev)
+        self.nz, self.nst = nz, nst
+        L = _bind()
+        L.lgb_listquery_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_uint32),
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_uint32),
+                                           C.c_size_t, C.c_void_p]
+        L.lgb_listquery_create.restype = C.c_void_p
+        L.lgb_listquery_run.argtypes = [C.c_void_p]
+        L.lgb_listquery_fetch.argtypes = [C.c_void_p, C.POINTER(_Result)]
+        L.lgb_listquery_destroy.argtypes = [C.c_void_p]
+        L.lgb_listquery_destroy.restype = None
+        base = self.recv.data_ptr()
+        zp = (C.c_void_p * world)(*[base + r * self.width * 8 for r in range(world)])
+        sp = (C.c_void_p * world)(*[base + (r * self.width + self.sizes[r][0]) * 8
+                                    for r in range(world)])
+        zn = (C.c_uint32 * world)(*[a for a, _ in self.sizes])
+        sn = (C.c_uint32 * world)(*[b for _, b in self.sizes])
+        self._L = L
+        self._h = L.lgb_listquery_create(zp, zn, sp, sn, world,
+                                         C.c_void_p(batch.stream.cuda_stream))
+        if not self._h:
+            raise RuntimeError("lgb_listquery_create failed: " + _err(L))
+
+    def run(self) -> None:
+        """Enqueue pack + all-gather + union query on the batch's stream."""
+        import torch
+
+        with torch.cuda.stream(self.batch.stream):
+            off = 0
+            for v in self.z_views + self.st_views:
+                n = v.numel()
+                if n:
+                    self.send[off:off + n].copy_(v, non_blocking=True)
+                off += n
+            self.dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        if self._L.lgb_listquery_run(self._h):
+            raise RuntimeError("lgb_listquery_run failed: " + _err(self._L))
+
+    def fetch(self) -> Measurement:
+        r = _Result()
+        if self._L.lgb_listquery_fetch(self._h, C.byref(r)):
+            raise RuntimeError("lgb_listquery_fetch failed: " + _err(self._L))
+        return Measurement(r.loudness, r.range, r.rel_threshold, r.sum_abs, r.sum_rel, r.n_abs,
+                           r.n_rel, r.n_shortterm)
+
+    def close(self) -> None:
+        if self._h:
+            self._L.lgb_listquery_destroy(self._h)
+            self._h = None
+
+
+def merge_album_across_ranks(batch: Batch, tracks, dist, world: int) -> Measurement:
+    """One-shot form of AlbumMerge."""
+    m = AlbumMerge(batch, tracks, dist, world)
+    try:
+        m.run()
+        return m.fetch()
+    finally:
+        m.close()
