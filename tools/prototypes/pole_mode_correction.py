@@ -1,6 +1,6 @@
 import numpy as np, scipy.signal as sg, sys
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/scratch')
-from proto import design, basis
+sys.path.insert(0,'/root/repo'); sys.path.insert(0, __import__("os").path.dirname(__file__))
+from chunked_iir_fp32 import design, basis
 f32=np.float32
 def run(rate=44100,secs=10,k=10,W=72,bass=False,dc=0.0,seed=1):
     cf=design(rate); cf['q1']=cf['pb'][1]/cf['pb'][0]; cf['q2']=cf['pb'][2]/cf['pb'][0]
