@@ -546,45 +546,63 @@ __device__ SumCount block_sum_count(double s, unsigned long long n, SumCount* sc
   return r;
 }
 
-// k-th smallest (0-based) among the member short-term energies >= floor_e.
-// Positive doubles order like their 64-bit patterns: 8 passes of 8-bit radix
-// select over the (L2-resident) values.
-__device__ double select_kth(const BlockList* lists, const uint32_t* members, uint32_t count,
-                             double floor_e, unsigned long long k,
-                             unsigned int* hist, unsigned long long* shared_k,
-                             unsigned long long* shared_prefix) {
-  unsigned long long prefix = 0, mask = 0;
+// The k-th smallest (0-based) values, for two ranks at once, among the member
+// short-term energies >= floor_e.  Positive doubles order like their 64-bit
+// patterns: 8 passes of 8-bit radix select over the (L2-resident) values,
+// one 256-bin histogram per rank and pass, bin search by a block-wide scan.
+struct SelectState {
+  unsigned long long prefix[2];
+  unsigned long long k[2];
+};
+
+__device__ void select_two(const BlockList* lists, const uint32_t* members, uint32_t count,
+                           double floor_e, unsigned long long k_lo, unsigned long long k_hi,
+                           unsigned int* hist /* [2][256] */, unsigned int* wsum /* [2][8] */,
+                           SelectState* st, double* out_lo, double* out_hi) {
+  if (threadIdx.x == 0) { st->prefix[0] = st->prefix[1] = 0; st->k[0] = k_lo; st->k[1] = k_hi; }
+  unsigned long long mask = 0;
   for (int shift = 56; shift >= 0; shift -= 8) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) hist[i] = 0;
     __syncthreads();
+    const unsigned long long p0 = st->prefix[0], p1 = st->prefix[1];
     for (uint32_t m = 0; m < count; ++m) {
       const BlockList bl = lists[members[m]];
       for (uint32_t i = threadIdx.x; i < bl.nst; i += blockDim.x) {
         const double e = bl.st[i];
         if (!(e >= floor_e)) continue;
         const unsigned long long bits = (unsigned long long) __double_as_longlong(e);
-        if ((bits & mask) != prefix) continue;
-        atomicAdd(&hist[(bits >> shift) & 0xffull], 1u);
+        const unsigned int digit = (unsigned int) ((bits >> shift) & 0xffull);
+        if ((bits & mask) == p0) atomicAdd(&hist[digit], 1u);
+        if ((bits & mask) == p1) atomicAdd(&hist[256 + digit], 1u);
       }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned long long acc = 0;
-      int b = 0;
-      for (; b < 255; ++b) {
-        if (acc + hist[b] > k) break;
-        acc += hist[b];
-      }
-      *shared_k = k - acc;
-      *shared_prefix = prefix | ((unsigned long long) b << shift);
+    // threads 0..255 own the bins of rank 0, 256..511 those of rank 1
+    const int which = threadIdx.x >> 8, bin = threadIdx.x & 255;
+    const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 7;
+    const unsigned int cnt = hist[threadIdx.x];
+    unsigned int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
     }
+    if (lane == 31) wsum[which * 8 + w] = inc;
     __syncthreads();
-    k = *shared_k;
-    prefix = *shared_prefix;
+    unsigned int base = 0;
+    for (int j = 0; j < w; ++j) base += wsum[which * 8 + j];
+    const unsigned long long excl = (unsigned long long) base + inc - cnt;
+    const unsigned long long kk = st->k[which];
+    __syncthreads();
+    if (cnt && excl <= kk && kk < excl + cnt) {
+      st->k[which] = kk - excl;
+      st->prefix[which] |= (unsigned long long) bin << shift;
+    }
     mask |= 0xffull << shift;
     __syncthreads();
   }
-  return __longlong_as_double((long long) prefix);
+  *out_lo = __longlong_as_double((long long) st->prefix[0]);
+  *out_hi = __longlong_as_double((long long) st->prefix[1]);
 }
 
 __global__ void __launch_bounds__(kQueryThreads)
@@ -592,8 +610,9 @@ query_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ quer
              const uint32_t* __restrict__ members, double abs_gate,
              QueryResult* __restrict__ results) {
   __shared__ SumCount scratch[32];
-  __shared__ unsigned int hist[256];
-  __shared__ unsigned long long sh_k, sh_prefix;
+  __shared__ unsigned int hist[512];
+  __shared__ unsigned int wsum[16];
+  __shared__ SelectState sel;
   const Query q = queries[blockIdx.x];
   const uint32_t* mem = members + q.first;
   QueryResult res;
@@ -653,8 +672,8 @@ query_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ quer
     if (c.n) {
       const unsigned long long k_hi = (unsigned long long) ((double) (c.n - 1) * 0.95 + 0.5);
       const unsigned long long k_lo = (unsigned long long) ((double) (c.n - 1) * 0.1 + 0.5);
-      const double hi = select_kth(lists, mem, q.count, floor_e, k_hi, hist, &sh_k, &sh_prefix);
-      const double lo = select_kth(lists, mem, q.count, floor_e, k_lo, hist, &sh_k, &sh_prefix);
+      double lo, hi;
+      select_two(lists, mem, q.count, floor_e, k_lo, k_hi, hist, wsum, &sel, &lo, &hi);
       res.range = energy_to_lufs(hi) - energy_to_lufs(lo);
     }
   }
