@@ -24,11 +24,21 @@ enum Format : uint32_t { FMT_S16 = 0, FMT_F32 = 1 };
 // Frames the sweep advances per unrolled iteration (= tap count of a 4x
 // true-peak phase, so that window slides by exactly one phase length).
 constexpr int kIter = 12;
-// A staging stage = kItersPerStage iterations.  24 frames of any even-sized
-// frame are a whole number of 16-byte units, which is what cp.async moves.
-constexpr int kItersPerStage = 2;
+// The sweep computes in pairs of iterations (24 frames: a whole number of
+// 16-byte units for any even-sized frame) and stages kPairsPerStage pairs per
+// row and stage from HBM, so that every bulk copy moves a few hundred
+// contiguous bytes.
+constexpr int kPairFrames = 2 * kIter;
+#ifndef LG_PAIRS_PER_STAGE
+#define LG_PAIRS_PER_STAGE 2
+#endif
+#ifndef LG_RING
+#define LG_RING 3
+#endif
+constexpr int kPairsPerStage = LG_PAIRS_PER_STAGE;
+constexpr int kItersPerStage = 2 * kPairsPerStage;
 constexpr int kStageFrames = kIter * kItersPerStage;
-constexpr int kRing = 3;            // cp.async ring depth (stages in flight + 1)
+constexpr int kRing = LG_RING;      // staging ring depth (stages in flight + 1)
 // Longest per-phase tap count (49-tap prototype / factor 2, zero taps dropped).
 constexpr int kMaxTaps = 24;
 // A lane starts on a 16-byte boundary of the track, i.e. on a multiple of
@@ -154,6 +164,7 @@ struct SweepParams {
   uint32_t lpc;            // lanes per chunk = min(channels, 32)
   uint32_t cpw;            // chunks per warp
   uint32_t stage_row_bytes, units, row_stride, stage_bytes, ncopies;
+  uint32_t ring_bytes;     // kRing * stage_bytes: offset of the candidate queue
   uint32_t warp_smem, nwarps;
   const Track* tracks;
   const WarpWork* work;

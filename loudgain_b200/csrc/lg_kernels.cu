@@ -55,21 +55,63 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- TMA bulk copy + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS)
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
+                                             uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LG_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LG_DONE_%=;\n"
+      "bra LG_WAIT_%=;\n"
+      "LG_DONE_%=:\n"
+      "}\n" ::"r"(mbar), "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ int sext_half(uint32_t w, uint32_t sel) {
+  int r;
+  asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(w), "r"(sel));
+  return r;
+}
+
 // Raw samples of one iteration of the lane's channel, from shared memory.
 // rowp -> first frame of the iteration in the lane's row.
 template <int FMT>
 __device__ __forceinline__ void smem_load_iter(const unsigned char* rowp, uint32_t fb, bool stereo,
                                                uint32_t ch, float* x) {
   if (FMT == FMT_S16 && stereo) {
+    // A frame is one 32-bit word (L | R << 16).  One PRMT sign-extends the
+    // lane's half (selector nibble bit 3 = replicate the sign of that byte).
     const uint4* p = reinterpret_cast<const uint4*>(rowp);
-    const uint32_t sh = ch << 4;
+    const uint32_t sel = ch ? 0xBB32u : 0x9910u;
 #pragma unroll
     for (int u = 0; u < kIter / 4; ++u) {
       const uint4 v = p[u];
-      x[4 * u + 0] = (float) (short) (v.x >> sh);
-      x[4 * u + 1] = (float) (short) (v.y >> sh);
-      x[4 * u + 2] = (float) (short) (v.z >> sh);
-      x[4 * u + 3] = (float) (short) (v.w >> sh);
+      x[4 * u + 0] = (float) sext_half(v.x, sel);
+      x[4 * u + 1] = (float) sext_half(v.y, sel);
+      x[4 * u + 2] = (float) sext_half(v.z, sel);
+      x[4 * u + 3] = (float) sext_half(v.w, sel);
     }
   } else if (FMT == FMT_S16) {
     const unsigned char* q = rowp + ch * 2u;
@@ -186,45 +228,56 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
   const bool active = compute && chunk < tr.nchunks;
   const bool stereo = C == 2;
 
-  // ---- staging: copy k of this lane moves unit (idx % units) of row (idx / units)
+  // ---- staging.  Per stage and row one contiguous piece of kStageFrames
+  // frames.  Interior warps (every staged byte inside the track) use TMA bulk
+  // copies completing on an mbarrier, one copy per row issued by the row's
+  // lane; warps at a track boundary use zero-filling 16-byte cp.async.
   const LaneGeom g0 = lane_geometry(frames, L, W, P.aq, ww.first_chunk);
-  const long long warp_byte0 = g0.a * (long long) fb;          // may be negative
   const long long track_bytes = frames * (long long) fb;
-  int32_t soff[KMAX];      // source byte offset at stage 0, relative to warp_byte0
-  uint32_t doff[KMAX];     // destination byte offset inside a stage buffer
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
-    const uint32_t idx = lane + 32u * k;
-    const uint32_t row = idx / P.units;
-    const uint32_t unit = idx - row * P.units;
-    const LaneGeom gr = lane_geometry(frames, L, W, P.aq, ww.first_chunk + row);
-    soff[k] = (int32_t) ((gr.a - g0.a) * (long long) fb) + (int32_t) (unit << 4);
-    doff[k] = idx < P.ncopies ? row * P.row_stride + (unit << 4) : 0xffffffffu;
-  }
   const bool interior = ww.interior != 0;
+  const uint32_t mbar0 = sm_addr + P.ring_bytes;              // kRing mbarriers (8 B each)
+  const LaneGeom grow = lane_geometry(frames, L, W, P.aq, ww.first_chunk + lane);
+  const unsigned char* row_src = pcm + grow.a * (long long) fb;   // valid for lane < cpw
+  if (interior) {
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < kRing; ++i) mbar_init(mbar0 + 8u * i, 1u);
+    }
+    fence_mbar_init();
+    __syncwarp();
+  }
 
   auto prefetch = [&](uint32_t stage) {
-    const uint32_t dst0 = sm_addr + (stage % kRing) * P.stage_bytes;
+    const uint32_t buf = stage % kRing;
+    const uint32_t dst0 = sm_addr + buf * P.stage_bytes;
     const long long adv = (long long) stage * P.stage_row_bytes;
     if (interior) {
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k)
-        if (doff[k] != 0xffffffffu) cp_async16(dst0 + doff[k], pcm + (warp_byte0 + adv + soff[k]));
+      fence_proxy_async();                       // earlier generic reads of this buffer
+      if (lane == 0) mbar_expect_tx(mbar0 + 8u * buf, P.cpw * P.stage_row_bytes);
+      __syncwarp();
+      if (lane < P.cpw)
+        tma_bulk_g2s(dst0 + lane * P.row_stride, row_src + adv, P.stage_row_bytes, mbar0 + 8u * buf);
     } else {
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        if (doff[k] == 0xffffffffu) continue;
-        const long long g = warp_byte0 + adv + soff[k];
+      for (uint32_t idx = lane; idx < P.ncopies; idx += 32u) {
+        const uint32_t row = idx / P.units;
+        const uint32_t unit = idx - row * P.units;
+        const LaneGeom gr = lane_geometry(frames, L, W, P.aq, ww.first_chunk + row);
+        const long long g = gr.a * (long long) fb + adv + (long long) (unit << 4);
         long long ok = g < 0 ? 0 : track_bytes - g;
         ok = ok < 0 ? 0 : (ok > 16 ? 16 : ok);
-        cp_async16_zfill(dst0 + doff[k], pcm + (ok ? g : 0), (uint32_t) ok);
+        cp_async16_zfill(dst0 + row * P.row_stride + (unit << 4), pcm + (ok ? g : 0), (uint32_t) ok);
       }
     }
+  };
+  auto stage_wait = [&](uint32_t stage) {
+    if (interior) mbar_wait(mbar0 + 8u * (stage % kRing), (stage / kRing) & 1u);
+    else cp_async_wait<kRing - 2>();
+    __syncwarp();                // everyone's data has landed; the previous stage is consumed
   };
 
   // ---- candidate queue and per-channel true-peak cells of this warp
   constexpr uint32_t EB = queue_entry_bytes<TPF>();
-  unsigned char* queue = sm + kRing * P.stage_bytes;
+  unsigned char* queue = sm + P.ring_bytes + 64u;
   uint32_t* tpq = reinterpret_cast<uint32_t*>(queue + (NT > 0 ? kQueue * EB : 0));
   tpq[lane] = 0u;
   uint32_t q_count = 0;
@@ -272,109 +325,125 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
   };
 
   const uint32_t niters = (uint32_t) P.niters;
-  const uint32_t nstages = (niters + kItersPerStage - 1) / kItersPerStage;
-  // Stages whose two iterations are both "fast" for every lane of the warp.
+  const uint32_t npairs = (niters + 1u) / 2u;
+  const uint32_t nstages = (npairs + kPairsPerStage - 1) / kPairsPerStage;
+  // Pairs whose two iterations are both "fast" for every lane of the warp.
   const int lfast = ww.lmin_valid < L ? ww.lmin_valid : L;
-  const uint32_t fast_lo = (uint32_t) ((W + P.aq - 1 + kStageFrames - 1) / kStageFrames);
-  const uint32_t fast_hi = (uint32_t) ((W + lfast) / kStageFrames);     // exclusive
-  prefetch(0);
-  cp_async_commit();
-  if (nstages > 1) prefetch(1);
-  cp_async_commit();
+  const uint32_t fast_lo = (uint32_t) ((W + P.aq - 1 + kPairFrames - 1) / kPairFrames);
+  const uint32_t fast_hi = (uint32_t) ((W + lfast) / kPairFrames);     // exclusive
+#pragma unroll
+  for (int i = 0; i < kRing - 1; ++i) {
+    if ((uint32_t) i < nstages) prefetch(i);
+    if (!interior) cp_async_commit();
+  }
 
   for (uint32_t s = 0; s < nstages; ++s) {
-    cp_async_wait<1>();          // this lane's copies of stage s have landed
-    __syncwarp();                // ... everyone's have, and stage s-1 is fully consumed
-    if (s + 2 < nstages) prefetch(s + 2);
-    cp_async_commit();
+    stage_wait(s);
+    if (s + kRing - 1 < nstages) prefetch(s + kRing - 1);
+    if (!interior) cp_async_commit();
     // What other warps have published for this channel.  Polled sparingly (the
     // cells are hot) and only folded into the bound at the next poll, so the
     // L2 round trip is off the critical path.
-    if (NT > 0 && compute && (s & 7u) == 0u) {
+    if (NT > 0 && compute && (s & 3u) == 0u) {
       thr = fmaxf(thr, __uint_as_float(seen.x > seen.y ? seen.x : seen.y));
       seen = __ldcg(reinterpret_cast<const uint2*>(my_peak));
     }
-    const unsigned char* buf = my_row + (s % kRing) * P.stage_bytes;
-    if (s >= fast_lo && s < fast_hi && tp_safe >= (int) ((s + 1) * kStageFrames)) {
-      // ---- both iterations fast: straight-line code, loads first
-      const int f0 = (int) (s * kStageFrames);
-      float x0[kIter], x1[kIter];
-      bool c0 = false, c1 = false;
-      float h1[NT > 0 ? NT : 1];      // history of the second iteration
-      if (compute) {
-        smem_load_iter<FMT>(buf, fb, stereo, ch, x0);
-        smem_load_iter<FMT>(buf + kIter * fb, fb, stereo, ch, x1);
-        const float m0 = iter_fast_energy<TPF>(c, P, x0, f0);
-        const float m1 = iter_fast_energy<TPF>(c, P, x1, f0 + kIter);
-        if (NT > 0) {
-          const float floor_ = fmaxf(thr, c.sp);
-          c0 = P.tp_bound * fmaxf(c.mprev, m0) > floor_;
-          c1 = P.tp_bound * fmaxf(m0, m1) > floor_;
-          c.mprev = m1;
-#pragma unroll
-          for (int i = 0; i < NT - kIter; ++i) h1[i] = c.hist[i + kIter];
-#pragma unroll
-          for (int i = 0; i < kIter; ++i) h1[NT - kIter + i] = x0[i];
-        }
-      }
-      if (NT > 0) {
-        enqueue(c0, c.hist, x0);
-        enqueue(c1, h1, x1);
-        if (compute) {
-          // hist <- last NT frames of (h1, x1)
-#pragma unroll
-          for (int i = 0; i < NT - kIter; ++i) c.hist[i] = h1[i + kIter];
-#pragma unroll
-          for (int i = 0; i < kIter; ++i) c.hist[NT - kIter + i] = x1[i];
-        }
-      }
-    } else {
+    const unsigned char* sbuf = my_row + (s % kRing) * P.stage_bytes;
 #pragma unroll 1
-      for (int it = 0; it < kItersPerStage; ++it) {
-        const uint32_t iter = s * kItersPerStage + it;
-        if (iter >= niters) break;
-        const int f0 = (int) iter * kIter;
-        const int kind = iter_kind(f0, W, P.aq, L, ww.lmin_valid);
-        float x[kIter];
-        bool cand = false;
+    for (uint32_t pr = 0; pr < (uint32_t) kPairsPerStage; ++pr) {
+      const uint32_t pair = s * kPairsPerStage + pr;
+      if (pair >= npairs) break;
+      const unsigned char* buf = sbuf + pr * kPairFrames * fb;
+      if (pair >= fast_lo && pair < fast_hi && tp_safe >= (int) ((pair + 1) * kPairFrames)) {
+        // ---- both iterations fast: straight-line code, loads first
+        const int f0 = (int) (pair * kPairFrames);
+        float x0[kIter], x1[kIter];
+        bool c0 = false, c1 = false;
+        float h1[NT > 0 ? NT : 1];      // history of the second iteration
         if (compute) {
-          smem_load_iter<FMT>(buf + it * kIter * fb, fb, stereo, ch, x);
-          if (kind == ITER_WARM) {
-            iter_warm<TPF>(c, P, x);
-          } else {
-            float m;
-            bool safe = true;
-            if (kind == ITER_FAST) {
-              m = iter_fast_energy<TPF>(c, P, x, f0);
-            } else {
-              iter_masked_energy<TPF>(c, P, x, f0);
-              m = max_abs12(x);
-              safe = f0 + kIter <= tp_safe;
-              if (safe) c.sp = fmaxf(c.sp, m);
-              else {                                       // track end: frame by frame
-                SlowPeakArgs<TPF> a;
+          smem_load_iter<FMT>(buf, fb, stereo, ch, x0);
+          smem_load_iter<FMT>(buf + kIter * fb, fb, stereo, ch, x1);
+#if defined(LG_ABLATE_COMPUTE)
+          const float m0 = max_abs12(x0), m1 = max_abs12(x1);
+          c.sp = fmaxf(c.sp, fmaxf(m0, m1));
+#else
+          const float m0 = iter_fast_energy<TPF>(c, P, x0, f0);
+          const float m1 = iter_fast_energy<TPF>(c, P, x1, f0 + kIter);
+#endif
+#if defined(LG_ABLATE_TP)
+          if (false) {
+#else
+          if (NT > 0) {
+#endif
+            const float floor_ = fmaxf(thr, c.sp);
+            c0 = P.tp_bound * fmaxf(c.mprev, m0) > floor_;
+            c1 = P.tp_bound * fmaxf(m0, m1) > floor_;
+            c.mprev = m1;
 #pragma unroll
-                for (int i = 0; i < NT; ++i) a.win[i] = c.hist[i];
+            for (int i = 0; i < NT - kIter; ++i) h1[i] = c.hist[i + kIter];
 #pragma unroll
-                for (int i = 0; i < kIter; ++i) a.win[NT + i] = x[i];
-                a.f0 = f0; a.f_lo = c.f_lo; a.f_tp = c.f_tp; a.sp = c.sp; a.tp = c.tp;
-                const float2 r = peaks_masked_slow<TPF>(a);
-                c.sp = r.x; c.tp = r.y;
-              }
-            }
-            if (NT > 0) {
-              cand = safe && P.tp_bound * fmaxf(c.mprev, m) > fmaxf(thr, c.sp);
-              c.mprev = m;
-            }
+            for (int i = 0; i < kIter; ++i) h1[NT - kIter + i] = x0[i];
           }
         }
-        if (NT > 0 && kind != ITER_WARM) {
-          enqueue(cand, c.hist, x);
-          if (compute) hist_advance(c, x);
+        if (NT > 0) {
+          enqueue(c0, c.hist, x0);
+          enqueue(c1, h1, x1);
+          if (compute) {
+            // hist <- last NT frames of (h1, x1)
+#pragma unroll
+            for (int i = 0; i < NT - kIter; ++i) c.hist[i] = h1[i + kIter];
+#pragma unroll
+            for (int i = 0; i < kIter; ++i) c.hist[NT - kIter + i] = x1[i];
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int it = 0; it < 2; ++it) {
+          const uint32_t iter = pair * 2u + it;
+          if (iter >= niters) break;
+          const int f0 = (int) iter * kIter;
+          const int kind = iter_kind(f0, W, P.aq, L, ww.lmin_valid);
+          float x[kIter];
+          bool cand = false;
+          if (compute) {
+            smem_load_iter<FMT>(buf + it * kIter * fb, fb, stereo, ch, x);
+            if (kind == ITER_WARM) {
+              iter_warm<TPF>(c, P, x);
+            } else {
+              float m;
+              bool safe = true;
+              if (kind == ITER_FAST) {
+                m = iter_fast_energy<TPF>(c, P, x, f0);
+              } else {
+                iter_masked_energy<TPF>(c, P, x, f0);
+                m = max_abs12(x);
+                safe = f0 + kIter <= tp_safe;
+                if (safe) c.sp = fmaxf(c.sp, m);
+                else {                                       // track end: frame by frame
+                  SlowPeakArgs<TPF> a;
+#pragma unroll
+                  for (int i = 0; i < NT; ++i) a.win[i] = c.hist[i];
+#pragma unroll
+                  for (int i = 0; i < kIter; ++i) a.win[NT + i] = x[i];
+                  a.f0 = f0; a.f_lo = c.f_lo; a.f_tp = c.f_tp; a.sp = c.sp; a.tp = c.tp;
+                  const float2 r = peaks_masked_slow<TPF>(a);
+                  c.sp = r.x; c.tp = r.y;
+                }
+              }
+              if (NT > 0) {
+                cand = safe && P.tp_bound * fmaxf(c.mprev, m) > fmaxf(thr, c.sp);
+                c.mprev = m;
+              }
+            }
+          }
+          if (NT > 0 && kind != ITER_WARM) {
+            enqueue(cand, c.hist, x);
+            if (compute) hist_advance(c, x);
+          }
         }
       }
     }
-    if (NT > 0 && compute && (s & 7u) == 7u) {
+    if (NT > 0 && compute && (s & 3u) == 3u) {
       // publish what this warp knows, if it is news
       const float theirs = __uint_as_float(seen.x > seen.y ? seen.x : seen.y);
       const float mine = fmaxf(fmaxf(c.sp, c.tp), __uint_as_float(tpq[chl]));
@@ -387,7 +456,7 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
       }
     }
   }
-  cp_async_wait<0>();
+  if (!interior) cp_async_wait<0>();
   if (NT > 0 && q_count) flush_round<TPF>(queue, q_count, lane, tpq);
   __syncwarp();
 

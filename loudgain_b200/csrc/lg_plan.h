@@ -61,7 +61,7 @@ struct Plan {
 inline uint32_t sweep_warp_smem_host(uint32_t channels, uint32_t fb, int tpf) {
   const uint32_t cpw = chunks_per_warp(channels);
   const uint32_t units = (kStageFrames * fb) >> 4;
-  uint32_t bytes = kRing * cpw * ((units | 1u) << 4);
+  uint32_t bytes = kRing * cpw * ((units | 1u) << 4) + 64u;   // ring + its mbarriers
   if (tpf) {
     const uint32_t nt = tpf == 4 ? 12u : 24u;
     bytes += 32u * (((((nt + kIter) * 4u + 4u + 15u) >> 4) | 1u) << 4);   // candidate queue
@@ -150,6 +150,7 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, uint64_t t
     sp.row_stride = (sp.units | 1u) << 4;
     sp.stage_bytes = sp.cpw * sp.row_stride;
     sp.ncopies = sp.cpw * sp.units;
+    sp.ring_bytes = kRing * sp.stage_bytes;
     sp.warp_smem = sweep_warp_smem_host(t0.channels, t0.fb, cs.tpf);
     const uint32_t k = (sp.ncopies + 31u) / 32u;
     g.kmax = k <= 3 ? 3 : (k <= 6 ? 6 : 12);
