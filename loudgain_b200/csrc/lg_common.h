@@ -26,11 +26,10 @@ enum Format : uint32_t { FMT_S16 = 0, FMT_F32 = 1 };
 constexpr int kIter = 12;
 // The sweep computes in pairs of iterations (24 frames: a whole number of
 // 16-byte units for any even-sized frame) and stages kPairsPerStage pairs per
-// row and stage from HBM, so that every bulk copy moves a few hundred
-// contiguous bytes.
+// row and stage from HBM.
 constexpr int kPairFrames = 2 * kIter;
 #ifndef LG_PAIRS_PER_STAGE
-#define LG_PAIRS_PER_STAGE 2
+#define LG_PAIRS_PER_STAGE 1
 #endif
 #ifndef LG_RING
 #define LG_RING 3

@@ -55,40 +55,6 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// ---- TMA bulk copy + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS)
-__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
-                                             uint32_t mbar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "LG_WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra LG_DONE_%=;\n"
-      "bra LG_WAIT_%=;\n"
-      "LG_DONE_%=:\n"
-      "}\n" ::"r"(mbar), "r"(parity)
-      : "memory");
-}
-
 __device__ __forceinline__ int sext_half(uint32_t w, uint32_t sel) {
   int r;
   asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(w), "r"(sel));
@@ -138,8 +104,8 @@ __host__ __device__ constexpr uint32_t queue_entry_bytes() {
 
 // Evaluates the n <= 32 queued windows, one per lane.
 template <int TPF>
-__device__ __forceinline__ void flush_round(const unsigned char* queue, uint32_t n, uint32_t lane,
-                                            uint32_t* tpq) {
+__device__ __noinline__ void flush_round(const unsigned char* queue, uint32_t n, uint32_t lane,
+                                         uint32_t* tpq) {
   constexpr int NT = TpTraits<TPF>::kTaps;
   constexpr uint32_t EB = queue_entry_bytes<TPF>();
   __syncwarp();                                   // entries written by other lanes are visible
@@ -229,55 +195,54 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
   const bool stereo = C == 2;
 
   // ---- staging.  Per stage and row one contiguous piece of kStageFrames
-  // frames.  Interior warps (every staged byte inside the track) use TMA bulk
-  // copies completing on an mbarrier, one copy per row issued by the row's
-  // lane; warps at a track boundary use zero-filling 16-byte cp.async.
+  // frames, moved with 16-byte cp.async copies: copy k of a lane moves unit
+  // (idx % units) of row (idx / units), idx = lane + 32 k, so consecutive
+  // lanes fetch consecutive units of one row.  Warps at a track boundary use
+  // the zero-filling form.  (TMA bulk copies were tried: UBLKCP is issued from
+  // uniform registers, i.e. one row at a time, and the rows are too short for
+  // that to pay -- see DESIGN.md.)
   const LaneGeom g0 = lane_geometry(frames, L, W, P.aq, ww.first_chunk);
+  const long long warp_byte0 = g0.a * (long long) fb;          // may be negative
   const long long track_bytes = frames * (long long) fb;
   const bool interior = ww.interior != 0;
-  const uint32_t mbar0 = sm_addr + P.ring_bytes;              // kRing mbarriers (8 B each)
-  const LaneGeom grow = lane_geometry(frames, L, W, P.aq, ww.first_chunk + lane);
-  const unsigned char* row_src = pcm + grow.a * (long long) fb;   // valid for lane < cpw
-  if (interior) {
-    if (lane == 0) {
+  int32_t soff[KMAX];      // source byte offset at stage 0, relative to warp_byte0
+  uint32_t doff[KMAX];     // destination byte offset inside a stage buffer
 #pragma unroll
-      for (int i = 0; i < kRing; ++i) mbar_init(mbar0 + 8u * i, 1u);
-    }
-    fence_mbar_init();
-    __syncwarp();
+  for (int k = 0; k < KMAX; ++k) {
+    const uint32_t idx = lane + 32u * k;
+    const uint32_t row = idx / P.units;
+    const uint32_t unit = idx - row * P.units;
+    const LaneGeom gr = lane_geometry(frames, L, W, P.aq, ww.first_chunk + row);
+    soff[k] = (int32_t) ((gr.a - g0.a) * (long long) fb) + (int32_t) (unit << 4);
+    doff[k] = idx < P.ncopies ? row * P.row_stride + (unit << 4) : 0xffffffffu;
   }
 
   auto prefetch = [&](uint32_t stage) {
-    const uint32_t buf = stage % kRing;
-    const uint32_t dst0 = sm_addr + buf * P.stage_bytes;
+    const uint32_t dst0 = sm_addr + (stage % kRing) * P.stage_bytes;
     const long long adv = (long long) stage * P.stage_row_bytes;
     if (interior) {
-      fence_proxy_async();                       // earlier generic reads of this buffer
-      if (lane == 0) mbar_expect_tx(mbar0 + 8u * buf, P.cpw * P.stage_row_bytes);
-      __syncwarp();
-      if (lane < P.cpw)
-        tma_bulk_g2s(dst0 + lane * P.row_stride, row_src + adv, P.stage_row_bytes, mbar0 + 8u * buf);
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        if (doff[k] != 0xffffffffu) cp_async16(dst0 + doff[k], pcm + (warp_byte0 + adv + soff[k]));
     } else {
-      for (uint32_t idx = lane; idx < P.ncopies; idx += 32u) {
-        const uint32_t row = idx / P.units;
-        const uint32_t unit = idx - row * P.units;
-        const LaneGeom gr = lane_geometry(frames, L, W, P.aq, ww.first_chunk + row);
-        const long long g = gr.a * (long long) fb + adv + (long long) (unit << 4);
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (doff[k] == 0xffffffffu) continue;
+        const long long g = warp_byte0 + adv + soff[k];
         long long ok = g < 0 ? 0 : track_bytes - g;
         ok = ok < 0 ? 0 : (ok > 16 ? 16 : ok);
-        cp_async16_zfill(dst0 + row * P.row_stride + (unit << 4), pcm + (ok ? g : 0), (uint32_t) ok);
+        cp_async16_zfill(dst0 + doff[k], pcm + (ok ? g : 0), (uint32_t) ok);
       }
     }
   };
-  auto stage_wait = [&](uint32_t stage) {
-    if (interior) mbar_wait(mbar0 + 8u * (stage % kRing), (stage / kRing) & 1u);
-    else cp_async_wait<kRing - 2>();
+  auto stage_wait = [&](uint32_t) {
+    cp_async_wait<kRing - 2>();
     __syncwarp();                // everyone's data has landed; the previous stage is consumed
   };
 
   // ---- candidate queue and per-channel true-peak cells of this warp
   constexpr uint32_t EB = queue_entry_bytes<TPF>();
-  unsigned char* queue = sm + P.ring_bytes + 64u;
+  unsigned char* queue = sm + P.ring_bytes;
   uint32_t* tpq = reinterpret_cast<uint32_t*>(queue + (NT > 0 ? kQueue * EB : 0));
   tpq[lane] = 0u;
   uint32_t q_count = 0;
@@ -334,13 +299,13 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
 #pragma unroll
   for (int i = 0; i < kRing - 1; ++i) {
     if ((uint32_t) i < nstages) prefetch(i);
-    if (!interior) cp_async_commit();
+    cp_async_commit();
   }
 
   for (uint32_t s = 0; s < nstages; ++s) {
     stage_wait(s);
     if (s + kRing - 1 < nstages) prefetch(s + kRing - 1);
-    if (!interior) cp_async_commit();
+    cp_async_commit();
     // What other warps have published for this channel.  Polled sparingly (the
     // cells are hot) and only folded into the bound at the next poll, so the
     // L2 round trip is off the critical path.
@@ -456,7 +421,7 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
       }
     }
   }
-  if (!interior) cp_async_wait<0>();
+  cp_async_wait<0>();
   if (NT > 0 && q_count) flush_round<TPF>(queue, q_count, lane, tpq);
   __syncwarp();
 

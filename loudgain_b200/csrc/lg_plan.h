@@ -61,7 +61,7 @@ struct Plan {
 inline uint32_t sweep_warp_smem_host(uint32_t channels, uint32_t fb, int tpf) {
   const uint32_t cpw = chunks_per_warp(channels);
   const uint32_t units = (kStageFrames * fb) >> 4;
-  uint32_t bytes = kRing * cpw * ((units | 1u) << 4) + 64u;   // ring + its mbarriers
+  uint32_t bytes = kRing * cpw * ((units | 1u) << 4);
   if (tpf) {
     const uint32_t nt = tpf == 4 ? 12u : 24u;
     bytes += 32u * (((((nt + kIter) * 4u + 4u + 15u) >> 4) | 1u) << 4);   // candidate queue
