@@ -42,6 +42,15 @@ UNIT = "Gsamples/s"
 WORKLOAD = "cfg2: 12-track 44.1 kHz stereo S16 album per GPU, album mode (-a -k quantities)"
 
 
+def _ncu_traffic():
+    """DRAM bytes per sweep launch from the committed ncu capture of this workload."""
+    path = os.path.join(ROOT, "profiles", "r01_sweep_ncu_summary.json")
+    try:
+        return float(json.load(open(path))["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -322,7 +331,9 @@ def gpu_arm(args):
                                    else "single GPU",
                        "e2e_feed": f"ebur128_add_frames_short, {chunk}-frame calls, pinned host PCM"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                         "frac": achieved / hbm if achieved else None, "traffic": None,
+                         "frac": achieved / hbm if achieved else None, "traffic": _ncu_traffic(),
+                         "traffic_source": "dram__bytes_read+write per launch, ncu --set full, "
+                                           "profiles/r01_sweep_ncu_summary.json",
                          "kernel": "sweep_kernel<S16,4x>", "kernel_ms": sweep_ms,
                          "peak_source": src,
                          "algorithmic_bytes": "2 B per S16 sample, read once (SURVEY 8d)"},

@@ -104,8 +104,8 @@ __host__ __device__ constexpr uint32_t queue_entry_bytes() {
 
 // Evaluates the n <= 32 queued windows, one per lane.
 template <int TPF>
-__device__ __noinline__ void flush_round(const unsigned char* queue, uint32_t n, uint32_t lane,
-                                         uint32_t* tpq) {
+__device__ __forceinline__ void flush_round(const unsigned char* queue, uint32_t n, uint32_t lane,
+                                            uint32_t* tpq) {
   constexpr int NT = TpTraits<TPF>::kTaps;
   constexpr uint32_t EB = queue_entry_bytes<TPF>();
   __syncwarp();                                   // entries written by other lanes are visible
@@ -264,29 +264,38 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
   float published = 0.0f;
   uint2 seen = make_uint2(0u, 0u);   // what other warps had published, as of the last poll
 
-  // Queues the window (hist, x) of every lane that has `cand` set; evaluates
-  // the queue first if it cannot take them all.
-  auto enqueue = [&](bool cand, const float* hist, const float* x) {
-    const unsigned mask = __ballot_sync(0xffffffffu, cand);
-    if (mask == 0u) return;
-    const uint32_t npush = __popc(mask);
-    if (q_count + npush > kQueue) {
-      flush_round<TPF>(queue, q_count, lane, tpq);
-      q_count = 0;
-      thr = fmaxf(thr, __uint_as_float(tpq[chl]));
-    }
-    if (cand) {
-      const uint32_t pos = q_count + __popc(mask & ((1u << lane) - 1u));
-      float4* e = reinterpret_cast<float4*>(queue + pos * EB);
+  // Queues the windows (hist, x) of the lanes whose flag is set, for the two
+  // iterations of a pair; evaluates the queue first if it cannot take them.
+  // The only place the queue is written and flushed from (the loop is kept
+  // rolled so that the evaluation code exists once).
+  auto enqueue2 = [&](bool cand0, const float* hist0, const float* xa, bool cand1,
+                      const float* hist1, const float* xb) {
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const bool cand = half ? cand1 : cand0;
+      const unsigned mask = __ballot_sync(0xffffffffu, cand);
+      if (mask == 0u) continue;
+      const uint32_t npush = __popc(mask);
+      if (q_count + npush > kQueue) {
+        flush_round<TPF>(queue, q_count, lane, tpq);
+        q_count = 0;
+        thr = fmaxf(thr, __uint_as_float(tpq[chl]));
+      }
+      if (cand) {
+        const uint32_t pos = q_count + __popc(mask & ((1u << lane) - 1u));
+        float4* e = reinterpret_cast<float4*>(queue + pos * EB);
 #pragma unroll
-      for (int i = 0; i < NT / 4; ++i)
-        e[i] = make_float4(hist[4 * i], hist[4 * i + 1], hist[4 * i + 2], hist[4 * i + 3]);
+        for (int i = 0; i < NT / 4; ++i)
+          e[i] = half ? make_float4(hist1[4 * i], hist1[4 * i + 1], hist1[4 * i + 2], hist1[4 * i + 3])
+                      : make_float4(hist0[4 * i], hist0[4 * i + 1], hist0[4 * i + 2], hist0[4 * i + 3]);
 #pragma unroll
-      for (int i = 0; i < kIter / 4; ++i)
-        e[NT / 4 + i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-      *reinterpret_cast<uint32_t*>(e + (NT + kIter) / 4) = chl;
+        for (int i = 0; i < kIter / 4; ++i)
+          e[NT / 4 + i] = half ? make_float4(xb[4 * i], xb[4 * i + 1], xb[4 * i + 2], xb[4 * i + 3])
+                               : make_float4(xa[4 * i], xa[4 * i + 1], xa[4 * i + 2], xa[4 * i + 3]);
+        *reinterpret_cast<uint32_t*>(e + (NT + kIter) / 4) = chl;
+      }
+      q_count += npush;
     }
-    q_count += npush;
   };
 
   const uint32_t niters = (uint32_t) P.niters;
@@ -319,12 +328,14 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
       const uint32_t pair = s * kPairsPerStage + pr;
       if (pair >= npairs) break;
       const unsigned char* buf = sbuf + pr * kPairFrames * fb;
+      // Both iterations of the pair leave their samples in x0 / x1 and their
+      // candidate flags in c0 / c1; the queue is fed from one place below.
+      float x0[kIter], x1[kIter];
+      bool c0 = false, c1 = false;
+      bool second = true;               // the pair has a second iteration
       if (pair >= fast_lo && pair < fast_hi && tp_safe >= (int) ((pair + 1) * kPairFrames)) {
         // ---- both iterations fast: straight-line code, loads first
         const int f0 = (int) (pair * kPairFrames);
-        float x0[kIter], x1[kIter];
-        bool c0 = false, c1 = false;
-        float h1[NT > 0 ? NT : 1];      // history of the second iteration
         if (compute) {
           smem_load_iter<FMT>(buf, fb, stereo, ch, x0);
           smem_load_iter<FMT>(buf + kIter * fb, fb, stereo, ch, x1);
@@ -335,45 +346,32 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
           const float m0 = iter_fast_energy<TPF>(c, P, x0, f0);
           const float m1 = iter_fast_energy<TPF>(c, P, x1, f0 + kIter);
 #endif
-#if defined(LG_ABLATE_TP)
-          if (false) {
-#else
+#if !defined(LG_ABLATE_TP)
           if (NT > 0) {
-#endif
             const float floor_ = fmaxf(thr, c.sp);
             c0 = P.tp_bound * fmaxf(c.mprev, m0) > floor_;
             c1 = P.tp_bound * fmaxf(m0, m1) > floor_;
             c.mprev = m1;
-#pragma unroll
-            for (int i = 0; i < NT - kIter; ++i) h1[i] = c.hist[i + kIter];
-#pragma unroll
-            for (int i = 0; i < kIter; ++i) h1[NT - kIter + i] = x0[i];
           }
-        }
-        if (NT > 0) {
-          enqueue(c0, c.hist, x0);
-          enqueue(c1, h1, x1);
-          if (compute) {
-            // hist <- last NT frames of (h1, x1)
-#pragma unroll
-            for (int i = 0; i < NT - kIter; ++i) c.hist[i] = h1[i + kIter];
-#pragma unroll
-            for (int i = 0; i < kIter; ++i) c.hist[NT - kIter + i] = x1[i];
-          }
+#endif
         }
       } else {
-#pragma unroll 1
+        // ---- chunk edges: warm-up and masked iterations, one at a time
+        second = pair * 2u + 1u < niters;
+#pragma unroll
         for (int it = 0; it < 2; ++it) {
-          const uint32_t iter = pair * 2u + it;
-          if (iter >= niters) break;
-          const int f0 = (int) iter * kIter;
+          if (it == 1 && !second) break;
+          float* x = it == 0 ? x0 : x1;
+          const int f0 = (int) (pair * kPairFrames) + it * kIter;
           const int kind = iter_kind(f0, W, P.aq, L, ww.lmin_valid);
-          float x[kIter];
           bool cand = false;
           if (compute) {
             smem_load_iter<FMT>(buf + it * kIter * fb, fb, stereo, ch, x);
             if (kind == ITER_WARM) {
-              iter_warm<TPF>(c, P, x);
+#pragma unroll
+              for (int i = 0; i < kIter; ++i) (void) k_step(c.st, x[i], P);
+              c.mprev = max_abs12(x);
+              c.pd = c.st.d1; c.pw = c.st.w2;
             } else {
               float m;
               bool safe = true;
@@ -386,8 +384,11 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
                 if (safe) c.sp = fmaxf(c.sp, m);
                 else {                                       // track end: frame by frame
                   SlowPeakArgs<TPF> a;
+                  // history of this iteration: c.hist, shifted by x0 for the second one
 #pragma unroll
-                  for (int i = 0; i < NT; ++i) a.win[i] = c.hist[i];
+                  for (int i = 0; i < NT; ++i)
+                    a.win[i] = it == 0 ? c.hist[i]
+                                       : (i < NT - kIter ? c.hist[i + kIter] : x0[i - (NT - kIter)]);
 #pragma unroll
                   for (int i = 0; i < kIter; ++i) a.win[NT + i] = x[i];
                   a.f0 = f0; a.f_lo = c.f_lo; a.f_tp = c.f_tp; a.sp = c.sp; a.tp = c.tp;
@@ -401,9 +402,30 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
               }
             }
           }
-          if (NT > 0 && kind != ITER_WARM) {
-            enqueue(cand, c.hist, x);
-            if (compute) hist_advance(c, x);
+          if (it == 0) c0 = cand; else c1 = cand;
+        }
+        if (!second) {
+#pragma unroll
+          for (int i = 0; i < kIter; ++i) x1[i] = 0.0f;
+        }
+      }
+      if (NT > 0) {
+        // history of the second iteration = last NT frames of (hist, x0)
+        float h1[NT > 0 ? NT : 1];
+#pragma unroll
+        for (int i = 0; i < NT - kIter; ++i) h1[i] = c.hist[i + kIter];
+#pragma unroll
+        for (int i = 0; i < kIter; ++i) h1[NT - kIter + i] = x0[i];
+        enqueue2(c0, c.hist, x0, c1, h1, x1);
+        if (compute) {
+          if (second) {
+#pragma unroll
+            for (int i = 0; i < NT - kIter; ++i) c.hist[i] = h1[i + kIter];
+#pragma unroll
+            for (int i = 0; i < kIter; ++i) c.hist[NT - kIter + i] = x1[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < NT; ++i) c.hist[i] = h1[i];
           }
         }
       }
