@@ -242,6 +242,8 @@ def gpu_arm(args):
     L.lgb_batch_enable_timing.argtypes = [C.c_void_p, C.c_int]
     L.lgb_batch_sweep_ms.argtypes = [C.c_void_p]
     L.lgb_batch_sweep_ms.restype = C.c_double
+    L.lgb_batch_truepeak_ms.argtypes = [C.c_void_p]
+    L.lgb_batch_truepeak_ms.restype = C.c_double
     samples = batch.total_samples
     pcm_bytes = sum(t.numel() * t.element_size() for t, _ in album)
 
@@ -273,13 +275,14 @@ def gpu_arm(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     sweep_ms = L.lgb_batch_sweep_ms(batch._h)
+    tp_ms = L.lgb_batch_truepeak_ms(batch._h)
     L.lgb_batch_enable_timing(batch._h, 0)
     value = samples * world * args.steps / (ms_total * 1e-3) / 1e9
 
     if args.quick:
         if rank == 0:
             print(json.dumps({"quick": True, "value": value, "ms_per_step": ms_total / args.steps,
-                              "sweep_ms": sweep_ms,
+                              "sweep_ms": sweep_ms, "truepeak_ms": tp_ms,
                               "sweep_gsamples": samples / (sweep_ms * 1e-3) / 1e9 if sweep_ms else None}),
                   flush=True)
         batch.close()

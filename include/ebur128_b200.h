@@ -85,6 +85,8 @@ uint64_t lgb_batch_blocks(const lgb_batch* b, size_t track, int kind, const doub
  * the runs fetched since timing was (re-)enabled, 0 if none. */
 void lgb_batch_enable_timing(lgb_batch* b, int on);
 double lgb_batch_sweep_ms(const lgb_batch* b);
+/* ... and the mean time of the true-peak pass that follows the sweep. */
+double lgb_batch_truepeak_ms(const lgb_batch* b);
 
 void lgb_batch_destroy(lgb_batch* b);
 

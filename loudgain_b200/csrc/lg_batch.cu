@@ -85,6 +85,7 @@ struct lgb_batch {
   BlockList* d_lists = nullptr;
   ChunkRec* d_recs = nullptr;
   uint32_t* d_peaks = nullptr;
+  uint32_t* d_mrec = nullptr;
   double* d_echunk = nullptr;
   double* d_eslot = nullptr;
   double* d_zblock = nullptr;
@@ -94,11 +95,11 @@ struct lgb_batch {
   std::vector<QueryResult> h_results;
   std::vector<uint32_t> h_peaks;
   double abs_gate = 0.0;
-  uint32_t launches = 0, sweep_launches = 0;
+  uint32_t launches = 0, sweep_launches = 0, sms = 148;
   // optional sweep timing
   bool timing = false, timed_run_pending = false;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  double sweep_ms_total = 0.0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  double sweep_ms_total = 0.0, tp_ms_total = 0.0;
   uint64_t sweep_runs = 0;
 
   DeviceTables tables() const {
@@ -142,6 +143,7 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
             upload(p.members, &b->d_members, b->stream) &&
             dalloc(&b->d_recs, p.total_recs, b->stream) &&
             dalloc(&b->d_peaks, 2 * p.total_peaks, b->stream) &&
+            dalloc(&b->d_mrec, p.total_mrec, b->stream) &&
             dalloc(&b->d_echunk, p.total_recs, b->stream) &&
             dalloc(&b->d_eslot, p.total_slots, b->stream) &&
             dalloc(&b->d_zblock, p.total_blocks, b->stream) &&
@@ -164,8 +166,11 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
     if (e != cudaSuccess) { set_error("lgb_batch_create", e); ok = false; }
   }
   if (!ok) { lgb_batch_destroy(b); return nullptr; }
+  b->sms = (uint32_t) sms;
   b->sweep_launches = (uint32_t) p.groups.size();
-  b->launches = b->sweep_launches + (p.total_recs ? 1 : 0) + (p.total_slots ? 1 : 0) +
+  uint32_t tp_launches = 0;
+  for (const SweepGroup& g : p.groups) tp_launches += g.tpf ? 1u : 0u;
+  b->launches = b->sweep_launches + tp_launches + (p.total_recs ? 1 : 0) + (p.total_slots ? 1 : 0) +
                 ((p.total_blocks + p.total_st) ? 1 : 0) + (p.queries.empty() ? 0 : 1);
   return b;
 }
@@ -180,10 +185,20 @@ extern "C" LG_EXPORT int lgb_batch_run(lgb_batch* b) {
   for (const SweepGroup& g : p.groups) {
     SweepParams sp = g.params;
     sp.tracks = t.tracks; sp.work = t.work + g.first_warp; sp.recs = t.recs; sp.peaks = t.peaks;
+    sp.mrec = b->d_mrec + g.mrec_base;
     e = launch_sweep(sp, g.format, g.tpf, g.kmax, b->stream);
     if (e != cudaSuccess) { set_error("launch_sweep", e); return 1; }
   }
   if (b->timing) { cudaEventRecord(b->ev1, b->stream); b->timed_run_pending = true; }
+  // The true-peak pass needs the final sample peaks of every track of a group.
+  for (const SweepGroup& g : p.groups) {
+    SweepParams sp = g.params;
+    sp.tracks = t.tracks; sp.work = t.work + g.first_warp; sp.recs = t.recs; sp.peaks = t.peaks;
+    sp.mrec = b->d_mrec + g.mrec_base;
+    e = launch_truepeak(sp, g.format, g.tpf, b->sms, b->stream);
+    if (e != cudaSuccess) { set_error("launch_truepeak", e); return 1; }
+  }
+  if (b->timing) cudaEventRecord(b->ev2, b->stream);
   PostSizes z{(uint32_t) p.tracks.size(), p.total_recs, p.total_slots, p.total_blocks, p.total_st};
   e = launch_post(t, z, b->stream);
   if (e != cudaSuccess) { set_error("launch_post", e); return 1; }
@@ -211,6 +226,7 @@ extern "C" LG_EXPORT int lgb_batch_fetch(lgb_batch* b, lgb_result* track_results
     if (cudaEventElapsedTime(&ms, b->ev0, b->ev1) == cudaSuccess) {
       b->sweep_ms_total += ms;
       ++b->sweep_runs;
+      if (cudaEventElapsedTime(&ms, b->ev1, b->ev2) == cudaSuccess) b->tp_ms_total += ms;
     }
     b->timed_run_pending = false;
   }
@@ -253,15 +269,21 @@ extern "C" LG_EXPORT void lgb_batch_enable_timing(lgb_batch* b, int on) {
   if (on && !b->ev0) {
     cudaEventCreate(&b->ev0);
     cudaEventCreate(&b->ev1);
+    cudaEventCreate(&b->ev2);
   }
   b->timing = on != 0;
   b->timed_run_pending = false;
   b->sweep_ms_total = 0.0;
+  b->tp_ms_total = 0.0;
   b->sweep_runs = 0;
 }
 
 extern "C" LG_EXPORT double lgb_batch_sweep_ms(const lgb_batch* b) {
   return b->sweep_runs ? b->sweep_ms_total / (double) b->sweep_runs : 0.0;
+}
+
+extern "C" LG_EXPORT double lgb_batch_truepeak_ms(const lgb_batch* b) {
+  return b->sweep_runs ? b->tp_ms_total / (double) b->sweep_runs : 0.0;
 }
 
 extern "C" LG_EXPORT int lgb_query_lists(const double* const* z, const uint32_t* nz,
@@ -334,9 +356,9 @@ extern "C" LG_EXPORT void lgb_listquery_destroy(lgb_listquery* q) {
 
 extern "C" LG_EXPORT void lgb_batch_destroy(lgb_batch* b) {
   if (!b) return;
-  if (b->ev0) { cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); }
+  if (b->ev0) { cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); cudaEventDestroy(b->ev2); }
   void* const mem[] = {b->d_tracks, b->d_coefs, b->d_work, b->d_queries, b->d_members, b->d_lists,
-                       b->d_recs, b->d_peaks, b->d_echunk, b->d_eslot, b->d_zblock, b->d_zst,
+                       b->d_recs, b->d_peaks, b->d_mrec, b->d_echunk, b->d_eslot, b->d_zblock, b->d_zst,
                        b->d_results};
   for (void* m : mem) if (m) cudaFreeAsync(m, b->stream);
   delete b;

@@ -159,16 +159,20 @@ struct SweepParams {
   float rot_re, rot_im;
   float tp_bound;          // ||taps||_1 bound used for true-peak screening
   int32_t W, L, niters, aq;
+  uint32_t npairs;         // (niters + 1) / 2: iteration pairs per lane
   uint32_t channels, fb;
   uint32_t lpc;            // lanes per chunk = min(channels, 32)
   uint32_t cpw;            // chunks per warp
   uint32_t stage_row_bytes, units, row_stride, stage_bytes, ncopies;
-  uint32_t ring_bytes;     // kRing * stage_bytes: offset of the candidate queue
   uint32_t warp_smem, nwarps;
   const Track* tracks;
   const WarpWork* work;
   ChunkRec* recs;
   uint32_t* peaks;
+  // Iteration maxima for the true-peak pass: one word per (warp, pair, lane),
+  // index (warp * npairs + pair) * 32 + lane, two 16-bit codes each
+  // (lg_sweep.cuh: peak_code).  Unused when the rate has no interpolator.
+  uint32_t* mrec;
 };
 
 // ---- lane geometry ---------------------------------------------------------

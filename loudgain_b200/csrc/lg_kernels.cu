@@ -27,18 +27,18 @@ namespace lg {
 //
 //  * it streams its rows HBM -> shared memory with 16-byte cp.async copies laid
 //    out so that consecutive lanes fetch consecutive units of one row
-//    (coalesced), kRing stages of 24 frames deep; rows start on 16-byte
-//    boundaries of the track and the row stride is an odd number of units, so
-//    128-bit shared loads of different rows do not collide;
-//  * every lane filters its channel (FP32) and accumulates energy and the
-//    correction cross terms;
-//  * true peak: a 12-frame window is evaluated only if ||c||_1 * max|x| over
-//    the window exceeds what the channel's peak is already known to reach
-//    (own maximum so far, the warp's, and the track-wide value other warps
-//    have published).  Such candidate windows are copied into a per-warp
-//    queue and evaluated 32 at a time, one window per lane, so the FIR runs
-//    dense instead of divergent.  The maximum is identical to evaluating
-//    every window (see lg_sweep.cuh).
+//    (coalesced), kRing stages deep; rows start on 16-byte boundaries of the
+//    track and the row stride is an odd number of units, so 128-bit shared
+//    loads of different rows do not collide;
+//  * every lane filters its channel (FP32) and accumulates energy, the
+//    correction cross terms and the sample peak; the interior of a chunk runs
+//    as straight-line code over 24 frames, the few warm-up / edge iterations
+//    go through a rolled loop;
+//  * true peak is NOT evaluated here: the lane only records max |x| of each
+//    12-frame iteration (16-bit code, one coalesced 128-byte store per warp
+//    and pair).  truepeak_kernel evaluates the polyphase FIR afterwards, only
+//    on the iterations whose bound ||c||_1 * max|x| exceeds the channel's
+//    final sample peak.
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -61,14 +61,25 @@ __device__ __forceinline__ int sext_half(uint32_t w, uint32_t sel) {
   return r;
 }
 
+// How a lane finds its samples in a staged row.
+enum RowLayout : int {
+  ROW_S16_STEREO = 0,   // frame = one 32-bit word (L | R << 16)
+  ROW_S16_MONO = 1,     // two frames per word
+  ROW_S16_ANY = 2,      // 16-bit loads, stride = frame bytes
+  ROW_F32_MONO = 3,
+  ROW_F32_STEREO = 4,
+  ROW_F32_ANY = 5,
+};
+
 // Raw samples of one iteration of the lane's channel, from shared memory.
-// rowp -> first frame of the iteration in the lane's row.
-template <int FMT>
-__device__ __forceinline__ void smem_load_iter(const unsigned char* rowp, uint32_t fb, bool stereo,
-                                               uint32_t ch, float* x) {
-  if (FMT == FMT_S16 && stereo) {
-    // A frame is one 32-bit word (L | R << 16).  One PRMT sign-extends the
-    // lane's half (selector nibble bit 3 = replicate the sign of that byte).
+// rowp -> first frame of the iteration in the lane's row (16-byte aligned for
+// the vector layouts: iterations are 12 frames).
+template <int LAYOUT>
+__device__ __forceinline__ void smem_load_iter(const unsigned char* rowp, uint32_t fb, uint32_t ch,
+                                               float* x) {
+  if (LAYOUT == ROW_S16_STEREO) {
+    // One PRMT sign-extends the lane's half of a frame word (selector nibble
+    // bit 3 = replicate the sign of that byte).
     const uint4* p = reinterpret_cast<const uint4*>(rowp);
     const uint32_t sel = ch ? 0xBB32u : 0x9910u;
 #pragma unroll
@@ -79,10 +90,36 @@ __device__ __forceinline__ void smem_load_iter(const unsigned char* rowp, uint32
       x[4 * u + 2] = (float) sext_half(v.z, sel);
       x[4 * u + 3] = (float) sext_half(v.w, sel);
     }
-  } else if (FMT == FMT_S16) {
+  } else if (LAYOUT == ROW_S16_MONO) {
+    // 12 frames = 24 bytes: an 8-byte-aligned window of three 64-bit loads
+    const uint2* p = reinterpret_cast<const uint2*>(rowp);
+#pragma unroll
+    for (int u = 0; u < kIter / 4; ++u) {
+      const uint2 v = p[u];
+      x[4 * u + 0] = (float) sext_half(v.x, 0x9910u);
+      x[4 * u + 1] = (float) sext_half(v.x, 0xBB32u);
+      x[4 * u + 2] = (float) sext_half(v.y, 0x9910u);
+      x[4 * u + 3] = (float) sext_half(v.y, 0xBB32u);
+    }
+  } else if (LAYOUT == ROW_S16_ANY) {
     const unsigned char* q = rowp + ch * 2u;
 #pragma unroll
-    for (int i = 0; i < kIter; ++i) x[i] = (float) *reinterpret_cast<const short*>(q + i * fb);
+    for (int i = 0; i < kIter; ++i) x[i] = (float) (int) *reinterpret_cast<const short*>(q + i * fb);
+  } else if (LAYOUT == ROW_F32_MONO) {
+    const float4* p = reinterpret_cast<const float4*>(rowp);
+#pragma unroll
+    for (int u = 0; u < kIter / 4; ++u) {
+      const float4 v = p[u];
+      x[4 * u] = v.x; x[4 * u + 1] = v.y; x[4 * u + 2] = v.z; x[4 * u + 3] = v.w;
+    }
+  } else if (LAYOUT == ROW_F32_STEREO) {
+    const float4* p = reinterpret_cast<const float4*>(rowp);
+#pragma unroll
+    for (int u = 0; u < kIter / 2; ++u) {
+      const float4 v = p[u];
+      x[2 * u] = ch ? v.y : v.x;
+      x[2 * u + 1] = ch ? v.w : v.z;
+    }
   } else {
     const unsigned char* q = rowp + ch * 4u;
 #pragma unroll
@@ -91,86 +128,12 @@ __device__ __forceinline__ void smem_load_iter(const unsigned char* rowp, uint32
 }
 
 #ifndef LG_SWEEP_MINBLOCKS
-#define LG_SWEEP_MINBLOCKS 4
+#define LG_SWEEP_MINBLOCKS 6
 #endif
 
-constexpr uint32_t kQueue = 32;     // candidate windows a warp can hold (one dense round)
-
-template <int TPF>
-__host__ __device__ constexpr uint32_t queue_entry_bytes() {
-  // window floats + one meta word, rounded up to an odd number of 16-byte units
-  return ((((TpTraits<TPF>::kTaps + kIter) * 4u + 4u + 15u) >> 4) | 1u) << 4;
-}
-
-// Evaluates the n <= 32 queued windows, one per lane.
-template <int TPF>
-__device__ __forceinline__ void flush_round(const unsigned char* queue, uint32_t n, uint32_t lane,
-                                            uint32_t* tpq) {
-  constexpr int NT = TpTraits<TPF>::kTaps;
-  constexpr uint32_t EB = queue_entry_bytes<TPF>();
-  __syncwarp();                                   // entries written by other lanes are visible
-  if (lane < n) {
-    const unsigned char* e = queue + lane * EB;
-    float win[NT + kIter];
-    const float4* p = reinterpret_cast<const float4*>(e);
-#pragma unroll
-    for (int i = 0; i < (NT + kIter) / 4; ++i) {
-      const float4 v = p[i];
-      win[4 * i] = v.x; win[4 * i + 1] = v.y; win[4 * i + 2] = v.z; win[4 * i + 3] = v.w;
-    }
-    const uint32_t slot = *reinterpret_cast<const uint32_t*>(e + (NT + kIter) * 4);
-    atomicMax(tpq + slot, __float_as_uint(tp_window<TPF>(win)));
-  }
-  __syncwarp();
-}
-
-// Peaks of a track-end iteration, frame by frame.  Rare (last warp of a
-// track), so it is kept out of line to keep the hot loop small; everything
-// goes in and out by value so that the lane state stays in registers.
-template <int TPF>
-struct SlowPeakArgs {
-  float win[TpTraits<TPF>::kTaps + kIter];
-  int f0, f_lo, f_tp;
-  float sp, tp;
-};
-
-template <int TPF>
-__device__ __noinline__ float2 peaks_masked_slow(const SlowPeakArgs<TPF> a) {
-  constexpr int NT = TpTraits<TPF>::kTaps;
-  float sp = a.sp, tp = a.tp;
-#pragma unroll 1
-  for (int i = 0; i < kIter; ++i) {
-    const int f = a.f0 + i;
-    if (f >= a.f_lo && f < a.f_tp) {
-      sp = fmaxf(sp, fabsf(a.win[NT + i]));
-      if (NT > 0) {
-        // same arithmetic as tp_frame, with a run-time window position
-        float m = 0.0f;
-        if (TPF == 4) {
-#pragma unroll
-          for (int p = 0; p < 3; ++p) {
-            float acc = 0.0f;
-#pragma unroll
-            for (int t = 0; t < 12; ++t) acc = fmaf(a.win[NT + i - t], kTp4f[p][t], acc);
-            m = fmaxf(m, fabsf(acc));
-          }
-        } else {
-          float acc = 0.0f;
-#pragma unroll
-          for (int t = 0; t < 24; ++t) acc = fmaf(a.win[NT + i - t], kTp2f[0][t], acc);
-          m = fabsf(acc);
-        }
-        tp = fmaxf(tp, m);
-      }
-    }
-  }
-  return make_float2(sp, tp);
-}
-
-template <int FMT, int TPF, int KMAX>
+template <int LAYOUT, bool TP, int KMAX>
 __global__ void __launch_bounds__(kSweepThreads, LG_SWEEP_MINBLOCKS)
 sweep_kernel(const __grid_constant__ SweepParams P) {
-  constexpr int NT = TpTraits<TPF>::kTaps;
   extern __shared__ __align__(16) unsigned char smem_all[];
   const uint32_t wic = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31u;
@@ -192,15 +155,12 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
   const uint32_t chunk = ww.first_chunk + slot;
   const bool compute = slot < P.cpw && ch < C;
   const bool active = compute && chunk < tr.nchunks;
-  const bool stereo = C == 2;
 
   // ---- staging.  Per stage and row one contiguous piece of kStageFrames
   // frames, moved with 16-byte cp.async copies: copy k of a lane moves unit
   // (idx % units) of row (idx / units), idx = lane + 32 k, so consecutive
   // lanes fetch consecutive units of one row.  Warps at a track boundary use
-  // the zero-filling form.  (TMA bulk copies were tried: UBLKCP is issued from
-  // uniform registers, i.e. one row at a time, and the rows are too short for
-  // that to pay -- see DESIGN.md.)
+  // the zero-filling form.
   const LaneGeom g0 = lane_geometry(frames, L, W, P.aq, ww.first_chunk);
   const long long warp_byte0 = g0.a * (long long) fb;          // may be negative
   const long long track_bytes = frames * (long long) fb;
@@ -221,9 +181,10 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
     const uint32_t dst0 = sm_addr + (stage % kRing) * P.stage_bytes;
     const long long adv = (long long) stage * P.stage_row_bytes;
     if (interior) {
+      const unsigned char* src0 = pcm + (warp_byte0 + adv);
 #pragma unroll
       for (int k = 0; k < KMAX; ++k)
-        if (doff[k] != 0xffffffffu) cp_async16(dst0 + doff[k], pcm + (warp_byte0 + adv + soff[k]));
+        if (doff[k] != 0xffffffffu) cp_async16(dst0 + doff[k], src0 + soff[k]);
     } else {
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
@@ -235,71 +196,16 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
       }
     }
   };
-  auto stage_wait = [&](uint32_t) {
-    cp_async_wait<kRing - 2>();
-    __syncwarp();                // everyone's data has landed; the previous stage is consumed
-  };
-
-  // ---- candidate queue and per-channel true-peak cells of this warp
-  constexpr uint32_t EB = queue_entry_bytes<TPF>();
-  unsigned char* queue = sm + P.ring_bytes;
-  uint32_t* tpq = reinterpret_cast<uint32_t*>(queue + (NT > 0 ? kQueue * EB : 0));
-  tpq[lane] = 0u;
-  uint32_t q_count = 0;
-  // Frames at or beyond this lane-local index may lie past the end of the
-  // track for some lane of the warp: true peak is then masked frame by frame.
-  const LaneGeom glast = lane_geometry(frames, L, W, P.aq, ww.first_chunk + P.cpw - 1);
-  const long long tp_safe_ll = frames - glast.a;
-  const int tp_safe = tp_safe_ll > 0x3fffffff ? 0x3fffffff : (int) tp_safe_ll;
 
   // ---- lane state
   const LaneGeom geo = lane_geometry(frames, L, W, P.aq, chunk);
-  LaneCtx<TPF> c;
+  LaneCtx c;
   lane_init(c, W, L, geo);
   const unsigned char* my_row = sm + slot * P.row_stride;
-  uint32_t* my_peak = P.peaks + 2 * (tr.peak_base + (compute ? ch : 0u));
-  const unsigned peers = __match_any_sync(0xffffffffu, compute ? chl : 0xffffu);
-  const bool leader = compute && lane == (uint32_t) (__ffs(peers) - 1);
-  float thr = 0.0f;        // the channel's peak is known to reach at least this (raw units)
-  float published = 0.0f;
-  uint2 seen = make_uint2(0u, 0u);   // what other warps had published, as of the last poll
-
-  // Queues the windows (hist, x) of the lanes whose flag is set, for the two
-  // iterations of a pair; evaluates the queue first if it cannot take them.
-  // The only place the queue is written and flushed from (the loop is kept
-  // rolled so that the evaluation code exists once).
-  auto enqueue2 = [&](bool cand0, const float* hist0, const float* xa, bool cand1,
-                      const float* hist1, const float* xb) {
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      const bool cand = half ? cand1 : cand0;
-      const unsigned mask = __ballot_sync(0xffffffffu, cand);
-      if (mask == 0u) continue;
-      const uint32_t npush = __popc(mask);
-      if (q_count + npush > kQueue) {
-        flush_round<TPF>(queue, q_count, lane, tpq);
-        q_count = 0;
-        thr = fmaxf(thr, __uint_as_float(tpq[chl]));
-      }
-      if (cand) {
-        const uint32_t pos = q_count + __popc(mask & ((1u << lane) - 1u));
-        float4* e = reinterpret_cast<float4*>(queue + pos * EB);
-#pragma unroll
-        for (int i = 0; i < NT / 4; ++i)
-          e[i] = half ? make_float4(hist1[4 * i], hist1[4 * i + 1], hist1[4 * i + 2], hist1[4 * i + 3])
-                      : make_float4(hist0[4 * i], hist0[4 * i + 1], hist0[4 * i + 2], hist0[4 * i + 3]);
-#pragma unroll
-        for (int i = 0; i < kIter / 4; ++i)
-          e[NT / 4 + i] = half ? make_float4(xb[4 * i], xb[4 * i + 1], xb[4 * i + 2], xb[4 * i + 3])
-                               : make_float4(xa[4 * i], xa[4 * i + 1], xa[4 * i + 2], xa[4 * i + 3]);
-        *reinterpret_cast<uint32_t*>(e + (NT + kIter) / 4) = chl;
-      }
-      q_count += npush;
-    }
-  };
+  uint32_t* const mrec = P.mrec + (size_t) warp * P.npairs * 32u + lane;
 
   const uint32_t niters = (uint32_t) P.niters;
-  const uint32_t npairs = (niters + 1u) / 2u;
+  const uint32_t npairs = P.npairs;
   const uint32_t nstages = (npairs + kPairsPerStage - 1) / kPairsPerStage;
   // Pairs whose two iterations are both "fast" for every lane of the warp.
   const int lfast = ww.lmin_valid < L ? ww.lmin_valid : L;
@@ -312,140 +218,44 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
   }
 
   for (uint32_t s = 0; s < nstages; ++s) {
-    stage_wait(s);
+    cp_async_wait<kRing - 2>();
+    __syncwarp();                // everyone's data has landed; the previous stage is consumed
     if (s + kRing - 1 < nstages) prefetch(s + kRing - 1);
     cp_async_commit();
-    // What other warps have published for this channel.  Polled sparingly (the
-    // cells are hot) and only folded into the bound at the next poll, so the
-    // L2 round trip is off the critical path.
-    if (NT > 0 && compute && (s & 3u) == 0u) {
-      thr = fmaxf(thr, __uint_as_float(seen.x > seen.y ? seen.x : seen.y));
-      seen = __ldcg(reinterpret_cast<const uint2*>(my_peak));
-    }
     const unsigned char* sbuf = my_row + (s % kRing) * P.stage_bytes;
 #pragma unroll 1
     for (uint32_t pr = 0; pr < (uint32_t) kPairsPerStage; ++pr) {
       const uint32_t pair = s * kPairsPerStage + pr;
       if (pair >= npairs) break;
       const unsigned char* buf = sbuf + pr * kPairFrames * fb;
-      // Both iterations of the pair leave their samples in x0 / x1 and their
-      // candidate flags in c0 / c1; the queue is fed from one place below.
-      float x0[kIter], x1[kIter];
-      bool c0 = false, c1 = false;
-      bool second = true;               // the pair has a second iteration
-      if (pair >= fast_lo && pair < fast_hi && tp_safe >= (int) ((pair + 1) * kPairFrames)) {
-        // ---- both iterations fast: straight-line code, loads first
-        const int f0 = (int) (pair * kPairFrames);
+      float m0 = 0.0f, m1 = 0.0f;
+      if (pair >= fast_lo && pair < fast_hi) {
+        // ---- interior of the chunk: straight-line code, loads first
         if (compute) {
-          smem_load_iter<FMT>(buf, fb, stereo, ch, x0);
-          smem_load_iter<FMT>(buf + kIter * fb, fb, stereo, ch, x1);
-#if defined(LG_ABLATE_COMPUTE)
-          const float m0 = max_abs12(x0), m1 = max_abs12(x1);
-          c.sp = fmaxf(c.sp, fmaxf(m0, m1));
-#else
-          const float m0 = iter_fast_energy<TPF>(c, P, x0, f0);
-          const float m1 = iter_fast_energy<TPF>(c, P, x1, f0 + kIter);
-#endif
-#if !defined(LG_ABLATE_TP)
-          if (NT > 0) {
-            const float floor_ = fmaxf(thr, c.sp);
-            c0 = P.tp_bound * fmaxf(c.mprev, m0) > floor_;
-            c1 = P.tp_bound * fmaxf(m0, m1) > floor_;
-            c.mprev = m1;
-          }
-#endif
+          float x0[kIter], x1[kIter];
+          smem_load_iter<LAYOUT>(buf, fb, ch, x0);
+          smem_load_iter<LAYOUT>(buf + kIter * fb, fb, ch, x1);
+          const int f0 = (int) (pair * kPairFrames);
+          m0 = iter_fast(c, P, x0, f0);
+          m1 = iter_fast(c, P, x1, f0 + kIter);
         }
-      } else {
+      } else if (compute) {
         // ---- chunk edges: warm-up and masked iterations, one at a time
-        second = pair * 2u + 1u < niters;
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-          if (it == 1 && !second) break;
-          float* x = it == 0 ? x0 : x1;
-          const int f0 = (int) (pair * kPairFrames) + it * kIter;
-          const int kind = iter_kind(f0, W, P.aq, L, ww.lmin_valid);
-          bool cand = false;
-          if (compute) {
-            smem_load_iter<FMT>(buf + it * kIter * fb, fb, stereo, ch, x);
-            if (kind == ITER_WARM) {
-#pragma unroll
-              for (int i = 0; i < kIter; ++i) (void) k_step(c.st, x[i], P);
-              c.mprev = max_abs12(x);
-              c.pd = c.st.d1; c.pw = c.st.w2;
-            } else {
-              float m;
-              bool safe = true;
-              if (kind == ITER_FAST) {
-                m = iter_fast_energy<TPF>(c, P, x, f0);
-              } else {
-                iter_masked_energy<TPF>(c, P, x, f0);
-                m = max_abs12(x);
-                safe = f0 + kIter <= tp_safe;
-                if (safe) c.sp = fmaxf(c.sp, m);
-                else {                                       // track end: frame by frame
-                  SlowPeakArgs<TPF> a;
-                  // history of this iteration: c.hist, shifted by x0 for the second one
-#pragma unroll
-                  for (int i = 0; i < NT; ++i)
-                    a.win[i] = it == 0 ? c.hist[i]
-                                       : (i < NT - kIter ? c.hist[i + kIter] : x0[i - (NT - kIter)]);
-#pragma unroll
-                  for (int i = 0; i < kIter; ++i) a.win[NT + i] = x[i];
-                  a.f0 = f0; a.f_lo = c.f_lo; a.f_tp = c.f_tp; a.sp = c.sp; a.tp = c.tp;
-                  const float2 r = peaks_masked_slow<TPF>(a);
-                  c.sp = r.x; c.tp = r.y;
-                }
-              }
-              if (NT > 0) {
-                cand = safe && P.tp_bound * fmaxf(c.mprev, m) > fmaxf(thr, c.sp);
-                c.mprev = m;
-              }
-            }
-          }
-          if (it == 0) c0 = cand; else c1 = cand;
-        }
-        if (!second) {
-#pragma unroll
-          for (int i = 0; i < kIter; ++i) x1[i] = 0.0f;
+#pragma unroll 1
+        for (uint32_t it = 0; it < 2u; ++it) {
+          const uint32_t iter = pair * 2u + it;
+          if (iter >= niters) break;
+          const int f0 = (int) (iter * kIter);
+          float x[kIter];
+          smem_load_iter<LAYOUT>(buf + it * kIter * fb, fb, ch, x);
+          const float m = f0 + kIter <= W ? iter_warm(c, P, x) : iter_masked(c, P, x, f0);
+          if (it == 0) m0 = m; else m1 = m;
         }
       }
-      if (NT > 0) {
-        // history of the second iteration = last NT frames of (hist, x0)
-        float h1[NT > 0 ? NT : 1];
-#pragma unroll
-        for (int i = 0; i < NT - kIter; ++i) h1[i] = c.hist[i + kIter];
-#pragma unroll
-        for (int i = 0; i < kIter; ++i) h1[NT - kIter + i] = x0[i];
-        enqueue2(c0, c.hist, x0, c1, h1, x1);
-        if (compute) {
-          if (second) {
-#pragma unroll
-            for (int i = 0; i < NT - kIter; ++i) c.hist[i] = h1[i + kIter];
-#pragma unroll
-            for (int i = 0; i < kIter; ++i) c.hist[NT - kIter + i] = x1[i];
-          } else {
-#pragma unroll
-            for (int i = 0; i < NT; ++i) c.hist[i] = h1[i];
-          }
-        }
-      }
-    }
-    if (NT > 0 && compute && (s & 3u) == 3u) {
-      // publish what this warp knows, if it is news
-      const float theirs = __uint_as_float(seen.x > seen.y ? seen.x : seen.y);
-      const float mine = fmaxf(fmaxf(c.sp, c.tp), __uint_as_float(tpq[chl]));
-      thr = fmaxf(thr, mine);
-      if (mine > published && mine > theirs) {
-        // goes into the true-peak cell: the reported true peak is the max of
-        // both cells anyway (ebur128_true_peak folds the sample peak in)
-        atomicMax(my_peak + 1, __float_as_uint(mine));
-        published = mine;
-      }
+      if (TP) mrec[(size_t) pair * 32u] = peak_code(m0) | (peak_code(m1) << 16);
     }
   }
   cp_async_wait<0>();
-  if (NT > 0 && q_count) flush_round<TPF>(queue, q_count, lane, tpq);
-  __syncwarp();
 
   if (active) {
     ChunkRec v;
@@ -453,54 +263,236 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
     v.pd = c.pd; v.pw = c.pw; v.qd = c.qd; v.qw = c.qw;
     P.recs[tr.rec_base + (uint64_t) chunk * C + ch] = v;
   }
-  // Peaks: non-negative floats order like their bit patterns.  Reduce over
-  // the lanes of the warp that hold the same channel, one atomic each.
-  uint32_t spb = __reduce_max_sync(peers, active ? __float_as_uint(c.sp) : 0u);
-  uint32_t tpb = __reduce_max_sync(peers, active ? __float_as_uint(c.tp) : 0u);
-  if (leader) {
-    if (NT > 0) { const uint32_t q = tpq[chl]; tpb = tpb > q ? tpb : q; }
-    atomicMax(my_peak + 0, spb);
-    atomicMax(my_peak + 1, tpb);
-  }
+  // Sample peak: non-negative floats order like their bit patterns.  Reduce
+  // over the lanes of the warp that hold the same channel, one atomic each.
+  const unsigned peers = __match_any_sync(0xffffffffu, compute ? chl : 0xffffu);
+  const uint32_t spb = __reduce_max_sync(peers, active ? __float_as_uint(c.sp) : 0u);
+  if (compute && lane == (uint32_t) (__ffs(peers) - 1))
+    atomicMax(P.peaks + 2 * (tr.peak_base + ch), spb);
 }
 
-template <int FMT, int TPF, int KMAX>
+template <int LAYOUT, bool TP, int KMAX>
 static cudaError_t launch_sweep_k(const SweepParams& p, cudaStream_t stream) {
   const uint32_t wpb = kSweepThreads / 32;
   const uint32_t blocks = (p.nwarps + wpb - 1) / wpb;
   const size_t smem = (size_t) p.warp_smem * wpb;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<FMT, TPF, KMAX>,
+    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<LAYOUT, TP, KMAX>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(sweep_kernel<FMT, TPF, KMAX>,
+      e = cudaFuncSetAttribute(sweep_kernel<LAYOUT, TP, KMAX>,
                                cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  sweep_kernel<FMT, TPF, KMAX><<<blocks, kSweepThreads, smem, stream>>>(p);
+  sweep_kernel<LAYOUT, TP, KMAX><<<blocks, kSweepThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
-template <int FMT, int TPF>
+template <int LAYOUT, bool TP>
 static cudaError_t launch_sweep_t(const SweepParams& p, uint32_t kmax, cudaStream_t stream) {
-  if (kmax <= 3) return launch_sweep_k<FMT, TPF, 3>(p, stream);
-  if (kmax <= 6) return launch_sweep_k<FMT, TPF, 6>(p, stream);
-  return launch_sweep_k<FMT, TPF, 12>(p, stream);
+  if (kmax <= 3) return launch_sweep_k<LAYOUT, TP, 3>(p, stream);
+  if (kmax <= 6) return launch_sweep_k<LAYOUT, TP, 6>(p, stream);
+  return launch_sweep_k<LAYOUT, TP, 12>(p, stream);
+}
+
+template <int LAYOUT>
+static cudaError_t launch_sweep_l(const SweepParams& p, int tpf, uint32_t kmax, cudaStream_t stream) {
+  return tpf ? launch_sweep_t<LAYOUT, true>(p, kmax, stream)
+             : launch_sweep_t<LAYOUT, false>(p, kmax, stream);
 }
 
 cudaError_t launch_sweep(const SweepParams& p, uint32_t format, int tpf, uint32_t kmax,
                          cudaStream_t stream) {
   if (p.nwarps == 0) return cudaSuccess;
   if (format == FMT_S16) {
-    if (tpf == 4) return launch_sweep_t<FMT_S16, 4>(p, kmax, stream);
-    if (tpf == 2) return launch_sweep_t<FMT_S16, 2>(p, kmax, stream);
-    return launch_sweep_t<FMT_S16, 0>(p, kmax, stream);
+    if (p.channels == 2) return launch_sweep_l<ROW_S16_STEREO>(p, tpf, kmax, stream);
+    if (p.channels == 1) return launch_sweep_l<ROW_S16_MONO>(p, tpf, kmax, stream);
+    return launch_sweep_l<ROW_S16_ANY>(p, tpf, kmax, stream);
   }
-  if (tpf == 4) return launch_sweep_t<FMT_F32, 4>(p, kmax, stream);
-  if (tpf == 2) return launch_sweep_t<FMT_F32, 2>(p, kmax, stream);
-  return launch_sweep_t<FMT_F32, 0>(p, kmax, stream);
+  if (p.channels == 2) return launch_sweep_l<ROW_F32_STEREO>(p, tpf, kmax, stream);
+  if (p.channels == 1) return launch_sweep_l<ROW_F32_MONO>(p, tpf, kmax, stream);
+  return launch_sweep_l<ROW_F32_ANY>(p, tpf, kmax, stream);
+}
+
+// -------------------------------------------------------------- true peak
+//
+// Second pass over the iteration maxima the sweep left behind.  The true peak
+// is a maximum, and a polyphase output cannot exceed ||c||_1 * max|x| over
+// its taps' window; the channel's true peak is at least its sample peak
+// (which is final by now).  So only iterations whose bound exceeds the
+// channel's current peak can matter -- a few percent of the audio on
+// programme material.  CTAs scan tiles of the code array, collect those
+// iterations in shared memory and evaluate them densely, one iteration per
+// thread, re-reading their 24 (36) frames from the PCM (L2 / HBM).  The
+// result is identical to evaluating every frame.
+
+constexpr int kTpThreads = 128;
+constexpr int kTpWarps = kTpThreads / 32;
+constexpr int kTpBatch = 4;                             // pairs a lane has in flight
+constexpr int kTpSegment = 16;                          // pairs per work item (one sweep lane row)
+constexpr int kTpCap = 32 + 2 * kTpBatch * 32;          // per-warp queue: remainder + one batch
+
+template <int FMT>
+__device__ __forceinline__ float pcm_sample(const unsigned char* p) {
+  if (FMT == FMT_S16) return (float) (int) *reinterpret_cast<const short*>(p);
+  return *reinterpret_cast<const float*>(p);
+}
+
+// A sweep lane's place in its track.
+struct TpLane {
+  uint32_t track, ch;
+  long long a;       // track frame of lane-local frame 0
+  int f_lo, f_end;   // lane-local frames the true-peak pass owns: [f_lo, f_end)
+  bool ok;
+};
+
+__device__ __forceinline__ TpLane tp_locate(const SweepParams& P, uint32_t w, uint32_t lane) {
+  const WarpWork ww = P.work[w];
+  const Track& tr = P.tracks[ww.track];
+  TpLane r;
+  r.track = ww.track;
+  const uint32_t slot = lane / P.lpc;
+  r.ch = ww.ch_base + (lane - slot * P.lpc);
+  const uint32_t chunk = ww.first_chunk + slot;
+  r.ok = slot < P.cpw && r.ch < P.channels && chunk < tr.nchunks;
+  const LaneGeom g = lane_geometry((long long) tr.frames, P.L, P.W, P.aq, chunk);
+  r.a = g.a;
+  r.f_lo = P.W + g.o;
+  const long long left = (long long) tr.frames - g.a;      // frames of the track from local 0
+  const int f_hi = r.f_lo + P.L;
+  r.f_end = left < (long long) f_hi ? (left < 0 ? 0 : (int) left) : f_hi;
+  return r;
+}
+
+// One queued iteration: (track, channel, track frame of its first frame).
+__device__ __forceinline__ uint4 tp_entry(uint32_t track, uint32_t ch, long long t0) {
+  return make_uint4(track, ch, (uint32_t) (unsigned long long) t0,
+                    (uint32_t) ((unsigned long long) t0 >> 32));
+}
+
+template <int FMT, int TPF>
+__device__ __forceinline__ void tp_evaluate(const SweepParams& P, const uint4 cd) {
+  constexpr int NT = TpTraits<TPF>::kTaps;
+  const Track& tr = P.tracks[cd.x];
+  const long long frames = (long long) tr.frames;
+  const long long t0 = (long long) ((unsigned long long) cd.z | ((unsigned long long) cd.w << 32));
+  const unsigned char* pcm = reinterpret_cast<const unsigned char*>(tr.pcm) +
+                             cd.y * (FMT == FMT_S16 ? 2u : 4u);
+  float win[NT + kIter];
+  float m;
+  if (t0 >= NT && t0 + kIter <= frames) {
+    const unsigned char* q = pcm + (t0 - NT) * (long long) P.fb;
+#pragma unroll
+    for (int k = 0; k < NT + kIter; ++k) win[k] = pcm_sample<FMT>(q + (uint32_t) k * P.fb);
+    m = tp_window_valid<TPF>(win, kIter);
+  } else {
+#pragma unroll
+    for (int k = 0; k < NT + kIter; ++k) {
+      const long long t = t0 - NT + k;
+      win[k] = (t >= 0 && t < frames) ? pcm_sample<FMT>(pcm + t * (long long) P.fb) : 0.0f;
+    }
+    const long long left = frames - t0;
+    m = tp_window_valid<TPF>(win, left > kIter ? kIter : (int) left);
+  }
+  uint32_t* cell = P.peaks + 2 * (tr.peak_base + cd.y) + 1;
+  if (__float_as_uint(m) > __ldcg(cell)) atomicMax(cell, __float_as_uint(m));
+}
+
+// Warps are autonomous.  A work item is kTpSegment consecutive pairs of one
+// sweep warp; scanning lane = sweep lane, so the lane's geometry and its
+// channel's current peak are loaded once per item and the previous pair's
+// codes stay in a register.  Iterations that can still matter go into the
+// warp's queue and are evaluated 32 at a time, one per lane.
+template <int FMT, int TPF>
+__global__ void __launch_bounds__(kTpThreads)
+truepeak_kernel(const __grid_constant__ SweepParams P) {
+  constexpr int NT = TpTraits<TPF>::kTaps;
+  __shared__ uint4 queue_all[kTpWarps][kTpCap];
+  const uint32_t npairs = P.npairs;
+  const uint32_t lane = threadIdx.x & 31u, wic = threadIdx.x >> 5;
+  uint4* queue = queue_all[wic];
+  const uint32_t nseg = (npairs + kTpSegment - 1) / kTpSegment;
+  const uint64_t nitems = (uint64_t) P.nwarps * nseg;
+  const uint64_t nscan = (uint64_t) gridDim.x * kTpWarps;
+  uint32_t qn = 0;                       // warp-uniform
+
+  for (uint64_t item = (uint64_t) blockIdx.x * kTpWarps + wic; item < nitems; item += nscan) {
+    const uint32_t w = (uint32_t) (item / nseg);
+    const uint32_t p_begin = (uint32_t) (item - (uint64_t) w * nseg) * kTpSegment;
+    const uint32_t p_end = p_begin + kTpSegment < npairs ? p_begin + kTpSegment : npairs;
+    const TpLane me = tp_locate(P, w, lane);
+    const uint32_t* codes = P.mrec + ((size_t) w * npairs) * 32u + lane;
+    uint32_t* cell = P.peaks + 2 * ((me.ok ? P.tracks[me.track].peak_base : 0) + (me.ok ? me.ch : 0));
+    const uint2 pk = __ldcg(reinterpret_cast<const uint2*>(cell));
+    float floor_ = __uint_as_float(pk.x > pk.y ? pk.x : pk.y);
+    uint32_t prev = p_begin ? __ldcs(codes + (size_t) (p_begin - 1) * 32u) : 0u;
+    uint32_t nxt[kTpBatch];
+#pragma unroll
+    for (int j = 0; j < kTpBatch; ++j)
+      nxt[j] = p_begin + j < p_end ? __ldcs(codes + (size_t) (p_begin + j) * 32u) : 0u;
+    for (uint32_t p0 = p_begin; p0 < p_end; p0 += kTpBatch) {
+      uint32_t cw[kTpBatch];
+#pragma unroll
+      for (int j = 0; j < kTpBatch; ++j) {
+        cw[j] = nxt[j];
+        const uint32_t pn = p0 + kTpBatch + j;
+        nxt[j] = pn < p_end ? __ldcs(codes + (size_t) pn * 32u) : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < kTpBatch; ++j) {
+        const uint32_t code = cw[j];
+        // codes of iterations 2p-2 .. 2p+1
+        const uint32_t c0 = prev & 0xffffu, c1 = prev >> 16, c2 = code & 0xffffu, c3 = code >> 16;
+        prev = code;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          uint32_t cm = it ? (c3 > c2 ? c3 : c2) : (c2 > c1 ? c2 : c1);
+          if (NT > kIter) { const uint32_t cb = it ? c1 : c0; cm = cm > cb ? cm : cb; }
+          const uint32_t iter = (p0 + j) * 2u + it;
+          const int f0 = (int) iter * kIter;
+          const bool hit = me.ok && p0 + j < p_end && P.tp_bound * peak_code_value(cm) > floor_ &&
+                           f0 + kIter > me.f_lo && f0 < me.f_end;
+          const unsigned mask = __ballot_sync(0xffffffffu, hit);
+          if (mask) {
+            if (hit)
+              queue[qn + __popc(mask & ((1u << lane) - 1u))] = tp_entry(me.track, me.ch, me.a + f0);
+            qn += __popc(mask);
+          }
+        }
+      }
+      if (qn >= 32u) {
+        __syncwarp();
+        while (qn >= 32u) {
+          qn -= 32u;
+          tp_evaluate<FMT, TPF>(P, queue[qn + lane]);
+        }
+        __syncwarp();
+        floor_ = fmaxf(floor_, __uint_as_float(__ldcg(cell + 1)));
+      }
+    }
+  }
+  __syncwarp();
+  if (lane < qn) tp_evaluate<FMT, TPF>(P, queue[lane]);
+}
+
+cudaError_t launch_truepeak(const SweepParams& p, uint32_t format, int tpf, uint32_t sms,
+                            cudaStream_t stream) {
+  if (p.nwarps == 0 || tpf == 0) return cudaSuccess;
+  const uint32_t nseg = (p.npairs + kTpSegment - 1) / kTpSegment;
+  const uint64_t nitems = (uint64_t) p.nwarps * nseg;
+  const uint64_t ctas = (nitems + kTpWarps - 1) / kTpWarps;
+  const uint64_t want = (uint64_t) sms * 8u;
+  const unsigned blocks = (unsigned) (ctas < want ? ctas : want);
+  if (format == FMT_S16) {
+    if (tpf == 4) truepeak_kernel<FMT_S16, 4><<<blocks, kTpThreads, 0, stream>>>(p);
+    else truepeak_kernel<FMT_S16, 2><<<blocks, kTpThreads, 0, stream>>>(p);
+  } else {
+    if (tpf == 4) truepeak_kernel<FMT_F32, 4><<<blocks, kTpThreads, 0, stream>>>(p);
+    else truepeak_kernel<FMT_F32, 2><<<blocks, kTpThreads, 0, stream>>>(p);
+  }
+  return cudaGetLastError();
 }
 
 // --------------------------------------------------------- post-processing

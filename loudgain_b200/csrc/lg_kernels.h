@@ -36,6 +36,10 @@ struct PostSizes {
 // One sweep launch; `p` carries the group's constants and device pointers.
 cudaError_t launch_sweep(const SweepParams& p, uint32_t format, int tpf, uint32_t kmax,
                          cudaStream_t stream);
+// True-peak pass of the same group (no-op for rates without an interpolator);
+// must follow the group's sweep on the stream.
+cudaError_t launch_truepeak(const SweepParams& p, uint32_t format, int tpf, uint32_t sms,
+                            cudaStream_t stream);
 cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t stream);
 // Gated loudness + range for `nqueries` queries; all pointers are device memory.
 cudaError_t launch_queries(const BlockList* lists, const Query* queries, const uint32_t* members,

@@ -40,6 +40,7 @@ struct SweepGroup {
   uint32_t first_warp;   // into Plan::work
   uint32_t nwarps;
   uint32_t kmax;         // cp.async copies per lane and stage, rounded to 3 / 6 / 12
+  uint64_t mrec_base;    // first word of the group's iteration maxima (tpf != 0)
   SweepParams params;
 };
 
@@ -51,22 +52,16 @@ struct Plan {
   std::vector<Query> queries;        // [ntracks] track queries, then [nalbums]
   std::vector<uint32_t> members;     // track indices referenced by queries
   uint64_t total_recs = 0, total_slots = 0, total_blocks = 0, total_st = 0,
-           total_peaks = 0;
+           total_peaks = 0, total_mrec = 0;
   uint64_t total_samples = 0;        // frames * channels over all tracks
   uint32_t nalbums = 0;
 };
 
-// Shared memory one warp of the sweep needs: staging ring, candidate queue,
-// per-channel true-peak cells.
-inline uint32_t sweep_warp_smem_host(uint32_t channels, uint32_t fb, int tpf) {
+// Shared memory one warp of the sweep needs: its staging ring.
+inline uint32_t sweep_warp_smem_host(uint32_t channels, uint32_t fb) {
   const uint32_t cpw = chunks_per_warp(channels);
   const uint32_t units = (kStageFrames * fb) >> 4;
-  uint32_t bytes = kRing * cpw * ((units | 1u) << 4);
-  if (tpf) {
-    const uint32_t nt = tpf == 4 ? 12u : 24u;
-    bytes += 32u * (((((nt + kIter) * 4u + 4u + 15u) >> 4) | 1u) << 4);   // candidate queue
-  }
-  return bytes + 32u * 4u;
+  return kRing * cpw * ((units | 1u) << 4);
 }
 
 inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, uint64_t target_tasks,
@@ -142,6 +137,7 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, uint64_t t
     fill_kcoef(cs, sp);
     sp.tp_bound = cs.tpf == 4 ? 1.8645f : 2.3072f;   // > ||taps||_1 (1.8642 / 2.3068)
     sp.W = cs.W; sp.L = cs.L; sp.niters = (int32_t) t0.niters; sp.aq = (int32_t) t0.aq;
+    sp.npairs = (t0.niters + 1u) / 2u;
     sp.channels = t0.channels; sp.fb = t0.fb;
     sp.lpc = t0.channels < 32u ? t0.channels : 32u;
     sp.cpw = chunks_per_warp(t0.channels);
@@ -150,8 +146,7 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, uint64_t t
     sp.row_stride = (sp.units | 1u) << 4;
     sp.stage_bytes = sp.cpw * sp.row_stride;
     sp.ncopies = sp.cpw * sp.units;
-    sp.ring_bytes = kRing * sp.stage_bytes;
-    sp.warp_smem = sweep_warp_smem_host(t0.channels, t0.fb, cs.tpf);
+    sp.warp_smem = sweep_warp_smem_host(t0.channels, t0.fb);
     const uint32_t k = (sp.ncopies + 31u) / 32u;
     g.kmax = k <= 3 ? 3 : (k <= 6 ? 6 : 12);
     const long long stage_frames =
@@ -175,6 +170,8 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, uint64_t t
     }
     g.nwarps = (uint32_t) p.work.size() - g.first_warp;
     sp.nwarps = g.nwarps;
+    g.mrec_base = p.total_mrec;
+    if (cs.tpf) p.total_mrec += (uint64_t) g.nwarps * sp.npairs * 32u;
     if (g.nwarps) p.groups.push_back(g);
   }
   // -- queries: one per track, then one per album

@@ -111,45 +111,22 @@ LG_HD float tp_window(const float* win) {
 }
 
 // Everything one lane carries through its chunk.
-template <int TPF>
 struct LaneCtx {
-  static constexpr int NT = TpTraits<TPF>::kTaps;
   KState st;
-  float hist[NT > 0 ? NT : 1];   // the NT frames before the current iteration
-  float mprev;                   // max |x| over the previous iteration
-  float sp, tp;                  // raw-unit sample / true peak
+  float sp;                      // raw-unit sample peak of everything the lane has read
   float yr, yi;                  // running sum y[f] lambda^(f - f0 of this iteration)
   double e0;
   float pd, pw, qd, qw;          // state snapshots
-  int f_lo, f_hi, f_tp;          // energy range, true-peak limit (lane-local)
+  int f_lo, f_hi;                // energy range (lane-local frames)
 };
 
-template <int TPF>
-LG_HD void lane_init(LaneCtx<TPF>& c, int W, int L, const LaneGeom& g) {
+LG_HD void lane_init(LaneCtx& c, int W, int L, const LaneGeom& g) {
   c.st.d1 = c.st.w1 = c.st.w2 = c.st.v1 = c.st.v2 = 0.0f;
-#pragma unroll
-  for (int i = 0; i < (LaneCtx<TPF>::NT > 0 ? LaneCtx<TPF>::NT : 1); ++i) c.hist[i] = 0.0f;
-  c.mprev = 0.0f;
-  c.sp = c.tp = c.yr = c.yi = 0.0f;
+  c.sp = c.yr = c.yi = 0.0f;
   c.e0 = 0.0;
   c.pd = c.pw = c.qd = c.qw = 0.0f;
   c.f_lo = W + g.o;
   c.f_hi = c.f_lo + L;
-  c.f_tp = c.f_lo + g.l_valid;
-}
-
-// hist <- last NT frames of (hist, x)
-template <int TPF>
-LG_HD void hist_advance(LaneCtx<TPF>& c, const float* x) {
-  constexpr int NT = LaneCtx<TPF>::NT;
-  if (NT > kIter) {
-#pragma unroll
-    for (int i = 0; i < NT - kIter; ++i) c.hist[i] = c.hist[i + kIter];
-  }
-  if (NT > 0) {
-#pragma unroll
-    for (int i = 0; i < kIter; ++i) c.hist[NT - kIter + i] = x[i];
-  }
 }
 
 LG_HD float max_abs12(const float* x) {
@@ -159,33 +136,49 @@ LG_HD float max_abs12(const float* x) {
   return m;
 }
 
-// Warm-up iteration: filter state and true-peak history only.
-template <int TPF>
-LG_HD void iter_warm(LaneCtx<TPF>& c, const KCoef& k, const float* x) {
-#pragma unroll
-  for (int i = 0; i < kIter; ++i) (void) k_step(c.st, x[i], k);
-  hist_advance(c, x);
-  c.mprev = max_abs12(x);
-  // state before the first chunk frame of a lane with offset 0; lanes with a
-  // larger offset overwrite it in their first masked iteration
-  c.pd = c.st.d1; c.pw = c.st.w2;
+// ----- iteration maxima: what the sweep leaves behind for the true-peak pass.
+// max |x| of an iteration is stored as a 16-bit code = the upper half of its
+// float pattern, rounded UP (a bfloat16 that is never below the value), two
+// iterations per 32-bit word.  Codes order like the values they bound.
+LG_HD uint32_t peak_code(float m) {
+  union { float f; uint32_t u; } v;
+  v.f = m;
+  return (v.u + 0xffffu) >> 16;
+}
+LG_HD float peak_code_value(uint32_t code) {
+  union { float f; uint32_t u; } v;
+  v.u = code << 16;
+  return v.f;
 }
 
 // Y <- Y * lambda^-kIter + S: keeps Y = sum y[f] lambda^(f - f0) relative to
 // the current iteration's first frame, so the constants lambda^i stay O(1).
-template <int TPF>
-LG_HD void mode_accumulate(LaneCtx<TPF>& c, const KCoef& k, float sr, float si) {
+LG_HD void mode_accumulate(LaneCtx& c, const KCoef& k, float sr, float si) {
   const float nr = fmaf(c.yr, k.rot_re, fmaf(-c.yi, k.rot_im, sr));
   const float ni = fmaf(c.yr, k.rot_im, fmaf(c.yi, k.rot_re, si));
   c.yr = nr;
   c.yi = ni;
 }
 
-// Filter + energy part of a fast iteration (all kIter frames lie inside the
-// lane's chunk).  Returns max |x| of the iteration; the caller owns the
-// true-peak part.
-template <int TPF>
-LG_HD float iter_fast_energy(LaneCtx<TPF>& c, const KCoef& k, const float* x, int f0) {
+// Every iteration kind returns max |x| over its kIter frames and folds it
+// into the lane's sample peak.  Frames the lane reads beyond its own chunk
+// belong to a neighbouring chunk of the same channel, frames beyond the
+// track read as zero: neither can change the channel's maximum.
+
+// Warm-up iteration: filter state only.
+LG_HD float iter_warm(LaneCtx& c, const KCoef& k, const float* x) {
+#pragma unroll
+  for (int i = 0; i < kIter; ++i) (void) k_step(c.st, x[i], k);
+  // state before the first chunk frame of a lane with offset 0; lanes with a
+  // larger offset overwrite it in their first masked iteration
+  c.pd = c.st.d1; c.pw = c.st.w2;
+  const float m = max_abs12(x);
+  c.sp = fmaxf(c.sp, m);
+  return m;
+}
+
+// Fast iteration: all kIter frames lie inside the lane's chunk.
+LG_HD float iter_fast(LaneCtx& c, const KCoef& k, const float* x, int f0) {
   float e = 0.0f, sr = 0.0f, si = 0.0f;
 #pragma unroll
   for (int i = 0; i < kIter; ++i) {
@@ -202,11 +195,9 @@ LG_HD float iter_fast_energy(LaneCtx<TPF>& c, const KCoef& k, const float* x, in
   return m;
 }
 
-// Filter + energy part of a masked iteration: frames are tested one by one
-// against the lane's energy range; takes the state snapshots.  Does NOT touch
-// the peaks.
-template <int TPF>
-LG_HD void iter_masked_energy(LaneCtx<TPF>& c, const KCoef& k, const float* x, int f0) {
+// Masked iteration: frames are tested one by one against the lane's energy
+// range; takes the state snapshots.
+LG_HD float iter_masked(LaneCtx& c, const KCoef& k, const float* x, int f0) {
   float e = 0.0f, sr = 0.0f, si = 0.0f;
 #pragma unroll
   for (int i = 0; i < kIter; ++i) {
@@ -222,44 +213,32 @@ LG_HD void iter_masked_energy(LaneCtx<TPF>& c, const KCoef& k, const float* x, i
   }
   c.e0 += (double) e;
   mode_accumulate(c, k, sr, si);
+  const float m = max_abs12(x);
+  c.sp = fmaxf(c.sp, m);
+  return m;
 }
 
-// Peaks of an iteration, frame by frame, limited to the lane's own chunk
-// frames that exist in the track: [f_lo, f_tp).  Exhaustive form.
+// ----- true peak of one iteration -----------------------------------------
+// win[0, NT) = the NT frames before the iteration, win[NT, NT + kIter) = its
+// frames; only the first `nvalid` frames exist in the track (the reference
+// produces no output beyond the last frame it was given).
 template <int TPF>
-LG_HD void iter_peaks_masked(LaneCtx<TPF>& c, const float* x, int f0) {
-  constexpr int NT = LaneCtx<TPF>::NT;
-  float win[NT + kIter];
+LG_HD float tp_window_valid(const float* win, int nvalid) {
+  constexpr int NT = TpTraits<TPF>::kTaps;
+  float m = 0.0f;
 #pragma unroll
-  for (int i = 0; i < NT; ++i) win[i] = c.hist[i];
-#pragma unroll
-  for (int i = 0; i < kIter; ++i) win[NT + i] = x[i];
-#pragma unroll
-  for (int i = 0; i < kIter; ++i) {
-    const int f = f0 + i;
-    if (f >= c.f_lo && f < c.f_tp) {
-      c.sp = fmaxf(c.sp, fabsf(x[i]));
-      if (NT > 0) c.tp = fmaxf(c.tp, tp_frame<TPF>(win, NT + i));
-    }
-  }
+  for (int i = 0; i < kIter; ++i)
+    if (i < nvalid) m = fmaxf(m, tp_frame<TPF>(win, NT + i));
+  return m;
 }
 
-// Peaks of an iteration whose frames all exist in the track.  Exhaustive form
-// (host emulation; the device defers this to the candidate queue).  Frames
-// outside [f_lo, f_hi) belong to a neighbouring chunk of the same channel, so
-// including them cannot change the channel's maximum.
-template <int TPF>
-LG_HD void iter_peaks_all(LaneCtx<TPF>& c, const float* x) {
-  constexpr int NT = LaneCtx<TPF>::NT;
-  c.sp = fmaxf(c.sp, max_abs12(x));
-  if (NT > 0) {
-    float win[NT + kIter];
-#pragma unroll
-    for (int i = 0; i < NT; ++i) win[i] = c.hist[i];
-#pragma unroll
-    for (int i = 0; i < kIter; ++i) win[NT + i] = x[i];
-    c.tp = fmaxf(c.tp, tp_window<TPF>(win));
-  }
+// Does the true-peak pass have to look at lane-local iteration `it` of a
+// lane at all?  Only if it overlaps the lane's own chunk frames (everything
+// else is covered by the neighbouring chunk's lane) and starts inside the
+// track.
+LG_BOTH bool tp_iter_owned(int it, int f_lo, int f_hi, long long a, long long frames) {
+  const int f0 = it * kIter;
+  return f0 + kIter > f_lo && f0 < f_hi && a + f0 < frames;
 }
 
 // ----- host-side sample access (tests/emu) ----------------------------------

@@ -20,51 +20,87 @@
 
 using namespace lg;
 
+// One lane's iteration maxima, kept for the screened true-peak pass.
+struct LaneCodes {
+  uint32_t track, ch;
+  LaneGeom geo;
+  std::vector<uint32_t> code;   // per iteration (lg_sweep.cuh: peak_code)
+};
+
+// peaks: [2 * total_peaks] = (sample peak, exhaustive true peak) per channel;
+// tp_screened: [total_peaks] true peak of the two-pass scheme the device runs
+// (sweep records iteration maxima, the true-peak pass evaluates only the
+// iterations whose bound exceeds the channel's final sample peak).
 template <int FMT, int TPF>
 static void run_group(const Plan& p, const SweepGroup& g, std::vector<ChunkRec>& recs,
-                      std::vector<float>& peaks) {
+                      std::vector<float>& peaks, std::vector<float>& tp_screened) {
+  constexpr int NT = TpTraits<TPF>::kTaps;
   const SweepParams& k = g.params;
+  std::vector<LaneCodes> lanes;
   for (uint32_t w = 0; w < g.nwarps; ++w) {
     const WarpWork ww = p.work[g.first_warp + w];
     const Track& tr = p.tracks[ww.track];
     const CoefSet& cs = p.coefs[tr.coef];
     const uint32_t C = tr.channels, lpc = k.lpc, cpw = k.cpw;
-    const LaneGeom glast = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq,
-                                         ww.first_chunk + cpw - 1);
-    const long long tp_safe = (long long) tr.frames - glast.a;
     for (uint32_t lane = 0; lane < 32; ++lane) {
       const uint32_t slot = lane / lpc, chl = lane - slot * lpc, ch = ww.ch_base + chl;
       const uint32_t chunk = ww.first_chunk + slot;
       if (!(slot < cpw && ch < C && chunk < tr.nchunks)) continue;
       const LaneGeom geo = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, chunk);
-      LaneCtx<TPF> c;
+      LaneCtx c;
       lane_init(c, cs.W, cs.L, geo);
+      LaneCodes lc{ww.track, ch, geo, {}};
+      float win[(NT > 0 ? NT : 1) + kIter] = {0};
+      float tp = 0.0f;
       for (uint32_t it = 0; it < tr.niters; ++it) {
         const int f0 = (int) it * kIter;
-        float x[kIter];
+        float* x = win + NT;
         host_load_iter<FMT>(tr.pcm, (long long) tr.frames, (int) C, geo.a, f0, (int) ch, x);
         const int kind = iter_kind(f0, cs.W, (int) tr.aq, cs.L, ww.lmin_valid);
-        if (kind == ITER_WARM) {
-          iter_warm<TPF>(c, k, x);
-          continue;
+        const float m = kind == ITER_WARM ? iter_warm(c, k, x)
+                      : kind == ITER_FAST ? iter_fast(c, k, x, f0) : iter_masked(c, k, x, f0);
+        lc.code.push_back(peak_code(m));
+        if (NT > 0) {
+          if (tp_iter_owned((int) it, c.f_lo, c.f_hi, geo.a, (long long) tr.frames)) {
+            const long long left = (long long) tr.frames - (geo.a + f0);
+            tp = std::max(tp, tp_window_valid<TPF>(win, left > kIter ? kIter : (int) left));
+          }
+          for (int i = 0; i < NT; ++i) win[i] = win[i + kIter];   // NT >= kIter
         }
-        if (kind == ITER_FAST) {
-          (void) iter_fast_energy<TPF>(c, k, x, f0);
-          iter_peaks_all<TPF>(c, x);        // the device defers this to its candidate queue
-        } else {
-          iter_masked_energy<TPF>(c, k, x, f0);
-          if ((long long) f0 + kIter <= tp_safe) iter_peaks_all<TPF>(c, x);
-          else iter_peaks_masked<TPF>(c, x, f0);
-        }
-        hist_advance(c, x);
       }
       ChunkRec& r = recs[tr.rec_base + (uint64_t) chunk * C + ch];
       r.e0 = c.e0; r.yr = c.yr; r.yi = c.yi;
       r.pd = c.pd; r.pw = c.pw; r.qd = c.qd; r.qw = c.qw;
       float& sp = peaks[2 * (tr.peak_base + ch)];
-      float& tp = peaks[2 * (tr.peak_base + ch) + 1];
+      float& tpx = peaks[2 * (tr.peak_base + ch) + 1];
       sp = std::max(sp, c.sp);
-      tp = std::max(tp, c.tp);
+      tpx = std::max(tpx, tp);
+      if (NT > 0) lanes.push_back(std::move(lc));
+    }
+  }
+  // ---- the device's second pass, on the recorded codes
+  for (const LaneCodes& lc : lanes) {
+    const Track& tr = p.tracks[lc.track];
+    const CoefSet& cs = p.coefs[tr.coef];
+    const int f_lo = cs.W + lc.geo.o, f_hi = f_lo + cs.L;
+    const float floor_ = peaks[2 * (tr.peak_base + lc.ch)];
+    float& out = tp_screened[tr.peak_base + lc.ch];
+    for (uint32_t it = 0; it < tr.niters; ++it) {
+      uint32_t cm = lc.code[it];
+      for (uint32_t b = 1; b <= (uint32_t) NT / kIter && b <= it; ++b) cm = std::max(cm, lc.code[it - b]);
+      if (!(k.tp_bound * peak_code_value(cm) > floor_)) continue;
+      if (!tp_iter_owned((int) it, f_lo, f_hi, lc.geo.a, (long long) tr.frames)) continue;
+      float win[(NT > 0 ? NT : 1) + kIter];
+      const long long t0 = lc.geo.a + (long long) it * kIter;
+      for (int q = 0; q < NT + kIter; ++q) {
+        const long long t = t0 - NT + q;
+        win[q] = 0.0f;
+        if (t < 0 || t >= (long long) tr.frames) continue;
+        if (FMT == FMT_S16) win[q] = (float) ((const short*) tr.pcm)[t * tr.channels + lc.ch];
+        else win[q] = ((const float*) tr.pcm)[t * tr.channels + lc.ch];
+      }
+      const long long left = (long long) tr.frames - t0;
+      out = std::max(out, tp_window_valid<TPF>(win, left > kIter ? kIter : (int) left));
     }
   }
 }
@@ -127,7 +163,8 @@ static void run_query(const Plan& p, const Query& q, const std::vector<double>& 
 extern "C" int emu_measure(const lgb_track* tracks, size_t ntracks, uint32_t nalbums,
                            uint64_t target_tasks, lgb_result* track_results,
                            lgb_result* album_results, double* sample_peaks, double* true_peaks,
-                           double* blocks_out, double* st_out, int32_t* chunk_len_out) {
+                           double* blocks_out, double* st_out, int32_t* chunk_len_out,
+                           double* true_peaks_screened) {
   std::vector<TrackIn> in(ntracks);
   for (size_t i = 0; i < ntracks; ++i)
     in[i] = TrackIn{tracks[i].pcm, tracks[i].frames, tracks[i].channels, tracks[i].samplerate,
@@ -135,16 +172,16 @@ extern "C" int emu_measure(const lgb_track* tracks, size_t ntracks, uint32_t nal
   Plan p;
   build_plan(in.data(), ntracks, nalbums, target_tasks, p);
   std::vector<ChunkRec> recs(p.total_recs);
-  std::vector<float> peaks(2 * p.total_peaks, 0.0f);
+  std::vector<float> peaks(2 * p.total_peaks, 0.0f), tps(p.total_peaks, 0.0f);
   for (const SweepGroup& g : p.groups) {
     if (g.format == FMT_S16) {
-      if (g.tpf == 4) run_group<FMT_S16, 4>(p, g, recs, peaks);
-      else if (g.tpf == 2) run_group<FMT_S16, 2>(p, g, recs, peaks);
-      else run_group<FMT_S16, 0>(p, g, recs, peaks);
+      if (g.tpf == 4) run_group<FMT_S16, 4>(p, g, recs, peaks, tps);
+      else if (g.tpf == 2) run_group<FMT_S16, 2>(p, g, recs, peaks, tps);
+      else run_group<FMT_S16, 0>(p, g, recs, peaks, tps);
     } else {
-      if (g.tpf == 4) run_group<FMT_F32, 4>(p, g, recs, peaks);
-      else if (g.tpf == 2) run_group<FMT_F32, 2>(p, g, recs, peaks);
-      else run_group<FMT_F32, 0>(p, g, recs, peaks);
+      if (g.tpf == 4) run_group<FMT_F32, 4>(p, g, recs, peaks, tps);
+      else if (g.tpf == 2) run_group<FMT_F32, 2>(p, g, recs, peaks, tps);
+      else run_group<FMT_F32, 0>(p, g, recs, peaks, tps);
     }
   }
   std::vector<double> echunk(p.total_recs, 0.0), eslot(p.total_slots), zblock(p.total_blocks),
@@ -180,6 +217,10 @@ extern "C" int emu_measure(const lgb_track* tracks, size_t ntracks, uint32_t nal
       const double t = (double) peaks[2 * (tr.peak_base + c) + 1] / scale;
       if (sample_peaks) sample_peaks[tr.peak_base + c] = s;
       if (true_peaks) true_peaks[tr.peak_base + c] = t > s ? t : s;
+      if (true_peaks_screened) {
+        const double u = (double) tps[tr.peak_base + c] / scale;
+        true_peaks_screened[tr.peak_base + c] = u > s ? u : s;
+      }
     }
   }
   if (blocks_out) std::copy(zblock.begin(), zblock.end(), blocks_out);

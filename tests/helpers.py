@@ -66,12 +66,12 @@ def emu_measure(tracks, albums=None, target_tasks=0):
     tres = (LgbResult * n)()
     ares = (LgbResult * max(nalb, 1))()
     npk = sum(t[0].shape[1] for t in tracks)
-    sp = np.zeros(npk); tp = np.zeros(npk)
+    sp = np.zeros(npk); tp = np.zeros(npk); tps = np.zeros(npk)
     blocks = np.zeros(max(tb.value, 1)); st = np.zeros(max(ts.value, 1))
     clen = np.zeros(n, dtype=np.int32)
     dp = lambda a: a.ctypes.data_as(C.c_void_p)
     rc = lib.emu_measure(arr, C.c_size_t(n), C.c_uint32(nalb), C.c_uint64(target_tasks), tres, ares,
-                         dp(sp), dp(tp), dp(blocks), dp(st), dp(clen))
+                         dp(sp), dp(tp), dp(blocks), dp(st), dp(clen), dp(tps))
     assert rc == 0
     out = {"tracks": [], "albums": [], "blocks": blocks[:tb.value], "st": st[:ts.value],
            "chunk_len": clen}
@@ -82,7 +82,9 @@ def emu_measure(tracks, albums=None, target_tasks=0):
         out["tracks"].append({"loudness": r.loudness, "range": r.range, "n_abs": r.n_abs,
                               "n_rel": r.n_rel, "n_st": r.n_shortterm,
                               "sample_peak": sp[off:off + ch].copy(),
-                              "true_peak": tp[off:off + ch].copy()})
+                              "true_peak": tp[off:off + ch].copy(),
+                              # the device's two-pass (screened) evaluation
+                              "true_peak_screened": tps[off:off + ch].copy()})
         off += ch
     for a in range(nalb):
         r = ares[a]
