@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -134,7 +135,9 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // Two full waves of resident threads when the audio is long enough.
-  build_plan(in.data(), ntracks, nalbums, (uint64_t) sms * 2048u, b->plan);
+  int force_k = 0;
+  if (const char* e = getenv("LOUDGAIN_B200_CHUNKS_PER_SLOT")) force_k = atoi(e);
+  build_plan(in.data(), ntracks, nalbums, (uint64_t) sms * 2048u, b->plan, force_k);
   const Plan& p = b->plan;
   b->abs_gate = pow(10.0, (-70.0 + 0.691) / 10.0);
   bool ok = upload(p.tracks, &b->d_tracks, b->stream) && upload(p.coefs, &b->d_coefs, b->stream) &&
@@ -186,7 +189,7 @@ extern "C" LG_EXPORT int lgb_batch_run(lgb_batch* b) {
     SweepParams sp = g.params;
     sp.tracks = t.tracks; sp.work = t.work + g.first_warp; sp.recs = t.recs; sp.peaks = t.peaks;
     sp.mrec = b->d_mrec + g.mrec_base;
-    e = launch_sweep(sp, g.format, g.tpf, g.kmax, b->stream);
+    e = launch_sweep(sp, g.format, g.tpf, b->stream);
     if (e != cudaSuccess) { set_error("launch_sweep", e); return 1; }
   }
   if (b->timing) { cudaEventRecord(b->ev1, b->stream); b->timed_run_pending = true; }

@@ -163,7 +163,10 @@ struct SweepParams {
   uint32_t channels, fb;
   uint32_t lpc;            // lanes per chunk = min(channels, 32)
   uint32_t cpw;            // chunks per warp
-  uint32_t stage_row_bytes, units, row_stride, stage_bytes, ncopies;
+  // staging: bytes one row advances per stage, 16-byte units of that piece,
+  // padded row stride in shared memory (odd number of units), bytes per stage
+  // buffer and per ring, copies per lane and stage (ceil(units / lpc))
+  uint32_t stage_row_bytes, units, row_stride, stage_bytes, ring_bytes, kcopies;
   uint32_t warp_smem, nwarps;
   const Track* tracks;
   const WarpWork* work;

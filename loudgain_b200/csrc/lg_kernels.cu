@@ -127,11 +127,27 @@ __device__ __forceinline__ void smem_load_iter(const unsigned char* rowp, uint32
   }
 }
 
+// Makes a per-lane invariant opaque to the compiler, so that it is kept in a
+// register instead of being recomputed (from S2R / parameter loads) inside
+// the streaming loop.
+__device__ __forceinline__ uint32_t pin(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
+template <class T>
+__device__ __forceinline__ T* pin(T* v) { asm volatile("" : "+l"(v)); return v; }
+
 #ifndef LG_SWEEP_MINBLOCKS
-#define LG_SWEEP_MINBLOCKS 6
+#define LG_SWEEP_MINBLOCKS 8
 #endif
 
-template <int LAYOUT, bool TP, int KMAX>
+// Lanes per chunk row when the layout fixes it (0 = run-time, P.lpc).
+template <int LAYOUT>
+__host__ __device__ constexpr uint32_t layout_lpc() {
+  return (LAYOUT == ROW_S16_STEREO || LAYOUT == ROW_F32_STEREO) ? 2u
+       : (LAYOUT == ROW_S16_MONO || LAYOUT == ROW_F32_MONO) ? 1u : 0u;
+}
+
+// KCOPY = 16-byte copies a lane issues per stage (0 = run-time count, for
+// more than 32 channels).
+template <int LAYOUT, bool TP, int KCOPY>
 __global__ void __launch_bounds__(kSweepThreads, LG_SWEEP_MINBLOCKS)
 sweep_kernel(const __grid_constant__ SweepParams P) {
   extern __shared__ __align__(16) unsigned char smem_all[];
@@ -140,7 +156,6 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
   const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + wic;
   if (warp >= P.nwarps) return;                // whole warps leave; no CTA barrier below
   unsigned char* sm = smem_all + wic * P.warp_smem;
-  const uint32_t sm_addr = (uint32_t) __cvta_generic_to_shared(sm);
 
   const WarpWork ww = P.work[warp];
   const Track& tr = P.tracks[ww.track];
@@ -149,60 +164,66 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
   const long long frames = (long long) tr.frames;
   const unsigned char* pcm = reinterpret_cast<const unsigned char*>(tr.pcm);
 
-  const uint32_t slot = lane / P.lpc;
-  const uint32_t chl = lane - slot * P.lpc;    // channel within the warp's group
+  constexpr uint32_t LPC = layout_lpc<LAYOUT>();
+  const uint32_t lpc = LPC ? LPC : P.lpc;
+  const uint32_t slot = lane / lpc;
+  const uint32_t chl = lane - slot * lpc;      // channel within the warp's group
   const uint32_t ch = ww.ch_base + chl;
   const uint32_t chunk = ww.first_chunk + slot;
   const bool compute = slot < P.cpw && ch < C;
   const bool active = compute && chunk < tr.nchunks;
 
-  // ---- staging.  Per stage and row one contiguous piece of kStageFrames
-  // frames, moved with 16-byte cp.async copies: copy k of a lane moves unit
-  // (idx % units) of row (idx / units), idx = lane + 32 k, so consecutive
-  // lanes fetch consecutive units of one row.  Warps at a track boundary use
-  // the zero-filling form.
-  const LaneGeom g0 = lane_geometry(frames, L, W, P.aq, ww.first_chunk);
-  const long long warp_byte0 = g0.a * (long long) fb;          // may be negative
-  const long long track_bytes = frames * (long long) fb;
-  const bool interior = ww.interior != 0;
-  int32_t soff[KMAX];      // source byte offset at stage 0, relative to warp_byte0
-  uint32_t doff[KMAX];     // destination byte offset inside a stage buffer
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
-    const uint32_t idx = lane + 32u * k;
-    const uint32_t row = idx / P.units;
-    const uint32_t unit = idx - row * P.units;
-    const LaneGeom gr = lane_geometry(frames, L, W, P.aq, ww.first_chunk + row);
-    soff[k] = (int32_t) ((gr.a - g0.a) * (long long) fb) + (int32_t) (unit << 4);
-    doff[k] = idx < P.ncopies ? row * P.row_stride + (unit << 4) : 0xffffffffu;
-  }
-
-  auto prefetch = [&](uint32_t stage) {
-    const uint32_t dst0 = sm_addr + (stage % kRing) * P.stage_bytes;
-    const long long adv = (long long) stage * P.stage_row_bytes;
-    if (interior) {
-      const unsigned char* src0 = pcm + (warp_byte0 + adv);
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k)
-        if (doff[k] != 0xffffffffu) cp_async16(dst0 + doff[k], src0 + soff[k]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        if (doff[k] == 0xffffffffu) continue;
-        const long long g = warp_byte0 + adv + soff[k];
-        long long ok = g < 0 ? 0 : track_bytes - g;
-        ok = ok < 0 ? 0 : (ok > 16 ? 16 : ok);
-        cp_async16_zfill(dst0 + doff[k], pcm + (ok ? g : 0), (uint32_t) ok);
-      }
-    }
-  };
-
   // ---- lane state
   const LaneGeom geo = lane_geometry(frames, L, W, P.aq, chunk);
   LaneCtx c;
   lane_init(c, W, L, geo);
-  const unsigned char* my_row = sm + slot * P.row_stride;
-  uint32_t* const mrec = P.mrec + (size_t) warp * P.npairs * 32u + lane;
+  const unsigned char* my_row = pin(sm + slot * P.row_stride);
+
+  // ---- staging.  Per stage every row receives one contiguous piece of
+  // kStageFrames frames, moved with 16-byte cp.async copies.  The lpc lanes of
+  // a row copy its units interleaved (lane chl takes units chl, chl + lpc, ...),
+  // so consecutive lanes fetch consecutive 16-byte units, and a lane only ever
+  // needs its own row's address.  Warps at a track boundary use the
+  // zero-filling form.
+  const uint32_t ustride = lpc << 4;                            // bytes between a lane's copies
+  const long long row_byte0 = geo.a * (long long) fb + (chl << 4);   // first copy, may be negative
+  const long long track_bytes = frames * (long long) fb;
+  const bool interior = ww.interior != 0;
+  const bool copier = slot < P.cpw;
+  const uint32_t ncopy = KCOPY ? (uint32_t) KCOPY : P.kcopies;
+  const uint32_t dst_row =
+      pin((uint32_t) __cvta_generic_to_shared(sm) + slot * P.row_stride + (chl << 4));
+  const unsigned char* src = pcm + row_byte0;                   // advanced stage by stage
+  uint32_t pf_off = 0;                                          // ring offset of the next prefetch
+
+  auto prefetch = [&]() {
+    const uint32_t dst = dst_row + pf_off;
+    if (copier) {
+      if (interior) {
+        if (KCOPY) {
+#pragma unroll
+          for (int k = 0; k < (KCOPY ? KCOPY : 1); ++k) cp_async16(dst + k * ustride, src + k * ustride);
+        } else {
+          for (uint32_t k = 0; k < ncopy; ++k)
+            if (chl + k * lpc < P.units) cp_async16(dst + k * ustride, src + k * ustride);
+        }
+      } else {
+#pragma unroll 1
+        for (uint32_t k = 0; k < ncopy; ++k) {
+          if (chl + k * lpc >= P.units) break;
+          const long long g = (src - pcm) + (long long) (k * ustride);
+          long long ok = g < 0 ? 0 : track_bytes - g;
+          ok = ok < 0 ? 0 : (ok > 16 ? 16 : ok);
+          cp_async16_zfill(dst + k * ustride, pcm + (ok ? g : 0), (uint32_t) ok);
+        }
+      }
+    }
+    src += P.stage_row_bytes;
+    pf_off += P.stage_bytes;
+    if (pf_off == P.ring_bytes) pf_off = 0;
+  };
+
+  uint32_t* mrec = pin(P.mrec + (size_t) warp * P.npairs * 32u + lane);   // advanced pair by pair
 
   const uint32_t niters = (uint32_t) P.niters;
   const uint32_t npairs = P.npairs;
@@ -213,19 +234,22 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
   const uint32_t fast_hi = (uint32_t) ((W + lfast) / kPairFrames);     // exclusive
 #pragma unroll
   for (int i = 0; i < kRing - 1; ++i) {
-    if ((uint32_t) i < nstages) prefetch(i);
+    if ((uint32_t) i < nstages) prefetch();
     cp_async_commit();
   }
 
+  uint32_t cs_off = 0;                                          // ring offset of the stage being consumed
+  uint32_t pair = 0;
   for (uint32_t s = 0; s < nstages; ++s) {
     cp_async_wait<kRing - 2>();
     __syncwarp();                // everyone's data has landed; the previous stage is consumed
-    if (s + kRing - 1 < nstages) prefetch(s + kRing - 1);
+    if (s + kRing - 1 < nstages) prefetch();
     cp_async_commit();
-    const unsigned char* sbuf = my_row + (s % kRing) * P.stage_bytes;
+    const unsigned char* sbuf = my_row + cs_off;
+    cs_off += P.stage_bytes;
+    if (cs_off == P.ring_bytes) cs_off = 0;
 #pragma unroll 1
-    for (uint32_t pr = 0; pr < (uint32_t) kPairsPerStage; ++pr) {
-      const uint32_t pair = s * kPairsPerStage + pr;
+    for (uint32_t pr = 0; pr < (uint32_t) kPairsPerStage; ++pr, ++pair) {
       if (pair >= npairs) break;
       const unsigned char* buf = sbuf + pr * kPairFrames * fb;
       float m0 = 0.0f, m1 = 0.0f;
@@ -252,7 +276,7 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
           if (it == 0) m0 = m; else m1 = m;
         }
       }
-      if (TP) mrec[(size_t) pair * 32u] = peak_code(m0) | (peak_code(m1) << 16);
+      if (TP) { *mrec = peak_code(m0) | (peak_code(m1) << 16); mrec += 32; }
     }
   }
   cp_async_wait<0>();
@@ -271,49 +295,51 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
     atomicMax(P.peaks + 2 * (tr.peak_base + ch), spb);
 }
 
-template <int LAYOUT, bool TP, int KMAX>
+template <int LAYOUT, bool TP, int KCOPY>
 static cudaError_t launch_sweep_k(const SweepParams& p, cudaStream_t stream) {
   const uint32_t wpb = kSweepThreads / 32;
   const uint32_t blocks = (p.nwarps + wpb - 1) / wpb;
   const size_t smem = (size_t) p.warp_smem * wpb;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<LAYOUT, TP, KMAX>,
+    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<LAYOUT, TP, KCOPY>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(sweep_kernel<LAYOUT, TP, KMAX>,
+      e = cudaFuncSetAttribute(sweep_kernel<LAYOUT, TP, KCOPY>,
                                cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  sweep_kernel<LAYOUT, TP, KMAX><<<blocks, kSweepThreads, smem, stream>>>(p);
+  sweep_kernel<LAYOUT, TP, KCOPY><<<blocks, kSweepThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
+// Copies per lane and stage: units / lpc = 3 per pair for 16-bit and 6 per
+// pair for float frames as long as a row's channels fit one warp.
 template <int LAYOUT, bool TP>
-static cudaError_t launch_sweep_t(const SweepParams& p, uint32_t kmax, cudaStream_t stream) {
-  if (kmax <= 3) return launch_sweep_k<LAYOUT, TP, 3>(p, stream);
-  if (kmax <= 6) return launch_sweep_k<LAYOUT, TP, 6>(p, stream);
-  return launch_sweep_k<LAYOUT, TP, 12>(p, stream);
+static cudaError_t launch_sweep_t(const SweepParams& p, cudaStream_t stream) {
+  constexpr bool f32 = LAYOUT >= ROW_F32_MONO;
+  constexpr int K = (f32 ? 6 : 3) * kPairsPerStage;
+  if (p.kcopies == (uint32_t) K && p.units == p.kcopies * p.lpc)
+    return launch_sweep_k<LAYOUT, TP, K>(p, stream);
+  return launch_sweep_k<LAYOUT, TP, 0>(p, stream);
 }
 
 template <int LAYOUT>
-static cudaError_t launch_sweep_l(const SweepParams& p, int tpf, uint32_t kmax, cudaStream_t stream) {
-  return tpf ? launch_sweep_t<LAYOUT, true>(p, kmax, stream)
-             : launch_sweep_t<LAYOUT, false>(p, kmax, stream);
+static cudaError_t launch_sweep_l(const SweepParams& p, int tpf, cudaStream_t stream) {
+  return tpf ? launch_sweep_t<LAYOUT, true>(p, stream) : launch_sweep_t<LAYOUT, false>(p, stream);
 }
 
-cudaError_t launch_sweep(const SweepParams& p, uint32_t format, int tpf, uint32_t kmax,
-                         cudaStream_t stream) {
+cudaError_t launch_sweep(const SweepParams& p, uint32_t format, int tpf, cudaStream_t stream) {
   if (p.nwarps == 0) return cudaSuccess;
   if (format == FMT_S16) {
-    if (p.channels == 2) return launch_sweep_l<ROW_S16_STEREO>(p, tpf, kmax, stream);
-    if (p.channels == 1) return launch_sweep_l<ROW_S16_MONO>(p, tpf, kmax, stream);
-    return launch_sweep_l<ROW_S16_ANY>(p, tpf, kmax, stream);
+    if (p.channels == 2) return launch_sweep_l<ROW_S16_STEREO>(p, tpf, stream);
+    if (p.channels == 1) return launch_sweep_l<ROW_S16_MONO>(p, tpf, stream);
+    return launch_sweep_l<ROW_S16_ANY>(p, tpf, stream);
   }
-  if (p.channels == 2) return launch_sweep_l<ROW_F32_STEREO>(p, tpf, kmax, stream);
-  if (p.channels == 1) return launch_sweep_l<ROW_F32_MONO>(p, tpf, kmax, stream);
-  return launch_sweep_l<ROW_F32_ANY>(p, tpf, kmax, stream);
+  if (p.channels == 2) return launch_sweep_l<ROW_F32_STEREO>(p, tpf, stream);
+  if (p.channels == 1) return launch_sweep_l<ROW_F32_MONO>(p, tpf, stream);
+  return launch_sweep_l<ROW_F32_ANY>(p, tpf, stream);
 }
 
 // -------------------------------------------------------------- true peak
@@ -331,7 +357,6 @@ cudaError_t launch_sweep(const SweepParams& p, uint32_t format, int tpf, uint32_
 constexpr int kTpThreads = 128;
 constexpr int kTpWarps = kTpThreads / 32;
 constexpr int kTpBatch = 4;                             // pairs a lane has in flight
-constexpr int kTpSegment = 16;                          // pairs per work item (one sweep lane row)
 constexpr int kTpCap = 32 + 2 * kTpBatch * 32;          // per-warp queue: remainder + one batch
 
 template <int FMT>
@@ -406,27 +431,32 @@ __device__ __forceinline__ void tp_evaluate(const SweepParams& P, const uint4 cd
 // codes stay in a register.  Iterations that can still matter go into the
 // warp's queue and are evaluated 32 at a time, one per lane.
 template <int FMT, int TPF>
-__global__ void __launch_bounds__(kTpThreads)
-truepeak_kernel(const __grid_constant__ SweepParams P) {
+__global__ void __launch_bounds__(kTpThreads, 5)
+truepeak_kernel(const __grid_constant__ SweepParams P, const uint32_t seg_pairs) {
   constexpr int NT = TpTraits<TPF>::kTaps;
   __shared__ uint4 queue_all[kTpWarps][kTpCap];
   const uint32_t npairs = P.npairs;
   const uint32_t lane = threadIdx.x & 31u, wic = threadIdx.x >> 5;
   uint4* queue = queue_all[wic];
-  const uint32_t nseg = (npairs + kTpSegment - 1) / kTpSegment;
+  const uint32_t nseg = (npairs + seg_pairs - 1) / seg_pairs;
   const uint64_t nitems = (uint64_t) P.nwarps * nseg;
   const uint64_t nscan = (uint64_t) gridDim.x * kTpWarps;
   uint32_t qn = 0;                       // warp-uniform
 
   for (uint64_t item = (uint64_t) blockIdx.x * kTpWarps + wic; item < nitems; item += nscan) {
     const uint32_t w = (uint32_t) (item / nseg);
-    const uint32_t p_begin = (uint32_t) (item - (uint64_t) w * nseg) * kTpSegment;
-    const uint32_t p_end = p_begin + kTpSegment < npairs ? p_begin + kTpSegment : npairs;
+    const uint32_t p_begin = (uint32_t) (item - (uint64_t) w * nseg) * seg_pairs;
+    const uint32_t p_end = p_begin + seg_pairs < npairs ? p_begin + seg_pairs : npairs;
     const TpLane me = tp_locate(P, w, lane);
     const uint32_t* codes = P.mrec + ((size_t) w * npairs) * 32u + lane;
     uint32_t* cell = P.peaks + 2 * ((me.ok ? P.tracks[me.track].peak_base : 0) + (me.ok ? me.ch : 0));
     const uint2 pk = __ldcg(reinterpret_cast<const uint2*>(cell));
     float floor_ = __uint_as_float(pk.x > pk.y ? pk.x : pk.y);
+    // Integer form of the bound test: codes order like the values they stand
+    // for, so "bound * value(code) > floor" can only hold for codes above the
+    // (truncated) code of floor / bound; the margin keeps the pre-test a
+    // superset of the exact test, which is repeated on the survivors.
+    uint32_t code_gate = me.ok ? __float_as_uint(floor_ / P.tp_bound * 0.999f) >> 16 : 0xffffffffu;
     uint32_t prev = p_begin ? __ldcs(codes + (size_t) (p_begin - 1) * 32u) : 0u;
     uint32_t nxt[kTpBatch];
 #pragma unroll
@@ -434,42 +464,51 @@ truepeak_kernel(const __grid_constant__ SweepParams P) {
       nxt[j] = p_begin + j < p_end ? __ldcs(codes + (size_t) (p_begin + j) * 32u) : 0u;
     for (uint32_t p0 = p_begin; p0 < p_end; p0 += kTpBatch) {
       uint32_t cw[kTpBatch];
+      uint32_t top = prev >> 16;
 #pragma unroll
       for (int j = 0; j < kTpBatch; ++j) {
         cw[j] = nxt[j];
         const uint32_t pn = p0 + kTpBatch + j;
         nxt[j] = pn < p_end ? __ldcs(codes + (size_t) pn * 32u) : 0u;
+        const uint32_t hi = cw[j] >> 16, lo = cw[j] & 0xffffu;
+        top = max(top, max(hi, lo));
       }
+      if (NT > kIter) top = max(top, prev & 0xffffu);
+      if (__any_sync(0xffffffffu, top > code_gate)) {
 #pragma unroll
-      for (int j = 0; j < kTpBatch; ++j) {
-        const uint32_t code = cw[j];
-        // codes of iterations 2p-2 .. 2p+1
-        const uint32_t c0 = prev & 0xffffu, c1 = prev >> 16, c2 = code & 0xffffu, c3 = code >> 16;
-        prev = code;
+        for (int j = 0; j < kTpBatch; ++j) {
+          const uint32_t code = cw[j];
+          // codes of iterations 2p-2 .. 2p+1
+          const uint32_t c0 = prev & 0xffffu, c1 = prev >> 16, c2 = code & 0xffffu, c3 = code >> 16;
+          prev = code;
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
-          uint32_t cm = it ? (c3 > c2 ? c3 : c2) : (c2 > c1 ? c2 : c1);
-          if (NT > kIter) { const uint32_t cb = it ? c1 : c0; cm = cm > cb ? cm : cb; }
-          const uint32_t iter = (p0 + j) * 2u + it;
-          const int f0 = (int) iter * kIter;
-          const bool hit = me.ok && p0 + j < p_end && P.tp_bound * peak_code_value(cm) > floor_ &&
-                           f0 + kIter > me.f_lo && f0 < me.f_end;
-          const unsigned mask = __ballot_sync(0xffffffffu, hit);
-          if (mask) {
-            if (hit)
-              queue[qn + __popc(mask & ((1u << lane) - 1u))] = tp_entry(me.track, me.ch, me.a + f0);
-            qn += __popc(mask);
+          for (int it = 0; it < 2; ++it) {
+            uint32_t cm = it ? (c3 > c2 ? c3 : c2) : (c2 > c1 ? c2 : c1);
+            if (NT > kIter) { const uint32_t cb = it ? c1 : c0; cm = cm > cb ? cm : cb; }
+            const uint32_t iter = (p0 + j) * 2u + it;
+            const int f0 = (int) iter * kIter;
+            const bool hit = me.ok && p0 + j < p_end && P.tp_bound * peak_code_value(cm) > floor_ &&
+                             f0 + kIter > me.f_lo && f0 < me.f_end;
+            const unsigned mask = __ballot_sync(0xffffffffu, hit);
+            if (mask) {
+              if (hit)
+                queue[qn + __popc(mask & ((1u << lane) - 1u))] = tp_entry(me.track, me.ch, me.a + f0);
+              qn += __popc(mask);
+            }
           }
         }
-      }
-      if (qn >= 32u) {
-        __syncwarp();
-        while (qn >= 32u) {
-          qn -= 32u;
-          tp_evaluate<FMT, TPF>(P, queue[qn + lane]);
+        if (qn >= 32u) {
+          __syncwarp();
+          while (qn >= 32u) {
+            qn -= 32u;
+            tp_evaluate<FMT, TPF>(P, queue[qn + lane]);
+          }
+          __syncwarp();
+          floor_ = fmaxf(floor_, __uint_as_float(__ldcg(cell + 1)));
+          code_gate = me.ok ? __float_as_uint(floor_ / P.tp_bound * 0.999f) >> 16 : 0xffffffffu;
         }
-        __syncwarp();
-        floor_ = fmaxf(floor_, __uint_as_float(__ldcg(cell + 1)));
+      } else {
+        prev = cw[kTpBatch - 1];
       }
     }
   }
@@ -477,22 +516,39 @@ truepeak_kernel(const __grid_constant__ SweepParams P) {
   if (lane < qn) tp_evaluate<FMT, TPF>(P, queue[lane]);
 }
 
+template <int FMT, int TPF>
+static cudaError_t launch_truepeak_t(const SweepParams& p, uint32_t sms, cudaStream_t stream) {
+  // Persistent grid: every resident warp scans work items of `seg` pairs of
+  // one sweep warp.  Items are as long as possible (the per-item set-up is a
+  // chain of dependent loads) while leaving about four per scanning warp.
+  static int per_sm = 0;
+  if (!per_sm) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, truepeak_kernel<FMT, TPF>, kTpThreads, 0) !=
+            cudaSuccess || per_sm < 1)
+      per_sm = 4;
+  }
+  const uint64_t nscan = (uint64_t) sms * per_sm * kTpWarps;
+  uint64_t nseg = (4 * nscan + p.nwarps - 1) / p.nwarps;
+  const uint64_t max_seg = (p.npairs + kTpBatch - 1) / kTpBatch;
+  if (nseg > max_seg) nseg = max_seg;
+  if (nseg < 1) nseg = 1;
+  uint32_t seg = (uint32_t) ((p.npairs + nseg - 1) / nseg);
+  seg = (seg + kTpBatch - 1) / kTpBatch * kTpBatch;
+  const uint64_t nitems = (uint64_t) p.nwarps * ((p.npairs + seg - 1) / seg);
+  const uint64_t ctas = (nitems + kTpWarps - 1) / kTpWarps;
+  const uint64_t want = (uint64_t) sms * per_sm;
+  truepeak_kernel<FMT, TPF><<<(unsigned) (ctas < want ? ctas : want), kTpThreads, 0, stream>>>(p, seg);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_truepeak(const SweepParams& p, uint32_t format, int tpf, uint32_t sms,
                             cudaStream_t stream) {
   if (p.nwarps == 0 || tpf == 0) return cudaSuccess;
-  const uint32_t nseg = (p.npairs + kTpSegment - 1) / kTpSegment;
-  const uint64_t nitems = (uint64_t) p.nwarps * nseg;
-  const uint64_t ctas = (nitems + kTpWarps - 1) / kTpWarps;
-  const uint64_t want = (uint64_t) sms * 8u;
-  const unsigned blocks = (unsigned) (ctas < want ? ctas : want);
-  if (format == FMT_S16) {
-    if (tpf == 4) truepeak_kernel<FMT_S16, 4><<<blocks, kTpThreads, 0, stream>>>(p);
-    else truepeak_kernel<FMT_S16, 2><<<blocks, kTpThreads, 0, stream>>>(p);
-  } else {
-    if (tpf == 4) truepeak_kernel<FMT_F32, 4><<<blocks, kTpThreads, 0, stream>>>(p);
-    else truepeak_kernel<FMT_F32, 2><<<blocks, kTpThreads, 0, stream>>>(p);
-  }
-  return cudaGetLastError();
+  if (format == FMT_S16)
+    return tpf == 4 ? launch_truepeak_t<FMT_S16, 4>(p, sms, stream)
+                    : launch_truepeak_t<FMT_S16, 2>(p, sms, stream);
+  return tpf == 4 ? launch_truepeak_t<FMT_F32, 4>(p, sms, stream)
+                  : launch_truepeak_t<FMT_F32, 2>(p, sms, stream);
 }
 
 // --------------------------------------------------------- post-processing

@@ -34,8 +34,7 @@ struct PostSizes {
 };
 
 // One sweep launch; `p` carries the group's constants and device pointers.
-cudaError_t launch_sweep(const SweepParams& p, uint32_t format, int tpf, uint32_t kmax,
-                         cudaStream_t stream);
+cudaError_t launch_sweep(const SweepParams& p, uint32_t format, int tpf, cudaStream_t stream);
 // True-peak pass of the same group (no-op for rates without an interpolator);
 // must follow the group's sweep on the stream.
 cudaError_t launch_truepeak(const SweepParams& p, uint32_t format, int tpf, uint32_t sms,

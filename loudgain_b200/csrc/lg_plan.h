@@ -39,7 +39,6 @@ struct SweepGroup {
   uint32_t channels;
   uint32_t first_warp;   // into Plan::work
   uint32_t nwarps;
-  uint32_t kmax;         // cp.async copies per lane and stage, rounded to 3 / 6 / 12
   uint64_t mrec_base;    // first word of the group's iteration maxima (tpf != 0)
   SweepParams params;
 };
@@ -64,8 +63,10 @@ inline uint32_t sweep_warp_smem_host(uint32_t channels, uint32_t fb) {
   return kRing * cpw * ((units | 1u) << 4);
 }
 
+// force_k > 0 pins the chunks per 100 ms slot (tuning / tests); it is
+// clamped to the nearest divisor of s100 that keeps the chunk >= 4 warm-ups.
 inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, uint64_t target_tasks,
-                       Plan& p) {
+                       Plan& p, int force_k = 0) {
   p = Plan();
   p.nalbums = nalbums;
   // -- chunk length from the total amount of work
@@ -91,7 +92,12 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, uint64_t t
     const int W = warmup_frames(kd);
     int min_len = 4 * W;
     if ((uint64_t) min_len < want_len) min_len = (int) (want_len > (uint64_t) s100 ? s100 : want_len);
-    const int k = pick_chunks_per_slot(s100, min_len);
+    int k = pick_chunks_per_slot(s100, min_len);
+    if (force_k > 0) {
+      k = 1;
+      for (int d = 1; d <= force_k; ++d)
+        if (s100 % d == 0 && s100 / d >= 4 * W) k = d;
+    }
     const auto key = std::make_tuple(t.samplerate, k, t.format);
     auto it = coef_index.find(key);
     if (it == coef_index.end()) {
@@ -145,10 +151,9 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, uint64_t t
     sp.units = sp.stage_row_bytes >> 4;
     sp.row_stride = (sp.units | 1u) << 4;
     sp.stage_bytes = sp.cpw * sp.row_stride;
-    sp.ncopies = sp.cpw * sp.units;
+    sp.ring_bytes = kRing * sp.stage_bytes;
+    sp.kcopies = (sp.units + sp.lpc - 1) / sp.lpc;
     sp.warp_smem = sweep_warp_smem_host(t0.channels, t0.fb);
-    const uint32_t k = (sp.ncopies + 31u) / 32u;
-    g.kmax = k <= 3 ? 3 : (k <= 6 ? 6 : 12);
     const long long stage_frames =
         (long long) ((t0.niters + kItersPerStage - 1) / kItersPerStage) * kStageFrames;
     for (uint32_t i : kv.second) {
