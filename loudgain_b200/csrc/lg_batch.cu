@@ -135,9 +135,11 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // Two full waves of resident threads when the audio is long enough.
-  int force_k = 0;
-  if (const char* e = getenv("LOUDGAIN_B200_CHUNKS_PER_SLOT")) force_k = atoi(e);
-  build_plan(in.data(), ntracks, nalbums, (uint64_t) sms * 2048u, b->plan, force_k);
+  PlanOptions opt;
+  opt.target_tasks = (uint64_t) sms * 2048u;
+  if (const char* e = getenv("LOUDGAIN_B200_CHUNKS_PER_SLOT")) opt.force_k = atoi(e);   // tuning
+  if (const char* e = getenv("LOUDGAIN_B200_SCALAR_SWEEP")) opt.allow_packed = atoi(e) == 0;
+  build_plan(in.data(), ntracks, nalbums, opt, b->plan);
   const Plan& p = b->plan;
   b->abs_gate = pow(10.0, (-70.0 + 0.691) / 10.0);
   bool ok = upload(p.tracks, &b->d_tracks, b->stream) && upload(p.coefs, &b->d_coefs, b->stream) &&
@@ -189,7 +191,8 @@ extern "C" LG_EXPORT int lgb_batch_run(lgb_batch* b) {
     SweepParams sp = g.params;
     sp.tracks = t.tracks; sp.work = t.work + g.first_warp; sp.recs = t.recs; sp.peaks = t.peaks;
     sp.mrec = b->d_mrec + g.mrec_base;
-    e = launch_sweep(sp, g.format, g.tpf, b->stream);
+    e = sp.packed ? launch_sweep_pair(sp, g.format, g.tpf, b->stream)
+                  : launch_sweep(sp, g.format, g.tpf, b->stream);
     if (e != cudaSuccess) { set_error("launch_sweep", e); return 1; }
   }
   if (b->timing) { cudaEventRecord(b->ev1, b->stream); b->timed_run_pending = true; }
@@ -198,7 +201,8 @@ extern "C" LG_EXPORT int lgb_batch_run(lgb_batch* b) {
     SweepParams sp = g.params;
     sp.tracks = t.tracks; sp.work = t.work + g.first_warp; sp.recs = t.recs; sp.peaks = t.peaks;
     sp.mrec = b->d_mrec + g.mrec_base;
-    e = launch_truepeak(sp, g.format, g.tpf, b->sms, b->stream);
+    e = sp.packed ? launch_truepeak_pair(sp, g.format, g.tpf, b->sms, b->stream)
+                  : launch_truepeak(sp, g.format, g.tpf, b->sms, b->stream);
     if (e != cudaSuccess) { set_error("launch_truepeak", e); return 1; }
   }
   if (b->timing) cudaEventRecord(b->ev2, b->stream);

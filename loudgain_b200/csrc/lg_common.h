@@ -38,6 +38,18 @@ constexpr int kPairsPerStage = LG_PAIRS_PER_STAGE;
 constexpr int kItersPerStage = 2 * kPairsPerStage;
 constexpr int kStageFrames = kIter * kItersPerStage;
 constexpr int kRing = LG_RING;      // staging ring depth (stages in flight + 1)
+// The packed sweep (lg_pair.cu: even channel counts, one lane = one chunk and
+// one channel PAIR) stages kPairPPS iteration pairs per row and stage through
+// a ring of kPairRing stages.
+#ifndef LG_PAIR_PPS
+#define LG_PAIR_PPS 2
+#endif
+#ifndef LG_PAIR_RING
+#define LG_PAIR_RING 2
+#endif
+constexpr int kPairPPS = LG_PAIR_PPS;
+constexpr int kPairRing = LG_PAIR_RING;
+constexpr int kPairStageFrames = kPairFrames * kPairPPS;
 // Longest per-phase tap count (49-tap prototype / factor 2, zero taps dropped).
 constexpr int kMaxTaps = 24;
 // A lane starts on a 16-byte boundary of the track, i.e. on a multiple of
@@ -161,8 +173,9 @@ struct SweepParams {
   int32_t W, L, niters, aq;
   uint32_t npairs;         // (niters + 1) / 2: iteration pairs per lane
   uint32_t channels, fb;
-  uint32_t lpc;            // lanes per chunk = min(channels, 32)
-  uint32_t cpw;            // chunks per warp
+  uint32_t packed;         // 1: packed sweep, a lane holds channels (2j, 2j+1) of its chunk
+  uint32_t lpc;            // lanes per chunk = min(channels, 32); channels / 2 when packed
+  uint32_t cpw;            // chunks per warp = 32 / lpc
   // staging: bytes one row advances per stage, 16-byte units of that piece,
   // padded row stride in shared memory (odd number of units), bytes per stage
   // buffer and per ring, copies per lane and stage (ceil(units / lpc))
@@ -173,8 +186,10 @@ struct SweepParams {
   ChunkRec* recs;
   uint32_t* peaks;
   // Iteration maxima for the true-peak pass: one word per (warp, pair, lane),
-  // index (warp * npairs + pair) * 32 + lane, two 16-bit codes each
-  // (lg_sweep.cuh: peak_code).  Unused when the rate has no interpolator.
+  // index (warp * npairs + pair) * 32 + lane, two 16-bit codes each: the
+  // lane's two iterations of the pair (lg_sweep.cuh: peak_code), or, when
+  // packed, the pair's maximum for each of the lane's two channels
+  // (lg_sweep.cuh: pair_code).  Unused when the rate has no interpolator.
   uint32_t* mrec;
 };
 

@@ -1,0 +1,62 @@
+// lg_device.cuh -- small device-side helpers shared by the sweep kernels
+// (lg_kernels.cu, lg_pair.cu): cp.async staging, sample extraction, register
+// pinning.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lg {
+
+// LG_CPASYNC_L2 (tuning): L2 prefetch size hint of the streaming copies, e.g. .L2::128B
+#ifndef LG_CPASYNC_L2
+#define LG_CPASYNC_L2 ""
+#endif
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global" LG_CPASYNC_L2 " [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ int sext_half(uint32_t w, uint32_t sel) {
+  int r;
+  asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(w), "r"(sel));
+  return r;
+}
+
+// Shared-memory loads by 32-bit shared address (a pinned generic pointer would
+// compile to generic LD instructions).
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// Makes a per-lane invariant opaque to the compiler, so that it is kept in a
+// register instead of being recomputed (from S2R / parameter loads) inside
+// the streaming loop.
+__device__ __forceinline__ uint32_t pin(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
+template <class T>
+__device__ __forceinline__ T* pin(T* v) { asm volatile("" : "+l"(v)); return v; }
+
+}  // namespace lg

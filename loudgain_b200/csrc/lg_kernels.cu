@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "lg_common.h"
+#include "lg_device.cuh"
 #include "lg_kernels.h"
 #include "lg_post.cuh"
 #include "lg_sweep.cuh"
@@ -39,27 +40,6 @@ namespace lg {
 //    and pair).  truepeak_kernel evaluates the polyphase FIR afterwards, only
 //    on the iterations whose bound ||c||_1 * max|x| exceeds the channel's
 //    final sample peak.
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() {
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-__device__ __forceinline__ int sext_half(uint32_t w, uint32_t sel) {
-  int r;
-  asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(w), "r"(sel));
-  return r;
-}
 
 // How a lane finds its samples in a staged row.
 enum RowLayout : int {
@@ -126,13 +106,6 @@ __device__ __forceinline__ void smem_load_iter(const unsigned char* rowp, uint32
     for (int i = 0; i < kIter; ++i) x[i] = *reinterpret_cast<const float*>(q + i * fb);
   }
 }
-
-// Makes a per-lane invariant opaque to the compiler, so that it is kept in a
-// register instead of being recomputed (from S2R / parameter loads) inside
-// the streaming loop.
-__device__ __forceinline__ uint32_t pin(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
-template <class T>
-__device__ __forceinline__ T* pin(T* v) { asm volatile("" : "+l"(v)); return v; }
 
 #ifndef LG_SWEEP_MINBLOCKS
 #define LG_SWEEP_MINBLOCKS 8

@@ -39,6 +39,11 @@ cudaError_t launch_sweep(const SweepParams& p, uint32_t format, int tpf, cudaStr
 // must follow the group's sweep on the stream.
 cudaError_t launch_truepeak(const SweepParams& p, uint32_t format, int tpf, uint32_t sms,
                             cudaStream_t stream);
+// The same two passes for groups with an even channel count (lg_pair.cu:
+// packed FP32, one lane per chunk and channel pair; SweepParams::packed).
+cudaError_t launch_sweep_pair(const SweepParams& p, uint32_t format, int tpf, cudaStream_t stream);
+cudaError_t launch_truepeak_pair(const SweepParams& p, uint32_t format, int tpf, uint32_t sms,
+                                 cudaStream_t stream);
 cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t stream);
 // Gated loudness + range for `nqueries` queries; all pointers are device memory.
 cudaError_t launch_queries(const BlockList* lists, const Query* queries, const uint32_t* members,

@@ -1,0 +1,618 @@
+// lg_pair.cu -- the packed sweep and its true-peak pass, for tracks with an
+// even channel count (stereo above all: what /root/reference/src/scan.c:448
+// feeds through ebur128_add_frames_short for almost every file).
+//
+// Same algorithm and the same per-channel FP32 operation sequence as
+// sweep_kernel (lg_kernels.cu, lg_sweep.cuh) -- the results are bit-identical --
+// but one lane owns one chunk and one channel PAIR (2j, 2j+1) and runs both
+// channels through Blackwell's packed FP32 instructions (FFMA2 / FADD2: two
+// independent IEEE FMAs per issue slot, the broadcast filter constant coming
+// from a uniform register).  The scalar kernel is bound by instruction issue
+// (ncu: 84 % of the issue slots busy at 41 % of HBM bandwidth); packing halves
+// the issue slots of the 11 FMA-pipe operations per sample, so the FMA pipe
+// itself (128 lanes per clock and SM) becomes the limit.
+//
+// A 16-bit stereo frame is one 32-bit word, so the sample peak of both
+// channels is tracked on the raw words with packed 16-bit integer min/max
+// (VIMNMX3.S16x2, two frames per instruction).
+//
+// True peak: the sweep leaves max |x| per (lane, iteration pair, channel) as a
+// 16-bit code; truepeak_pair_kernel evaluates the polyphase FIR only on the
+// pairs whose bound ||c||_1 * max|x| exceeds the channel's final sample peak.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "lg_common.h"
+#include "lg_device.cuh"
+#include "lg_kernels.h"
+#include "lg_sweep.cuh"
+
+namespace lg {
+
+// How a lane finds the frames of its channel pair in a staged row.
+enum PairLayout : int {
+  PAIR_S16_STEREO = 0,   // frame = one 32-bit word, 128-bit loads of 4 frames
+  PAIR_F32_STEREO = 1,   // frame = 8 bytes, 128-bit loads of 2 frames
+  PAIR_S16_EVEN = 2,     // 32-bit load per frame, stride = frame bytes
+  PAIR_F32_EVEN = 3,     // 64-bit load per frame
+};
+
+template <int LAYOUT>
+__host__ __device__ constexpr int pair_format() {
+  return (LAYOUT == PAIR_S16_STEREO || LAYOUT == PAIR_S16_EVEN) ? (int) FMT_S16 : (int) FMT_F32;
+}
+
+// Everything one lane carries through its chunk: .x = channel 2j, .y = 2j+1.
+struct PairCtx {
+  float2 d1, w1, w2, v1, v2;     // filter state (lg_sweep.cuh: KState)
+  float2 yr, yi;                 // running mode sums
+  double e0x, e0y;
+  float2 pd, pw, qd, qw;         // state snapshots
+  int f_lo, f_hi;
+};
+
+__device__ __forceinline__ float2 bc2(float v) { return make_float2(v, v); }
+
+// lg_sweep.cuh: k_step, both channels at once.  d - d1 is written as
+// fma(-1, d1, d): one rounding, the same value as the scalar subtraction.
+__device__ __forceinline__ float2 k_step2(PairCtx& s, const float2 x, const SweepParams& k) {
+  const float2 t = __ffma2_rn(bc2(k.ne2), s.w2, x);
+  const float2 d = __ffma2_rn(bc2(k.c), s.d1, t);
+  const float2 w = __fadd2_rn(s.w1, d);
+  const float2 yh = __ffma2_rn(bc2(-1.0f), s.d1, d);
+  const float2 u = __ffma2_rn(bc2(k.np2), s.v2, yh);
+  const float2 v = __ffma2_rn(bc2(k.np1), s.v1, u);
+  const float2 y = __ffma2_rn(bc2(k.q2), s.v2, __ffma2_rn(bc2(k.q1), s.v1, v));
+  s.w2 = s.w1; s.w1 = w; s.d1 = d;
+  s.v2 = s.v1; s.v1 = v;
+  return y;
+}
+
+// lg_sweep.cuh: iter_fast.
+__device__ __forceinline__ void iter_fast2(PairCtx& c, const SweepParams& k, const float2* x, int f0) {
+  float2 e = bc2(0.0f), sr = bc2(0.0f), si = bc2(0.0f);
+#pragma unroll
+  for (int i = 0; i < kIter; ++i) {
+    const float2 y = k_step2(c, x[i], k);
+    e = __ffma2_rn(y, y, e);
+    sr = __ffma2_rn(y, bc2(k.lam_re[i]), sr);
+    si = __ffma2_rn(y, bc2(k.lam_im[i]), si);
+  }
+  c.e0x += (double) e.x;
+  c.e0y += (double) e.y;
+  // mode_accumulate: fma(-yi, rot_im, sr) == fma(yi, -rot_im, sr)
+  const float2 nr = __ffma2_rn(c.yr, bc2(k.rot_re), __ffma2_rn(c.yi, bc2(-k.rot_im), sr));
+  const float2 ni = __ffma2_rn(c.yr, bc2(k.rot_im), __ffma2_rn(c.yi, bc2(k.rot_re), si));
+  c.yr = nr;
+  c.yi = ni;
+  if (f0 + kIter == c.f_hi) { c.qd = c.d1; c.qw = c.w2; }
+}
+
+// lg_sweep.cuh: iter_warm (filter state only).
+__device__ __forceinline__ void iter_warm2(PairCtx& c, const SweepParams& k, const float2* x) {
+#pragma unroll
+  for (int i = 0; i < kIter; ++i) (void) k_step2(c, x[i], k);
+  c.pd = c.d1; c.pw = c.w2;
+}
+
+// One channel of the lane as the scalar context of lg_sweep.cuh, for the few
+// masked iterations at the chunk edges.
+template <int H>
+__device__ __forceinline__ float pick(const float2 v) { return H ? v.y : v.x; }
+template <int H>
+__device__ __forceinline__ void put(float2& v, float s) { if (H) v.y = s; else v.x = s; }
+
+template <int H>
+__device__ __forceinline__ void masked_half(PairCtx& c, const SweepParams& k, const float2* x2, int f0) {
+  LaneCtx s;
+  s.st.d1 = pick<H>(c.d1); s.st.w1 = pick<H>(c.w1); s.st.w2 = pick<H>(c.w2);
+  s.st.v1 = pick<H>(c.v1); s.st.v2 = pick<H>(c.v2);
+  s.sp = 0.0f;
+  s.yr = pick<H>(c.yr); s.yi = pick<H>(c.yi);
+  s.e0 = H ? c.e0y : c.e0x;
+  s.pd = pick<H>(c.pd); s.pw = pick<H>(c.pw); s.qd = pick<H>(c.qd); s.qw = pick<H>(c.qw);
+  s.f_lo = c.f_lo; s.f_hi = c.f_hi;
+  float x[kIter];
+#pragma unroll
+  for (int i = 0; i < kIter; ++i) x[i] = pick<H>(x2[i]);
+  (void) iter_masked(s, k, x, f0);
+  put<H>(c.d1, s.st.d1); put<H>(c.w1, s.st.w1); put<H>(c.w2, s.st.w2);
+  put<H>(c.v1, s.st.v1); put<H>(c.v2, s.st.v2);
+  put<H>(c.yr, s.yr); put<H>(c.yi, s.yi);
+  if (H) c.e0y = s.e0; else c.e0x = s.e0;
+  put<H>(c.pd, s.pd); put<H>(c.pw, s.pw); put<H>(c.qd, s.qd); put<H>(c.qw, s.qw);
+}
+
+// Per-pair maxima of the lane's two channels.  16-bit input: packed signed
+// max / min of the raw frame words; float input: two running |x| maxima.
+template <int FMT> struct PairPeak;
+template <> struct PairPeak<FMT_S16> {
+  uint32_t mx, mn;               // packed s16x2
+  __device__ __forceinline__ void reset() { mx = 0u; mn = 0u; }
+  __device__ __forceinline__ void words(uint32_t a, uint32_t b) {
+    mx = __vimax3_s16x2(mx, a, b);
+    mn = __vimin3_s16x2(mn, a, b);
+  }
+  // max |x| per channel: 0 .. 32768.  mx >= 0 >= mn per half; the negation
+  // is done on zero-extended halves so that |-32768| = 32768 survives (a
+  // 16-bit negate would wrap it).
+  __device__ __forceinline__ void get(int& ax, int& ay) const {
+    const uint32_t nlo = (0u - (mn & 0xffffu)) & 0xffffu, nhi = (0u - (mn >> 16)) & 0xffffu;
+    ax = (int) max(mx & 0xffffu, nlo);
+    ay = (int) max(mx >> 16, nhi);
+  }
+};
+template <> struct PairPeak<FMT_F32> {
+  float px, py;
+  __device__ __forceinline__ void reset() { px = 0.0f; py = 0.0f; }
+  __device__ __forceinline__ void frames(const float2 a, const float2 b) {
+    px = fmaxf(px, fmaxf(fabsf(a.x), fabsf(b.x)));
+    py = fmaxf(py, fmaxf(fabsf(a.y), fabsf(b.y)));
+  }
+};
+
+// Loads one iteration (kIter frames) of the lane's channel pair from the
+// staged row and folds the raw samples into the pair's maxima.
+template <int LAYOUT>
+__device__ __forceinline__ void load_iter2(const uint32_t rowp, uint32_t fb, uint32_t chl,
+                                           float2* x, PairPeak<pair_format<LAYOUT>()>& pk) {
+  if constexpr (LAYOUT == PAIR_S16_STEREO) {
+#pragma unroll
+    for (int u = 0; u < kIter / 4; ++u) {
+      const uint4 v = lds128(rowp + 16u * u);
+      pk.words(v.x, v.y);
+      pk.words(v.z, v.w);
+      x[4 * u + 0] = make_float2((float) sext_half(v.x, 0x9910u), (float) sext_half(v.x, 0xBB32u));
+      x[4 * u + 1] = make_float2((float) sext_half(v.y, 0x9910u), (float) sext_half(v.y, 0xBB32u));
+      x[4 * u + 2] = make_float2((float) sext_half(v.z, 0x9910u), (float) sext_half(v.z, 0xBB32u));
+      x[4 * u + 3] = make_float2((float) sext_half(v.w, 0x9910u), (float) sext_half(v.w, 0xBB32u));
+    }
+  } else if constexpr (LAYOUT == PAIR_F32_STEREO) {
+#pragma unroll
+    for (int u = 0; u < kIter / 2; ++u) {
+      const uint4 v = lds128(rowp + 16u * u);
+      x[2 * u] = make_float2(__uint_as_float(v.x), __uint_as_float(v.y));
+      x[2 * u + 1] = make_float2(__uint_as_float(v.z), __uint_as_float(v.w));
+      pk.frames(x[2 * u], x[2 * u + 1]);
+    }
+  } else if constexpr (LAYOUT == PAIR_S16_EVEN) {
+    const uint32_t q = rowp + chl * 4u;
+#pragma unroll
+    for (int i = 0; i < kIter; i += 2) {
+      const uint32_t a = lds32(q + i * fb);
+      const uint32_t b = lds32(q + (i + 1) * fb);
+      pk.words(a, b);
+      x[i] = make_float2((float) sext_half(a, 0x9910u), (float) sext_half(a, 0xBB32u));
+      x[i + 1] = make_float2((float) sext_half(b, 0x9910u), (float) sext_half(b, 0xBB32u));
+    }
+  } else {
+    const uint32_t q = rowp + chl * 8u;
+#pragma unroll
+    for (int i = 0; i < kIter; i += 2) {
+      const uint2 a = lds64(q + i * fb), b = lds64(q + (i + 1) * fb);
+      x[i] = make_float2(__uint_as_float(a.x), __uint_as_float(a.y));
+      x[i + 1] = make_float2(__uint_as_float(b.x), __uint_as_float(b.y));
+      pk.frames(x[i], x[i + 1]);
+    }
+  }
+}
+
+#ifndef LG_PAIR_MINBLOCKS
+#define LG_PAIR_MINBLOCKS 4
+#endif
+
+template <int LAYOUT, bool TP>
+__global__ void __launch_bounds__(kSweepThreads, LG_PAIR_MINBLOCKS)
+sweep_pair_kernel(const __grid_constant__ SweepParams P) {
+  constexpr int FMT = pair_format<LAYOUT>();
+  constexpr bool STEREO = LAYOUT == PAIR_S16_STEREO || LAYOUT == PAIR_F32_STEREO;
+  extern __shared__ __align__(16) unsigned char smem_all[];
+  const uint32_t wic = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + wic;
+  if (warp >= P.nwarps) return;                // whole warps leave; no CTA barrier below
+  unsigned char* sm = smem_all + wic * P.warp_smem;
+
+  const WarpWork ww = P.work[warp];
+  const Track& tr = P.tracks[ww.track];
+  const int W = P.W, L = P.L;
+  const uint32_t C = P.channels, fb = P.fb;
+  const long long frames = (long long) tr.frames;
+  const unsigned char* pcm = reinterpret_cast<const unsigned char*>(tr.pcm);
+
+  const uint32_t lpc = STEREO ? 1u : P.lpc;    // lanes per chunk = channel pairs
+  const uint32_t slot = lane / lpc;
+  const uint32_t chl = lane - slot * lpc;      // channel pair within the chunk
+  const uint32_t chunk = ww.first_chunk + slot;
+  const bool compute = slot < P.cpw;
+  const bool active = compute && chunk < tr.nchunks;
+
+  // ---- lane state
+  const LaneGeom geo = lane_geometry(frames, L, W, P.aq, chunk);
+  PairCtx c;
+  c.d1 = c.w1 = c.w2 = c.v1 = c.v2 = bc2(0.0f);
+  c.yr = c.yi = bc2(0.0f);
+  c.e0x = c.e0y = 0.0;
+  c.pd = c.pw = c.qd = c.qw = bc2(0.0f);
+  c.f_lo = W + geo.o;
+  c.f_hi = c.f_lo + L;
+  const uint32_t my_row = pin((uint32_t) __cvta_generic_to_shared(sm) + slot * P.row_stride);
+
+  // ---- staging.  Per stage every row receives one contiguous piece of
+  // kPairStageFrames frames, moved with 16-byte cp.async copies.
+  //
+  // Stereo, interior warps (every byte they stage lies inside the track): kLPR
+  // adjacent lanes copy kLPR adjacent units of ONE row per instruction, so an
+  // instruction touches 32 / kLPR rows with 16 * kLPR contiguous bytes each
+  // (fewer L1 tag look-ups and L2 sector requests than one row per lane); the
+  // rows are taken in kLPR groups, lane l serving rows g * (32 / kLPR) + l / kLPR.
+  //
+  // Other layouts, and warps at a track boundary (zero-filling form): the lpc
+  // lanes of a row copy its units interleaved.
+  constexpr uint32_t kUnits = STEREO ? (uint32_t) (kPairStageFrames * (FMT == FMT_S16 ? 4 : 8) / 16) : 0u;
+  constexpr uint32_t kLPR = STEREO ? (kUnits % 4u == 0u ? 4u : 2u) : 1u;
+  constexpr uint32_t kRowsPerCopy = 32u / kLPR;
+  constexpr uint32_t kRowStride = ((kUnits | 1u) << 4);
+  const uint32_t ustride = lpc << 4;
+  const long long row_byte0 = geo.a * (long long) fb + (chl << 4);
+  const long long track_bytes = frames * (long long) fb;
+  const bool interior = ww.interior != 0;
+  const bool coop = STEREO && interior;
+  const uint32_t ncopy = P.kcopies;
+  const uint32_t sm_base = (uint32_t) __cvta_generic_to_shared(sm);
+  const uint32_t dst_row = pin(sm_base + slot * P.row_stride + (chl << 4));
+  const unsigned char* src = pcm + row_byte0;          // own row (boundary warps, other layouts)
+  // cooperative mapping: this lane's unit column and its row in every group
+  const uint32_t q = lane & (kLPR - 1u), rb = lane / kLPR;
+  const uint32_t dst_coop = pin(sm_base + rb * kRowStride + (q << 4));
+  const unsigned char* src_g[kLPR];
+#pragma unroll
+  for (uint32_t g = 0; g < kLPR; ++g) {
+    const long long a_row = __shfl_sync(0xffffffffu, geo.a, (int) (g * kRowsPerCopy + rb));
+    src_g[g] = pcm + a_row * (long long) fb + (q << 4);
+  }
+  uint32_t pf_off = 0;
+
+  auto prefetch = [&]() {
+#ifdef LG_PAIR_NOLOAD   // ablation: no HBM traffic, compute on whatever is in shared memory
+    if (false) {
+#else
+    if (coop) {
+      const uint32_t dst = dst_coop + pf_off;
+#pragma unroll
+      for (uint32_t g = 0; g < kLPR; ++g) {
+#pragma unroll
+        for (uint32_t j = 0; j < (STEREO ? kUnits / kLPR : 1u); ++j)
+          cp_async16(dst + g * kRowsPerCopy * kRowStride + j * (kLPR << 4), src_g[g] + j * (kLPR << 4));
+        src_g[g] += P.stage_row_bytes;
+      }
+    } else if (compute) {
+#endif
+      const uint32_t dst = dst_row + pf_off;
+#pragma unroll 1
+      for (uint32_t k = 0; k < ncopy; ++k) {
+        if (chl + k * lpc >= P.units) break;
+        const long long g = (src - pcm) + (long long) (k * ustride);
+        long long ok = g < 0 ? 0 : track_bytes - g;
+        ok = ok < 0 ? 0 : (ok > 16 ? 16 : ok);
+        cp_async16_zfill(dst + k * ustride, pcm + (ok ? g : 0), (uint32_t) ok);
+      }
+    }
+    src += P.stage_row_bytes;
+    pf_off += P.stage_bytes;
+    if (pf_off == P.ring_bytes) pf_off = 0;
+  };
+
+  uint32_t* mrec = pin(P.mrec + (size_t) warp * P.npairs * 32u + lane);   // advanced pair by pair
+
+  const uint32_t niters = (uint32_t) P.niters;
+  const uint32_t npairs = P.npairs;
+  const uint32_t nstages = (npairs + kPairPPS - 1) / kPairPPS;
+  // Pairs whose two iterations are both "fast" for every lane of the warp.
+  const int lfast = ww.lmin_valid < L ? ww.lmin_valid : L;
+  const uint32_t fast_lo = (uint32_t) ((W + P.aq - 1 + kPairFrames - 1) / kPairFrames);
+  const uint32_t fast_hi = (uint32_t) ((W + lfast) / kPairFrames);     // exclusive
+  const uint32_t warm_hi = (uint32_t) (W / kPairFrames);               // pairs entirely in the warm-up
+#pragma unroll
+  for (int i = 0; i < kPairRing - 1; ++i) {
+    if ((uint32_t) i < nstages) prefetch();
+    cp_async_commit();
+  }
+
+  // lane-wide sample peak, raw units: integer for 16-bit input
+  int spx_i = 0, spy_i = 0;
+  float spx_f = 0.0f, spy_f = 0.0f;
+
+  uint32_t cs_off = 0;
+  uint32_t pair = 0;
+  for (uint32_t s = 0; s < nstages; ++s) {
+    cp_async_wait<kPairRing - 2>();
+    __syncwarp();                // everyone's data has landed; the previous stage is consumed
+    if (s + kPairRing - 1 < nstages) prefetch();
+    cp_async_commit();
+    const uint32_t sbuf = my_row + cs_off;
+    cs_off += P.stage_bytes;
+    if (cs_off == P.ring_bytes) cs_off = 0;
+#pragma unroll 1
+    for (uint32_t pr = 0; pr < (uint32_t) kPairPPS; ++pr, ++pair) {
+      if (pair >= npairs) break;
+      const uint32_t buf = sbuf + pr * kPairFrames * fb;
+      PairPeak<FMT> pk;
+      pk.reset();
+#ifdef LG_PAIR_NOCOMP   // ablation: staging only
+      if (false) {
+#else
+      if (compute) {
+#endif
+        if (pair >= fast_lo && pair < fast_hi) {
+          // ---- interior of the chunk: straight-line packed code
+          float2 x0[kIter], x1[kIter];
+          load_iter2<LAYOUT>(buf, fb, chl, x0, pk);
+          load_iter2<LAYOUT>(buf + kIter * fb, fb, chl, x1, pk);
+          const int f0 = (int) (pair * kPairFrames);
+          iter_fast2(c, P, x0, f0);
+          iter_fast2(c, P, x1, f0 + kIter);
+        } else if (pair < warm_hi) {
+          float2 x0[kIter], x1[kIter];
+          load_iter2<LAYOUT>(buf, fb, chl, x0, pk);
+          load_iter2<LAYOUT>(buf + kIter * fb, fb, chl, x1, pk);
+          iter_warm2(c, P, x0);
+          iter_warm2(c, P, x1);
+        } else {
+          // ---- chunk edges: one iteration at a time, scalar masked code per channel
+#pragma unroll 1
+          for (uint32_t it = 0; it < 2u; ++it) {
+            const uint32_t iter = pair * 2u + it;
+            if (iter >= niters) break;
+            const int f0 = (int) (iter * kIter);
+            float2 x[kIter];
+            load_iter2<LAYOUT>(buf + it * kIter * fb, fb, chl, x, pk);
+            if (f0 + kIter <= W) {
+              iter_warm2(c, P, x);
+            } else {
+              masked_half<0>(c, P, x, f0);
+              masked_half<1>(c, P, x, f0);
+            }
+          }
+        }
+      }
+      uint32_t cx, cy;
+      if constexpr (FMT == FMT_S16) {
+        int ax, ay;
+        pk.get(ax, ay);
+        spx_i = max(spx_i, ax); spy_i = max(spy_i, ay);
+        cx = (uint32_t) ax; cy = (uint32_t) ay;
+      } else {
+        spx_f = fmaxf(spx_f, pk.px); spy_f = fmaxf(spy_f, pk.py);
+        cx = peak_code(pk.px); cy = peak_code(pk.py);
+      }
+      if (TP) { *mrec = cx | (cy << 16); mrec += 32; }
+    }
+  }
+  cp_async_wait<0>();
+
+  const uint32_t ch = 2u * chl;
+  if (active) {
+    ChunkRec v;
+    v.e0 = c.e0x; v.yr = c.yr.x; v.yi = c.yi.x;
+    v.pd = c.pd.x; v.pw = c.pw.x; v.qd = c.qd.x; v.qw = c.qw.x;
+    ChunkRec* out = P.recs + tr.rec_base + (uint64_t) chunk * C + ch;
+    out[0] = v;
+    v.e0 = c.e0y; v.yr = c.yr.y; v.yi = c.yi.y;
+    v.pd = c.pd.y; v.pw = c.pw.y; v.qd = c.qd.y; v.qw = c.qw.y;
+    out[1] = v;
+  }
+  // Sample peak: non-negative floats order like their bit patterns.  Reduce
+  // over the lanes of the warp that hold the same channel pair.
+  const float spx = FMT == FMT_S16 ? (float) spx_i : spx_f;
+  const float spy = FMT == FMT_S16 ? (float) spy_i : spy_f;
+  const unsigned peers = __match_any_sync(0xffffffffu, compute ? chl : 0xffffu);
+  const uint32_t bx = __reduce_max_sync(peers, active ? __float_as_uint(spx) : 0u);
+  const uint32_t by = __reduce_max_sync(peers, active ? __float_as_uint(spy) : 0u);
+  if (compute && lane == (uint32_t) (__ffs(peers) - 1)) {
+    atomicMax(P.peaks + 2 * (tr.peak_base + ch), bx);
+    atomicMax(P.peaks + 2 * (tr.peak_base + ch + 1), by);
+  }
+}
+
+template <int LAYOUT, bool TP>
+static cudaError_t launch_pair_k(const SweepParams& p, cudaStream_t stream) {
+  const uint32_t wpb = kSweepThreads / 32;
+  const uint32_t blocks = (p.nwarps + wpb - 1) / wpb;
+  const size_t smem = (size_t) p.warp_smem * wpb;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(sweep_pair_kernel<LAYOUT, TP>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(sweep_pair_kernel<LAYOUT, TP>,
+                               cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  sweep_pair_kernel<LAYOUT, TP><<<blocks, kSweepThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <int LAYOUT>
+static cudaError_t launch_pair_l(const SweepParams& p, int tpf, cudaStream_t stream) {
+  return tpf ? launch_pair_k<LAYOUT, true>(p, stream) : launch_pair_k<LAYOUT, false>(p, stream);
+}
+
+cudaError_t launch_sweep_pair(const SweepParams& p, uint32_t format, int tpf, cudaStream_t stream) {
+  if (p.nwarps == 0) return cudaSuccess;
+  if (format == FMT_S16)
+    return p.channels == 2 ? launch_pair_l<PAIR_S16_STEREO>(p, tpf, stream)
+                           : launch_pair_l<PAIR_S16_EVEN>(p, tpf, stream);
+  return p.channels == 2 ? launch_pair_l<PAIR_F32_STEREO>(p, tpf, stream)
+                         : launch_pair_l<PAIR_F32_EVEN>(p, tpf, stream);
+}
+
+// -------------------------------------------------------------- true peak
+//
+// Second pass over the pair maxima.  The true peak is a maximum, and a
+// polyphase output cannot exceed ||c||_1 * max|x| over its taps' window; the
+// channel's true peak is at least its sample peak (final by now).  So only
+// pairs whose bound (over the pair and the pair before it, which holds the
+// taps' history) exceeds the channel's current peak can matter -- a few
+// percent of programme material.  Warps are autonomous: a work item is a run
+// of consecutive pairs of one sweep warp, scanning lane = sweep lane.  Pairs
+// that can still matter go into the warp's queue as (track, channel, first
+// frame) and are evaluated 32 at a time, one per lane, re-reading their
+// frames from the PCM (L2 / HBM).  The result is identical to evaluating
+// every frame.
+
+constexpr int kTp2Threads = 128;
+constexpr int kTp2Warps = kTp2Threads / 32;
+constexpr int kTp2Cap = 32 + 64;            // remainder + both channels of one pair per lane
+
+template <int FMT>
+__device__ __forceinline__ float pcm_at(const unsigned char* p) {
+  if (FMT == FMT_S16) return (float) (int) *reinterpret_cast<const short*>(p);
+  return *reinterpret_cast<const float*>(p);
+}
+
+template <int FMT, int TPF>
+__device__ __forceinline__ void tp_pair_evaluate(const SweepParams& P, const uint4 cd) {
+  constexpr int NT = TpTraits<TPF>::kTaps;
+  const Track& tr = P.tracks[cd.x];
+  const long long frames = (long long) tr.frames;
+  const long long t0 = (long long) ((unsigned long long) cd.z | ((unsigned long long) cd.w << 32));
+  const unsigned char* pcm = reinterpret_cast<const unsigned char*>(tr.pcm) +
+                             cd.y * (FMT == FMT_S16 ? 2u : 4u);
+  float m = 0.0f;
+  // two iterations, each with its own window (keeps the register footprint of
+  // the scalar pass)
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    const long long th = t0 + h * kIter;
+    if (th >= frames) break;
+    float win[NT + kIter];
+    if (th >= NT && th + kIter <= frames) {
+      const unsigned char* q = pcm + (th - NT) * (long long) P.fb;
+#pragma unroll
+      for (int k = 0; k < NT + kIter; ++k) win[k] = pcm_at<FMT>(q + (uint32_t) k * P.fb);
+      m = fmaxf(m, tp_window_valid<TPF>(win, kIter));
+    } else {
+#pragma unroll
+      for (int k = 0; k < NT + kIter; ++k) {
+        const long long t = th - NT + k;
+        win[k] = (t >= 0 && t < frames) ? pcm_at<FMT>(pcm + t * (long long) P.fb) : 0.0f;
+      }
+      const long long left = frames - th;
+      m = fmaxf(m, tp_window_valid<TPF>(win, left > kIter ? kIter : (int) left));
+    }
+  }
+  uint32_t* cell = P.peaks + 2 * (tr.peak_base + cd.y) + 1;
+  if (__float_as_uint(m) > __ldcg(cell)) atomicMax(cell, __float_as_uint(m));
+}
+
+template <int FMT, int TPF>
+__global__ void __launch_bounds__(kTp2Threads, 4)
+truepeak_pair_kernel(const __grid_constant__ SweepParams P, const uint32_t seg_pairs) {
+  __shared__ uint4 queue_all[kTp2Warps][kTp2Cap];
+  const uint32_t npairs = P.npairs;
+  const uint32_t lane = threadIdx.x & 31u, wic = threadIdx.x >> 5;
+  uint4* queue = queue_all[wic];
+  const uint32_t nseg = (npairs + seg_pairs - 1) / seg_pairs;
+  const uint64_t nitems = (uint64_t) P.nwarps * nseg;
+  const uint64_t nscan = (uint64_t) gridDim.x * kTp2Warps;
+  uint32_t qn = 0;                       // warp-uniform
+
+  for (uint64_t item = (uint64_t) blockIdx.x * kTp2Warps + wic; item < nitems; item += nscan) {
+    const uint32_t w = (uint32_t) (item / nseg);
+    const uint32_t p_begin = (uint32_t) (item - (uint64_t) w * nseg) * seg_pairs;
+    const uint32_t p_end = p_begin + seg_pairs < npairs ? p_begin + seg_pairs : npairs;
+    // the sweep lane's place in its track
+    const WarpWork ww = P.work[w];
+    const Track& tr = P.tracks[ww.track];
+    const uint32_t slot = lane / P.lpc;
+    const uint32_t ch = 2u * (lane - slot * P.lpc);
+    const uint32_t chunk = ww.first_chunk + slot;
+    const bool ok = slot < P.cpw && chunk < tr.nchunks;
+    const LaneGeom g = lane_geometry((long long) tr.frames, P.L, P.W, P.aq, chunk);
+    const int f_lo = P.W + g.o;
+    const long long left = (long long) tr.frames - g.a;
+    const int f_hi = f_lo + P.L;
+    const int f_end = left < (long long) f_hi ? (left < 0 ? 0 : (int) left) : f_hi;
+
+    const uint32_t* codes = P.mrec + ((size_t) w * npairs) * 32u + lane;
+    uint32_t* cell = P.peaks + 2 * ((ok ? tr.peak_base : 0) + (ok ? ch : 0));
+    const uint2 pk0 = __ldcg(reinterpret_cast<const uint2*>(cell));       // (sample, true) peak
+    const uint2 pk1 = __ldcg(reinterpret_cast<const uint2*>(cell + 2));
+    float floor0 = __uint_as_float(pk0.x > pk0.y ? pk0.x : pk0.y);
+    float floor1 = __uint_as_float(pk1.x > pk1.y ? pk1.x : pk1.y);
+    uint32_t prev = p_begin ? __ldcs(codes + (size_t) (p_begin - 1) * 32u) : 0u;
+    uint32_t nxt = __ldcs(codes + (size_t) p_begin * 32u);
+    for (uint32_t p = p_begin; p < p_end; ++p) {
+      const uint32_t code = nxt;
+      if (p + 1 < p_end) nxt = __ldcs(codes + (size_t) (p + 1) * 32u);
+      const uint32_t cm = __vmaxu2(code, prev);      // per channel: this pair and its history
+      prev = code;
+      const int f0 = (int) (p * kPairFrames);
+      const bool own = ok && f0 + kPairFrames > f_lo && f0 < f_end;
+      const bool hit0 = own && P.tp_bound * pair_code_value<FMT>(cm & 0xffffu) > floor0;
+      const bool hit1 = own && P.tp_bound * pair_code_value<FMT>(cm >> 16) > floor1;
+      const unsigned m0 = __ballot_sync(0xffffffffu, hit0);
+      const unsigned m1 = __ballot_sync(0xffffffffu, hit1);
+      if (m0 | m1) {
+        const unsigned below = (1u << lane) - 1u;
+        const long long t0 = g.a + f0;
+        if (hit0)
+          queue[qn + __popc(m0 & below)] =
+              make_uint4(ww.track, ch, (uint32_t) (unsigned long long) t0, (uint32_t) ((unsigned long long) t0 >> 32));
+        qn += __popc(m0);
+        if (hit1)
+          queue[qn + __popc(m1 & below)] =
+              make_uint4(ww.track, ch + 1, (uint32_t) (unsigned long long) t0, (uint32_t) ((unsigned long long) t0 >> 32));
+        qn += __popc(m1);
+        if (qn >= 32u) {
+          __syncwarp();
+          while (qn >= 32u) {
+            qn -= 32u;
+            tp_pair_evaluate<FMT, TPF>(P, queue[qn + lane]);
+          }
+          __syncwarp();
+          floor0 = fmaxf(floor0, __uint_as_float(__ldcg(cell + 1)));
+          floor1 = fmaxf(floor1, __uint_as_float(__ldcg(cell + 3)));
+        }
+      }
+    }
+  }
+  __syncwarp();
+  if (lane < qn) tp_pair_evaluate<FMT, TPF>(P, queue[lane]);
+}
+
+template <int FMT, int TPF>
+static cudaError_t launch_truepeak_pair_t(const SweepParams& p, uint32_t sms, cudaStream_t stream) {
+  static int per_sm = 0;
+  if (!per_sm) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, truepeak_pair_kernel<FMT, TPF>,
+                                                      kTp2Threads, 0) != cudaSuccess || per_sm < 1)
+      per_sm = 4;
+  }
+  // Persistent grid; about four work items per scanning warp, as long as possible.
+  const uint64_t nscan = (uint64_t) sms * per_sm * kTp2Warps;
+  uint64_t nseg = (4 * nscan + p.nwarps - 1) / p.nwarps;
+  if (nseg > p.npairs) nseg = p.npairs;
+  if (nseg < 1) nseg = 1;
+  const uint32_t seg = (uint32_t) ((p.npairs + nseg - 1) / nseg);
+  const uint64_t nitems = (uint64_t) p.nwarps * ((p.npairs + seg - 1) / seg);
+  const uint64_t ctas = (nitems + kTp2Warps - 1) / kTp2Warps;
+  const uint64_t want = (uint64_t) sms * per_sm;
+  truepeak_pair_kernel<FMT, TPF><<<(unsigned) (ctas < want ? ctas : want), kTp2Threads, 0, stream>>>(p, seg);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_truepeak_pair(const SweepParams& p, uint32_t format, int tpf, uint32_t sms,
+                                 cudaStream_t stream) {
+  if (p.nwarps == 0 || tpf == 0) return cudaSuccess;
+  if (format == FMT_S16)
+    return tpf == 4 ? launch_truepeak_pair_t<FMT_S16, 4>(p, sms, stream)
+                    : launch_truepeak_pair_t<FMT_S16, 2>(p, sms, stream);
+  return tpf == 4 ? launch_truepeak_pair_t<FMT_F32, 4>(p, sms, stream)
+                  : launch_truepeak_pair_t<FMT_F32, 2>(p, sms, stream);
+}
+
+}  // namespace lg

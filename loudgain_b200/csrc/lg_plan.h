@@ -7,6 +7,8 @@
 // on the CPU.
 #pragma once
 
+#include <math.h>
+
 #include <map>
 #include <tuple>
 #include <vector>
@@ -56,23 +58,100 @@ struct Plan {
   uint32_t nalbums = 0;
 };
 
-// Shared memory one warp of the sweep needs: its staging ring.
-inline uint32_t sweep_warp_smem_host(uint32_t channels, uint32_t fb) {
-  const uint32_t cpw = chunks_per_warp(channels);
-  const uint32_t units = (kStageFrames * fb) >> 4;
-  return kRing * cpw * ((units | 1u) << 4);
+// Even channel counts run the packed sweep (lg_pair.cu): a lane holds one
+// chunk and one channel pair.
+inline bool track_is_packed(uint32_t channels, bool allow_packed) {
+  return allow_packed && channels >= 2 && (channels & 1u) == 0 && channels <= 64;
 }
 
-// force_k > 0 pins the chunks per 100 ms slot (tuning / tests); it is
-// clamped to the nearest divisor of s100 that keeps the chunk >= 4 warm-ups.
-inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, uint64_t target_tasks,
-                       Plan& p, int force_k = 0) {
+// Resident sweep warps per SM (launch bounds of the two kernels) and the
+// relative cost of one 12-frame iteration of one warp, for the chunk-length
+// search below.
+constexpr uint32_t kScalarWarpsPerSM = 32, kPackedWarpsPerSM = 16;
+constexpr double kScalarIterCost = 1.0, kPackedIterCost = 1.3;
+
+struct PlanOptions {
+  uint64_t target_tasks = 0;   // about 2048 x SM count; 0 = shortest chunks
+  int force_k = 0;             // > 0 pins the chunks per 100 ms slot (tuning / tests)
+  bool allow_packed = true;
+};
+
+// Chunks per 100 ms slot of one track for a wanted chunk length.
+inline int chunks_per_slot_for(int s100, int W, uint64_t want_len, int force_k) {
+  if (force_k > 0) {
+    int k = 1;
+    for (int d = 1; d <= force_k; ++d)
+      if (s100 % d == 0 && s100 / d >= 4 * W) k = d;
+    return k;
+  }
+  int min_len = 4 * W;
+  if ((uint64_t) min_len < want_len) min_len = (int) (want_len > (uint64_t) s100 ? s100 : want_len);
+  return pick_chunks_per_slot(s100, min_len);
+}
+
+// Modelled sweep time of a batch for a wanted chunk length: per launch group
+// (format, rate, channels) the number of waves of resident warps times the
+// iterations per chunk.  A partly filled last wave is cheaper, but not below
+// half a wave (too few warps per SM to keep the pipes busy).
+inline double plan_cost(const TrackIn* in, size_t n, uint64_t want_len, uint32_t sms, bool allow_packed) {
+  struct Acc { uint64_t warps = 0; uint32_t niters = 0; bool packed = false; };
+  std::map<std::tuple<uint32_t, uint32_t, uint32_t>, Acc> groups;
+  for (size_t i = 0; i < n; ++i) {
+    const TrackIn& t = in[i];
+    const int s100 = (int) ((t.samplerate + 5) / 10);
+    const int W = warmup_frames(k_design(t.samplerate));
+    const int k = chunks_per_slot_for(s100, W, want_len, 0);
+    const int L = s100 / k;
+    const uint32_t fb = t.channels * (t.format == FMT_S16 ? 2u : 4u);
+    const bool packed = track_is_packed(t.channels, allow_packed);
+    const uint32_t lpc = packed ? t.channels / 2u : (t.channels < 32u ? t.channels : 32u);
+    const uint32_t cpw = 32u / lpc;
+    const uint64_t nchunks = (t.frames + L - 1) / (uint64_t) L;
+    Acc& a = groups[std::make_tuple(t.format, t.samplerate, t.channels)];
+    a.warps += (nchunks + cpw - 1) / cpw * (packed ? 1u : (t.channels + 31u) / 32u);
+    a.niters = (uint32_t) sweep_iters(W, L, (int) align_quantum(fb));
+    a.packed = packed;
+  }
+  double cost = 0.0;
+  for (const auto& kv : groups) {
+    const Acc& a = kv.second;
+    const double cap = (double) sms * (a.packed ? kPackedWarpsPerSM : kScalarWarpsPerSM);
+    const double waves = (double) a.warps / cap;
+    double full = floor(waves), frac = waves - full;
+    if (frac > 0.0 && frac < 0.5) frac = 0.5;
+    cost += (full + frac) * cap * a.niters * (a.packed ? kPackedIterCost : kScalarIterCost);
+  }
+  return cost;
+}
+
+inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, const PlanOptions& opt, Plan& p) {
   p = Plan();
   p.nalbums = nalbums;
-  // -- chunk length from the total amount of work
-  uint64_t samples = 0;
-  for (size_t i = 0; i < n; ++i) samples += in[i].frames * (uint64_t) in[i].channels;
-  uint64_t want_len = target_tasks ? samples / target_tasks : 0;
+  // -- chunk length: the candidate (a chunk length of one of the batch's
+  // rates) with the lowest modelled sweep time.
+  uint64_t want_len = 0;
+  const uint32_t sms = (uint32_t) (opt.target_tasks / 2048u);
+  if (opt.force_k <= 0 && opt.target_tasks) {
+    uint64_t samples = 0;
+    for (size_t i = 0; i < n; ++i) samples += in[i].frames * (uint64_t) in[i].channels;
+    want_len = samples / opt.target_tasks;
+    if (sms) {
+      std::map<uint32_t, int> rates;
+      for (size_t i = 0; i < n && rates.size() < 8; ++i) rates[in[i].samplerate] = 1;
+      double best = plan_cost(in, n, want_len, sms, opt.allow_packed);
+      for (const auto& r : rates) {
+        const int s100 = (int) ((r.first + 5) / 10);
+        const int W = warmup_frames(k_design(r.first));
+        for (int k = 1; k <= s100; ++k) {
+          if (s100 % k) continue;
+          const int L = s100 / k;
+          if (L < 4 * W) break;
+          const double c = plan_cost(in, n, (uint64_t) L, sms, opt.allow_packed);
+          if (c < best) { best = c; want_len = (uint64_t) L; }
+        }
+      }
+    }
+  }
 
   std::map<std::tuple<uint32_t, int, uint32_t>, uint32_t> coef_index;
   p.tracks.resize(n);
@@ -89,15 +168,7 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, uint64_t t
     else default_weight_classes(t.channels, tr.wclass);
     const int s100 = (int) ((t.samplerate + 5) / 10);
     const KDesign kd = k_design(t.samplerate);
-    const int W = warmup_frames(kd);
-    int min_len = 4 * W;
-    if ((uint64_t) min_len < want_len) min_len = (int) (want_len > (uint64_t) s100 ? s100 : want_len);
-    int k = pick_chunks_per_slot(s100, min_len);
-    if (force_k > 0) {
-      k = 1;
-      for (int d = 1; d <= force_k; ++d)
-        if (s100 % d == 0 && s100 / d >= 4 * W) k = d;
-    }
+    const int k = chunks_per_slot_for(s100, warmup_frames(kd), want_len, opt.force_k);
     const auto key = std::make_tuple(t.samplerate, k, t.format);
     auto it = coef_index.find(key);
     if (it == coef_index.end()) {
@@ -145,17 +216,20 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, uint64_t t
     sp.W = cs.W; sp.L = cs.L; sp.niters = (int32_t) t0.niters; sp.aq = (int32_t) t0.aq;
     sp.npairs = (t0.niters + 1u) / 2u;
     sp.channels = t0.channels; sp.fb = t0.fb;
-    sp.lpc = t0.channels < 32u ? t0.channels : 32u;
-    sp.cpw = chunks_per_warp(t0.channels);
-    sp.stage_row_bytes = kStageFrames * t0.fb;
+    const bool packed = track_is_packed(t0.channels, opt.allow_packed);
+    sp.packed = packed ? 1u : 0u;
+    sp.lpc = packed ? t0.channels / 2u : (t0.channels < 32u ? t0.channels : 32u);
+    sp.cpw = 32u / sp.lpc;
+    const uint32_t pps = packed ? (uint32_t) kPairPPS : (uint32_t) kPairsPerStage;
+    const uint32_t ring = packed ? (uint32_t) kPairRing : (uint32_t) kRing;
+    sp.stage_row_bytes = pps * kPairFrames * t0.fb;
     sp.units = sp.stage_row_bytes >> 4;
     sp.row_stride = (sp.units | 1u) << 4;
     sp.stage_bytes = sp.cpw * sp.row_stride;
-    sp.ring_bytes = kRing * sp.stage_bytes;
+    sp.ring_bytes = ring * sp.stage_bytes;
     sp.kcopies = (sp.units + sp.lpc - 1) / sp.lpc;
-    sp.warp_smem = sweep_warp_smem_host(t0.channels, t0.fb);
-    const long long stage_frames =
-        (long long) ((t0.niters + kItersPerStage - 1) / kItersPerStage) * kStageFrames;
+    sp.warp_smem = sp.ring_bytes;
+    const long long stage_frames = (long long) ((sp.npairs + pps - 1) / pps) * pps * kPairFrames;
     for (uint32_t i : kv.second) {
       const Track& tr = p.tracks[i];
       for (uint32_t c = 0; c < tr.nchunks; c += sp.cpw) {
@@ -169,7 +243,7 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, uint64_t t
           lmin = gl.l_valid;
         }
         const bool interior = g0.a >= 0 && g1.a + stage_frames <= (long long) tr.frames;
-        for (uint32_t cb = 0; cb < tr.channels; cb += 32)
+        for (uint32_t cb = 0; cb < (packed ? 1u : tr.channels); cb += 32)
           p.work.push_back(WarpWork{i, c, lmin, (uint16_t) (interior ? 1 : 0), (uint16_t) cb});
       }
     }

@@ -151,6 +151,15 @@ LG_HD float peak_code_value(uint32_t code) {
   return v.f;
 }
 
+// Packed sweep: one code per PAIR of iterations and channel.  16-bit PCM
+// maxima are small integers and are stored exactly; float maxima as above.
+template <int FMT>
+LG_HD uint32_t pair_code(float m) { return FMT == FMT_S16 ? (uint32_t) (int) m : peak_code(m); }
+template <int FMT>
+LG_HD float pair_code_value(uint32_t code) {
+  return FMT == FMT_S16 ? (float) (int) code : peak_code_value(code);
+}
+
 // Y <- Y * lambda^-kIter + S: keeps Y = sum y[f] lambda^(f - f0) relative to
 // the current iteration's first frame, so the constants lambda^i stay O(1).
 LG_HD void mode_accumulate(LaneCtx& c, const KCoef& k, float sr, float si) {

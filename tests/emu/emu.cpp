@@ -25,6 +25,7 @@ struct LaneCodes {
   uint32_t track, ch;
   LaneGeom geo;
   std::vector<uint32_t> code;   // per iteration (lg_sweep.cuh: peak_code)
+  std::vector<float> iter_max;  // per iteration: max |x|
 };
 
 // peaks: [2 * total_peaks] = (sample peak, exhaustive true peak) per channel;
@@ -42,14 +43,17 @@ static void run_group(const Plan& p, const SweepGroup& g, std::vector<ChunkRec>&
     const Track& tr = p.tracks[ww.track];
     const CoefSet& cs = p.coefs[tr.coef];
     const uint32_t C = tr.channels, lpc = k.lpc, cpw = k.cpw;
-    for (uint32_t lane = 0; lane < 32; ++lane) {
-      const uint32_t slot = lane / lpc, chl = lane - slot * lpc, ch = ww.ch_base + chl;
+    // a packed lane (even channel counts, lg_pair.cu) holds channels 2j and 2j+1
+    for (uint32_t vlane = 0; vlane < (k.packed ? 64u : 32u); ++vlane) {
+      const uint32_t lane = k.packed ? vlane / 2u : vlane;
+      const uint32_t slot = lane / lpc, chl = lane - slot * lpc;
+      const uint32_t ch = k.packed ? 2u * chl + (vlane & 1u) : ww.ch_base + chl;
       const uint32_t chunk = ww.first_chunk + slot;
       if (!(slot < cpw && ch < C && chunk < tr.nchunks)) continue;
       const LaneGeom geo = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, chunk);
       LaneCtx c;
       lane_init(c, cs.W, cs.L, geo);
-      LaneCodes lc{ww.track, ch, geo, {}};
+      LaneCodes lc{ww.track, ch, geo, {}, {}};
       float win[(NT > 0 ? NT : 1) + kIter] = {0};
       float tp = 0.0f;
       for (uint32_t it = 0; it < tr.niters; ++it) {
@@ -60,6 +64,7 @@ static void run_group(const Plan& p, const SweepGroup& g, std::vector<ChunkRec>&
         const float m = kind == ITER_WARM ? iter_warm(c, k, x)
                       : kind == ITER_FAST ? iter_fast(c, k, x, f0) : iter_masked(c, k, x, f0);
         lc.code.push_back(peak_code(m));
+        lc.iter_max.push_back(m);
         if (NT > 0) {
           if (tp_iter_owned((int) it, c.f_lo, c.f_hi, geo.a, (long long) tr.frames)) {
             const long long left = (long long) tr.frames - (geo.a + f0);
@@ -85,6 +90,39 @@ static void run_group(const Plan& p, const SweepGroup& g, std::vector<ChunkRec>&
     const int f_lo = cs.W + lc.geo.o, f_hi = f_lo + cs.L;
     const float floor_ = peaks[2 * (tr.peak_base + lc.ch)];
     float& out = tp_screened[tr.peak_base + lc.ch];
+    if (k.packed) {
+      // truepeak_pair_kernel: one code per pair of iterations, screened over
+      // the pair and the pair before it; both iterations are evaluated
+      const long long left0 = (long long) tr.frames - lc.geo.a;
+      const int f_end = left0 < (long long) f_hi ? (left0 < 0 ? 0 : (int) left0) : f_hi;
+      auto pcode = [&](uint32_t pr) {
+        uint32_t c0 = pair_code<FMT>(lc.iter_max[2 * pr]);
+        if (2 * pr + 1 < tr.niters) c0 = std::max(c0, pair_code<FMT>(lc.iter_max[2 * pr + 1]));
+        return c0;
+      };
+      for (uint32_t pr = 0; pr < k.npairs; ++pr) {
+        uint32_t cm = pcode(pr);
+        if (pr) cm = std::max(cm, pcode(pr - 1));
+        const int f0 = (int) pr * kPairFrames;
+        if (!(f0 + kPairFrames > f_lo && f0 < f_end)) continue;
+        if (!(k.tp_bound * pair_code_value<FMT>(cm) > floor_)) continue;
+        for (int h = 0; h < 2; ++h) {
+          const long long t0 = lc.geo.a + f0 + h * kIter;
+          if (t0 >= (long long) tr.frames) break;
+          float win[(NT > 0 ? NT : 1) + kIter];
+          for (int q = 0; q < NT + kIter; ++q) {
+            const long long t = t0 - NT + q;
+            win[q] = 0.0f;
+            if (t < 0 || t >= (long long) tr.frames) continue;
+            if (FMT == FMT_S16) win[q] = (float) ((const short*) tr.pcm)[t * tr.channels + lc.ch];
+            else win[q] = ((const float*) tr.pcm)[t * tr.channels + lc.ch];
+          }
+          const long long left = (long long) tr.frames - t0;
+          out = std::max(out, tp_window_valid<TPF>(win, left > kIter ? kIter : (int) left));
+        }
+      }
+      continue;
+    }
     for (uint32_t it = 0; it < tr.niters; ++it) {
       uint32_t cm = lc.code[it];
       for (uint32_t b = 1; b <= (uint32_t) NT / kIter && b <= it; ++b) cm = std::max(cm, lc.code[it - b]);
@@ -170,7 +208,9 @@ extern "C" int emu_measure(const lgb_track* tracks, size_t ntracks, uint32_t nal
     in[i] = TrackIn{tracks[i].pcm, tracks[i].frames, tracks[i].channels, tracks[i].samplerate,
                     tracks[i].format, tracks[i].album, tracks[i].weight_class};
   Plan p;
-  build_plan(in.data(), ntracks, nalbums, target_tasks, p);
+  PlanOptions opt;
+  opt.target_tasks = target_tasks;
+  build_plan(in.data(), ntracks, nalbums, opt, p);
   std::vector<ChunkRec> recs(p.total_recs);
   std::vector<float> peaks(2 * p.total_peaks, 0.0f), tps(p.total_peaks, 0.0f);
   for (const SweepGroup& g : p.groups) {
@@ -235,7 +275,9 @@ extern "C" void emu_plan_sizes(const lgb_track* tracks, size_t ntracks, uint64_t
     in[i] = TrackIn{tracks[i].pcm, tracks[i].frames, tracks[i].channels, tracks[i].samplerate,
                     tracks[i].format, LGB_NO_ALBUM, nullptr};
   Plan p;
-  build_plan(in.data(), ntracks, 0, target_tasks, p);
+  PlanOptions opt;
+  opt.target_tasks = target_tasks;
+  build_plan(in.data(), ntracks, 0, opt, p);
   *total_blocks = p.total_blocks;
   *total_st = p.total_st;
 }
