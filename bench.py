@@ -258,10 +258,9 @@ def gpu_arm(args):
         res = batch.fetch()
         return res, (merge.fetch() if merge is not None else None)
 
-    # ---- resident-PCM throughput
+    # ---- resident-PCM throughput (steps replay the batch's CUDA graph)
     for _ in range(args.warmup):
         step()
-    L.lgb_batch_enable_timing(batch._h, 1)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
@@ -274,6 +273,11 @@ def gpu_arm(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
+    # ---- roofline leg: the same steps launched directly, with CUDA events
+    # around the sweep kernel on the launching stream
+    L.lgb_batch_enable_timing(batch._h, 1)
+    for _ in range(args.steps):
+        step()
     sweep_ms = L.lgb_batch_sweep_ms(batch._h)
     tp_ms = L.lgb_batch_truepeak_ms(batch._h)
     L.lgb_batch_enable_timing(batch._h, 0)

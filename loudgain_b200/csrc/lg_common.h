@@ -191,6 +191,7 @@ struct SweepParams {
   // packed, the pair's maximum for each of the lane's two channels
   // (lg_sweep.cuh: pair_code).  Unused when the rate has no interpolator.
   uint32_t* mrec;
+  uint32_t* tp_ticket;     // work-item counter of the group's true-peak pass (zeroed per run)
 };
 
 // ---- lane geometry ---------------------------------------------------------

@@ -588,7 +588,7 @@ block_kernel(const Track* __restrict__ tracks, uint32_t ntracks,
 
 // ------------------------------------------------------------- reductions
 
-constexpr int kQueryThreads = 512;
+constexpr int kQueryThreads = 1024;
 
 struct SumCount {
   double s;
@@ -623,16 +623,87 @@ __device__ SumCount block_sum_count(double s, unsigned long long n, SumCount* sc
   return r;
 }
 
-// The k-th smallest (0-based) values, for two ranks at once, among the member
+// A query's member block lists, flattened: element g of the concatenation of
+// all members' lists.  Up to kQueryCache member descriptors (and their prefix
+// offsets) are staged in shared memory so that every thread's loads are
+// independent; larger queries walk the member list.
+constexpr int kQueryCache = 256;
+constexpr int kStCache = 4096;          // short-term energies kept in shared memory
+
+struct QueryView {
+  const BlockList* lists;     // global
+  const uint32_t* mem;        // global member indices of this query
+  uint32_t count;
+  bool cached;
+  const BlockList* s_lists;   // shared copies (cached)
+  const uint32_t* s_zoff;     // [count + 1]
+  const uint32_t* s_stoff;    // [count + 1]
+};
+
+// Index of the member whose range holds element g: fixed-depth, branch-free
+// search over the (shared-memory) prefix offsets, count <= kQueryCache.
+__device__ __forceinline__ uint32_t find_member(const uint32_t* off, uint32_t count, uint32_t g) {
+  uint32_t lo = 0;
+#pragma unroll
+  for (uint32_t step = kQueryCache / 2; step; step >>= 1) {
+    const uint32_t mid = lo + step;
+    if (mid < count && off[mid] <= g) lo = mid;
+  }
+  return lo;
+}
+
+// f(e, g) for every gating block energy (ST = false) or short-term energy
+// (ST = true).  Cached queries work in batches of kQueryBatch elements per
+// thread: all searches, then all loads, then the callbacks, so that a thread
+// has kQueryBatch independent loads in flight instead of one.
+constexpr int kQueryBatch = 8;
+
+template <bool ST, class F>
+__device__ __forceinline__ void for_each_energy(const QueryView& v, F f) {
+  if (v.cached) {
+    const uint32_t* off = ST ? v.s_stoff : v.s_zoff;
+    const uint32_t total = off[v.count];
+    for (uint32_t g0 = threadIdx.x; g0 < total; g0 += blockDim.x * kQueryBatch) {
+      const double* src[kQueryBatch];
+      double e[kQueryBatch];
+#pragma unroll
+      for (int u = 0; u < kQueryBatch; ++u) {
+        const uint32_t g = g0 + u * blockDim.x;
+        const uint32_t gc = g < total ? g : g0;
+        const uint32_t m = find_member(off, v.count, gc);
+        src[u] = (ST ? v.s_lists[m].st : v.s_lists[m].z) + (gc - off[m]);
+      }
+#pragma unroll
+      for (int u = 0; u < kQueryBatch; ++u) e[u] = *src[u];
+#pragma unroll
+      for (int u = 0; u < kQueryBatch; ++u) {
+        const uint32_t g = g0 + u * blockDim.x;
+        if (g < total) f(e[u], g);
+      }
+    }
+  } else {
+    uint32_t base = 0;
+    for (uint32_t m = 0; m < v.count; ++m) {
+      const BlockList bl = v.lists[v.mem[m]];
+      const double* p = ST ? bl.st : bl.z;
+      const uint32_t n = ST ? bl.nst : bl.nz;
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) f(p[i], base + i);
+      base += n;
+    }
+  }
+}
+
+// The k-th smallest (0-based) values, for two ranks at once, among the
 // short-term energies >= floor_e.  Positive doubles order like their 64-bit
-// patterns: 8 passes of 8-bit radix select over the (L2-resident) values,
-// one 256-bin histogram per rank and pass, bin search by a block-wide scan.
+// patterns: 8 passes of 8-bit radix select, one 256-bin histogram per rank and
+// pass, bin search by a block-wide scan.  The values come from shared memory
+// (s_st, n_st of them) when they fit, else from the member lists.
 struct SelectState {
   unsigned long long prefix[2];
   unsigned long long k[2];
 };
 
-__device__ void select_two(const BlockList* lists, const uint32_t* members, uint32_t count,
+__device__ void select_two(const QueryView& v, const double* s_st, uint32_t n_st, bool st_cached,
                            double floor_e, unsigned long long k_lo, unsigned long long k_hi,
                            unsigned int* hist /* [2][256] */, unsigned int* wsum /* [2][8] */,
                            SelectState* st, double* out_lo, double* out_hi) {
@@ -642,36 +713,38 @@ __device__ void select_two(const BlockList* lists, const uint32_t* members, uint
     for (int i = threadIdx.x; i < 512; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     const unsigned long long p0 = st->prefix[0], p1 = st->prefix[1];
-    for (uint32_t m = 0; m < count; ++m) {
-      const BlockList bl = lists[members[m]];
-      for (uint32_t i = threadIdx.x; i < bl.nst; i += blockDim.x) {
-        const double e = bl.st[i];
-        if (!(e >= floor_e)) continue;
-        const unsigned long long bits = (unsigned long long) __double_as_longlong(e);
-        const unsigned int digit = (unsigned int) ((bits >> shift) & 0xffull);
-        if ((bits & mask) == p0) atomicAdd(&hist[digit], 1u);
-        if ((bits & mask) == p1) atomicAdd(&hist[256 + digit], 1u);
-      }
+    auto count = [&](double e, uint32_t) {
+      if (!(e >= floor_e)) return;
+      const unsigned long long bits = (unsigned long long) __double_as_longlong(e);
+      const unsigned int digit = (unsigned int) ((bits >> shift) & 0xffull);
+      if ((bits & mask) == p0) atomicAdd(&hist[digit], 1u);
+      if ((bits & mask) == p1) atomicAdd(&hist[256 + digit], 1u);
+    };
+    if (st_cached) {
+      for (uint32_t i = threadIdx.x; i < n_st; i += blockDim.x) count(s_st[i], i);
+    } else {
+      for_each_energy<true>(v, count);
     }
     __syncthreads();
     // threads 0..255 own the bins of rank 0, 256..511 those of rank 1
-    const int which = threadIdx.x >> 8, bin = threadIdx.x & 255;
+    const bool owner = threadIdx.x < 512;
+    const int which = (threadIdx.x >> 8) & 1, bin = threadIdx.x & 255;
     const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 7;
-    const unsigned int cnt = hist[threadIdx.x];
+    const unsigned int cnt = owner ? hist[threadIdx.x] : 0u;
     unsigned int inc = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += v;
+      const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
     }
-    if (lane == 31) wsum[which * 8 + w] = inc;
+    if (owner && lane == 31) wsum[which * 8 + w] = inc;
     __syncthreads();
     unsigned int base = 0;
     for (int j = 0; j < w; ++j) base += wsum[which * 8 + j];
     const unsigned long long excl = (unsigned long long) base + inc - cnt;
     const unsigned long long kk = st->k[which];
     __syncthreads();
-    if (cnt && excl <= kk && kk < excl + cnt) {
+    if (owner && cnt && excl <= kk && kk < excl + cnt) {
       st->k[which] = kk - excl;
       st->prefix[which] |= (unsigned long long) bin << shift;
     }
@@ -690,8 +763,27 @@ query_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ quer
   __shared__ unsigned int hist[512];
   __shared__ unsigned int wsum[16];
   __shared__ SelectState sel;
+  __shared__ BlockList s_lists[kQueryCache];
+  __shared__ uint32_t s_zoff[kQueryCache + 1], s_stoff[kQueryCache + 1];
+  __shared__ double s_st[kStCache];
   const Query q = queries[blockIdx.x];
-  const uint32_t* mem = members + q.first;
+  QueryView v;
+  v.lists = lists; v.mem = members + q.first; v.count = q.count;
+  v.cached = q.count <= (uint32_t) kQueryCache;
+  v.s_lists = s_lists; v.s_zoff = s_zoff; v.s_stoff = s_stoff;
+  if (v.cached) {
+    for (uint32_t m = threadIdx.x; m < q.count; m += blockDim.x) s_lists[m] = lists[v.mem[m]];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t az = 0, ast = 0;
+      for (uint32_t m = 0; m < q.count; ++m) {
+        s_zoff[m] = az; s_stoff[m] = ast;
+        az += s_lists[m].nz; ast += s_lists[m].nst;
+      }
+      s_zoff[q.count] = az; s_stoff[q.count] = ast;
+    }
+    __syncthreads();
+  }
   QueryResult res;
   res.loudness = -HUGE_VAL; res.range = 0.0; res.rel_thr = 0.0;
   res.sum1 = res.sum2 = 0.0; res.n1 = res.n2 = res.nst = 0;
@@ -699,58 +791,46 @@ query_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ quer
   // ---- integrated loudness: absolute gate, then relative gate at -10 LU
   double s = 0.0;
   unsigned long long n = 0;
-  for (uint32_t m = 0; m < q.count; ++m) {
-    const BlockList bl = lists[mem[m]];
-    for (uint32_t i = threadIdx.x; i < bl.nz; i += blockDim.x) {
-      const double e = bl.z[i];
-      if (e >= abs_gate) { s += e; ++n; }
-    }
-  }
+  for_each_energy<false>(v, [&](double e, uint32_t) { if (e >= abs_gate) { s += e; ++n; } });
   SumCount a = block_sum_count(s, n, scratch);
   res.sum1 = a.s; res.n1 = a.n;
   if (a.n) {
     const double thr = a.s / (double) a.n * 0.1;
     res.rel_thr = thr;
     s = 0.0; n = 0;
-    for (uint32_t m = 0; m < q.count; ++m) {
-      const BlockList bl = lists[mem[m]];
-      for (uint32_t i = threadIdx.x; i < bl.nz; i += blockDim.x) {
-        const double e = bl.z[i];
-        if (e >= abs_gate && e >= thr) { s += e; ++n; }
-      }
-    }
+    for_each_energy<false>(v, [&](double e, uint32_t) { if (e >= abs_gate && e >= thr) { s += e; ++n; } });
     SumCount b = block_sum_count(s, n, scratch);
     res.sum2 = b.s; res.n2 = b.n;
     if (b.n) res.loudness = energy_to_lufs(b.s / (double) b.n);
   }
 
   // ---- loudness range: -20 LU relative gate on short-term energies, then the
-  //      10th / 95th percentile by rank
+  //      10th / 95th percentile by rank.  The energies are staged in shared
+  //      memory during the first pass when they fit.
+  const bool st_cached = v.cached && s_stoff[q.count] <= (uint32_t) kStCache;
+  const uint32_t n_st = st_cached ? s_stoff[q.count] : 0u;
   s = 0.0; n = 0;
-  for (uint32_t m = 0; m < q.count; ++m) {
-    const BlockList bl = lists[mem[m]];
-    for (uint32_t i = threadIdx.x; i < bl.nst; i += blockDim.x) {
-      const double e = bl.st[i];
-      if (e >= abs_gate) { s += e; ++n; }
-    }
-  }
-  a = block_sum_count(s, n, scratch);
+  for_each_energy<true>(v, [&](double e, uint32_t g) {
+    if (st_cached) s_st[g] = e;
+    if (e >= abs_gate) { s += e; ++n; }
+  });
+  a = block_sum_count(s, n, scratch);          // (its barriers publish s_st)
   res.nst = a.n;
   if (a.n) {
     double floor_e = a.s / (double) a.n * 0.01;
     if (floor_e < abs_gate) floor_e = abs_gate;
-    s = 0.0; n = 0;
-    for (uint32_t m = 0; m < q.count; ++m) {
-      const BlockList bl = lists[mem[m]];
-      for (uint32_t i = threadIdx.x; i < bl.nst; i += blockDim.x)
-        if (bl.st[i] >= floor_e) ++n;
+    n = 0;
+    if (st_cached) {
+      for (uint32_t i = threadIdx.x; i < n_st; i += blockDim.x) if (s_st[i] >= floor_e) ++n;
+    } else {
+      for_each_energy<true>(v, [&](double e, uint32_t) { if (e >= floor_e) ++n; });
     }
     const SumCount c = block_sum_count(0.0, n, scratch);
     if (c.n) {
       const unsigned long long k_hi = (unsigned long long) ((double) (c.n - 1) * 0.95 + 0.5);
       const unsigned long long k_lo = (unsigned long long) ((double) (c.n - 1) * 0.1 + 0.5);
       double lo, hi;
-      select_two(lists, mem, q.count, floor_e, k_lo, k_hi, hist, wsum, &sel, &lo, &hi);
+      select_two(v, s_st, n_st, st_cached, floor_e, k_lo, k_hi, hist, wsum, &sel, &lo, &hi);
       res.range = energy_to_lufs(hi) - energy_to_lufs(lo);
     }
   }

@@ -126,6 +126,12 @@ __device__ __forceinline__ void masked_half(PairCtx& c, const SweepParams& k, co
 
 // Per-pair maxima of the lane's two channels.  16-bit input: packed signed
 // max / min of the raw frame words; float input: two running |x| maxima.
+// One 16-bit stereo frame word -> (left, right) as floats: PRMT sign-extends a
+// half, I2FP converts (both ALU pipe; the XU-pipe I2F.S16 was measured no faster).
+__device__ __forceinline__ float2 frame_s16(uint32_t w) {
+  return make_float2((float) sext_half(w, 0x9910u), (float) sext_half(w, 0xBB32u));
+}
+
 template <int FMT> struct PairPeak;
 template <> struct PairPeak<FMT_S16> {
   uint32_t mx, mn;               // packed s16x2
@@ -163,10 +169,10 @@ __device__ __forceinline__ void load_iter2(const uint32_t rowp, uint32_t fb, uin
       const uint4 v = lds128(rowp + 16u * u);
       pk.words(v.x, v.y);
       pk.words(v.z, v.w);
-      x[4 * u + 0] = make_float2((float) sext_half(v.x, 0x9910u), (float) sext_half(v.x, 0xBB32u));
-      x[4 * u + 1] = make_float2((float) sext_half(v.y, 0x9910u), (float) sext_half(v.y, 0xBB32u));
-      x[4 * u + 2] = make_float2((float) sext_half(v.z, 0x9910u), (float) sext_half(v.z, 0xBB32u));
-      x[4 * u + 3] = make_float2((float) sext_half(v.w, 0x9910u), (float) sext_half(v.w, 0xBB32u));
+      x[4 * u + 0] = frame_s16(v.x);
+      x[4 * u + 1] = frame_s16(v.y);
+      x[4 * u + 2] = frame_s16(v.z);
+      x[4 * u + 3] = frame_s16(v.w);
     }
   } else if constexpr (LAYOUT == PAIR_F32_STEREO) {
 #pragma unroll
@@ -183,8 +189,8 @@ __device__ __forceinline__ void load_iter2(const uint32_t rowp, uint32_t fb, uin
       const uint32_t a = lds32(q + i * fb);
       const uint32_t b = lds32(q + (i + 1) * fb);
       pk.words(a, b);
-      x[i] = make_float2((float) sext_half(a, 0x9910u), (float) sext_half(a, 0xBB32u));
-      x[i + 1] = make_float2((float) sext_half(b, 0x9910u), (float) sext_half(b, 0xBB32u));
+      x[i] = frame_s16(a);
+      x[i + 1] = frame_s16(b);
     }
   } else {
     const uint32_t q = rowp + chl * 8u;
@@ -198,12 +204,19 @@ __device__ __forceinline__ void load_iter2(const uint32_t rowp, uint32_t fb, uin
   }
 }
 
-#ifndef LG_PAIR_MINBLOCKS
-#define LG_PAIR_MINBLOCKS 4
+// CTA size and resident warps per SM of the packed sweep.  Warps are autonomous,
+// so small CTAs only make the distribution of warps over the SMs finer.
+#ifndef LG_PAIR_THREADS
+#define LG_PAIR_THREADS 64
 #endif
+#ifndef LG_PAIR_WARPS_PER_SM
+#define LG_PAIR_WARPS_PER_SM 16
+#endif
+constexpr int kPairThreads = LG_PAIR_THREADS;
+constexpr int kPairMinBlocks = LG_PAIR_WARPS_PER_SM / (LG_PAIR_THREADS / 32);
 
 template <int LAYOUT, bool TP>
-__global__ void __launch_bounds__(kSweepThreads, LG_PAIR_MINBLOCKS)
+__global__ void __launch_bounds__(kPairThreads, kPairMinBlocks)
 sweep_pair_kernel(const __grid_constant__ SweepParams P) {
   constexpr int FMT = pair_format<LAYOUT>();
   constexpr bool STEREO = LAYOUT == PAIR_S16_STEREO || LAYOUT == PAIR_F32_STEREO;
@@ -418,7 +431,7 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
 
 template <int LAYOUT, bool TP>
 static cudaError_t launch_pair_k(const SweepParams& p, cudaStream_t stream) {
-  const uint32_t wpb = kSweepThreads / 32;
+  const uint32_t wpb = kPairThreads / 32;
   const uint32_t blocks = (p.nwarps + wpb - 1) / wpb;
   const size_t smem = (size_t) p.warp_smem * wpb;
   static bool attr_set = false;
@@ -431,7 +444,7 @@ static cudaError_t launch_pair_k(const SweepParams& p, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  sweep_pair_kernel<LAYOUT, TP><<<blocks, kSweepThreads, smem, stream>>>(p);
+  sweep_pair_kernel<LAYOUT, TP><<<blocks, kPairThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -466,6 +479,7 @@ cudaError_t launch_sweep_pair(const SweepParams& p, uint32_t format, int tpf, cu
 constexpr int kTp2Threads = 128;
 constexpr int kTp2Warps = kTp2Threads / 32;
 constexpr int kTp2Cap = 32 + 64;            // remainder + both channels of one pair per lane
+constexpr int kTp2ItemsPerWarp = 2;
 
 template <int FMT>
 __device__ __forceinline__ float pcm_at(const unsigned char* p) {
@@ -473,41 +487,69 @@ __device__ __forceinline__ float pcm_at(const unsigned char* p) {
   return *reinterpret_cast<const float*>(p);
 }
 
+// One queued pair: both of its iterations share one window of NT history
+// frames + 24 frames.  Stereo frames are read with 16-byte loads (the window
+// starts on a 16-byte boundary of the track: lane origins and pairs are
+// multiples of four frames); other layouts and windows that touch the track's
+// ends read sample by sample.
 template <int FMT, int TPF>
 __device__ __forceinline__ void tp_pair_evaluate(const SweepParams& P, const uint4 cd) {
   constexpr int NT = TpTraits<TPF>::kTaps;
+  constexpr int NW = NT + kPairFrames;
   const Track& tr = P.tracks[cd.x];
   const long long frames = (long long) tr.frames;
   const long long t0 = (long long) ((unsigned long long) cd.z | ((unsigned long long) cd.w << 32));
-  const unsigned char* pcm = reinterpret_cast<const unsigned char*>(tr.pcm) +
-                             cd.y * (FMT == FMT_S16 ? 2u : 4u);
-  float m = 0.0f;
-  // two iterations, each with its own window (keeps the register footprint of
-  // the scalar pass)
-#pragma unroll 1
-  for (int h = 0; h < 2; ++h) {
-    const long long th = t0 + h * kIter;
-    if (th >= frames) break;
-    float win[NT + kIter];
-    if (th >= NT && th + kIter <= frames) {
-      const unsigned char* q = pcm + (th - NT) * (long long) P.fb;
+  const unsigned char* pcm = reinterpret_cast<const unsigned char*>(tr.pcm);
+  float win[NW];
+  const bool inside = t0 >= NT && t0 + kPairFrames <= frames;
+  if (inside && P.channels == 2) {
+    const unsigned char* q = pcm + (t0 - NT) * (long long) P.fb;
+    if (FMT == FMT_S16) {
+      const uint32_t sel = cd.y ? 0xBB32u : 0x9910u;
 #pragma unroll
-      for (int k = 0; k < NT + kIter; ++k) win[k] = pcm_at<FMT>(q + (uint32_t) k * P.fb);
-      m = fmaxf(m, tp_window_valid<TPF>(win, kIter));
+      for (int k = 0; k < NW / 4; ++k) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(q) + k);
+        win[4 * k + 0] = (float) sext_half(v.x, sel);
+        win[4 * k + 1] = (float) sext_half(v.y, sel);
+        win[4 * k + 2] = (float) sext_half(v.z, sel);
+        win[4 * k + 3] = (float) sext_half(v.w, sel);
+      }
     } else {
 #pragma unroll
-      for (int k = 0; k < NT + kIter; ++k) {
-        const long long t = th - NT + k;
-        win[k] = (t >= 0 && t < frames) ? pcm_at<FMT>(pcm + t * (long long) P.fb) : 0.0f;
+      for (int k = 0; k < NW / 2; ++k) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(q) + k);
+        win[2 * k + 0] = cd.y ? v.y : v.x;
+        win[2 * k + 1] = cd.y ? v.w : v.z;
       }
-      const long long left = frames - th;
-      m = fmaxf(m, tp_window_valid<TPF>(win, left > kIter ? kIter : (int) left));
     }
+  } else {
+    const unsigned char* pc = pcm + cd.y * (FMT == FMT_S16 ? 2u : 4u);
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+      const long long t = t0 - NT + k;
+      win[k] = (t >= 0 && t < frames) ? pcm_at<FMT>(pc + t * (long long) P.fb) : 0.0f;
+    }
+  }
+  // the reference produces no output beyond the last frame it was given
+  const long long left = frames - t0;
+  const int nvalid = left > kPairFrames ? kPairFrames : (int) left;
+  float m = 0.0f;
+  if (inside) {
+#pragma unroll
+    for (int i = 0; i < kPairFrames; ++i) m = fmaxf(m, tp_frame<TPF>(win, NT + i));
+  } else {
+#pragma unroll
+    for (int i = 0; i < kPairFrames; ++i)
+      if (i < nvalid) m = fmaxf(m, tp_frame<TPF>(win, NT + i));
   }
   uint32_t* cell = P.peaks + 2 * (tr.peak_base + cd.y) + 1;
   if (__float_as_uint(m) > __ldcg(cell)) atomicMax(cell, __float_as_uint(m));
 }
 
+// Warps draw work items from a ticket counter (candidates cluster in the loud
+// passages, a static split leaves SMs idle) and leave after kTp2ItemsPerWarp
+// of them: CTAs turn over, so the post-processing kernels of the forked step
+// (lg_batch.cu) find room on the SMs while this pass runs.
 template <int FMT, int TPF>
 __global__ void __launch_bounds__(kTp2Threads, 4)
 truepeak_pair_kernel(const __grid_constant__ SweepParams P, const uint32_t seg_pairs) {
@@ -517,12 +559,15 @@ truepeak_pair_kernel(const __grid_constant__ SweepParams P, const uint32_t seg_p
   uint4* queue = queue_all[wic];
   const uint32_t nseg = (npairs + seg_pairs - 1) / seg_pairs;
   const uint64_t nitems = (uint64_t) P.nwarps * nseg;
-  const uint64_t nscan = (uint64_t) gridDim.x * kTp2Warps;
   uint32_t qn = 0;                       // warp-uniform
 
-  for (uint64_t item = (uint64_t) blockIdx.x * kTp2Warps + wic; item < nitems; item += nscan) {
-    const uint32_t w = (uint32_t) (item / nseg);
-    const uint32_t p_begin = (uint32_t) (item - (uint64_t) w * nseg) * seg_pairs;
+  for (int round = 0; round < kTp2ItemsPerWarp; ++round) {
+    uint32_t ticket = 0;
+    if (lane == 0) ticket = atomicAdd(P.tp_ticket, 1u);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket >= nitems) break;
+    const uint32_t w = ticket / nseg;
+    const uint32_t p_begin = (ticket - w * nseg) * seg_pairs;
     const uint32_t p_end = p_begin + seg_pairs < npairs ? p_begin + seg_pairs : npairs;
     // the sweep lane's place in its track
     const WarpWork ww = P.work[w];
@@ -592,16 +637,13 @@ static cudaError_t launch_truepeak_pair_t(const SweepParams& p, uint32_t sms, cu
                                                       kTp2Threads, 0) != cudaSuccess || per_sm < 1)
       per_sm = 4;
   }
-  // Persistent grid; about four work items per scanning warp, as long as possible.
+  // Items of 32 pairs (fewer for small batches, so that every SM gets several).
   const uint64_t nscan = (uint64_t) sms * per_sm * kTp2Warps;
-  uint64_t nseg = (4 * nscan + p.nwarps - 1) / p.nwarps;
-  if (nseg > p.npairs) nseg = p.npairs;
-  if (nseg < 1) nseg = 1;
-  const uint32_t seg = (uint32_t) ((p.npairs + nseg - 1) / nseg);
+  uint32_t seg = 32;
+  while (seg > 4 && (uint64_t) p.nwarps * ((p.npairs + seg - 1) / seg) < 4 * nscan) seg >>= 1;
   const uint64_t nitems = (uint64_t) p.nwarps * ((p.npairs + seg - 1) / seg);
-  const uint64_t ctas = (nitems + kTp2Warps - 1) / kTp2Warps;
-  const uint64_t want = (uint64_t) sms * per_sm;
-  truepeak_pair_kernel<FMT, TPF><<<(unsigned) (ctas < want ? ctas : want), kTp2Threads, 0, stream>>>(p, seg);
+  const uint64_t ctas = (nitems + kTp2Warps * kTp2ItemsPerWarp - 1) / (kTp2Warps * kTp2ItemsPerWarp);
+  truepeak_pair_kernel<FMT, TPF><<<(unsigned) ctas, kTp2Threads, 0, stream>>>(p, seg);
   return cudaGetLastError();
 }
 

@@ -64,11 +64,9 @@ inline bool track_is_packed(uint32_t channels, bool allow_packed) {
   return allow_packed && channels >= 2 && (channels & 1u) == 0 && channels <= 64;
 }
 
-// Resident sweep warps per SM (launch bounds of the two kernels) and the
-// relative cost of one 12-frame iteration of one warp, for the chunk-length
-// search below.
+// Resident sweep warps per SM (launch bounds of the two kernels), for the
+// chunk-length choice below.
 constexpr uint32_t kScalarWarpsPerSM = 32, kPackedWarpsPerSM = 16;
-constexpr double kScalarIterCost = 1.0, kPackedIterCost = 1.3;
 
 struct PlanOptions {
   uint64_t target_tasks = 0;   // about 2048 x SM count; 0 = shortest chunks
@@ -76,81 +74,46 @@ struct PlanOptions {
   bool allow_packed = true;
 };
 
-// Chunks per 100 ms slot of one track for a wanted chunk length.
+// Chunks per 100 ms slot of one track: the longest chunk (a divisor of the
+// slot) not above the wanted length, but never below four warm-ups.
 inline int chunks_per_slot_for(int s100, int W, uint64_t want_len, int force_k) {
-  if (force_k > 0) {
-    int k = 1;
-    for (int d = 1; d <= force_k; ++d)
-      if (s100 % d == 0 && s100 / d >= 4 * W) k = d;
-    return k;
-  }
-  int min_len = 4 * W;
-  if ((uint64_t) min_len < want_len) min_len = (int) (want_len > (uint64_t) s100 ? s100 : want_len);
-  return pick_chunks_per_slot(s100, min_len);
-}
-
-// Modelled sweep time of a batch for a wanted chunk length: per launch group
-// (format, rate, channels) the number of waves of resident warps times the
-// iterations per chunk.  A partly filled last wave is cheaper, but not below
-// half a wave (too few warps per SM to keep the pipes busy).
-inline double plan_cost(const TrackIn* in, size_t n, uint64_t want_len, uint32_t sms, bool allow_packed) {
-  struct Acc { uint64_t warps = 0; uint32_t niters = 0; bool packed = false; };
-  std::map<std::tuple<uint32_t, uint32_t, uint32_t>, Acc> groups;
-  for (size_t i = 0; i < n; ++i) {
-    const TrackIn& t = in[i];
-    const int s100 = (int) ((t.samplerate + 5) / 10);
-    const int W = warmup_frames(k_design(t.samplerate));
-    const int k = chunks_per_slot_for(s100, W, want_len, 0);
+  int best = 1;
+  for (int k = 1; k <= s100; ++k) {
+    if (s100 % k) continue;
     const int L = s100 / k;
-    const uint32_t fb = t.channels * (t.format == FMT_S16 ? 2u : 4u);
-    const bool packed = track_is_packed(t.channels, allow_packed);
-    const uint32_t lpc = packed ? t.channels / 2u : (t.channels < 32u ? t.channels : 32u);
-    const uint32_t cpw = 32u / lpc;
-    const uint64_t nchunks = (t.frames + L - 1) / (uint64_t) L;
-    Acc& a = groups[std::make_tuple(t.format, t.samplerate, t.channels)];
-    a.warps += (nchunks + cpw - 1) / cpw * (packed ? 1u : (t.channels + 31u) / 32u);
-    a.niters = (uint32_t) sweep_iters(W, L, (int) align_quantum(fb));
-    a.packed = packed;
+    if (L < 4 * W) break;
+    best = k;
+    if (force_k > 0 ? k >= force_k : (uint64_t) L <= want_len) break;
   }
-  double cost = 0.0;
-  for (const auto& kv : groups) {
-    const Acc& a = kv.second;
-    const double cap = (double) sms * (a.packed ? kPackedWarpsPerSM : kScalarWarpsPerSM);
-    const double waves = (double) a.warps / cap;
-    double full = floor(waves), frac = waves - full;
-    if (frac > 0.0 && frac < 0.5) frac = 0.5;
-    cost += (full + frac) * cap * a.niters * (a.packed ? kPackedIterCost : kScalarIterCost);
-  }
-  return cost;
+  return best;
 }
 
 inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, const PlanOptions& opt, Plan& p) {
   p = Plan();
   p.nalbums = nalbums;
-  // -- chunk length: the candidate (a chunk length of one of the batch's
-  // rates) with the lowest modelled sweep time.
+  // -- chunk length.  Measured on the B200 (profiles/r01_pair_tuning.txt): the
+  // sweep time is flat once a batch fills about two waves of resident warps and
+  // rises below that, while longer chunks only save warm-up frames.  So: the
+  // longest chunk that still gives every launch group ~1.8 waves.
   uint64_t want_len = 0;
-  const uint32_t sms = (uint32_t) (opt.target_tasks / 2048u);
   if (opt.force_k <= 0 && opt.target_tasks) {
-    uint64_t samples = 0;
-    for (size_t i = 0; i < n; ++i) samples += in[i].frames * (uint64_t) in[i].channels;
-    want_len = samples / opt.target_tasks;
+    const uint32_t sms = (uint32_t) (opt.target_tasks / 2048u);
     if (sms) {
-      std::map<uint32_t, int> rates;
-      for (size_t i = 0; i < n && rates.size() < 8; ++i) rates[in[i].samplerate] = 1;
-      double best = plan_cost(in, n, want_len, sms, opt.allow_packed);
-      for (const auto& r : rates) {
-        const int s100 = (int) ((r.first + 5) / 10);
-        const int W = warmup_frames(k_design(r.first));
-        for (int k = 1; k <= s100; ++k) {
-          if (s100 % k) continue;
-          const int L = s100 / k;
-          if (L < 4 * W) break;
-          const double c = plan_cost(in, n, (uint64_t) L, sms, opt.allow_packed);
-          if (c < best) { best = c; want_len = (uint64_t) L; }
-        }
+      double waves_frames = 0.0;       // sum over tracks of frames / (lane capacity of its kernel)
+      for (size_t i = 0; i < n; ++i) {
+        const bool packed = track_is_packed(in[i].channels, opt.allow_packed);
+        const double lanes_per_frame = packed ? in[i].channels / 2.0 : (double) in[i].channels;
+        const double cap = (double) sms * (packed ? kPackedWarpsPerSM : kScalarWarpsPerSM) * 32.0;
+        waves_frames += (double) in[i].frames * lanes_per_frame / cap;
       }
+      want_len = (uint64_t) (waves_frames / 1.8);
+    } else {
+      uint64_t samples = 0;
+      for (size_t i = 0; i < n; ++i) samples += in[i].frames * (uint64_t) in[i].channels;
+      want_len = samples / opt.target_tasks;
     }
+  } else if (opt.force_k <= 0) {
+    want_len = 0;                       // shortest chunks
   }
 
   std::map<std::tuple<uint32_t, int, uint32_t>, uint32_t> coef_index;
