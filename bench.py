@@ -300,22 +300,31 @@ def gpu_arm(args):
     for i, (h, (_, rate)) in enumerate(zip(host, album)):
         arr[i] = HostTrack(h.data_ptr(), h.shape[0], h.shape[1], rate, 0)
     out = (ScanResult * len(host))()
-    L.lgb_scan_host.argtypes = [C.POINTER(HostTrack), C.c_size_t, C.c_size_t, C.c_int, C.c_double,
-                                C.POINTER(ScanResult)]
+    L.lgb_scan_host_mt.argtypes = [C.POINTER(HostTrack), C.c_size_t, C.c_size_t, C.c_int, C.c_double,
+                                   C.c_uint, C.POINTER(ScanResult)]
     chunk = 4096
     os.environ.setdefault("LOUDGAIN_B200_DEVICE", str(local))
     e2e_steps = max(1, min(args.steps, 5))
-    for _ in range(min(args.warmup, 2)):
-        assert L.lgb_scan_host(arr, len(host), chunk, 1, 0.0, out) == 0
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        assert L.lgb_scan_host(arr, len(host), chunk, 1, 0.0, out) == 0
-    torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_value = samples * world * e2e_steps / float(dt.item()) / 1e9
+    # one scanner thread per track, as many as this rank's share of the host
+    # cores allows: the reference arm's model (one worker per track, rgbpm2)
+    cores = os.cpu_count() or 1
+    threads = max(1, min(len(host), cores // world))
+
+    def e2e_leg(nthreads):
+        for _ in range(min(args.warmup, 2)):
+            assert L.lgb_scan_host_mt(arr, len(host), chunk, 1, 0.0, nthreads, out) == 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            assert L.lgb_scan_host_mt(arr, len(host), chunk, 1, 0.0, nthreads, out) == 0
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return samples * world * e2e_steps / float(dt.item()) / 1e9
+
+    e2e_single = e2e_leg(1)
+    e2e_value = e2e_leg(threads) if threads > 1 else e2e_single
     d2h = (len(host) + 1) * 64 + 2 * 4 * sum(h.shape[1] for h in host)
 
     # ---- consistency: both paths measured the same album
@@ -336,7 +345,8 @@ def gpu_arm(args):
                        "l2_policy": "input (508 MB per GPU) is larger than L2 (126 MB); no flush",
                        "sharding": "by track; album block lists all-gathered over NCCL" if world > 1
                                    else "single GPU",
-                       "e2e_feed": f"ebur128_add_frames_short, {chunk}-frame calls, pinned host PCM"},
+                       "e2e_feed": f"ebur128_add_frames_short, {chunk}-frame calls from host PCM, "
+                                   f"{threads} scanner thread(s) per GPU (one file each at a time)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm if achieved else None, "traffic": _ncu_traffic(),
                          "traffic_source": "dram__bytes_read+write per launch, ncu --set full, "
@@ -347,7 +357,8 @@ def gpu_arm(args):
             "cpu_baseline": cpu,
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pcm_bytes,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "scanner_threads": threads,
+                    "single_thread_value": e2e_single},
             "gpu_launches": batch.kernel_launches * args.steps,
             "album_loudness": ares[0].loudness, "album_range": ares[0].range,
             "merged_album_loudness": merged.loudness if merged else None,

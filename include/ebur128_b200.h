@@ -133,6 +133,14 @@ typedef struct {              /* mirrors scan_result (scan.h:35-53) */
 int lgb_scan_host(const lgb_host_track* tracks, size_t ntracks, size_t chunk_frames,
                   int do_album, double pre_gain, lgb_scan_result* out);
 
+/* The same with up to `nthreads` scanner threads, one file per thread at a time
+ * (the reference parallelises over files and albums with one process each,
+ * bin/rgbpm2:170; ebur128 states are independent, so here the scanners share
+ * one library instance and the whole album is measured in one GPU batch).
+ * Queries run after all files are scanned, as in loudgain.c:299-340. */
+int lgb_scan_host_mt(const lgb_host_track* tracks, size_t ntracks, size_t chunk_frames,
+                     int do_album, double pre_gain, unsigned nthreads, lgb_scan_result* out);
+
 #ifdef __cplusplus
 }
 #endif

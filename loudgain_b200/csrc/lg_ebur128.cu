@@ -7,8 +7,11 @@
 //   files are scanned, per-track queries (:294-307) and per-album queries
 //   (:383-391), the latter repeated once per track; ebur128_destroy (:102).
 //
-// So add_frames only stages: host memcpy into a pinned double buffer, then
-// cudaMemcpyAsync into the state's device PCM.  The first query measures every
+// So add_frames only stages: host memcpy into a pinned staging buffer, then
+// cudaMemcpyAsync into the state's device PCM.  States are independent, as in
+// libebur128: different threads may feed different states at the same time
+// (the memcpy runs outside the library lock; the lock is only taken to claim
+// or flush a staging buffer), which is how the ingest reaches PCIe rate.  The first query measures every
 // state that has unmeasured audio in ONE batch (sweep + fix-up + gating on the
 // GPU); later queries read cached scalars, and *_multiple queries run only the
 // small gating/range kernel over block lists that are already in HBM.
@@ -23,6 +26,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <memory>
 #include <mutex>
 #include <vector>
@@ -34,8 +38,9 @@
 
 namespace {
 
-constexpr size_t kStageBytes = 8u << 20;   // each pinned staging buffer
-constexpr int kStageSlots = 4;             // ring of staging buffers, shared by all states
+constexpr size_t kStageBytes = 4u << 20;   // each pinned staging buffer
+constexpr int kStageSlots = 32;            // pool of staging buffers (allocated on first use),
+                                           // shared by all states: bounds the feeding threads
 
 struct BatchHolder {
   lgb_batch* b = nullptr;
@@ -62,9 +67,10 @@ struct Segment {
 // One pinned staging buffer.  A state owns a slot while it is filling it; a
 // flushed slot stays "in flight" until its H2D copy has completed.
 struct StageSlot {
-  char* buf = nullptr;
+  char* buf = nullptr;             // allocated on first use
   cudaEvent_t ev = nullptr;
   bool in_flight = false;
+  unsigned long long seq = 0;      // order of the flushes (oldest copy completes first)
   ebur128_state* owner = nullptr;
   size_t fill = 0;
 };
@@ -75,7 +81,7 @@ struct Context {
   int device = 0;
   cudaStream_t stream = nullptr;
   StageSlot slots[kStageSlots];
-  int next_slot = 0;
+  unsigned long long flush_seq = 0;
   std::vector<ebur128_state*> live;
   // cache of the last *_multiple query (loudgain repeats it per track)
   std::vector<std::pair<const void*, size_t>> multi_key;
@@ -109,10 +115,8 @@ bool ctx_init() {
   if (g_ctx.device < 0 || g_ctx.device >= n) g_ctx.device = 0;
   e = cudaSetDevice(g_ctx.device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking);
-  for (int i = 0; i < kStageSlots && e == cudaSuccess; ++i) {
-    e = cudaMallocHost((void**) &g_ctx.slots[i].buf, kStageBytes);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_ctx.slots[i].ev, cudaEventDisableTiming);
-  }
+  for (int i = 0; i < kStageSlots && e == cudaSuccess; ++i)
+    e = cudaEventCreateWithFlags(&g_ctx.slots[i].ev, cudaEventDisableTiming);
   if (e == cudaSuccess) {
     // keep freed device memory in the stream-ordered pool: states come and go
     cudaMemPool_t pool;
@@ -136,6 +140,7 @@ struct ebur128_state_internal {
   std::vector<Segment> segs;
   int chmap[lg::kMaxChannels];
   int slot = -1;                // staging slot this state is filling, or -1
+  std::atomic<bool> busy{false};  // inside add_frames (its slot must not be taken away)
   unsigned long window_ms = 400, history_ms = ULONG_MAX;
   std::vector<float> convert;   // host scratch for int / double input
 };
@@ -206,40 +211,79 @@ bool flush_stage(ebur128_state* st) {
     return false;
   cudaEventRecord(sl.ev, g_ctx.stream);
   sl.in_flight = true;
+  sl.seq = ++g_ctx.flush_seq;
   s.fill += sl.fill;
   sl.fill = 0;
   return true;
 }
 
-// Finds a staging slot for `st`: the next one in the ring, waiting for its
-// copy if it is still in flight, or taking it from a state that left it
-// partly filled (that state's bytes are flushed first).
+// Finds a staging slot for `st` (library lock held): a free one; else one
+// whose copy has completed; else one that an idle state left partly filled
+// (its bytes are flushed first); else the oldest copy in flight is waited for.
 bool acquire_slot(ebur128_state* st) {
-  StageSlot& sl = g_ctx.slots[g_ctx.next_slot];
-  if (sl.owner && !flush_stage(sl.owner)) return false;
-  if (sl.in_flight) {
-    if (!ctx_device() || cudaEventSynchronize(sl.ev) != cudaSuccess) return false;
-    sl.in_flight = false;
+  int pick = -1;
+  for (int i = 0; i < kStageSlots && pick < 0; ++i)
+    if (!g_ctx.slots[i].owner && !g_ctx.slots[i].in_flight && g_ctx.slots[i].buf) pick = i;
+  for (int i = 0; i < kStageSlots && pick < 0; ++i)
+    if (!g_ctx.slots[i].owner && !g_ctx.slots[i].in_flight) pick = i;        // not allocated yet
+  if (pick < 0 && !ctx_device()) return false;
+  for (int i = 0; i < kStageSlots && pick < 0; ++i) {
+    StageSlot& sl = g_ctx.slots[i];
+    if (!sl.owner && sl.in_flight && cudaEventQuery(sl.ev) == cudaSuccess) { sl.in_flight = false; pick = i; }
+  }
+  if (pick < 0) {
+    for (int i = 0; i < kStageSlots; ++i) {
+      StageSlot& sl = g_ctx.slots[i];
+      if (sl.owner && sl.owner != st && !sl.owner->d->busy.load(std::memory_order_acquire)) {
+        if (!flush_stage(sl.owner)) return false;
+        break;
+      }
+    }
+    unsigned long long oldest = ~0ull;
+    for (int i = 0; i < kStageSlots; ++i) {
+      const StageSlot& sl = g_ctx.slots[i];
+      if (!sl.owner && sl.in_flight && sl.seq < oldest) { oldest = sl.seq; pick = i; }
+    }
+    if (pick < 0) {
+      fprintf(stderr, "libebur128 (B200): more than %d states are being fed at the same time\n",
+              kStageSlots);
+      return false;
+    }
+    if (cudaEventSynchronize(g_ctx.slots[pick].ev) != cudaSuccess) return false;
+    g_ctx.slots[pick].in_flight = false;
+  }
+  StageSlot& sl = g_ctx.slots[pick];
+  if (!sl.buf) {
+    if (!ctx_device() || cudaMallocHost((void**) &sl.buf, kStageBytes) != cudaSuccess) {
+      sl.buf = nullptr;
+      return false;
+    }
   }
   sl.owner = st;
   sl.fill = 0;
-  st->d->slot = g_ctx.next_slot;
-  g_ctx.next_slot = (g_ctx.next_slot + 1) % kStageSlots;
+  st->d->slot = pick;
   return true;
 }
 
-// Copies `bytes` of caller PCM through the pinned staging ring.
+// Copies `bytes` of caller PCM through the pinned staging pool.  The memcpy
+// runs without the library lock; the lock is taken to claim or flush a slot.
 bool stage_bytes(ebur128_state* st, const char* src, size_t bytes) {
   ebur128_state_internal* d = st->d;
   while (bytes) {
-    if (d->slot < 0 && !acquire_slot(st)) return false;
+    if (d->slot < 0) {
+      std::lock_guard<std::mutex> lock(g_ctx.mu);
+      if (!acquire_slot(st)) return false;
+    }
     StageSlot& sl = g_ctx.slots[d->slot];
     const size_t n = std::min(bytes, kStageBytes - sl.fill);
     memcpy(sl.buf + sl.fill, src, n);
     sl.fill += n;
     src += n;
     bytes -= n;
-    if (sl.fill == kStageBytes && !flush_stage(st)) return false;
+    if (sl.fill == kStageBytes) {
+      std::lock_guard<std::mutex> lock(g_ctx.mu);
+      if (!flush_stage(st)) return false;
+    }
   }
   return true;
 }
@@ -247,22 +291,26 @@ bool stage_bytes(ebur128_state* st, const char* src, size_t bytes) {
 int add_frames(ebur128_state* st, const void* src, size_t frames, uint32_t format) {
   if (!st || !st->d) return EBUR128_ERROR_NOMEM;
   if (!frames) return EBUR128_SUCCESS;
-  std::lock_guard<std::mutex> lock(g_ctx.mu);
-  if (!g_ctx.ready) return EBUR128_ERROR_NOMEM;
   ebur128_state_internal* d = st->d;
   Segment* s = &d->segs.back();
-  if (s->frames == 0) s->format = format;
-  if (s->format != format) {
-    // Mixing sample types on one state is not supported: the PCM of a state
-    // is kept in one format in HBM.
-    fprintf(stderr, "libebur128 (B200): mixing sample formats on one state is not supported\n");
-    return EBUR128_ERROR_INVALID_MODE;
+  {
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    if (!g_ctx.ready) return EBUR128_ERROR_NOMEM;
+    if (s->frames == 0) s->format = format;
+    if (s->format != format) {
+      // Mixing sample types on one state is not supported: the PCM of a state
+      // is kept in one format in HBM.
+      fprintf(stderr, "libebur128 (B200): mixing sample formats on one state is not supported\n");
+      return EBUR128_ERROR_INVALID_MODE;
+    }
+    if (s->measured) invalidate(*s);
+    d->busy.store(true, std::memory_order_relaxed);
   }
-  if (s->measured) invalidate(*s);
   const size_t bytes = frames * st->channels * sample_bytes(format);
-  if (!stage_bytes(st, (const char*) src, bytes)) return EBUR128_ERROR_NOMEM;
-  s->frames += frames;
-  return EBUR128_SUCCESS;
+  const bool ok = stage_bytes(st, (const char*) src, bytes);
+  if (ok) s->frames += frames;
+  d->busy.store(false, std::memory_order_release);
+  return ok ? EBUR128_SUCCESS : EBUR128_ERROR_NOMEM;
 }
 
 // Measures every live state that has audio the GPU has not looked at yet, in
@@ -270,6 +318,9 @@ int add_frames(ebur128_state* st, const void* src, size_t frames, uint32_t forma
 bool measure_pending() {
   std::vector<Segment*> todo;
   for (ebur128_state* st : g_ctx.live) {
+    // a state another thread is feeding right now is left alone (the caller
+    // does not query a state while feeding it, as with libebur128)
+    if (st->d->busy.load(std::memory_order_acquire)) continue;
     if (!flush_stage(st)) return false;
     for (Segment& s : st->d->segs)
       if (!s.measured) todo.push_back(&s);

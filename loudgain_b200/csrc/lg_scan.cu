@@ -7,6 +7,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "../../include/ebur128.h"
@@ -30,28 +32,60 @@ double max_true_peak(ebur128_state* st) {
 
 }  // namespace
 
+// scan_file (scan.c:110-273) for one track: init, then one add_frames call per
+// `chunk_frames` frames.
+static int scan_one(const lgb_host_track& t, size_t chunk_frames, ebur128_state** out) {
+  *out = ebur128_init(t.channels, t.samplerate,
+                      EBUR128_MODE_S | EBUR128_MODE_I | EBUR128_MODE_LRA |
+                          EBUR128_MODE_SAMPLE_PEAK | EBUR128_MODE_TRUE_PEAK);
+  if (!*out) return 1;
+  const size_t step = chunk_frames ? chunk_frames : (t.frames ? t.frames : 1);
+  const size_t fb = t.channels * (t.format == LGB_FORMAT_S16 ? 2u : 4u);
+  for (uint64_t pos = 0; pos < t.frames; pos += step) {
+    const size_t n = (size_t) (t.frames - pos < step ? t.frames - pos : step);
+    const char* p = (const char*) t.pcm + pos * fb;
+    const int e = t.format == LGB_FORMAT_S16
+                      ? ebur128_add_frames_short(*out, (const short*) p, n)
+                      : ebur128_add_frames_float(*out, (const float*) p, n);
+    if (e != EBUR128_SUCCESS) return 2;
+  }
+  return 0;
+}
+
 extern "C" LG_EXPORT int lgb_scan_host(const lgb_host_track* tracks, size_t ntracks,
                                        size_t chunk_frames, int do_album, double pre_gain,
                                        lgb_scan_result* out) {
+  return lgb_scan_host_mt(tracks, ntracks, chunk_frames, do_album, pre_gain, 1, out);
+}
+
+// The same with `nthreads` feeding threads, one file per thread at a time --
+// the reference's own parallel model is one scanner per file/album
+// (bin/rgbpm2:170, multiprocessing.Pool); here the scanners share one library
+// instance, so that all files of the album are measured in one GPU batch.
+extern "C" LG_EXPORT int lgb_scan_host_mt(const lgb_host_track* tracks, size_t ntracks,
+                                          size_t chunk_frames, int do_album, double pre_gain,
+                                          unsigned nthreads, lgb_scan_result* out) {
   std::vector<ebur128_state*> states(ntracks, nullptr);
   int rc = 0;
   // ---- scan_file for every file first (loudgain.c:299-305)
-  for (size_t i = 0; i < ntracks && !rc; ++i) {
-    const lgb_host_track& t = tracks[i];
-    states[i] = ebur128_init(t.channels, t.samplerate,
-                             EBUR128_MODE_S | EBUR128_MODE_I | EBUR128_MODE_LRA |
-                                 EBUR128_MODE_SAMPLE_PEAK | EBUR128_MODE_TRUE_PEAK);
-    if (!states[i]) { rc = 1; break; }
-    const size_t step = chunk_frames ? chunk_frames : (t.frames ? t.frames : 1);
-    const size_t fb = t.channels * (t.format == LGB_FORMAT_S16 ? 2u : 4u);
-    for (uint64_t pos = 0; pos < t.frames; pos += step) {
-      const size_t n = (size_t) (t.frames - pos < step ? t.frames - pos : step);
-      const char* p = (const char*) t.pcm + pos * fb;
-      const int e = t.format == LGB_FORMAT_S16
-                        ? ebur128_add_frames_short(states[i], (const short*) p, n)
-                        : ebur128_add_frames_float(states[i], (const float*) p, n);
-      if (e != EBUR128_SUCCESS) { rc = 2; break; }
-    }
+  if (nthreads <= 1 || ntracks <= 1) {
+    for (size_t i = 0; i < ntracks && !rc; ++i) rc = scan_one(tracks[i], chunk_frames, &states[i]);
+  } else {
+    std::atomic<size_t> next{0};
+    std::atomic<int> err{0};
+    auto worker = [&]() {
+      for (;;) {
+        const size_t i = next.fetch_add(1);
+        if (i >= ntracks || err.load()) break;
+        const int e = scan_one(tracks[i], chunk_frames, &states[i]);
+        if (e) err.store(e);
+      }
+    };
+    std::vector<std::thread> pool;
+    const unsigned n = nthreads < ntracks ? nthreads : (unsigned) ntracks;
+    for (unsigned k = 0; k < n; ++k) pool.emplace_back(worker);
+    for (std::thread& th : pool) th.join();
+    rc = err.load();
   }
   // ---- results (loudgain.c:323-340): track, then album, per file
   for (size_t i = 0; i < ntracks && !rc; ++i) {

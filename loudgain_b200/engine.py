@@ -335,3 +335,39 @@ def merge_album_across_ranks(batch: Batch, tracks, dist, world: int) -> Measurem
         return m.fetch()
     finally:
         m.close()
+
+
+# ------------------------------------------------------------- scan.c driver
+
+class _HostTrack(C.Structure):
+    _fields_ = [("pcm", C.c_void_p), ("frames", C.c_uint64), ("channels", C.c_uint32),
+                ("samplerate", C.c_uint32), ("format", C.c_uint32)]
+
+
+class ScanResult(C.Structure):
+    """Mirror of the reference's scan_result (scan.h:35-53)."""
+    _fields_ = [(n, C.c_double) for n in (
+        "track_gain", "track_peak", "track_loudness", "track_loudness_range", "album_gain",
+        "album_peak", "album_loudness", "album_loudness_range", "loudness_reference")]
+
+
+def scan_host(tracks, chunk_frames=4096, do_album=True, pre_gain=0.0, threads=1):
+    """scan.c's call sequence over host PCM (numpy int16 / float32 arrays
+    [frames, channels]) through the drop-in ebur128_* ABI: one
+    ebur128_add_frames call per `chunk_frames` frames, `threads` scanner
+    threads (one file each at a time), queries after all files.  Returns one
+    ScanResult per track."""
+    import numpy as np
+    L = _bind()
+    L.lgb_scan_host_mt.argtypes = [C.POINTER(_HostTrack), C.c_size_t, C.c_size_t, C.c_int,
+                                   C.c_double, C.c_uint, C.POINTER(ScanResult)]
+    keep = [np.ascontiguousarray(p) for p, _ in tracks]
+    arr = (_HostTrack * len(tracks))()
+    for i, (p, (_, rate)) in enumerate(zip(keep, tracks)):
+        assert p.dtype in (np.int16, np.float32) and p.ndim == 2
+        arr[i] = _HostTrack(p.ctypes.data, p.shape[0], p.shape[1], rate, 0 if p.dtype == np.int16 else 1)
+    out = (ScanResult * len(tracks))()
+    rc = L.lgb_scan_host_mt(arr, len(tracks), chunk_frames, 1 if do_album else 0, pre_gain, threads, out)
+    if rc:
+        raise RuntimeError(f"lgb_scan_host_mt failed ({rc}): {_err(L)}")
+    return list(out)

@@ -153,6 +153,26 @@ def test_chunking_invariance(product):
         assert got == ref
 
 
+def test_threaded_scanners_match_single_thread(product):
+    """Different threads feed different states at the same time (states are
+    independent, as in libebur128): the results do not depend on it, also with
+    more files than scanner threads and more states than staging buffers."""
+    from loudgain_b200 import engine
+    rng = np.random.default_rng(11)
+    tracks = []
+    for i in range(40):
+        n = int(rng.integers(30000, 400000))
+        ch = 2 if i % 5 else 1
+        tracks.append(((rng.standard_normal((n, ch)) * (1500 + 300 * i)).astype(np.int16),
+                       44100 if i % 3 else 48000))
+    fields = [n for n, _ in engine.ScanResult._fields_]
+    one = engine.scan_host(tracks, chunk_frames=1024, threads=1)
+    for threads in (4, 12):
+        many = engine.scan_host(tracks, chunk_frames=1024, threads=threads)
+        for a, b in zip(one, many):
+            assert [getattr(a, f) for f in fields] == [getattr(b, f) for f in fields]
+
+
 @pytest.mark.parametrize("frames", [0, 1, 11, 4409, 17639, 17640, 17641, 132300])
 def test_ragged_lengths(product, oracle, frames):
     rng = np.random.default_rng(frames)
