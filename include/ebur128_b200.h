@@ -37,6 +37,11 @@ typedef struct {
   uint32_t album;              /* album index < nalbums, or LGB_NO_ALBUM */
   const uint8_t* weight_class; /* optional HOST array [channels]: 0 unused, 1 -> 1.0,
                                   2 -> 1.41, 3 -> 2.0; NULL = default channel map */
+  uint64_t lead_in;            /* frames at the start that are context only: the tail of the
+                                  preceding audio when the track is one time segment of a
+                                  longer stream (lgb_slots_query).  They warm the filters and
+                                  the interpolator; no true-peak output is taken inside them.
+                                  Must be a whole number of 100 ms slots.  0 = a whole track. */
 } lgb_track;
 
 typedef struct {
@@ -95,6 +100,16 @@ void lgb_batch_destroy(lgb_batch* b);
  * z[i] / st[i] are DEVICE pointers to doubles.  Synchronous.  0 on success. */
 int lgb_query_lists(const double* const* z, const uint32_t* nz, const double* const* st,
                     const uint32_t* nst, size_t n, void* cuda_stream, lgb_result* out);
+
+/* Gated loudness + range of ONE stream from its 100 ms slot energies (kind 2 of
+ * lgb_batch_blocks), e.g. the slot lists of the time segments of a long stream
+ * measured on several GPUs, concatenated in time order after dropping each
+ * segment's lead-in slots: forms the 400 ms gating blocks (hop 100 ms) and the
+ * 3 s short-term blocks (hop 1 s) over the whole list, then gates.
+ * `slots` is a DEVICE pointer; s100 = frames per slot = (rate + 5) / 10.
+ * Synchronous.  0 on success. */
+int lgb_slots_query(const double* slots, uint64_t nslots, uint32_t s100, void* cuda_stream,
+                    lgb_result* out);
 
 /* Persistent form of lgb_query_lists for a fixed set of device buffers (a
  * pre-allocated all-gather target that is refilled every step): tables are

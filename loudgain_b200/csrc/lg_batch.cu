@@ -138,7 +138,13 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
       set_error("lgb_batch_create: invalid track descriptor");
       return nullptr;
     }
-    in[i] = TrackIn{t.pcm, t.frames, t.channels, t.samplerate, t.format, t.album, t.weight_class};
+    const uint32_t s100 = (t.samplerate + 5) / 10;
+    if (t.lead_in % s100 || t.lead_in > t.frames) {
+      set_error("lgb_batch_create: lead_in must be a whole number of 100 ms slots within the track");
+      return nullptr;
+    }
+    in[i] = TrackIn{t.pcm, t.frames, t.channels, t.samplerate, t.format, t.album, t.weight_class,
+                    t.lead_in};
   }
   lgb_batch* b = new lgb_batch();
   b->stream = (cudaStream_t) cuda_stream;
@@ -372,6 +378,34 @@ extern "C" LG_EXPORT int lgb_query_lists(const double* const* z, const uint32_t*
   for (size_t i = 0; i < n; ++i) lists[i] = BlockList{z[i], st[i], nz[i], nst[i]};
   QueryResult q;
   if (query_lists_sync(lists.data(), n, (cudaStream_t) cuda_stream, &q)) return 1;
+  to_result(q, *out);
+  return 0;
+}
+
+extern "C" LG_EXPORT int lgb_slots_query(const double* slots, uint64_t nslots, uint32_t s100,
+                                         void* cuda_stream, lgb_result* out) {
+  g_error.clear();
+  if (!s100 || (nslots && !slots) || nslots > 0xfffffff0ull) {
+    set_error("lgb_slots_query: invalid arguments");
+    return 1;
+  }
+  cudaStream_t stream = (cudaStream_t) cuda_stream;
+  const uint64_t nblocks = nslots >= 4 ? nslots - 3 : 0;
+  const uint64_t nst = nslots >= 30 ? (nslots - 30) / 10 + 1 : 0;
+  double *zblock = nullptr, *zst = nullptr;
+  bool ok = dalloc(&zblock, nblocks, stream) && dalloc(&zst, nst, stream);
+  QueryResult q;
+  if (ok) {
+    const cudaError_t e = launch_stream_blocks(slots, (int) s100, nblocks, nst, zblock, zst, stream);
+    if (e != cudaSuccess) { set_error("launch_stream_blocks", e); ok = false; }
+  }
+  if (ok) {
+    const BlockList bl{zblock, zst, (uint32_t) nblocks, (uint32_t) nst};
+    ok = query_lists_sync(&bl, 1, stream, &q) == 0;
+  }
+  if (zblock) cudaFreeAsync(zblock, stream);
+  if (zst) cudaFreeAsync(zst, stream);
+  if (!ok) return 1;
   to_result(q, *out);
   return 0;
 }

@@ -113,6 +113,7 @@ struct Track {
   uint64_t block_base; // first gating block
   uint64_t st_base;    // first short-term block
   uint64_t peak_base;  // first per-channel peak cell
+  uint64_t lead_in;    // leading context frames: no true-peak output is taken inside them
   // BS.1770 channel weight class: 0 unused, 1 -> 1.0, 2 -> 1.41, 3 -> 2.0
   uint8_t wclass[kMaxChannels];
 };

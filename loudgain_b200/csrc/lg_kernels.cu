@@ -343,6 +343,7 @@ struct TpLane {
   uint32_t track, ch;
   long long a;       // track frame of lane-local frame 0
   int f_lo, f_end;   // lane-local frames the true-peak pass owns: [f_lo, f_end)
+  long long lead_in; // track frames of leading context (no true-peak output inside)
   bool ok;
 };
 
@@ -357,6 +358,7 @@ __device__ __forceinline__ TpLane tp_locate(const SweepParams& P, uint32_t w, ui
   r.ok = slot < P.cpw && r.ch < P.channels && chunk < tr.nchunks;
   const LaneGeom g = lane_geometry((long long) tr.frames, P.L, P.W, P.aq, chunk);
   r.a = g.a;
+  r.lead_in = (long long) tr.lead_in;
   r.f_lo = P.W + g.o;
   const long long left = (long long) tr.frames - g.a;      // frames of the track from local 0
   const int f_hi = r.f_lo + P.L;
@@ -461,7 +463,7 @@ truepeak_kernel(const __grid_constant__ SweepParams P, const uint32_t seg_pairs)
             const uint32_t iter = (p0 + j) * 2u + it;
             const int f0 = (int) iter * kIter;
             const bool hit = me.ok && p0 + j < p_end && P.tp_bound * peak_code_value(cm) > floor_ &&
-                             f0 + kIter > me.f_lo && f0 < me.f_end;
+                             f0 + kIter > me.f_lo && f0 < me.f_end && me.a + f0 + kIter > me.lead_in;
             const unsigned mask = __ballot_sync(0xffffffffu, hit);
             if (mask) {
               if (hit)
@@ -584,6 +586,24 @@ block_kernel(const Track* __restrict__ tracks, uint32_t ntracks,
     const Track& tr = tracks[ti];
     zst[j] = shortterm_block(eslot + tr.slot_base, coefs[tr.coef], (uint32_t) (j - tr.st_base));
   }
+}
+
+// Blocks of one stream from its complete slot list (time segments measured
+// separately, e.g. on several GPUs, and concatenated: lgb_slots_query).
+__global__ void __launch_bounds__(256)
+stream_block_kernel(const double* __restrict__ eslot, int s100, uint64_t nblocks, uint64_t nst,
+                    double* __restrict__ zblock, double* __restrict__ zst) {
+  const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nblocks) zblock[i] = gating_block(eslot, s100, i);
+  else if (i < nblocks + nst) zst[i - nblocks] = shortterm_block(eslot, s100, i - nblocks);
+}
+
+cudaError_t launch_stream_blocks(const double* eslot, int s100, uint64_t nblocks, uint64_t nst,
+                                 double* zblock, double* zst, cudaStream_t stream) {
+  if (nblocks + nst == 0) return cudaSuccess;
+  const unsigned blocks = (unsigned) ((nblocks + nst + 255) / 256);
+  stream_block_kernel<<<blocks, 256, 0, stream>>>(eslot, s100, nblocks, nst, zblock, zst);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------- reductions

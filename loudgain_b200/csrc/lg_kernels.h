@@ -45,6 +45,9 @@ cudaError_t launch_sweep_pair(const SweepParams& p, uint32_t format, int tpf, cu
 cudaError_t launch_truepeak_pair(const SweepParams& p, uint32_t format, int tpf, uint32_t sms,
                                  cudaStream_t stream);
 cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t stream);
+// 400 ms / 3 s blocks of one stream from its complete 100 ms slot list.
+cudaError_t launch_stream_blocks(const double* eslot, int s100, uint64_t nblocks, uint64_t nst,
+                                 double* zblock, double* zst, cudaStream_t stream);
 // Gated loudness + range for `nqueries` queries; all pointers are device memory.
 cudaError_t launch_queries(const BlockList* lists, const Query* queries, const uint32_t* members,
                            uint32_t nqueries, double abs_gate, QueryResult* results,

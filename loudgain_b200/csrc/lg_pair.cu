@@ -596,7 +596,8 @@ truepeak_pair_kernel(const __grid_constant__ SweepParams P, const uint32_t seg_p
       const uint32_t cm = __vmaxu2(code, prev);      // per channel: this pair and its history
       prev = code;
       const int f0 = (int) (p * kPairFrames);
-      const bool own = ok && f0 + kPairFrames > f_lo && f0 < f_end;
+      const bool own = ok && f0 + kPairFrames > f_lo && f0 < f_end &&
+                       g.a + f0 + kPairFrames > (long long) tr.lead_in;
       const bool hit0 = own && P.tp_bound * pair_code_value<FMT>(cm & 0xffffu) > floor0;
       const bool hit1 = own && P.tp_bound * pair_code_value<FMT>(cm >> 16) > floor1;
       const unsigned m0 = __ballot_sync(0xffffffffu, hit0);

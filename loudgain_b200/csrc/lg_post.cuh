@@ -71,15 +71,21 @@ LG_HD double slot_energy(const Track& tr, const CoefSet& cs, const double* echun
   return total * cs.gain;
 }
 
-LG_HD double gating_block(const double* eslot, const CoefSet& cs, uint32_t b) {
+LG_HD double gating_block(const double* eslot, int s100, uint64_t b) {
   const double s = (eslot[b] + eslot[b + 1]) + (eslot[b + 2] + eslot[b + 3]);
-  return s / (4.0 * (double) cs.s100);
+  return s / (4.0 * (double) s100);
+}
+LG_HD double gating_block(const double* eslot, const CoefSet& cs, uint32_t b) {
+  return gating_block(eslot, cs.s100, b);
 }
 
-LG_HD double shortterm_block(const double* eslot, const CoefSet& cs, uint32_t j) {
+LG_HD double shortterm_block(const double* eslot, int s100, uint64_t j) {
   double s = 0.0;
   for (int i = 0; i < 30; ++i) s += eslot[10u * j + i];
-  return s / (30.0 * (double) cs.s100);
+  return s / (30.0 * (double) s100);
+}
+LG_HD double shortterm_block(const double* eslot, const CoefSet& cs, uint32_t j) {
+  return shortterm_block(eslot, cs.s100, j);
 }
 
 // 10^((-70 + 0.691)/10): absolute gate as block energy.

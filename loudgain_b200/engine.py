@@ -26,7 +26,7 @@ FORMAT_S16, FORMAT_F32 = 0, 1
 class _Track(C.Structure):
     _fields_ = [("pcm", C.c_void_p), ("frames", C.c_uint64), ("channels", C.c_uint32),
                 ("samplerate", C.c_uint32), ("format", C.c_uint32), ("album", C.c_uint32),
-                ("weight_class", C.c_void_p)]
+                ("weight_class", C.c_void_p), ("lead_in", C.c_uint64)]
 
 
 class _Result(C.Structure):
@@ -87,7 +87,10 @@ class Batch:
     """A planned measurement of `tracks` = [(cuda tensor [frames, channels] of
     int16 or float32, sample rate)], optionally grouped into albums."""
 
-    def __init__(self, tracks: Sequence, albums: Sequence[int] | None = None, stream=None):
+    def __init__(self, tracks: Sequence, albums: Sequence[int] | None = None, stream=None,
+                 lead_in: Sequence[int] | None = None):
+        """lead_in[i]: leading context frames of track i (a whole number of
+        100 ms slots) when the track is one time segment of a longer stream."""
         import torch
 
         L = _bind()
@@ -109,7 +112,8 @@ class Batch:
                 nalb = max(nalb, alb + 1)
             self._keep.append(pcm)
             self.channels.append(pcm.shape[1])
-            arr[i] = _Track(pcm.data_ptr(), pcm.shape[0], pcm.shape[1], int(rate), fmt, alb, None)
+            arr[i] = _Track(pcm.data_ptr(), pcm.shape[0], pcm.shape[1], int(rate), fmt, alb, None,
+                            0 if lead_in is None else int(lead_in[i]))
         self.ntracks, self.nalbums = n, nalb
         self.stream = stream if stream is not None else torch.cuda.current_stream()
         self._h = L.lgb_batch_create(arr, n, nalb, C.c_void_p(self.stream.cuda_stream))
@@ -278,6 +282,20 @@ class AlbumMerge:
         self.send = torch.zeros(self.width, dtype=torch.float64, device=dev)
         self.recv = torch.zeros(world * self.width, dtype=torch.float64, device=dev)
         self.nz, self.nst = nz, nst
+        # Pack plan: the library lays the block lists of consecutive tracks out
+        # back to back, so adjacent views are merged into one device copy each.
+        self._runs = []
+        off = 0
+        for v in self.z_views + self.st_views:
+            n = v.numel()
+            if n:
+                if self._runs and self._runs[-1][0] + self._runs[-1][1] * 8 == v.data_ptr() \
+                        and self._runs[-1][2] + self._runs[-1][1] == off:
+                    self._runs[-1][1] += n
+                else:
+                    self._runs.append([v.data_ptr(), n, off])
+            off += n
+        self._run_views = [(torch.as_tensor(_DeviceView(p, n), device=dev), o) for p, n, o in self._runs]
         L = _bind()
         L.lgb_listquery_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_uint32),
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_uint32),
@@ -304,12 +322,8 @@ class AlbumMerge:
         import torch
 
         with torch.cuda.stream(self.batch.stream):
-            off = 0
-            for v in self.z_views + self.st_views:
-                n = v.numel()
-                if n:
-                    self.send[off:off + n].copy_(v, non_blocking=True)
-                off += n
+            for v, off in self._run_views:
+                self.send[off:off + v.numel()].copy_(v, non_blocking=True)
             self.dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
         if self._L.lgb_listquery_run(self._h):
             raise RuntimeError("lgb_listquery_run failed: " + _err(self._L))
@@ -335,6 +349,88 @@ def merge_album_across_ranks(batch: Batch, tracks, dist, world: int) -> Measurem
         return m.fetch()
     finally:
         m.close()
+
+
+# ------------------------------------------------- one stream, sharded by time
+
+def segment_plan(frames: int, rate: int, parts: int, lead_in_slots: int = 10):
+    """Cuts a stream of `frames` frames into `parts` contiguous time segments
+    (BASELINE config 4).  Segments start on whole seconds (10
+    slots of 100 ms), so that neither a slot nor a 1 s short-term hop straddles
+    two segments; every segment but the first is preceded by `lead_in_slots`
+    slots of the audio before it.  Returns [(first_frame_incl_lead_in,
+    lead_in_frames, end_frame)] -- segment i measures frames
+    [first + lead_in, end) and reads [first, end).
+
+    The lead-in replaces an exchange of filter state between neighbours: a
+    rank starts its filters at zero state one second early, and the K-filter's
+    slowest mode (|pole| <= 0.9987 at 192 kHz) has decayed below 1e-18 of the
+    state it started from long before the segment's own first frame."""
+    s100 = (rate + 5) // 10
+    sec = 10 * s100
+    nsec = max(frames // sec, 1)
+    cuts = [min((nsec * i // parts) * sec, frames) for i in range(parts)] + [frames]
+    plan = []
+    for i in range(parts):
+        lead = min(lead_in_slots * s100, cuts[i]) if i else 0
+        plan.append((cuts[i] - lead, lead, cuts[i + 1]))
+    return plan
+
+
+def slots_query(slots: "torch.Tensor", rate: int, stream=None) -> Measurement:
+    """Gated loudness + range of one stream from its complete list of 100 ms
+    slot energies on the device (lgb_slots_query)."""
+    import torch
+
+    L = _bind()
+    L.lgb_slots_query.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(_Result)]
+    stream = stream if stream is not None else torch.cuda.current_stream()
+    slots = slots.contiguous()
+    r = _Result()
+    if L.lgb_slots_query(C.c_void_p(slots.data_ptr() if slots.numel() else None), slots.numel(),
+                         (int(rate) + 5) // 10, C.c_void_p(stream.cuda_stream), C.byref(r)):
+        raise RuntimeError("lgb_slots_query failed: " + _err(L))
+    return Measurement(r.loudness, r.range, r.rel_threshold, r.sum_abs, r.sum_rel, r.n_abs,
+                       r.n_rel, r.n_shortterm)
+
+
+def measure_stream_segments(segments, rate: int, dist=None, world: int = 1, group=None,
+                            stream=None) -> Measurement:
+    """Measures ONE stream whose time segments are spread over ranks.
+
+    `segments`: this rank's segments in time order, [(cuda tensor [frames,
+    channels] holding lead-in + segment, lead_in_frames)], cut by segment_plan;
+    rank r holds the segments that precede rank r+1's.  Every rank sweeps its
+    segments in one batch, drops the lead-in slots, all-gathers the 100 ms slot
+    energies (a few MB for ten hours) and the per-channel peaks over
+    NCCL/NVLink, and forms blocks, gates and the range over the whole slot list
+    (lgb_slots_query).  The result is the same on every rank and equals the
+    single-device measurement of the whole stream."""
+    import torch
+
+    s100 = (int(rate) + 5) // 10
+    b = Batch([(p, rate) for p, _ in segments], None, stream, lead_in=[l for _, l in segments])
+    try:
+        b.run()
+        tres, _ = b.fetch()
+        parts = [device_blocks(b, i, 2)[lead // s100:] for i, (_, lead) in enumerate(segments)]
+        dev = segments[0][0].device if segments else torch.device("cuda")
+        local = torch.cat(parts) if parts else torch.zeros(0, dtype=torch.float64, device=dev)
+        nch = segments[0][0].shape[1] if segments else 0
+        peaks = torch.zeros(2, max(nch, 1), dtype=torch.float64, device=dev)
+        for m in tres:
+            peaks[0, :nch] = torch.maximum(peaks[0, :nch], torch.as_tensor(m.sample_peak, device=dev))
+            peaks[1, :nch] = torch.maximum(peaks[1, :nch], torch.as_tensor(m.true_peak, device=dev))
+        if world > 1:
+            lists = gather_block_lists(dist, local, world, group)
+            local = torch.cat(lists)
+            dist.all_reduce(peaks, op=dist.ReduceOp.MAX, group=group)
+        out = slots_query(local, rate, stream)
+        out.sample_peak = peaks[0, :nch].cpu().numpy()
+        out.true_peak = peaks[1, :nch].cpu().numpy()
+        return out
+    finally:
+        b.close()
 
 
 # ------------------------------------------------------------- scan.c driver

@@ -66,7 +66,8 @@ static void run_group(const Plan& p, const SweepGroup& g, std::vector<ChunkRec>&
         lc.code.push_back(peak_code(m));
         lc.iter_max.push_back(m);
         if (NT > 0) {
-          if (tp_iter_owned((int) it, c.f_lo, c.f_hi, geo.a, (long long) tr.frames)) {
+          if (tp_iter_owned((int) it, c.f_lo, c.f_hi, geo.a, (long long) tr.frames) &&
+              geo.a + f0 + kIter > (long long) tr.lead_in) {
             const long long left = (long long) tr.frames - (geo.a + f0);
             tp = std::max(tp, tp_window_valid<TPF>(win, left > kIter ? kIter : (int) left));
           }
@@ -105,6 +106,7 @@ static void run_group(const Plan& p, const SweepGroup& g, std::vector<ChunkRec>&
         if (pr) cm = std::max(cm, pcode(pr - 1));
         const int f0 = (int) pr * kPairFrames;
         if (!(f0 + kPairFrames > f_lo && f0 < f_end)) continue;
+        if (!(lc.geo.a + f0 + kPairFrames > (long long) tr.lead_in)) continue;
         if (!(k.tp_bound * pair_code_value<FMT>(cm) > floor_)) continue;
         for (int h = 0; h < 2; ++h) {
           const long long t0 = lc.geo.a + f0 + h * kIter;
@@ -128,6 +130,7 @@ static void run_group(const Plan& p, const SweepGroup& g, std::vector<ChunkRec>&
       for (uint32_t b = 1; b <= (uint32_t) NT / kIter && b <= it; ++b) cm = std::max(cm, lc.code[it - b]);
       if (!(k.tp_bound * peak_code_value(cm) > floor_)) continue;
       if (!tp_iter_owned((int) it, f_lo, f_hi, lc.geo.a, (long long) tr.frames)) continue;
+      if (!(lc.geo.a + (long long) it * kIter + kIter > (long long) tr.lead_in)) continue;
       float win[(NT > 0 ? NT : 1) + kIter];
       const long long t0 = lc.geo.a + (long long) it * kIter;
       for (int q = 0; q < NT + kIter; ++q) {
@@ -202,11 +205,11 @@ extern "C" int emu_measure(const lgb_track* tracks, size_t ntracks, uint32_t nal
                            uint64_t target_tasks, lgb_result* track_results,
                            lgb_result* album_results, double* sample_peaks, double* true_peaks,
                            double* blocks_out, double* st_out, int32_t* chunk_len_out,
-                           double* true_peaks_screened) {
+                           double* true_peaks_screened, double* slots_out) {
   std::vector<TrackIn> in(ntracks);
   for (size_t i = 0; i < ntracks; ++i)
     in[i] = TrackIn{tracks[i].pcm, tracks[i].frames, tracks[i].channels, tracks[i].samplerate,
-                    tracks[i].format, tracks[i].album, tracks[i].weight_class};
+                    tracks[i].format, tracks[i].album, tracks[i].weight_class, tracks[i].lead_in};
   Plan p;
   PlanOptions opt;
   opt.target_tasks = target_tasks;
@@ -263,6 +266,7 @@ extern "C" int emu_measure(const lgb_track* tracks, size_t ntracks, uint32_t nal
       }
     }
   }
+  if (slots_out) std::copy(eslot.begin(), eslot.end(), slots_out);   // [sum of frames / s100]
   if (blocks_out) std::copy(zblock.begin(), zblock.end(), blocks_out);
   if (st_out) std::copy(zst.begin(), zst.end(), st_out);
   return 0;

@@ -21,7 +21,7 @@ GOAL_LU = 2e-4
 class LgbTrack(C.Structure):
     _fields_ = [("pcm", C.c_void_p), ("frames", C.c_uint64), ("channels", C.c_uint32),
                 ("samplerate", C.c_uint32), ("format", C.c_uint32), ("album", C.c_uint32),
-                ("weight_class", C.c_void_p)]
+                ("weight_class", C.c_void_p), ("lead_in", C.c_uint64)]
 
 
 class LgbResult(C.Structure):
@@ -45,7 +45,7 @@ def build_emu() -> str:
     return so
 
 
-def emu_measure(tracks, albums=None, target_tasks=0):
+def emu_measure(tracks, albums=None, target_tasks=0, lead_in=None):
     """tracks: list of (pcm ndarray [frames, ch] int16/float32, rate).
     Returns dict with per-track / per-album results, peaks and block lists."""
     lib = C.CDLL(build_emu())
@@ -60,7 +60,8 @@ def emu_measure(tracks, albums=None, target_tasks=0):
         alb = NO_ALBUM if albums is None else albums[i]
         if alb != NO_ALBUM:
             nalb = max(nalb, alb + 1)
-        arr[i] = LgbTrack(pcm.ctypes.data, pcm.shape[0], pcm.shape[1], rate, fmt, alb, None)
+        arr[i] = LgbTrack(pcm.ctypes.data, pcm.shape[0], pcm.shape[1], rate, fmt, alb, None,
+                          0 if lead_in is None else lead_in[i])
     tb, ts = C.c_uint64(), C.c_uint64()
     lib.emu_plan_sizes(arr, C.c_size_t(n), C.c_uint64(target_tasks), C.byref(tb), C.byref(ts))
     tres = (LgbResult * n)()
@@ -69,12 +70,15 @@ def emu_measure(tracks, albums=None, target_tasks=0):
     sp = np.zeros(npk); tp = np.zeros(npk); tps = np.zeros(npk)
     blocks = np.zeros(max(tb.value, 1)); st = np.zeros(max(ts.value, 1))
     clen = np.zeros(n, dtype=np.int32)
+    nslots = [t[0].shape[0] // ((t[1] + 5) // 10) for t in tracks]
+    slots = np.zeros(max(sum(nslots), 1))
     dp = lambda a: a.ctypes.data_as(C.c_void_p)
     rc = lib.emu_measure(arr, C.c_size_t(n), C.c_uint32(nalb), C.c_uint64(target_tasks), tres, ares,
-                         dp(sp), dp(tp), dp(blocks), dp(st), dp(clen), dp(tps))
+                         dp(sp), dp(tp), dp(blocks), dp(st), dp(clen), dp(tps), dp(slots))
     assert rc == 0
     out = {"tracks": [], "albums": [], "blocks": blocks[:tb.value], "st": st[:ts.value],
-           "chunk_len": clen}
+           "chunk_len": clen,
+           "slots": np.split(slots[:sum(nslots)], np.cumsum(nslots)[:-1]) if n else []}
     off = 0
     for i, (pcm, _) in enumerate(tracks):
         ch = pcm.shape[1]
@@ -127,3 +131,29 @@ def rel_diff(a, b):
     d = np.abs(a - b)
     m = np.maximum(np.abs(b), 1e-300)
     return float(np.max(np.where(d == 0, 0.0, d / m))) if a.size else 0.0
+
+
+def gate_slots(slots, rate):
+    """Integrated loudness and range of one stream from its 100 ms slot
+    energies (numpy restatement of lgb_slots_query / SURVEY.md A.2, A.6, A.7)."""
+    s100 = (rate + 5) // 10
+    slots = np.asarray(slots, dtype=np.float64)
+    n = len(slots)
+    z = np.array([slots[b:b + 4].sum() for b in range(max(n - 3, 0))]) / (4.0 * s100)
+    st = np.array([slots[10 * j:10 * j + 30].sum() for j in range((n - 30) // 10 + 1 if n >= 30 else 0)])
+    st = st / (30.0 * s100)
+    gate = 10 ** ((-70 + 0.691) / 10)
+    z = z[z >= gate]
+    loud = -np.inf
+    if len(z):
+        z = z[z >= 0.1 * z.mean()]
+        loud = 10 * np.log10(z.mean()) - 0.691
+    st = np.sort(st[st >= gate])
+    rng = 0.0
+    if len(st):
+        st = st[st >= 0.01 * st.mean()]
+        if len(st):
+            hi = st[int((len(st) - 1) * 0.95 + 0.5)]
+            lo = st[int((len(st) - 1) * 0.1 + 0.5)]
+            rng = 10 * np.log10(hi / lo)
+    return loud, rng

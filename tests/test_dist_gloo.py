@@ -75,3 +75,48 @@ def test_empty_rank_contributes_nothing():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), per_rank, out), nprocs=2, join=True)
     assert out[0] == out[1] == _gated(per_rank[0])
+
+
+def _segment_worker(rank, world, port, slots, rate, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from loudgain_b200.engine import gather_block_lists
+        from tests.helpers import gate_slots
+        lists = gather_block_lists(dist, torch.from_numpy(slots[rank]), world)
+        peaks = torch.tensor([float(rank + 1)], dtype=torch.float64)
+        dist.all_reduce(peaks, op=dist.ReduceOp.MAX)
+        out[rank] = gate_slots(np.concatenate([x.numpy() for x in lists]), rate) + (float(peaks[0]),)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_time_sharded_stream_across_two_ranks(oracle):
+    """BASELINE config 4 in small: one stream, two ranks, each sweeping its time
+    segment (one second of lead-in instead of a filter-state exchange, host
+    emulation of the device math), the 100 ms slot energies all-gathered in rank
+    = time order, blocks and gates formed over the whole list on every rank."""
+    from loudgain_b200 import synth
+    from loudgain_b200.engine import segment_plan
+    from tests.helpers import emu_measure, oracle_measure
+    rate = 48000
+    spec = synth.config1_spec(31.7)
+    spec.rate = rate
+    pcm = synth.programme_s16(spec).numpy()
+    want = oracle_measure(oracle, [(pcm, rate)])["tracks"][0]
+    s100 = (rate + 5) // 10
+    plan = segment_plan(len(pcm), rate, 2)
+    per_rank = []
+    for a, lead, e in plan:
+        r = emu_measure([(pcm[a:e], rate)], lead_in=[lead])
+        per_rank.append(np.ascontiguousarray(r["slots"][0][lead // s100:]))
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_segment_worker, args=(2, _free_port(), per_rank, rate, out), nprocs=2, join=True)
+    for rank in range(2):
+        loud, rng, pk = out[rank]
+        assert abs(loud - want["loudness"]) < 2e-4 and abs(rng - want["range"]) < 2e-4
+        assert pk == 2.0
+    assert out[0] == out[1]

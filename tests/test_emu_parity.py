@@ -153,3 +153,33 @@ def test_true_peak_at_every_chunk_offset(oracle, rate):
         e = emu_measure([(pcm, rate)])["tracks"][0]
         assert o["true_peak"][0] > o["sample_peak"][0] * 1.05
         assert rel_diff(e["true_peak"], o["true_peak"]) <= TOL_TP_REL, off
+
+
+def test_time_segments_with_lead_in(oracle):
+    """cfg4's time sharding, on the host emulation: a stream cut into segments
+    that start one second early (lead-in instead of a filter-state exchange);
+    the concatenated slot energies give the whole stream's loudness and range,
+    and the maxima of the segments' peaks the whole stream's peaks."""
+    from loudgain_b200.engine import segment_plan
+    from tests.helpers import gate_slots
+    rate = 48000
+    spec = synth.config1_spec(47.3)
+    spec.rate = rate
+    pcm = synth.programme_s16(spec).numpy()
+    o = oracle_measure(oracle, [(pcm, rate)])["tracks"][0]
+    s100 = (rate + 5) // 10
+    for parts in (2, 3):
+        plan = segment_plan(len(pcm), rate, parts)
+        assert plan[0][:2] == (0, 0) and plan[-1][2] == len(pcm)
+        segs = [(pcm[a:e], rate) for a, _, e in plan]
+        e = emu_measure(segs, lead_in=[l for _, l, _ in plan])
+        slots = np.concatenate([s[l // s100:] for s, (_, l, _) in zip(e["slots"], plan)])
+        assert len(slots) == len(pcm) // s100
+        loud, rng = gate_slots(slots, rate)
+        assert lu_diff(loud, o["loudness"]) <= GOAL_LU and lu_diff(rng, o["range"]) <= GOAL_LU
+        sp = np.max([t["sample_peak"] for t in e["tracks"]], axis=0)
+        tp = np.max([t["true_peak"] for t in e["tracks"]], axis=0)
+        tps = np.max([t["true_peak_screened"] for t in e["tracks"]], axis=0)
+        np.testing.assert_array_equal(sp, o["sample_peak"])
+        assert rel_diff(tp, o["true_peak"]) <= TOL_TP_REL
+        np.testing.assert_array_equal(tps, tp)

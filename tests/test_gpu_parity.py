@@ -153,6 +153,30 @@ def test_chunking_invariance(product):
         assert got == ref
 
 
+def test_config4_time_segments(product, oracle):
+    """cfg4 shape, scaled: one long stereo 48 kHz stream measured as time
+    segments with one second of lead-in each (the per-rank work of the
+    time-sharded scan, here all on one GPU), merged through lgb_slots_query."""
+    import torch
+    from loudgain_b200 import engine
+    spec = synth.config1_spec(64.2)
+    spec.rate = 48000
+    pcm = synth.programme_s16(spec).numpy()
+    o = oracle_measure(oracle, [(pcm, 48000)])["tracks"][0]
+    whole, _ = engine.measure([(torch.from_numpy(pcm).cuda(), 48000)])
+    for parts in (1, 2, 5):
+        plan = engine.segment_plan(len(pcm), 48000, parts)
+        segs = [(torch.from_numpy(pcm[a:e]).cuda(), lead) for a, lead, e in plan]
+        m = engine.measure_stream_segments(segs, 48000)
+        _check(o, {"loudness": m.loudness, "range": m.range, "sample_peak": m.sample_peak,
+                   "true_peak": m.true_peak})
+        # against the unsegmented device measurement: same blocks up to the
+        # FP64 rounding of the state carry, identical peaks
+        assert abs(m.loudness - whole[0].loudness) < 1e-9 and abs(m.range - whole[0].range) < 1e-9
+        np.testing.assert_array_equal(m.true_peak, whole[0].true_peak)
+        assert m.n_abs == whole[0].n_abs and m.n_shortterm == whole[0].n_shortterm
+
+
 def test_threaded_scanners_match_single_thread(product):
     """Different threads feed different states at the same time (states are
     independent, as in libebur128): the results do not depend on it, also with
