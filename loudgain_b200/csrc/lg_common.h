@@ -49,7 +49,11 @@ constexpr int kRing = LG_RING;      // staging ring depth (stages in flight + 1)
 #endif
 constexpr int kPairPPS = LG_PAIR_PPS;
 constexpr int kPairRing = LG_PAIR_RING;
-constexpr int kPairStageFrames = kPairFrames * kPairPPS;
+// Float frames are twice as large: half the pairs per stage keeps the stage (and
+// with it the resident warps per SM) the same as for 16-bit input.
+LG_BOTH constexpr int pair_pps(uint32_t format) {
+  return format == FMT_S16 ? kPairPPS : (kPairPPS > 1 ? kPairPPS / 2 : 1);
+}
 // Longest per-phase tap count (49-tap prototype / factor 2, zero taps dropped).
 constexpr int kMaxTaps = 24;
 // A lane starts on a 16-byte boundary of the track, i.e. on a multiple of

@@ -219,6 +219,7 @@ template <int LAYOUT, bool TP>
 __global__ void __launch_bounds__(kPairThreads, kPairMinBlocks)
 sweep_pair_kernel(const __grid_constant__ SweepParams P) {
   constexpr int FMT = pair_format<LAYOUT>();
+  constexpr int kPPS = pair_pps((uint32_t) FMT);
   constexpr bool STEREO = LAYOUT == PAIR_S16_STEREO || LAYOUT == PAIR_F32_STEREO;
   extern __shared__ __align__(16) unsigned char smem_all[];
   const uint32_t wic = threadIdx.x >> 5;
@@ -253,7 +254,7 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
   const uint32_t my_row = pin((uint32_t) __cvta_generic_to_shared(sm) + slot * P.row_stride);
 
   // ---- staging.  Per stage every row receives one contiguous piece of
-  // kPairStageFrames frames, moved with 16-byte cp.async copies.
+  // kPPS * 24 frames, moved with 16-byte cp.async copies.
   //
   // Stereo, interior warps (every byte they stage lies inside the track): kLPR
   // adjacent lanes copy kLPR adjacent units of ONE row per instruction, so an
@@ -263,7 +264,7 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
   //
   // Other layouts, and warps at a track boundary (zero-filling form): the lpc
   // lanes of a row copy its units interleaved.
-  constexpr uint32_t kUnits = STEREO ? (uint32_t) (kPairStageFrames * (FMT == FMT_S16 ? 4 : 8) / 16) : 0u;
+  constexpr uint32_t kUnits = STEREO ? (uint32_t) (kPPS * kPairFrames * (FMT == FMT_S16 ? 4 : 8) / 16) : 0u;
   constexpr uint32_t kLPR = STEREO ? (kUnits % 4u == 0u ? 4u : 2u) : 1u;
   constexpr uint32_t kRowsPerCopy = 32u / kLPR;
   constexpr uint32_t kRowStride = ((kUnits | 1u) << 4);
@@ -321,7 +322,7 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
 
   const uint32_t niters = (uint32_t) P.niters;
   const uint32_t npairs = P.npairs;
-  const uint32_t nstages = (npairs + kPairPPS - 1) / kPairPPS;
+  const uint32_t nstages = (npairs + kPPS - 1) / kPPS;
   // Pairs whose two iterations are both "fast" for every lane of the warp.
   const int lfast = ww.lmin_valid < L ? ww.lmin_valid : L;
   const uint32_t fast_lo = (uint32_t) ((W + P.aq - 1 + kPairFrames - 1) / kPairFrames);
@@ -348,7 +349,7 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
     cs_off += P.stage_bytes;
     if (cs_off == P.ring_bytes) cs_off = 0;
 #pragma unroll 1
-    for (uint32_t pr = 0; pr < (uint32_t) kPairPPS; ++pr, ++pair) {
+    for (uint32_t pr = 0; pr < (uint32_t) kPPS; ++pr, ++pair) {
       if (pair >= npairs) break;
       const uint32_t buf = sbuf + pr * kPairFrames * fb;
       PairPeak<FMT> pk;

@@ -185,7 +185,7 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, const Plan
     sp.packed = packed ? 1u : 0u;
     sp.lpc = packed ? t0.channels / 2u : (t0.channels < 32u ? t0.channels : 32u);
     sp.cpw = 32u / sp.lpc;
-    const uint32_t pps = packed ? (uint32_t) kPairPPS : (uint32_t) kPairsPerStage;
+    const uint32_t pps = packed ? (uint32_t) pair_pps(t0.format) : (uint32_t) kPairsPerStage;
     const uint32_t ring = packed ? (uint32_t) kPairRing : (uint32_t) kRing;
     sp.stage_row_bytes = pps * kPairFrames * t0.fb;
     sp.units = sp.stage_row_bytes >> 4;

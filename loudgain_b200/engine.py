@@ -394,43 +394,99 @@ def slots_query(slots: "torch.Tensor", rate: int, stream=None) -> Measurement:
                        r.n_rel, r.n_shortterm)
 
 
+class StreamShard:
+    """This rank's part of ONE stream that is sharded by time over `world`
+    ranks (BASELINE config 4).
+
+    `segments`: the rank's segments in time order, [(cuda tensor [frames,
+    channels] holding lead-in + segment, lead_in_frames)], cut by segment_plan;
+    rank r holds the segments that precede rank r+1's.  Planned once; every
+    run() sweeps the local segments in one batch, packs their 100 ms slot
+    energies (lead-in slots dropped), all-gathers them over NCCL/NVLink into a
+    pre-allocated buffer in rank = time order, and fetch() forms blocks, gates
+    and the range over the whole slot list (lgb_slots_query) and reduces the
+    per-channel peaks with a MAX all-reduce.  The result is the same on every
+    rank and equals the single-device measurement of the whole stream.
+    """
+
+    def __init__(self, segments, rate: int, dist=None, world: int = 1, group=None, stream=None):
+        import torch
+
+        self.rate, self.dist, self.world, self.group = int(rate), dist, world, group
+        self.s100 = (self.rate + 5) // 10
+        self.segments = list(segments)
+        self.batch = Batch([(p, rate) for p, _ in self.segments], None, stream,
+                           lead_in=[l for _, l in self.segments])
+        self.stream = self.batch.stream
+        self.dev = self.segments[0][0].device if self.segments else torch.device("cuda")
+        self.nch = self.segments[0][0].shape[1] if self.segments else 0
+        self.views = None
+        nloc = sum((p.shape[0] - lead) // self.s100 for p, lead in self.segments)
+        mine = torch.tensor([nloc], dtype=torch.int64, device=self.dev)
+        sizes = [torch.zeros_like(mine) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(sizes, mine, group=group)
+            self.sizes = [int(x.item()) for x in sizes]
+        else:
+            self.sizes = [nloc]
+        self.width = max(max(self.sizes), 1)
+        self.send = torch.zeros(self.width, dtype=torch.float64, device=self.dev)
+        self.recv = torch.zeros(world * self.width, dtype=torch.float64, device=self.dev)
+        self.union = torch.zeros(max(sum(self.sizes), 1), dtype=torch.float64, device=self.dev)
+        self.peaks = torch.zeros(2, max(self.nch, 1), dtype=torch.float64, device=self.dev)
+
+    def run(self) -> None:
+        import torch
+
+        self.batch.run()
+        if self.views is None:                   # device views of the slot lists, lead-in dropped
+            self.views = [device_blocks(self.batch, i, 2)[lead // self.s100:]
+                          for i, (_, lead) in enumerate(self.segments)]
+        with torch.cuda.stream(self.stream):
+            off = 0
+            for v in self.views:
+                self.send[off:off + v.numel()].copy_(v, non_blocking=True)
+                off += v.numel()
+            if self.world > 1:
+                self.dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+                off = 0
+                for r, n in enumerate(self.sizes):
+                    self.union[off:off + n].copy_(self.recv[r * self.width:r * self.width + n],
+                                                  non_blocking=True)
+                    off += n
+            else:
+                self.union[:self.sizes[0]].copy_(self.send[:self.sizes[0]], non_blocking=True)
+
+    def fetch(self) -> Measurement:
+        import torch
+
+        tres, _ = self.batch.fetch()
+        nch = self.nch
+        sp = np.max([m.sample_peak for m in tres], axis=0) if tres else np.zeros(nch)
+        tp = np.max([m.true_peak for m in tres], axis=0) if tres else np.zeros(nch)
+        with torch.cuda.stream(self.stream):
+            self.peaks[:, :nch] = torch.as_tensor(np.stack([sp, tp]), device=self.dev)
+            if self.world > 1:
+                self.dist.all_reduce(self.peaks, op=self.dist.ReduceOp.MAX, group=self.group)
+            out = slots_query(self.union[:sum(self.sizes)], self.rate, self.stream)
+            pk = self.peaks.cpu().numpy()
+        out.sample_peak, out.true_peak = pk[0, :nch].copy(), pk[1, :nch].copy()
+        return out
+
+    def close(self) -> None:
+        self.views = None
+        self.batch.close()
+
+
 def measure_stream_segments(segments, rate: int, dist=None, world: int = 1, group=None,
                             stream=None) -> Measurement:
-    """Measures ONE stream whose time segments are spread over ranks.
-
-    `segments`: this rank's segments in time order, [(cuda tensor [frames,
-    channels] holding lead-in + segment, lead_in_frames)], cut by segment_plan;
-    rank r holds the segments that precede rank r+1's.  Every rank sweeps its
-    segments in one batch, drops the lead-in slots, all-gathers the 100 ms slot
-    energies (a few MB for ten hours) and the per-channel peaks over
-    NCCL/NVLink, and forms blocks, gates and the range over the whole slot list
-    (lgb_slots_query).  The result is the same on every rank and equals the
-    single-device measurement of the whole stream."""
-    import torch
-
-    s100 = (int(rate) + 5) // 10
-    b = Batch([(p, rate) for p, _ in segments], None, stream, lead_in=[l for _, l in segments])
+    """One-shot form of StreamShard."""
+    s = StreamShard(segments, rate, dist, world, group, stream)
     try:
-        b.run()
-        tres, _ = b.fetch()
-        parts = [device_blocks(b, i, 2)[lead // s100:] for i, (_, lead) in enumerate(segments)]
-        dev = segments[0][0].device if segments else torch.device("cuda")
-        local = torch.cat(parts) if parts else torch.zeros(0, dtype=torch.float64, device=dev)
-        nch = segments[0][0].shape[1] if segments else 0
-        peaks = torch.zeros(2, max(nch, 1), dtype=torch.float64, device=dev)
-        for m in tres:
-            peaks[0, :nch] = torch.maximum(peaks[0, :nch], torch.as_tensor(m.sample_peak, device=dev))
-            peaks[1, :nch] = torch.maximum(peaks[1, :nch], torch.as_tensor(m.true_peak, device=dev))
-        if world > 1:
-            lists = gather_block_lists(dist, local, world, group)
-            local = torch.cat(lists)
-            dist.all_reduce(peaks, op=dist.ReduceOp.MAX, group=group)
-        out = slots_query(local, rate, stream)
-        out.sample_peak = peaks[0, :nch].cpu().numpy()
-        out.true_peak = peaks[1, :nch].cpu().numpy()
-        return out
+        s.run()
+        return s.fetch()
     finally:
-        b.close()
+        s.close()
 
 
 # ------------------------------------------------------------- scan.c driver

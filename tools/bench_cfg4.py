@@ -7,7 +7,7 @@ The stream is the concatenation of 60 s programme pieces (piece i has seed
 segment plus one second of lead-in (loudgain_b200.engine.segment_plan) -- on
 its own GPU.  A step = sweep of the rank's segment, all-gather of the 100 ms
 slot energies and peaks over NCCL, blocks + gating + range over the whole slot
-list on every rank (engine.measure_stream_segments).  With --check the result
+list on every rank (engine.StreamShard).  With --check the result
 is compared with rank 0 measuring the whole stream alone (use a --seconds that
 fits one GPU).  Prints one JSON line on rank 0."""
 import argparse
@@ -58,8 +58,11 @@ def main():
     first, lead, end = engine.segment_plan(total, RATE, world)[rank]
     seg = [(stream_part(first, end, total, dev), lead)]
 
+    shard = engine.StreamShard(seg, RATE, dist if world > 1 else None, world)
+
     def step():
-        return engine.measure_stream_segments(seg, RATE, dist if world > 1 else None, world)
+        shard.run()
+        return shard.fetch()
 
     for _ in range(args.warmup):
         m = step()
@@ -91,6 +94,7 @@ def main():
         # so the FP32 filter rounds differently: equal to ~1e-5 LU, not bit for bit
         assert line["check"]["loudness_diff"] < 1e-4 and line["check"]["range_diff"] < 1e-4
         assert line["check"]["true_peak_equal"] and line["check"]["sample_peak_equal"]
+    shard.close()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
