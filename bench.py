@@ -351,7 +351,7 @@ def gpu_arm(args):
                          "frac": achieved / hbm if achieved else None, "traffic": _ncu_traffic(),
                          "traffic_source": "dram__bytes_read+write per launch, ncu --set full, "
                                            "profiles/r01_sweep_ncu_summary.json",
-                         "kernel": "sweep_kernel<S16,4x>", "kernel_ms": sweep_ms,
+                         "kernel": "sweep_pair_kernel<S16 stereo, 4x true-peak codes>", "kernel_ms": sweep_ms,
                          "peak_source": src,
                          "algorithmic_bytes": "2 B per S16 sample, read once (SURVEY 8d)"},
             "cpu_baseline": cpu,

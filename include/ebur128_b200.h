@@ -84,6 +84,12 @@ uint32_t lgb_batch_sweep_launches(const lgb_batch* b);  /* of which sweep kernel
  * pointer (doubles). */
 uint64_t lgb_batch_blocks(const lgb_batch* b, size_t track, int kind, const double** dev_ptr);
 
+/* Makes `cuda_stream` wait until the block lists (and slot energies) of the most
+ * recently enqueued run are complete -- earlier than the end of the run, which
+ * still has its true-peak pass and queries in flight.  For consumers of
+ * lgb_batch_blocks on another stream (the multi-GPU album merge).  0 on success. */
+int lgb_batch_wait_blocks(lgb_batch* b, void* cuda_stream);
+
 /* Kernel timing for benchmarks: when enabled, every run brackets its sweep
  * launches with CUDA events on the batch's stream; fetch accumulates them.
  * lgb_batch_sweep_ms returns the mean sweep time per run in milliseconds over

@@ -106,6 +106,7 @@ struct lgb_batch {
   // to the true-peak pass on the main stream; joined before the result copy.
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_blocks = nullptr;   // block lists of the current run are complete (lgb_batch_wait_blocks)
   double abs_gate = 0.0;
   uint32_t launches = 0, sweep_launches = 0, sms = 148;
   // optional sweep timing
@@ -199,7 +200,8 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithPriority(&b->side, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_blocks, cudaEventDisableTiming) != cudaSuccess) {
       cudaGetLastError();
       if (b->side) { cudaStreamDestroy(b->side); b->side = nullptr; }
     }
@@ -257,6 +259,16 @@ static int enqueue_step(lgb_batch* b) {
   PostSizes z{(uint32_t) p.tracks.size(), p.total_recs, p.total_slots, p.total_blocks, p.total_st};
   e = launch_post(t, z, ps);
   if (e != cudaSuccess) { set_error("launch_post", e); return 1; }
+  if (b->ev_blocks) {
+    // while the step is being captured into its graph the record must be an
+    // external event node, so that streams outside the graph can wait for it
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(ps, &cap);
+    e = cap == cudaStreamCaptureStatusActive
+            ? cudaEventRecordWithFlags(b->ev_blocks, ps, cudaEventRecordExternal)
+            : cudaEventRecord(b->ev_blocks, ps);
+    if (e != cudaSuccess) { set_error("cudaEventRecord(blocks)", e); return 1; }
+  }
   e = launch_queries(t.lists, t.queries, t.members, (uint32_t) p.queries.size(), b->abs_gate,
                      t.results, ps);
   if (e != cudaSuccess) { set_error("launch_queries", e); return 1; }
@@ -332,6 +344,20 @@ extern "C" LG_EXPORT int lgb_batch_fetch(lgb_batch* b, lgb_result* track_results
       }
     }
   }
+  return 0;
+}
+
+extern "C" LG_EXPORT int lgb_batch_wait_blocks(lgb_batch* b, void* cuda_stream) {
+  if (!b->ev_blocks || !b->side) {           // no fork: order after everything enqueued so far
+    cudaEvent_t ev;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return 1;
+    cudaEventRecord(ev, b->stream);
+    const cudaError_t e = cudaStreamWaitEvent((cudaStream_t) cuda_stream, ev, 0);
+    cudaEventDestroy(ev);
+    return e == cudaSuccess ? 0 : 1;
+  }
+  const cudaError_t e = cudaStreamWaitEvent((cudaStream_t) cuda_stream, b->ev_blocks, 0);
+  if (e != cudaSuccess) { set_error("lgb_batch_wait_blocks", e); return 1; }
   return 0;
 }
 
@@ -478,6 +504,7 @@ extern "C" LG_EXPORT void lgb_batch_destroy(lgb_batch* b) {
   if (b->graph) cudaGraphExecDestroy(b->graph);
   if (b->ev_fork) cudaEventDestroy(b->ev_fork);
   if (b->ev_join) cudaEventDestroy(b->ev_join);
+  if (b->ev_blocks) cudaEventDestroy(b->ev_blocks);
   if (b->side) cudaStreamDestroy(b->side);
   if (b->h_results) cudaFreeHost(b->h_results);
   if (b->h_peaks) cudaFreeHost(b->h_peaks);

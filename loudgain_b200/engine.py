@@ -268,6 +268,9 @@ class AlbumMerge:
 
         self.batch, self.dist, self.world, self.group = batch, dist, world, group
         self.tracks = list(tracks)
+        # The merge runs on its own stream: it only waits for the batch's block
+        # lists (lgb_batch_wait_blocks), not for its true-peak pass and queries.
+        self.mstream = torch.cuda.Stream(device=torch.cuda.current_device())
         batch.stream.synchronize()
         self.z_views = [device_blocks(batch, t, 0) for t in self.tracks]
         self.st_views = [device_blocks(batch, t, 1) for t in self.tracks]
@@ -312,16 +315,20 @@ class AlbumMerge:
         zn = (C.c_uint32 * world)(*[a for a, _ in self.sizes])
         sn = (C.c_uint32 * world)(*[b for _, b in self.sizes])
         self._L = L
+        L.lgb_batch_wait_blocks.argtypes = [C.c_void_p, C.c_void_p]
         self._h = L.lgb_listquery_create(zp, zn, sp, sn, world,
-                                         C.c_void_p(batch.stream.cuda_stream))
+                                         C.c_void_p(self.mstream.cuda_stream))
         if not self._h:
             raise RuntimeError("lgb_listquery_create failed: " + _err(L))
 
     def run(self) -> None:
-        """Enqueue pack + all-gather + union query on the batch's stream."""
+        """Enqueue pack + all-gather + union query behind the batch's block
+        kernels (call after batch.run(); fetch() before the next batch.run())."""
         import torch
 
-        with torch.cuda.stream(self.batch.stream):
+        if self._L.lgb_batch_wait_blocks(self.batch._h, C.c_void_p(self.mstream.cuda_stream)):
+            raise RuntimeError("lgb_batch_wait_blocks failed: " + _err(self._L))
+        with torch.cuda.stream(self.mstream):
             for v, off in self._run_views:
                 self.send[off:off + v.numel()].copy_(v, non_blocking=True)
             self.dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
