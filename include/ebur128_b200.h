@@ -162,6 +162,31 @@ int lgb_scan_host(const lgb_host_track* tracks, size_t ntracks, size_t chunk_fra
 int lgb_scan_host_mt(const lgb_host_track* tracks, size_t ntracks, size_t chunk_frames,
                      int do_album, double pre_gain, unsigned nthreads, lgb_scan_result* out);
 
+/* ---- what loudgain does with a scan result --------------
+ * Clipping prevention of loudgain.c:323-379 (-k / -K n): the peak a track /
+ * album would have after its gain is compared with the limit
+ * `max_true_peak_db` (dBTP; loudgain's default for -k is -1.0); with `prevent`
+ * the gains in `r` are lowered so that the new peak just meets the limit.
+ * Host arithmetic only (no GPU involved).  0 on success. */
+typedef struct {
+  int will_clip;               /* a peak is above the limit and was not corrected */
+  int track_clipped;           /* track gain was lowered (loudgain's tclip) */
+  int album_clipped;           /* album gain was lowered (aclip) */
+  int album_would_clip;        /* album peak above the limit, not corrected (the album row's flag) */
+  double track_new_peak;       /* linear peak after the (corrected) track gain */
+  double album_new_peak;
+} lgb_clip_info;
+
+int lgb_clip_prevention(lgb_scan_result* r, int do_album, int prevent, double max_true_peak_db,
+                        lgb_clip_info* info);
+
+/* One row of loudgain's tab-separated `-O` output (loudgain.c:586-612) for a
+ * track (album_row = 0) or for the album (album_row = 1, name "Album"); `unit`
+ * is "dB" or "LU".  Returns the length written (without the terminating NUL),
+ * or the length needed if `cap` is too small. */
+size_t lgb_format_tab_row(const char* name, const lgb_scan_result* r, const lgb_clip_info* info,
+                          int album_row, const char* unit, char* buf, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

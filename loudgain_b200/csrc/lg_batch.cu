@@ -87,6 +87,7 @@ struct lgb_batch {
   ChunkRec* d_recs = nullptr;
   uint32_t* d_peaks = nullptr;
   uint32_t* d_mrec = nullptr;
+  uint64_t* d_tpq = nullptr;           // candidate queue of the packed true-peak pass
   double* d_echunk = nullptr;
   double* d_eslot = nullptr;
   double* d_zblock = nullptr;
@@ -167,6 +168,7 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
             dalloc(&b->d_recs, p.total_recs, b->stream) &&
             dalloc(&b->d_peaks, 2 * p.total_peaks + p.groups.size() + 1, b->stream) &&
             dalloc(&b->d_mrec, p.total_mrec, b->stream) &&
+            dalloc(&b->d_tpq, 2 * p.total_mrec, b->stream) &&
             dalloc(&b->d_echunk, p.total_recs, b->stream) &&
             dalloc(&b->d_eslot, p.total_slots, b->stream) &&
             dalloc(&b->d_zblock, p.total_blocks, b->stream) &&
@@ -210,7 +212,7 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
   b->sms = (uint32_t) sms;
   b->sweep_launches = (uint32_t) p.groups.size();
   uint32_t tp_launches = 0;
-  for (const SweepGroup& g : p.groups) tp_launches += g.tpf ? 1u : 0u;
+  for (const SweepGroup& g : p.groups) tp_launches += g.tpf ? (g.params.packed ? 2u : 1u) : 0u;
   b->launches = b->sweep_launches + tp_launches + (p.total_recs ? 1 : 0) + (p.total_slots ? 1 : 0) +
                 ((p.total_blocks + p.total_st) ? 1 : 0) + (p.queries.empty() ? 0 : 1);
   return b;
@@ -251,6 +253,7 @@ static int enqueue_step(lgb_batch* b) {
     sp.tracks = t.tracks; sp.work = t.work + g.first_warp; sp.recs = t.recs; sp.peaks = t.peaks;
     sp.mrec = b->d_mrec + g.mrec_base;
     sp.tp_ticket = b->d_peaks + 2 * p.total_peaks + gi++;
+    sp.tp_queue = b->d_tpq + 2 * g.mrec_base;
     e = sp.packed ? launch_truepeak_pair(sp, g.format, g.tpf, b->sms, b->stream)
                   : launch_truepeak(sp, g.format, g.tpf, b->sms, b->stream);
     if (e != cudaSuccess) { set_error("launch_truepeak", e); return 1; }
@@ -497,7 +500,7 @@ extern "C" LG_EXPORT void lgb_batch_destroy(lgb_batch* b) {
   if (!b) return;
   if (b->ev0) { cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); cudaEventDestroy(b->ev2); }
   void* const mem[] = {b->d_tracks, b->d_coefs, b->d_work, b->d_queries, b->d_members, b->d_lists,
-                       b->d_recs, b->d_peaks, b->d_mrec, b->d_echunk, b->d_eslot, b->d_zblock, b->d_zst,
+                       b->d_recs, b->d_peaks, b->d_mrec, b->d_tpq, b->d_echunk, b->d_eslot, b->d_zblock, b->d_zst,
                        b->d_results};
   if (b->h_results) cudaStreamSynchronize(b->stream);   // a run may still be writing the mirrors
   for (void* m : mem) if (m) cudaFreeAsync(m, b->stream);

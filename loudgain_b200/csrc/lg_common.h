@@ -196,7 +196,9 @@ struct SweepParams {
   // packed, the pair's maximum for each of the lane's two channels
   // (lg_sweep.cuh: pair_code).  Unused when the rate has no interpolator.
   uint32_t* mrec;
-  uint32_t* tp_ticket;     // work-item counter of the group's true-peak pass (zeroed per run)
+  uint32_t* tp_ticket;     // counter of the group's true-peak pass (zeroed per run): work
+                           // items drawn (scalar pass) / candidates queued (packed pass)
+  uint64_t* tp_queue;        // packed pass: candidate queue, 2 entries per mrec word at most
 };
 
 // ---- lane geometry ---------------------------------------------------------

@@ -478,9 +478,6 @@ cudaError_t launch_sweep_pair(const SweepParams& p, uint32_t format, int tpf, cu
 // every frame.
 
 constexpr int kTp2Threads = 128;
-constexpr int kTp2Warps = kTp2Threads / 32;
-constexpr int kTp2Cap = 32 + 64;            // remainder + both channels of one pair per lane
-constexpr int kTp2ItemsPerWarp = 2;
 
 template <int FMT>
 __device__ __forceinline__ float pcm_at(const unsigned char* p) {
@@ -547,105 +544,145 @@ __device__ __forceinline__ void tp_pair_evaluate(const SweepParams& P, const uin
   if (__float_as_uint(m) > __ldcg(cell)) atomicMax(cell, __float_as_uint(m));
 }
 
-// Warps draw work items from a ticket counter (candidates cluster in the loud
-// passages, a static split leaves SMs idle) and leave after kTp2ItemsPerWarp
-// of them: CTAs turn over, so the post-processing kernels of the forked step
-// (lg_batch.cu) find room on the SMs while this pass runs.
-template <int FMT, int TPF>
-__global__ void __launch_bounds__(kTp2Threads, 4)
-truepeak_pair_kernel(const __grid_constant__ SweepParams P, const uint32_t seg_pairs) {
-  __shared__ uint4 queue_all[kTp2Warps][kTp2Cap];
+// The pass runs as two kernels.  tp_scan_pair_kernel streams over the pair
+// maxima (one warp per run of pairs of one sweep warp, scanning lane = sweep
+// lane) and appends the pairs that can still matter to a global queue as
+// (sweep warp, lane, channel, pair); tp_eval_pair_kernel evaluates the queue,
+// one candidate per thread, grid-stride.  Candidates cluster in the loud
+// passages: evaluating them where they are found leaves most SMs idle while a
+// few warps work through dense runs; the queue spreads them evenly.
+constexpr int kTpScanThreads = 256;
+constexpr int kTpScanWarps = kTpScanThreads / 32;
+constexpr int kTpScanCap = 32 + 64;         // per-warp staging: remainder + one pair's hits
+
+__device__ __forceinline__ uint64_t tp_entry(uint32_t w, uint32_t lane, uint32_t ch1, uint32_t pair) {
+  return (uint64_t) w | ((uint64_t) (pair | (lane << 16) | (ch1 << 21)) << 32);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kTpScanThreads)
+tp_scan_pair_kernel(const __grid_constant__ SweepParams P, const uint32_t seg_pairs) {
+  __shared__ uint64_t stage_all[kTpScanWarps][kTpScanCap];
   const uint32_t npairs = P.npairs;
   const uint32_t lane = threadIdx.x & 31u, wic = threadIdx.x >> 5;
-  uint4* queue = queue_all[wic];
+  uint64_t* stage = stage_all[wic];
   const uint32_t nseg = (npairs + seg_pairs - 1) / seg_pairs;
-  const uint64_t nitems = (uint64_t) P.nwarps * nseg;
+  const uint64_t item = (uint64_t) blockIdx.x * kTpScanWarps + wic;
+  if (item >= (uint64_t) P.nwarps * nseg) return;
+  const uint32_t w = (uint32_t) (item / nseg);
+  const uint32_t p_begin = (uint32_t) (item - (uint64_t) w * nseg) * seg_pairs;
+  const uint32_t p_end = p_begin + seg_pairs < npairs ? p_begin + seg_pairs : npairs;
+  // the sweep lane's place in its track
+  const WarpWork ww = P.work[w];
+  const Track& tr = P.tracks[ww.track];
+  const uint32_t slot = lane / P.lpc;
+  const uint32_t ch = 2u * (lane - slot * P.lpc);
+  const uint32_t chunk = ww.first_chunk + slot;
+  const bool ok = slot < P.cpw && chunk < tr.nchunks;
+  const LaneGeom g = lane_geometry((long long) tr.frames, P.L, P.W, P.aq, chunk);
+  const int f_lo = P.W + g.o;
+  const long long left = (long long) tr.frames - g.a;
+  const int f_hi = f_lo + P.L;
+  const int f_end = left < (long long) f_hi ? (left < 0 ? 0 : (int) left) : f_hi;
+  const long long lead_in = (long long) tr.lead_in;
+
+  const uint32_t* codes = P.mrec + ((size_t) w * npairs) * 32u + lane;
+  const uint32_t* cell = P.peaks + 2 * ((ok ? tr.peak_base : 0) + (ok ? ch : 0));
+  // the channel's true peak is at least its sample peak (final by now)
+  const float floor0 = __uint_as_float(__ldcg(cell));
+  const float floor1 = __uint_as_float(__ldcg(cell + 2));
   uint32_t qn = 0;                       // warp-uniform
-
-  for (int round = 0; round < kTp2ItemsPerWarp; ++round) {
-    uint32_t ticket = 0;
-    if (lane == 0) ticket = atomicAdd(P.tp_ticket, 1u);
-    ticket = __shfl_sync(0xffffffffu, ticket, 0);
-    if (ticket >= nitems) break;
-    const uint32_t w = ticket / nseg;
-    const uint32_t p_begin = (ticket - w * nseg) * seg_pairs;
-    const uint32_t p_end = p_begin + seg_pairs < npairs ? p_begin + seg_pairs : npairs;
-    // the sweep lane's place in its track
-    const WarpWork ww = P.work[w];
-    const Track& tr = P.tracks[ww.track];
-    const uint32_t slot = lane / P.lpc;
-    const uint32_t ch = 2u * (lane - slot * P.lpc);
-    const uint32_t chunk = ww.first_chunk + slot;
-    const bool ok = slot < P.cpw && chunk < tr.nchunks;
-    const LaneGeom g = lane_geometry((long long) tr.frames, P.L, P.W, P.aq, chunk);
-    const int f_lo = P.W + g.o;
-    const long long left = (long long) tr.frames - g.a;
-    const int f_hi = f_lo + P.L;
-    const int f_end = left < (long long) f_hi ? (left < 0 ? 0 : (int) left) : f_hi;
-
-    const uint32_t* codes = P.mrec + ((size_t) w * npairs) * 32u + lane;
-    uint32_t* cell = P.peaks + 2 * ((ok ? tr.peak_base : 0) + (ok ? ch : 0));
-    const uint2 pk0 = __ldcg(reinterpret_cast<const uint2*>(cell));       // (sample, true) peak
-    const uint2 pk1 = __ldcg(reinterpret_cast<const uint2*>(cell + 2));
-    float floor0 = __uint_as_float(pk0.x > pk0.y ? pk0.x : pk0.y);
-    float floor1 = __uint_as_float(pk1.x > pk1.y ? pk1.x : pk1.y);
-    uint32_t prev = p_begin ? __ldcs(codes + (size_t) (p_begin - 1) * 32u) : 0u;
-    uint32_t nxt = __ldcs(codes + (size_t) p_begin * 32u);
-    for (uint32_t p = p_begin; p < p_end; ++p) {
-      const uint32_t code = nxt;
-      if (p + 1 < p_end) nxt = __ldcs(codes + (size_t) (p + 1) * 32u);
+  auto flush = [&](uint32_t n) {         // the n oldest staged entries go to the global queue
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(P.tp_ticket, n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    __syncwarp();
+    for (uint32_t i = lane; i < n; i += 32u) P.tp_queue[base + i] = stage[i];
+    __syncwarp();
+  };
+  uint32_t prev = p_begin ? __ldcs(codes + (size_t) (p_begin - 1) * 32u) : 0u;
+  constexpr int kAhead = 4;
+  uint32_t nxt[kAhead];
+#pragma unroll
+  for (int j = 0; j < kAhead; ++j)
+    nxt[j] = p_begin + j < p_end ? __ldcs(codes + (size_t) (p_begin + j) * 32u) : 0u;
+  for (uint32_t p0 = p_begin; p0 < p_end; p0 += kAhead) {
+    uint32_t cur[kAhead];
+#pragma unroll
+    for (int j = 0; j < kAhead; ++j) {
+      cur[j] = nxt[j];
+      const uint32_t pn = p0 + kAhead + j;
+      nxt[j] = pn < p_end ? __ldcs(codes + (size_t) pn * 32u) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < kAhead; ++j) {
+      const uint32_t p = p0 + j;
+      const uint32_t code = cur[j];
       const uint32_t cm = __vmaxu2(code, prev);      // per channel: this pair and its history
       prev = code;
       const int f0 = (int) (p * kPairFrames);
-      const bool own = ok && f0 + kPairFrames > f_lo && f0 < f_end &&
-                       g.a + f0 + kPairFrames > (long long) tr.lead_in;
+      const bool own = ok && p < p_end && f0 + kPairFrames > f_lo && f0 < f_end &&
+                       g.a + f0 + kPairFrames > lead_in;
       const bool hit0 = own && P.tp_bound * pair_code_value<FMT>(cm & 0xffffu) > floor0;
       const bool hit1 = own && P.tp_bound * pair_code_value<FMT>(cm >> 16) > floor1;
       const unsigned m0 = __ballot_sync(0xffffffffu, hit0);
       const unsigned m1 = __ballot_sync(0xffffffffu, hit1);
       if (m0 | m1) {
         const unsigned below = (1u << lane) - 1u;
-        const long long t0 = g.a + f0;
-        if (hit0)
-          queue[qn + __popc(m0 & below)] =
-              make_uint4(ww.track, ch, (uint32_t) (unsigned long long) t0, (uint32_t) ((unsigned long long) t0 >> 32));
+        if (hit0) stage[qn + __popc(m0 & below)] = tp_entry(w, lane, 0u, p);
         qn += __popc(m0);
-        if (hit1)
-          queue[qn + __popc(m1 & below)] =
-              make_uint4(ww.track, ch + 1, (uint32_t) (unsigned long long) t0, (uint32_t) ((unsigned long long) t0 >> 32));
+        if (hit1) stage[qn + __popc(m1 & below)] = tp_entry(w, lane, 1u, p);
         qn += __popc(m1);
         if (qn >= 32u) {
           __syncwarp();
-          while (qn >= 32u) {
-            qn -= 32u;
-            tp_pair_evaluate<FMT, TPF>(P, queue[qn + lane]);
-          }
-          __syncwarp();
-          floor0 = fmaxf(floor0, __uint_as_float(__ldcg(cell + 1)));
-          floor1 = fmaxf(floor1, __uint_as_float(__ldcg(cell + 3)));
+          flush(qn);
+          qn = 0;
         }
       }
     }
   }
   __syncwarp();
-  if (lane < qn) tp_pair_evaluate<FMT, TPF>(P, queue[lane]);
+  if (qn) flush(qn);
+}
+
+template <int FMT, int TPF>
+__global__ void __launch_bounds__(kTp2Threads, 4)
+tp_eval_pair_kernel(const __grid_constant__ SweepParams P) {
+  const uint32_t count = __ldcg(P.tp_ticket);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const uint64_t e = P.tp_queue[i];
+    const uint32_t hi = (uint32_t) (e >> 32);
+    const uint32_t pair = hi & 0xffffu, lane = (hi >> 16) & 31u, ch1 = hi >> 21;
+    const WarpWork ww = P.work[(uint32_t) e];
+    const Track& tr = P.tracks[ww.track];
+    const uint32_t slot = lane / P.lpc;
+    const uint32_t ch = 2u * (lane - slot * P.lpc) + ch1;
+    const LaneGeom g = lane_geometry((long long) tr.frames, P.L, P.W, P.aq, ww.first_chunk + slot);
+    const long long t0 = g.a + (long long) pair * kPairFrames;
+    tp_pair_evaluate<FMT, TPF>(P, make_uint4(ww.track, ch, (uint32_t) (unsigned long long) t0,
+                                             (uint32_t) ((unsigned long long) t0 >> 32)));
+  }
 }
 
 template <int FMT, int TPF>
 static cudaError_t launch_truepeak_pair_t(const SweepParams& p, uint32_t sms, cudaStream_t stream) {
+  if (p.npairs > 0xffffu) return cudaErrorInvalidValue;      // pair index is a 16-bit field
   static int per_sm = 0;
   if (!per_sm) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, truepeak_pair_kernel<FMT, TPF>,
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tp_eval_pair_kernel<FMT, TPF>,
                                                       kTp2Threads, 0) != cudaSuccess || per_sm < 1)
       per_sm = 4;
   }
-  // Items of 32 pairs (fewer for small batches, so that every SM gets several).
-  const uint64_t nscan = (uint64_t) sms * per_sm * kTp2Warps;
+  // scan: runs of 32 pairs per warp (fewer for small batches, so that every SM gets several)
+  const uint64_t nscan = (uint64_t) sms * 8 * kTpScanWarps;
   uint32_t seg = 32;
-  while (seg > 4 && (uint64_t) p.nwarps * ((p.npairs + seg - 1) / seg) < 4 * nscan) seg >>= 1;
+  while (seg > 4 && (uint64_t) p.nwarps * ((p.npairs + seg - 1) / seg) < nscan) seg >>= 1;
   const uint64_t nitems = (uint64_t) p.nwarps * ((p.npairs + seg - 1) / seg);
-  const uint64_t ctas = (nitems + kTp2Warps * kTp2ItemsPerWarp - 1) / (kTp2Warps * kTp2ItemsPerWarp);
-  truepeak_pair_kernel<FMT, TPF><<<(unsigned) ctas, kTp2Threads, 0, stream>>>(p, seg);
+  const uint64_t ctas = (nitems + kTpScanWarps - 1) / kTpScanWarps;
+  tp_scan_pair_kernel<FMT><<<(unsigned) ctas, kTpScanThreads, 0, stream>>>(p, seg);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  tp_eval_pair_kernel<FMT, TPF><<<sms * per_sm, kTp2Threads, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -7,7 +7,11 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <atomic>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -67,6 +71,11 @@ extern "C" LG_EXPORT int lgb_scan_host_mt(const lgb_host_track* tracks, size_t n
                                           unsigned nthreads, lgb_scan_result* out) {
   std::vector<ebur128_state*> states(ntracks, nullptr);
   int rc = 0;
+  const bool trace = getenv("LOUDGAIN_B200_TRACE") != nullptr;     // phase times on stderr
+  const auto t_start = std::chrono::steady_clock::now();
+  auto ms_since = [&](std::chrono::steady_clock::time_point t) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+  };
   // ---- scan_file for every file first (loudgain.c:299-305)
   if (nthreads <= 1 || ntracks <= 1) {
     for (size_t i = 0; i < ntracks && !rc; ++i) rc = scan_one(tracks[i], chunk_frames, &states[i]);
@@ -87,8 +96,12 @@ extern "C" LG_EXPORT int lgb_scan_host_mt(const lgb_host_track* tracks, size_t n
     for (std::thread& th : pool) th.join();
     rc = err.load();
   }
+  const double ms_feed = ms_since(t_start);
+  const auto t_query = std::chrono::steady_clock::now();
+  double ms_first = 0.0;
   // ---- results (loudgain.c:323-340): track, then album, per file
   for (size_t i = 0; i < ntracks && !rc; ++i) {
+    if (i == 1) ms_first = ms_since(t_query);
     lgb_scan_result& r = out[i];
     double global, range;
     if (ebur128_loudness_global(states[i], &global) != EBUR128_SUCCESS) global = 0.0;
@@ -115,6 +128,68 @@ extern "C" LG_EXPORT int lgb_scan_host_mt(const lgb_host_track* tracks, size_t n
       r.album_loudness_range = range;
     }
   }
+  const double ms_query = ms_since(t_query);
+  const auto t_free = std::chrono::steady_clock::now();
   for (size_t i = 0; i < ntracks; ++i) ebur128_destroy(&states[i]);   // scan_deinit
+  if (trace)
+    fprintf(stderr, "lgb_scan_host: feed %.2f ms, queries %.2f ms (first track incl. the GPU batch "
+            "%.2f ms), destroy %.2f ms\n", ms_feed, ms_query, ms_first, ms_since(t_free));
   return rc;
+}
+
+// ---- loudgain's use of a scan result ---------------------------------------
+
+namespace {
+
+// Gain (dB) applied to a linear peak; and the gain change that moves a peak
+// from `from` to `to`.
+inline double peak_after_gain(double gain_db, double peak) { return pow(10.0, gain_db / 20.0) * peak; }
+inline double db_between(double from, double to) { return 20.0 * log10(from / to); }
+
+}  // namespace
+
+extern "C" LG_EXPORT int lgb_clip_prevention(lgb_scan_result* r, int do_album, int prevent,
+                                             double max_true_peak_db, lgb_clip_info* info) {
+  if (!r || !info) return 1;
+  const double limit = pow(10.0, max_true_peak_db / 20.0);
+  lgb_clip_info c = {0, 0, 0, 0, 0.0, 0.0};
+  const double tpeak = peak_after_gain(r->track_gain, r->track_peak);
+  const double apeak = do_album ? peak_after_gain(r->album_gain, r->album_peak) : 0.0;
+  const bool t_over = tpeak > limit, a_over = do_album && apeak > limit;
+  c.track_new_peak = tpeak;
+  c.album_new_peak = apeak;
+  c.will_clip = t_over || a_over;
+  if (c.will_clip && prevent) {
+    if (t_over) {
+      r->track_gain -= db_between(tpeak, limit);
+      c.track_new_peak = limit;
+      c.track_clipped = 1;
+    }
+    if (a_over) {
+      r->album_gain -= db_between(apeak, limit);
+      c.album_new_peak = limit;
+      c.album_clipped = 1;
+    }
+    c.will_clip = 0;
+  }
+  c.album_would_clip = a_over && !c.album_clipped;
+  *info = c;
+  return 0;
+}
+
+extern "C" LG_EXPORT size_t lgb_format_tab_row(const char* name, const lgb_scan_result* r,
+                                               const lgb_clip_info* info, int album_row,
+                                               const char* unit, char* buf, size_t cap) {
+  const double loud = album_row ? r->album_loudness : r->track_loudness;
+  const double range = album_row ? r->album_loudness_range : r->track_loudness_range;
+  const double peak = album_row ? r->album_peak : r->track_peak;
+  const double gain = album_row ? r->album_gain : r->track_gain;
+  const double npeak = album_row ? info->album_new_peak : info->track_new_peak;
+  const int clip = album_row ? info->album_would_clip : info->will_clip;
+  const int fixed = album_row ? info->album_clipped : info->track_clipped;
+  const int n = snprintf(buf, cap,
+                         "%s\t%.2f LUFS\t%.2f %s\t%.6f\t%.2f dBTP\t%.2f LUFS\t%s\t%s\t%.2f %s\t%.6f\t%.2f dBTP\n",
+                         name, loud, range, unit, peak, 20.0 * log10(peak), r->loudness_reference,
+                         clip ? "Y" : "N", fixed ? "Y" : "N", gain, unit, npeak, 20.0 * log10(npeak));
+  return n < 0 ? 0 : (size_t) n;
 }

@@ -49,6 +49,11 @@ class Measurement:
     true_peak: np.ndarray = field(default_factory=lambda: np.zeros(0))
 
 
+_RESULT_DTYPE = np.dtype([("loudness", "<f8"), ("range", "<f8"), ("rel_threshold", "<f8"),
+                          ("sum_abs", "<f8"), ("sum_rel", "<f8"), ("n_abs", "<u8"), ("n_rel", "<u8"),
+                          ("n_shortterm", "<u8")])
+_NO_PEAKS = np.zeros(0)
+
 _lib = None
 
 
@@ -115,6 +120,15 @@ class Batch:
             arr[i] = _Track(pcm.data_ptr(), pcm.shape[0], pcm.shape[1], int(rate), fmt, alb, None,
                             0 if lead_in is None else int(lead_in[i]))
         self.ntracks, self.nalbums = n, nalb
+        # result buffers are allocated once: fetch() sits between two steps of a
+        # repeatedly run batch, where host time is GPU idle time
+        self._tres = (_Result * max(n, 1))()
+        self._ares = (_Result * max(nalb, 1))()
+        self._npk = sum(self.channels)
+        self._sp = np.zeros(max(self._npk, 1))
+        self._tp = np.zeros(max(self._npk, 1))
+        self._spp = self._sp.ctypes.data_as(C.c_void_p)
+        self._tpp = self._tp.ctypes.data_as(C.c_void_p)
         self.stream = stream if stream is not None else torch.cuda.current_stream()
         self._h = L.lgb_batch_create(arr, n, nalb, C.c_void_p(self.stream.cuda_stream))
         if not self._h:
@@ -140,28 +154,19 @@ class Batch:
     def fetch(self) -> tuple[list[Measurement], list[Measurement]]:
         """Wait and read back per-track and per-album results."""
         L = self._L
-        tres = (_Result * max(self.ntracks, 1))()
-        ares = (_Result * max(self.nalbums, 1))()
-        npk = L.lgb_batch_peak_count(self._h)
-        sp = np.zeros(max(npk, 1))
-        tp = np.zeros(max(npk, 1))
-        if L.lgb_batch_fetch(self._h, tres, ares, sp.ctypes.data_as(C.c_void_p),
-                             tp.ctypes.data_as(C.c_void_p)):
+        tres, ares, sp, tp = self._tres, self._ares, self._sp, self._tp
+        if L.lgb_batch_fetch(self._h, tres, ares, self._spp, self._tpp):
             raise RuntimeError("lgb_batch_fetch failed: " + _err(L))
 
-        def conv(r, s=None, t=None):
-            m = Measurement(r.loudness, r.range, r.rel_threshold, r.sum_abs, r.sum_rel,
-                            r.n_abs, r.n_rel, r.n_shortterm)
-            if s is not None:
-                m.sample_peak, m.true_peak = s, t
-            return m
-
+        # one C-level pass over the result structs, one copy of the peaks
+        rows = np.frombuffer(tres, dtype=_RESULT_DTYPE, count=self.ntracks).tolist()
+        spc, tpc = sp.copy(), tp.copy()
         out_t, off = [], 0
-        for i in range(self.ntracks):
-            ch = self.channels[i]
-            out_t.append(conv(tres[i], sp[off:off + ch].copy(), tp[off:off + ch].copy()))
+        for row, ch in zip(rows, self.channels):
+            out_t.append(Measurement(*row, spc[off:off + ch], tpc[off:off + ch]))
             off += ch
-        return out_t, [conv(ares[a]) for a in range(self.nalbums)]
+        arows = np.frombuffer(ares, dtype=_RESULT_DTYPE, count=self.nalbums).tolist()
+        return out_t, [Measurement(*row, _NO_PEAKS, _NO_PEAKS) for row in arows]
 
     def blocks(self, track: int, kind: int = 0) -> np.ndarray:
         """Block energies of one track, copied to the host (0 = 400 ms gating

@@ -1,0 +1,83 @@
+"""loudgain's use of a scan result: clipping prevention
+(/root/reference/src/loudgain.c:323-379) and the `-O` row
+(loudgain.c:586-612).  Host arithmetic of the product library; no GPU."""
+import ctypes as C
+import math
+
+import pytest
+
+from loudgain_b200 import load_library
+
+
+class ScanResult(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "track_gain", "track_peak", "track_loudness", "track_loudness_range", "album_gain",
+        "album_peak", "album_loudness", "album_loudness_range", "loudness_reference")]
+
+
+class ClipInfo(C.Structure):
+    _fields_ = [("will_clip", C.c_int), ("track_clipped", C.c_int), ("album_clipped", C.c_int),
+                ("album_would_clip", C.c_int), ("track_new_peak", C.c_double),
+                ("album_new_peak", C.c_double)]
+
+
+@pytest.fixture(scope="module")
+def L():
+    lib = load_library().lib
+    lib.lgb_clip_prevention.argtypes = [C.POINTER(ScanResult), C.c_int, C.c_int, C.c_double,
+                                        C.POINTER(ClipInfo)]
+    lib.lgb_format_tab_row.argtypes = [C.c_char_p, C.POINTER(ScanResult), C.POINTER(ClipInfo), C.c_int,
+                                       C.c_char_p, C.c_char_p, C.c_size_t]
+    lib.lgb_format_tab_row.restype = C.c_size_t
+    return lib
+
+
+def _result(tl, tp, al, ap):
+    # scan.c:64: gain = -18 - loudness (reference -18 LUFS)
+    return ScanResult(-18.0 - tl, tp, tl, 7.5, -18.0 - al, ap, al, 9.25, -18.0)
+
+
+def test_no_clipping_needed(L):
+    r, c = _result(-9.0, 0.98, -10.0, 1.02), ClipInfo()
+    assert L.lgb_clip_prevention(r, 1, 1, -1.0, c) == 0
+    assert (c.will_clip, c.track_clipped, c.album_clipped) == (0, 0, 0)
+    assert r.track_gain == -9.0 and r.album_gain == -8.0
+    assert c.track_new_peak == pytest.approx(10 ** (-9 / 20) * 0.98)
+
+
+def test_quiet_track_is_limited(L):
+    # a quiet track with a full-scale peak: +5 dB would push the peak to 1.78
+    r, c = _result(-23.0, 1.0, -20.0, 1.0), ClipInfo()
+    L.lgb_clip_prevention(r, 1, 0, -1.0, c)
+    assert c.will_clip == 1 and c.track_clipped == 0 and c.album_would_clip == 1
+    assert r.track_gain == 5.0
+    L.lgb_clip_prevention(r, 1, 1, -1.0, c)
+    limit = 10 ** (-1 / 20)
+    assert (c.will_clip, c.track_clipped, c.album_clipped, c.album_would_clip) == (0, 1, 1, 0)
+    assert c.track_new_peak == pytest.approx(limit) and c.album_new_peak == pytest.approx(limit)
+    # the corrected gains put the peaks exactly on the limit
+    assert 10 ** (r.track_gain / 20) * r.track_peak == pytest.approx(limit, rel=1e-12)
+    assert 10 ** (r.album_gain / 20) * r.album_peak == pytest.approx(limit, rel=1e-12)
+    assert r.track_gain == pytest.approx(-1.0) and r.album_gain == pytest.approx(-1.0)
+
+
+def test_track_only_mode_ignores_album(L):
+    r, c = _result(-23.0, 0.5, -30.0, 1.0), ClipInfo()
+    L.lgb_clip_prevention(r, 0, 1, -1.0, c)
+    assert (c.will_clip, c.track_clipped, c.album_clipped) == (0, 0, 0) and r.album_gain == 12.0
+
+
+def test_tab_row_format(L):
+    r, c = _result(-23.0, 1.0, -20.0, 1.0), ClipInfo()
+    L.lgb_clip_prevention(r, 1, 1, -1.0, c)
+    buf = C.create_string_buffer(512)
+    n = L.lgb_format_tab_row(b"a.flac", r, c, 0, b"dB", buf, 512)
+    row = buf.value.decode()
+    assert n == len(row)
+    assert row == ("a.flac\t-23.00 LUFS\t7.50 dB\t1.000000\t0.00 dBTP\t-18.00 LUFS\tN\tY\t-1.00 dB\t"
+                   "%.6f\t-1.00 dBTP\n" % 10 ** (-1 / 20))
+    L.lgb_format_tab_row(b"Album", r, c, 1, b"LU", buf, 512)
+    cols = buf.value.decode().rstrip("\n").split("\t")
+    assert cols[0] == "Album" and cols[1] == "-20.00 LUFS" and cols[2] == "9.25 LU"
+    assert cols[6:9] == ["N", "Y", "-1.00 LU"] and len(cols) == 11
+    assert math.isclose(float(cols[9]), 10 ** (-1 / 20), abs_tol=1e-6)
