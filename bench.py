@@ -284,8 +284,19 @@ def gpu_arm(args):
     value = samples * world * args.steps / (ms_total * 1e-3) / 1e9
 
     if args.quick:
+        # diagnostic: the same steps enqueued back to back, one read-back at the
+        # end -- GPU time per step without the host turn-around between steps
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            batch.run()
+        e1.record(stream)
+        batch.fetch()
+        barrier()
+        piped_ms = e0.elapsed_time(e1) / args.steps
         if rank == 0:
             print(json.dumps({"quick": True, "value": value, "ms_per_step": ms_total / args.steps,
+                              "ms_per_step_back_to_back": piped_ms,
                               "sweep_ms": sweep_ms, "truepeak_ms": tp_ms,
                               "sweep_gsamples": samples / (sweep_ms * 1e-3) / 1e9 if sweep_ms else None}),
                   flush=True)

@@ -106,7 +106,7 @@ struct lgb_batch {
   // post-processing kernels go to a high-priority side stream and slip in next
   // to the true-peak pass on the main stream; joined before the result copy.
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_post = nullptr;
   cudaEvent_t ev_blocks = nullptr;   // block lists of the current run are complete (lgb_batch_wait_blocks)
   double abs_gate = 0.0;
   uint32_t launches = 0, sweep_launches = 0, sms = 148;
@@ -203,6 +203,7 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
     if (cudaStreamCreateWithPriority(&b->side, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_post, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_blocks, cudaEventDisableTiming) != cudaSuccess) {
       cudaGetLastError();
       if (b->side) { cudaStreamDestroy(b->side); b->side = nullptr; }
@@ -238,13 +239,38 @@ static int enqueue_step(lgb_batch* b) {
   }
   if (b->timing) { cudaEventRecord(b->ev1, b->stream); b->timed_run_pending = true; }
   // Fork (not in timed runs: those keep everything on the main stream, between
-  // the events).
+  // the events): fix-up, slot and block kernels go to the high-priority side
+  // stream first.  The true-peak evaluation fills every SM for its whole
+  // duration, so it is held back until the block kernel is done: then the query
+  // kernel (a handful of large CTAs, high priority) and the evaluation become
+  // ready together and share the GPU, instead of the queries waiting for SMs.
   const bool fork = !b->timing && b->side != nullptr;
   cudaStream_t ps = fork ? b->side : b->stream;
+  PostSizes z{(uint32_t) p.tracks.size(), p.total_recs, p.total_slots, p.total_blocks, p.total_st};
+  auto post_kernels = [&]() -> int {
+    e = launch_post(t, z, ps);
+    if (e != cudaSuccess) { set_error("launch_post", e); return 1; }
+    if (fork) {
+      e = cudaEventRecord(b->ev_post, ps);
+      if (e != cudaSuccess) { set_error("cudaEventRecord(post)", e); return 1; }
+    }
+    if (b->ev_blocks) {
+      // while the step is being captured into its graph the record must be an
+      // external event node, so that streams outside the graph can wait for it
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(ps, &cap);
+      e = cap == cudaStreamCaptureStatusActive
+              ? cudaEventRecordWithFlags(b->ev_blocks, ps, cudaEventRecordExternal)
+              : cudaEventRecord(b->ev_blocks, ps);
+      if (e != cudaSuccess) { set_error("cudaEventRecord(blocks)", e); return 1; }
+    }
+    return 0;
+  };
   if (fork) {
     e = cudaEventRecord(b->ev_fork, b->stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(b->side, b->ev_fork, 0);
     if (e != cudaSuccess) { set_error("fork(post-processing stream)", e); return 1; }
+    if (post_kernels()) return 1;
   }
   // The true-peak pass needs the final sample peaks of every track of a group.
   uint32_t gi = 0;
@@ -254,24 +280,13 @@ static int enqueue_step(lgb_batch* b) {
     sp.mrec = b->d_mrec + g.mrec_base;
     sp.tp_ticket = b->d_peaks + 2 * p.total_peaks + gi++;
     sp.tp_queue = b->d_tpq + 2 * g.mrec_base;
-    e = sp.packed ? launch_truepeak_pair(sp, g.format, g.tpf, b->sms, b->stream)
-                  : launch_truepeak(sp, g.format, g.tpf, b->sms, b->stream);
+    cudaEvent_t hold = fork ? b->ev_post : nullptr;
+    e = sp.packed ? launch_truepeak_pair(sp, g.format, g.tpf, b->sms, b->stream, hold)
+                  : launch_truepeak(sp, g.format, g.tpf, b->sms, b->stream, hold);
     if (e != cudaSuccess) { set_error("launch_truepeak", e); return 1; }
   }
   if (b->timing) cudaEventRecord(b->ev2, b->stream);
-  PostSizes z{(uint32_t) p.tracks.size(), p.total_recs, p.total_slots, p.total_blocks, p.total_st};
-  e = launch_post(t, z, ps);
-  if (e != cudaSuccess) { set_error("launch_post", e); return 1; }
-  if (b->ev_blocks) {
-    // while the step is being captured into its graph the record must be an
-    // external event node, so that streams outside the graph can wait for it
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(ps, &cap);
-    e = cap == cudaStreamCaptureStatusActive
-            ? cudaEventRecordWithFlags(b->ev_blocks, ps, cudaEventRecordExternal)
-            : cudaEventRecord(b->ev_blocks, ps);
-    if (e != cudaSuccess) { set_error("cudaEventRecord(blocks)", e); return 1; }
-  }
+  if (!fork && post_kernels()) return 1;
   e = launch_queries(t.lists, t.queries, t.members, (uint32_t) p.queries.size(), b->abs_gate,
                      t.results, ps);
   if (e != cudaSuccess) { set_error("launch_queries", e); return 1; }
@@ -507,6 +522,7 @@ extern "C" LG_EXPORT void lgb_batch_destroy(lgb_batch* b) {
   if (b->graph) cudaGraphExecDestroy(b->graph);
   if (b->ev_fork) cudaEventDestroy(b->ev_fork);
   if (b->ev_join) cudaEventDestroy(b->ev_join);
+  if (b->ev_post) cudaEventDestroy(b->ev_post);
   if (b->ev_blocks) cudaEventDestroy(b->ev_blocks);
   if (b->side) cudaStreamDestroy(b->side);
   if (b->h_results) cudaFreeHost(b->h_results);

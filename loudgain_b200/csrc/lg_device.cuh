@@ -12,8 +12,12 @@ namespace lg {
 #ifndef LG_CPASYNC_L2
 #define LG_CPASYNC_L2 ""
 #endif
+// cache operator of the streaming copies: cg = L2 only, ca = also L1
+#ifndef LG_CPASYNC_OP
+#define LG_CPASYNC_OP "cg"
+#endif
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global" LG_CPASYNC_L2 " [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  asm volatile("cp.async." LG_CPASYNC_OP ".shared.global" LG_CPASYNC_L2 " [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes)

@@ -517,8 +517,12 @@ static cudaError_t launch_truepeak_t(const SweepParams& p, uint32_t sms, cudaStr
 }
 
 cudaError_t launch_truepeak(const SweepParams& p, uint32_t format, int tpf, uint32_t sms,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, cudaEvent_t hold) {
   if (p.nwarps == 0 || tpf == 0) return cudaSuccess;
+  if (hold) {
+    const cudaError_t e = cudaStreamWaitEvent(stream, hold, 0);
+    if (e != cudaSuccess) return e;
+  }
   if (format == FMT_S16)
     return tpf == 4 ? launch_truepeak_t<FMT_S16, 4>(p, sms, stream)
                     : launch_truepeak_t<FMT_S16, 2>(p, sms, stream);
@@ -541,13 +545,34 @@ __device__ uint32_t find_track(const Track* tracks, uint32_t ntracks, uint64_t i
   return lo;
 }
 
+// The same with the tracks' base offsets staged in shared memory by the CTA
+// (one coalesced pass instead of a chain of dependent global loads per thread);
+// batches with more than kTrackCache tracks search the global table.
+constexpr uint32_t kTrackCache = 1024;
+
+template <class GetBase>
+__device__ uint32_t find_track_cta(const Track* tracks, uint32_t ntracks, uint64_t idx, bool valid,
+                                   uint64_t* s_base, GetBase base) {
+  if (ntracks > kTrackCache) return valid ? find_track(tracks, ntracks, idx, base) : 0u;
+  for (uint32_t i = threadIdx.x; i < ntracks; i += blockDim.x) s_base[i] = base(tracks[i]);
+  __syncthreads();
+  uint32_t lo = 0, hi = ntracks;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (s_base[mid] <= idx) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
 __global__ void __launch_bounds__(256)
 fixup_kernel(const Track* __restrict__ tracks, uint32_t ntracks,
              const CoefSet* __restrict__ coefs, const ChunkRec* __restrict__ recs,
              uint64_t total_recs, double* __restrict__ echunk) {
+  __shared__ uint64_t s_base[kTrackCache];
   const uint64_t r = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t ti = find_track_cta(tracks, ntracks, r, r < total_recs, s_base,
+                                     [](const Track& t) { return t.rec_base; });
   if (r >= total_recs) return;
-  const uint32_t ti = find_track(tracks, ntracks, r, [](const Track& t) { return t.rec_base; });
   const Track& tr = tracks[ti];
   const CoefSet& cs = coefs[tr.coef];
   const uint64_t local = r - tr.rec_base;
@@ -563,9 +588,11 @@ __global__ void __launch_bounds__(256)
 slot_kernel(const Track* __restrict__ tracks, uint32_t ntracks,
             const CoefSet* __restrict__ coefs, const double* __restrict__ echunk,
             uint64_t total_slots, double* __restrict__ eslot) {
+  __shared__ uint64_t s_base[kTrackCache];
   const uint64_t s = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t ti = find_track_cta(tracks, ntracks, s, s < total_slots, s_base,
+                                     [](const Track& t) { return t.slot_base; });
   if (s >= total_slots) return;
-  const uint32_t ti = find_track(tracks, ntracks, s, [](const Track& t) { return t.slot_base; });
   const Track& tr = tracks[ti];
   eslot[s] = slot_energy(tr, coefs[tr.coef], echunk, (uint32_t) (s - tr.slot_base));
 }
@@ -575,14 +602,32 @@ block_kernel(const Track* __restrict__ tracks, uint32_t ntracks,
              const CoefSet* __restrict__ coefs, const double* __restrict__ eslot,
              uint64_t total_blocks, uint64_t total_st, double* __restrict__ zblock,
              double* __restrict__ zst) {
+  __shared__ uint64_t s_bbase[kTrackCache], s_sbase[kTrackCache];
+  const bool cached = ntracks <= kTrackCache;
+  if (cached) {
+    for (uint32_t k = threadIdx.x; k < ntracks; k += blockDim.x) {
+      s_bbase[k] = tracks[k].block_base;
+      s_sbase[k] = tracks[k].st_base;
+    }
+    __syncthreads();
+  }
+  auto locate = [&](const uint64_t* sb, uint64_t idx, auto base) {
+    if (!cached) return find_track(tracks, ntracks, idx, base);
+    uint32_t lo = 0, hi = ntracks;
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (sb[mid] <= idx) lo = mid; else hi = mid;
+    }
+    return lo;
+  };
   const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (i < total_blocks) {
-    const uint32_t ti = find_track(tracks, ntracks, i, [](const Track& t) { return t.block_base; });
+    const uint32_t ti = locate(s_bbase, i, [](const Track& t) { return t.block_base; });
     const Track& tr = tracks[ti];
     zblock[i] = gating_block(eslot + tr.slot_base, coefs[tr.coef], (uint32_t) (i - tr.block_base));
   } else if (i < total_blocks + total_st) {
     const uint64_t j = i - total_blocks;
-    const uint32_t ti = find_track(tracks, ntracks, j, [](const Track& t) { return t.st_base; });
+    const uint32_t ti = locate(s_sbase, j, [](const Track& t) { return t.st_base; });
     const Track& tr = tracks[ti];
     zst[j] = shortterm_block(eslot + tr.slot_base, coefs[tr.coef], (uint32_t) (j - tr.st_base));
   }
@@ -660,18 +705,6 @@ struct QueryView {
   const uint32_t* s_stoff;    // [count + 1]
 };
 
-// Index of the member whose range holds element g: fixed-depth, branch-free
-// search over the (shared-memory) prefix offsets, count <= kQueryCache.
-__device__ __forceinline__ uint32_t find_member(const uint32_t* off, uint32_t count, uint32_t g) {
-  uint32_t lo = 0;
-#pragma unroll
-  for (uint32_t step = kQueryCache / 2; step; step >>= 1) {
-    const uint32_t mid = lo + step;
-    if (mid < count && off[mid] <= g) lo = mid;
-  }
-  return lo;
-}
-
 // f(e, g) for every gating block energy (ST = false) or short-term energy
 // (ST = true).  Cached queries work in batches of kQueryBatch elements per
 // thread: all searches, then all loads, then the callbacks, so that a thread
@@ -683,14 +716,17 @@ __device__ __forceinline__ void for_each_energy(const QueryView& v, F f) {
   if (v.cached) {
     const uint32_t* off = ST ? v.s_stoff : v.s_zoff;
     const uint32_t total = off[v.count];
+    // a thread's elements come in increasing order, so its member index only
+    // ever moves forward: no search per element
+    uint32_t m = 0;
     for (uint32_t g0 = threadIdx.x; g0 < total; g0 += blockDim.x * kQueryBatch) {
       const double* src[kQueryBatch];
       double e[kQueryBatch];
 #pragma unroll
       for (int u = 0; u < kQueryBatch; ++u) {
         const uint32_t g = g0 + u * blockDim.x;
-        const uint32_t gc = g < total ? g : g0;
-        const uint32_t m = find_member(off, v.count, gc);
+        const uint32_t gc = g < total ? g : total - 1;
+        while (off[m + 1] <= gc) ++m;            // off[count] = total > gc: stops in range
         src[u] = (ST ? v.s_lists[m].st : v.s_lists[m].z) + (gc - off[m]);
       }
 #pragma unroll

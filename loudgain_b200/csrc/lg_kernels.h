@@ -37,13 +37,15 @@ struct PostSizes {
 cudaError_t launch_sweep(const SweepParams& p, uint32_t format, int tpf, cudaStream_t stream);
 // True-peak pass of the same group (no-op for rates without an interpolator);
 // must follow the group's sweep on the stream.
+// `hold` (optional): an event the heavy part of the pass waits for on `stream`
+// (lg_batch.cu lets the small post-processing kernels go first).
 cudaError_t launch_truepeak(const SweepParams& p, uint32_t format, int tpf, uint32_t sms,
-                            cudaStream_t stream);
+                            cudaStream_t stream, cudaEvent_t hold = nullptr);
 // The same two passes for groups with an even channel count (lg_pair.cu:
 // packed FP32, one lane per chunk and channel pair; SweepParams::packed).
 cudaError_t launch_sweep_pair(const SweepParams& p, uint32_t format, int tpf, cudaStream_t stream);
 cudaError_t launch_truepeak_pair(const SweepParams& p, uint32_t format, int tpf, uint32_t sms,
-                                 cudaStream_t stream);
+                                 cudaStream_t stream, cudaEvent_t hold = nullptr);
 cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t stream);
 // 400 ms / 3 s blocks of one stream from its complete 100 ms slot list.
 cudaError_t launch_stream_blocks(const double* eslot, int s100, uint64_t nblocks, uint64_t nst,

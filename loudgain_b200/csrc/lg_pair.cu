@@ -553,7 +553,7 @@ __device__ __forceinline__ void tp_pair_evaluate(const SweepParams& P, const uin
 // few warps work through dense runs; the queue spreads them evenly.
 constexpr int kTpScanThreads = 256;
 constexpr int kTpScanWarps = kTpScanThreads / 32;
-constexpr int kTpScanCap = 32 + 64;         // per-warp staging: remainder + one pair's hits
+constexpr int kTpSeg = 16;                  // pairs per scan item (codes held in registers)
 
 __device__ __forceinline__ uint64_t tp_entry(uint32_t w, uint32_t lane, uint32_t ch1, uint32_t pair) {
   return (uint64_t) w | ((uint64_t) (pair | (lane << 16) | (ch1 << 21)) << 32);
@@ -562,23 +562,25 @@ __device__ __forceinline__ uint64_t tp_entry(uint32_t w, uint32_t lane, uint32_t
 template <int FMT>
 __global__ void __launch_bounds__(kTpScanThreads)
 tp_scan_pair_kernel(const __grid_constant__ SweepParams P, const uint32_t seg_pairs) {
-  __shared__ uint64_t stage_all[kTpScanWarps][kTpScanCap];
+  // seg_pairs <= kTpSeg: a lane keeps its item's codes in registers, the hits
+  // are counted first and written second, with ONE queue reservation per CTA
+  // (a reservation per warp and flush serialises on the counter's address).
+  __shared__ uint32_t s_count[kTpScanWarps + 1];
   const uint32_t npairs = P.npairs;
   const uint32_t lane = threadIdx.x & 31u, wic = threadIdx.x >> 5;
-  uint64_t* stage = stage_all[wic];
   const uint32_t nseg = (npairs + seg_pairs - 1) / seg_pairs;
   const uint64_t item = (uint64_t) blockIdx.x * kTpScanWarps + wic;
-  if (item >= (uint64_t) P.nwarps * nseg) return;
-  const uint32_t w = (uint32_t) (item / nseg);
-  const uint32_t p_begin = (uint32_t) (item - (uint64_t) w * nseg) * seg_pairs;
-  const uint32_t p_end = p_begin + seg_pairs < npairs ? p_begin + seg_pairs : npairs;
+  const bool live = item < (uint64_t) P.nwarps * nseg;
+  const uint32_t w = live ? (uint32_t) (item / nseg) : 0u;
+  const uint32_t p_begin = live ? (uint32_t) (item - (uint64_t) w * nseg) * seg_pairs : 0u;
+  const uint32_t p_end = !live ? 0u : (p_begin + seg_pairs < npairs ? p_begin + seg_pairs : npairs);
   // the sweep lane's place in its track
   const WarpWork ww = P.work[w];
   const Track& tr = P.tracks[ww.track];
   const uint32_t slot = lane / P.lpc;
   const uint32_t ch = 2u * (lane - slot * P.lpc);
   const uint32_t chunk = ww.first_chunk + slot;
-  const bool ok = slot < P.cpw && chunk < tr.nchunks;
+  const bool ok = live && slot < P.cpw && chunk < tr.nchunks;
   const LaneGeom g = lane_geometry((long long) tr.frames, P.L, P.W, P.aq, chunk);
   const int f_lo = P.W + g.o;
   const long long left = (long long) tr.frames - g.a;
@@ -591,58 +593,70 @@ tp_scan_pair_kernel(const __grid_constant__ SweepParams P, const uint32_t seg_pa
   // the channel's true peak is at least its sample peak (final by now)
   const float floor0 = __uint_as_float(__ldcg(cell));
   const float floor1 = __uint_as_float(__ldcg(cell + 2));
-  uint32_t qn = 0;                       // warp-uniform
-  auto flush = [&](uint32_t n) {         // the n oldest staged entries go to the global queue
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(P.tp_ticket, n);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    __syncwarp();
-    for (uint32_t i = lane; i < n; i += 32u) P.tp_queue[base + i] = stage[i];
-    __syncwarp();
-  };
-  uint32_t prev = p_begin ? __ldcs(codes + (size_t) (p_begin - 1) * 32u) : 0u;
-  constexpr int kAhead = 4;
-  uint32_t nxt[kAhead];
-#pragma unroll
-  for (int j = 0; j < kAhead; ++j)
-    nxt[j] = p_begin + j < p_end ? __ldcs(codes + (size_t) (p_begin + j) * 32u) : 0u;
-  for (uint32_t p0 = p_begin; p0 < p_end; p0 += kAhead) {
-    uint32_t cur[kAhead];
-#pragma unroll
-    for (int j = 0; j < kAhead; ++j) {
-      cur[j] = nxt[j];
-      const uint32_t pn = p0 + kAhead + j;
-      nxt[j] = pn < p_end ? __ldcs(codes + (size_t) pn * 32u) : 0u;
+  // Pairs this lane owns: those that overlap its own chunk frames [f_lo, f_end)
+  // and do not lie entirely inside the track's lead-in.
+  int p_lo = f_lo / kPairFrames, p_hi = (f_end + kPairFrames - 1) / kPairFrames;
+  {
+    const long long lead_local = lead_in - g.a;            // lane-local frame where the lead-in ends
+    if (lead_local > 0) {
+      const long long q = lead_local / kPairFrames;        // first pair with frames past the lead-in
+      if (q > p_lo) p_lo = q > 0x7fffffff ? 0x7fffffff : (int) q;
     }
+    if (!ok) p_hi = 0;
+  }
+  // all codes of the item, and the one before it (history of the first pair)
+  uint32_t code[kTpSeg];
 #pragma unroll
-    for (int j = 0; j < kAhead; ++j) {
-      const uint32_t p = p0 + j;
-      const uint32_t code = cur[j];
-      const uint32_t cm = __vmaxu2(code, prev);      // per channel: this pair and its history
-      prev = code;
-      const int f0 = (int) (p * kPairFrames);
-      const bool own = ok && p < p_end && f0 + kPairFrames > f_lo && f0 < f_end &&
-                       g.a + f0 + kPairFrames > lead_in;
-      const bool hit0 = own && P.tp_bound * pair_code_value<FMT>(cm & 0xffffu) > floor0;
-      const bool hit1 = own && P.tp_bound * pair_code_value<FMT>(cm >> 16) > floor1;
-      const unsigned m0 = __ballot_sync(0xffffffffu, hit0);
-      const unsigned m1 = __ballot_sync(0xffffffffu, hit1);
-      if (m0 | m1) {
-        const unsigned below = (1u << lane) - 1u;
-        if (hit0) stage[qn + __popc(m0 & below)] = tp_entry(w, lane, 0u, p);
-        qn += __popc(m0);
-        if (hit1) stage[qn + __popc(m1 & below)] = tp_entry(w, lane, 1u, p);
-        qn += __popc(m1);
-        if (qn >= 32u) {
-          __syncwarp();
-          flush(qn);
-          qn = 0;
-        }
-      }
+  for (int j = 0; j < kTpSeg; ++j)
+    code[j] = p_begin + j < p_end ? __ldcs(codes + (size_t) (p_begin + j) * 32u) : 0u;
+  const uint32_t before = (live && p_begin) ? __ldcs(codes + (size_t) (p_begin - 1) * 32u) : 0u;
+
+  // per pair: which of the lane's two channels can still raise its peak
+  auto hits = [&](int j, uint32_t prev, bool& hit0, bool& hit1) {
+    const int p = (int) p_begin + j;
+    const uint32_t cm = __vmaxu2(code[j], prev);     // per channel: this pair and its history
+    const bool own = p >= p_lo && p < p_hi && p < (int) p_end;
+    hit0 = own && P.tp_bound * pair_code_value<FMT>(cm & 0xffffu) > floor0;
+    hit1 = own && P.tp_bound * pair_code_value<FMT>(cm >> 16) > floor1;
+  };
+  uint32_t mine = 0;                     // hits of this lane
+  {
+    uint32_t prev = before;
+#pragma unroll
+    for (int j = 0; j < kTpSeg; ++j) {
+      bool h0, h1;
+      hits(j, prev, h0, h1);
+      prev = code[j];
+      mine += (h0 ? 1u : 0u) + (h1 ? 1u : 0u);
     }
   }
-  __syncwarp();
-  if (qn) flush(qn);
+  // exclusive prefix of the lanes' counts within the warp, warps within the CTA
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (uint32_t) o) incl += v;
+  }
+  const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
+  if (lane == 0) s_count[wic] = warp_total;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+    for (int k = 0; k < kTpScanWarps; ++k) { const uint32_t c = s_count[k]; s_count[k] = total; total += c; }
+    s_count[kTpScanWarps] = total ? atomicAdd(P.tp_ticket, total) : 0u;
+  }
+  __syncthreads();
+  if (!warp_total) return;
+  uint64_t* out = P.tp_queue + s_count[kTpScanWarps] + s_count[wic] + (incl - mine);
+  uint32_t prev = before;
+#pragma unroll
+  for (int j = 0; j < kTpSeg; ++j) {
+    bool h0, h1;
+    hits(j, prev, h0, h1);
+    prev = code[j];
+    if (h0) *out++ = tp_entry(w, lane, 0u, p_begin + j);
+    if (h1) *out++ = tp_entry(w, lane, 1u, p_begin + j);
+  }
 }
 
 template <int FMT, int TPF>
@@ -665,7 +679,8 @@ tp_eval_pair_kernel(const __grid_constant__ SweepParams P) {
 }
 
 template <int FMT, int TPF>
-static cudaError_t launch_truepeak_pair_t(const SweepParams& p, uint32_t sms, cudaStream_t stream) {
+static cudaError_t launch_truepeak_pair_t(const SweepParams& p, uint32_t sms, cudaStream_t stream,
+                                          cudaEvent_t hold) {
   if (p.npairs > 0xffffu) return cudaErrorInvalidValue;      // pair index is a 16-bit field
   static int per_sm = 0;
   if (!per_sm) {
@@ -673,27 +688,28 @@ static cudaError_t launch_truepeak_pair_t(const SweepParams& p, uint32_t sms, cu
                                                       kTp2Threads, 0) != cudaSuccess || per_sm < 1)
       per_sm = 4;
   }
-  // scan: runs of 32 pairs per warp (fewer for small batches, so that every SM gets several)
+  // scan: runs of kTpSeg pairs per warp (fewer for small batches, so that every SM gets several)
   const uint64_t nscan = (uint64_t) sms * 8 * kTpScanWarps;
-  uint32_t seg = 32;
+  uint32_t seg = kTpSeg;
   while (seg > 4 && (uint64_t) p.nwarps * ((p.npairs + seg - 1) / seg) < nscan) seg >>= 1;
   const uint64_t nitems = (uint64_t) p.nwarps * ((p.npairs + seg - 1) / seg);
   const uint64_t ctas = (nitems + kTpScanWarps - 1) / kTpScanWarps;
   tp_scan_pair_kernel<FMT><<<(unsigned) ctas, kTpScanThreads, 0, stream>>>(p, seg);
   cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && hold) e = cudaStreamWaitEvent(stream, hold, 0);
   if (e != cudaSuccess) return e;
   tp_eval_pair_kernel<FMT, TPF><<<sms * per_sm, kTp2Threads, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_truepeak_pair(const SweepParams& p, uint32_t format, int tpf, uint32_t sms,
-                                 cudaStream_t stream) {
+                                 cudaStream_t stream, cudaEvent_t hold) {
   if (p.nwarps == 0 || tpf == 0) return cudaSuccess;
   if (format == FMT_S16)
-    return tpf == 4 ? launch_truepeak_pair_t<FMT_S16, 4>(p, sms, stream)
-                    : launch_truepeak_pair_t<FMT_S16, 2>(p, sms, stream);
-  return tpf == 4 ? launch_truepeak_pair_t<FMT_F32, 4>(p, sms, stream)
-                  : launch_truepeak_pair_t<FMT_F32, 2>(p, sms, stream);
+    return tpf == 4 ? launch_truepeak_pair_t<FMT_S16, 4>(p, sms, stream, hold)
+                    : launch_truepeak_pair_t<FMT_S16, 2>(p, sms, stream, hold);
+  return tpf == 4 ? launch_truepeak_pair_t<FMT_F32, 4>(p, sms, stream, hold)
+                  : launch_truepeak_pair_t<FMT_F32, 2>(p, sms, stream, hold);
 }
 
 }  // namespace lg
