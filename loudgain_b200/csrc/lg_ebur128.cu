@@ -642,11 +642,76 @@ extern "C" LG_EXPORT int ebur128_true_peak(ebur128_state* st, unsigned int ch, d
   return peak_query(st, ch, out, true);
 }
 
-// The sliding-window queries (momentary / short-term / arbitrary window) and
-// the per-call "prev" peaks are live-metering features that loudgain never
-// uses; they are not on the B200 path yet.
-extern "C" LG_EXPORT int ebur128_loudness_momentary(ebur128_state*, double*) { return EBUR128_ERROR_INVALID_MODE; }
-extern "C" LG_EXPORT int ebur128_loudness_shortterm(ebur128_state*, double*) { return EBUR128_ERROR_INVALID_MODE; }
-extern "C" LG_EXPORT int ebur128_loudness_window(ebur128_state*, unsigned long, double*) { return EBUR128_ERROR_INVALID_MODE; }
+// ---- sliding-window queries -------------------------------------------------
+// ebur128_loudness_momentary / _shortterm / _window: the loudness of the last
+// 400 ms / 3 s / `window` ms fed so far (frames before the start of the audio
+// count as silence).  loudgain never calls them; they are served from the same
+// kernels: the tail of the state's PCM (the window plus one second of lead-in,
+// right-aligned behind zeros when the audio is shorter) is measured as one
+// track with `lead_in` set, and the window's 100 ms slot energies are summed.
+// Windows must therefore be whole multiples of 100 ms (all three standard
+// ones are).
+namespace {
+
+int window_query(ebur128_state* st, size_t nframes, double* out) {
+  std::lock_guard<std::mutex> lock(g_ctx.mu);
+  if (!ctx_init()) return EBUR128_ERROR_NOMEM;
+  const size_t s100 = (st->samplerate + 5) / 10;
+  const size_t ring = (st->d->window_ms * st->samplerate + 999) / 1000;
+  if (!nframes || nframes % s100 || nframes > ((ring + s100 - 1) / s100) * s100)
+    return EBUR128_ERROR_INVALID_MODE;
+  if (!flush_stage(st)) return EBUR128_ERROR_NOMEM;
+  Segment& s = st->d->segs.back();          // a parameter change restarts the window
+  const size_t fb = s.channels * sample_bytes(s.format);
+  const size_t lead = 10 * s100, total = lead + nframes;
+  const size_t have = std::min<size_t>(s.frames, total);
+  char* tmp = nullptr;
+  if (cudaMallocAsync((void**) &tmp, total * fb, g_ctx.stream) != cudaSuccess) return EBUR128_ERROR_NOMEM;
+  bool ok = cudaMemsetAsync(tmp, 0, (total - have) * fb, g_ctx.stream) == cudaSuccess;
+  if (ok && have)
+    ok = cudaMemcpyAsync(tmp + (total - have) * fb, s.d_pcm + (s.frames - have) * fb, have * fb,
+                         cudaMemcpyDeviceToDevice, g_ctx.stream) == cudaSuccess;
+  double energy = 0.0;
+  if (ok) {
+    lgb_track t{tmp, total, s.channels, (uint32_t) s.rate, s.format, LGB_NO_ALBUM, s.wclass, lead};
+    BatchHolder h;
+    h.b = lgb_batch_create(&t, 1, 0, g_ctx.stream);
+    ok = h.b && lgb_batch_run(h.b) == 0 && lgb_batch_fetch(h.b, nullptr, nullptr, nullptr, nullptr) == 0;
+    if (ok) {
+      const double* dev = nullptr;
+      const uint64_t nslots = lgb_batch_blocks(h.b, 0, 2, &dev);
+      std::vector<double> slots(nslots);
+      ok = nslots == total / s100 &&
+           cudaMemcpyAsync(slots.data(), dev, nslots * sizeof(double), cudaMemcpyDeviceToHost,
+                           g_ctx.stream) == cudaSuccess &&
+           cudaStreamSynchronize(g_ctx.stream) == cudaSuccess;
+      for (size_t i = lead / s100; ok && i < nslots; ++i) energy += slots[i];
+    }
+    if (!ok) fprintf(stderr, "libebur128 (B200): %s\n", lgb_last_error());
+  }
+  cudaFreeAsync(tmp, g_ctx.stream);
+  if (!ok) return EBUR128_ERROR_NOMEM;
+  energy /= (double) nframes;
+  *out = energy <= 0.0 ? -HUGE_VAL : 10.0 * log10(energy) - 0.691;
+  return EBUR128_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" LG_EXPORT int ebur128_loudness_momentary(ebur128_state* st, double* out) {
+  return window_query(st, 4 * ((st->samplerate + 5) / 10), out);
+}
+
+extern "C" LG_EXPORT int ebur128_loudness_shortterm(ebur128_state* st, double* out) {
+  if (!has_mode(st, EBUR128_MODE_S)) return EBUR128_ERROR_INVALID_MODE;
+  return window_query(st, 30 * ((st->samplerate + 5) / 10), out);
+}
+
+extern "C" LG_EXPORT int ebur128_loudness_window(ebur128_state* st, unsigned long window, double* out) {
+  return window_query(st, (size_t) (st->samplerate * window / 1000), out);
+}
+
+// The per-call "prev" peaks are a live-metering feature that loudgain never
+// uses; they are not on the B200 path.
 extern "C" LG_EXPORT int ebur128_prev_sample_peak(ebur128_state*, unsigned int, double*) { return EBUR128_ERROR_INVALID_MODE; }
 extern "C" LG_EXPORT int ebur128_prev_true_peak(ebur128_state*, unsigned int, double*) { return EBUR128_ERROR_INVALID_MODE; }

@@ -177,6 +177,30 @@ def test_config4_time_segments(product, oracle):
         assert m.n_abs == whole[0].n_abs and m.n_shortterm == whole[0].n_shortterm
 
 
+@pytest.mark.parametrize("seconds", [0.25, 2.0, 7.3])
+def test_sliding_window_queries(product, oracle, seconds):
+    """ebur128_loudness_momentary / _shortterm / _window (not used by loudgain):
+    the last 400 ms / 3 s / n x 100 ms of what was fed, silence before the start."""
+    rng = np.random.default_rng(int(seconds * 100))
+    n = int(seconds * 44100)
+    env = np.linspace(0.2, 1.0, n)[:, None]
+    pcm = (rng.standard_normal((n, 2)) * 6000 * env).astype(np.int16)
+
+    def drive(L):
+        st = L.init(2, 44100)
+        st.add_frames(pcm[: n // 3], 1000)
+        first = st.loudness_momentary()
+        st.add_frames(pcm[n // 3:], 4096)
+        out = (first, st.loudness_momentary(), st.loudness_shortterm(), st.loudness_window(1000),
+               st.loudness_global())
+        st.destroy()
+        return out
+
+    got, want = drive(product), drive(oracle)
+    for g, w in zip(got, want):
+        assert lu_diff(g, w) <= GOAL_LU
+
+
 def test_threaded_scanners_match_single_thread(product):
     """Different threads feed different states at the same time (states are
     independent, as in libebur128): the results do not depend on it, also with
