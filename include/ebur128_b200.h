@@ -187,6 +187,17 @@ int lgb_clip_prevention(lgb_scan_result* r, int do_album, int prevent, double ma
 size_t lgb_format_tab_row(const char* name, const lgb_scan_result* r, const lgb_clip_info* info,
                           int album_row, const char* unit, char* buf, size_t cap);
 
+/* The tag values loudgain would write for a scan result, as text at the
+ * reference's tag precision (tag.cc:178-203: gains "%.2f <unit>", peaks
+ * "%.6f", reference "%.2f LUFS"; Opus files carry Q7.8 integers instead,
+ * tag.cc:442-445,474-480).  One "NAME=value" pair per line; album lines only
+ * with do_album, range / reference lines only with `extended` (loudgain's
+ * -s e / -s l); `opus` selects the R128_* form.  Actual tag writing (TagLib)
+ * stays with the host application.  Returns the length written, or the
+ * length needed if `cap` is too small. */
+size_t lgb_format_tags(const lgb_scan_result* r, int do_album, int extended, int opus,
+                       const char* unit, char* buf, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -193,3 +193,30 @@ extern "C" LG_EXPORT size_t lgb_format_tab_row(const char* name, const lgb_scan_
                          clip ? "Y" : "N", fixed ? "Y" : "N", gain, unit, npeak, 20.0 * log10(npeak));
   return n < 0 ? 0 : (size_t) n;
 }
+
+extern "C" LG_EXPORT size_t lgb_format_tags(const lgb_scan_result* r, int do_album, int extended,
+                                            int opus, const char* unit, char* buf, size_t cap) {
+  size_t len = 0;
+  auto put = [&](const char* fmt, auto... args) {
+    const int n = snprintf(len < cap ? buf + len : nullptr, len < cap ? cap - len : 0, fmt, args...);
+    if (n > 0) len += (size_t) n;
+  };
+  if (opus) {
+    // Q7.8 fixed point: round(gain * 2^8)
+    put("R128_TRACK_GAIN=%d\n", (int) round(r->track_gain * 256.0));
+    if (do_album) put("R128_ALBUM_GAIN=%d\n", (int) round(r->album_gain * 256.0));
+    return len;
+  }
+  put("REPLAYGAIN_TRACK_GAIN=%.2f %s\n", r->track_gain, unit);
+  put("REPLAYGAIN_TRACK_PEAK=%.6f\n", r->track_peak);
+  if (do_album) {
+    put("REPLAYGAIN_ALBUM_GAIN=%.2f %s\n", r->album_gain, unit);
+    put("REPLAYGAIN_ALBUM_PEAK=%.6f\n", r->album_peak);
+  }
+  if (extended) {
+    put("REPLAYGAIN_REFERENCE_LOUDNESS=%.2f LUFS\n", r->loudness_reference);
+    put("REPLAYGAIN_TRACK_RANGE=%.2f %s\n", r->track_loudness_range, unit);
+    if (do_album) put("REPLAYGAIN_ALBUM_RANGE=%.2f %s\n", r->album_loudness_range, unit);
+  }
+  return len;
+}

@@ -29,6 +29,9 @@ def L():
     lib.lgb_format_tab_row.argtypes = [C.c_char_p, C.POINTER(ScanResult), C.POINTER(ClipInfo), C.c_int,
                                        C.c_char_p, C.c_char_p, C.c_size_t]
     lib.lgb_format_tab_row.restype = C.c_size_t
+    lib.lgb_format_tags.argtypes = [C.POINTER(ScanResult), C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                    C.c_char_p, C.c_size_t]
+    lib.lgb_format_tags.restype = C.c_size_t
     return lib
 
 
@@ -81,3 +84,24 @@ def test_tab_row_format(L):
     assert cols[0] == "Album" and cols[1] == "-20.00 LUFS" and cols[2] == "9.25 LU"
     assert cols[6:9] == ["N", "Y", "-1.00 LU"] and len(cols) == 11
     assert math.isclose(float(cols[9]), 10 ** (-1 / 20), abs_tol=1e-6)
+
+
+def test_tag_values_at_reference_precision(L):
+    """tag.cc:178-203 (ReplayGain text tags) and tag.cc:442-445 (Opus Q7.8)."""
+    r = _result(-9.456, 0.9876543, -10.004, 1.0234567)
+    buf = C.create_string_buffer(512)
+    n = L.lgb_format_tags(r, 1, 1, 0, b"dB", buf, 512)
+    text = buf.value.decode()
+    assert n == len(text)
+    assert text.splitlines() == [
+        "REPLAYGAIN_TRACK_GAIN=-8.54 dB", "REPLAYGAIN_TRACK_PEAK=0.987654",
+        "REPLAYGAIN_ALBUM_GAIN=-8.00 dB", "REPLAYGAIN_ALBUM_PEAK=1.023457",
+        "REPLAYGAIN_REFERENCE_LOUDNESS=-18.00 LUFS", "REPLAYGAIN_TRACK_RANGE=7.50 dB",
+        "REPLAYGAIN_ALBUM_RANGE=9.25 dB"]
+    L.lgb_format_tags(r, 0, 0, 0, b"LU", buf, 512)
+    assert buf.value.decode().splitlines() == ["REPLAYGAIN_TRACK_GAIN=-8.54 LU",
+                                               "REPLAYGAIN_TRACK_PEAK=0.987654"]
+    L.lgb_format_tags(r, 1, 0, 1, b"dB", buf, 512)
+    assert buf.value.decode().splitlines() == ["R128_TRACK_GAIN=%d" % round(-8.544 * 256),
+                                               "R128_ALBUM_GAIN=%d" % round(-7.996 * 256)]
+    assert L.lgb_format_tags(r, 1, 1, 0, b"dB", None, 0) == n      # length query
