@@ -363,6 +363,11 @@ def gpu_arm(args):
                          "traffic_source": "dram__bytes_read+write per launch, ncu --set full, "
                                            "profiles/r01_sweep_ncu_summary.json",
                          "kernel": "sweep_pair_kernel<S16 stereo, 4x true-peak codes>", "kernel_ms": sweep_ms,
+                         # the true-peak evaluation is a separate pass over the sweep's pair
+                         # maxima (tp_scan_pair_kernel + tp_eval_pair_kernel); with it:
+                         "truepeak_pass_ms": tp_ms,
+                         "achieved_incl_truepeak_pass": samples * 2 / ((sweep_ms + tp_ms) * 1e-3) / 1e9
+                         if sweep_ms > 0 else None,
                          "peak_source": src,
                          "algorithmic_bytes": "2 B per S16 sample, read once (SURVEY 8d)"},
             "cpu_baseline": cpu,
