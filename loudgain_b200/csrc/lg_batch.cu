@@ -55,7 +55,10 @@ int query_lists_sync(const BlockList* lists, size_t n, cudaStream_t stream, Quer
   bool ok = upload(hl, &dl, stream) && upload(hm, &dm, stream) && upload(hq, &dq, stream) &&
             dalloc(&dr, 1, stream);
   if (ok) {
-    cudaError_t e = launch_queries(dl, dq, dm, 1, pow(10.0, (-70.0 + 0.691) / 10.0), dr, stream);
+    uint64_t blocks = 0;
+    for (size_t i = 0; i < n; ++i) blocks += lists[i].nz;
+    cudaError_t e = launch_queries(dl, dq, dm, 1, pow(10.0, (-70.0 + 0.691) / 10.0), dr, stream,
+                                   query_cluster_size(blocks));
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, dr, sizeof(QueryResult), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) { set_error("query_lists_sync", e); ok = false; }
@@ -110,6 +113,7 @@ struct lgb_batch {
   cudaEvent_t ev_blocks = nullptr;   // block lists of the current run are complete (lgb_batch_wait_blocks)
   double abs_gate = 0.0;
   uint32_t launches = 0, sweep_launches = 0, sms = 148;
+  uint32_t query_cluster = 1;        // CTAs per query (lg_kernels.cu: query_kernel)
   // optional sweep timing
   bool timing = false, timed_run_pending = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -211,6 +215,15 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
   }
   if (!ok) { lgb_batch_destroy(b); return nullptr; }
   b->sms = (uint32_t) sms;
+  {
+    uint64_t most = 0;
+    for (const Query& q : p.queries) {
+      uint64_t blocks = 0;
+      for (uint32_t m = 0; m < q.count; ++m) blocks += p.tracks[p.members[q.first + m]].nblocks;
+      if (blocks > most) most = blocks;
+    }
+    b->query_cluster = query_cluster_size(most);
+  }
   b->sweep_launches = (uint32_t) p.groups.size();
   uint32_t tp_launches = 0;
   for (const SweepGroup& g : p.groups) tp_launches += g.tpf ? (g.params.packed ? 2u : 1u) : 0u;
@@ -288,7 +301,7 @@ static int enqueue_step(lgb_batch* b) {
   if (b->timing) cudaEventRecord(b->ev2, b->stream);
   if (!fork && post_kernels()) return 1;
   e = launch_queries(t.lists, t.queries, t.members, (uint32_t) p.queries.size(), b->abs_gate,
-                     t.results, ps);
+                     t.results, ps, b->query_cluster);
   if (e != cudaSuccess) { set_error("launch_queries", e); return 1; }
   if (fork) {
     e = cudaEventRecord(b->ev_join, b->side);
@@ -462,6 +475,7 @@ struct lgb_listquery {
   QueryResult* d_result = nullptr;
   QueryResult* h_result = nullptr;   // pinned
   double abs_gate = 0.0;
+  uint32_t cluster = 1;
 };
 
 extern "C" LG_EXPORT lgb_listquery* lgb_listquery_create(const double* const* z, const uint32_t* nz,
@@ -475,6 +489,11 @@ extern "C" LG_EXPORT lgb_listquery* lgb_listquery_create(const double* const* z,
   std::vector<uint32_t> hm(n);
   for (size_t i = 0; i < n; ++i) { hl[i] = BlockList{z[i], st[i], nz[i], nst[i]}; hm[i] = (uint32_t) i; }
   std::vector<Query> hq(1, Query{0, (uint32_t) n});
+  {
+    uint64_t blocks = 0;
+    for (size_t i = 0; i < n; ++i) blocks += nz[i];
+    q->cluster = query_cluster_size(blocks);
+  }
   bool ok = upload(hl, &q->d_lists, q->stream) && upload(hm, &q->d_members, q->stream) &&
             upload(hq, &q->d_query, q->stream) && dalloc(&q->d_result, 1, q->stream);
   if (ok) {
@@ -488,7 +507,7 @@ extern "C" LG_EXPORT lgb_listquery* lgb_listquery_create(const double* const* z,
 
 extern "C" LG_EXPORT int lgb_listquery_run(lgb_listquery* q) {
   cudaError_t e = launch_queries(q->d_lists, q->d_query, q->d_members, 1, q->abs_gate, q->d_result,
-                                 q->stream);
+                                 q->stream, q->cluster);
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(q->h_result, q->d_result, sizeof(QueryResult), cudaMemcpyDeviceToHost,
                         q->stream);

@@ -9,6 +9,7 @@
 //   query_kernel    gated integrated loudness and loudness range over a set
 //                   of tracks (ebur128_loudness_global[_multiple],
 //                   ebur128_loudness_range[_multiple]: scan.c:294,297,383,388)
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -703,6 +704,10 @@ struct QueryView {
   const BlockList* s_lists;   // shared copies (cached)
   const uint32_t* s_zoff;     // [count + 1]
   const uint32_t* s_stoff;    // [count + 1]
+  // how the elements are dealt out: this thread takes first, first + stride, ...
+  // (one CTA: threadIdx.x / blockDim.x; a cluster sharing the gating blocks:
+  // rank * blockDim.x + threadIdx.x / cluster size * blockDim.x)
+  uint32_t first, stride;
 };
 
 // f(e, g) for every gating block energy (ST = false) or short-term energy
@@ -719,12 +724,12 @@ __device__ __forceinline__ void for_each_energy(const QueryView& v, F f) {
     // a thread's elements come in increasing order, so its member index only
     // ever moves forward: no search per element
     uint32_t m = 0;
-    for (uint32_t g0 = threadIdx.x; g0 < total; g0 += blockDim.x * kQueryBatch) {
+    for (uint32_t g0 = v.first; g0 < total; g0 += v.stride * kQueryBatch) {
       const double* src[kQueryBatch];
       double e[kQueryBatch];
 #pragma unroll
       for (int u = 0; u < kQueryBatch; ++u) {
-        const uint32_t g = g0 + u * blockDim.x;
+        const uint32_t g = g0 + u * v.stride;
         const uint32_t gc = g < total ? g : total - 1;
         while (off[m + 1] <= gc) ++m;            // off[count] = total > gc: stops in range
         src[u] = (ST ? v.s_lists[m].st : v.s_lists[m].z) + (gc - off[m]);
@@ -733,7 +738,7 @@ __device__ __forceinline__ void for_each_energy(const QueryView& v, F f) {
       for (int u = 0; u < kQueryBatch; ++u) e[u] = *src[u];
 #pragma unroll
       for (int u = 0; u < kQueryBatch; ++u) {
-        const uint32_t g = g0 + u * blockDim.x;
+        const uint32_t g = g0 + u * v.stride;
         if (g < total) f(e[u], g);
       }
     }
@@ -743,7 +748,7 @@ __device__ __forceinline__ void for_each_energy(const QueryView& v, F f) {
       const BlockList bl = v.lists[v.mem[m]];
       const double* p = ST ? bl.st : bl.z;
       const uint32_t n = ST ? bl.nst : bl.nz;
-      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) f(p[i], base + i);
+      for (uint32_t i = v.first; i < n; i += v.stride) f(p[i], base + i);
       base += n;
     }
   }
@@ -811,18 +816,43 @@ __device__ void select_two(const QueryView& v, const double* s_st, uint32_t n_st
   *out_hi = __longlong_as_double((long long) st->prefix[1]);
 }
 
+// One query per thread-block CLUSTER.  The gating blocks (the long lists: 10 per
+// second of audio) are dealt out over the cluster's CTAs, whose partial sums
+// meet in rank 0's shared memory (DSMEM); the short-term energies (1 per
+// second) and the final result are rank 0's alone.  Cluster size 1 is the
+// plain one-CTA query.
+constexpr int kMaxQueryCluster = 8;
+
+__device__ SumCount cluster_sum_count(cooperative_groups::cluster_group& cluster, SumCount mine,
+                                      SumCount* xch /* [kMaxQueryCluster], this round's buffer */) {
+  const unsigned R = cluster.num_blocks();
+  if (R == 1) return mine;
+  if (threadIdx.x == 0) cluster.map_shared_rank(xch, 0)[cluster.block_rank()] = mine;
+  cluster.sync();
+  const SumCount* all = cluster.map_shared_rank(xch, 0);
+  SumCount t{0.0, 0ull};
+  for (unsigned r = 0; r < R; ++r) { t.s += all[r].s; t.n += all[r].n; }   // fixed order
+  return t;
+}
+
 __global__ void __launch_bounds__(kQueryThreads)
 query_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ queries,
              const uint32_t* __restrict__ members, double abs_gate,
              QueryResult* __restrict__ results) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned R = cluster.num_blocks(), rk = cluster.block_rank();
+  const unsigned qi = blockIdx.x / R;
+  if (R > 1) cluster.sync();      // every CTA of the cluster runs before its shared memory is touched
   __shared__ SumCount scratch[32];
+  __shared__ SumCount xch[2][kMaxQueryCluster];
   __shared__ unsigned int hist[512];
   __shared__ unsigned int wsum[16];
   __shared__ SelectState sel;
   __shared__ BlockList s_lists[kQueryCache];
   __shared__ uint32_t s_zoff[kQueryCache + 1], s_stoff[kQueryCache + 1];
   __shared__ double s_st[kStCache];
-  const Query q = queries[blockIdx.x];
+  const Query q = queries[qi];
   QueryView v;
   v.lists = lists; v.mem = members + q.first; v.count = q.count;
   v.cached = q.count <= (uint32_t) kQueryCache;
@@ -844,25 +874,35 @@ query_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ quer
   res.loudness = -HUGE_VAL; res.range = 0.0; res.rel_thr = 0.0;
   res.sum1 = res.sum2 = 0.0; res.n1 = res.n2 = res.nst = 0;
 
-  // ---- integrated loudness: absolute gate, then relative gate at -10 LU
+  // ---- integrated loudness: absolute gate, then relative gate at -10 LU;
+  //      the blocks are shared out over the cluster
+  v.first = rk * blockDim.x + threadIdx.x;
+  v.stride = R * blockDim.x;
   double s = 0.0;
   unsigned long long n = 0;
   for_each_energy<false>(v, [&](double e, uint32_t) { if (e >= abs_gate) { s += e; ++n; } });
-  SumCount a = block_sum_count(s, n, scratch);
+  SumCount a = cluster_sum_count(cluster, block_sum_count(s, n, scratch), xch[0]);
   res.sum1 = a.s; res.n1 = a.n;
-  if (a.n) {
+  SumCount b{0.0, 0ull};
+  if (a.n) {                                   // cluster-uniform
     const double thr = a.s / (double) a.n * 0.1;
     res.rel_thr = thr;
     s = 0.0; n = 0;
     for_each_energy<false>(v, [&](double e, uint32_t) { if (e >= abs_gate && e >= thr) { s += e; ++n; } });
-    SumCount b = block_sum_count(s, n, scratch);
+    b = cluster_sum_count(cluster, block_sum_count(s, n, scratch), xch[1]);
     res.sum2 = b.s; res.n2 = b.n;
     if (b.n) res.loudness = energy_to_lufs(b.s / (double) b.n);
   }
+  if (R > 1) {
+    cluster.sync();                            // everyone has read rank 0's exchange buffers
+    if (rk != 0) return;
+  }
 
-  // ---- loudness range: -20 LU relative gate on short-term energies, then the
-  //      10th / 95th percentile by rank.  The energies are staged in shared
-  //      memory during the first pass when they fit.
+  // ---- loudness range (rank 0): -20 LU relative gate on short-term energies,
+  //      then the 10th / 95th percentile by rank.  The energies are staged in
+  //      shared memory during the first pass when they fit.
+  v.first = threadIdx.x;
+  v.stride = blockDim.x;
   const bool st_cached = v.cached && s_stoff[q.count] <= (uint32_t) kStCache;
   const uint32_t n_st = st_cached ? s_stoff[q.count] : 0u;
   s = 0.0; n = 0;
@@ -890,7 +930,7 @@ query_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ quer
       res.range = energy_to_lufs(hi) - energy_to_lufs(lo);
     }
   }
-  if (threadIdx.x == 0) results[blockIdx.x] = res;
+  if (threadIdx.x == 0) results[qi] = res;
 }
 
 cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t stream) {
@@ -912,12 +952,31 @@ cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t 
   return cudaGetLastError();
 }
 
+uint32_t query_cluster_size(uint64_t max_gating_blocks) {
+  // one more CTA per 32 k gating blocks of the largest query (about an hour of audio)
+  uint64_t r = max_gating_blocks / 32768u;
+  return (uint32_t) (r < 1 ? 1 : (r > (uint64_t) kMaxQueryCluster ? kMaxQueryCluster : r));
+}
+
 cudaError_t launch_queries(const BlockList* lists, const Query* queries, const uint32_t* members,
                            uint32_t nqueries, double abs_gate, QueryResult* results,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, uint32_t cluster) {
   if (!nqueries) return cudaSuccess;
-  query_kernel<<<nqueries, kQueryThreads, 0, stream>>>(lists, queries, members, abs_gate, results);
-  return cudaGetLastError();
+  if (cluster < 1) cluster = 1;
+  if (cluster > (uint32_t) kMaxQueryCluster) cluster = kMaxQueryCluster;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nqueries * cluster);
+  cfg.blockDim = dim3(kQueryThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = cluster;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, query_kernel, lists, queries, members, abs_gate, results);
 }
 
 }  // namespace lg

@@ -51,8 +51,11 @@ cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t 
 cudaError_t launch_stream_blocks(const double* eslot, int s100, uint64_t nblocks, uint64_t nst,
                                  double* zblock, double* zst, cudaStream_t stream);
 // Gated loudness + range for `nqueries` queries; all pointers are device memory.
+// `cluster` = CTAs per query (thread-block cluster sharing the gating blocks of a
+// query); query_cluster_size() picks it from the largest query's block count.
 cudaError_t launch_queries(const BlockList* lists, const Query* queries, const uint32_t* members,
                            uint32_t nqueries, double abs_gate, QueryResult* results,
-                           cudaStream_t stream);
+                           cudaStream_t stream, uint32_t cluster = 1);
+uint32_t query_cluster_size(uint64_t max_gating_blocks);
 
 }  // namespace lg

@@ -201,6 +201,24 @@ def test_sliding_window_queries(product, oracle, seconds):
         assert lu_diff(g, w) <= GOAL_LU
 
 
+@pytest.mark.parametrize("nslots", [29, 3000, 70000, 400000])
+def test_slots_query_sizes(product, nslots):
+    """lgb_slots_query against a numpy restatement, from a list too short for a
+    short-term block up to eleven hours of slots (the gating blocks of a large
+    query are shared out over a thread-block cluster; short-term energies beyond
+    the shared-memory cache come from global memory)."""
+    import torch
+    from loudgain_b200 import engine
+    from tests.helpers import gate_slots
+    rng = np.random.default_rng(nslots)
+    # 100 ms slot energy sums at 48 kHz: programme around -20 LUFS with quiet and silent stretches
+    level = rng.choice([0.0, 1e-9, 1e-3, 1e-2, 3e-2], size=nslots, p=[0.05, 0.1, 0.25, 0.4, 0.2])
+    slots = level * rng.uniform(0.5, 1.5, nslots) * 4800
+    m = engine.slots_query(torch.from_numpy(slots).cuda(), 48000)
+    loud, rng_lu = gate_slots(slots, 48000)
+    assert lu_diff(m.loudness, loud) < 1e-9 and abs(m.range - rng_lu) < 1e-9
+
+
 def test_threaded_scanners_match_single_thread(product):
     """Different threads feed different states at the same time (states are
     independent, as in libebur128): the results do not depend on it, also with
