@@ -17,8 +17,9 @@
 // (VIMNMX3.S16x2, two frames per instruction).
 //
 // True peak: the sweep leaves max |x| per (lane, iteration pair, channel) as a
-// 16-bit code; truepeak_pair_kernel evaluates the polyphase FIR only on the
-// pairs whose bound ||c||_1 * max|x| exceeds the channel's final sample peak.
+// 16-bit code; tp_scan_pair_kernel + tp_eval_pair_kernel evaluate the polyphase
+// FIR only on the pairs whose bound ||c||_1 * max|x| exceeds the channel's
+// final sample peak.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -272,7 +273,7 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
   const long long row_byte0 = geo.a * (long long) fb + (chl << 4);
   const long long track_bytes = frames * (long long) fb;
   const bool interior = ww.interior != 0;
-  const bool coop = STEREO && interior;
+  [[maybe_unused]] const bool coop = STEREO && interior;
   const uint32_t ncopy = P.kcopies;
   const uint32_t sm_base = (uint32_t) __cvta_generic_to_shared(sm);
   const uint32_t dst_row = pin(sm_base + slot * P.row_stride + (chl << 4));
@@ -469,13 +470,10 @@ cudaError_t launch_sweep_pair(const SweepParams& p, uint32_t format, int tpf, cu
 // polyphase output cannot exceed ||c||_1 * max|x| over its taps' window; the
 // channel's true peak is at least its sample peak (final by now).  So only
 // pairs whose bound (over the pair and the pair before it, which holds the
-// taps' history) exceeds the channel's current peak can matter -- a few
-// percent of programme material.  Warps are autonomous: a work item is a run
-// of consecutive pairs of one sweep warp, scanning lane = sweep lane.  Pairs
-// that can still matter go into the warp's queue as (track, channel, first
-// frame) and are evaluated 32 at a time, one per lane, re-reading their
-// frames from the PCM (L2 / HBM).  The result is identical to evaluating
-// every frame.
+// taps' history) exceeds the channel's sample peak can matter -- a few percent
+// of programme material.  They are collected in a queue and evaluated one per
+// thread, re-reading their frames from the PCM (L2 / HBM).  The result is
+// identical to evaluating every frame.
 
 constexpr int kTp2Threads = 128;
 
