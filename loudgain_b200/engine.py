@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass, field
-from typing import Sequence
+from collections.abc import Sequence
 
 import numpy as np
 
@@ -53,6 +53,28 @@ _RESULT_DTYPE = np.dtype([("loudness", "<f8"), ("range", "<f8"), ("rel_threshold
                           ("sum_abs", "<f8"), ("sum_rel", "<f8"), ("n_abs", "<u8"), ("n_rel", "<u8"),
                           ("n_shortterm", "<u8")])
 _NO_PEAKS = np.zeros(0)
+
+class _Results(Sequence):
+    """Per-track (or per-album) results of one fetch; Measurement objects are
+    built on access."""
+
+    def __init__(self, rows, sp, tp, offsets):
+        self._rows, self._sp, self._tp, self._off = rows, sp, tp, offsets
+
+    def __len__(self):
+        return len(self._rows)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        row = self._rows[i].item()
+        if self._off is None:
+            return Measurement(*row, _NO_PEAKS, _NO_PEAKS)
+        lo, hi = self._off[i], self._off[i + 1]
+        return Measurement(*row, self._sp[lo:hi], self._tp[lo:hi])
+
 
 _lib = None
 
@@ -125,6 +147,7 @@ class Batch:
         self._tres = (_Result * max(n, 1))()
         self._ares = (_Result * max(nalb, 1))()
         self._npk = sum(self.channels)
+        self._offsets = np.concatenate([[0], np.cumsum(self.channels)]).astype(np.int64)
         self._sp = np.zeros(max(self._npk, 1))
         self._tp = np.zeros(max(self._npk, 1))
         self._spp = self._sp.ctypes.data_as(C.c_void_p)
@@ -158,15 +181,13 @@ class Batch:
         if L.lgb_batch_fetch(self._h, tres, ares, self._spp, self._tpp):
             raise RuntimeError("lgb_batch_fetch failed: " + _err(L))
 
-        # one C-level pass over the result structs, one copy of the peaks
-        rows = np.frombuffer(tres, dtype=_RESULT_DTYPE, count=self.ntracks).tolist()
-        spc, tpc = sp.copy(), tp.copy()
-        out_t, off = [], 0
-        for row, ch in zip(rows, self.channels):
-            out_t.append(Measurement(*row, spc[off:off + ch], tpc[off:off + ch]))
-            off += ch
-        arows = np.frombuffer(ares, dtype=_RESULT_DTYPE, count=self.nalbums).tolist()
-        return out_t, [Measurement(*row, _NO_PEAKS, _NO_PEAKS) for row in arows]
+        # fetch() sits between two steps of a repeatedly run batch, where host
+        # time is GPU idle time: snapshot the raw results (three small copies)
+        # and build Measurement objects only for the entries that are looked at
+        rows = np.frombuffer(tres, dtype=_RESULT_DTYPE, count=self.ntracks).copy()
+        arows = np.frombuffer(ares, dtype=_RESULT_DTYPE, count=self.nalbums).copy()
+        return (_Results(rows, sp.copy(), tp.copy(), self._offsets),
+                _Results(arows, None, None, None))
 
     def blocks(self, track: int, kind: int = 0) -> np.ndarray:
         """Block energies of one track, copied to the host (0 = 400 ms gating
