@@ -343,10 +343,31 @@ def gpu_arm(args):
         assert abs(out[i].track_loudness - tres[i].loudness) < 1e-9, "e2e and resident paths disagree"
     assert abs(out[0].album_loudness - ares[0].loudness) < 1e-9
 
+    # ---- the same album as float32 (the ebur128_add_frames_float layout: 4 B per
+    # sample, where the sweep is bound by HBM rather than by instruction dispatch)
+    f32_ms = None
+    launches = batch.kernel_launches
+    rates = [r for _, r in album]
+    if world == 1:
+        batch.close()
+        del album, batch
+        torch.cuda.empty_cache()
+        falbum = make_album(dev, rank, "f32")
+        fbatch = engine.Batch(falbum, [0] * len(falbum), stream)
+        for _ in range(args.warmup):
+            fbatch.run(); fbatch.fetch()
+        L.lgb_batch_enable_timing(fbatch._h, 1)
+        for _ in range(args.steps):
+            fbatch.run(); fbatch.fetch()
+        f32_ms = L.lgb_batch_sweep_ms(fbatch._h)
+        f32_bytes = sum(t.numel() * t.element_size() for t, _ in falbum)
+        fbatch.close()
+        del falbum
+
     if rank == 0:
         hbm, src = _peaks()
         achieved = samples * 2 / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None
-        cpu = cpu_baseline_leg([h.numpy() for h in host], [r for _, r in album])
+        cpu = cpu_baseline_leg([h.numpy() for h in host], rates)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -370,12 +391,17 @@ def gpu_arm(args):
                          if sweep_ms > 0 else None,
                          "peak_source": src,
                          "algorithmic_bytes": "2 B per S16 sample, read once (SURVEY 8d)"},
+            "roofline_float_input": None if not f32_ms else {
+                "bound": "hbm", "achieved": f32_bytes / (f32_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                "frac": f32_bytes / (f32_ms * 1e-3) / 1e9 / hbm, "kernel": "sweep_pair_kernel<F32 stereo>",
+                "kernel_ms": f32_ms, "algorithmic_bytes": "4 B per float sample, read once (SURVEY 8d)",
+                "note": "same album as float32 PCM; informational, the metric's workload is the S16 album"},
             "cpu_baseline": cpu,
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pcm_bytes,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "scanner_threads": threads,
                     "single_thread_value": e2e_single},
-            "gpu_launches": batch.kernel_launches * args.steps,
+            "gpu_launches": launches * args.steps,
             "album_loudness": ares[0].loudness, "album_range": ares[0].range,
             "merged_album_loudness": merged.loudness if merged else None,
             "host_cores": os.cpu_count(),
@@ -383,8 +409,8 @@ def gpu_arm(args):
         print(json.dumps(line), flush=True)
     if merge is not None:
         merge.close()
-    batch.close()
     if world > 1:
+        batch.close()
         dist.destroy_process_group()
 
 

@@ -1,5 +1,7 @@
 // lg_batch.cu -- host layer of the batch API (include/ebur128_b200.h): plan
 // upload, workspace, launch sequencing on one CUDA stream, result fetch.
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -90,6 +92,7 @@ struct lgb_batch {
   ChunkRec* d_recs = nullptr;
   uint32_t* d_peaks = nullptr;
   uint32_t* d_mrec = nullptr;
+  unsigned char* d_tmaps = nullptr;    // tensor maps of the TMA-staged groups, kTmaMaxM x 128 B per track
   uint64_t* d_tpq = nullptr;           // candidate queue of the packed true-peak pass
   double* d_echunk = nullptr;
   double* d_eslot = nullptr;
@@ -130,6 +133,67 @@ struct lgb_batch {
   }
 };
 
+// Tensor maps for the groups the planner gave 2-D TMA staging (lg_common.h:
+// tma_class): per track and chunk class r one map over rows of m*L frames.
+static bool make_tensor_maps(lgb_batch* b) {
+  const Plan& p = b->plan;
+  bool any = false;
+  for (const SweepGroup& g : p.groups) any = any || g.params.tma_m != 0;
+  if (!any) return true;
+  static PFN_cuTensorMapEncodeTiled encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess || !fn) {
+      set_error("cuTensorMapEncodeTiled is not available");
+      return false;
+    }
+    encode = (PFN_cuTensorMapEncodeTiled) fn;
+  }
+  std::vector<CUtensorMap> maps(p.tracks.size() * kTmaMaxM);
+  memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+  for (const SweepGroup& g : p.groups) {
+    const SweepParams& sp = g.params;
+    if (!sp.tma_m) continue;
+    const long long m = sp.tma_m, mL = m * sp.L;
+    const uint32_t wpf = sp.fb / 4u;                        // 32-bit words per frame
+    for (uint32_t w = 0; w < g.nwarps; ++w) {
+      const WarpWork& ww = p.work[g.first_warp + w];
+      if (ww.interior != 2 || maps[(size_t) ww.track * kTmaMaxM].opaque[0]) continue;   // done
+      const Track& tr = p.tracks[ww.track];
+      for (int r = 0; r < (int) m; ++r) {
+        const TmaClass tc = tma_class(sp.L, sp.W, (int) tr.aq, (int) m, r);
+        const long long nrows = ((long long) tr.frames - tc.base_frame) / mL;
+        if (nrows < 1) continue;
+        const cuuint64_t dims[2] = {(cuuint64_t) (mL * wpf), (cuuint64_t) nrows};
+        const cuuint64_t strides[1] = {(cuuint64_t) (mL * sp.fb)};
+        const cuuint32_t box[2] = {(cuuint32_t) (sp.stage_row_bytes / 4u + kTmaBoxPad), (cuuint32_t) (32 / m)};
+        const cuuint32_t estr[2] = {1, 1};
+        void* base = (void*) ((const unsigned char*) tr.pcm + tc.base_frame * (long long) sp.fb);
+        const CUresult rc = encode(&maps[(size_t) ww.track * kTmaMaxM + r], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2,
+                                   base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) {
+          char msg[96];
+          snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (%d)", (int) rc);
+          set_error(msg);
+          return false;
+        }
+      }
+    }
+  }
+  if (cudaMallocAsync((void**) &b->d_tmaps, maps.size() * sizeof(CUtensorMap), b->stream) != cudaSuccess ||
+      cudaMemcpyAsync(b->d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice,
+                      b->stream) != cudaSuccess ||
+      cudaStreamSynchronize(b->stream) != cudaSuccess) {
+    set_error("tensor map upload failed");
+    return false;
+  }
+  return true;
+}
+
 extern "C" LG_EXPORT const char* lgb_last_error(void) { return g_error.c_str(); }
 
 extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t ntracks, uint32_t nalbums,
@@ -162,6 +226,7 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
   opt.target_tasks = (uint64_t) sms * 2048u;
   if (const char* e = getenv("LOUDGAIN_B200_CHUNKS_PER_SLOT")) opt.force_k = atoi(e);   // tuning
   if (const char* e = getenv("LOUDGAIN_B200_SCALAR_SWEEP")) opt.allow_packed = atoi(e) == 0;
+  if (const char* e = getenv("LOUDGAIN_B200_TMA")) opt.use_tma = atoi(e) != 0;   // 0: cp.async staging only
   build_plan(in.data(), ntracks, nalbums, opt, b->plan);
   const Plan& p = b->plan;
   b->abs_gate = pow(10.0, (-70.0 + 0.691) / 10.0);
@@ -178,6 +243,7 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
             dalloc(&b->d_zblock, p.total_blocks, b->stream) &&
             dalloc(&b->d_zst, p.total_st, b->stream) &&
             dalloc(&b->d_results, (uint64_t) p.queries.size(), b->stream);
+  if (ok) ok = make_tensor_maps(b);
   if (ok) {
     std::vector<BlockList> lists(p.tracks.size());
     for (size_t i = 0; i < p.tracks.size(); ++i) {
@@ -246,6 +312,7 @@ static int enqueue_step(lgb_batch* b) {
     SweepParams sp = g.params;
     sp.tracks = t.tracks; sp.work = t.work + g.first_warp; sp.recs = t.recs; sp.peaks = t.peaks;
     sp.mrec = b->d_mrec + g.mrec_base;
+    sp.tmaps = b->d_tmaps;
     e = sp.packed ? launch_sweep_pair(sp, g.format, g.tpf, b->stream)
                   : launch_sweep(sp, g.format, g.tpf, b->stream);
     if (e != cudaSuccess) { set_error("launch_sweep", e); return 1; }
@@ -534,7 +601,7 @@ extern "C" LG_EXPORT void lgb_batch_destroy(lgb_batch* b) {
   if (!b) return;
   if (b->ev0) { cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); cudaEventDestroy(b->ev2); }
   void* const mem[] = {b->d_tracks, b->d_coefs, b->d_work, b->d_queries, b->d_members, b->d_lists,
-                       b->d_recs, b->d_peaks, b->d_mrec, b->d_tpq, b->d_echunk, b->d_eslot, b->d_zblock, b->d_zst,
+                       b->d_recs, b->d_peaks, b->d_mrec, b->d_tpq, b->d_tmaps, b->d_echunk, b->d_eslot, b->d_zblock, b->d_zst,
                        b->d_results};
   if (b->h_results) cudaStreamSynchronize(b->stream);   // a run may still be writing the mirrors
   for (void* m : mem) if (m) cudaFreeAsync(m, b->stream);

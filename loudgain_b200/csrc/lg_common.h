@@ -198,8 +198,41 @@ struct SweepParams {
   uint32_t* mrec;
   uint32_t* tp_ticket;     // counter of the group's true-peak pass (zeroed per run): work
                            // items drawn (scalar pass) / candidates queued (packed pass)
+  // 2-D TMA staging (packed stereo sweep, WarpWork::interior == 2): m tensor
+  // maps per track (one per chunk class j mod m), 8 slots of 128 bytes each
+  const void* tmaps;
+  uint32_t tma_m;
   uint64_t* tp_queue;        // packed pass: candidate queue, 2 entries per mrec word at most
 };
+
+// ---- 2-D TMA view of a track -------------------------------------------------
+// Chunks j = i*m + r of one class r start m*L frames apart, a multiple of 16
+// bytes when m is chosen so, and every lane of the class has the same
+// alignment offset.  So class r is a 2-D tensor: row i = the m*L frames from
+// lane-local frame 0 of chunk i*m + r.  Class 0 starts W frames before the
+// track; it is shifted by one row (row i - 1 holds chunk i*m).
+constexpr int kTmaMaxM = 8;
+constexpr int kTmaBoxPad = 4;       // 32-bit words appended to a box row (odd 16-byte pitch in shared memory)
+
+struct TmaClass {
+  long long base_frame;   // track frame of word 0 of row 0
+  int shift;              // chunk i*m + r lives in row i - shift
+};
+
+LG_BOTH int tma_interleave(int L, int aq) {
+  int m = 2;
+  while (m < kTmaMaxM && ((long long) m * L) % aq) m <<= 1;
+  return ((long long) m * L) % aq ? 0 : m;
+}
+
+LG_BOTH TmaClass tma_class(int L, int W, int aq, int m, int r) {
+  const long long s = (long long) r * L - W;
+  const long long a = s & ~(long long) (aq - 1);       // as lane_geometry: floor, also for s < 0
+  TmaClass c;
+  c.shift = a < 0 ? 1 : 0;
+  c.base_frame = a + (c.shift ? (long long) m * L : 0);
+  return c;
+}
 
 // ---- lane geometry ---------------------------------------------------------
 // Chunk j covers track frames [j*L, j*L + L).  Its lane starts filtering from

@@ -222,7 +222,7 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
   constexpr int FMT = pair_format<LAYOUT>();
   constexpr int kPPS = pair_pps((uint32_t) FMT);
   constexpr bool STEREO = LAYOUT == PAIR_S16_STEREO || LAYOUT == PAIR_F32_STEREO;
-  extern __shared__ __align__(16) unsigned char smem_all[];
+  extern __shared__ __align__(128) unsigned char smem_all[];
   const uint32_t wic = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + wic;
@@ -252,7 +252,13 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
   c.pd = c.pw = c.qd = c.qw = bc2(0.0f);
   c.f_lo = W + geo.o;
   c.f_hi = c.f_lo + L;
-  const uint32_t my_row = pin((uint32_t) __cvta_generic_to_shared(sm) + slot * P.row_stride);
+  // 2-D TMA staging (stereo, WarpWork::interior == 2): the warp's chunks of class
+  // r = chunk mod m are consecutive rows of that class's tensor; one box per
+  // class and stage lands them as rows r * (32 / m) ... of the stage buffer.
+  const bool tma = STEREO && ww.interior == 2;
+  const uint32_t tm = STEREO ? P.tma_m : 1u;
+  const uint32_t my_slot = tma ? (lane % tm) * (32u / tm) + lane / tm : slot;
+  const uint32_t my_row = pin((uint32_t) __cvta_generic_to_shared(sm) + my_slot * P.row_stride);
 
   // ---- staging.  Per stage every row receives one contiguous piece of
   // kPPS * 24 frames, moved with 16-byte cp.async copies.
@@ -288,8 +294,44 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
     src_g[g] = pcm + a_row * (long long) fb + (q << 4);
   }
   uint32_t pf_off = 0;
+  // TMA bookkeeping (lane 0 issues): one mbarrier per ring stage behind the ring
+  const uint32_t bar0 = sm_base + P.ring_bytes;
+  uint32_t pf_buf = 0;
+  int pf_x = 0;                                  // first word of the next stage within a row
+  int tma_row[kTmaMaxM];                         // first row of the warp in each class's tensor
+  const unsigned char* tma_map = nullptr;
+  if (tma) {
+    tma_map = reinterpret_cast<const unsigned char*>(P.tmaps) + (size_t) ww.track * kTmaMaxM * 128u;
+#pragma unroll
+    for (int r = 0; r < kTmaMaxM; ++r) {
+      const TmaClass tc = tma_class(L, W, P.aq, (int) tm, r);
+      tma_row[r] = (int) ((ww.first_chunk + (uint32_t) r) / tm) - tc.shift;
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < kPairRing; ++i) mbar_init(bar0 + 8u * i, 1u);
+      mbar_fence_init();
+    }
+    __syncwarp();
+  }
 
   auto prefetch = [&]() {
+    if (tma) {
+      if (lane == 0) {
+        const uint32_t bar = bar0 + 8u * pf_buf;
+        mbar_arrive_expect_tx(bar, P.stage_bytes);
+        const uint32_t dst = sm_base + pf_off;
+        const uint32_t class_bytes = (32u / tm) * P.row_stride;
+#pragma unroll
+        for (int r = 0; r < kTmaMaxM; ++r)
+          if ((uint32_t) r < tm)
+            tma_load_2d(dst + (uint32_t) r * class_bytes, tma_map + r * 128, pf_x, tma_row[r], bar);
+      }
+      pf_x += (int) (P.stage_row_bytes >> 2);
+      pf_off += P.stage_bytes;
+      if (++pf_buf == (uint32_t) kPairRing) { pf_buf = 0; pf_off = 0; }
+      return;
+    }
 #ifdef LG_PAIR_NOLOAD   // ablation: no HBM traffic, compute on whatever is in shared memory
     if (false) {
 #else
@@ -339,10 +381,15 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
   int spx_i = 0, spy_i = 0;
   float spx_f = 0.0f, spy_f = 0.0f;
 
-  uint32_t cs_off = 0;
+  uint32_t cs_off = 0, cs_buf = 0, cs_parity = 0;
   uint32_t pair = 0;
   for (uint32_t s = 0; s < nstages; ++s) {
-    cp_async_wait<kPairRing - 2>();
+    if (tma) {
+      mbar_wait(bar0 + 8u * cs_buf, cs_parity);
+      if (++cs_buf == (uint32_t) kPairRing) { cs_buf = 0; cs_parity ^= 1u; }
+    } else {
+      cp_async_wait<kPairRing - 2>();
+    }
     __syncwarp();                // everyone's data has landed; the previous stage is consumed
     if (s + kPairRing - 1 < nstages) prefetch();
     cp_async_commit();

@@ -73,6 +73,7 @@ struct PlanOptions {
   uint64_t target_tasks = 0;   // about 2048 x SM count; 0 = shortest chunks
   int force_k = 0;             // > 0 pins the chunks per 100 ms slot (tuning / tests)
   bool allow_packed = true;
+  bool use_tma = true;         // 2-D TMA staging for packed stereo groups
 };
 
 // Chunks per 100 ms slot of one track: the longest chunk (a divisor of the
@@ -194,6 +195,16 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, const Plan
     sp.ring_bytes = ring * sp.stage_bytes;
     sp.kcopies = (sp.units + sp.lpc - 1) / sp.lpc;
     sp.warp_smem = sp.ring_bytes;
+    // 2-D TMA staging: stereo, one lane per row, rows of a class 16-byte pitched
+    const bool stereo = packed && t0.channels == 2;
+    const int tma_m = (opt.use_tma && stereo) ? tma_interleave(cs.L, (int) t0.aq) : 0;
+    sp.tma_m = 0;
+    if (tma_m && (sp.units | 1u) == sp.units + 1u &&
+        (long long) tma_m * cs.L >= (long long) ((sp.npairs + pps - 1) / pps) * pps * kPairFrames + 8) {
+      sp.tma_m = (uint32_t) tma_m;
+      // ring, then one mbarrier per stage; TMA destinations are 128-byte aligned
+      sp.warp_smem = (sp.ring_bytes + ring * 8u + 127u) & ~127u;
+    }
     const long long stage_frames = (long long) ((sp.npairs + pps - 1) / pps) * pps * kPairFrames;
     for (uint32_t i : kv.second) {
       const Track& tr = p.tracks[i];
@@ -208,8 +219,22 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, const Plan
           lmin = gl.l_valid;
         }
         const bool interior = g0.a >= 0 && g1.a + stage_frames <= (long long) tr.frames;
+        uint16_t mode = interior ? 1 : 0;
+        if (interior && sp.tma_m) {
+          // every class's rows of this warp must exist in the class's tensor
+          bool ok = true;
+          const long long m = sp.tma_m, mL = m * cs.L;
+          for (int r = 0; r < (int) m && ok; ++r) {
+            const TmaClass tc = tma_class(cs.L, cs.W, (int) tr.aq, (int) m, r);
+            const long long nrows = (long long) tr.frames > tc.base_frame
+                                        ? ((long long) tr.frames - tc.base_frame) / mL : 0;
+            const long long first = ((long long) c + r) / m - tc.shift;
+            ok = first >= 0 && first + 32 / m <= nrows;
+          }
+          if (ok) mode = 2;
+        }
         for (uint32_t cb = 0; cb < (packed ? 1u : tr.channels); cb += 32)
-          p.work.push_back(WarpWork{i, c, lmin, (uint16_t) (interior ? 1 : 0), (uint16_t) cb});
+          p.work.push_back(WarpWork{i, c, lmin, mode, (uint16_t) cb});
       }
     }
     g.nwarps = (uint32_t) p.work.size() - g.first_warp;
