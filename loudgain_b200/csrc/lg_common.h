@@ -202,6 +202,7 @@ struct SweepParams {
   // maps per track (one per chunk class j mod m), 8 slots of 128 bytes each
   const void* tmaps;
   uint32_t tma_m;
+  uint32_t tma_shift;      // bit r: class r's chunks live one row earlier (tma_class)
   uint64_t* tp_queue;        // packed pass: candidate queue, 2 entries per mrec word at most
 };
 

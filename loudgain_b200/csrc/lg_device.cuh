@@ -47,7 +47,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "W_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 4000;\n"   // suspend up to ~4 us per try
       "@p bra D_%=;\n"
       "bra W_%=;\n"
       "D_%=:\n"

@@ -9,8 +9,11 @@
 // independent IEEE FMAs per issue slot, the broadcast filter constant coming
 // from a uniform register).  The scalar kernel is bound by instruction issue
 // (ncu: 84 % of the issue slots busy at 41 % of HBM bandwidth); packing halves
-// the issue slots of the 11 FMA-pipe operations per sample, so the FMA pipe
-// itself (128 lanes per clock and SM) becomes the limit.
+// the issue slots of the 11 FMA-pipe operations per sample.
+//
+// Stereo rows reach shared memory as 2-D TMA tiles (cp.async.bulk.tensor.2d,
+// one box per chunk class and stage, issued by one elected lane, completion on
+// an mbarrier); track ends and other channel counts use 16-byte cp.async.
 //
 // A 16-bit stereo frame is one 32-bit word, so the sample peak of both
 // channels is tracked on the raw words with packed 16-bit integer min/max
@@ -303,10 +306,8 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
   if (tma) {
     tma_map = reinterpret_cast<const unsigned char*>(P.tmaps) + (size_t) ww.track * kTmaMaxM * 128u;
 #pragma unroll
-    for (int r = 0; r < kTmaMaxM; ++r) {
-      const TmaClass tc = tma_class(L, W, P.aq, (int) tm, r);
-      tma_row[r] = (int) ((ww.first_chunk + (uint32_t) r) / tm) - tc.shift;
-    }
+    for (int r = 0; r < kTmaMaxM; ++r)
+      tma_row[r] = (int) ((ww.first_chunk + (uint32_t) r) / tm) - (int) ((P.tma_shift >> r) & 1u);
     if (lane == 0) {
 #pragma unroll
       for (int i = 0; i < kPairRing; ++i) mbar_init(bar0 + 8u * i, 1u);

@@ -202,6 +202,9 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, const Plan
     if (tma_m && (sp.units | 1u) == sp.units + 1u &&
         (long long) tma_m * cs.L >= (long long) ((sp.npairs + pps - 1) / pps) * pps * kPairFrames + 8) {
       sp.tma_m = (uint32_t) tma_m;
+      sp.tma_shift = 0;
+      for (int r = 0; r < tma_m; ++r)
+        if (tma_class(cs.L, cs.W, (int) t0.aq, tma_m, r).shift) sp.tma_shift |= 1u << r;
       // ring, then one mbarrier per stage; TMA destinations are 128-byte aligned
       sp.warp_smem = (sp.ring_bytes + ring * 8u + 127u) & ~127u;
     }

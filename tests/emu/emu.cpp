@@ -285,3 +285,51 @@ extern "C" void emu_plan_sizes(const lgb_track* tracks, size_t ntracks, uint64_t
   *total_blocks = p.total_blocks;
   *total_st = p.total_st;
 }
+
+// Checks the 2-D TMA view of the plan against the lane geometry: for every
+// warp the planner marked for TMA staging (WarpWork::interior == 2) and every
+// lane, the tensor row of the lane's chunk must start at the lane's own frame
+// 0 and must lie inside the class's tensor.  Returns the number of TMA warps,
+// or -1 - (index of the first bad warp).
+extern "C" long long emu_check_tma_view(const lgb_track* tracks, size_t ntracks, uint64_t target_tasks,
+                                        long long* total_warps) {
+  std::vector<TrackIn> in(ntracks);
+  for (size_t i = 0; i < ntracks; ++i)
+    in[i] = TrackIn{tracks[i].pcm, tracks[i].frames, tracks[i].channels, tracks[i].samplerate,
+                    tracks[i].format, LGB_NO_ALBUM, nullptr, tracks[i].lead_in};
+  Plan p;
+  PlanOptions opt;
+  opt.target_tasks = target_tasks;
+  build_plan(in.data(), ntracks, 0, opt, p);
+  long long ntma = 0;
+  *total_warps = (long long) p.work.size();
+  for (const SweepGroup& g : p.groups) {
+    const SweepParams& sp = g.params;
+    for (uint32_t w = 0; w < g.nwarps; ++w) {
+      const WarpWork& ww = p.work[g.first_warp + w];
+      if (ww.interior != 2) continue;
+      if (!sp.tma_m || sp.cpw != 32) return -1 - (long long) (g.first_warp + w);
+      const Track& tr = p.tracks[ww.track];
+      const long long m = sp.tma_m, mL = m * sp.L;
+      const long long stage_words = sp.stage_row_bytes / 4, wpf = sp.fb / 4;
+      const long long nstages = (sp.npairs + pair_pps(g.format) - 1) / pair_pps(g.format);
+      for (uint32_t lane = 0; lane < 32; ++lane) {
+        const long long chunk = ww.first_chunk + lane;
+        const int r = (int) (chunk % m);
+        const TmaClass tc = tma_class(sp.L, sp.W, (int) tr.aq, (int) m, r);
+        if (tc.shift != (int) ((sp.tma_shift >> r) & 1u)) return -1 - (long long) (g.first_warp + w);
+        const long long row = chunk / m - tc.shift;
+        const long long nrows = ((long long) tr.frames - tc.base_frame) / mL;
+        const LaneGeom geo = lane_geometry((long long) tr.frames, sp.L, sp.W, (int) tr.aq, chunk);
+        const bool ok = row >= 0 && row < nrows && tc.base_frame >= 0 &&
+                        (tc.base_frame * (long long) sp.fb) % 16 == 0 && (mL * sp.fb) % 16 == 0 &&
+                        tc.base_frame + row * mL == geo.a &&                       // row starts at the lane's frame 0
+                        (nstages * stage_words + kTmaBoxPad) <= mL * wpf &&          // boxes stay inside the row
+                        lane / 1 == lane;
+        if (!ok) return -1 - (long long) (g.first_warp + w);
+      }
+      ++ntma;
+    }
+  }
+  return ntma;
+}

@@ -183,3 +183,28 @@ def test_time_segments_with_lead_in(oracle):
         np.testing.assert_array_equal(sp, o["sample_peak"])
         assert rel_diff(tp, o["true_peak"]) <= TOL_TP_REL
         np.testing.assert_array_equal(tps, tp)
+
+
+@pytest.mark.parametrize("rate,seconds,dtype", [(44100, 61.3, np.int16), (48000, 33.0, np.int16),
+                                              (96000, 20.0, np.float32), (22050, 45.0, np.float32),
+                                              (44100, 0.9, np.int16)])
+def test_tma_view_matches_lane_geometry(rate, seconds, dtype):
+    """The 2-D tensor view the stereo sweep stages through (lg_common.h: tma_class;
+    maps built in lg_batch.cu) against the lane geometry, on the host: every
+    TMA-staged warp's rows start at the lanes' own frame 0, are 16-byte pitched
+    and lie inside the track; all but the first and last warps of a long track
+    qualify."""
+    import ctypes as C
+    from tests.helpers import LgbTrack, build_emu
+    lib = C.CDLL(build_emu())
+    lib.emu_check_tma_view.restype = C.c_longlong
+    n = int(rate * seconds)
+    pcm = np.zeros((n, 2), dtype=dtype)
+    arr = (LgbTrack * 1)(LgbTrack(pcm.ctypes.data, n, 2, rate, 0 if dtype == np.int16 else 1,
+                                  0xffffffff, None, 0))
+    total = C.c_longlong()
+    for tasks in (0, 148 * 2048):
+        ntma = lib.emu_check_tma_view(arr, C.c_size_t(1), C.c_uint64(tasks), C.byref(total))
+        assert ntma >= 0, f"warp {-1 - ntma} has an inconsistent tensor view"
+        if seconds > 10:
+            assert total.value - 3 <= ntma <= total.value - 1
