@@ -313,6 +313,7 @@ static int enqueue_step(lgb_batch* b) {
     sp.tracks = t.tracks; sp.work = t.work + g.first_warp; sp.recs = t.recs; sp.peaks = t.peaks;
     sp.mrec = b->d_mrec + g.mrec_base;
     sp.tmaps = b->d_tmaps;
+    sp.tp_queue = b->d_tpq + 2 * g.mrec_base;
     e = sp.packed ? launch_sweep_pair(sp, g.format, g.tpf, b->stream)
                   : launch_sweep(sp, g.format, g.tpf, b->stream);
     if (e != cudaSuccess) { set_error("launch_sweep", e); return 1; }
@@ -458,6 +459,18 @@ extern "C" LG_EXPORT int lgb_batch_wait_blocks(lgb_batch* b, void* cuda_stream) 
   if (e != cudaSuccess) { set_error("lgb_batch_wait_blocks", e); return 1; }
   return 0;
 }
+
+#ifdef LG_PAIR_TRACE
+// tuning builds only: the sweep's per-warp trace of group 0 (lg_pair.cu)
+extern "C" LG_EXPORT uint64_t lgb_debug_trace(lgb_batch* b, uint64_t* out, uint64_t cap) {
+  const SweepGroup& g = b->plan.groups[0];
+  const uint64_t n = 2ull * g.nwarps;
+  const uint64_t off = 2ull * g.nwarps * g.params.npairs * 32ull - n;
+  cudaStreamSynchronize(b->stream);
+  if (n <= cap) cudaMemcpy(out, b->d_tpq + 2 * g.mrec_base + off, n * 8, cudaMemcpyDeviceToHost);
+  return n;
+}
+#endif
 
 extern "C" LG_EXPORT uint64_t lgb_batch_total_samples(const lgb_batch* b) { return b->plan.total_samples; }
 extern "C" LG_EXPORT uint64_t lgb_batch_peak_count(const lgb_batch* b) { return b->plan.total_peaks; }

@@ -232,6 +232,10 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
   if (warp >= P.nwarps) return;                // whole warps leave; no CTA barrier below
   unsigned char* sm = smem_all + wic * P.warp_smem;
 
+#ifdef LG_PAIR_TRACE     // tuning: per-warp start / end times and SM at the tail of the candidate queue
+  unsigned long long trace_t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace_t0));
+#endif
   const WarpWork ww = P.work[warp];
   const Track& tr = P.tracks[ww.track];
   const int W = P.W, L = P.L;
@@ -466,6 +470,16 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
     v.pd = c.pd.y; v.pw = c.pw.y; v.qd = c.qd.y; v.qw = c.qw.y;
     out[1] = v;
   }
+#ifdef LG_PAIR_TRACE
+  if (lane == 0) {
+    unsigned long long t1; uint32_t smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    uint64_t* tb = P.tp_queue + 2ull * P.nwarps * P.npairs * 32ull - 2ull * P.nwarps;
+    tb[2ull * warp] = trace_t0;
+    tb[2ull * warp + 1] = (t1 - trace_t0) | ((uint64_t) smid << 48);
+  }
+#endif
   // Sample peak: non-negative floats order like their bit patterns.  Reduce
   // over the lanes of the warp that hold the same channel pair.
   const float spx = FMT == FMT_S16 ? (float) spx_i : spx_f;
