@@ -113,6 +113,13 @@ struct lgb_batch {
   // to the true-peak pass on the main stream; joined before the result copy.
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_post = nullptr;
+  // Sweep launch groups after the first go round-robin to these streams, so
+  // that the CTAs of the next group fill the SMs while the previous group's
+  // last work items run out (the groups touch disjoint tracks).
+  static constexpr int kGroupStreams = 3;
+  cudaStream_t gstream[kGroupStreams] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_gfork = nullptr, ev_gjoin[kGroupStreams] = {nullptr, nullptr, nullptr};
+  int ngstreams = 0;
   cudaEvent_t ev_blocks = nullptr;   // block lists of the current run are complete (lgb_batch_wait_blocks)
   double abs_gate = 0.0;
   uint32_t launches = 0, sweep_launches = 0, sms = 148;
@@ -227,6 +234,8 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
   if (const char* e = getenv("LOUDGAIN_B200_CHUNKS_PER_SLOT")) opt.force_k = atoi(e);   // tuning
   if (const char* e = getenv("LOUDGAIN_B200_SCALAR_SWEEP")) opt.allow_packed = atoi(e) == 0;
   if (const char* e = getenv("LOUDGAIN_B200_TMA")) opt.use_tma = atoi(e) != 0;   // 0: cp.async staging only
+  if (const char* e = getenv("LOUDGAIN_B200_TAIL_FRAC")) opt.tail_frac = atof(e);      // tuning
+  if (const char* e = getenv("LOUDGAIN_B200_TAIL_DIV")) opt.tail_div = atoi(e);
   build_plan(in.data(), ntracks, nalbums, opt, b->plan);
   const Plan& p = b->plan;
   b->abs_gate = pow(10.0, (-70.0 + 0.691) / 10.0);
@@ -278,6 +287,18 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
       cudaGetLastError();
       if (b->side) { cudaStreamDestroy(b->side); b->side = nullptr; }
     }
+    // streams for the sweep launch groups after the first (only if there are any)
+    if (p.groups.size() > 1 && cudaEventCreateWithFlags(&b->ev_gfork, cudaEventDisableTiming) == cudaSuccess) {
+      const int want = (int) std::min<size_t>(p.groups.size() - 1, (size_t) lgb_batch::kGroupStreams);
+      for (int j = 0; j < want; ++j) {
+        if (cudaStreamCreateWithFlags(&b->gstream[j], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b->ev_gjoin[j], cudaEventDisableTiming) != cudaSuccess) {
+          cudaGetLastError();
+          break;
+        }
+        b->ngstreams = j + 1;
+      }
+    }
   }
   if (!ok) { lgb_batch_destroy(b); return nullptr; }
   b->sms = (uint32_t) sms;
@@ -308,15 +329,39 @@ static int enqueue_step(lgb_batch* b) {
                                   b->stream);
   if (e != cudaSuccess) { set_error("cudaMemsetAsync(peaks)", e); return 1; }
   if (b->timing) cudaEventRecord(b->ev0, b->stream);
+  const bool gfork = p.groups.size() > 1 && b->ngstreams > 0;
+  if (gfork) {
+    e = cudaEventRecord(b->ev_gfork, b->stream);
+    if (e != cudaSuccess) { set_error("fork(group streams)", e); return 1; }
+  }
+  size_t gidx = 0;
   for (const SweepGroup& g : p.groups) {
     SweepParams sp = g.params;
     sp.tracks = t.tracks; sp.work = t.work + g.first_warp; sp.recs = t.recs; sp.peaks = t.peaks;
     sp.mrec = b->d_mrec + g.mrec_base;
     sp.tmaps = b->d_tmaps;
     sp.tp_queue = b->d_tpq + 2 * g.mrec_base;
-    e = sp.packed ? launch_sweep_pair(sp, g.format, g.tpf, b->stream)
-                  : launch_sweep(sp, g.format, g.tpf, b->stream);
+    cudaStream_t gs = b->stream;
+    if (gfork && gidx > 0) {
+      gs = b->gstream[(gidx - 1) % (size_t) b->ngstreams];
+      if (gidx <= (size_t) b->ngstreams) {          // first use of this stream in the step
+        e = cudaStreamWaitEvent(gs, b->ev_gfork, 0);
+        if (e != cudaSuccess) { set_error("fork(group streams)", e); return 1; }
+      }
+    }
+    ++gidx;
+    if (const char* env = getenv("LOUDGAIN_B200_PAIR_CTAS")) sp.ctas_per_sm = (uint32_t) atoi(env);   // tuning
+    e = sp.packed ? launch_sweep_pair(sp, g.format, g.tpf, gs)
+                  : launch_sweep(sp, g.format, g.tpf, gs);
     if (e != cudaSuccess) { set_error("launch_sweep", e); return 1; }
+  }
+  if (gfork) {
+    const size_t used = std::min<size_t>(p.groups.size() - 1, (size_t) b->ngstreams);
+    for (size_t j = 0; j < used; ++j) {
+      e = cudaEventRecord(b->ev_gjoin[j], b->gstream[j]);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(b->stream, b->ev_gjoin[j], 0);
+      if (e != cudaSuccess) { set_error("join(group streams)", e); return 1; }
+    }
   }
   if (b->timing) { cudaEventRecord(b->ev1, b->stream); b->timed_run_pending = true; }
   // Fork (not in timed runs: those keep everything on the main stream, between
@@ -624,6 +669,11 @@ extern "C" LG_EXPORT void lgb_batch_destroy(lgb_batch* b) {
   if (b->ev_post) cudaEventDestroy(b->ev_post);
   if (b->ev_blocks) cudaEventDestroy(b->ev_blocks);
   if (b->side) cudaStreamDestroy(b->side);
+  if (b->ev_gfork) cudaEventDestroy(b->ev_gfork);
+  for (int j = 0; j < lgb_batch::kGroupStreams; ++j) {
+    if (b->ev_gjoin[j]) cudaEventDestroy(b->ev_gjoin[j]);
+    if (b->gstream[j]) cudaStreamDestroy(b->gstream[j]);
+  }
   if (b->h_results) cudaFreeHost(b->h_results);
   if (b->h_peaks) cudaFreeHost(b->h_peaks);
   delete b;

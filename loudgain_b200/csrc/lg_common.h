@@ -204,6 +204,7 @@ struct SweepParams {
   uint32_t tma_m;
   uint32_t tma_shift;      // bit r: class r's chunks live one row earlier (tma_class)
   uint64_t* tp_queue;        // packed pass: candidate queue, 2 entries per mrec word at most
+  uint32_t ctas_per_sm;      // packed sweep: cap on resident CTAs per SM (0 = the kernel's own limit)
 };
 
 // ---- 2-D TMA view of a track -------------------------------------------------

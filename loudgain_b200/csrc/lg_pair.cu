@@ -100,32 +100,30 @@ __device__ __forceinline__ void iter_warm2(PairCtx& c, const SweepParams& k, con
   c.pd = c.d1; c.pw = c.w2;
 }
 
-// One channel of the lane as the scalar context of lg_sweep.cuh, for the few
-// masked iterations at the chunk edges.
-template <int H>
-__device__ __forceinline__ float pick(const float2 v) { return H ? v.y : v.x; }
-template <int H>
-__device__ __forceinline__ void put(float2& v, float s) { if (H) v.y = s; else v.x = s; }
-
-template <int H>
-__device__ __forceinline__ void masked_half(PairCtx& c, const SweepParams& k, const float2* x2, int f0) {
-  LaneCtx s;
-  s.st.d1 = pick<H>(c.d1); s.st.w1 = pick<H>(c.w1); s.st.w2 = pick<H>(c.w2);
-  s.st.v1 = pick<H>(c.v1); s.st.v2 = pick<H>(c.v2);
-  s.sp = 0.0f;
-  s.yr = pick<H>(c.yr); s.yi = pick<H>(c.yi);
-  s.e0 = H ? c.e0y : c.e0x;
-  s.pd = pick<H>(c.pd); s.pw = pick<H>(c.pw); s.qd = pick<H>(c.qd); s.qw = pick<H>(c.qw);
-  s.f_lo = c.f_lo; s.f_hi = c.f_hi;
-  float x[kIter];
+// lg_sweep.cuh: iter_masked, both channels at once (the lane's two channels
+// share the energy range).  Frames outside [f_lo, f_hi) only advance the
+// filter; the snapshots are taken where the scalar code takes them, and the
+// accumulation is the same FMA sequence, so the sums are bit-identical.
+__device__ __forceinline__ void iter_masked2(PairCtx& c, const SweepParams& k, const float2* x, int f0) {
+  float2 e = bc2(0.0f), sr = bc2(0.0f), si = bc2(0.0f);
+  const int ilo = c.f_lo - f0, ihi = c.f_hi - f0;
 #pragma unroll
-  for (int i = 0; i < kIter; ++i) x[i] = pick<H>(x2[i]);
-  (void) iter_masked(s, k, x, f0);
-  put<H>(c.d1, s.st.d1); put<H>(c.w1, s.st.w1); put<H>(c.w2, s.st.w2);
-  put<H>(c.v1, s.st.v1); put<H>(c.v2, s.st.v2);
-  put<H>(c.yr, s.yr); put<H>(c.yi, s.yi);
-  if (H) c.e0y = s.e0; else c.e0x = s.e0;
-  put<H>(c.pd, s.pd); put<H>(c.pw, s.pw); put<H>(c.qd, s.qd); put<H>(c.qw, s.qw);
+  for (int i = 0; i < kIter; ++i) {
+    if (i == ilo) { c.pd = c.d1; c.pw = c.w2; }
+    const float2 y = k_step2(c, x[i], k);
+    if (i >= ilo && i < ihi) {
+      e = __ffma2_rn(y, y, e);
+      sr = __ffma2_rn(y, bc2(k.lam_re[i]), sr);
+      si = __ffma2_rn(y, bc2(k.lam_im[i]), si);
+    }
+    if (i + 1 == ihi) { c.qd = c.d1; c.qw = c.w2; }
+  }
+  c.e0x += (double) e.x;
+  c.e0y += (double) e.y;
+  const float2 nr = __ffma2_rn(c.yr, bc2(k.rot_re), __ffma2_rn(c.yi, bc2(-k.rot_im), sr));
+  const float2 ni = __ffma2_rn(c.yr, bc2(k.rot_im), __ffma2_rn(c.yi, bc2(k.rot_re), si));
+  c.yr = nr;
+  c.yi = ni;
 }
 
 // Per-pair maxima of the lane's two channels.  16-bit input: packed signed
@@ -211,7 +209,7 @@ __device__ __forceinline__ void load_iter2(const uint32_t rowp, uint32_t fb, uin
 // CTA size and resident warps per SM of the packed sweep.  Warps are autonomous,
 // so small CTAs only make the distribution of warps over the SMs finer.
 #ifndef LG_PAIR_THREADS
-#define LG_PAIR_THREADS 64
+#define LG_PAIR_THREADS 32
 #endif
 #ifndef LG_PAIR_WARPS_PER_SM
 #define LG_PAIR_WARPS_PER_SM 16
@@ -427,7 +425,9 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
           iter_warm2(c, P, x0);
           iter_warm2(c, P, x1);
         } else {
-          // ---- chunk edges: one iteration at a time, scalar masked code per channel
+          // ---- chunk edges: one iteration at a time, each as its kind
+          // (lg_common.h: iter_kind) -- of the two iterations of an edge
+          // pair only the one that holds the chunk boundary is masked
 #pragma unroll 1
           for (uint32_t it = 0; it < 2u; ++it) {
             const uint32_t iter = pair * 2u + it;
@@ -435,12 +435,10 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
             const int f0 = (int) (iter * kIter);
             float2 x[kIter];
             load_iter2<LAYOUT>(buf + it * kIter * fb, fb, chl, x, pk);
-            if (f0 + kIter <= W) {
-              iter_warm2(c, P, x);
-            } else {
-              masked_half<0>(c, P, x, f0);
-              masked_half<1>(c, P, x, f0);
-            }
+            const int kind = iter_kind(f0, W, P.aq, L, ww.lmin_valid);
+            if (kind == ITER_WARM) iter_warm2(c, P, x);
+            else if (kind == ITER_FAST) iter_fast2(c, P, x, f0);
+            else iter_masked2(c, P, x, f0);
           }
         }
       }
@@ -497,7 +495,13 @@ template <int LAYOUT, bool TP>
 static cudaError_t launch_pair_k(const SweepParams& p, cudaStream_t stream) {
   const uint32_t wpb = kPairThreads / 32;
   const uint32_t blocks = (p.nwarps + wpb - 1) / wpb;
-  const size_t smem = (size_t) p.warp_smem * wpb;
+  size_t smem = (size_t) p.warp_smem * wpb;
+  // Resident CTAs per SM can be capped by padding the dynamic shared memory
+  // (p.ctas_per_sm, lg_plan.h: the planner rounds the launch to whole waves).
+  if (p.ctas_per_sm) {
+    const size_t cap = ((size_t) 233472 / p.ctas_per_sm - 1024) & ~(size_t) 127;
+    if (cap > smem) smem = cap;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(sweep_pair_kernel<LAYOUT, TP>,

@@ -74,6 +74,12 @@ struct PlanOptions {
   int force_k = 0;             // > 0 pins the chunks per 100 ms slot (tuning / tests)
   bool allow_packed = true;
   bool use_tma = true;         // 2-D TMA staging for packed stereo groups
+  // Tail filler (profiles/r01_pair_tuning.txt I/J): the tracks that hold the last
+  // `tail_frac` of the batch's lane-frames get chunks `tail_div` times shorter.
+  // Their launch group follows the main one on a second stream, and its short
+  // work items keep the SMs full while the main group's long ones run out.
+  double tail_frac = 0.0;      // 0 = off
+  int tail_div = 3;
 };
 
 // Chunks per 100 ms slot of one track: the longest chunk (a divisor of the
@@ -98,6 +104,10 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, const Plan
   // rises below that, while longer chunks only save warm-up frames.  So: the
   // longest chunk that still gives every launch group ~1.8 waves.
   uint64_t want_len = 0;
+  double total_work = 0.0;             // lane-frames of the batch
+  for (size_t i = 0; i < n; ++i)
+    total_work += (double) in[i].frames *
+                  (track_is_packed(in[i].channels, opt.allow_packed) ? in[i].channels / 2.0 : (double) in[i].channels);
   if (opt.force_k <= 0 && opt.target_tasks) {
     const uint32_t sms = (uint32_t) (opt.target_tasks / 2048u);
     if (sms) {
@@ -120,9 +130,15 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, const Plan
 
   std::map<std::tuple<uint32_t, int, uint32_t>, uint32_t> coef_index;
   p.tracks.resize(n);
+  double work_before = 0.0;
   for (size_t i = 0; i < n; ++i) {
     const TrackIn& t = in[i];
     Track& tr = p.tracks[i];
+    // a tail track: starts inside the last tail_frac of the batch (never the first track)
+    const bool tail = opt.tail_frac > 0.0 && opt.force_k <= 0 && want_len && i > 0 &&
+                      work_before >= (1.0 - opt.tail_frac) * total_work;
+    work_before += (double) t.frames *
+                   (track_is_packed(t.channels, opt.allow_packed) ? t.channels / 2.0 : (double) t.channels);
     tr = Track();
     tr.pcm = t.pcm;
     tr.frames = t.frames;
@@ -134,7 +150,9 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, const Plan
     else default_weight_classes(t.channels, tr.wclass);
     const int s100 = (int) ((t.samplerate + 5) / 10);
     const KDesign kd = k_design(t.samplerate);
-    const int k = chunks_per_slot_for(s100, warmup_frames(kd), want_len, opt.force_k);
+    const int k = chunks_per_slot_for(s100, warmup_frames(kd),
+                                      tail ? want_len / (uint64_t) (opt.tail_div > 1 ? opt.tail_div : 1) : want_len,
+                                      opt.force_k);
     const auto key = std::make_tuple(t.samplerate, k, t.format);
     auto it = coef_index.find(key);
     if (it == coef_index.end()) {
