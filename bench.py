@@ -61,6 +61,10 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# untimed steps of the same load before / after the timed region (clock sampling)
+CLOCK_LOAD_STEPS = (1500, 800)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
@@ -88,7 +92,6 @@ class ClockSampler:
 
     def __exit__(self, *exc):
         if self.proc:
-            time.sleep(0.15)
             self.proc.terminate()
             self.thread.join(timeout=2)
 
@@ -259,15 +262,23 @@ def gpu_arm(args):
         return res, (merge.fetch() if merge is not None else None)
 
     # ---- resident-PCM throughput (steps replay the batch's CUDA graph)
-    for _ in range(args.warmup):
-        step()
-    barrier()
+    # The timed region is a few milliseconds, far shorter than nvidia-smi's
+    # start-up and sampling period.  So the sampler starts first and the same
+    # step keeps running untimed before and after the timed region (a fixed
+    # count on every rank: the multi-GPU step holds a collective); every clock
+    # sample is then taken under the load the timed steps run in.
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
+        for _ in range(args.warmup + CLOCK_LOAD_STEPS[0]):
+            step()
+        barrier()
         e0.record(stream)
         for _ in range(args.steps):
             (tres, ares), merged = step()
         e1.record(stream)
+        barrier()
+        for _ in range(CLOCK_LOAD_STEPS[1]):
+            step()
         barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -375,6 +386,8 @@ def gpu_arm(args):
             "config": {"workload": WORKLOAD, "samples_per_gpu": samples,
                        "pcm_bytes_per_gpu": pcm_bytes,
                        "l2_policy": "input (508 MB per GPU) is larger than L2 (126 MB); no flush",
+                       "clock_sampling": f"{CLOCK_LOAD_STEPS[0]} + {CLOCK_LOAD_STEPS[1]} untimed steps of the "
+                                         "same load around the timed steps, nvidia-smi every 100 ms",
                        "sharding": "by track; album block lists all-gathered over NCCL" if world > 1
                                    else "single GPU",
                        "e2e_feed": f"ebur128_add_frames_short, {chunk}-frame calls from host PCM, "

@@ -11,6 +11,7 @@
 //                   ebur128_loudness_range[_multiple]: scan.c:294,297,383,388)
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <math.h>
 #include <stdint.h>
 
@@ -954,7 +955,12 @@ cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t 
 
 uint32_t query_cluster_size(uint64_t max_gating_blocks) {
   // one more CTA per 32 k gating blocks of the largest query (about an hour of audio)
-  uint64_t r = max_gating_blocks / 32768u;
+  static const uint64_t per_cta = [] {
+    const char* e = getenv("LOUDGAIN_B200_QUERY_BLOCKS_PER_CTA");   // tuning
+    const long long v = e ? atoll(e) : 0;
+    return (uint64_t) (v > 0 ? v : 32768);
+  }();
+  uint64_t r = max_gating_blocks / per_cta;
   return (uint32_t) (r < 1 ? 1 : (r > (uint64_t) kMaxQueryCluster ? kMaxQueryCluster : r));
 }
 
