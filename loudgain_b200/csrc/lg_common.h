@@ -203,6 +203,7 @@ struct SweepParams {
   const void* tmaps;
   uint32_t tma_m;
   uint32_t tma_shift;      // bit r: class r's chunks live one row earlier (tma_class)
+  uint32_t tma_class_bytes;  // (32 / tma_m) * row_stride: one class's rows in a stage buffer
   uint64_t* tp_queue;        // packed pass: candidate queue, 2 entries per mrec word at most
   uint32_t ctas_per_sm;      // packed sweep: cap on resident CTAs per SM (0 = the kernel's own limit)
 };

@@ -324,7 +324,7 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
         const uint32_t bar = bar0 + 8u * pf_buf;
         mbar_arrive_expect_tx(bar, P.stage_bytes);
         const uint32_t dst = sm_base + pf_off;
-        const uint32_t class_bytes = (32u / tm) * P.row_stride;
+        const uint32_t class_bytes = P.tma_class_bytes;    // (32 / tm) rows: no division per stage
 #pragma unroll
         for (int r = 0; r < kTmaMaxM; ++r)
           if ((uint32_t) r < tm)

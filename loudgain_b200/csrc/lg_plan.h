@@ -220,6 +220,7 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, const Plan
     if (tma_m && (sp.units | 1u) == sp.units + 1u &&
         (long long) tma_m * cs.L >= (long long) ((sp.npairs + pps - 1) / pps) * pps * kPairFrames + 8) {
       sp.tma_m = (uint32_t) tma_m;
+      sp.tma_class_bytes = (32u / (uint32_t) tma_m) * sp.row_stride;
       sp.tma_shift = 0;
       for (int r = 0; r < tma_m; ++r)
         if (tma_class(cs.L, cs.W, (int) t0.aq, tma_m, r).shift) sp.tma_shift |= 1u << r;
