@@ -199,7 +199,7 @@ struct SweepParams {
   uint32_t* tp_ticket;     // counter of the group's true-peak pass (zeroed per run): work
                            // items drawn (scalar pass) / candidates queued (packed pass)
   // 2-D TMA staging (packed stereo sweep, WarpWork::interior == 2): m tensor
-  // maps per track (one per chunk class j mod m), 8 slots of 128 bytes each
+  // maps per track (one per chunk class j mod m), kTmaMaxM slots of 128 bytes each
   const void* tmaps;
   uint32_t tma_m;
   uint32_t tma_shift;      // bit r: class r's chunks live one row earlier (tma_class)
@@ -214,7 +214,7 @@ struct SweepParams {
 // alignment offset.  So class r is a 2-D tensor: row i = the m*L frames from
 // lane-local frame 0 of chunk i*m + r.  Class 0 starts W frames before the
 // track; it is shifted by one row (row i - 1 holds chunk i*m).
-constexpr int kTmaMaxM = 8;
+constexpr int kTmaMaxM = 4;     // stereo rows: 16-byte pitch at m = 2 or 4 (aq <= 4 frames)
 constexpr int kTmaBoxPad = 4;       // 32-bit words appended to a box row (odd 16-byte pitch in shared memory)
 
 struct TmaClass {

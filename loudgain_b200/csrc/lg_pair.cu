@@ -225,7 +225,7 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
   constexpr bool STEREO = LAYOUT == PAIR_S16_STEREO || LAYOUT == PAIR_F32_STEREO;
   extern __shared__ __align__(128) unsigned char smem_all[];
   const uint32_t wic = threadIdx.x >> 5;
-  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lane = pin(threadIdx.x & 31u);   // kept in a register: S2R per stage and pair otherwise
   const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + wic;
   if (warp >= P.nwarps) return;                // whole warps leave; no CTA barrier below
   unsigned char* sm = smem_all + wic * P.warp_smem;
