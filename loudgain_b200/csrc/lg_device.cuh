@@ -42,6 +42,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
 }
+// One lane of the (converged) warp: the form the compiler recognises as "a single
+// thread issues this", so a tensor copy behind it needs no loop over active lanes.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"

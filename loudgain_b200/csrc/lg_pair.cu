@@ -320,7 +320,7 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
 
   auto prefetch = [&]() {
     if (tma) {
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t bar = bar0 + 8u * pf_buf;
         mbar_arrive_expect_tx(bar, P.stage_bytes);
         const uint32_t dst = sm_base + pf_off;
