@@ -137,6 +137,7 @@ int ebur128_loudness_range_multiple(ebur128_state** sts, size_t size, double* ou
 
 /* Named by the north-star API list; linear amplitude per channel. */
 int ebur128_sample_peak(ebur128_state* st, unsigned int channel_number, double* out);
+/* Peak of the frames of the last add_frames call only (live metering; not used by loudgain). */
 int ebur128_prev_sample_peak(ebur128_state* st, unsigned int channel_number, double* out);
 
 /* scan.c:303 and scan.c:371 -- linear amplitude, max(true peak, sample peak). */

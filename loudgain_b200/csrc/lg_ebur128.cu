@@ -39,6 +39,7 @@
 #include "../../include/ebur128_b200.h"
 #include "lg_batch.h"
 #include "lg_design.h"
+#include "lg_kernels.h"
 
 namespace {
 
@@ -147,6 +148,11 @@ struct ebur128_state_internal {
   std::atomic<bool> busy{false};  // inside add_frames (its slot must not be taken away)
   unsigned long window_ms = 400, history_ms = ULONG_MAX;
   std::vector<float> convert;   // host scratch for int / double input
+  // frames of the last add_frames call within the current segment, and their
+  // peaks once asked for (ebur128_prev_sample_peak / _prev_true_peak)
+  uint64_t prev_first = 0, prev_count = 0;
+  bool prev_valid = false;
+  std::vector<double> prev_sp, prev_tp;
 };
 
 namespace {
@@ -323,9 +329,12 @@ bool stage_bytes(ebur128_state* st, const char* src, size_t bytes) {
 
 int add_frames(ebur128_state* st, const void* src, size_t frames, uint32_t format) {
   if (!st || !st->d) return EBUR128_ERROR_NOMEM;
-  if (!frames) return EBUR128_SUCCESS;
   ebur128_state_internal* d = st->d;
   Segment* s = &d->segs.back();
+  d->prev_first = s->frames;       // the "prev" peaks are those of this call's frames
+  d->prev_count = frames;
+  d->prev_valid = false;
+  if (!frames) return EBUR128_SUCCESS;
   {
     std::lock_guard<std::mutex> lock(g_ctx.mu);
     if (!g_ctx.ready) return EBUR128_ERROR_NOMEM;
@@ -533,6 +542,8 @@ extern "C" LG_EXPORT int ebur128_change_parameters(ebur128_state* st, unsigned i
   const uint32_t fmt = st->d->segs.back().format;
   if (st->d->segs.back().frames == 0) st->d->segs.pop_back();
   open_segment(st, fmt);
+  st->d->prev_first = st->d->prev_count = 0;
+  st->d->prev_valid = false;
   g_ctx.multi_valid = false;
   return EBUR128_SUCCESS;
 }
@@ -711,7 +722,65 @@ extern "C" LG_EXPORT int ebur128_loudness_window(ebur128_state* st, unsigned lon
   return window_query(st, (size_t) (st->samplerate * window / 1000), out);
 }
 
-// The per-call "prev" peaks are a live-metering feature that loudgain never
-// uses; they are not on the B200 path.
-extern "C" LG_EXPORT int ebur128_prev_sample_peak(ebur128_state*, unsigned int, double*) { return EBUR128_ERROR_INVALID_MODE; }
-extern "C" LG_EXPORT int ebur128_prev_true_peak(ebur128_state*, unsigned int, double*) { return EBUR128_ERROR_INVALID_MODE; }
+// ---- peaks of the last add_frames call ---------------------------------------
+// ebur128_prev_sample_peak / _prev_true_peak: a live-metering feature loudgain
+// never uses.  The frames of the last call are still in
+// the state's device PCM, so the query runs one small kernel over that range
+// (lg_kernels.cu: range_peak_kernel; the interpolator's history is the audio
+// before it) and caches the result until the next add_frames.
+namespace {
+
+int prev_peak_query(ebur128_state* st, unsigned ch, double* out, bool true_peak) {
+  if (!has_mode(st, true_peak ? EBUR128_MODE_TRUE_PEAK : EBUR128_MODE_SAMPLE_PEAK))
+    return EBUR128_ERROR_INVALID_MODE;
+  if (ch >= st->channels) return EBUR128_ERROR_INVALID_CHANNEL_INDEX;
+  std::lock_guard<std::mutex> lock(g_ctx.mu);
+  if (!ctx_init()) return EBUR128_ERROR_NOMEM;
+  ebur128_state_internal* d = st->d;
+  if (!d->prev_valid) {
+    if (!flush_stage(st)) return EBUR128_ERROR_NOMEM;
+    Segment& s = d->segs.back();
+    const unsigned C = s.channels;
+    d->prev_sp.assign(C, 0.0);
+    d->prev_tp.assign(C, 0.0);
+    if (d->prev_count) {
+      uint32_t* dev = nullptr;
+      std::vector<uint32_t> host(2 * C);
+      bool ok = cudaMallocAsync((void**) &dev, 2 * C * sizeof(uint32_t), g_ctx.stream) == cudaSuccess;
+      if (ok)
+        ok = lg::launch_range_peaks(s.d_pcm, s.format, C, d->prev_first, d->prev_count,
+                                    lg::true_peak_factor(s.rate), dev, g_ctx.stream) == cudaSuccess &&
+             cudaMemcpyAsync(host.data(), dev, 2 * C * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                             g_ctx.stream) == cudaSuccess &&
+             cudaStreamSynchronize(g_ctx.stream) == cudaSuccess;
+      if (dev) cudaFreeAsync(dev, g_ctx.stream);
+      if (!ok) {
+        fprintf(stderr, "libebur128 (B200): prev-peak query failed: %s\n",
+                cudaGetErrorString(cudaGetLastError()));
+        return EBUR128_ERROR_NOMEM;
+      }
+      const double scale = s.format == LGB_FORMAT_S16 ? 32768.0 : 1.0;
+      for (unsigned c = 0; c < C; ++c) {
+        float sp, tp;
+        memcpy(&sp, &host[2 * c], 4);
+        memcpy(&tp, &host[2 * c + 1], 4);
+        d->prev_sp[c] = (double) sp / scale;
+        d->prev_tp[c] = (double) tp / scale;
+      }
+    }
+    d->prev_valid = true;
+  }
+  // as ebur128_true_peak: never below the sample peak of the same frames
+  *out = true_peak ? std::max(d->prev_tp[ch], d->prev_sp[ch]) : d->prev_sp[ch];
+  return EBUR128_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" LG_EXPORT int ebur128_prev_sample_peak(ebur128_state* st, unsigned int ch, double* out) {
+  return prev_peak_query(st, ch, out, false);
+}
+
+extern "C" LG_EXPORT int ebur128_prev_true_peak(ebur128_state* st, unsigned int ch, double* out) {
+  return prev_peak_query(st, ch, out, true);
+}

@@ -953,6 +953,62 @@ cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t 
   return cudaGetLastError();
 }
 
+// ---- peaks of a frame range (ebur128_prev_sample_peak / _prev_true_peak) ------
+// max |x| and max |polyphase output| over track frames [first, first + count) of
+// every channel: what libebur128 reports for the frames of the LAST add_frames
+// call (the interpolator's history being the frames before them, zero before
+// the start of the audio).  Exhaustive evaluation with the sweep's own tap order
+// (lg_sweep.cuh: tp_frame); a thread keeps one channel and strides over frames.
+template <int FMT, int TPF>
+__global__ void __launch_bounds__(256)
+range_peak_kernel(const void* __restrict__ pcm, uint32_t C, uint64_t first, uint64_t count,
+                  uint32_t* __restrict__ out) {
+  constexpr int NT = TpTraits<TPF>::kTaps;
+  const uint64_t n = count * C;
+  // stride: a multiple of C, so that a thread's channel never changes
+  const uint64_t stride = ((uint64_t) gridDim.x * blockDim.x + C - 1) / C * C;
+  uint64_t idx = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const uint32_t c = (uint32_t) (idx % C);
+  auto sample = [&](long long f) -> float {
+    if (f < 0) return 0.0f;
+    if (FMT == FMT_S16) return (float) reinterpret_cast<const short*>(pcm)[(uint64_t) f * C + c];
+    return reinterpret_cast<const float*>(pcm)[(uint64_t) f * C + c];
+  };
+  float sp = 0.0f, tp = 0.0f;
+  for (; idx < n; idx += stride) {
+    const long long t = (long long) (first + idx / C);
+    float win[NT > 0 ? NT : 1];
+    if (NT > 0) {
+#pragma unroll
+      for (int q = 0; q < NT; ++q) win[q] = sample(t - (NT - 1) + q);
+      sp = fmaxf(sp, fabsf(win[NT - 1]));
+      tp = fmaxf(tp, tp_frame<TPF>(win, NT - 1));
+    } else {
+      sp = fmaxf(sp, fabsf(sample(t)));
+    }
+  }
+  // non-negative floats order like their bit patterns
+  atomicMax(out + 2 * c, __float_as_uint(sp));
+  atomicMax(out + 2 * c + 1, __float_as_uint(tp));
+}
+
+cudaError_t launch_range_peaks(const void* pcm, uint32_t format, uint32_t channels, uint64_t first,
+                               uint64_t count, int tpf, uint32_t* out, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(out, 0, 2 * channels * sizeof(uint32_t), stream);
+  if (e != cudaSuccess || !count) return e;
+  const uint64_t n = count * channels;
+  const uint32_t blocks = (uint32_t) ((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+#define LG_RANGE(F, T) range_peak_kernel<F, T><<<blocks, 256, 0, stream>>>(pcm, channels, first, count, out)
+  if (format == FMT_S16) {
+    if (tpf == 4) LG_RANGE(FMT_S16, 4); else if (tpf == 2) LG_RANGE(FMT_S16, 2); else LG_RANGE(FMT_S16, 0);
+  } else {
+    if (tpf == 4) LG_RANGE(FMT_F32, 4); else if (tpf == 2) LG_RANGE(FMT_F32, 2); else LG_RANGE(FMT_F32, 0);
+  }
+#undef LG_RANGE
+  return cudaGetLastError();
+}
+
 uint32_t query_cluster_size(uint64_t max_gating_blocks) {
   // one more CTA per 32 k gating blocks of the largest query (about an hour of audio)
   static const uint64_t per_cta = [] {

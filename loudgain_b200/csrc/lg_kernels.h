@@ -57,5 +57,9 @@ cudaError_t launch_queries(const BlockList* lists, const Query* queries, const u
                            uint32_t nqueries, double abs_gate, QueryResult* results,
                            cudaStream_t stream, uint32_t cluster = 1);
 uint32_t query_cluster_size(uint64_t max_gating_blocks);
+// Sample peak and true peak (float bits, raw sample units) of track frames
+// [first, first + count) per channel into out[2 * channels] (device memory).
+cudaError_t launch_range_peaks(const void* pcm, uint32_t format, uint32_t channels, uint64_t first,
+                               uint64_t count, int tpf, uint32_t* out, cudaStream_t stream);
 
 }  // namespace lg

@@ -275,6 +275,34 @@ def test_sample_peak_full_scale(product):
     st.destroy()
 
 
+@pytest.mark.parametrize("rate,channels,dtype", [(44100, 2, np.int16), (96000, 6, np.int16),
+                                                 (192000, 2, np.int16), (48000, 1, np.float32)])
+def test_prev_peaks_of_last_call(product, oracle, rate, channels, dtype):
+    """ebur128_prev_sample_peak / _prev_true_peak: peaks of the frames of the last
+    add_frames call only (interpolator history = the audio before it), after
+    every call of a ragged sequence; sample peak exact, true peak within 1e-6."""
+    rng = np.random.default_rng(1234 + rate + channels)
+    n = rate // 2
+    x = rng.uniform(-0.9, 0.9, size=(n, channels)) * np.linspace(0.2, 1.0, n)[:, None]
+    pcm = np.round(x * 32767).astype(np.int16) if dtype == np.int16 else x.astype(np.float32)
+    a, b = product.init(channels, rate), oracle.init(channels, rate)
+    pos = 0
+    for count in (1, 7, 1024, 4097, 333, n):
+        count = min(count, n - pos)
+        if count == 0:
+            break
+        for st in (a, b):
+            st.add_frames(pcm[pos:pos + count])
+        pos += count
+        for ch in range(channels):
+            assert a.prev_sample_peak(ch) == b.prev_sample_peak(ch)
+            assert a.prev_true_peak(ch) == pytest.approx(b.prev_true_peak(ch), rel=1e-6, abs=0)
+    # the running peaks are unaffected by the queries
+    assert a.sample_peaks() == b.sample_peaks()
+    assert np.allclose(a.true_peaks(), b.true_peaks(), rtol=1e-6, atol=0)
+    a.destroy(); b.destroy()
+
+
 def test_known_answers(product):
     """EBU Tech 3341 / 3342 / BS.1770 cases straight through the CUDA path."""
     for name, (pcm, rate, want, tol) in cases.loudness_cases().items():
