@@ -120,6 +120,7 @@ struct lgb_batch {
   cudaStream_t gstream[kGroupStreams] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_gfork = nullptr, ev_gjoin[kGroupStreams] = {nullptr, nullptr, nullptr};
   int ngstreams = 0;
+  uint32_t pair_ctas = 0;            // tuning: cap on resident CTAs per SM of the packed sweep (0 = none)
   cudaEvent_t ev_blocks = nullptr;   // block lists of the current run are complete (lgb_batch_wait_blocks)
   double abs_gate = 0.0;
   uint32_t launches = 0, sweep_launches = 0, sms = 148;
@@ -234,6 +235,7 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
   if (const char* e = getenv("LOUDGAIN_B200_CHUNKS_PER_SLOT")) opt.force_k = atoi(e);   // tuning
   if (const char* e = getenv("LOUDGAIN_B200_SCALAR_SWEEP")) opt.allow_packed = atoi(e) == 0;
   if (const char* e = getenv("LOUDGAIN_B200_TMA")) opt.use_tma = atoi(e) != 0;   // 0: cp.async staging only
+  if (const char* e = getenv("LOUDGAIN_B200_PAIR_CTAS")) b->pair_ctas = (uint32_t) atoi(e);   // tuning
   if (const char* e = getenv("LOUDGAIN_B200_TAIL_FRAC")) opt.tail_frac = atof(e);      // tuning
   if (const char* e = getenv("LOUDGAIN_B200_TAIL_DIV")) opt.tail_div = atoi(e);
   build_plan(in.data(), ntracks, nalbums, opt, b->plan);
@@ -350,7 +352,7 @@ static int enqueue_step(lgb_batch* b) {
       }
     }
     ++gidx;
-    if (const char* env = getenv("LOUDGAIN_B200_PAIR_CTAS")) sp.ctas_per_sm = (uint32_t) atoi(env);   // tuning
+    sp.ctas_per_sm = b->pair_ctas;
     e = sp.packed ? launch_sweep_pair(sp, g.format, g.tpf, gs)
                   : launch_sweep(sp, g.format, g.tpf, gs);
     if (e != cudaSuccess) { set_error("launch_sweep", e); return 1; }
