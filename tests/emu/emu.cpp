@@ -6,6 +6,7 @@
 // tests can check the kernel logic against the oracle before any GPU time is
 // spent.  It is NOT part of the product: libebur128.so does not contain it and
 // has no CPU path; nothing under loudgain_b200/ loads this library.
+#include <stdlib.h>
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
@@ -32,6 +33,15 @@ struct LaneCodes {
 // tp_screened: [total_peaks] true peak of the two-pass scheme the device runs
 // (sweep records iteration maxima, the true-peak pass evaluates only the
 // iterations whose bound exceeds the channel's final sample peak).
+// Plan options as lgb_batch_create sets them (lg_batch.cu), tuning variables included.
+static PlanOptions emu_options(uint64_t target_tasks) {
+  PlanOptions opt;
+  opt.target_tasks = target_tasks;
+  if (const char* e = getenv("LOUDGAIN_B200_TAIL_FRAC")) opt.tail_frac = atof(e);
+  if (const char* e = getenv("LOUDGAIN_B200_TAIL_DIV")) opt.tail_div = atoi(e);
+  return opt;
+}
+
 template <int FMT, int TPF>
 static void run_group(const Plan& p, const SweepGroup& g, std::vector<ChunkRec>& recs,
                       std::vector<float>& peaks, std::vector<float>& tp_screened) {
@@ -211,8 +221,7 @@ extern "C" int emu_measure(const lgb_track* tracks, size_t ntracks, uint32_t nal
     in[i] = TrackIn{tracks[i].pcm, tracks[i].frames, tracks[i].channels, tracks[i].samplerate,
                     tracks[i].format, tracks[i].album, tracks[i].weight_class, tracks[i].lead_in};
   Plan p;
-  PlanOptions opt;
-  opt.target_tasks = target_tasks;
+  const PlanOptions opt = emu_options(target_tasks);
   build_plan(in.data(), ntracks, nalbums, opt, p);
   std::vector<ChunkRec> recs(p.total_recs);
   std::vector<float> peaks(2 * p.total_peaks, 0.0f), tps(p.total_peaks, 0.0f);
@@ -279,8 +288,7 @@ extern "C" void emu_plan_sizes(const lgb_track* tracks, size_t ntracks, uint64_t
     in[i] = TrackIn{tracks[i].pcm, tracks[i].frames, tracks[i].channels, tracks[i].samplerate,
                     tracks[i].format, LGB_NO_ALBUM, nullptr};
   Plan p;
-  PlanOptions opt;
-  opt.target_tasks = target_tasks;
+  const PlanOptions opt = emu_options(target_tasks);
   build_plan(in.data(), ntracks, 0, opt, p);
   *total_blocks = p.total_blocks;
   *total_st = p.total_st;
@@ -298,8 +306,7 @@ extern "C" long long emu_check_tma_view(const lgb_track* tracks, size_t ntracks,
     in[i] = TrackIn{tracks[i].pcm, tracks[i].frames, tracks[i].channels, tracks[i].samplerate,
                     tracks[i].format, LGB_NO_ALBUM, nullptr, tracks[i].lead_in};
   Plan p;
-  PlanOptions opt;
-  opt.target_tasks = target_tasks;
+  const PlanOptions opt = emu_options(target_tasks);
   build_plan(in.data(), ntracks, 0, opt, p);
   long long ntma = 0;
   *total_warps = (long long) p.work.size();

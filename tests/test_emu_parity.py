@@ -208,3 +208,22 @@ def test_tma_view_matches_lane_geometry(rate, seconds, dtype):
         assert ntma >= 0, f"warp {-1 - ntma} has an inconsistent tensor view"
         if seconds > 10:
             assert total.value - 3 <= ntma <= total.value - 1
+
+
+def test_tail_filler_plan(oracle, monkeypatch):
+    """Planner option behind LOUDGAIN_B200_TAIL_FRAC / _TAIL_DIV: the tracks that hold the
+    last part of the batch get shorter chunks (their own launch group); results
+    stay within the parity goals, track by track and for the album."""
+    specs = [synth.TrackSpec(seed=900 + i, rate=44100, channels=2, seconds=12.0 + 3 * i) for i in range(3)]
+    tracks = [(synth.programme_s16(s).numpy(), s.rate) for s in specs]
+    o = oracle_measure(oracle, tracks, albums=[0, 0, 0])
+    base = emu_measure(tracks, albums=[0, 0, 0], target_tasks=2500)
+    monkeypatch.setenv("LOUDGAIN_B200_TAIL_FRAC", "0.4")
+    monkeypatch.setenv("LOUDGAIN_B200_TAIL_DIV", "3")
+    e = emu_measure(tracks, albums=[0, 0, 0], target_tasks=2500)
+    assert list(base["chunk_len"]) == [base["chunk_len"][0]] * 3
+    assert e["chunk_len"][0] == base["chunk_len"][0] and e["chunk_len"][2] < base["chunk_len"][2]
+    for i in range(3):
+        _check(o["tracks"][i], e["tracks"][i])
+    assert lu_diff(e["albums"][0]["loudness"], o["albums"][0]["loudness"]) <= GOAL_LU
+    assert lu_diff(e["albums"][0]["range"], o["albums"][0]["range"]) <= GOAL_LU
