@@ -68,8 +68,8 @@ struct cplx { double re, im; };
 // input scale) combination.  Floats feed the sweep, doubles the fix-up.
 struct CoefSet {
   // --- sweep, FP32.  High-pass in "leaky double integrator" form
-  //   t = x - e2*w2 ; d = c*d1 + t ; w = w1 + d ; yh = d - d1
-  // (algebraically w[n] = x[n] - a1 w[n-1] - a2 w[n-2], yh = w - 2w1 + w2)
+  //   q = x - x1 ; t = q - e2*w2 ; d = c*d1 + t ; w = w1 + d ; yh = d
+  // (algebraically w[n] = q[n] - a1 w[n-1] - a2 w[n-2], yh = w - w1, q = x - x1)
   // followed by the shelf  v = yh - p1 v1 - p2 v2 ; y = v + q1 v1 + q2 v2.
   float c, e2, p1, p2, q1, q2;
   // lambda = the high-pass pole (Im > 0).  The response of the K-weighted

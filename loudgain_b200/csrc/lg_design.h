@@ -154,14 +154,16 @@ inline void make_coefset(unsigned long rate, int k, double full_scale, CoefSet& 
   // Response of the K-weighted output to a start state tau = (d1, w2) at
   // lane-local frame 0, once the shelf has settled: Re(A lambda^f) with
   //   tau = a v + conj(a v),  v = (lambda - 1, 1),
-  //   A = 2 a (lambda - 1)^2 Hs(lambda),  Hs = shelf transfer function.
+  //   A = 2 a (lambda - 1) lambda Hs(lambda),  Hs = shelf transfer function
+  // (the state's d component at frame f is d[f-1] = 2 Re(a (lambda-1) lambda^f),
+  // and the high-pass output is yh[f] = d[f]).
   {
     const cplx one{1, 0};
     const cplx lm1 = c_sub(lam, one);
     const cplx il = c_div(one, lam), il2 = c_mul(il, il);
     const cplx num = c_add(one, c_add(c_mul(cplx{q1, 0}, il), c_mul(cplx{q2, 0}, il2)));
     const cplx den = c_add(one, c_add(c_mul(cplx{d.sa[1], 0}, il), c_mul(cplx{d.sa[2], 0}, il2)));
-    const cplx g = c_mul(c_mul(cplx{2, 0}, c_mul(lm1, lm1)), c_div(num, den));
+    const cplx g = c_mul(c_mul(cplx{2, 0}, c_mul(lm1, lam)), c_div(num, den));
     // a = p + iq with p = tau_w / 2, q = (tau_w x - tau_d) / (2 y), lambda - 1 = x + iy
     const double x = lm1.re, y = lm1.im;
     const cplx a_d{0.0, -1.0 / (2.0 * y)};          // d a / d tau_d

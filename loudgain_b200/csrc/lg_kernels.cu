@@ -247,7 +247,7 @@ sweep_kernel(const __grid_constant__ SweepParams P) {
           const int f0 = (int) (iter * kIter);
           float x[kIter];
           smem_load_iter<LAYOUT>(buf + it * kIter * fb, fb, ch, x);
-          const float m = f0 + kIter <= W ? iter_warm(c, P, x) : iter_masked(c, P, x, f0);
+          const float m = f0 + kIter <= W ? iter_warm(c, P, x, iter == 0) : iter_masked(c, P, x, f0);
           if (it == 0) m0 = m; else m1 = m;
         }
       }

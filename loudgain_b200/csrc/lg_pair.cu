@@ -49,7 +49,7 @@ __host__ __device__ constexpr int pair_format() {
 
 // Everything one lane carries through its chunk: .x = channel 2j, .y = 2j+1.
 struct PairCtx {
-  float2 d1, w1, w2, v1, v2;     // filter state (lg_sweep.cuh: KState)
+  float2 xp, d1, w1, w2, v1, v2; // filter state (lg_sweep.cuh: KState)
   float2 yr, yi;                 // running mode sums
   double e0x, e0y;
   float2 pd, pw, qd, qw;         // state snapshots
@@ -58,16 +58,17 @@ struct PairCtx {
 
 __device__ __forceinline__ float2 bc2(float v) { return make_float2(v, v); }
 
-// lg_sweep.cuh: k_step, both channels at once.  d - d1 is written as
-// fma(-1, d1, d): one rounding, the same value as the scalar subtraction.
+// lg_sweep.cuh: k_step, both channels at once.  x - xp is written as
+// fma(-1, xp, x): one rounding, the same value as the scalar subtraction.
 __device__ __forceinline__ float2 k_step2(PairCtx& s, const float2 x, const SweepParams& k) {
-  const float2 t = __ffma2_rn(bc2(k.ne2), s.w2, x);
+  const float2 q = __ffma2_rn(bc2(-1.0f), s.xp, x);
+  const float2 t = __ffma2_rn(bc2(k.ne2), s.w2, q);
   const float2 d = __ffma2_rn(bc2(k.c), s.d1, t);
   const float2 w = __fadd2_rn(s.w1, d);
-  const float2 yh = __ffma2_rn(bc2(-1.0f), s.d1, d);
-  const float2 u = __ffma2_rn(bc2(k.np2), s.v2, yh);
+  const float2 u = __ffma2_rn(bc2(k.np2), s.v2, d);
   const float2 v = __ffma2_rn(bc2(k.np1), s.v1, u);
   const float2 y = __ffma2_rn(bc2(k.q2), s.v2, __ffma2_rn(bc2(k.q1), s.v1, v));
+  s.xp = x;
   s.w2 = s.w1; s.w1 = w; s.d1 = d;
   s.v2 = s.v1; s.v1 = v;
   return y;
@@ -94,7 +95,8 @@ __device__ __forceinline__ void iter_fast2(PairCtx& c, const SweepParams& k, con
 }
 
 // lg_sweep.cuh: iter_warm (filter state only).
-__device__ __forceinline__ void iter_warm2(PairCtx& c, const SweepParams& k, const float2* x) {
+__device__ __forceinline__ void iter_warm2(PairCtx& c, const SweepParams& k, const float2* x, bool first) {
+  if (first) c.xp = x[0];      // lg_sweep.cuh: lane_start
 #pragma unroll
   for (int i = 0; i < kIter; ++i) (void) k_step2(c, x[i], k);
   c.pd = c.d1; c.pw = c.w2;
@@ -251,7 +253,7 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
   // ---- lane state
   const LaneGeom geo = lane_geometry(frames, L, W, P.aq, chunk);
   PairCtx c;
-  c.d1 = c.w1 = c.w2 = c.v1 = c.v2 = bc2(0.0f);
+  c.xp = c.d1 = c.w1 = c.w2 = c.v1 = c.v2 = bc2(0.0f);
   c.yr = c.yi = bc2(0.0f);
   c.e0x = c.e0y = 0.0;
   c.pd = c.pw = c.qd = c.qw = bc2(0.0f);
@@ -422,8 +424,8 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
           float2 x0[kIter], x1[kIter];
           load_iter2<LAYOUT>(buf, fb, chl, x0, pk);
           load_iter2<LAYOUT>(buf + kIter * fb, fb, chl, x1, pk);
-          iter_warm2(c, P, x0);
-          iter_warm2(c, P, x1);
+          iter_warm2(c, P, x0, pair == 0);
+          iter_warm2(c, P, x1, false);
         } else {
           // ---- chunk edges: one iteration at a time, each as its kind
           // (lg_common.h: iter_kind) -- of the two iterations of an edge
@@ -436,7 +438,7 @@ sweep_pair_kernel(const __grid_constant__ SweepParams P) {
             float2 x[kIter];
             load_iter2<LAYOUT>(buf + it * kIter * fb, fb, chl, x, pk);
             const int kind = iter_kind(f0, W, P.aq, L, ww.lmin_valid);
-            if (kind == ITER_WARM) iter_warm2(c, P, x);
+            if (kind == ITER_WARM) iter_warm2(c, P, x, iter == 0);
             else if (kind == ITER_FAST) iter_fast2(c, P, x, f0);
             else iter_masked2(c, P, x, f0);
           }

@@ -48,6 +48,7 @@ template <int TPF> LG_HD float tp_gain_bound() { return TPF == 4 ? 1.8645f : 2.3
 
 // ----- filter state of one channel ----------------------------------------
 struct KState {
+  float xp;           // previous input sample
   float d1, w1, w2;   // high-pass: last difference, last two integrator values
   float v1, v2;       // shelf
 };
@@ -64,14 +65,22 @@ inline void fill_kcoef(const CoefSet& cs, SweepParams& k) {
 }
 
 // One frame of K-weighting.  Returns the (unnormalised) K-weighted sample.
+// High-pass: the numerator (1 - z^-1)^2 is split around the recursion -- the
+// first difference is taken on the INPUT (exact for 16-bit samples, and it
+// removes any constant offset before it can reach a state variable), the
+// second one falls out of the integrator form for free (w[n] - w[n-1] = d[n]):
+//   q = x - x[n-1] ; t = q - e2*w[n-2] ; d = c*d[n-1] + t ; w = w[n-1] + d ; yh = d
+// so no state ever grows with the input's offset (a direct-form state sits at
+// offset / e2, ~3e4 times the offset).
 LG_HD float k_step(KState& s, float x, const KCoef& k) {
-  const float t = fmaf(k.ne2, s.w2, x);
+  const float q = x - s.xp;
+  const float t = fmaf(k.ne2, s.w2, q);
   const float d = fmaf(k.c, s.d1, t);
   const float w = s.w1 + d;
-  const float yh = d - s.d1;
-  const float u = fmaf(k.np2, s.v2, yh);
+  const float u = fmaf(k.np2, s.v2, d);
   const float v = fmaf(k.np1, s.v1, u);
   const float y = fmaf(k.q2, s.v2, fmaf(k.q1, s.v1, v));
+  s.xp = x;
   s.w2 = s.w1; s.w1 = w; s.d1 = d;
   s.v2 = s.v1; s.v1 = v;
   return y;
@@ -121,7 +130,7 @@ struct LaneCtx {
 };
 
 LG_HD void lane_init(LaneCtx& c, int W, int L, const LaneGeom& g) {
-  c.st.d1 = c.st.w1 = c.st.w2 = c.st.v1 = c.st.v2 = 0.0f;
+  c.st.xp = c.st.d1 = c.st.w1 = c.st.w2 = c.st.v1 = c.st.v2 = 0.0f;
   c.sp = c.yr = c.yi = 0.0f;
   c.e0 = 0.0;
   c.pd = c.pw = c.qd = c.qw = 0.0f;
@@ -174,8 +183,21 @@ LG_HD void mode_accumulate(LaneCtx& c, const KCoef& k, float sr, float si) {
 // belong to a neighbouring chunk of the same channel, frames beyond the
 // track read as zero: neither can change the channel's maximum.
 
-// Warm-up iteration: filter state only.
-LG_HD float iter_warm(LaneCtx& c, const KCoef& k, const float* x) {
+// Start state of a lane: everything at rest and the input difference of the
+// very first frame taken as zero (xp = x[0]).  Any start state is exact after
+// the fix-up (lg_post.cuh works with the lane's own snapshots); this one adds
+// no start transient for an input that rides on a constant offset.  Frames
+// before the track read as zero: the first lane of a track starts from the
+// reference's own zero state.
+LG_HD void lane_start(KState& s, float x0) {
+  s.xp = x0;
+  s.d1 = s.w1 = s.w2 = s.v1 = s.v2 = 0.0f;
+}
+
+// Warm-up iteration: filter state only.  `first`: the lane's very first
+// iteration (lane-local frame 0), which sets the start state.
+LG_HD float iter_warm(LaneCtx& c, const KCoef& k, const float* x, bool first) {
+  if (first) lane_start(c.st, x[0]);
 #pragma unroll
   for (int i = 0; i < kIter; ++i) (void) k_step(c.st, x[i], k);
   // state before the first chunk frame of a lane with offset 0; lanes with a

@@ -87,3 +87,22 @@ def true_peak_cases():
 
 def to_s16(x: np.ndarray) -> np.ndarray:
     return np.clip(np.round(x * 32767.0), -32768, 32767).astype(np.int16)
+
+
+def dc_offset_quiet_programme(rate, dc, kind, channels=2, seconds=9.0, seed=5):
+    """A quiet programme riding on a large constant offset (float64 [frames, ch]).
+
+    kind "tone": 1 kHz at -60 dBFS swept +/-10 dB; "noise": white noise around
+    -50 dBFS swept +/-8 dB.  Channel 0 carries offset `dc`, the others 0.7 * dc
+    with the programme inverted.  The offset starts at frame 0 (a real step the
+    reference's filter sees too); afterwards the K-weighted output is 1e4..1e5
+    times smaller than the offset, which is what breaks an implementation that
+    lets the offset into its filter state in single precision."""
+    t = np.arange(int(rate * seconds)) / rate
+    rng = np.random.default_rng(seed)
+    if kind == "tone":
+        sig = 10 ** ((-60 + 10 * np.sin(2 * np.pi * 0.13 * t)) / 20) * np.sin(2 * np.pi * 1000 * t)
+    else:
+        sig = 10 ** ((-50 + 8 * np.sin(2 * np.pi * 0.13 * t)) / 20) * 0.5 * rng.standard_normal(len(t))
+    cols = [dc + sig] + [0.7 * dc - sig] * (channels - 1)
+    return np.stack(cols, axis=1)

@@ -71,7 +71,7 @@ static void run_group(const Plan& p, const SweepGroup& g, std::vector<ChunkRec>&
         float* x = win + NT;
         host_load_iter<FMT>(tr.pcm, (long long) tr.frames, (int) C, geo.a, f0, (int) ch, x);
         const int kind = iter_kind(f0, cs.W, (int) tr.aq, cs.L, ww.lmin_valid);
-        const float m = kind == ITER_WARM ? iter_warm(c, k, x)
+        const float m = kind == ITER_WARM ? iter_warm(c, k, x, it == 0)
                       : kind == ITER_FAST ? iter_fast(c, k, x, f0) : iter_masked(c, k, x, f0);
         lc.code.push_back(peak_code(m));
         lc.iter_max.push_back(m);

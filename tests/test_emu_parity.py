@@ -110,6 +110,28 @@ def test_dc_offset_and_bass(oracle):
         _check(o, e)
 
 
+@pytest.mark.parametrize("rate,channels,fmt", [(44100, 2, "s16"), (44100, 2, "f32"), (48000, 2, "s16"),
+                                               (96000, 2, "f32"), (96000, 6, "s16"), (48000, 1, "f32"),
+                                               (44100, 1, "s16")])
+@pytest.mark.parametrize("kind", ["tone", "noise"])
+def test_dc_offset_quiet_programme(oracle, rate, channels, fmt, kind):
+    """a -60 dBFS programme on an offset of 0.1 .. 0.9 FS.
+    Block energies within 1e-5 relative of the reference's double-precision
+    direct form II (oracle/ebur128_oracle.c: filter loop; scan.c:448), loudness
+    and range within 2e-4 LU."""
+    for dc in (0.1, 0.3, 0.6, 0.9):
+        x = cases.dc_offset_quiet_programme(rate, dc, kind, channels)
+        pcm = cases.to_s16(x) if fmt == "s16" else x.astype(np.float32)
+        o = oracle_measure(oracle, [(pcm, rate)])["tracks"][0]
+        e = emu_measure([(pcm, rate)])
+        _check(o, e["tracks"][0])
+        got = e["blocks"][e["blocks"] >= ABS_GATE]
+        assert len(got) == len(o["blocks"])
+        assert rel_diff(got, o["blocks"]) <= 1e-5, dc
+        got = e["st"][e["st"] >= ABS_GATE]
+        assert len(got) == len(o["st"]) and rel_diff(got, o["st"]) <= 1e-5, dc
+
+
 def test_full_scale_square_and_impulses(oracle):
     rate = 48000
     n = rate * 5

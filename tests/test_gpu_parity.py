@@ -134,6 +134,36 @@ def test_batch_blocks_match_oracle(product, oracle):
     assert len(st) == len(o["st"]) and rel_diff(st, o["st"]) < 2e-5
 
 
+@pytest.mark.parametrize("rate,channels,fmt", [(44100, 2, "s16"), (44100, 2, "f32"), (48000, 2, "s16"),
+                                               (96000, 2, "f32"), (96000, 6, "s16"), (48000, 1, "f32")])
+@pytest.mark.parametrize("kind", ["tone", "noise"])
+def test_dc_offset_quiet_programme(product, oracle, rate, channels, fmt, kind):
+    """a -60 dBFS programme on an offset of 0.1 .. 0.9 FS
+    (tests/cases.py).  Through the batch API (block lists within 1e-5 relative of
+    the oracle's double-precision filter) and through ebur128_add_frames_*."""
+    import torch
+    from loudgain_b200 import engine
+    gate = 10 ** ((-70 + 0.691) / 10)
+    for dc in (0.1, 0.3, 0.6, 0.9):
+        x = cases.dc_offset_quiet_programme(rate, dc, kind, channels)
+        pcm = cases.to_s16(x) if fmt == "s16" else x.astype(np.float32)
+        o = oracle_measure(oracle, [(pcm, rate)])["tracks"][0]
+        b = engine.Batch([(torch.from_numpy(pcm).cuda(), rate)])
+        b.run()
+        tres, _ = b.fetch()
+        z, st = b.blocks(0, 0), b.blocks(0, 1)
+        b.close()
+        m = tres[0]
+        _check(o, {"loudness": m.loudness, "range": m.range, "sample_peak": m.sample_peak,
+                   "true_peak": m.true_peak})
+        z, st = z[z >= gate], st[st >= gate]
+        assert len(z) == len(o["blocks"]) and rel_diff(z, o["blocks"]) <= 1e-5, dc
+        assert len(st) == len(o["st"]) and rel_diff(st, o["st"]) <= 1e-5, dc
+        if dc == 0.6:
+            g = _drive(product, [(pcm, rate)], None, 1024)
+            _check(o, g["tracks"][0])
+
+
 def test_chunking_invariance(product):
     """Any split of add_frames calls gives identical results."""
     rng = np.random.default_rng(5)
