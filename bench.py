@@ -331,8 +331,11 @@ def gpu_arm(args):
         batch.fetch()
         barrier()
         piped_ms = e0.elapsed_time(e1) / args.steps
+        L.lgb_batch_truepeak_candidates.argtypes = [C.c_void_p]
+        L.lgb_batch_truepeak_candidates.restype = C.c_uint64
+        cand = L.lgb_batch_truepeak_candidates(batch._h)
         if rank == 0:
-            emit({"quick": True, "value": value, "ms_per_step": ms_total / args.steps,
+            emit({"quick": True, "value": value, "tp_candidates": cand, "tp_candidate_frac": cand / (samples / 24.0), "ms_per_step": ms_total / args.steps,
                   "ms_per_step_back_to_back": piped_ms,
                   "sweep_ms": sweep_ms, "truepeak_ms": tp_ms,
                   "sweep_gsamples": samples / (sweep_ms * 1e-3) / 1e9 if sweep_ms else None})

@@ -77,6 +77,11 @@ uint64_t lgb_batch_total_samples(const lgb_batch* b);   /* frames*channels over 
 uint64_t lgb_batch_peak_count(const lgb_batch* b);      /* sum of channels */
 uint32_t lgb_batch_kernel_launches(const lgb_batch* b); /* kernels one run launches */
 uint32_t lgb_batch_sweep_launches(const lgb_batch* b);  /* of which sweep kernels */
+/* True-peak candidates the last run's sweeps queued for the evaluation pass
+ * (stereo tracks; diagnostic: the 24-frame pairs the screening against the
+ * channel's running peak could not rule out, two per pair at most).  Waits for
+ * the run. */
+uint64_t lgb_batch_truepeak_candidates(lgb_batch* b);
 
 /* Device views for diagnostics and multi-GPU merges (valid after run + sync):
  * kind 0 = 400 ms gating blocks, 1 = 3 s short-term blocks, 2 = 100 ms slot

@@ -17,7 +17,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 # LG_LIB_SUFFIX / LG_NVCC_EXTRA build tuning variants next to the product library
 _SUFFIX = os.environ.get("LG_LIB_SUFFIX", "")
 LIB_PATH = os.path.join(LIB_DIR, f"libebur128{'_' + _SUFFIX if _SUFFIX else ''}.so")
-SOURCES = ("lg_kernels.cu", "lg_pair.cu", "lg_batch.cu", "lg_ebur128.cu", "lg_scan.cu")
+SOURCES = ("lg_kernels.cu", "lg_pair.cu", "lg_run.cu", "lg_batch.cu", "lg_ebur128.cu", "lg_scan.cu")
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",

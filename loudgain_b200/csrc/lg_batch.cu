@@ -94,6 +94,11 @@ struct lgb_batch {
   uint32_t* d_mrec = nullptr;
   unsigned char* d_tmaps = nullptr;    // tensor maps of the TMA-staged groups, kTmaMaxM x 128 B per track
   uint64_t* d_tpq = nullptr;           // candidate queue of the packed true-peak pass
+  RunItem* d_items = nullptr;          // work items of the run-sweep groups
+  cplx* d_xi = nullptr;                // plan.xi_table
+  uint32_t* d_runq = nullptr;          // candidate queues of the run-sweep groups (32-bit entries)
+  uint32_t* d_runcnt = nullptr;        // [items * 32] candidates queued per sweep lane
+  uint4* d_rundense = nullptr;      // the candidates that passed the final screening, packed
   double* d_echunk = nullptr;
   double* d_eslot = nullptr;
   double* d_zblock = nullptr;
@@ -136,7 +141,7 @@ struct lgb_batch {
     t.tracks = d_tracks; t.coefs = d_coefs; t.work = d_work;
     t.queries = d_queries; t.members = d_members; t.lists = d_lists; t.recs = d_recs; t.peaks = d_peaks;
     t.echunk = d_echunk; t.eslot = d_eslot; t.zblock = d_zblock; t.zst = d_zst;
-    t.results = d_results;
+    t.results = d_results; t.xi_table = d_xi;
     return t;
   }
 };
@@ -146,7 +151,7 @@ struct lgb_batch {
 static bool make_tensor_maps(lgb_batch* b) {
   const Plan& p = b->plan;
   bool any = false;
-  for (const SweepGroup& g : p.groups) any = any || g.params.tma_m != 0;
+  for (const SweepGroup& g : p.groups) any = any || g.params.tma_m != 0 || g.run;
   if (!any) return true;
   static PFN_cuTensorMapEncodeTiled encode = nullptr;
   if (!encode) {
@@ -161,6 +166,57 @@ static bool make_tensor_maps(lgb_batch* b) {
   }
   std::vector<CUtensorMap> maps(p.tracks.size() * kTmaMaxM);
   memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+  auto fail = [](CUresult rc) {
+    char msg[96];
+    snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (%d)", (int) rc);
+    set_error(msg);
+    return false;
+  };
+  // Run sweep (lg_run.cu): per track the 2-D view "row y = run y" with a 32-row box,
+  // the same view with a box of the last item's complete rows, and the partial
+  // last run as a one-row tensor that ends with the track.
+  for (const SweepGroup& g : p.groups) {
+    if (!g.run) continue;
+    const SweepParams& sp = g.params;
+    const cuuint32_t wpf = sp.fb / 4u, boxw = sp.run_stage_frames * wpf + 4u;
+    const cuuint32_t estr[2] = {1, 1};
+    for (uint32_t ii = 0; ii < g.nitems; ++ii) {
+      const RunItem& it = p.items[g.first_item + ii];
+      if (it.first_run != 0) continue;                     // once per track
+      const Track& tr = p.tracks[it.track];
+      CUtensorMap* m = &maps[(size_t) it.track * kTmaMaxM];
+      const cuuint64_t pitch[1] = {(cuuint64_t) sp.Lr * sp.fb};
+      {
+        const cuuint64_t dims[2] = {tr.nfull ? (cuuint64_t) sp.Lr * wpf : (cuuint64_t) tr.frames * wpf,
+                                    tr.nfull ? (cuuint64_t) tr.nfull : 1u};
+        const cuuint32_t box[2] = {boxw, 32u};
+        const CUresult rc = encode(&m[0], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*) tr.pcm, dims, pitch, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) return fail(rc);
+      }
+      const uint32_t last_first = ((tr.nruns - 1u) / 32u) * 32u;
+      const uint32_t tail_rows = tr.nfull > last_first ? tr.nfull - last_first : 0u;
+      if (tail_rows > 0 && tail_rows < 32u) {
+        const cuuint64_t dims[2] = {(cuuint64_t) sp.Lr * wpf, (cuuint64_t) tr.nfull};
+        const cuuint32_t box[2] = {boxw, tail_rows};
+        const CUresult rc = encode(&m[1], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*) tr.pcm, dims, pitch, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) return fail(rc);
+      }
+      if (tr.nruns > tr.nfull) {
+        const uint64_t done = (uint64_t) tr.nfull * (uint64_t) sp.Lr;
+        const cuuint64_t dims[2] = {(cuuint64_t) (tr.frames - done) * wpf, 1u};
+        const cuuint32_t box[2] = {boxw, 1u};
+        void* base = (void*) ((const unsigned char*) tr.pcm + done * sp.fb);
+        const CUresult rc = encode(&m[2], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, base, dims, pitch, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) return fail(rc);
+      }
+    }
+  }
   for (const SweepGroup& g : p.groups) {
     const SweepParams& sp = g.params;
     if (!sp.tma_m) continue;
@@ -216,6 +272,10 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
       set_error("lgb_batch_create: invalid track descriptor");
       return nullptr;
     }
+    if (((uintptr_t) t.pcm & 15u) != 0) {
+      set_error("lgb_batch_create: pcm must be 16-byte aligned");
+      return nullptr;
+    }
     const uint32_t s100 = (t.samplerate + 5) / 10;
     if (t.lead_in % s100 || t.lead_in > t.frames) {
       set_error("lgb_batch_create: lead_in must be a whole number of 100 ms slots within the track");
@@ -235,17 +295,30 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
   if (const char* e = getenv("LOUDGAIN_B200_CHUNKS_PER_SLOT")) opt.force_k = atoi(e);   // tuning
   if (const char* e = getenv("LOUDGAIN_B200_SCALAR_SWEEP")) opt.allow_packed = atoi(e) == 0;
   if (const char* e = getenv("LOUDGAIN_B200_TMA")) opt.use_tma = atoi(e) != 0;   // 0: cp.async staging only
+  opt.sms = (uint32_t) sms;
+  if (const char* e = getenv("LOUDGAIN_B200_RUN")) opt.use_run = atoi(e) != 0;   // 0: stereo through lg_pair.cu
+  if (const char* e = getenv("LOUDGAIN_B200_RUN_CHUNKS")) opt.force_run_chunks = atoi(e);   // tuning
+  if (const char* e = getenv("LOUDGAIN_B200_RUN_WARPS")) opt.run_warps_per_sm = (uint32_t) atoi(e);   // tuning
   if (const char* e = getenv("LOUDGAIN_B200_PAIR_CTAS")) b->pair_ctas = (uint32_t) atoi(e);   // tuning
   if (const char* e = getenv("LOUDGAIN_B200_TAIL_FRAC")) opt.tail_frac = atof(e);      // tuning
   if (const char* e = getenv("LOUDGAIN_B200_TAIL_DIV")) opt.tail_div = atoi(e);
   build_plan(in.data(), ntracks, nalbums, opt, b->plan);
   const Plan& p = b->plan;
+  if (getenv("LOUDGAIN_B200_VERBOSE"))
+    for (const SweepGroup& g : p.groups)
+      fprintf(stderr, "[lgb] group fmt=%u ch=%u run=%d L=%d R=%d Wp=%d niters=%d xi_iters=%d items/warps=%u nstages=%u\n",
+              g.format, g.channels, (int) g.run, g.params.L, g.params.R, g.params.Wp, g.params.niters,
+              g.params.xi_iters, g.nwarps, g.params.run_nstages);
   b->abs_gate = pow(10.0, (-70.0 + 0.691) / 10.0);
   bool ok = upload(p.tracks, &b->d_tracks, b->stream) && upload(p.coefs, &b->d_coefs, b->stream) &&
             upload(p.work, &b->d_work, b->stream) &&
             upload(p.queries, &b->d_queries, b->stream) &&
             upload(p.members, &b->d_members, b->stream) &&
             dalloc(&b->d_recs, p.total_recs, b->stream) &&
+            upload(p.items, &b->d_items, b->stream) && upload(p.xi_table, &b->d_xi, b->stream) &&
+            dalloc(&b->d_runq, p.total_queue, b->stream) &&
+            dalloc(&b->d_runcnt, (uint64_t) p.items.size() * 32u, b->stream) &&
+            dalloc(&b->d_rundense, p.total_queue, b->stream) &&
             dalloc(&b->d_peaks, 2 * p.total_peaks + p.groups.size() + 1, b->stream) &&
             dalloc(&b->d_mrec, p.total_mrec, b->stream) &&
             dalloc(&b->d_tpq, 2 * p.total_mrec, b->stream) &&
@@ -327,6 +400,7 @@ static int enqueue_step(lgb_batch* b) {
   const Plan& p = b->plan;
   const DeviceTables t = b->tables();
   // peak cells, then one true-peak ticket counter per launch group
+  // peak cells, then per launch group a true-peak queue counter and a work-item ticket
   cudaError_t e = cudaMemsetAsync(b->d_peaks, 0, (2 * p.total_peaks + p.groups.size() + 1) * sizeof(uint32_t),
                                   b->stream);
   if (e != cudaSuccess) { set_error("cudaMemsetAsync(peaks)", e); return 1; }
@@ -351,10 +425,17 @@ static int enqueue_step(lgb_batch* b) {
         if (e != cudaSuccess) { set_error("fork(group streams)", e); return 1; }
       }
     }
-    ++gidx;
     sp.ctas_per_sm = b->pair_ctas;
-    e = sp.packed ? launch_sweep_pair(sp, g.format, g.tpf, gs)
-                  : launch_sweep(sp, g.format, g.tpf, gs);
+    if (g.run) {
+      sp.items = b->d_items + g.first_item;
+      sp.tp_ticket = b->d_peaks + 2 * p.total_peaks + gidx;
+      sp.run_counts = b->d_runcnt + (size_t) g.first_item * 32u;
+      sp.run_queue = b->d_runq + g.queue_base;
+    }
+    ++gidx;
+    e = g.run ? launch_sweep_run(sp, g.format, g.tpf, b->sms, gs)
+        : sp.packed ? launch_sweep_pair(sp, g.format, g.tpf, gs)
+                    : launch_sweep(sp, g.format, g.tpf, gs);
     if (e != cudaSuccess) { set_error("launch_sweep", e); return 1; }
   }
   if (gfork) {
@@ -408,9 +489,16 @@ static int enqueue_step(lgb_batch* b) {
     sp.mrec = b->d_mrec + g.mrec_base;
     sp.tp_ticket = b->d_peaks + 2 * p.total_peaks + gi++;
     sp.tp_queue = b->d_tpq + 2 * g.mrec_base;
+    if (g.run) {
+      sp.items = b->d_items + g.first_item;
+      sp.run_counts = b->d_runcnt + (size_t) g.first_item * 32u;
+      sp.run_queue = b->d_runq + g.queue_base;
+      sp.tp_dense = b->d_rundense + g.queue_base;
+    }
     cudaEvent_t hold = fork ? b->ev_post : nullptr;
-    e = sp.packed ? launch_truepeak_pair(sp, g.format, g.tpf, b->sms, b->stream, hold)
-                  : launch_truepeak(sp, g.format, g.tpf, b->sms, b->stream, hold);
+    e = g.run ? launch_truepeak_run(sp, g.format, g.tpf, b->sms, b->stream, hold)
+        : sp.packed ? launch_truepeak_pair(sp, g.format, g.tpf, b->sms, b->stream, hold)
+                    : launch_truepeak(sp, g.format, g.tpf, b->sms, b->stream, hold);
     if (e != cudaSuccess) { set_error("launch_truepeak", e); return 1; }
   }
   if (b->timing) cudaEventRecord(b->ev2, b->stream);
@@ -518,6 +606,20 @@ extern "C" LG_EXPORT uint64_t lgb_debug_trace(lgb_batch* b, uint64_t* out, uint6
   return n;
 }
 #endif
+
+// True-peak candidates the last run's sweeps queued for evaluation (run-sweep
+// groups; diagnostic: how much of the audio the screening could not rule out).
+extern "C" LG_EXPORT uint64_t lgb_batch_truepeak_candidates(lgb_batch* b) {
+  const size_t n = b->plan.items.size() * 32u;
+  if (!n) return 0;
+  std::vector<uint32_t> h(n);
+  if (cudaStreamSynchronize(b->stream) != cudaSuccess ||
+      cudaMemcpy(h.data(), b->d_runcnt, n * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return 0;
+  uint64_t total = 0;
+  for (uint32_t c : h) total += c;
+  return total;
+}
 
 extern "C" LG_EXPORT uint64_t lgb_batch_total_samples(const lgb_batch* b) { return b->plan.total_samples; }
 extern "C" LG_EXPORT uint64_t lgb_batch_peak_count(const lgb_batch* b) { return b->plan.total_peaks; }
@@ -661,7 +763,7 @@ extern "C" LG_EXPORT void lgb_batch_destroy(lgb_batch* b) {
   if (!b) return;
   if (b->ev0) { cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); cudaEventDestroy(b->ev2); }
   void* const mem[] = {b->d_tracks, b->d_coefs, b->d_work, b->d_queries, b->d_members, b->d_lists,
-                       b->d_recs, b->d_peaks, b->d_mrec, b->d_tpq, b->d_tmaps, b->d_echunk, b->d_eslot, b->d_zblock, b->d_zst,
+                       b->d_recs, b->d_peaks, b->d_mrec, b->d_tpq, b->d_tmaps, b->d_items, b->d_xi, b->d_runq, b->d_runcnt, b->d_rundense, b->d_echunk, b->d_eslot, b->d_zblock, b->d_zst,
                        b->d_results};
   if (b->h_results) cudaStreamSynchronize(b->stream);   // a run may still be writing the mirrors
   for (void* m : mem) if (m) cudaFreeAsync(m, b->stream);

@@ -54,6 +54,28 @@ constexpr int kPairRing = LG_PAIR_RING;
 LG_BOTH constexpr int pair_pps(uint32_t format) {
   return format == FMT_S16 ? kPairPPS : (kPairPPS > 1 ? kPairPPS / 2 : 1);
 }
+// Run sweep (lg_run.cu): frames per staged piece of a row, ring depth, resident
+// one-warp CTAs per SM, and the unit 16-bit samples are converted in: a frame
+// word's halves become (int) (w << 16) and (int) (w & 0xffff0000), i.e. 65536
+// times the sample (exact in FP32; one shift / mask per sample instead of a
+// sign-extending byte permute).
+#ifndef LG_RUN_STAGE_FRAMES
+#define LG_RUN_STAGE_FRAMES 48
+#endif
+#ifndef LG_RUN_RING
+#define LG_RUN_RING 2
+#endif
+#ifndef LG_RUN_WARPS_PER_SM
+#define LG_RUN_WARPS_PER_SM 16
+#endif
+constexpr uint32_t kRunStageFrames = LG_RUN_STAGE_FRAMES;   // 16-bit input; a multiple of 2 * kPairFrames
+// float frames are twice as large: half the frames per stage, the same bytes
+LG_BOTH constexpr uint32_t run_stage_frames(uint32_t format) {
+  return (format == FMT_S16 || kRunStageFrames < 2u * kPairFrames) ? kRunStageFrames : kRunStageFrames / 2u;
+}
+constexpr int kRunRing = LG_RUN_RING;
+constexpr uint32_t kRunWarpsPerSM = LG_RUN_WARPS_PER_SM;
+constexpr float kRunS16Scale = 65536.0f;
 // Longest per-phase tap count (49-tap prototype / factor 2, zero taps dropped).
 constexpr int kMaxTaps = 24;
 // A lane starts on a 16-byte boundary of the track, i.e. on a multiple of
@@ -91,6 +113,15 @@ struct CoefSet {
   double S1o[kMaxAlign];          // sum over the chunk of |lambda|^(2f), per offset o
   cplx S2o[kMaxAlign];            // sum over the chunk of lambda^(2f), per offset o
   double gain;      // (shelf b0 / input full scale)^2: raw energy -> K-weighted
+  // --- run sweep (lg_run.cu; run_chunks > 0): a lane filters run_chunks
+  // consecutive chunks in one go, the mode sums restart at every chunk's first
+  // frame and stop xi_frames after the run's first frame
+  int32_t run_chunks;     // R: chunks per run (0: one chunk per lane, kernels of lg_kernels.cu / lg_pair.cu)
+  int32_t run_warm;       // Wp: warm-up frames before a run (multiple of the stage length)
+  int32_t xi_frames;      // mode sums are accumulated for run-local frames < xi_frames (multiple of kIter)
+  uint32_t xi_off;        // first of run_chunks entries in the plan's xi table (lg_plan.h)
+  double S1run;           // sum over a chunk of |lambda|^(2f), f from the chunk's first frame
+  cplx S2run;             // sum over a chunk of lambda^(2f)
 };
 
 // Sweep iterations per chunk for a lane alignment quantum aq.
@@ -118,6 +149,8 @@ struct Track {
   uint64_t st_base;    // first short-term block
   uint64_t peak_base;  // first per-channel peak cell
   uint64_t lead_in;    // leading context frames: no true-peak output is taken inside them
+  uint32_t nruns;      // run sweep: runs of run_chunks chunks (the last one may be partial)
+  uint32_t nfull;      // run sweep: runs that lie completely inside the track
   // BS.1770 channel weight class: 0 unused, 1 -> 1.0, 2 -> 1.41, 3 -> 2.0
   uint8_t wclass[kMaxChannels];
 };
@@ -165,6 +198,17 @@ struct WarpWork {
   uint16_t ch_base;     // first channel this warp handles (0 unless C > 32)
 };
 
+// Work item of the run sweep (lg_run.cu): one warp = 32 consecutive runs of one
+// stereo track, lane l = run first_run + l.
+struct RunItem {
+  uint32_t track;
+  uint32_t first_run;
+  uint32_t tail_rows;   // 32: every row is a complete run of the track's 2-D tensor view;
+                        // < 32: the track's last item -- rows [0, tail_rows) complete, row
+                        // tail_rows partial (or absent), the rest beyond the track
+  uint32_t pad_;
+};
+
 LG_BOTH uint32_t chunks_per_warp(uint32_t channels) { return 32u / (channels < 32u ? channels : 32u); }
 
 // Everything that is uniform over one sweep launch (one format, coefficient
@@ -206,6 +250,19 @@ struct SweepParams {
   uint32_t tma_class_bytes;  // (32 / tma_m) * row_stride: one class's rows in a stage buffer
   uint64_t* tp_queue;        // packed pass: candidate queue, 2 entries per mrec word at most
   uint32_t ctas_per_sm;      // packed sweep: cap on resident CTAs per SM (0 = the kernel's own limit)
+  // ---- run sweep (lg_run.cu)
+  const RunItem* items;
+  uint32_t nitems;
+  int32_t R, Lr, Wp;         // chunks per run, frames per run (R * L), warm-up frames
+  int32_t xi_iters;          // iterations (from run-local frame -Wp) that accumulate the mode sums
+  uint32_t run_stage_frames; // frames per staged piece of a row
+  uint32_t run_nstages;      // stages per item = ceil((Wp + Lr) / stage frames)
+  uint32_t run_warps_per_sm; // resident one-warp CTAs per SM
+  uint32_t* run_queue;       // true-peak candidates: 32-bit entries, one stretch per (item, lane)
+  void* tp_dense;            // ... that passed the final screening, packed (lg_run.cu: tp_filter_run_kernel)
+  uint32_t* run_counts;      // [nitems * 32] entries a lane queued
+  uint32_t run_lane_stride;  // queue entries reserved per lane = npairs * 2 channels
+  float peak_scale;          // raw sample unit / the sweep's internal unit (16-bit input is scaled by 65536)
 };
 
 // ---- 2-D TMA view of a track -------------------------------------------------

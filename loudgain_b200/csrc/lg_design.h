@@ -187,6 +187,35 @@ inline void make_coefset(unsigned long rate, int k, double full_scale, CoefSet& 
   }
 }
 
+// Run-sweep part of a coefficient set (lg_run.cu, lg_post.cuh): a lane filters
+// R chunks in one go starting Wp frames early; chunk j of a run starts at
+// run-local frame j * L.  Its mode sum is kept relative to the first frame of
+// the last iteration that fed it (iterations are kIter frames from run-local
+// frame -Wp, Wp a multiple of kIter) and only over run-local frames
+// < xi_frames; xi[j] = lambda^(that iteration's first frame - j * L) refers it to
+// the chunk's own first frame (0 if the chunk starts past xi_frames: no sum).
+inline void make_run_coefs(const KDesign& d, int R, int Wp, int xi_frames, CoefSet& cs,
+                           std::vector<cplx>& xi_table) {
+  cs.run_chunks = R;
+  cs.run_warm = Wp;
+  cs.xi_frames = xi_frames;
+  cs.xi_off = (uint32_t) xi_table.size();
+  const double tr = 1.0 + d.c, dt = d.c + d.e2, disc = tr * tr - 4.0 * dt;
+  const cplx lam = disc < 0 ? cplx{tr / 2.0, std::sqrt(-disc) / 2.0}
+                            : cplx{(tr + std::sqrt(disc)) / 2.0, 0.0};
+  for (int j = 0; j < R; ++j) {
+    const long f = (long) j * cs.L;
+    if (f >= xi_frames) { xi_table.push_back(cplx{0.0, 0.0}); continue; }
+    const long end = f + cs.L < xi_frames ? f + cs.L : xi_frames;     // exclusive
+    const long it_last = (end - 1) / kIter;
+    xi_table.push_back(c_pow(lam, it_last * kIter - f));
+  }
+  const double r2 = lam.re * lam.re + lam.im * lam.im;
+  const cplx l2 = c_mul(lam, lam);
+  cs.S1run = (1.0 - std::pow(r2, (double) cs.L)) / (1.0 - r2);
+  cs.S2run = c_div(c_sub(cplx{1, 0}, c_pow(l2, cs.L)), c_sub(cplx{1, 0}, l2));
+}
+
 inline uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }
 
 // Frames between consecutive 16-byte-aligned frame boundaries.

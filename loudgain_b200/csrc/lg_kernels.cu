@@ -569,7 +569,7 @@ __device__ uint32_t find_track_cta(const Track* tracks, uint32_t ntracks, uint64
 __global__ void __launch_bounds__(256)
 fixup_kernel(const Track* __restrict__ tracks, uint32_t ntracks,
              const CoefSet* __restrict__ coefs, const ChunkRec* __restrict__ recs,
-             uint64_t total_recs, double* __restrict__ echunk) {
+             uint64_t total_recs, double* __restrict__ echunk, const cplx* __restrict__ xi_table) {
   __shared__ uint64_t s_base[kTrackCache];
   const uint64_t r = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t ti = find_track_cta(tracks, ntracks, r, r < total_recs, s_base,
@@ -583,7 +583,7 @@ fixup_kernel(const Track* __restrict__ tracks, uint32_t ntracks,
   if (chunk >= (uint64_t) tr.nslots * cs.k) return;   // tail chunks carry peaks only
   const LaneGeom geo = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, (long long) chunk);
   echunk[r] = chunk_true_energy(cs, recs + tr.rec_base + ch, tr.channels, (long long) chunk,
-                                geo.o, 31 - __clz((int) tr.aq));
+                                geo.o, 31 - __clz((int) tr.aq), xi_table);
 }
 
 __global__ void __launch_bounds__(256)
@@ -938,7 +938,7 @@ cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t 
   if (z.total_recs) {
     const unsigned blocks = (unsigned) ((z.total_recs + 255) / 256);
     fixup_kernel<<<blocks, 256, 0, stream>>>(t.tracks, z.ntracks, t.coefs, t.recs, z.total_recs,
-                                            t.echunk);
+                                            t.echunk, t.xi_table);
   }
   if (z.total_slots) {
     const unsigned blocks = (unsigned) ((z.total_slots + 255) / 256);

@@ -19,6 +19,7 @@ struct DeviceTables {
   const Query* queries;
   const uint32_t* members;
   const BlockList* lists; // [ntracks]
+  const cplx* xi_table;   // run sweep: mode-sum reference per chunk position (lg_design.h: make_run_coefs)
   ChunkRec* recs;       // [total_recs]
   uint32_t* peaks;      // [total_peaks][2]: sample peak, true peak (float bits)
   double* echunk;       // [total_recs] corrected chunk energies
@@ -46,6 +47,11 @@ cudaError_t launch_truepeak(const SweepParams& p, uint32_t format, int tpf, uint
 cudaError_t launch_sweep_pair(const SweepParams& p, uint32_t format, int tpf, cudaStream_t stream);
 cudaError_t launch_truepeak_pair(const SweepParams& p, uint32_t format, int tpf, uint32_t sms,
                                  cudaStream_t stream, cudaEvent_t hold = nullptr);
+// The run sweep and its true-peak pass (lg_run.cu: stereo tracks, one lane per
+// run of chunks, persistent one-warp CTAs).
+cudaError_t launch_sweep_run(const SweepParams& p, uint32_t format, int tpf, uint32_t sms, cudaStream_t stream);
+cudaError_t launch_truepeak_run(const SweepParams& p, uint32_t format, int tpf, uint32_t sms,
+                                cudaStream_t stream, cudaEvent_t hold = nullptr);
 cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t stream);
 // 400 ms / 3 s blocks of one stream from its complete 100 ms slot list.
 cudaError_t launch_stream_blocks(const double* eslot, int s100, uint64_t nblocks, uint64_t nst,

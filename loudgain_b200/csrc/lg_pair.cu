@@ -30,6 +30,7 @@
 #include "lg_common.h"
 #include "lg_device.cuh"
 #include "lg_kernels.h"
+#include "lg_packed.cuh"
 #include "lg_sweep.cuh"
 
 namespace lg {
@@ -55,24 +56,6 @@ struct PairCtx {
   float2 pd, pw, qd, qw;         // state snapshots
   int f_lo, f_hi;
 };
-
-__device__ __forceinline__ float2 bc2(float v) { return make_float2(v, v); }
-
-// lg_sweep.cuh: k_step, both channels at once.  x - xp is written as
-// fma(-1, xp, x): one rounding, the same value as the scalar subtraction.
-__device__ __forceinline__ float2 k_step2(PairCtx& s, const float2 x, const SweepParams& k) {
-  const float2 q = __ffma2_rn(bc2(-1.0f), s.xp, x);
-  const float2 t = __ffma2_rn(bc2(k.ne2), s.w2, q);
-  const float2 d = __ffma2_rn(bc2(k.c), s.d1, t);
-  const float2 w = __fadd2_rn(s.w1, d);
-  const float2 u = __ffma2_rn(bc2(k.np2), s.v2, d);
-  const float2 v = __ffma2_rn(bc2(k.np1), s.v1, u);
-  const float2 y = __ffma2_rn(bc2(k.q2), s.v2, __ffma2_rn(bc2(k.q1), s.v1, v));
-  s.xp = x;
-  s.w2 = s.w1; s.w1 = w; s.d1 = d;
-  s.v2 = s.v1; s.v1 = v;
-  return y;
-}
 
 // lg_sweep.cuh: iter_fast.
 __device__ __forceinline__ void iter_fast2(PairCtx& c, const SweepParams& k, const float2* x, int f0) {

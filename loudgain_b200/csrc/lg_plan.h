@@ -43,6 +43,9 @@ struct SweepGroup {
   uint32_t first_warp;   // into Plan::work
   uint32_t nwarps;
   uint64_t mrec_base;    // first word of the group's iteration maxima (tpf != 0)
+  bool run = false;      // run sweep (lg_run.cu): work items are Plan::items[first_item, +nitems)
+  uint32_t first_item = 0, nitems = 0;
+  uint64_t queue_base = 0, queue_cap = 0;   // true-peak candidate queue of a run group (entries)
   SweepParams params;
 };
 
@@ -53,8 +56,11 @@ struct Plan {
   std::vector<SweepGroup> groups;
   std::vector<Query> queries;        // [ntracks] track queries, then [nalbums]
   std::vector<uint32_t> members;     // track indices referenced by queries
+  std::vector<RunItem> items;        // work items of the run-sweep groups
+  std::vector<cplx> xi_table;        // per coefficient set with run_chunks > 0: lambda^(n_j), j < run_chunks
   uint64_t total_recs = 0, total_slots = 0, total_blocks = 0, total_st = 0,
            total_peaks = 0, total_mrec = 0;
+  uint64_t total_queue = 0;          // candidate queue entries over all run groups
   uint64_t total_samples = 0;        // frames * channels over all tracks
   uint32_t nalbums = 0;
 };
@@ -74,6 +80,10 @@ struct PlanOptions {
   int force_k = 0;             // > 0 pins the chunks per 100 ms slot (tuning / tests)
   bool allow_packed = true;
   bool use_tma = true;         // 2-D TMA staging for packed stereo groups
+  bool use_run = true;         // stereo tracks go through the run sweep (lg_run.cu)
+  uint32_t sms = 148;          // SMs of the device (run sweep: one wave of work items when the batch is small)
+  uint32_t run_warps_per_sm = 0;   // resident warps per SM of the run sweep (0 = kRunWarpsPerSM)
+  int force_run_chunks = 0;    // > 0 pins the chunks per run (tuning / tests)
   // Tail filler (profiles/r01_pair_tuning.txt I/J): the tracks that hold the last
   // `tail_frac` of the batch's lane-frames get chunks `tail_div` times shorter.
   // Their launch group follows the main one on a second stream, and its short
@@ -93,6 +103,69 @@ inline int chunks_per_slot_for(int s100, int W, uint64_t want_len, int force_k) 
     best = k;
     if (force_k > 0 ? k >= force_k : (uint64_t) L <= want_len) break;
   }
+  return best;
+}
+
+// ---- run sweep planning ------------------------------------------------------
+// A stereo track is cut into RUNS of R chunks (R * L frames); one lane filters
+// one run in one go, starting Wp frames early.  Longer runs mean less warm-up
+// and fewer frames that need the mode sums (they stop xi_frames into the run),
+// but fewer lanes: (k, R) is chosen so that the group's work items fill the
+// resident warps in as few equal waves as possible.
+
+inline bool track_is_run(uint32_t channels, bool use_run) { return use_run && channels == 2; }
+
+// Frames after which a start-state error has decayed by 1e-5 in amplitude
+// (its energy by 1e-10), rounded up to whole iterations.
+inline int xi_horizon(const KDesign& d) {
+  const int h = (int) std::ceil(std::log(1e-5) / std::log(d.hp_pole_radius));
+  return ((h + kIter - 1) / kIter) * kIter;
+}
+
+inline int run_warmup(const KDesign& d) {
+  const int w = warmup_frames(d);
+  return ((w + kRunStageFrames - 1) / kRunStageFrames) * kRunStageFrames;
+}
+
+struct RunChoice { int k = 1, R = 0; };
+
+inline uint64_t run_items_of(uint64_t frames, uint64_t Lr) {
+  const uint64_t runs = (frames + Lr - 1) / Lr;
+  return (runs + 31) / 32;
+}
+
+inline RunChoice choose_run(uint32_t rate, const std::vector<uint64_t>& frames, uint32_t aq,
+                            uint64_t slots, int force_k, int force_R) {
+  const KDesign d = k_design(rate);
+  const int s100 = (int) ((rate + 5) / 10);
+  const int Wp = run_warmup(d), H = xi_horizon(d);
+  RunChoice best;
+  double best_cost = 0.0;
+  for (int k = 1; k <= s100; ++k) {
+    if (s100 % k) continue;
+    const int L = s100 / k;
+    if (force_k > 0 ? k != force_k : (L > 2400 && k < s100)) continue;   // chunk records every <= 2400 frames
+    if (force_k <= 0 && L < 256 && k > 1) break;
+    int rstep = 12 / (int) gcd_u32((uint32_t) L, 12u);
+    while (((long long) rstep * L) % aq) rstep += 12 / (int) gcd_u32((uint32_t) L, 12u);
+    for (int R = rstep; R <= 4096; R += rstep) {
+      if (force_R > 0 && R < force_R) continue;
+      const long long Lr = (long long) R * L;
+      if (Lr < Wp) continue;
+      if (Lr + Wp > 24 * 32000ll) break;               // pair index is a 15-bit field of the queue entries
+      uint64_t nitems = 0;
+      for (uint64_t f : frames) nitems += run_items_of(f, (uint64_t) Lr);
+      const double ops = 9.0 + 2.0 * (H < Lr ? (double) H / (double) Lr : 1.0);
+      const double item = (double) (Wp + Lr) * ops + 4000.0;
+      const double waves = nitems <= 6 * slots ? (double) ((nitems + slots - 1) / slots)
+                                               : (double) nitems / (double) slots + 1.0;
+      const double cost = waves * item;
+      if (best.R == 0 || cost < best_cost * 0.999 ) { best.k = k; best.R = R; best_cost = cost; }
+      if (force_R > 0) break;
+      if (nitems <= slots / 2) break;                  // longer runs would leave warps idle
+    }
+  }
+  if (best.R == 0) { best.k = 1; best.R = 12; }
   return best;
 }
 
@@ -128,7 +201,20 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, const Plan
     want_len = 0;                       // shortest chunks
   }
 
-  std::map<std::tuple<uint32_t, int, uint32_t>, uint32_t> coef_index;
+  // -- run sweep: one (k, R) per (rate, format) of the stereo tracks
+  std::map<std::pair<uint32_t, uint32_t>, RunChoice> run_choice;
+  {
+    std::map<std::pair<uint32_t, uint32_t>, std::vector<uint64_t>> by_rate;
+    for (size_t i = 0; i < n; ++i)
+      if (track_is_run(in[i].channels, opt.use_run))
+        by_rate[std::make_pair(in[i].samplerate, in[i].format)].push_back(in[i].frames);
+    const uint64_t slots = (uint64_t) opt.sms * (opt.run_warps_per_sm ? opt.run_warps_per_sm : kRunWarpsPerSM);
+    for (const auto& kv : by_rate)
+      run_choice[kv.first] = choose_run(kv.first.first, kv.second,
+                                        align_quantum(2u * (kv.first.second == FMT_S16 ? 2u : 4u)), slots,
+                                        opt.force_k, opt.force_run_chunks);
+  }
+  std::map<std::tuple<uint32_t, int, uint32_t, int>, uint32_t> coef_index;
   p.tracks.resize(n);
   double work_before = 0.0;
   for (size_t i = 0; i < n; ++i) {
@@ -150,14 +236,24 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, const Plan
     else default_weight_classes(t.channels, tr.wclass);
     const int s100 = (int) ((t.samplerate + 5) / 10);
     const KDesign kd = k_design(t.samplerate);
-    const int k = chunks_per_slot_for(s100, warmup_frames(kd),
-                                      tail ? want_len / (uint64_t) (opt.tail_div > 1 ? opt.tail_div : 1) : want_len,
-                                      opt.force_k);
-    const auto key = std::make_tuple(t.samplerate, k, t.format);
+    const bool is_run = track_is_run(t.channels, opt.use_run);
+    int k, R = 0;
+    if (is_run) {
+      const RunChoice rc = run_choice[std::make_pair(t.samplerate, t.format)];
+      k = rc.k; R = rc.R;
+    } else {
+      k = chunks_per_slot_for(s100, warmup_frames(kd),
+                              tail ? want_len / (uint64_t) (opt.tail_div > 1 ? opt.tail_div : 1) : want_len,
+                              opt.force_k);
+    }
+    const auto key = std::make_tuple(t.samplerate, k, t.format, R);
     auto it = coef_index.find(key);
     if (it == coef_index.end()) {
       CoefSet cs;
-      make_coefset(t.samplerate, k, t.format == FMT_S16 ? 32768.0 : 1.0, cs);
+      const double unit = (t.format == FMT_S16 ? 32768.0 : 1.0) *
+                          (is_run && t.format == FMT_S16 ? (double) kRunS16Scale : 1.0);
+      make_coefset(t.samplerate, k, unit, cs);
+      if (is_run) make_run_coefs(kd, R, run_warmup(kd), xi_horizon(kd), cs, p.xi_table);
       it = coef_index.emplace(key, (uint32_t) p.coefs.size()).first;
       p.coefs.push_back(cs);
     }
@@ -166,6 +262,12 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, const Plan
     tr.fb = t.channels * (t.format == FMT_S16 ? 2u : 4u);
     tr.aq = align_quantum(tr.fb);
     tr.niters = (uint32_t) sweep_iters(cs.W, cs.L, (int) tr.aq);
+    if (is_run) {
+      const uint64_t Lr = (uint64_t) cs.run_chunks * (uint64_t) cs.L;
+      tr.niters = (uint32_t) ((cs.run_warm + (int64_t) Lr) / kIter);
+      tr.nruns = (uint32_t) ((t.frames + Lr - 1) / Lr);
+      tr.nfull = (uint32_t) (t.frames / Lr);
+    }
     tr.nslots = (uint32_t) (t.frames / (uint64_t) s100);
     tr.nchunks = (uint32_t) ((t.frames + cs.L - 1) / (uint64_t) cs.L);
     tr.nblocks = tr.nslots >= 4 ? tr.nslots - 3 : 0;
@@ -200,6 +302,37 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, const Plan
     sp.W = cs.W; sp.L = cs.L; sp.niters = (int32_t) t0.niters; sp.aq = (int32_t) t0.aq;
     sp.npairs = (t0.niters + 1u) / 2u;
     sp.channels = t0.channels; sp.fb = t0.fb;
+    if (cs.run_chunks) {
+      // ---- run sweep group: work items of 32 consecutive runs
+      g.run = true;
+      sp.R = cs.run_chunks; sp.Lr = cs.run_chunks * cs.L; sp.Wp = cs.run_warm;
+      sp.xi_iters = (cs.run_warm + cs.xi_frames) / kIter;
+      sp.niters = (cs.run_warm + sp.Lr) / kIter;
+      sp.npairs = ((uint32_t) sp.niters + 1u) / 2u;
+      sp.run_stage_frames = run_stage_frames(t0.format);
+      sp.run_nstages = ((uint32_t) (sp.Wp + sp.Lr) + sp.run_stage_frames - 1u) / sp.run_stage_frames;
+      sp.run_warps_per_sm = opt.run_warps_per_sm ? opt.run_warps_per_sm : kRunWarpsPerSM;
+      sp.peak_scale = t0.format == FMT_S16 ? 1.0f / (float) kRunS16Scale : 1.0f;
+      sp.packed = 1u; sp.lpc = 1u; sp.cpw = 32u;
+      g.first_item = (uint32_t) p.items.size();
+      for (uint32_t i : kv.second) {
+        const Track& tr = p.tracks[i];
+        for (uint32_t r0 = 0; r0 < tr.nruns; r0 += 32u) {
+          const uint32_t full = tr.nfull > r0 ? tr.nfull - r0 : 0u;
+          p.items.push_back(RunItem{i, r0, full < 32u ? full : 32u, 0u});
+        }
+      }
+      g.nitems = (uint32_t) p.items.size() - g.first_item;
+      sp.nitems = g.nitems;
+      g.nwarps = g.nitems;
+      sp.nwarps = g.nitems;
+      g.queue_base = p.total_queue;
+      sp.run_lane_stride = (sp.npairs * 2u + 3u) & ~3u;        // 16-byte multiples
+      g.queue_cap = cs.tpf ? (uint64_t) g.nitems * 32u * sp.run_lane_stride : 0u;
+      p.total_queue += g.queue_cap;
+      if (g.nitems) p.groups.push_back(g);
+      continue;
+    }
     const bool packed = track_is_packed(t0.channels, opt.allow_packed);
     sp.packed = packed ? 1u : 0u;
     sp.lpc = packed ? t0.channels / 2u : (t0.channels < 32u ? t0.channels : 32u);

@@ -21,8 +21,16 @@ LG_HD void mat2_vec(const double m[4], double x, double y, double& ox, double& o
 // recs points at the channel's record of chunk 0; consecutive chunks are
 // `stride` records apart.  `o` is the lane's alignment offset and `aq_log2`
 // the track's alignment class (lg_common.h, lane_geometry).
+//
+// Run sweep (cs.run_chunks > 0, lg_run.cu): the snapshots P, Q are taken at every
+// chunk boundary of a run, so the carry is the same recurrence; the lane's
+// error at the chunk's first frame is T - P itself, its response Re(A lambda^f)
+// counts f from that frame, and the mode sum is referred to it by
+// xi_table[cs.xi_off + (j mod R)] (lg_design.h: make_run_coefs).  Chunks that
+// start past the run's mode-sum horizon have no cross term (the error has
+// decayed by 1e-5 there); the quadratic term is always exact.
 LG_HD double chunk_true_energy(const CoefSet& cs, const ChunkRec* recs, long long stride,
-                               long long j, int o, int aq_log2) {
+                               long long j, int o, int aq_log2, const cplx* xi_table) {
   // T = true high-pass state at the first frame of chunk j.
   double td = 0.0, tw = 0.0;
   long long i = j - cs.horner;
@@ -36,6 +44,18 @@ LG_HD double chunk_true_energy(const CoefSet& cs, const ChunkRec* recs, long lon
     tw = (double) r.qw + my;
   }
   const ChunkRec& r = recs[j * stride];
+  if (cs.run_chunks > 0) {
+    const double ad = td - (double) r.pd, aw = tw - (double) r.pw;
+    const double Are = ad * cs.Ad.re + aw * cs.Aw.re, Aim = ad * cs.Ad.im + aw * cs.Aw.im;
+    const cplx sc = xi_table[cs.xi_off + (uint32_t) (j % cs.run_chunks)];
+    const double xr = (double) r.yr * sc.re - (double) r.yi * sc.im;
+    const double xi = (double) r.yr * sc.im + (double) r.yi * sc.re;
+    const double cross = Are * xr - Aim * xi;
+    const double a2r = Are * Are - Aim * Aim, a2i = 2.0 * Are * Aim;
+    const double quad = 0.5 * (Are * Are + Aim * Aim) * cs.S1run +
+                        0.5 * (a2r * cs.S2run.re - a2i * cs.S2run.im);
+    return r.e0 + 2.0 * cross + quad;
+  }
   // State the zero-started run was missing at its own first (warm-up) frame,
   // W + o frames before the chunk ...
   double ad, aw;

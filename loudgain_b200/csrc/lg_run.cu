@@ -1,0 +1,637 @@
+// lg_run.cu -- the run sweep: fused K-weighting + chunk energies + sample peak +
+// true-peak screening for STEREO tracks (what /root/reference/src/scan.c:448
+// feeds through ebur128_add_frames_short for almost every file).
+//
+// A track is cut into runs of R chunks (R * L frames, lg_plan.h: choose_run).
+// One lane filters one run in one go: it starts Wp frames early (warm-up), so
+// only its high-pass state is still wrong when the run begins, and what that
+// costs the output is a decaying mode that lg_post.cuh removes exactly from the
+// chunk energies (the lane leaves sum y^2, the mode sums and state snapshots per
+// chunk).  The error decays, so the mode sums stop xi_frames into the run: the
+// rest of a long run costs 9 packed FP32 operations per frame instead of 11,
+// and the warm-up is paid once per run instead of once per chunk.
+//
+// One persistent CTA per SM (run_warps_per_sm autonomous warps, no CTA barrier
+// after the start): CTA b owns the work items b, b + grid, b + 2 grid, ... -- an
+// item is 32 consecutive runs of one track, lane l = run first_run + l -- and its
+// warps draw them from a ticket in shared memory, so every SM gets the same
+// number of items (+-1) whatever order the hardware places CTAs in.  A track is a 2-D tensor (row y = run y, pitch R * L frames, a multiple
+// of 16 bytes): per stage ONE tensor copy (cp.async.bulk.tensor.2d, completion on
+// an mbarrier) lands the next piece of all 32 rows in shared memory, rows padded
+// to an odd number of 16-byte units so that LDS.128 of different rows do not
+// collide; the warm-up pieces are the tail of the rows one above (row -1 and
+// everything past the track read as zeros: the tensor copy fills them in).  The
+// last item of a track gets its complete rows from a second map with a smaller
+// box and its partial row from a one-row map that ends with the track.
+//
+// Both channels of a frame run through FFMA2 / FADD2 (lg_packed.cuh).  16-bit
+// frames are one 32-bit word; its halves are converted as (int) (w << 16) and
+// (int) (w & 0xffff0000), i.e. in units of 1/65536 sample (exact; the scale is
+// folded into the gain and the peaks).
+//
+// True peak is a maximum: a polyphase output cannot exceed ||c||_1 * max|x|
+// over its window, and the channel's true peak is at least the largest sample
+// seen so far.  The sweep tests every 24-frame pair against the channel's
+// current peak cell and appends the survivors to the lane's own stretch of the
+// candidate queue (no atomics, no votes: the cursor is a register);
+// tp_filter_run_kernel re-tests them against the final sample peak and packs
+// what is left into a dense queue, tp_eval_run_kernel evaluates the FIR on it
+// (identical to evaluating every frame).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "lg_common.h"
+#include "lg_device.cuh"
+#include "lg_kernels.h"
+#include "lg_packed.cuh"
+#include "lg_sweep.cuh"
+
+namespace lg {
+
+// Warps of the persistent CTA the kernel is compiled for (register budget:
+// 64 K / (32 * warps)); fewer may be launched (SweepParams::run_warps_per_sm).
+#ifndef LG_RUN_MAX_WARPS
+#define LG_RUN_MAX_WARPS 16
+#endif
+constexpr uint32_t kRunMaxWarps = LG_RUN_MAX_WARPS;
+constexpr size_t kRunMaxSmem = 227u * 1024u - 1024u;   // dynamic; the kernel also has a few static bytes
+
+template <int FMT> struct RunGeom {
+  static constexpr uint32_t kFB = FMT == FMT_S16 ? 4u : 8u;          // bytes per stereo frame
+  static constexpr uint32_t kSF = run_stage_frames((uint32_t) FMT);  // frames per stage
+  static constexpr uint32_t kRowBytes = kSF * kFB + 16u;              // odd number of 16-byte units
+  static constexpr uint32_t kAuxOff = 32u * kRowBytes;                // partial row of a track's last item
+  static constexpr uint32_t kSlotBytes = kAuxOff + 256u;
+  static constexpr uint32_t kWarpBytes = kRunRing * kSlotBytes + 128u; // ring + mbarriers
+  static_assert((kSF * kFB / 16u) % 2u == 0u, "row pitch must be an odd number of 16-byte units");
+  static_assert(kSF % kPairFrames == 0u && kRunStageFrames % kSF == 0u, "stages are whole pairs; the warm-up whole stages");
+  static_assert(kSlotBytes % 128u == 0u, "tensor copies land on 128-byte boundaries");
+};
+
+// Filter state and sums of one lane: .x = left, .y = right.
+struct RunCtx {
+  float2 xp, d1, w1, w2, v1, v2;
+  float2 yr, yi;
+  double e0x, e0y;
+  float2 pd, pw;
+};
+
+// 12 frames of the lane's row -> float2 frames, in the sweep's unit.
+template <int FMT>
+__device__ __forceinline__ void run_load12(uint32_t rowp, float2* x) {
+  if constexpr (FMT == FMT_S16) {
+#pragma unroll
+    for (int u = 0; u < kIter / 4; ++u) {
+      const uint4 v = lds128(rowp + 16u * u);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        x[4 * u + i] = make_float2((float) (int) (w[i] << 16), (float) (int) (w[i] & 0xffff0000u));
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < kIter / 2; ++u) {
+      const uint4 v = lds128(rowp + 16u * u);
+      x[2 * u] = make_float2(__uint_as_float(v.x), __uint_as_float(v.y));
+      x[2 * u + 1] = make_float2(__uint_as_float(v.z), __uint_as_float(v.w));
+    }
+  }
+}
+
+// max |x| per channel over 12 frames, folded into m.
+__device__ __forceinline__ void run_max12(const float2* x, float2& m) {
+#pragma unroll
+  for (int i = 0; i < kIter; i += 2) {
+    m.x = fmaxf(m.x, fmaxf(fabsf(x[i].x), fabsf(x[i + 1].x)));
+    m.y = fmaxf(m.y, fmaxf(fabsf(x[i].y), fabsf(x[i + 1].y)));
+  }
+}
+
+// One iteration inside a chunk, mode sums on (11 operations per frame).
+__device__ __forceinline__ void run_iter_xi(RunCtx& c, const SweepParams& k, const float2* x) {
+  float2 e = bc2(0.0f), sr = bc2(0.0f), si = bc2(0.0f);
+#pragma unroll
+  for (int i = 0; i < kIter; ++i) {
+    const float2 y = k_step2(c, x[i], k);
+    e = __ffma2_rn(y, y, e);
+    sr = __ffma2_rn(y, bc2(k.lam_re[i]), sr);
+    si = __ffma2_rn(y, bc2(k.lam_im[i]), si);
+  }
+  c.e0x += (double) e.x;
+  c.e0y += (double) e.y;
+  mode_accumulate2(c.yr, c.yi, k, sr, si);
+}
+
+// ... past the mode-sum horizon (9 operations per frame).
+__device__ __forceinline__ void run_iter_lean(RunCtx& c, const SweepParams& k, const float2* x) {
+  float2 e = bc2(0.0f);
+#pragma unroll
+  for (int i = 0; i < kIter; ++i) {
+    const float2 y = k_step2(c, x[i], k);
+    e = __ffma2_rn(y, y, e);
+  }
+  c.e0x += (double) e.x;
+  c.e0y += (double) e.y;
+}
+
+__device__ __forceinline__ void run_iter_warm(RunCtx& c, const SweepParams& k, const float2* x) {
+#pragma unroll
+  for (int i = 0; i < kIter; ++i) (void) k_step2(c, x[i], k);
+}
+
+// Queue entry of a true-peak candidate (32 bits, in the lane's own stretch of the
+// item's queue): channel (1) | pair (15) | code of the bound (16; lg_sweep.cuh:
+// peak_code of max |x| in the sweep's unit, rounded up).
+template <int FMT, bool TP>
+__global__ void __launch_bounds__(kRunMaxWarps * 32, 1)
+run_sweep_kernel(const __grid_constant__ SweepParams P) {
+  using G = RunGeom<FMT>;
+  constexpr uint32_t SF = G::kSF, FB = G::kFB, WPF = FB / 4u;
+  constexpr uint32_t kPairsPerStageRun = SF / kPairFrames;
+  extern __shared__ __align__(128) unsigned char smem_all[];
+  __shared__ uint32_t s_ticket;
+  const uint32_t lane = pin(threadIdx.x & 31u);
+  const uint32_t sm_base = (uint32_t) __cvta_generic_to_shared(smem_all) + (threadIdx.x >> 5) * G::kWarpBytes;
+  const uint32_t bar0 = sm_base + kRunRing * G::kSlotBytes;
+  if (threadIdx.x == 0) s_ticket = 0u;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kRunRing; ++i) mbar_init(bar0 + 8u * i, 1u);
+    mbar_fence_init();
+  }
+  __syncthreads();                                 // the only CTA-wide barrier: warps are autonomous from here
+  uint32_t phase = 0;                              // bit i: parity the next wait on slot i expects
+
+  const int L = P.L, Wp = P.Wp;
+  const uint32_t R = (uint32_t) P.R;
+  const uint32_t nstages = P.run_nstages, niters = (uint32_t) P.niters;
+  const uint32_t warm_stages = (uint32_t) Wp / SF;
+#ifdef LG_RUN_NOLOAD       // ablation: compute on zeros (LG_RUN_NOLOAD=2: on pseudo-random samples)
+  for (uint32_t i = lane; i < kRunRing * G::kSlotBytes / 4u; i += 32u) {
+    uint32_t h = (i + 977u * threadIdx.x + 131071u * blockIdx.x) * 2654435761u;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    // two 16-bit samples of about -12 dBFS peak
+    reinterpret_cast<uint32_t*>(smem_all + (threadIdx.x >> 5) * G::kWarpBytes)[i] =
+        LG_RUN_NOLOAD == 2 ? (((h & 0x3fffu) - 0x2000u) & 0xffffu) | ((((h >> 16) & 0x3fffu) - 0x2000u) << 16) : 0u;
+  }
+  __syncwarp();
+#endif
+  const uint32_t xi_iters = (uint32_t) P.xi_iters;
+  const float thr_scale = 0.999f / (P.tp_bound * P.peak_scale);   // peak cell (raw units) -> |x| threshold
+
+  // this CTA's items: blockIdx.x + k * gridDim.x, k drawn from the CTA's ticket
+  uint32_t item = 0;
+  if (lane == 0) item = atomicAdd(&s_ticket, 1u);
+  item = blockIdx.x + __shfl_sync(0xffffffffu, item, 0) * gridDim.x;
+
+  while (item < P.nitems) {
+    const RunItem it = P.items[item];
+    const Track& tr = P.tracks[it.track];
+    const uint32_t run = it.first_run + lane;
+    const bool active = run < tr.nruns;
+    const uint32_t nchunks = tr.nchunks;
+    const bool tail_item = it.tail_rows < 32u;
+    const bool has_partial = tail_item && it.first_run + it.tail_rows < tr.nruns;
+    const bool partial_lane = has_partial && lane == it.tail_rows;
+    const unsigned char* maps = reinterpret_cast<const unsigned char*>(P.tmaps) + (size_t) it.track * kTmaMaxM * 128u;
+    ChunkRec* recs = P.recs + tr.rec_base;
+    uint32_t* cell = P.peaks + 2 * tr.peak_base;               // [ch][sample peak, true peak]
+
+    // ---- staging: stage s of the item -> ring slot
+    auto issue = [&](uint32_t s, uint32_t slot) {
+#ifdef LG_RUN_NOLOAD       // ablation: no HBM traffic, compute on whatever is in shared memory
+      return;
+#endif
+      if (elect_one()) {
+        const uint32_t bar = bar0 + 8u * slot;
+        const uint32_t dst = sm_base + slot * G::kSlotBytes;
+        if (s < warm_stages) {
+          // tail of the rows one above: rows first_run - 1 ... first_run + 30
+          mbar_arrive_expect_tx(bar, 32u * G::kRowBytes);
+          tma_load_2d(dst, maps, (int) ((uint32_t) (P.Lr - Wp) + s * SF) * (int) WPF, (int) it.first_run - 1, bar);
+        } else {
+          const int x = (int) ((s - warm_stages) * SF * WPF);
+          if (!tail_item) {
+            mbar_arrive_expect_tx(bar, 32u * G::kRowBytes);
+            tma_load_2d(dst, maps, x, (int) it.first_run, bar);
+          } else {
+            mbar_arrive_expect_tx(bar, (it.tail_rows + (has_partial ? 1u : 0u)) * G::kRowBytes);
+            if (it.tail_rows) tma_load_2d(dst, maps + 128, x, (int) it.first_run, bar);
+            if (has_partial) tma_load_2d(dst + G::kAuxOff, maps + 256, x, 0, bar);
+          }
+        }
+      }
+    };
+
+    RunCtx c;
+    c.xp = c.d1 = c.w1 = c.w2 = c.v1 = c.v2 = bc2(0.0f);
+    c.yr = c.yi = bc2(0.0f);
+    c.e0x = c.e0y = 0.0;
+    c.pd = c.pw = bc2(0.0f);
+    uint32_t j = 0;                                // chunk of the run being filled (warp-uniform)
+    int nb = Wp + L;                               // lane-local frame where it ends
+    float2 sp = bc2(0.0f), prev_pm = bc2(0.0f);    // lane's sample peak, previous pair's maxima
+    // screening thresholds from the channel's peak cells (refreshed per stage)
+    uint32_t cellx = TP ? __ldcg(cell) : 0u, celly = TP ? __ldcg(cell + 2) : 0u;
+    float2 thr = make_float2(__uint_as_float(cellx) * thr_scale, __uint_as_float(celly) * thr_scale);
+    uint32_t seen_x = 0, seen_y = 0;               // what this warp last published
+    // this lane's own stretch of the candidate queue, and how much of it is filled
+    uint32_t* const qlane = P.run_queue + ((size_t) item * 32u + lane) * P.run_lane_stride;
+    uint32_t* qp = qlane;
+    if (!active) thr = make_float2(3.0e38f, 3.0e38f);          // lanes past the track's end queue nothing
+
+    auto close_chunk = [&]() {
+      const uint32_t chunk = run * R + j;
+      if (active && chunk < nchunks) {
+        uint4* out = reinterpret_cast<uint4*>(recs + (size_t) chunk * 2u);
+        const unsigned long long ex = (unsigned long long) __double_as_longlong(c.e0x);
+        const unsigned long long ey = (unsigned long long) __double_as_longlong(c.e0y);
+        out[0] = make_uint4((uint32_t) ex, (uint32_t) (ex >> 32), __float_as_uint(c.yr.x), __float_as_uint(c.yi.x));
+        out[1] = make_uint4(__float_as_uint(c.pd.x), __float_as_uint(c.pw.x), __float_as_uint(c.d1.x),
+                            __float_as_uint(c.w2.x));
+        out[2] = make_uint4((uint32_t) ey, (uint32_t) (ey >> 32), __float_as_uint(c.yr.y), __float_as_uint(c.yi.y));
+        out[3] = make_uint4(__float_as_uint(c.pd.y), __float_as_uint(c.pw.y), __float_as_uint(c.d1.y),
+                            __float_as_uint(c.w2.y));
+      }
+      c.e0x = c.e0y = 0.0;
+      c.yr = c.yi = bc2(0.0f);
+      c.pd = c.d1; c.pw = c.w2;
+      ++j;
+      nb += L;
+    };
+
+#pragma unroll
+    for (int i = 0; i < kRunRing - 1; ++i)
+      if ((uint32_t) i < nstages) issue((uint32_t) i, (uint32_t) i);
+
+    uint32_t slot = 0;
+    float2 half_pm = bc2(0.0f);
+    for (uint32_t s = 0; s < nstages; ++s) {
+#ifndef LG_RUN_NOLOAD
+      mbar_wait(bar0 + 8u * slot, (phase >> slot) & 1u);
+#endif
+      phase ^= 1u << slot;
+      __syncwarp();                    // the previous stage is consumed by every lane
+      {
+        const uint32_t ps = s + kRunRing - 1;
+        if (ps < nstages) issue(ps, slot == 0 ? (uint32_t) kRunRing - 1 : slot - 1);
+      }
+      // the partial row of a track's last item comes from its own buffer in the main stages
+      const uint32_t rowp = sm_base + slot * G::kSlotBytes +
+                            ((partial_lane && s >= warm_stages) ? G::kAuxOff : lane * G::kRowBytes);
+      if (++slot == (uint32_t) kRunRing) slot = 0;
+#ifndef LG_RUN_NOCOMP       // (ablation: staging only)
+      // sample peak + true-peak screening of one pair: a pair (and the history
+      // before it) that cannot beat the channel's peak is done
+      auto screen = [&](const float2 pm, const uint32_t pair) {
+        sp.x = fmaxf(sp.x, pm.x);
+        sp.y = fmaxf(sp.y, pm.y);
+        if (TP) {
+          // no vote, no branch: a predicated store and a predicated bump of the lane's cursor
+          const float cx = fmaxf(pm.x, prev_pm.x), cy = fmaxf(pm.y, prev_pm.y);
+          prev_pm = pm;
+          const uint32_t ex = (pair << 16) | peak_code(cx), ey = 0x80000000u | (pair << 16) | peak_code(cy);
+          const bool hx = cx > thr.x, hy = cy > thr.y;
+          if (hx) *qp = ex;
+          qp += hx ? 1 : 0;
+          if (hy) *qp = ey;
+          qp += hy ? 1 : 0;
+        }
+      };
+      const uint32_t pair0 = s * kPairsPerStageRun;
+      const int fe = (int) ((pair0 + kPairsPerStageRun) * kPairFrames);     // lane-local end of the stage
+      if (s < warm_stages) {
+        // ---- warm-up: filter state only (the warm-up is a whole number of stages)
+#pragma unroll
+        for (uint32_t pr = 0; pr < kPairsPerStageRun; ++pr) {
+          const uint32_t buf = rowp + pr * kPairFrames * FB;
+          float2 x0[kIter], x1[kIter], pm = bc2(0.0f);
+          run_load12<FMT>(buf, x0);
+          run_load12<FMT>(buf + kIter * FB, x1);
+          run_max12(x0, pm);
+          run_max12(x1, pm);
+          if (pr == 0 && s == 0) c.xp = x0[0];               // lg_sweep.cuh: lane_start
+          run_iter_warm(c, P, x0);
+          run_iter_warm(c, P, x1);
+          // the warm-up's pairs belong to the lane of the run before: peaks only
+          sp.x = fmaxf(sp.x, pm.x);
+          sp.y = fmaxf(sp.y, pm.y);
+          prev_pm = pm;
+        }
+        if (s + 1 == warm_stages) { c.pd = c.d1; c.pw = c.w2; }
+      } else if (nb >= fe && 2u * (pair0 + kPairsPerStageRun) <= niters &&
+                 (2u * (pair0 + kPairsPerStageRun) <= xi_iters || 2u * pair0 >= xi_iters)) {
+        // ---- the whole stage inside one chunk: straight-line code
+        // (the pairs' maxima are screened after the stage's arithmetic: a vote and a
+        // branch per pair inside it would cut the filter's instruction stream in two)
+        float2 pms[kPairsPerStageRun];
+        if (2u * pair0 < xi_iters) {
+#pragma unroll
+          for (uint32_t pr = 0; pr < kPairsPerStageRun; ++pr) {
+            const uint32_t buf = rowp + pr * kPairFrames * FB;
+            float2 x0[kIter], x1[kIter];
+            pms[pr] = bc2(0.0f);
+            run_load12<FMT>(buf, x0);
+            run_load12<FMT>(buf + kIter * FB, x1);
+            run_max12(x0, pms[pr]);
+            run_max12(x1, pms[pr]);
+            run_iter_xi(c, P, x0);
+            run_iter_xi(c, P, x1);
+          }
+        } else {
+#pragma unroll
+          for (uint32_t pr = 0; pr < kPairsPerStageRun; ++pr) {
+            const uint32_t buf = rowp + pr * kPairFrames * FB;
+            float2 x0[kIter], x1[kIter];
+            pms[pr] = bc2(0.0f);
+            run_load12<FMT>(buf, x0);
+            run_load12<FMT>(buf + kIter * FB, x1);
+            run_max12(x0, pms[pr]);
+            run_max12(x1, pms[pr]);
+            run_iter_lean(c, P, x0);
+            run_iter_lean(c, P, x1);
+          }
+        }
+#pragma unroll
+        for (uint32_t pr = 0; pr < kPairsPerStageRun; ++pr) screen(pms[pr], pair0 + pr);
+        if (nb == fe) close_chunk();
+      } else {
+        // ---- a chunk (or the mode sums, or the run) ends inside the stage: one
+        // iteration at a time, split at the boundary (tests/emu: run_group_runs)
+#pragma unroll 1
+        for (uint32_t it2 = 0; it2 < 2u * kPairsPerStageRun; ++it2) {
+          const uint32_t iter = 2u * pair0 + it2;
+          if (iter >= niters) break;
+          const int g0 = (int) (iter * kIter);
+          float2 x[kIter], pm = bc2(0.0f);
+          run_load12<FMT>(rowp + it2 * kIter * FB, x);
+          run_max12(x, pm);
+          const bool xi_on = iter < xi_iters;
+          const int ib = nb >= g0 + kIter ? kIter : nb - g0;
+          float2 e = bc2(0.0f), sr = bc2(0.0f), si = bc2(0.0f);
+#pragma unroll
+          for (int i = 0; i < kIter; ++i) {
+            if (i == ib) {
+              c.e0x += (double) e.x;
+              c.e0y += (double) e.y;
+              if (xi_on) mode_accumulate2(c.yr, c.yi, P, sr, si);
+              close_chunk();
+              e = sr = si = bc2(0.0f);
+            }
+            const float2 y = k_step2(c, x[i], P);
+            e = __ffma2_rn(y, y, e);
+            if (xi_on) {
+              sr = __ffma2_rn(y, bc2(P.lam_re[i]), sr);
+              si = __ffma2_rn(y, bc2(P.lam_im[i]), si);
+            }
+          }
+          c.e0x += (double) e.x;
+          c.e0y += (double) e.y;
+          if (xi_on) mode_accumulate2(c.yr, c.yi, P, sr, si);
+          if (nb == g0 + kIter) close_chunk();
+          // screening works on pairs: fold the first iteration's maxima into the second's
+          if (it2 & 1u) screen(make_float2(fmaxf(pm.x, half_pm.x), fmaxf(pm.y, half_pm.y)), iter >> 1);
+          else if (iter + 1u >= niters) screen(pm, iter >> 1);
+          else half_pm = pm;
+        }
+      }
+#endif
+      if (TP && ((s & 7u) == 7u || s < 2u)) {
+        // after the first two stages, then every eighth: publish this warp's sample peak when it raises the cell, and
+        // screen on against the larger of the two.  The cell values are the ones loaded at
+        // the refresh before; the next load is issued here and used at the next refresh.
+        const uint32_t ux = __reduce_max_sync(0xffffffffu, active ? __float_as_uint(sp.x * P.peak_scale) : 0u);
+        const uint32_t uy = __reduce_max_sync(0xffffffffu, active ? __float_as_uint(sp.y * P.peak_scale) : 0u);
+        if (lane == 0) {
+          if (ux > cellx && ux > seen_x) atomicMax(cell, ux);
+          if (uy > celly && uy > seen_y) atomicMax(cell + 2, uy);
+        }
+        seen_x = max(seen_x, ux); seen_y = max(seen_y, uy);
+        if (active)
+          thr = make_float2(__uint_as_float(max(cellx, ux)) * thr_scale, __uint_as_float(max(celly, uy)) * thr_scale);
+        cellx = __ldcg(cell); celly = __ldcg(cell + 2);
+      }
+    }
+    {
+      const uint32_t ux = __reduce_max_sync(0xffffffffu, active ? __float_as_uint(sp.x * P.peak_scale) : 0u);
+      const uint32_t uy = __reduce_max_sync(0xffffffffu, active ? __float_as_uint(sp.y * P.peak_scale) : 0u);
+      if (lane == 0) {
+        atomicMax(cell, ux);
+        atomicMax(cell + 2, uy);
+      }
+    }
+    if (TP) P.run_counts[(size_t) item * 32u + lane] = (uint32_t) (qp - qlane);
+    __syncwarp();                      // every lane is done with the ring before the next item refills it
+    uint32_t next = 0;
+    if (lane == 0) next = atomicAdd(&s_ticket, 1u);
+    item = blockIdx.x + __shfl_sync(0xffffffffu, next, 0) * gridDim.x;
+  }
+}
+
+template <int FMT, bool TP>
+static cudaError_t launch_run_k(const SweepParams& p, uint32_t sms, cudaStream_t stream) {
+  using G = RunGeom<FMT>;
+  uint32_t warps = p.run_warps_per_sm ? p.run_warps_per_sm : kRunWarpsPerSM;
+  if (warps > kRunMaxWarps) warps = kRunMaxWarps;
+  while (warps > 1 && (size_t) warps * G::kWarpBytes > kRunMaxSmem) --warps;
+  // one CTA per SM: more than half of an SM's shared memory, whatever the ring needs
+  size_t smem = (size_t) warps * G::kWarpBytes;
+  if (smem < 120u * 1024u) smem = 120u * 1024u;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(run_sweep_kernel<FMT, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int) kRunMaxSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(run_sweep_kernel<FMT, TP>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const uint32_t blocks = sms < p.nitems ? sms : p.nitems;
+  run_sweep_kernel<FMT, TP><<<blocks, warps * 32u, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sweep_run(const SweepParams& p, uint32_t format, int tpf, uint32_t sms, cudaStream_t stream) {
+  if (p.nitems == 0) return cudaSuccess;
+#ifdef LG_RUN_NOTP         // ablation: no true-peak screening
+  tpf = 0;
+#endif
+  if (format == FMT_S16)
+    return tpf ? launch_run_k<FMT_S16, true>(p, sms, stream) : launch_run_k<FMT_S16, false>(p, sms, stream);
+  return tpf ? launch_run_k<FMT_F32, true>(p, sms, stream) : launch_run_k<FMT_F32, false>(p, sms, stream);
+}
+
+// -------------------------------------------------------------- true peak
+//
+// The candidates the sweep left behind: sweep lane (item, l) queued
+// run_counts[item * 32 + l] entries at run_queue + (item * 32 + l) *
+// run_lane_stride.  tp_filter_run_kernel drops every candidate whose bound does
+// not exceed the channel's FINAL sample peak (so what is evaluated does not
+// depend on how far the peak cells had got when the sweep tested the pair) and
+// packs the rest into one dense queue -- counted first, written second, one
+// reservation per warp; tp_eval_run_kernel evaluates the polyphase FIR on that
+// queue, one candidate per thread, grid-stride: candidates cluster in the loud
+// passages, the dense queue spreads them over the whole GPU.
+constexpr int kTpRunThreads = 128;
+
+// Dense queue entry (16 bytes): .x/.y = address of the first frame of the
+// candidate's window (NT frames of history + the pair; 16-byte aligned, bit 0
+// carries the channel), .z = the channel's peak cell, .w = kTpInterior.  A window
+// that touches the track's ends (or its lead-in) carries (item, lane) in .x and
+// (channel, pair) in .w instead and is located again by the evaluation.
+constexpr uint32_t kTpInterior = 0xffffffffu;
+template <int FMT, int TPF>
+__global__ void __launch_bounds__(256)
+tp_filter_run_kernel(const __grid_constant__ SweepParams P) {
+  constexpr int NT = TpTraits<TPF>::kTaps;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < P.nitems; item += warps) {
+    const uint32_t slot = item * 32u + lane;
+    const uint32_t count = __ldcg(P.run_counts + slot);
+    if (!__any_sync(0xffffffffu, count != 0u)) continue;
+    const RunItem it = P.items[item];
+    const Track& tr = P.tracks[it.track];
+    const uint32_t cell0 = (uint32_t) tr.peak_base;
+    const uint32_t* cell = P.peaks + 2 * (size_t) cell0;
+    const float f0 = __uint_as_float(__ldcg(cell)), f1 = __uint_as_float(__ldcg(cell + 2));
+    const long long frames = (long long) tr.frames, lead_in = (long long) tr.lead_in;
+    const long long a = (long long) (it.first_run + lane) * P.Lr - P.Wp;      // track frame of the lane's frame 0
+    const unsigned char* pcm = reinterpret_cast<const unsigned char*>(tr.pcm);
+    // the lane's stretch is read with 16-byte loads (run_lane_stride is a multiple of 4)
+    const uint4* q = reinterpret_cast<const uint4*>(P.run_queue + (size_t) slot * P.run_lane_stride);
+    auto pass = [&](uint32_t e) {
+      return P.tp_bound * (peak_code_value(e & 0xffffu) * P.peak_scale) > ((e >> 31) ? f1 : f0);
+    };
+    const uint32_t nvec = (count + 3u) >> 2;
+    uint32_t mine = 0;
+    for (uint32_t i = 0; i < nvec; ++i) {
+      const uint4 v = __ldcg(q + i);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mine += (4u * i + k < count && pass(w[k])) ? 1u : 0u;
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t) o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (!total) continue;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(P.tp_ticket, total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    uint4* out = reinterpret_cast<uint4*>(P.tp_dense) + base + (incl - mine);
+    for (uint32_t i = 0; i < nvec; ++i) {
+      const uint4 v = __ldcg(q + i);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t e = w[k];
+        if (!(4u * i + k < count && pass(e))) continue;
+        const uint32_t ch = e >> 31, pair = (e >> 16) & 0x7fffu;
+        const long long t0 = a + (long long) pair * kPairFrames;
+        if (t0 >= NT && t0 + kPairFrames <= frames && t0 >= lead_in) {
+          const unsigned long long p = (unsigned long long) (pcm + (t0 - NT) * (long long) P.fb) | ch;
+          *out++ = make_uint4((uint32_t) p, (uint32_t) (p >> 32), cell0 + ch, kTpInterior);
+        } else {
+          *out++ = make_uint4(slot, 0u, cell0 + ch, (ch << 15) | pair);
+        }
+      }
+    }
+  }
+}
+
+template <int FMT, int TPF>
+__global__ void __launch_bounds__(kTpRunThreads, 4)
+tp_eval_run_kernel(const __grid_constant__ SweepParams P) {
+  constexpr int NT = TpTraits<TPF>::kTaps;
+  constexpr int NW = NT + kPairFrames;
+  const uint32_t count = __ldcg(P.tp_ticket);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const uint4 e = __ldcs(reinterpret_cast<const uint4*>(P.tp_dense) + i);
+    uint32_t* cell = P.peaks + 2 * (size_t) e.z + 1;
+    float win[NW];
+    float m = 0.0f;
+    if (e.w == kTpInterior) {
+      const uint32_t ch = e.x & 1u;
+      const unsigned char* q = reinterpret_cast<const unsigned char*>(
+          ((unsigned long long) e.y << 32) | (unsigned long long) (e.x & ~15u));
+      if (FMT == FMT_S16) {
+        const uint32_t sel = ch ? 0xBB32u : 0x9910u;
+#pragma unroll
+        for (int k = 0; k < NW / 4; ++k) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(q) + k);
+          win[4 * k + 0] = (float) sext_half(v.x, sel);
+          win[4 * k + 1] = (float) sext_half(v.y, sel);
+          win[4 * k + 2] = (float) sext_half(v.z, sel);
+          win[4 * k + 3] = (float) sext_half(v.w, sel);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < NW / 2; ++k) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(q) + k);
+          win[2 * k + 0] = ch ? v.y : v.x;
+          win[2 * k + 1] = ch ? v.w : v.z;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kPairFrames; ++k) m = fmaxf(m, tp_frame<TPF>(win, NT + k));
+    } else {
+      // a window at the track's ends or across the lead-in: located through the item
+      const uint32_t slot = e.x, ch = e.w >> 15, pair = e.w & 0x7fffu;
+      const RunItem it = P.items[slot >> 5];
+      const Track& tr = P.tracks[it.track];
+      const long long frames = (long long) tr.frames;
+      const long long t0 = (long long) (it.first_run + (slot & 31u)) * P.Lr - P.Wp + (long long) pair * kPairFrames;
+      if (t0 >= frames || t0 + kPairFrames <= (long long) tr.lead_in) continue;
+      const unsigned char* pcm = reinterpret_cast<const unsigned char*>(tr.pcm);
+#pragma unroll
+      for (int k = 0; k < NW; ++k) {
+        const long long t = t0 - NT + k;
+        float v = 0.0f;
+        if (t >= 0 && t < frames) {
+          if (FMT == FMT_S16) v = (float) (int) reinterpret_cast<const short*>(pcm)[t * 2 + ch];
+          else v = reinterpret_cast<const float*>(pcm)[t * 2 + ch];
+        }
+        win[k] = v;
+      }
+      // the reference produces no output beyond the last frame it was given
+      const long long left = frames - t0;
+      const int nvalid = left > kPairFrames ? kPairFrames : (int) left;
+#pragma unroll
+      for (int k = 0; k < kPairFrames; ++k)
+        if (k < nvalid) m = fmaxf(m, tp_frame<TPF>(win, NT + k));
+    }
+    if (__float_as_uint(m) > __ldcg(cell)) atomicMax(cell, __float_as_uint(m));
+  }
+}
+
+template <int FMT, int TPF>
+static cudaError_t launch_tp_run_t(const SweepParams& p, uint32_t sms, cudaStream_t stream, cudaEvent_t hold) {
+  static int per_sm = 0;
+  if (!per_sm) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tp_eval_run_kernel<FMT, TPF>, kTpRunThreads, 0) !=
+            cudaSuccess || per_sm < 1)
+      per_sm = 4;
+  }
+  const uint32_t fblocks = (p.nitems + 7u) / 8u;            // one warp per item
+  tp_filter_run_kernel<FMT, TPF><<<fblocks < sms * 8u ? fblocks : sms * 8u, 256, 0, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && hold) e = cudaStreamWaitEvent(stream, hold, 0);
+  if (e != cudaSuccess) return e;
+  tp_eval_run_kernel<FMT, TPF><<<sms * per_sm, kTpRunThreads, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_truepeak_run(const SweepParams& p, uint32_t format, int tpf, uint32_t sms,
+                                cudaStream_t stream, cudaEvent_t hold) {
+  if (p.nitems == 0 || tpf == 0) return cudaSuccess;
+  if (format == FMT_S16)
+    return tpf == 4 ? launch_tp_run_t<FMT_S16, 4>(p, sms, stream, hold) : launch_tp_run_t<FMT_S16, 2>(p, sms, stream, hold);
+  return tpf == 4 ? launch_tp_run_t<FMT_F32, 4>(p, sms, stream, hold) : launch_tp_run_t<FMT_F32, 2>(p, sms, stream, hold);
+}
+
+}  // namespace lg

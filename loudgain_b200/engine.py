@@ -133,6 +133,9 @@ class Batch:
             if pcm.dim() == 1:
                 pcm = pcm.view(-1, 1)
             pcm = pcm.contiguous()
+            if pcm.data_ptr() % 16:
+                # a row slice of a larger tensor: the sweep stages 16-byte units from frame 0
+                pcm = pcm.clone()
             fmt = {torch.int16: FORMAT_S16, torch.float32: FORMAT_F32}[pcm.dtype]
             alb = NO_ALBUM if albums is None else int(albums[i])
             if alb != NO_ALBUM:

@@ -37,6 +37,10 @@ struct LaneCodes {
 static PlanOptions emu_options(uint64_t target_tasks) {
   PlanOptions opt;
   opt.target_tasks = target_tasks;
+  if (const char* e = getenv("LOUDGAIN_B200_RUN")) opt.use_run = atoi(e) != 0;
+  if (const char* e = getenv("LOUDGAIN_B200_RUN_CHUNKS")) opt.force_run_chunks = atoi(e);
+  if (const char* e = getenv("LOUDGAIN_B200_CHUNKS_PER_SLOT")) opt.force_k = atoi(e);
+  if (const char* e = getenv("LOUDGAIN_B200_SMS")) opt.sms = (uint32_t) atoi(e);
   if (const char* e = getenv("LOUDGAIN_B200_TAIL_FRAC")) opt.tail_frac = atof(e);
   if (const char* e = getenv("LOUDGAIN_B200_TAIL_DIV")) opt.tail_div = atoi(e);
   return opt;
@@ -156,6 +160,148 @@ static void run_group(const Plan& p, const SweepGroup& g, std::vector<ChunkRec>&
   }
 }
 
+// ---- run sweep (lg_run.cu): one lane = one run of R chunks, both channels of a
+// stereo track; the scalar restatement of the kernel's per-channel arithmetic.
+template <int FMT, int TPF>
+static void run_group_runs(const Plan& p, const SweepGroup& g, std::vector<ChunkRec>& recs,
+                           std::vector<float>& peaks, std::vector<float>& tp_screened) {
+  constexpr int NT = TpTraits<TPF>::kTaps;
+  const SweepParams& k = g.params;
+  for (uint32_t ii = 0; ii < g.nitems; ++ii) {
+    const RunItem item = p.items[g.first_item + ii];
+    const Track& tr = p.tracks[item.track];
+    const CoefSet& cs = p.coefs[tr.coef];
+    const int L = cs.L, R = cs.run_chunks, Wp = cs.run_warm;
+    const long long Lr = (long long) R * L;
+    for (uint32_t lane = 0; lane < 32; ++lane) {
+      const uint32_t run = item.first_run + lane;
+      if (run >= tr.nruns) continue;
+      const long long a = (long long) run * Lr - Wp;       // track frame of lane-local frame 0
+      for (uint32_t ch = 0; ch < 2; ++ch) {
+        KState st;
+        st.xp = st.d1 = st.w1 = st.w2 = st.v1 = st.v2 = 0.0f;
+        double e = 0.0;
+        LaneCtx c;                 // only yr / yi (mode_accumulate)
+        c.yr = c.yi = 0.0f;
+        float pd = 0.0f, pw = 0.0f, sp = 0.0f, tp = 0.0f;
+        int j = 0;
+        long long nb = Wp + L;
+        std::vector<float> iter_max;
+        float win[(NT > 0 ? NT : 1) + kIter] = {0};
+        auto close_chunk = [&]() {
+          const uint64_t chunk = (uint64_t) run * R + j;
+          if (chunk < tr.nchunks) {
+            ChunkRec& r = recs[tr.rec_base + chunk * 2 + ch];
+            r.e0 = e; r.yr = c.yr; r.yi = c.yi; r.pd = pd; r.pw = pw; r.qd = st.d1; r.qw = st.w2;
+          }
+          e = 0.0; c.yr = c.yi = 0.0f;
+          pd = st.d1; pw = st.w2;
+          ++j; nb += L;
+        };
+        for (uint32_t it = 0; it < tr.niters; ++it) {
+          const int g0 = (int) it * kIter;
+          float* x = win + NT;
+          host_load_iter<FMT>(tr.pcm, (long long) tr.frames, 2, a, g0, (int) ch, x);
+          const float m = max_abs12(x);
+          sp = std::max(sp, m);
+          iter_max.push_back(m);
+          // the kernel filters 16-bit samples in units of 1 / 65536 (exact scaling)
+          float xs[kIter];
+          for (int i = 0; i < kIter; ++i) xs[i] = FMT == FMT_S16 ? x[i] * kRunS16Scale : x[i];
+          x = xs;
+          if (it == 0) lane_start(st, x[0]);
+          if (g0 + kIter <= Wp) {
+            for (int i = 0; i < kIter; ++i) (void) k_step(st, x[i], k);
+            if (g0 + kIter == Wp) { pd = st.d1; pw = st.w2; }
+          } else {
+            const bool xi_on = (int) it < k.xi_iters;
+            const int ib = nb >= g0 + kIter ? kIter : (int) (nb - g0);    // split position (kIter: none)
+            float ef = 0.0f, sr = 0.0f, si = 0.0f;
+            for (int i = 0; i < kIter; ++i) {
+              if (i == ib) {
+                e += (double) ef;
+                if (xi_on) mode_accumulate(c, k, sr, si);
+                close_chunk();
+                ef = sr = si = 0.0f;
+              }
+              const float y = k_step(st, x[i], k);
+              ef = fmaf(y, y, ef);
+              if (xi_on) { sr = fmaf(y, k.lam_re[i], sr); si = fmaf(y, k.lam_im[i], si); }
+            }
+            e += (double) ef;
+            if (xi_on) mode_accumulate(c, k, sr, si);
+            if (nb == g0 + kIter) close_chunk();
+          }
+          if (NT > 0) {
+            // exhaustive true peak over the pairs the lane owns (pair granularity, as the device)
+            const int p0 = (g0 / kPairFrames) * kPairFrames;
+            if (p0 >= Wp && a + p0 < (long long) tr.frames && a + p0 + kPairFrames > (long long) tr.lead_in) {
+              const long long left = (long long) tr.frames - (a + g0);
+              if (left > 0) tp = std::max(tp, tp_window_valid<TPF>(win, left > kIter ? kIter : (int) left));
+            }
+            for (int i = 0; i < NT; ++i) win[i] = win[i + kIter];
+          }
+        }
+        float& spo = peaks[2 * (tr.peak_base + ch)];
+        float& tpo = peaks[2 * (tr.peak_base + ch) + 1];
+        spo = std::max(spo, sp);
+        tpo = std::max(tpo, tp);
+        if (NT > 0) {
+          // deferred: needs the channel's final sample peak -> second loop below
+        }
+      }
+    }
+  }
+  if (NT == 0) return;
+  // ---- the device's screened pass: a pair is evaluated iff the bound over it
+  // and the pair before it exceeds the channel's final sample peak
+  for (uint32_t ii = 0; ii < g.nitems; ++ii) {
+    const RunItem item = p.items[g.first_item + ii];
+    const Track& tr = p.tracks[item.track];
+    const CoefSet& cs = p.coefs[tr.coef];
+    const int Wp = cs.run_warm;
+    const long long Lr = (long long) cs.run_chunks * cs.L;
+    for (uint32_t lane = 0; lane < 32; ++lane) {
+      const uint32_t run = item.first_run + lane;
+      if (run >= tr.nruns) continue;
+      const long long a = (long long) run * Lr - Wp;
+      for (uint32_t ch = 0; ch < 2; ++ch) {
+        const float floor_ = peaks[2 * (tr.peak_base + ch)];
+        float& out = tp_screened[tr.peak_base + ch];
+        auto pair_max = [&](uint32_t pr) {
+          float m = 0.0f;
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t it = 2 * pr + h;
+            if (it >= tr.niters) break;
+            float x[kIter];
+            host_load_iter<FMT>(tr.pcm, (long long) tr.frames, 2, a, (int) it * kIter, (int) ch, x);
+            m = std::max(m, max_abs12(x));
+          }
+          return m;
+        };
+        for (uint32_t pr = (uint32_t) Wp / kPairFrames; pr < k.npairs; ++pr) {
+          uint32_t cm = pair_code<FMT>(pair_max(pr));
+          if (pr) cm = std::max(cm, pair_code<FMT>(pair_max(pr - 1)));
+          const long long t0 = a + (long long) pr * kPairFrames;
+          if (t0 >= (long long) tr.frames || t0 + kPairFrames <= (long long) tr.lead_in) continue;
+          if (!(k.tp_bound * pair_code_value<FMT>(cm) > floor_)) continue;
+          float win[(NT > 0 ? NT : 1) + kPairFrames];
+          for (int q = 0; q < NT + kPairFrames; ++q) {
+            const long long t = t0 - NT + q;
+            win[q] = 0.0f;
+            if (t < 0 || t >= (long long) tr.frames) continue;
+            if (FMT == FMT_S16) win[q] = (float) ((const short*) tr.pcm)[t * 2 + ch];
+            else win[q] = ((const float*) tr.pcm)[t * 2 + ch];
+          }
+          const long long left = (long long) tr.frames - t0;
+          const int nvalid = left > kPairFrames ? kPairFrames : (int) left;
+          for (int i = 0; i < nvalid; ++i) out = std::max(out, tp_frame<TPF>(win, NT + i));
+        }
+      }
+    }
+  }
+}
+
 static int log2u(uint32_t v) { int r = 0; while (v > 1) { v >>= 1; ++r; } return r; }
 
 static void run_query(const Plan& p, const Query& q, const std::vector<double>& zblock,
@@ -226,6 +372,18 @@ extern "C" int emu_measure(const lgb_track* tracks, size_t ntracks, uint32_t nal
   std::vector<ChunkRec> recs(p.total_recs);
   std::vector<float> peaks(2 * p.total_peaks, 0.0f), tps(p.total_peaks, 0.0f);
   for (const SweepGroup& g : p.groups) {
+    if (g.run) {
+      if (g.format == FMT_S16) {
+        if (g.tpf == 4) run_group_runs<FMT_S16, 4>(p, g, recs, peaks, tps);
+        else if (g.tpf == 2) run_group_runs<FMT_S16, 2>(p, g, recs, peaks, tps);
+        else run_group_runs<FMT_S16, 0>(p, g, recs, peaks, tps);
+      } else {
+        if (g.tpf == 4) run_group_runs<FMT_F32, 4>(p, g, recs, peaks, tps);
+        else if (g.tpf == 2) run_group_runs<FMT_F32, 2>(p, g, recs, peaks, tps);
+        else run_group_runs<FMT_F32, 0>(p, g, recs, peaks, tps);
+      }
+      continue;
+    }
     if (g.format == FMT_S16) {
       if (g.tpf == 4) run_group<FMT_S16, 4>(p, g, recs, peaks, tps);
       else if (g.tpf == 2) run_group<FMT_S16, 2>(p, g, recs, peaks, tps);
@@ -247,7 +405,7 @@ extern "C" int emu_measure(const lgb_track* tracks, size_t ntracks, uint32_t nal
       for (uint32_t ch = 0; ch < tr.channels; ++ch)
         echunk[tr.rec_base + chunk * tr.channels + ch] =
             chunk_true_energy(cs, recs.data() + tr.rec_base + ch, tr.channels, (long long) chunk,
-                              geo.o, log2u(tr.aq));
+                              geo.o, log2u(tr.aq), p.xi_table.data());
     }
     for (uint32_t s = 0; s < tr.nslots; ++s)
       eslot[tr.slot_base + s] = slot_energy(tr, cs, echunk.data(), s);
@@ -294,13 +452,15 @@ extern "C" void emu_plan_sizes(const lgb_track* tracks, size_t ntracks, uint64_t
   *total_st = p.total_st;
 }
 
-// Checks the 2-D TMA view of the plan against the lane geometry: for every
-// warp the planner marked for TMA staging (WarpWork::interior == 2) and every
-// lane, the tensor row of the lane's chunk must start at the lane's own frame
-// 0 and must lie inside the class's tensor.  Returns the number of TMA warps,
-// or -1 - (index of the first bad warp).
-extern "C" long long emu_check_tma_view(const lgb_track* tracks, size_t ntracks, uint64_t target_tasks,
-                                        long long* total_warps) {
+// Checks the run sweep's view of a plan (lg_run.cu stages rows of the track's
+// 2-D tensor: row y = run y, 16-byte pitched): every item's rows start on
+// 16-byte boundaries, the stages cover warm-up + run exactly, the warm-up is a
+// whole number of stages (so that its boxes come from row y - 1 and end at the
+// row's end), complete / partial rows are classified right, and every chunk of
+// every track is covered by exactly one lane.  Returns the number of items, or
+// -1 - (index of the first bad item).
+extern "C" long long emu_check_run_view(const lgb_track* tracks, size_t ntracks, uint64_t target_tasks,
+                                        long long* full_items) {
   std::vector<TrackIn> in(ntracks);
   for (size_t i = 0; i < ntracks; ++i)
     in[i] = TrackIn{tracks[i].pcm, tracks[i].frames, tracks[i].channels, tracks[i].samplerate,
@@ -308,35 +468,45 @@ extern "C" long long emu_check_tma_view(const lgb_track* tracks, size_t ntracks,
   Plan p;
   const PlanOptions opt = emu_options(target_tasks);
   build_plan(in.data(), ntracks, 0, opt, p);
-  long long ntma = 0;
-  *total_warps = (long long) p.work.size();
+  long long nitems = 0;
+  *full_items = 0;
+  std::vector<std::vector<int>> covered(ntracks);
+  for (size_t i = 0; i < ntracks; ++i) covered[i].assign(p.tracks[i].nchunks, 0);
   for (const SweepGroup& g : p.groups) {
+    if (!g.run) continue;
     const SweepParams& sp = g.params;
-    for (uint32_t w = 0; w < g.nwarps; ++w) {
-      const WarpWork& ww = p.work[g.first_warp + w];
-      if (ww.interior != 2) continue;
-      if (!sp.tma_m || sp.cpw != 32) return -1 - (long long) (g.first_warp + w);
-      const Track& tr = p.tracks[ww.track];
-      const long long m = sp.tma_m, mL = m * sp.L;
-      const long long stage_words = sp.stage_row_bytes / 4, wpf = sp.fb / 4;
-      const long long nstages = (sp.npairs + pair_pps(g.format) - 1) / pair_pps(g.format);
-      for (uint32_t lane = 0; lane < 32; ++lane) {
-        const long long chunk = ww.first_chunk + lane;
-        const int r = (int) (chunk % m);
-        const TmaClass tc = tma_class(sp.L, sp.W, (int) tr.aq, (int) m, r);
-        if (tc.shift != (int) ((sp.tma_shift >> r) & 1u)) return -1 - (long long) (g.first_warp + w);
-        const long long row = chunk / m - tc.shift;
-        const long long nrows = ((long long) tr.frames - tc.base_frame) / mL;
-        const LaneGeom geo = lane_geometry((long long) tr.frames, sp.L, sp.W, (int) tr.aq, chunk);
-        const bool ok = row >= 0 && row < nrows && tc.base_frame >= 0 &&
-                        (tc.base_frame * (long long) sp.fb) % 16 == 0 && (mL * sp.fb) % 16 == 0 &&
-                        tc.base_frame + row * mL == geo.a &&                       // row starts at the lane's frame 0
-                        (nstages * stage_words + kTmaBoxPad) <= mL * wpf &&          // boxes stay inside the row
-                        lane / 1 == lane;
-        if (!ok) return -1 - (long long) (g.first_warp + w);
+    for (uint32_t ii = 0; ii < g.nitems; ++ii) {
+      const RunItem it = p.items[g.first_item + ii];
+      const Track& tr = p.tracks[it.track];
+      const CoefSet& cs = p.coefs[tr.coef];
+      const long long Lr = (long long) cs.run_chunks * cs.L;
+      bool ok = sp.Lr == Lr && sp.Wp == cs.run_warm && sp.R == cs.run_chunks &&
+                (Lr * tr.fb) % 16 == 0 && ((long long) sp.Wp * tr.fb) % 16 == 0 &&
+                sp.Wp % (int) sp.run_stage_frames == 0 && sp.run_stage_frames % kPairFrames == 0 &&
+                Lr % kIter == 0 && sp.Wp % kPairFrames == 0 && Lr >= sp.Wp &&
+                (long long) sp.run_nstages * sp.run_stage_frames >= sp.Wp + Lr &&
+                (long long) (sp.run_nstages - 1) * sp.run_stage_frames < sp.Wp + Lr &&
+                (long long) sp.niters * kIter == sp.Wp + Lr && sp.xi_iters * kIter == sp.Wp + cs.xi_frames &&
+                it.first_run % 32 == 0 && it.first_run < tr.nruns &&
+                tr.nfull == tr.frames / (uint64_t) Lr && tr.nruns == (tr.frames + Lr - 1) / (uint64_t) Lr;
+      // rows [0, tail_rows) complete, row tail_rows partial or absent
+      for (uint32_t lane = 0; lane < 32 && ok; ++lane) {
+        const uint64_t run = it.first_run + lane;
+        const bool complete = (run + 1) * (uint64_t) Lr <= tr.frames;
+        ok = complete == (lane < it.tail_rows);
+        if (run < tr.nruns)
+          for (int j = 0; j < cs.run_chunks; ++j) {
+            const uint64_t c = run * cs.run_chunks + j;
+            if (c < tr.nchunks) ++covered[it.track][c];
+          }
       }
-      ++ntma;
+      if (!ok) return -1 - (long long) (g.first_item + ii);
+      ++nitems;
+      if (it.tail_rows == 32) ++*full_items;
     }
   }
-  return ntma;
+  for (size_t i = 0; i < ntracks; ++i)
+    if (p.tracks[i].nruns)
+      for (int c : covered[i]) if (c != 1) return -1000000 - (long long) i;
+  return nitems;
 }

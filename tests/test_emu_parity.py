@@ -209,27 +209,29 @@ def test_time_segments_with_lead_in(oracle):
 
 @pytest.mark.parametrize("rate,seconds,dtype", [(44100, 61.3, np.int16), (48000, 33.0, np.int16),
                                               (96000, 20.0, np.float32), (22050, 45.0, np.float32),
-                                              (44100, 0.9, np.int16)])
-def test_tma_view_matches_lane_geometry(rate, seconds, dtype):
-    """The 2-D tensor view the stereo sweep stages through (lg_common.h: tma_class;
-    maps built in lg_batch.cu) against the lane geometry, on the host: every
-    TMA-staged warp's rows start at the lanes' own frame 0, are 16-byte pitched
-    and lie inside the track; all but the first and last warps of a long track
-    qualify."""
+                                              (44100, 0.9, np.int16), (32000, 12.0, np.int16),
+                                              (11025, 30.0, np.float32), (192000, 6.0, np.int16)])
+def test_run_view_of_a_plan(rate, seconds, dtype, monkeypatch):
+    """The run sweep's view of a stereo track (lg_run.cu stages rows of a 2-D tensor,
+    row = run, through TMA): 16-byte pitched rows, stages that tile warm-up + run,
+    complete / partial rows classified right, every chunk owned by exactly one
+    lane -- on small and machine-filling plans."""
     import ctypes as C
     from tests.helpers import LgbTrack, build_emu
     lib = C.CDLL(build_emu())
-    lib.emu_check_tma_view.restype = C.c_longlong
+    lib.emu_check_run_view.restype = C.c_longlong
     n = int(rate * seconds)
     pcm = np.zeros((n, 2), dtype=dtype)
-    arr = (LgbTrack * 1)(LgbTrack(pcm.ctypes.data, n, 2, rate, 0 if dtype == np.int16 else 1,
+    arr = (LgbTrack * 2)(LgbTrack(pcm.ctypes.data, n, 2, rate, 0 if dtype == np.int16 else 1,
+                                  0xffffffff, None, 0),
+                         LgbTrack(pcm.ctypes.data, n // 3, 2, rate, 0 if dtype == np.int16 else 1,
                                   0xffffffff, None, 0))
-    total = C.c_longlong()
-    for tasks in (0, 148 * 2048):
-        ntma = lib.emu_check_tma_view(arr, C.c_size_t(1), C.c_uint64(tasks), C.byref(total))
-        assert ntma >= 0, f"warp {-1 - ntma} has an inconsistent tensor view"
-        if seconds > 10:
-            assert total.value - 3 <= ntma <= total.value - 1
+    full = C.c_longlong()
+    for sms in ("148", "4", "1"):
+        monkeypatch.setenv("LOUDGAIN_B200_SMS", sms)
+        got = lib.emu_check_run_view(arr, C.c_size_t(2), C.c_uint64(0), C.byref(full))
+        assert got >= 2, f"item {-1 - got} has an inconsistent view"
+        assert full.value <= got
 
 
 def test_tail_filler_plan(oracle, monkeypatch):
@@ -238,6 +240,7 @@ def test_tail_filler_plan(oracle, monkeypatch):
     stay within the parity goals, track by track and for the album."""
     specs = [synth.TrackSpec(seed=900 + i, rate=44100, channels=2, seconds=12.0 + 3 * i) for i in range(3)]
     tracks = [(synth.programme_s16(s).numpy(), s.rate) for s in specs]
+    monkeypatch.setenv("LOUDGAIN_B200_RUN", "0")       # the option belongs to the one-chunk-per-lane sweeps
     o = oracle_measure(oracle, tracks, albums=[0, 0, 0])
     base = emu_measure(tracks, albums=[0, 0, 0], target_tasks=2500)
     monkeypatch.setenv("LOUDGAIN_B200_TAIL_FRAC", "0.4")
