@@ -92,8 +92,10 @@ struct CoefSet {
   // --- sweep, FP32.  High-pass in "leaky double integrator" form
   //   q = x - x1 ; t = q - e2*w2 ; d = c*d1 + t ; w = w1 + d ; yh = d
   // (algebraically w[n] = q[n] - a1 w[n-1] - a2 w[n-2], yh = w - w1, q = x - x1)
-  // followed by the shelf  v = yh - p1 v1 - p2 v2 ; y = v + q1 v1 + q2 v2.
+  // followed by the shelf  v = yh - p1 v1 - p2 v2 ; y = v + q1 v1 + q2 v2
+  // (computed as y = yh + r1 v1 + r2 v2, r = q - p).
   float c, e2, p1, p2, q1, q2;
+  float r1, r2;     // q1 - p1, q2 - p2: the shelf's output taps on its OLD state
   // lambda = the high-pass pole (Im > 0).  The response of the K-weighted
   // output to a high-pass start state is, after the warm-up, Re(A lambda^f);
   // the sweep accumulates Xi = sum y[f] lambda^f with these constants.
@@ -215,7 +217,7 @@ LG_BOTH uint32_t chunks_per_warp(uint32_t channels) { return 32u / (channels < 3
 // set and channel count).  Passed by value as the kernel parameter, so the
 // filter constants reach the FMAs straight from the constant bank.
 struct SweepParams {
-  float c, ne2, np1, np2, q1, q2;
+  float c, ne2, np1, np2, r1, r2;
   float lam_re[kIter], lam_im[kIter];
   float rot_re, rot_im;
   float tp_bound;          // ||taps||_1 bound used for true-peak screening

@@ -124,6 +124,8 @@ inline void make_coefset(unsigned long rate, int k, double full_scale, CoefSet& 
   const double q1 = d.sb[1] / d.sb[0], q2 = d.sb[2] / d.sb[0];
   cs.q1 = (float) q1;
   cs.q2 = (float) q2;
+  cs.r1 = (float) (q1 - d.sa[1]);
+  cs.r2 = (float) (q2 - d.sa[2]);
   cs.gain = (d.sb[0] / full_scale) * (d.sb[0] / full_scale);
   const double M[4] = {d.c, -d.e2, 1.0, 1.0};   // (d1, w2) -> one frame later
   mat2_pow(M, (unsigned long) cs.L, cs.ML);

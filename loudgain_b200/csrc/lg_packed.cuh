@@ -25,7 +25,7 @@ __device__ __forceinline__ float2 k_step2(S& s, const float2 x, const SweepParam
   const float2 w = __fadd2_rn(s.w1, d);
   const float2 u = __ffma2_rn(bc2(k.np2), s.v2, d);
   const float2 v = __ffma2_rn(bc2(k.np1), s.v1, u);
-  const float2 y = __ffma2_rn(bc2(k.q2), s.v2, __ffma2_rn(bc2(k.q1), s.v1, v));
+  const float2 y = __ffma2_rn(bc2(k.r2), s.v2, __ffma2_rn(bc2(k.r1), s.v1, d));
   s.xp = x;
   s.w2 = s.w1; s.w1 = w; s.d1 = d;
   s.v2 = s.v1; s.v1 = v;

@@ -198,30 +198,31 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
     ChunkRec* recs = P.recs + tr.rec_base;
     uint32_t* cell = P.peaks + 2 * tr.peak_base;               // [ch][sample peak, true peak]
 
-    // ---- staging: stage s of the item -> ring slot
-    auto issue = [&](uint32_t s, uint32_t slot) {
-#ifdef LG_RUN_NOLOAD       // ablation: no HBM traffic, compute on whatever is in shared memory
-      return;
-#endif
+    // ---- staging.  The prefetch cursor walks the item's stages: the warm-up ones are the
+    // tail of the rows one above (rows first_run - 1 ... first_run + 30), then the rows
+    // themselves from their first frame on.
+    int pf_x = (P.Lr - Wp) * (int) WPF, pf_y = (int) it.first_run - 1;
+    uint32_t pf_s = 0, pf_slot = 0;
+    const uint32_t tail_bytes = (it.tail_rows + (has_partial ? 1u : 0u)) * G::kRowBytes;
+    auto issue = [&]() {
+#ifndef LG_RUN_NOLOAD       // (ablation: no HBM traffic, compute on whatever is in shared memory)
       if (elect_one()) {
-        const uint32_t bar = bar0 + 8u * slot;
-        const uint32_t dst = sm_base + slot * G::kSlotBytes;
-        if (s < warm_stages) {
-          // tail of the rows one above: rows first_run - 1 ... first_run + 30
+        const uint32_t bar = bar0 + 8u * pf_slot;
+        const uint32_t dst = sm_base + pf_slot * G::kSlotBytes;
+        if (!tail_item || pf_s < warm_stages) {
           mbar_arrive_expect_tx(bar, 32u * G::kRowBytes);
-          tma_load_2d(dst, maps, (int) ((uint32_t) (P.Lr - Wp) + s * SF) * (int) WPF, (int) it.first_run - 1, bar);
+          tma_load_2d(dst, maps, pf_x, pf_y, bar);
         } else {
-          const int x = (int) ((s - warm_stages) * SF * WPF);
-          if (!tail_item) {
-            mbar_arrive_expect_tx(bar, 32u * G::kRowBytes);
-            tma_load_2d(dst, maps, x, (int) it.first_run, bar);
-          } else {
-            mbar_arrive_expect_tx(bar, (it.tail_rows + (has_partial ? 1u : 0u)) * G::kRowBytes);
-            if (it.tail_rows) tma_load_2d(dst, maps + 128, x, (int) it.first_run, bar);
-            if (has_partial) tma_load_2d(dst + G::kAuxOff, maps + 256, x, 0, bar);
-          }
+          // a track's last item: its complete rows (smaller box), its partial row (one-row map)
+          mbar_arrive_expect_tx(bar, tail_bytes);
+          if (it.tail_rows) tma_load_2d(dst, maps + 128, pf_x, pf_y, bar);
+          if (has_partial) tma_load_2d(dst + G::kAuxOff, maps + 256, pf_x, 0, bar);
         }
       }
+#endif
+      pf_x += (int) (SF * WPF);
+      if (++pf_s == warm_stages) { pf_x = 0; ++pf_y; }
+      if (++pf_slot == (uint32_t) kRunRing) pf_slot = 0;
     };
 
     RunCtx c;
@@ -233,13 +234,19 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
     int nb = Wp + L;                               // lane-local frame where it ends
     float2 sp = bc2(0.0f), prev_pm = bc2(0.0f);    // lane's sample peak, previous pair's maxima
     // screening thresholds from the channel's peak cells (refreshed per stage)
-    uint32_t cellx = TP ? __ldcg(cell) : 0u, celly = TP ? __ldcg(cell + 2) : 0u;
-    float2 thr = make_float2(__uint_as_float(cellx) * thr_scale, __uint_as_float(celly) * thr_scale);
+    // The cells are fetched with 4-byte cp.async copies into the warp's shared memory and read
+    // from there at the next refresh: a register load in flight across stages is waited for at
+    // the top of the stage loop (the scoreboards do not survive the back-edge), a stall per refresh.
+    const uint32_t cellbuf = bar0 + 64u;
+    if (TP && lane < 2u) cp_async4(cellbuf + 4u * lane, cell + 2u * lane);
+    cp_async_commit();
+    float2 thr = bc2(0.0f);
     uint32_t seen_x = 0, seen_y = 0;               // what this warp last published
     // this lane's own stretch of the candidate queue, and how much of it is filled
     uint32_t* const qlane = P.run_queue + ((size_t) item * 32u + lane) * P.run_lane_stride;
     uint32_t* qp = qlane;
     if (!active) thr = make_float2(3.0e38f, 3.0e38f);          // lanes past the track's end queue nothing
+    // (until the first refresh, at the end of the first stage, every pair of an active lane is queued)
 
     auto close_chunk = [&]() {
       const uint32_t chunk = run * R + j;
@@ -263,7 +270,7 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
 
 #pragma unroll
     for (int i = 0; i < kRunRing - 1; ++i)
-      if ((uint32_t) i < nstages) issue((uint32_t) i, (uint32_t) i);
+      if ((uint32_t) i < nstages) issue();
 
     uint32_t slot = 0;
     float2 half_pm = bc2(0.0f);
@@ -273,10 +280,7 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
 #endif
       phase ^= 1u << slot;
       __syncwarp();                    // the previous stage is consumed by every lane
-      {
-        const uint32_t ps = s + kRunRing - 1;
-        if (ps < nstages) issue(ps, slot == 0 ? (uint32_t) kRunRing - 1 : slot - 1);
-      }
+      if (pf_s < nstages) issue();
       // the partial row of a track's last item comes from its own buffer in the main stages
       const uint32_t rowp = sm_base + slot * G::kSlotBytes +
                             ((partial_lane && s >= warm_stages) ? G::kAuxOff : lane * G::kRowBytes);
@@ -293,10 +297,11 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
           prev_pm = pm;
           const uint32_t ex = (pair << 16) | peak_code(cx), ey = 0x80000000u | (pair << 16) | peak_code(cy);
           const bool hx = cx > thr.x, hy = cy > thr.y;
+#ifndef LG_RUN_NOSTORE      // (ablation: screening without the queue)
           if (hx) *qp = ex;
-          qp += hx ? 1 : 0;
-          if (hy) *qp = ey;
-          qp += hy ? 1 : 0;
+          if (hy) qp[hx ? 1 : 0] = ey;
+#endif
+          qp += (hx ? 1 : 0) + (hy ? 1 : 0);
         }
       };
       const uint32_t pair0 = s * kPairsPerStageRun;
@@ -397,12 +402,16 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
         }
       }
 #endif
+#ifndef LG_RUN_NOFLOOR        // (ablation: thresholds from the item's start only)
       if (TP && ((s & 7u) == 7u || s < 2u)) {
         // after the first two stages, then every eighth: publish this warp's sample peak when it raises the cell, and
         // screen on against the larger of the two.  The cell values are the ones loaded at
         // the refresh before; the next load is issued here and used at the next refresh.
         const uint32_t ux = __reduce_max_sync(0xffffffffu, active ? __float_as_uint(sp.x * P.peak_scale) : 0u);
         const uint32_t uy = __reduce_max_sync(0xffffffffu, active ? __float_as_uint(sp.y * P.peak_scale) : 0u);
+        cp_async_wait<0>();
+        __syncwarp();
+        const uint32_t cellx = lds32(cellbuf), celly = lds32(cellbuf + 4u);
         if (lane == 0) {
           if (ux > cellx && ux > seen_x) atomicMax(cell, ux);
           if (uy > celly && uy > seen_y) atomicMax(cell + 2, uy);
@@ -410,8 +419,11 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
         seen_x = max(seen_x, ux); seen_y = max(seen_y, uy);
         if (active)
           thr = make_float2(__uint_as_float(max(cellx, ux)) * thr_scale, __uint_as_float(max(celly, uy)) * thr_scale);
-        cellx = __ldcg(cell); celly = __ldcg(cell + 2);
+        __syncwarp();                          // everyone has read the buffer before it is refilled
+        if (lane < 2u) cp_async4(cellbuf + 4u * lane, cell + 2u * lane);
+        cp_async_commit();
       }
+#endif
     }
     {
       const uint32_t ux = __reduce_max_sync(0xffffffffu, active ? __float_as_uint(sp.x * P.peak_scale) : 0u);
@@ -422,6 +434,7 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
       }
     }
     if (TP) P.run_counts[(size_t) item * 32u + lane] = (uint32_t) (qp - qlane);
+    cp_async_wait<0>();                // no cell fetch of this item's track may land in the next item's buffer
     __syncwarp();                      // every lane is done with the ring before the next item refills it
     uint32_t next = 0;
     if (lane == 0) next = atomicAdd(&s_ticket, 1u);

@@ -59,7 +59,7 @@ typedef SweepParams KCoef;
 
 // Host-side: the filter part of a SweepParams from a coefficient set.
 inline void fill_kcoef(const CoefSet& cs, SweepParams& k) {
-  k.c = cs.c; k.ne2 = -cs.e2; k.np1 = -cs.p1; k.np2 = -cs.p2; k.q1 = cs.q1; k.q2 = cs.q2;
+  k.c = cs.c; k.ne2 = -cs.e2; k.np1 = -cs.p1; k.np2 = -cs.p2; k.r1 = cs.r1; k.r2 = cs.r2;
   for (int i = 0; i < kIter; ++i) { k.lam_re[i] = cs.lam_re[i]; k.lam_im[i] = cs.lam_im[i]; }
   k.rot_re = cs.rot_re; k.rot_im = cs.rot_im;
 }
@@ -77,9 +77,11 @@ LG_HD float k_step(KState& s, float x, const KCoef& k) {
   const float t = fmaf(k.ne2, s.w2, q);
   const float d = fmaf(k.c, s.d1, t);
   const float w = s.w1 + d;
+  // shelf: v = d - p1 v1 - p2 v2 ; y = v + q1 v1 + q2 v2 = d + (q1 - p1) v1 + (q2 - p2) v2:
+  // the output does not wait for the new state (two short chains instead of one of four)
   const float u = fmaf(k.np2, s.v2, d);
   const float v = fmaf(k.np1, s.v1, u);
-  const float y = fmaf(k.q2, s.v2, fmaf(k.q1, s.v1, v));
+  const float y = fmaf(k.r2, s.v2, fmaf(k.r1, s.v1, d));
   s.xp = x;
   s.w2 = s.w1; s.w1 = w; s.d1 = d;
   s.v2 = s.v1; s.v1 = v;
