@@ -99,7 +99,6 @@ struct lgb_batch {
   uint32_t* d_runq = nullptr;          // candidate queues of the run-sweep groups (32-bit entries)
   uint32_t* d_runcnt = nullptr;        // [items * 32] candidates queued per sweep lane
   uint4* d_rundense = nullptr;      // the candidates that passed the final screening, packed
-  double* d_echunk = nullptr;
   double* d_eslot = nullptr;
   double* d_zblock = nullptr;
   double* d_zst = nullptr;
@@ -140,7 +139,7 @@ struct lgb_batch {
     DeviceTables t;
     t.tracks = d_tracks; t.coefs = d_coefs; t.work = d_work;
     t.queries = d_queries; t.members = d_members; t.lists = d_lists; t.recs = d_recs; t.peaks = d_peaks;
-    t.echunk = d_echunk; t.eslot = d_eslot; t.zblock = d_zblock; t.zst = d_zst;
+    t.eslot = d_eslot; t.zblock = d_zblock; t.zst = d_zst;
     t.results = d_results; t.xi_table = d_xi;
     return t;
   }
@@ -322,7 +321,6 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
             dalloc(&b->d_peaks, 2 * p.total_peaks + p.groups.size() + 1, b->stream) &&
             dalloc(&b->d_mrec, p.total_mrec, b->stream) &&
             dalloc(&b->d_tpq, 2 * p.total_mrec, b->stream) &&
-            dalloc(&b->d_echunk, p.total_recs, b->stream) &&
             dalloc(&b->d_eslot, p.total_slots, b->stream) &&
             dalloc(&b->d_zblock, p.total_blocks, b->stream) &&
             dalloc(&b->d_zst, p.total_st, b->stream) &&
@@ -389,7 +387,7 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
   b->sweep_launches = (uint32_t) p.groups.size();
   uint32_t tp_launches = 0;
   for (const SweepGroup& g : p.groups) tp_launches += g.tpf ? (g.params.packed ? 2u : 1u) : 0u;
-  b->launches = b->sweep_launches + tp_launches + (p.total_recs ? 1 : 0) + (p.total_slots ? 1 : 0) +
+  b->launches = b->sweep_launches + tp_launches + (p.total_slots ? 1 : 0) +
                 ((p.total_blocks + p.total_st) ? 1 : 0) + (p.queries.empty() ? 0 : 1);
   return b;
 }
@@ -763,7 +761,7 @@ extern "C" LG_EXPORT void lgb_batch_destroy(lgb_batch* b) {
   if (!b) return;
   if (b->ev0) { cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); cudaEventDestroy(b->ev2); }
   void* const mem[] = {b->d_tracks, b->d_coefs, b->d_work, b->d_queries, b->d_members, b->d_lists,
-                       b->d_recs, b->d_peaks, b->d_mrec, b->d_tpq, b->d_tmaps, b->d_items, b->d_xi, b->d_runq, b->d_runcnt, b->d_rundense, b->d_echunk, b->d_eslot, b->d_zblock, b->d_zst,
+                       b->d_recs, b->d_peaks, b->d_mrec, b->d_tpq, b->d_tmaps, b->d_items, b->d_xi, b->d_runq, b->d_runcnt, b->d_rundense, b->d_eslot, b->d_zblock, b->d_zst,
                        b->d_results};
   if (b->h_results) cudaStreamSynchronize(b->stream);   // a run may still be writing the mirrors
   for (void* m : mem) if (m) cudaFreeAsync(m, b->stream);

@@ -3,8 +3,7 @@
 //   sweep_kernel    fused K-weight + chunk energy + sample peak + true peak
 //                   (what ebur128_add_frames_short does per call in the
 //                   reference path, /root/reference/src/scan.c:448)
-//   fixup_kernel    FP64 state carry + energy correction per chunk
-//   slot_kernel     100 ms slot energies (channel-weighted)
+//   fixslot_kernel  FP64 state carry + energy correction + channel weighting: 100 ms slot energies
 //   block_kernel    400 ms gating blocks and 3 s short-term blocks
 //   query_kernel    gated integrated loudness and loudness range over a set
 //                   of tracks (ebur128_loudness_global[_multiple],
@@ -566,37 +565,20 @@ __device__ uint32_t find_track_cta(const Track* tracks, uint32_t ntracks, uint64
   return lo;
 }
 
-__global__ void __launch_bounds__(256)
-fixup_kernel(const Track* __restrict__ tracks, uint32_t ntracks,
-             const CoefSet* __restrict__ coefs, const ChunkRec* __restrict__ recs,
-             uint64_t total_recs, double* __restrict__ echunk, const cplx* __restrict__ xi_table) {
-  __shared__ uint64_t s_base[kTrackCache];
-  const uint64_t r = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t ti = find_track_cta(tracks, ntracks, r, r < total_recs, s_base,
-                                     [](const Track& t) { return t.rec_base; });
-  if (r >= total_recs) return;
-  const Track& tr = tracks[ti];
-  const CoefSet& cs = coefs[tr.coef];
-  const uint64_t local = r - tr.rec_base;
-  const uint64_t chunk = local / tr.channels;
-  const uint32_t ch = (uint32_t) (local - chunk * tr.channels);
-  if (chunk >= (uint64_t) tr.nslots * cs.k) return;   // tail chunks carry peaks only
-  const LaneGeom geo = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, (long long) chunk);
-  echunk[r] = chunk_true_energy(cs, recs + tr.rec_base + ch, tr.channels, (long long) chunk,
-                                geo.o, 31 - __clz((int) tr.aq), xi_table);
-}
-
-__global__ void __launch_bounds__(256)
-slot_kernel(const Track* __restrict__ tracks, uint32_t ntracks,
-            const CoefSet* __restrict__ coefs, const double* __restrict__ echunk,
-            uint64_t total_slots, double* __restrict__ eslot) {
+// FP64 state carry + energy correction + channel weighting, one thread per 100 ms slot
+// (lg_post.cuh: slot_energy_fused).
+__global__ void __launch_bounds__(128)
+fixslot_kernel(const Track* __restrict__ tracks, uint32_t ntracks, const CoefSet* __restrict__ coefs,
+               const ChunkRec* __restrict__ recs, uint64_t total_slots, double* __restrict__ eslot,
+               const cplx* __restrict__ xi_table) {
   __shared__ uint64_t s_base[kTrackCache];
   const uint64_t s = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t ti = find_track_cta(tracks, ntracks, s, s < total_slots, s_base,
                                      [](const Track& t) { return t.slot_base; });
   if (s >= total_slots) return;
   const Track& tr = tracks[ti];
-  eslot[s] = slot_energy(tr, coefs[tr.coef], echunk, (uint32_t) (s - tr.slot_base));
+  eslot[s] = slot_energy_fused(tr, coefs[tr.coef], recs, (uint32_t) (s - tr.slot_base), xi_table,
+                               31 - __clz((int) tr.aq));
 }
 
 __global__ void __launch_bounds__(256)
@@ -935,15 +917,10 @@ query_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ quer
 }
 
 cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t stream) {
-  if (z.total_recs) {
-    const unsigned blocks = (unsigned) ((z.total_recs + 255) / 256);
-    fixup_kernel<<<blocks, 256, 0, stream>>>(t.tracks, z.ntracks, t.coefs, t.recs, z.total_recs,
-                                            t.echunk, t.xi_table);
-  }
   if (z.total_slots) {
-    const unsigned blocks = (unsigned) ((z.total_slots + 255) / 256);
-    slot_kernel<<<blocks, 256, 0, stream>>>(t.tracks, z.ntracks, t.coefs, t.echunk, z.total_slots,
-                                           t.eslot);
+    const unsigned blocks = (unsigned) ((z.total_slots + 127) / 128);
+    fixslot_kernel<<<blocks, 128, 0, stream>>>(t.tracks, z.ntracks, t.coefs, t.recs, z.total_slots, t.eslot,
+                                              t.xi_table);
   }
   if (z.total_blocks + z.total_st) {
     const unsigned blocks = (unsigned) ((z.total_blocks + z.total_st + 255) / 256);
@@ -1010,11 +987,11 @@ cudaError_t launch_range_peaks(const void* pcm, uint32_t format, uint32_t channe
 }
 
 uint32_t query_cluster_size(uint64_t max_gating_blocks) {
-  // one more CTA per 32 k gating blocks of the largest query (about an hour of audio)
+  // one more CTA per 4 k gating blocks of the largest query (about seven minutes of audio)
   static const uint64_t per_cta = [] {
     const char* e = getenv("LOUDGAIN_B200_QUERY_BLOCKS_PER_CTA");   // tuning
     const long long v = e ? atoll(e) : 0;
-    return (uint64_t) (v > 0 ? v : 32768);
+    return (uint64_t) (v > 0 ? v : 4096);
   }();
   uint64_t r = max_gating_blocks / per_cta;
   return (uint32_t) (r < 1 ? 1 : (r > (uint64_t) kMaxQueryCluster ? kMaxQueryCluster : r));

@@ -22,7 +22,6 @@ struct DeviceTables {
   const cplx* xi_table;   // run sweep: mode-sum reference per chunk position (lg_design.h: make_run_coefs)
   ChunkRec* recs;       // [total_recs]
   uint32_t* peaks;      // [total_peaks][2]: sample peak, true peak (float bits)
-  double* echunk;       // [total_recs] corrected chunk energies
   double* eslot;        // [total_slots]
   double* zblock;       // [total_blocks]
   double* zst;          // [total_st]

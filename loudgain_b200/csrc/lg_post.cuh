@@ -29,21 +29,18 @@ LG_HD void mat2_vec(const double m[4], double x, double y, double& ox, double& o
 // xi_table[cs.xi_off + (j mod R)] (lg_design.h: make_run_coefs).  Chunks that
 // start past the run's mode-sum horizon have no cross term (the error has
 // decayed by 1e-5 there); the quadratic term is always exact.
-LG_HD double chunk_true_energy(const CoefSet& cs, const ChunkRec* recs, long long stride,
-                               long long j, int o, int aq_log2, const cplx* xi_table) {
-  // T = true high-pass state at the first frame of chunk j.
-  double td = 0.0, tw = 0.0;
-  long long i = j - cs.horner;
-  if (i < 0) i = 0;
-  for (; i < j; ++i) {
-    const ChunkRec& r = recs[i * stride];
-    // zero-state response of chunk i: R = Q - M^L P, then T <- R + M^L T
-    double mx, my;
-    mat2_vec(cs.ML, td - (double) r.pd, tw - (double) r.pw, mx, my);
-    td = (double) r.qd + mx;
-    tw = (double) r.qw + my;
-  }
-  const ChunkRec& r = recs[j * stride];
+// T <- Q + M^L (T - P): the true high-pass state one chunk on, given the lane's own
+// snapshots of that chunk.
+LG_HD void carry_step(const CoefSet& cs, const ChunkRec& r, double& td, double& tw) {
+  double mx, my;
+  mat2_vec(cs.ML, td - (double) r.pd, tw - (double) r.pw, mx, my);
+  td = (double) r.qd + mx;
+  tw = (double) r.qw + my;
+}
+
+// Energy of chunk j (record r) given the true high-pass state (td, tw) at its first frame.
+LG_HD double chunk_energy_at(const CoefSet& cs, const ChunkRec& r, double td, double tw, long long j, int o,
+                             int aq_log2, const cplx* xi_table) {
   if (cs.run_chunks > 0) {
     const double ad = td - (double) r.pd, aw = tw - (double) r.pw;
     const double Are = ad * cs.Ad.re + aw * cs.Aw.re, Aim = ad * cs.Ad.im + aw * cs.Aw.im;
@@ -72,20 +69,48 @@ LG_HD double chunk_true_energy(const CoefSet& cs, const ChunkRec* recs, long lon
   return r.e0 + 2.0 * cross + quad;
 }
 
+LG_HD double chunk_true_energy(const CoefSet& cs, const ChunkRec* recs, long long stride,
+                               long long j, int o, int aq_log2, const cplx* xi_table) {
+  // T = true high-pass state at the first frame of chunk j.
+  double td = 0.0, tw = 0.0;
+  long long i = j - cs.horner;
+  if (i < 0) i = 0;
+  for (; i < j; ++i) carry_step(cs, recs[i * stride], td, tw);
+  return chunk_energy_at(cs, recs[j * stride], td, tw, j, o, aq_log2, xi_table);
+}
+
 LG_HD double weight_of(uint8_t wclass) {
   return wclass == 1 ? 1.0 : (wclass == 2 ? 1.41 : (wclass == 3 ? 2.0 : 0.0));
 }
 
-// Weighted, scaled energy (sum over frames, not yet the mean) of one slot.
-LG_HD double slot_energy(const Track& tr, const CoefSet& cs, const double* echunk,
-                         uint32_t slot) {
+// Weighted, scaled energy (sum over frames, not yet the mean) of one 100 ms slot,
+// straight from the sweep's records: per channel one pass of the state
+// carry from `horner` chunks before the slot through its k chunks (what the
+// fix-up and slot kernels did in two steps; the carry is shared by the slot's
+// chunks instead of being restarted for each).
+LG_HD double slot_energy_fused(const Track& tr, const CoefSet& cs, const ChunkRec* recs, uint32_t slot,
+                               const cplx* xi_table, int aq_log2) {
   double total = 0.0;
+  const long long j0 = (long long) slot * cs.k;
   for (uint32_t c = 0; c < tr.channels; ++c) {
     const double w = weight_of(tr.wclass[c]);
     if (w == 0.0) continue;
+    const ChunkRec* rc = recs + tr.rec_base + c;
+    const long long stride = tr.channels;
+    double td = 0.0, tw = 0.0;
+    long long i = j0 - cs.horner;
+    if (i < 0) i = 0;
+    for (; i < j0; ++i) carry_step(cs, rc[i * stride], td, tw);
     double s = 0.0;
-    const uint64_t base = tr.rec_base + (uint64_t) slot * cs.k * tr.channels + c;
-    for (int i = 0; i < cs.k; ++i) s += echunk[base + (uint64_t) i * tr.channels];
+    for (int q = 0; q < cs.k; ++q) {
+      const long long j = j0 + q;
+      const ChunkRec& r = rc[j * stride];
+      int o = 0;
+      if (cs.run_chunks == 0)
+        o = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, j).o;
+      s += chunk_energy_at(cs, r, td, tw, j, o, aq_log2, xi_table);
+      carry_step(cs, r, td, tw);
+    }
     total += w * s;
   }
   return total * cs.gain;

@@ -494,36 +494,35 @@ constexpr int kTpRunThreads = 128;
 // that touches the track's ends (or its lead-in) carries (item, lane) in .x and
 // (channel, pair) in .w instead and is located again by the evaluation.
 constexpr uint32_t kTpInterior = 0xffffffffu;
+// One CTA of 8 warps per item; warp w reads the stretches of sweep lanes 4w ... 4w + 3,
+// 32 consecutive entries per load (coalesced), so the whole item is in flight at once.
+constexpr int kTpFilterThreads = 256;
+
 template <int FMT, int TPF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kTpFilterThreads)
 tp_filter_run_kernel(const __grid_constant__ SweepParams P) {
   constexpr int NT = TpTraits<TPF>::kTaps;
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < P.nitems; item += warps) {
-    const uint32_t slot = item * 32u + lane;
-    const uint32_t count = __ldcg(P.run_counts + slot);
-    if (!__any_sync(0xffffffffu, count != 0u)) continue;
+  __shared__ uint32_t s_warp[kTpFilterThreads / 32 + 1];
+  const uint32_t lane = threadIdx.x & 31u, wic = threadIdx.x >> 5;
+  for (uint32_t item = blockIdx.x; item < P.nitems; item += gridDim.x) {
     const RunItem it = P.items[item];
     const Track& tr = P.tracks[it.track];
     const uint32_t cell0 = (uint32_t) tr.peak_base;
     const uint32_t* cell = P.peaks + 2 * (size_t) cell0;
     const float f0 = __uint_as_float(__ldcg(cell)), f1 = __uint_as_float(__ldcg(cell + 2));
     const long long frames = (long long) tr.frames, lead_in = (long long) tr.lead_in;
-    const long long a = (long long) (it.first_run + lane) * P.Lr - P.Wp;      // track frame of the lane's frame 0
     const unsigned char* pcm = reinterpret_cast<const unsigned char*>(tr.pcm);
-    // the lane's stretch is read with 16-byte loads (run_lane_stride is a multiple of 4)
-    const uint4* q = reinterpret_cast<const uint4*>(P.run_queue + (size_t) slot * P.run_lane_stride);
     auto pass = [&](uint32_t e) {
       return P.tp_bound * (peak_code_value(e & 0xffffu) * P.peak_scale) > ((e >> 31) ? f1 : f0);
     };
-    const uint32_t nvec = (count + 3u) >> 2;
-    uint32_t mine = 0;
-    for (uint32_t i = 0; i < nvec; ++i) {
-      const uint4 v = __ldcg(q + i);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    // ---- count
+    uint32_t cnt[4], mine = 0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) mine += (4u * i + k < count && pass(w[k])) ? 1u : 0u;
+    for (int k = 0; k < 4; ++k) cnt[k] = __ldcg(P.run_counts + item * 32u + 4u * wic + k);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t* q = P.run_queue + ((size_t) item * 32u + 4u * wic + k) * P.run_lane_stride;
+      for (uint32_t i = lane; i < cnt[k]; i += 32u) mine += pass(__ldg(q + i)) ? 1u : 0u;
     }
     uint32_t incl = mine;
 #pragma unroll
@@ -531,26 +530,33 @@ tp_filter_run_kernel(const __grid_constant__ SweepParams P) {
       const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= (uint32_t) o) incl += v;
     }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    if (!total) continue;
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(P.tp_ticket, total);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    uint4* out = reinterpret_cast<uint4*>(P.tp_dense) + base + (incl - mine);
-    for (uint32_t i = 0; i < nvec; ++i) {
-      const uint4 v = __ldcg(q + i);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    __syncthreads();                       // s_warp is free again
+    if (lane == 31) s_warp[wic] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t total = 0;
+      for (int w = 0; w < kTpFilterThreads / 32; ++w) { const uint32_t c = s_warp[w]; s_warp[w] = total; total += c; }
+      s_warp[kTpFilterThreads / 32] = total ? atomicAdd(P.tp_ticket, total) : 0u;
+    }
+    __syncthreads();
+    // ---- write: this thread's survivors go to base + (warps before) + (lanes before), in the
+    // order it met them
+    uint4* out = reinterpret_cast<uint4*>(P.tp_dense) + s_warp[kTpFilterThreads / 32] + s_warp[wic] + (incl - mine);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t e = w[k];
-        if (!(4u * i + k < count && pass(e))) continue;
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t sl = item * 32u + 4u * wic + k;
+      const uint32_t* q = P.run_queue + (size_t) sl * P.run_lane_stride;
+      const long long a = (long long) (it.first_run + 4u * wic + k) * P.Lr - P.Wp;   // track frame of the lane's frame 0
+      for (uint32_t i = lane; i < cnt[k]; i += 32u) {
+        const uint32_t e = __ldg(q + i);
+        if (!pass(e)) continue;
         const uint32_t ch = e >> 31, pair = (e >> 16) & 0x7fffu;
         const long long t0 = a + (long long) pair * kPairFrames;
         if (t0 >= NT && t0 + kPairFrames <= frames && t0 >= lead_in) {
           const unsigned long long p = (unsigned long long) (pcm + (t0 - NT) * (long long) P.fb) | ch;
           *out++ = make_uint4((uint32_t) p, (uint32_t) (p >> 32), cell0 + ch, kTpInterior);
         } else {
-          *out++ = make_uint4(slot, 0u, cell0 + ch, (ch << 15) | pair);
+          *out++ = make_uint4(sl, 0u, cell0 + ch, (ch << 15) | pair);
         }
       }
     }
@@ -630,8 +636,8 @@ static cudaError_t launch_tp_run_t(const SweepParams& p, uint32_t sms, cudaStrea
             cudaSuccess || per_sm < 1)
       per_sm = 4;
   }
-  const uint32_t fblocks = (p.nitems + 7u) / 8u;            // one warp per item
-  tp_filter_run_kernel<FMT, TPF><<<fblocks < sms * 8u ? fblocks : sms * 8u, 256, 0, stream>>>(p);
+  const uint32_t fblocks = p.nitems < sms * 8u ? p.nitems : sms * 8u;          // one CTA per item at a time
+  tp_filter_run_kernel<FMT, TPF><<<fblocks, kTpFilterThreads, 0, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess && hold) e = cudaStreamWaitEvent(stream, hold, 0);
   if (e != cudaSuccess) return e;

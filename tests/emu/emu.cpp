@@ -394,21 +394,14 @@ extern "C" int emu_measure(const lgb_track* tracks, size_t ntracks, uint32_t nal
       else run_group<FMT_F32, 0>(p, g, recs, peaks, tps);
     }
   }
-  std::vector<double> echunk(p.total_recs, 0.0), eslot(p.total_slots), zblock(p.total_blocks),
+  std::vector<double> eslot(p.total_slots), zblock(p.total_blocks),
       zst(p.total_st);
   for (size_t ti = 0; ti < ntracks; ++ti) {
     const Track& tr = p.tracks[ti];
     const CoefSet& cs = p.coefs[tr.coef];
     if (chunk_len_out) chunk_len_out[ti] = cs.L;
-    for (uint64_t chunk = 0; chunk < (uint64_t) tr.nslots * cs.k; ++chunk) {
-      const LaneGeom geo = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, (long long) chunk);
-      for (uint32_t ch = 0; ch < tr.channels; ++ch)
-        echunk[tr.rec_base + chunk * tr.channels + ch] =
-            chunk_true_energy(cs, recs.data() + tr.rec_base + ch, tr.channels, (long long) chunk,
-                              geo.o, log2u(tr.aq), p.xi_table.data());
-    }
     for (uint32_t s = 0; s < tr.nslots; ++s)
-      eslot[tr.slot_base + s] = slot_energy(tr, cs, echunk.data(), s);
+      eslot[tr.slot_base + s] = slot_energy_fused(tr, cs, recs.data(), s, p.xi_table.data(), log2u(tr.aq));
     for (uint32_t b = 0; b < tr.nblocks; ++b)
       zblock[tr.block_base + b] = gating_block(eslot.data() + tr.slot_base, cs, b);
     for (uint32_t j = 0; j < tr.nst; ++j)

@@ -105,3 +105,55 @@ def test_tag_values_at_reference_precision(L):
     assert buf.value.decode().splitlines() == ["R128_TRACK_GAIN=%d" % round(-8.544 * 256),
                                                "R128_ALBUM_GAIN=%d" % round(-7.996 * 256)]
     assert L.lgb_format_tags(r, 1, 1, 0, b"dB", None, 0) == n      # length query
+
+
+# ---- the reference's own numbers: docs/images/test-{1,2,3}.csv.png -------------------------
+
+def _golden_rows():
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loudgain_O_rows.json")
+    return json.load(open(path))
+
+
+def test_reference_screenshot_tables(L):
+    """The three `-O` tables of the reference's README (transcribed to
+    tests/golden/loudgain_O_rows.json).  The tables print loudness with two
+    decimals only, so the unrounded loudness of a row is recovered from test-1
+    (no clipping prevention: New_Peak = 10^(gain/20) * True_Peak with gain = -18 - L,
+    scan.c:64,317) and must round back to the printed value; lgb_clip_prevention +
+    lgb_format_tab_row then have to reproduce every column of all three tables
+    (loudgain.c:323-379,586-612): text columns exactly, the 6-decimal peaks to the
+    last digit the 6-digit inputs determine."""
+    g = _golden_rows()
+    n = len(g["names"]) - 1                       # tracks; the last row is the album
+    t1 = g["tables"]["test-1"]
+    loud = [-18.0 - 20.0 * math.log10(t1["new_peak"][i] / g["true_peak"][i]) for i in range(n + 1)]
+    for i in range(n + 1):
+        assert "%.2f" % loud[i] == "%.2f" % g["loudness"][i]
+    buf = C.create_string_buffer(1024)
+    for name, t in g["tables"].items():
+        pre = t["pre_gain"]
+        for i in range(n):
+            # scan_get_track_result / scan_set_album_result (scan.c:317,327,399-403)
+            r = ScanResult(-18.0 - loud[i] + pre, g["true_peak"][i], loud[i], g["range"][i],
+                           -18.0 - loud[n] + pre, g["true_peak"][n], loud[n], g["range"][n], -18.0 + pre)
+            c = ClipInfo()
+            assert L.lgb_clip_prevention(r, 1, 1 if t["prevent"] else 0, g["max_true_peak_db"], c) == 0
+            rows = []
+            L.lgb_format_tab_row(g["names"][i].encode(), r, c, 0, b"dB", buf, 1024)
+            rows.append((i, buf.value.decode()))
+            if i == n - 1:                        # loudgain prints the album after the last track
+                L.lgb_format_tab_row(b"Album", r, c, 1, b"dB", buf, 1024)
+                rows.append((n, buf.value.decode()))
+            for k, row in rows:
+                cols = row.rstrip("\n").split("\t")
+                assert len(cols) == len(g["columns"])
+                want = [g["names"][k], "%.2f LUFS" % g["loudness"][k], "%.2f dB" % g["range"][k],
+                        "%.6f" % g["true_peak"][k], "%.2f dBTP" % g["true_peak_db"][k],
+                        "%.2f LUFS" % t["reference"], t["will_clip"][k], t["clip_prevent"][k],
+                        "%.2f dB" % t["gain"][k], None, "%.2f dBTP" % t["new_peak_db"][k]]
+                for col, (got, exp) in enumerate(zip(cols, want)):
+                    if exp is not None:
+                        assert got == exp, (name, k, g["columns"][col], got, exp)
+                assert abs(float(cols[9]) - t["new_peak"][k]) <= 2.5e-6, (name, k, cols[9])
