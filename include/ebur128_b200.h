@@ -42,7 +42,13 @@ typedef struct {
                                   longer stream (lgb_slots_query).  They warm the filters and
                                   the interpolator; no true-peak output is taken inside them.
                                   Must be a whole number of 100 ms slots.  0 = a whole track. */
+  uint32_t flags;              /* LGB_TRACK_* */
 } lgb_track;
+
+/* EBUR128_MODE_HISTOGRAM semantics for this track: its 400 ms and 3 s block energies
+ * are replaced by the centre energies of libebur128's 0.1 LU histogram bins (blocks
+ * below -70 LUFS are dropped) before any gate, sum or percentile sees them. */
+#define LGB_TRACK_HISTOGRAM 1u
 
 typedef struct {
   double loudness;             /* LUFS; -HUGE_VAL if nothing passed the gates */
@@ -133,6 +139,50 @@ lgb_listquery* lgb_listquery_create(const double* const* z, const uint32_t* nz,
 int lgb_listquery_run(lgb_listquery* q);
 int lgb_listquery_fetch(lgb_listquery* q, lgb_result* out);
 void lgb_listquery_destroy(lgb_listquery* q);
+
+/* Device PCM the drop-in ebur128_* layer holds for all live states: current bytes,
+ * high-water mark, and how many release passes have run.  States keep their PCM
+ * in HBM until they are measured; when the total outgrows
+ * LOUDGAIN_B200_PCM_BUDGET_MB (default 32768) the complete part of every state is
+ * measured in one batch, its 100 ms energies and peaks are kept and the PCM is
+ * freed (libebur128 itself keeps only block energies per state; scan.c:98-108
+ * keeps every state alive until scan_deinit).  Any pointer may be NULL. */
+void lgb_dropin_pcm_bytes(uint64_t* now, uint64_t* peak, uint64_t* releases);
+
+/* ---- albums whose tracks were measured on several GPUs --------------------
+ * ebur128_loudness_global_multiple / _range_multiple (scan.c:383-391) over
+ * states that live on different ranks (one process per GPU; bin/rgbpm2:150-175
+ * is the reference's process-per-album model).  Every rank creates an exchange
+ * region in its own HBM, the 64-byte handles are passed around by the host
+ * (any transport; torch.distributed in engine.py), and every rank opens the
+ * others' regions (CUDA IPC: the GPUs must have peer access, i.e. NVLink /
+ * NVSwitch).  A batch with an exchange attached answers its ALBUM queries
+ * together with the other ranks: album indices are global (the same nalbums
+ * on every rank; a rank may hold no track of an album), per-track results stay
+ * local.  Inside a run each rank reduces its own gating blocks; its kernels
+ * store (sum, count) pairs and the short-term energies straight into the
+ * peers' regions and wait on per-rank flags -- no host round trip, the whole
+ * step stays one CUDA graph.  Every rank must run the batch the same number
+ * of times; a rank that never arrives makes lgb_batch_fetch fail after 20 s.
+ *
+ * st_capacity: the largest lgb_batch_album_shortterm_blocks() of any rank. */
+typedef struct lgb_exchange lgb_exchange;
+lgb_exchange* lgb_exchange_create(uint32_t world, uint32_t rank, uint32_t nalbums,
+                                  uint64_t st_capacity);
+/* Writes this rank's 64-byte handle. 0 on success. */
+int lgb_exchange_handle(lgb_exchange* x, void* out, size_t cap);
+/* handles: world x 64 bytes in rank order (the own entry is ignored). */
+int lgb_exchange_open(lgb_exchange* x, const void* handles);
+void lgb_exchange_destroy(lgb_exchange* x);
+/* 3 s short-term blocks of all tracks of the batch that belong to an album. */
+uint64_t lgb_batch_album_shortterm_blocks(const lgb_batch* b);
+/* Before the batch is run (or between runs, after a fetch). 0 on success. */
+int lgb_batch_attach_exchange(lgb_batch* b, lgb_exchange* x);
+
+/* Longest-processing-time-first assignment of `n` work items (tracks; cost =
+ * frames x channels) to `world` ranks: rank_out[i] = rank of item i.  Host
+ * arithmetic only.  Returns the largest rank load. */
+uint64_t lgb_lpt_assign(const uint64_t* cost, size_t n, uint32_t world, uint32_t* rank_out);
 
 /* ---- scan.c-shaped host driver -------------------------------------------
  * Replays the reference scanner's call sequence against the ebur128_* ABI of

@@ -29,6 +29,7 @@ SUCCESS, ERROR_NOMEM, ERROR_INVALID_MODE, ERROR_INVALID_CHANNEL_INDEX, ERROR_NO_
 
 # enum channel (subset used by tests)
 UNUSED, LEFT, RIGHT, CENTER, LEFT_SURROUND, RIGHT_SURROUND, DUAL_MONO = range(7)
+Mp060, Mm060, Mp090, Mm090 = 9, 10, 11, 12        # include/ebur128.h: side positions, weight 1.41
 
 
 class StateStruct(C.Structure):
@@ -249,6 +250,15 @@ class State:
 
     def set_channel(self, ch: int, role: int) -> int:
         return self._lib.lib.ebur128_set_channel(self.ptr, ch, role)
+
+    def change_parameters(self, channels: int, samplerate: int) -> int:
+        return self._lib.lib.ebur128_change_parameters(self.ptr, channels, samplerate)
+
+    def set_max_history(self, history_ms: int) -> int:
+        return self._lib.lib.ebur128_set_max_history(self.ptr, history_ms)
+
+    def set_max_window(self, window_ms: int) -> int:
+        return self._lib.lib.ebur128_set_max_window(self.ptr, window_ms)
 
     def sample_peaks(self) -> list[float]:
         return [self.sample_peak(c) for c in range(self.channels)]

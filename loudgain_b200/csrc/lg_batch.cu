@@ -70,6 +70,32 @@ int query_lists_sync(const BlockList* lists, size_t n, cudaStream_t stream, Quer
   return ok ? 0 : 1;
 }
 
+int query_each_sync(const BlockList* lists, size_t n, cudaStream_t stream, QueryResult* out) {
+  if (!n) return 0;
+  std::vector<BlockList> hl(lists, lists + n);
+  std::vector<uint32_t> hm(n);
+  std::vector<Query> hq(n);
+  uint64_t largest = 0;
+  for (size_t i = 0; i < n; ++i) {
+    hm[i] = (uint32_t) i;
+    hq[i] = Query{(uint32_t) i, 1u};
+    if (lists[i].nz > largest) largest = lists[i].nz;
+  }
+  BlockList* dl = nullptr; uint32_t* dm = nullptr; Query* dq = nullptr; QueryResult* dr = nullptr;
+  bool ok = upload(hl, &dl, stream) && upload(hm, &dm, stream) && upload(hq, &dq, stream) &&
+            dalloc(&dr, n, stream);
+  if (ok) {
+    cudaError_t e = launch_queries(dl, dq, dm, (uint32_t) n, pow(10.0, (-70.0 + 0.691) / 10.0), dr, stream,
+                                   query_cluster_size(largest));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dr, n * sizeof(QueryResult), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { set_error("query_each_sync", e); ok = false; }
+  }
+  cudaFreeAsync(dl, stream); cudaFreeAsync(dm, stream); cudaFreeAsync(dq, stream);
+  cudaFreeAsync(dr, stream);
+  return ok ? 0 : 1;
+}
+
 }  // namespace lg
 
 using namespace lg;
@@ -78,6 +104,18 @@ static void to_result(const QueryResult& q, lgb_result& r) {
   r.loudness = q.loudness; r.range = q.range; r.rel_threshold = q.rel_thr;
   r.sum_abs = q.sum1; r.sum_rel = q.sum2; r.n_abs = q.n1; r.n_rel = q.n2; r.n_shortterm = q.nst;
 }
+
+// Exchange region of one rank for album queries over tracks on several GPUs
+// (lg_common.h: XchgParams; kernels in lg_kernels.cu).
+struct lgb_exchange {
+  uint32_t world = 1, rank = 0, nalbums = 0;
+  uint64_t st_cap = 0;
+  unsigned char* region = nullptr;               // cudaMalloc (IPC-exportable), this rank's
+  unsigned char* peer[kMaxWorld] = {nullptr};    // every rank's region as mapped here
+  bool opened = false;
+  unsigned long long* d_ctl = nullptr;           // [8]: step, CTA counters, time-outs
+  unsigned long long* h_ctl = nullptr;           // pinned mirror of the time-out counter
+};
 
 struct lgb_batch {
   Plan plan;
@@ -126,9 +164,13 @@ struct lgb_batch {
   int ngstreams = 0;
   uint32_t pair_ctas = 0;            // tuning: cap on resident CTAs per SM of the packed sweep (0 = none)
   cudaEvent_t ev_blocks = nullptr;   // block lists of the current run are complete (lgb_batch_wait_blocks)
+  const double* hist_tab = nullptr;  // set when a track asks for histogram-mode block energies
   double abs_gate = 0.0;
   uint32_t launches = 0, sweep_launches = 0, sms = 148;
   uint32_t query_cluster = 1;        // CTAs per query (lg_kernels.cu: query_kernel)
+  // album queries answered together with other ranks (lgb_batch_attach_exchange)
+  lgb_exchange* xchg = nullptr;
+  uint32_t* d_xstoff = nullptr;
   // optional sweep timing
   bool timing = false, timed_run_pending = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -140,7 +182,7 @@ struct lgb_batch {
     t.tracks = d_tracks; t.coefs = d_coefs; t.work = d_work;
     t.queries = d_queries; t.members = d_members; t.lists = d_lists; t.recs = d_recs; t.peaks = d_peaks;
     t.eslot = d_eslot; t.zblock = d_zblock; t.zst = d_zst;
-    t.results = d_results; t.xi_table = d_xi;
+    t.results = d_results; t.xi_table = d_xi; t.hist_tab = hist_tab;
     return t;
   }
 };
@@ -263,6 +305,7 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
                                        void* cuda_stream) {
   g_error.clear();
   std::vector<TrackIn> in(ntracks);
+  bool any_hist = false;
   for (size_t i = 0; i < ntracks; ++i) {
     const lgb_track& t = tracks[i];
     if (t.channels == 0 || t.channels > (uint32_t) kMaxChannels || t.samplerate < 16 ||
@@ -281,9 +324,15 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
       return nullptr;
     }
     in[i] = TrackIn{t.pcm, t.frames, t.channels, t.samplerate, t.format, t.album, t.weight_class,
-                    t.lead_in};
+                    t.lead_in, t.flags & LGB_TRACK_HISTOGRAM};
+    any_hist = any_hist || (t.flags & LGB_TRACK_HISTOGRAM);
   }
   lgb_batch* b = new lgb_batch();
+  if (any_hist && !(b->hist_tab = hist_table())) {
+    set_error("lgb_batch_create: the histogram table could not be created");
+    delete b;
+    return nullptr;
+  }
   b->stream = (cudaStream_t) cuda_stream;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -501,8 +550,29 @@ static int enqueue_step(lgb_batch* b) {
   }
   if (b->timing) cudaEventRecord(b->ev2, b->stream);
   if (!fork && post_kernels()) return 1;
-  e = launch_queries(t.lists, t.queries, t.members, (uint32_t) p.queries.size(), b->abs_gate,
-                     t.results, ps, b->query_cluster);
+  if (b->xchg) {
+    // albums span ranks: this rank's share goes out first, the track queries hide the
+    // peers' latency, then the album totals are gated (lg_kernels.cu: xchg_*_kernel)
+    lgb_exchange* x = b->xchg;
+    XchgParams xp{};
+    xp.world = x->world; xp.rank = x->rank; xp.nalbums = x->nalbums;
+    xp.first_query = (uint32_t) p.tracks.size();
+    xp.st_cap = x->st_cap;
+    for (uint32_t r = 0; r < x->world; ++r) xp.peer[r] = x->peer[r];
+    xp.st_off = b->d_xstoff;
+    xp.ctl = x->d_ctl;
+    e = launch_exchange_publish(t.lists, t.queries, t.members, b->abs_gate, xp, ps);
+    if (e == cudaSuccess)
+      e = launch_queries(t.lists, t.queries, t.members, (uint32_t) p.tracks.size(), b->abs_gate, t.results,
+                         ps, 1);
+    if (e == cudaSuccess)
+      e = launch_exchange_finish(t.lists, t.queries, t.members, b->abs_gate, t.results, xp, ps);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(x->h_ctl, x->d_ctl + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ps);
+  } else {
+    e = launch_queries(t.lists, t.queries, t.members, (uint32_t) p.queries.size(), b->abs_gate,
+                       t.results, ps, b->query_cluster);
+  }
   if (e != cudaSuccess) { set_error("launch_queries", e); return 1; }
   if (fork) {
     e = cudaEventRecord(b->ev_join, b->side);
@@ -550,6 +620,10 @@ extern "C" LG_EXPORT int lgb_batch_fetch(lgb_batch* b, lgb_result* track_results
   const Plan& p = b->plan;
   const cudaError_t e = cudaStreamSynchronize(b->stream);
   if (e != cudaSuccess) { set_error("lgb_batch_fetch", e); return 1; }
+  if (b->xchg && *b->xchg->h_ctl) {
+    set_error("lgb_batch_fetch: a rank of the album exchange did not arrive (timed out)");
+    return 1;
+  }
   if (b->timed_run_pending) {
     float ms = 0.0f;
     if (cudaEventElapsedTime(&ms, b->ev0, b->ev1) == cudaSuccess) {
@@ -757,12 +831,104 @@ extern "C" LG_EXPORT void lgb_listquery_destroy(lgb_listquery* q) {
   delete q;
 }
 
+// ---- album exchange across ranks ------------------------------------------------
+extern "C" LG_EXPORT lgb_exchange* lgb_exchange_create(uint32_t world, uint32_t rank, uint32_t nalbums,
+                                                       uint64_t st_capacity) {
+  g_error.clear();
+  if (world < 1 || world > kMaxWorld || rank >= world) {
+    set_error("lgb_exchange_create: world must be 1..16 and rank < world");
+    return nullptr;
+  }
+  lgb_exchange* x = new lgb_exchange();
+  x->world = world; x->rank = rank; x->nalbums = nalbums;
+  x->st_cap = st_capacity ? st_capacity : 1;
+  const size_t bytes = xchg_region_bytes(world, nalbums, x->st_cap);
+  const unsigned long long ctl0[8] = {1ull, 0, 0, 0, 0, 0, 0, 0};      // steps count from 1: flags start at 0
+  cudaError_t e = cudaMalloc((void**) &x->region, bytes);
+  if (e == cudaSuccess) e = cudaMemset(x->region, 0, bytes);
+  if (e == cudaSuccess) e = cudaMalloc((void**) &x->d_ctl, sizeof ctl0);
+  if (e == cudaSuccess) e = cudaMemcpy(x->d_ctl, ctl0, sizeof ctl0, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMallocHost((void**) &x->h_ctl, sizeof(unsigned long long));
+  if (e != cudaSuccess) {
+    set_error("lgb_exchange_create", e);
+    lgb_exchange_destroy(x);
+    return nullptr;
+  }
+  *x->h_ctl = 0;
+  x->peer[rank] = x->region;
+  return x;
+}
+
+extern "C" LG_EXPORT int lgb_exchange_handle(lgb_exchange* x, void* out, size_t cap) {
+  if (cap < sizeof(cudaIpcMemHandle_t)) { set_error("lgb_exchange_handle: 64 bytes are needed"); return 1; }
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, x->region);
+  if (e != cudaSuccess) { set_error("cudaIpcGetMemHandle", e); return 1; }
+  memcpy(out, &h, sizeof h);
+  return 0;
+}
+
+extern "C" LG_EXPORT int lgb_exchange_open(lgb_exchange* x, const void* handles) {
+  for (uint32_t r = 0; r < x->world; ++r) {
+    if (r == x->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const unsigned char*) handles + (size_t) r * sizeof h, sizeof h);
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { set_error("cudaIpcOpenMemHandle (peer access between the GPUs is required)", e); return 1; }
+    x->peer[r] = (unsigned char*) p;
+  }
+  x->opened = true;
+  return 0;
+}
+
+extern "C" LG_EXPORT void lgb_exchange_destroy(lgb_exchange* x) {
+  if (!x) return;
+  cudaDeviceSynchronize();
+  for (uint32_t r = 0; r < x->world; ++r)
+    if (r != x->rank && x->peer[r]) cudaIpcCloseMemHandle(x->peer[r]);
+  if (x->region) cudaFree(x->region);
+  if (x->d_ctl) cudaFree(x->d_ctl);
+  if (x->h_ctl) cudaFreeHost(x->h_ctl);
+  delete x;
+}
+
+extern "C" LG_EXPORT uint64_t lgb_batch_album_shortterm_blocks(const lgb_batch* b) {
+  const Plan& p = b->plan;
+  uint64_t n = 0;
+  for (const Track& tr : p.tracks) if (tr.album != LGB_NO_ALBUM) n += tr.nst;
+  return n;
+}
+
+extern "C" LG_EXPORT int lgb_batch_attach_exchange(lgb_batch* b, lgb_exchange* x) {
+  g_error.clear();
+  const Plan& p = b->plan;
+  if (x->nalbums != p.nalbums) { set_error("lgb_batch_attach_exchange: album counts differ"); return 1; }
+  if (x->world > 1 && !x->opened) { set_error("lgb_batch_attach_exchange: lgb_exchange_open first"); return 1; }
+  const size_t nt = p.tracks.size();
+  std::vector<uint32_t> off(p.nalbums + 1, 0);
+  for (uint32_t a = 0; a < p.nalbums; ++a) {
+    const Query& q = p.queries[nt + a];
+    uint32_t n = 0;
+    for (uint32_t m = 0; m < q.count; ++m) n += p.tracks[p.members[q.first + m]].nst;
+    off[a + 1] = off[a] + n;
+  }
+  if (off[p.nalbums] > x->st_cap) { set_error("lgb_batch_attach_exchange: st_capacity is too small"); return 1; }
+  if (cudaStreamSynchronize(b->stream) != cudaSuccess) { set_error("lgb_batch_attach_exchange: stream error"); return 1; }
+  if (b->d_xstoff) cudaFreeAsync(b->d_xstoff, b->stream);
+  if (!upload(off, &b->d_xstoff, b->stream) || cudaStreamSynchronize(b->stream) != cudaSuccess) return 1;
+  if (b->graph) { cudaGraphExecDestroy(b->graph); b->graph = nullptr; }
+  if (!b->xchg) b->launches += 3u - (nt ? 0u : 1u);      // publish, gate, finish; the query launch stays if there are tracks
+  b->xchg = x;
+  return 0;
+}
+
 extern "C" LG_EXPORT void lgb_batch_destroy(lgb_batch* b) {
   if (!b) return;
   if (b->ev0) { cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); cudaEventDestroy(b->ev2); }
   void* const mem[] = {b->d_tracks, b->d_coefs, b->d_work, b->d_queries, b->d_members, b->d_lists,
                        b->d_recs, b->d_peaks, b->d_mrec, b->d_tpq, b->d_tmaps, b->d_items, b->d_xi, b->d_runq, b->d_runcnt, b->d_rundense, b->d_eslot, b->d_zblock, b->d_zst,
-                       b->d_results};
+                       b->d_results, b->d_xstoff};
   if (b->h_results) cudaStreamSynchronize(b->stream);   // a run may still be writing the mirrors
   for (void* m : mem) if (m) cudaFreeAsync(m, b->stream);
   if (b->graph) cudaGraphExecDestroy(b->graph);

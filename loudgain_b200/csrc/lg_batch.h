@@ -17,5 +17,7 @@ void set_error(const char* what);
 // Runs one gating/range query over the union of `n` block lists (device
 // pointers inside) and waits for the result.  0 on success.
 int query_lists_sync(const BlockList* lists, size_t n, cudaStream_t stream, QueryResult* out);
+// ... and `n` queries at once, query i over list i alone (out[n]).
+int query_each_sync(const BlockList* lists, size_t n, cudaStream_t stream, QueryResult* out);
 
 }  // namespace lg

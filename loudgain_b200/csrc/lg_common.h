@@ -4,6 +4,7 @@
 // scan.c:294-307,383-391).
 #pragma once
 
+#include <stddef.h>
 #include <stdint.h>
 
 // Per-thread math is written once: device code under nvcc, plain inline host
@@ -144,7 +145,7 @@ struct Track {
   uint32_t nblocks;    // 400 ms gating blocks
   uint32_t nst;        // 3 s short-term blocks
   uint32_t album;      // album (query group) index
-  uint32_t pad_;
+  uint32_t flags;      // bit 0: EBUR128_MODE_HISTOGRAM semantics (block energies become 0.1 LU bin centres)
   uint64_t rec_base;   // first chunk record (index = rec_base + chunk*channels + ch)
   uint64_t slot_base;  // first slot energy
   uint64_t block_base; // first gating block
@@ -189,6 +190,47 @@ struct QueryResult {
   uint64_t n2;      // rel-gated block count
   uint64_t nst;     // abs-gated short-term block count
 };
+
+// ---- album queries over tracks that live on several GPUs (lg_kernels.cu:
+// xchg_*_kernel, lg_batch.cu: lgb_exchange_*) --------------------------------
+// Every rank keeps one exchange region in its own HBM, mapped into every peer
+// (CUDA IPC, NVLink peer access); the layout is the same on every rank:
+//   flags  [2 phases][kMaxWorld] uint64   step number rank r has completed phase p of
+//   hdr    [2 parities][world][nalbums]   XchgHdr: rank r's share of album a
+//   st     [2 parities][world][st_cap]    rank r's short-term energies, album after album
+// A rank WRITES its own row into every peer's region (and its own) and READS
+// only its local region.  Steps alternate between the two parities, so step
+// k + 1 never overwrites what a slower peer still reads for step k.
+constexpr uint32_t kMaxWorld = 16;
+
+struct XchgHdr {
+  double s1; uint64_t n1;     // gating blocks above the absolute gate: energy sum, count
+  double sst; uint64_t nst;   // short-term blocks above the absolute gate
+  double s2; uint64_t n2;     // gating blocks above the relative gate (second phase)
+  uint32_t st_off, st_cnt;    // where the rank's short-term energies of the album are in its stretch
+  uint64_t pad_;
+};
+static_assert(sizeof(XchgHdr) == 64, "one header is four 16-byte stores");
+
+struct XchgParams {
+  uint32_t world, rank, nalbums, first_query;   // album a is query first_query + a of the batch
+  uint64_t st_cap;                              // doubles per rank and parity
+  unsigned char* peer[kMaxWorld];               // region of rank p as mapped here (peer[rank] = local)
+  const uint32_t* st_off;                       // [nalbums + 1] local prefix of the albums' short-term counts
+  unsigned long long* ctl;                      // local: [0] step, [1..3] CTAs done per phase, [4] time-outs
+};
+
+LG_BOTH size_t xchg_flags_bytes() { return 2u * kMaxWorld * sizeof(uint64_t); }
+LG_BOTH size_t xchg_hdr_off(uint32_t world, uint32_t nalbums, uint32_t parity, uint32_t r, uint32_t a) {
+  return xchg_flags_bytes() + (((size_t) parity * world + r) * nalbums + a) * sizeof(XchgHdr);
+}
+LG_BOTH size_t xchg_st_off(uint32_t world, uint32_t nalbums, uint64_t st_cap, uint32_t parity, uint32_t r) {
+  const size_t hdr_end = xchg_flags_bytes() + (size_t) 2 * world * nalbums * sizeof(XchgHdr);
+  return ((hdr_end + 255u) & ~(size_t) 255u) + ((size_t) parity * world + r) * st_cap * sizeof(double);
+}
+LG_BOTH size_t xchg_region_bytes(uint32_t world, uint32_t nalbums, uint64_t st_cap) {
+  return xchg_st_off(world, nalbums, st_cap, 2, 0);
+}
 
 // Work descriptor: one warp of the sweep = up to 32/min(C,32) consecutive
 // chunks of one track, for channels [ch_base, ch_base + 32).

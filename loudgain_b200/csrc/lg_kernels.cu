@@ -14,6 +14,9 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <mutex>
+#include <vector>
+
 #include "lg_common.h"
 #include "lg_device.cuh"
 #include "lg_kernels.h"
@@ -581,11 +584,30 @@ fixslot_kernel(const Track* __restrict__ tracks, uint32_t ntracks, const CoefSet
                                31 - __clz((int) tr.aq));
 }
 
+// EBUR128_MODE_HISTOGRAM: libebur128 then does not store block energies but counts
+// them in 1000 bins of 0.1 LU from -70 to +30 LUFS, and every later sum, gate and
+// percentile works on the bins' centre energies.  That is the same as replacing each
+// block energy by the centre of its bin at the moment it is stored (a block below
+// the first edge -- the absolute gate -- is dropped: 0 never passes a gate), which
+// is what the block kernels do for tracks with Track::flags bit 0.  tab = 1001 bin
+// edges, then 1000 centre energies (hist_table(): the reference's own expressions,
+// evaluated on the host); the bin is the reference's binary search result.
+constexpr int kHistBins = 1000;
+
+__device__ double hist_quantise(double e, const double* __restrict__ tab) {
+  if (!(e >= tab[0])) return 0.0;
+  int i = (int) floor((10.0 * log10(e) + 0.691 + 70.0) * 10.0);
+  i = i < 0 ? 0 : (i > kHistBins - 1 ? kHistBins - 1 : i);
+  while (i > 0 && e < tab[i]) --i;
+  while (i < kHistBins - 1 && e >= tab[i + 1]) ++i;
+  return tab[kHistBins + 1 + i];
+}
+
 __global__ void __launch_bounds__(256)
 block_kernel(const Track* __restrict__ tracks, uint32_t ntracks,
              const CoefSet* __restrict__ coefs, const double* __restrict__ eslot,
              uint64_t total_blocks, uint64_t total_st, double* __restrict__ zblock,
-             double* __restrict__ zst) {
+             double* __restrict__ zst, const double* __restrict__ hist_tab) {
   __shared__ uint64_t s_bbase[kTrackCache], s_sbase[kTrackCache];
   const bool cached = ntracks <= kTrackCache;
   if (cached) {
@@ -608,12 +630,14 @@ block_kernel(const Track* __restrict__ tracks, uint32_t ntracks,
   if (i < total_blocks) {
     const uint32_t ti = locate(s_bbase, i, [](const Track& t) { return t.block_base; });
     const Track& tr = tracks[ti];
-    zblock[i] = gating_block(eslot + tr.slot_base, coefs[tr.coef], (uint32_t) (i - tr.block_base));
+    const double e = gating_block(eslot + tr.slot_base, coefs[tr.coef], (uint32_t) (i - tr.block_base));
+    zblock[i] = (tr.flags & 1u) ? hist_quantise(e, hist_tab) : e;
   } else if (i < total_blocks + total_st) {
     const uint64_t j = i - total_blocks;
     const uint32_t ti = locate(s_sbase, j, [](const Track& t) { return t.st_base; });
     const Track& tr = tracks[ti];
-    zst[j] = shortterm_block(eslot + tr.slot_base, coefs[tr.coef], (uint32_t) (j - tr.st_base));
+    const double e = shortterm_block(eslot + tr.slot_base, coefs[tr.coef], (uint32_t) (j - tr.st_base));
+    zst[j] = (tr.flags & 1u) ? hist_quantise(e, hist_tab) : e;
   }
 }
 
@@ -621,18 +645,47 @@ block_kernel(const Track* __restrict__ tracks, uint32_t ntracks,
 // separately, e.g. on several GPUs, and concatenated: lgb_slots_query).
 __global__ void __launch_bounds__(256)
 stream_block_kernel(const double* __restrict__ eslot, int s100, uint64_t nblocks, uint64_t nst,
-                    double* __restrict__ zblock, double* __restrict__ zst) {
+                    double* __restrict__ zblock, double* __restrict__ zst,
+                    const double* __restrict__ hist_tab) {
   const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nblocks) zblock[i] = gating_block(eslot, s100, i);
-  else if (i < nblocks + nst) zst[i - nblocks] = shortterm_block(eslot, s100, i - nblocks);
+  if (i < nblocks) {
+    const double e = gating_block(eslot, s100, i);
+    zblock[i] = hist_tab ? hist_quantise(e, hist_tab) : e;
+  } else if (i < nblocks + nst) {
+    const double e = shortterm_block(eslot, s100, i - nblocks);
+    zst[i - nblocks] = hist_tab ? hist_quantise(e, hist_tab) : e;
+  }
 }
 
 cudaError_t launch_stream_blocks(const double* eslot, int s100, uint64_t nblocks, uint64_t nst,
-                                 double* zblock, double* zst, cudaStream_t stream) {
+                                 double* zblock, double* zst, cudaStream_t stream, const double* hist_tab) {
   if (nblocks + nst == 0) return cudaSuccess;
   const unsigned blocks = (unsigned) ((nblocks + nst + 255) / 256);
-  stream_block_kernel<<<blocks, 256, 0, stream>>>(eslot, s100, nblocks, nst, zblock, zst);
+  stream_block_kernel<<<blocks, 256, 0, stream>>>(eslot, s100, nblocks, nst, zblock, zst, hist_tab);
   return cudaGetLastError();
+}
+
+// The histogram table of the current device (created on first use, never freed).
+const double* hist_table() {
+  static std::mutex mu;
+  static const double* tabs[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (tabs[dev]) return tabs[dev];
+  std::vector<double> h(2 * kHistBins + 1);
+  // libebur128 1.2.x ebur128.c: histogram_energy_boundaries / histogram_energies
+  h[0] = pow(10.0, (-70.0 + 0.691) / 10.0);
+  for (int i = 1; i <= kHistBins; ++i) h[i] = pow(10.0, ((double) i / 10.0 - 70.0 + 0.691) / 10.0);
+  for (int i = 0; i < kHistBins; ++i) h[kHistBins + 1 + i] = pow(10.0, ((double) i / 10.0 - 69.95 + 0.691) / 10.0);
+  double* d = nullptr;
+  if (cudaMalloc((void**) &d, h.size() * sizeof(double)) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(d);
+    return nullptr;
+  }
+  tabs[dev] = d;
+  return d;
 }
 
 // ------------------------------------------------------------- reductions
@@ -916,6 +969,267 @@ query_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ quer
   if (threadIdx.x == 0) results[qi] = res;
 }
 
+// ---------------------------------------------------------------------------
+// Album queries over tracks that are sharded across GPUs
+// (ebur128_loudness_global_multiple / _range_multiple of scan.c:383-391 when the
+// album's tracks were measured on different ranks).
+//
+// The gating is distributed, not the block lists: every rank reduces ITS OWN
+// gating blocks and only (sum, count) pairs travel -- written by the kernels
+// themselves into every peer's exchange region over NVLink (peer-mapped memory,
+// lg_common.h: XchgParams), ordered by system-scope release / acquire on one
+// flag per rank and phase.  Three launches per step, each of which waits only
+// for the peers' PREVIOUS launch, so nothing depends on how any GPU schedules
+// its CTAs:
+//   xchg_publish_kernel   sums behind the absolute gate (gating and short-term
+//                         blocks) + the rank's short-term energies -> all peers
+//   xchg_gate_kernel      waits for phase 0 of every rank; relative threshold
+//                         from the rank-ordered totals; sums behind it -> all peers
+//   xchg_finish_kernel    waits for phase 1; loudness from the totals; range by
+//                         rank selection over the union of the short-term
+//                         energies every rank received
+// Totals are added in rank order on every rank: all ranks get the same bits.
+// The short-term lists are one value per second of audio, a tenth of the gating
+// blocks, which never leave their GPU.
+struct ViewSmem {
+  BlockList lists[kQueryCache];
+  uint32_t zoff[kQueryCache + 1], stoff[kQueryCache + 1];
+};
+
+__device__ void load_view(QueryView& v, ViewSmem& sm, const BlockList* lists, const uint32_t* members,
+                          const Query q) {
+  v.lists = lists; v.mem = members + q.first; v.count = q.count;
+  v.cached = q.count <= (uint32_t) kQueryCache;
+  v.s_lists = sm.lists; v.s_zoff = sm.zoff; v.s_stoff = sm.stoff;
+  v.first = threadIdx.x; v.stride = blockDim.x;
+  if (v.cached) {
+    for (uint32_t m = threadIdx.x; m < q.count; m += blockDim.x) sm.lists[m] = lists[v.mem[m]];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t az = 0, ast = 0;
+      for (uint32_t m = 0; m < q.count; ++m) {
+        sm.zoff[m] = az; sm.stoff[m] = ast;
+        az += sm.lists[m].nz; ast += sm.lists[m].nst;
+      }
+      sm.zoff[q.count] = az; sm.stoff[q.count] = ast;
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ XchgHdr* xchg_hdr(const XchgParams& X, uint32_t target, uint32_t parity, uint32_t r,
+                                             uint32_t a) {
+  return reinterpret_cast<XchgHdr*>(X.peer[target] + xchg_hdr_off(X.world, X.nalbums, parity, r, a));
+}
+__device__ __forceinline__ double* xchg_st(const XchgParams& X, uint32_t target, uint32_t parity, uint32_t r) {
+  return reinterpret_cast<double*>(X.peer[target] + xchg_st_off(X.world, X.nalbums, X.st_cap, parity, r));
+}
+__device__ __forceinline__ unsigned long long* xchg_flag(const XchgParams& X, uint32_t target, uint32_t phase,
+                                                         uint32_t r) {
+  return reinterpret_cast<unsigned long long*>(X.peer[target]) + phase * kMaxWorld + r;
+}
+
+// Every thread has fenced its own peer stores; the CTA that finishes last tells
+// every rank that this rank's `phase` of `step` is complete.
+__device__ void xchg_signal(const XchgParams& X, uint32_t phase, unsigned long long step) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long done = atomicAdd(X.ctl + 1 + phase, 1ull);
+    if (done == gridDim.x - 1) {
+      X.ctl[1 + phase] = 0ull;
+      __threadfence_system();
+      for (uint32_t p = 0; p < X.world; ++p) st_release_sys(xchg_flag(X, p, phase, X.rank), step);
+    }
+  }
+}
+
+// Waits until every rank has completed `phase` of `step` (flags only grow).  A
+// peer that never arrives (a rank that died) is given up on after kXchgTimeoutNs:
+// the time-out is counted in ctl[4] and reported by the fetch, the GPU does not hang.
+constexpr unsigned long long kXchgTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+__device__ void xchg_wait(const XchgParams& X, uint32_t phase, unsigned long long step) {
+  if (threadIdx.x < X.world) {
+    const unsigned long long* f = xchg_flag(X, X.rank, phase, threadIdx.x);
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(f) < step) {
+      if (global_ns() - t0 > kXchgTimeoutNs) { atomicAdd(X.ctl + 4, 1ull); break; }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kQueryThreads)
+xchg_publish_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ queries,
+                    const uint32_t* __restrict__ members, double abs_gate, const __grid_constant__ XchgParams X) {
+  __shared__ SumCount scratch[32];
+  __shared__ ViewSmem vs;
+  const uint32_t a = blockIdx.x;
+  const unsigned long long step = __ldcg(X.ctl);
+  const uint32_t parity = (uint32_t) (step & 1ull);
+  QueryView v;
+  load_view(v, vs, lists, members, queries[X.first_query + a]);
+  double s = 0.0;
+  unsigned long long n = 0;
+  for_each_energy<false>(v, [&](double e, uint32_t) { if (e >= abs_gate) { s += e; ++n; } });
+  const SumCount za = block_sum_count(s, n, scratch);
+  const uint32_t off = X.st_off[a], cnt = X.st_off[a + 1] - off;
+  s = 0.0; n = 0;
+  for_each_energy<true>(v, [&](double e, uint32_t g) {
+    for (uint32_t p = 0; p < X.world; ++p) xchg_st(X, p, parity, X.rank)[off + g] = e;
+    if (e >= abs_gate) { s += e; ++n; }
+  });
+  const SumCount sa = block_sum_count(s, n, scratch);
+  if (threadIdx.x == 0) {
+    for (uint32_t p = 0; p < X.world; ++p) {
+      XchgHdr* h = xchg_hdr(X, p, parity, X.rank, a);
+      h->s1 = za.s; h->n1 = za.n; h->sst = sa.s; h->nst = sa.n;
+      h->st_off = off; h->st_cnt = cnt;
+    }
+  }
+  xchg_signal(X, 0, step);
+}
+
+struct XchgTotals {
+  double s1, sst, s2;
+  unsigned long long n1, nst, n2;
+};
+
+// Totals of album `a` over all ranks, added in rank order (thread 0; broadcast by the caller).
+__device__ XchgTotals xchg_totals(const XchgParams& X, uint32_t parity, uint32_t a) {
+  XchgTotals t{0.0, 0.0, 0.0, 0ull, 0ull, 0ull};
+  for (uint32_t r = 0; r < X.world; ++r) {
+    const XchgHdr* h = xchg_hdr(X, X.rank, parity, r, a);
+    t.s1 += __ldcg(&h->s1); t.n1 += __ldcg(&h->n1);
+    t.sst += __ldcg(&h->sst); t.nst += __ldcg(&h->nst);
+    t.s2 += __ldcg(&h->s2); t.n2 += __ldcg(&h->n2);
+  }
+  return t;
+}
+
+__global__ void __launch_bounds__(kQueryThreads)
+xchg_gate_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ queries,
+                 const uint32_t* __restrict__ members, double abs_gate, const __grid_constant__ XchgParams X) {
+  __shared__ SumCount scratch[32];
+  __shared__ ViewSmem vs;
+  __shared__ XchgTotals tot;
+  const uint32_t a = blockIdx.x;
+  const unsigned long long step = __ldcg(X.ctl);
+  const uint32_t parity = (uint32_t) (step & 1ull);
+  QueryView v;
+  load_view(v, vs, lists, members, queries[X.first_query + a]);
+  xchg_wait(X, 0, step);
+  if (threadIdx.x == 0) tot = xchg_totals(X, parity, a);
+  __syncthreads();
+  double s = 0.0;
+  unsigned long long n = 0;
+  if (tot.n1) {
+    const double thr = tot.s1 / (double) tot.n1 * 0.1;
+    for_each_energy<false>(v, [&](double e, uint32_t) { if (e >= abs_gate && e >= thr) { s += e; ++n; } });
+  }
+  const SumCount b = block_sum_count(s, n, scratch);
+  if (threadIdx.x == 0) {
+    for (uint32_t p = 0; p < X.world; ++p) {
+      XchgHdr* h = xchg_hdr(X, p, parity, X.rank, a);
+      h->s2 = b.s; h->n2 = b.n;
+    }
+  }
+  xchg_signal(X, 1, step);
+}
+
+__global__ void __launch_bounds__(kQueryThreads)
+xchg_finish_kernel(double abs_gate, QueryResult* __restrict__ results, const __grid_constant__ XchgParams X) {
+  __shared__ SumCount scratch[32];
+  __shared__ ViewSmem vs;
+  __shared__ XchgTotals tot;
+  __shared__ unsigned int hist[512];
+  __shared__ unsigned int wsum[16];
+  __shared__ SelectState sel;
+  const uint32_t a = blockIdx.x;
+  const unsigned long long step = __ldcg(X.ctl);
+  const uint32_t parity = (uint32_t) (step & 1ull);
+  xchg_wait(X, 1, step);
+  if (threadIdx.x == 0) {
+    tot = xchg_totals(X, parity, a);
+    // the union of the short-term energies: one list per rank, in this rank's own region
+    uint32_t ast = 0;
+    for (uint32_t r = 0; r < X.world; ++r) {
+      const XchgHdr* h = xchg_hdr(X, X.rank, parity, r, a);
+      const uint32_t cnt = __ldcg(&h->st_cnt);
+      vs.lists[r] = BlockList{nullptr, xchg_st(X, X.rank, parity, r) + __ldcg(&h->st_off), 0u, cnt};
+      vs.zoff[r] = 0; vs.stoff[r] = ast;
+      ast += cnt;
+    }
+    vs.zoff[X.world] = 0; vs.stoff[X.world] = ast;
+  }
+  __syncthreads();
+  QueryView v;
+  v.lists = nullptr; v.mem = nullptr; v.count = X.world; v.cached = true;
+  v.s_lists = vs.lists; v.s_zoff = vs.zoff; v.s_stoff = vs.stoff;
+  v.first = threadIdx.x; v.stride = blockDim.x;
+  QueryResult res;
+  res.loudness = -HUGE_VAL; res.range = 0.0; res.rel_thr = 0.0;
+  res.sum1 = tot.s1; res.n1 = tot.n1; res.sum2 = tot.s2; res.n2 = tot.n2; res.nst = tot.nst;
+  if (tot.n1) {
+    res.rel_thr = tot.s1 / (double) tot.n1 * 0.1;
+    if (tot.n2) res.loudness = energy_to_lufs(tot.s2 / (double) tot.n2);
+  }
+  if (tot.nst) {
+    double floor_e = tot.sst / (double) tot.nst * 0.01;
+    if (floor_e < abs_gate) floor_e = abs_gate;
+    unsigned long long n = 0;
+    for_each_energy<true>(v, [&](double e, uint32_t) { if (e >= floor_e) ++n; });
+    const SumCount c = block_sum_count(0.0, n, scratch);
+    if (c.n) {
+      const unsigned long long k_hi = (unsigned long long) ((double) (c.n - 1) * 0.95 + 0.5);
+      const unsigned long long k_lo = (unsigned long long) ((double) (c.n - 1) * 0.1 + 0.5);
+      double lo, hi;
+      select_two(v, nullptr, 0u, false, floor_e, k_lo, k_hi, hist, wsum, &sel, &lo, &hi);
+      res.range = energy_to_lufs(hi) - energy_to_lufs(lo);
+    }
+  }
+  if (threadIdx.x == 0) {
+    results[X.first_query + a] = res;
+    // the step is over on this rank once every album is done
+    __threadfence();
+    if (atomicAdd(X.ctl + 3, 1ull) == gridDim.x - 1) { X.ctl[3] = 0ull; X.ctl[0] = step + 1ull; }
+  }
+}
+
+cudaError_t launch_exchange_publish(const BlockList* lists, const Query* queries, const uint32_t* members,
+                                    double abs_gate, const XchgParams& x, cudaStream_t stream) {
+  if (!x.nalbums) return cudaSuccess;
+  xchg_publish_kernel<<<x.nalbums, kQueryThreads, 0, stream>>>(lists, queries, members, abs_gate, x);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_exchange_finish(const BlockList* lists, const Query* queries, const uint32_t* members,
+                                   double abs_gate, QueryResult* results, const XchgParams& x,
+                                   cudaStream_t stream) {
+  if (!x.nalbums) return cudaSuccess;
+  xchg_gate_kernel<<<x.nalbums, kQueryThreads, 0, stream>>>(lists, queries, members, abs_gate, x);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  xchg_finish_kernel<<<x.nalbums, kQueryThreads, 0, stream>>>(abs_gate, results, x);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t stream) {
   if (z.total_slots) {
     const unsigned blocks = (unsigned) ((z.total_slots + 127) / 128);
@@ -925,7 +1239,7 @@ cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t 
   if (z.total_blocks + z.total_st) {
     const unsigned blocks = (unsigned) ((z.total_blocks + z.total_st + 255) / 256);
     block_kernel<<<blocks, 256, 0, stream>>>(t.tracks, z.ntracks, t.coefs, t.eslot, z.total_blocks,
-                                            z.total_st, t.zblock, t.zst);
+                                            z.total_st, t.zblock, t.zst, t.hist_tab);
   }
   return cudaGetLastError();
 }
@@ -983,6 +1297,22 @@ cudaError_t launch_range_peaks(const void* pcm, uint32_t format, uint32_t channe
     if (tpf == 4) LG_RANGE(FMT_F32, 4); else if (tpf == 2) LG_RANGE(FMT_F32, 2); else LG_RANGE(FMT_F32, 0);
   }
 #undef LG_RANGE
+  return cudaGetLastError();
+}
+
+// 16-bit samples -> float in full-scale units (x / 32768: what ebur128_add_frames_short
+// does to every sample), for a state that is then fed float frames.
+__global__ void __launch_bounds__(256)
+widen_s16_kernel(const short* __restrict__ in, float* __restrict__ out, size_t n) {
+  for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+    out[i] = (float) in[i] * (1.0f / 32768.0f);
+}
+
+cudaError_t launch_widen_s16(const void* in, void* out, size_t n, cudaStream_t stream) {
+  if (!n) return cudaSuccess;
+  const size_t blocks = (n + 255) / 256;
+  widen_s16_kernel<<<(unsigned) (blocks < 148u * 16u ? blocks : 148u * 16u), 256, 0, stream>>>(
+      (const short*) in, (float*) out, n);
   return cudaGetLastError();
 }
 

@@ -26,6 +26,7 @@ struct DeviceTables {
   double* zblock;       // [total_blocks]
   double* zst;          // [total_st]
   QueryResult* results; // [nqueries]
+  const double* hist_tab; // hist_table() when a track has Track::flags bit 0, else unused
 };
 
 struct PostSizes {
@@ -53,8 +54,13 @@ cudaError_t launch_truepeak_run(const SweepParams& p, uint32_t format, int tpf, 
                                 cudaStream_t stream, cudaEvent_t hold = nullptr);
 cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t stream);
 // 400 ms / 3 s blocks of one stream from its complete 100 ms slot list.
+// hist_tab: hist_table() for EBUR128_MODE_HISTOGRAM semantics, nullptr for exact energies.
 cudaError_t launch_stream_blocks(const double* eslot, int s100, uint64_t nblocks, uint64_t nst,
-                                 double* zblock, double* zst, cudaStream_t stream);
+                                 double* zblock, double* zst, cudaStream_t stream,
+                                 const double* hist_tab = nullptr);
+// 1001 bin edges + 1000 bin centre energies of libebur128's histogram mode in the
+// current device's memory (nullptr on failure).
+const double* hist_table();
 // Gated loudness + range for `nqueries` queries; all pointers are device memory.
 // `cluster` = CTAs per query (thread-block cluster sharing the gating blocks of a
 // query); query_cluster_size() picks it from the largest query's block count.
@@ -62,9 +68,21 @@ cudaError_t launch_queries(const BlockList* lists, const Query* queries, const u
                            uint32_t nqueries, double abs_gate, QueryResult* results,
                            cudaStream_t stream, uint32_t cluster = 1);
 uint32_t query_cluster_size(uint64_t max_gating_blocks);
+// Album queries over tracks sharded across GPUs (lg_common.h: XchgParams): the first
+// launch publishes this rank's share to every peer, the second pair gates against the
+// totals of all ranks and writes results[first_query + album].  Launch the publish as
+// early as the block lists allow; whatever runs in between hides the peers' latency.
+cudaError_t launch_exchange_publish(const BlockList* lists, const Query* queries, const uint32_t* members,
+                                    double abs_gate, const XchgParams& x, cudaStream_t stream);
+cudaError_t launch_exchange_finish(const BlockList* lists, const Query* queries, const uint32_t* members,
+                                   double abs_gate, QueryResult* results, const XchgParams& x,
+                                   cudaStream_t stream);
 // Sample peak and true peak (float bits, raw sample units) of track frames
 // [first, first + count) per channel into out[2 * channels] (device memory).
 cudaError_t launch_range_peaks(const void* pcm, uint32_t format, uint32_t channels, uint64_t first,
                                uint64_t count, int tpf, uint32_t* out, cudaStream_t stream);
+
+// n 16-bit samples -> float, x / 32768 (device pointers).
+cudaError_t launch_widen_s16(const void* in, void* out, size_t n, cudaStream_t stream);
 
 }  // namespace lg

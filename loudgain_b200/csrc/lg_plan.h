@@ -28,6 +28,7 @@ struct TrackIn {
   uint32_t album;           // album index, or kNoAlbum
   const uint8_t* wclass;    // optional explicit weight classes [channels]
   uint64_t lead_in = 0;     // leading context frames (segment of a longer stream)
+  uint32_t flags = 0;       // Track::flags
 };
 
 constexpr uint32_t kNoAlbum = 0xffffffffu;
@@ -232,6 +233,7 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, const Plan
     tr.format = t.format;
     tr.album = t.album;
     tr.lead_in = t.lead_in;
+    tr.flags = t.flags;
     if (t.wclass) for (uint32_t c = 0; c < t.channels; ++c) tr.wclass[c] = t.wclass[c];
     else default_weight_classes(t.channels, tr.wclass);
     const int s100 = (int) ((t.samplerate + 5) / 10);

@@ -10,8 +10,11 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <functional>
+#include <queue>
 #include <thread>
 #include <vector>
 
@@ -219,4 +222,32 @@ extern "C" LG_EXPORT size_t lgb_format_tags(const lgb_scan_result* r, int do_alb
     if (do_album) put("REPLAYGAIN_ALBUM_RANGE=%.2f %s\n", r->album_loudness_range, unit);
   }
   return len;
+}
+
+// ---- library scans over several GPUs: which rank scans which track -------------
+// The reference parallelises a library over files and albums with one process
+// each and lets the OS balance them (bin/rgbpm2:150-175).  With one process per
+// GPU the tracks are dealt out ahead of time: longest processing time first,
+// always to the rank with the smallest load so far (cost = frames x channels,
+// what the sweep's time is proportional to).  Ties go to the lower rank, equal
+// costs keep their input order, so every rank computes the same assignment.
+extern "C" LG_EXPORT uint64_t lgb_lpt_assign(const uint64_t* cost, size_t n, uint32_t world, uint32_t* rank_out) {
+  if (!world) return 0;
+  std::vector<size_t> order(n);
+  for (size_t i = 0; i < n; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return cost[a] > cost[b]; });
+  // (load, rank) min-heap
+  typedef std::pair<uint64_t, uint32_t> Slot;
+  std::priority_queue<Slot, std::vector<Slot>, std::greater<Slot>> heap;
+  for (uint32_t r = 0; r < world; ++r) heap.push(Slot(0, r));
+  uint64_t worst = 0;
+  for (size_t i : order) {
+    Slot s = heap.top();
+    heap.pop();
+    rank_out[i] = s.second;
+    s.first += cost[i];
+    if (s.first > worst) worst = s.first;
+    heap.push(s);
+  }
+  return worst;
 }

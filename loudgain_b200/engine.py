@@ -26,7 +26,7 @@ FORMAT_S16, FORMAT_F32 = 0, 1
 class _Track(C.Structure):
     _fields_ = [("pcm", C.c_void_p), ("frames", C.c_uint64), ("channels", C.c_uint32),
                 ("samplerate", C.c_uint32), ("format", C.c_uint32), ("album", C.c_uint32),
-                ("weight_class", C.c_void_p), ("lead_in", C.c_uint64)]
+                ("weight_class", C.c_void_p), ("lead_in", C.c_uint64), ("flags", C.c_uint32)]
 
 
 class _Result(C.Structure):
@@ -115,7 +115,7 @@ class Batch:
     int16 or float32, sample rate)], optionally grouped into albums."""
 
     def __init__(self, tracks: Sequence, albums: Sequence[int] | None = None, stream=None,
-                 lead_in: Sequence[int] | None = None):
+                 lead_in: Sequence[int] | None = None, nalbums: int | None = None):
         """lead_in[i]: leading context frames of track i (a whole number of
         100 ms slots) when the track is one time segment of a longer stream."""
         import torch
@@ -125,7 +125,7 @@ class Batch:
         self._keep = []
         n = len(tracks)
         arr = (_Track * max(n, 1))()
-        nalb = 0
+        nalb = int(nalbums) if nalbums is not None else 0
         self.channels = []
         for i, (pcm, rate) in enumerate(tracks):
             if not pcm.is_cuda:
@@ -143,7 +143,7 @@ class Batch:
             self._keep.append(pcm)
             self.channels.append(pcm.shape[1])
             arr[i] = _Track(pcm.data_ptr(), pcm.shape[0], pcm.shape[1], int(rate), fmt, alb, None,
-                            0 if lead_in is None else int(lead_in[i]))
+                            0 if lead_in is None else int(lead_in[i]), 0)
         self.ntracks, self.nalbums = n, nalb
         # result buffers are allocated once: fetch() sits between two steps of a
         # repeatedly run batch, where host time is GPU idle time
@@ -375,6 +375,74 @@ class AlbumMerge:
         if self._h:
             self._L.lgb_listquery_destroy(self._h)
             self._h = None
+
+
+class AlbumExchange:
+    """Album results over tracks that are sharded across ranks, computed inside
+    the batch's own step (include/ebur128_b200.h: lgb_exchange_*).
+
+    Album indices are global: every rank builds its Batch with the same
+    `nalbums` (give Batch(..., nalbums=...) when a rank may hold no track of the
+    last album).  Each rank reduces its own gating blocks; the kernels store the
+    partial sums and the short-term energies straight into the peers' HBM over
+    NVLink (CUDA IPC mappings of one region per rank) and wait on per-rank
+    flags.  torch.distributed only carries the 64-byte handles and one size,
+    once, here.  After this, batch.run() / batch.fetch() return the album
+    results of ALL ranks' tracks, the same bits on every rank.
+    """
+
+    def __init__(self, batch: Batch, dist=None, world: int = 1, rank: int = 0, group=None):
+        import torch
+
+        L = _bind()
+        L.lgb_exchange_create.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64]
+        L.lgb_exchange_create.restype = C.c_void_p
+        L.lgb_exchange_handle.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.lgb_exchange_open.argtypes = [C.c_void_p, C.c_void_p]
+        L.lgb_exchange_destroy.argtypes = [C.c_void_p]
+        L.lgb_exchange_destroy.restype = None
+        L.lgb_batch_album_shortterm_blocks.argtypes = [C.c_void_p]
+        L.lgb_batch_album_shortterm_blocks.restype = C.c_uint64
+        L.lgb_batch_attach_exchange.argtypes = [C.c_void_p, C.c_void_p]
+        self._L, self.batch, self.world, self.rank = L, batch, world, rank
+        dev = torch.device("cuda", torch.cuda.current_device())
+        cap = torch.tensor([L.lgb_batch_album_shortterm_blocks(batch._h)], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=group)
+        self._h = L.lgb_exchange_create(world, rank, batch.nalbums, int(cap.item()))
+        if not self._h:
+            raise RuntimeError("lgb_exchange_create failed: " + _err(L))
+        if world > 1:
+            mine = (C.c_ubyte * 64)()
+            if L.lgb_exchange_handle(self._h, mine, 64):
+                raise RuntimeError("lgb_exchange_handle failed: " + _err(L))
+            t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+            out = torch.empty(world * 64, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(out, t, group=group)
+            raw = bytes(out.cpu().numpy().tobytes())
+            if L.lgb_exchange_open(self._h, raw):
+                raise RuntimeError("lgb_exchange_open failed: " + _err(L))
+            dist.barrier(group=group)            # every region is mapped everywhere before anyone runs
+        if L.lgb_batch_attach_exchange(batch._h, self._h):
+            raise RuntimeError("lgb_batch_attach_exchange failed: " + _err(L))
+
+    def close(self) -> None:
+        if self._h:
+            self._L.lgb_exchange_destroy(self._h)
+            self._h = None
+
+
+def lpt_assign(costs, world: int):
+    """Rank of every work item, longest processing time first
+    (lgb_lpt_assign; cost = frames x channels of a track)."""
+    L = _bind()
+    L.lgb_lpt_assign.argtypes = [C.POINTER(C.c_uint64), C.c_size_t, C.c_uint32, C.POINTER(C.c_uint32)]
+    L.lgb_lpt_assign.restype = C.c_uint64
+    n = len(costs)
+    c = (C.c_uint64 * max(n, 1))(*[int(x) for x in costs])
+    out = (C.c_uint32 * max(n, 1))()
+    worst = L.lgb_lpt_assign(c, n, world, out)
+    return [int(out[i]) for i in range(n)], int(worst)
 
 
 def merge_album_across_ranks(batch: Batch, tracks, dist, world: int) -> Measurement:

@@ -21,7 +21,7 @@ GOAL_LU = 2e-4
 class LgbTrack(C.Structure):
     _fields_ = [("pcm", C.c_void_p), ("frames", C.c_uint64), ("channels", C.c_uint32),
                 ("samplerate", C.c_uint32), ("format", C.c_uint32), ("album", C.c_uint32),
-                ("weight_class", C.c_void_p), ("lead_in", C.c_uint64)]
+                ("weight_class", C.c_void_p), ("lead_in", C.c_uint64), ("flags", C.c_uint32)]
 
 
 class LgbResult(C.Structure):

@@ -383,3 +383,35 @@ def test_gpu_matches_host_emulation(product):
     np.testing.assert_allclose(z, e["blocks"], rtol=1e-13)
     np.testing.assert_array_equal(tres[0].true_peak, e["tracks"][0]["true_peak"])
     np.testing.assert_array_equal(tres[0].sample_peak, e["tracks"][0]["sample_peak"])
+
+
+def test_album_exchange_single_rank(product):
+    """The cross-rank album path (lgb_exchange_*: publish / gate / finish kernels over
+    the exchange region) with one rank must give what the plain album query gives, on
+    every repeat (the steps alternate between the region's two halves and the second
+    run on replays the step as a CUDA graph)."""
+    import torch
+    from loudgain_b200 import engine
+
+    specs = synth.config2_specs(ntracks=6, scale=0.08)
+    tracks = [(synth.programme_s16(s, device="cuda"), s.rate) for s in specs]
+    albums = [0, 1, 0, 1, 0, 2]
+    want_t, want_a = engine.measure(tracks, albums)
+    b = engine.Batch(tracks, albums, nalbums=4)            # album 3 has no track at all
+    x = engine.AlbumExchange(b)
+    try:
+        for _ in range(4):
+            b.run()
+            got_t, got_a = b.fetch()
+            for w, g in zip(want_t, got_t):
+                assert g.loudness == w.loudness and g.range == w.range
+            for a in range(3):
+                assert lu_diff(got_a[a].loudness, want_a[a].loudness) <= 1e-10
+                assert got_a[a].range == want_a[a].range
+                assert (got_a[a].n_abs, got_a[a].n_rel, got_a[a].n_shortterm) == \
+                       (want_a[a].n_abs, want_a[a].n_rel, want_a[a].n_shortterm)
+            assert got_a[3].loudness == -np.inf and got_a[3].range == 0.0
+    finally:
+        b.close()
+        x.close()
+    torch.cuda.synchronize()
