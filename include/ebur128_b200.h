@@ -195,8 +195,14 @@ typedef struct {
   uint64_t frames;
   uint32_t channels;
   uint32_t samplerate;
-  uint32_t format;            /* LGB_FORMAT_* */
+  uint32_t format;            /* LGB_FORMAT_*, optionally | LGB_HOST_CODEC_OPUS */
 } lgb_host_track;
+
+/* The file is an Opus stream: its gains are relative to -23 LUFS, i.e. the pre-gain is
+ * lowered by 5 dB for the track (scan.c:309-311) and for an album that holds such a
+ * track (scan.c:394-398), and loudness_reference follows (scan.c:328). */
+#define LGB_HOST_CODEC_OPUS 0x100u
+#define LGB_HOST_FORMAT_MASK 0xffu
 
 typedef struct {              /* mirrors scan_result (scan.h:35-53) */
   double track_gain, track_peak, track_loudness, track_loudness_range;
@@ -241,6 +247,16 @@ int lgb_clip_prevention(lgb_scan_result* r, int do_album, int prevent, double ma
  * or the length needed if `cap` is too small. */
 size_t lgb_format_tab_row(const char* name, const lgb_scan_result* r, const lgb_clip_info* info,
                           int album_row, const char* unit, char* buf, size_t cap);
+
+/* One row of the old mp3gain-compatible list, loudgain -o (loudgain.c:566-585):
+ * "name<TAB>0<TAB>gain %.2f<TAB>peak * 32768 %.6f<TAB>0<TAB>0". */
+size_t lgb_format_old_row(const char* name, const lgb_scan_result* r, int album_row, char* buf,
+                          size_t cap);
+
+/* loudgain's default human-readable block for a track or for the album
+ * (loudgain.c:613-649); `opus` adds the Q7.8 number to the gain line. */
+size_t lgb_format_human(const char* name, const lgb_scan_result* r, const lgb_clip_info* info,
+                        int album_row, int opus, const char* unit, char* buf, size_t cap);
 
 /* The tag values loudgain would write for a scan result, as text at the
  * reference's tag precision (tag.cc:178-203: gains "%.2f <unit>", peaks

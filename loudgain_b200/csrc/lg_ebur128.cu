@@ -289,9 +289,10 @@ bool acquire_slot(ebur128_state* st) {
   if (pick < 0) {
     for (int i = 0; i < kStageSlots; ++i) {
       StageSlot& sl = g_ctx.slots[i];
-      if (sl.owner && sl.owner != st && sl.owner->d->feed.try_lock()) {
-        const bool ok = flush_stage(sl.owner, true);
-        sl.owner->d->feed.unlock();
+      ebur128_state* idle = sl.owner;              // (flush_stage clears sl.owner)
+      if (idle && idle != st && idle->d->feed.try_lock()) {
+        const bool ok = flush_stage(idle, true);
+        idle->d->feed.unlock();
         if (!ok) return false;
         break;
       }
@@ -324,7 +325,12 @@ bool acquire_slot(ebur128_state* st) {
 // with several scanner threads the host DRAM, not PCIe, is the ingest limit.
 void stage_copy(char* dst, const char* src, size_t n) {
 #if defined(__SSE2__)
-  if (n >= 256) {
+  static const size_t nt_min = [] {
+    const char* e = getenv("LOUDGAIN_B200_NT_MIN");      // tuning: smallest copy that uses streaming stores
+    const long long v = e ? atoll(e) : 0;
+    return (size_t) (v > 0 ? v : 256);
+  }();
+  if (n >= nt_min) {
     const size_t head = (16 - ((uintptr_t) dst & 15)) & 15;
     memcpy(dst, src, head);
     dst += head; src += head; n -= head;
@@ -684,6 +690,30 @@ bool widen_to_float(ebur128_state* st) {
   return true;
 }
 
+// ebur128_set_max_history: libebur128 stores only blocks above the absolute gate and
+// keeps the newest `room` of them; `bl` is cut down to the stretch that holds them
+// (the blocks below the gate inside it fail every gate anyway) and the rooms shrink
+// by what was used.  A metering feature loudgain never touches: the lists are simply
+// looked at on the host.
+bool bound_lists(lg::BlockList& bl, uint64_t& room_z, uint64_t& room_st) {
+  const double gate = pow(10.0, (-70.0 + 0.691) / 10.0);
+  auto cut = [&](const double*& p, uint32_t& n, uint64_t& room) {
+    std::vector<double> h(n);
+    if (n && (cudaMemcpyAsync(h.data(), p, n * sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream) != cudaSuccess ||
+              cudaStreamSynchronize(g_ctx.stream) != cudaSuccess))
+      return false;
+    uint32_t first = n;
+    while (first > 0 && room > 0) {
+      --first;
+      if (h[first] >= gate) --room;
+    }
+    p += first;
+    n -= first;
+    return true;
+  };
+  return cut(bl.z, bl.nz, room_z) && cut(bl.st, bl.nst, room_st);
+}
+
 // Gated loudness + range over the union of the given states' block lists.
 int query_union(ebur128_state** sts, size_t n, lg::QueryResult* out) {
   if (!measure_pending()) return EBUR128_ERROR_NOMEM;
@@ -706,12 +736,7 @@ int query_union(ebur128_state** sts, size_t n, lg::QueryResult* out) {
         return EBUR128_ERROR_NOMEM;
       }
       lg::BlockList bl = segment_lists(s);
-      if (!s.hist) {
-        if (bl.nz > room_z) { bl.z += bl.nz - room_z; bl.nz = (uint32_t) room_z; }
-        if (bl.nst > room_st) { bl.st += bl.nst - room_st; bl.nst = (uint32_t) room_st; }
-        room_z -= bl.nz;
-        room_st -= bl.nst;
-      }
+      if (!s.hist && hist_ms != ULONG_MAX && !bound_lists(bl, room_z, room_st)) return EBUR128_ERROR_NOMEM;
       lists.push_back(bl);
       key.emplace_back((const void*) bl.z, ((size_t) bl.nz << 32) ^ (size_t) bl.nst);
     }

@@ -47,11 +47,12 @@ static int scan_one(const lgb_host_track& t, size_t chunk_frames, ebur128_state*
                           EBUR128_MODE_SAMPLE_PEAK | EBUR128_MODE_TRUE_PEAK);
   if (!*out) return 1;
   const size_t step = chunk_frames ? chunk_frames : (t.frames ? t.frames : 1);
-  const size_t fb = t.channels * (t.format == LGB_FORMAT_S16 ? 2u : 4u);
+  const uint32_t format = t.format & LGB_HOST_FORMAT_MASK;
+  const size_t fb = t.channels * (format == LGB_FORMAT_S16 ? 2u : 4u);
   for (uint64_t pos = 0; pos < t.frames; pos += step) {
     const size_t n = (size_t) (t.frames - pos < step ? t.frames - pos : step);
     const char* p = (const char*) t.pcm + pos * fb;
-    const int e = t.format == LGB_FORMAT_S16
+    const int e = format == LGB_FORMAT_S16
                       ? ebur128_add_frames_short(*out, (const short*) p, n)
                       : ebur128_add_frames_float(*out, (const float*) p, n);
     if (e != EBUR128_SUCCESS) return 2;
@@ -102,8 +103,15 @@ extern "C" LG_EXPORT int lgb_scan_host_mt(const lgb_host_track* tracks, size_t n
   const double ms_feed = ms_since(t_start);
   const auto t_query = std::chrono::steady_clock::now();
   double ms_first = 0.0;
+  // Opus gains are relative to -23 LUFS: scan.c:309-311 lowers the pre-gain by 5 dB for an
+  // Opus track, scan.c:394-398 for an album that has one (loudgain refuses albums that
+  // mix Opus with other codecs before it gets there)
+  bool album_has_opus = false;
+  for (size_t i = 0; i < ntracks; ++i) album_has_opus = album_has_opus || (tracks[i].format & LGB_HOST_CODEC_OPUS);
+  const double user_pre_gain = pre_gain;
   // ---- results (loudgain.c:323-340): track, then album, per file
   for (size_t i = 0; i < ntracks && !rc; ++i) {
+    pre_gain = user_pre_gain - ((tracks[i].format & LGB_HOST_CODEC_OPUS) ? 5.0 : 0.0);
     if (i == 1) ms_first = ms_since(t_query);
     lgb_scan_result& r = out[i];
     double global, range;
@@ -125,7 +133,7 @@ extern "C" LG_EXPORT int lgb_scan_host_mt(const lgb_host_track* tracks, size_t n
         const double p = max_true_peak(states[j]);
         if (p > apeak) apeak = p;
       }
-      r.album_gain = lufs_to_rg(global) + pre_gain;
+      r.album_gain = lufs_to_rg(global) + user_pre_gain - (album_has_opus ? 5.0 : 0.0);
       r.album_peak = apeak;
       r.album_loudness = global;
       r.album_loudness_range = range;
@@ -195,6 +203,43 @@ extern "C" LG_EXPORT size_t lgb_format_tab_row(const char* name, const lgb_scan_
                          name, loud, range, unit, peak, 20.0 * log10(peak), r->loudness_reference,
                          clip ? "Y" : "N", fixed ? "Y" : "N", gain, unit, npeak, 20.0 * log10(npeak));
   return n < 0 ? 0 : (size_t) n;
+}
+
+// loudgain.c:566-585: the old mp3gain-compatible list (-o).  Peaks in 16-bit sample
+// units; the columns mp3gain used for MP3 gain steps and min / max are always 0.
+extern "C" LG_EXPORT size_t lgb_format_old_row(const char* name, const lgb_scan_result* r, int album_row,
+                                               char* buf, size_t cap) {
+  const int n = snprintf(buf, cap, "%s\t%d\t%.2f\t%.6f\t%d\t%d\n", name, 0,
+                         album_row ? r->album_gain : r->track_gain,
+                         (album_row ? r->album_peak : r->track_peak) * 32768.0, 0, 0);
+  return n < 0 ? 0 : (size_t) n;
+}
+
+// loudgain.c:613-649: the human-readable block of a track ("\nTrack: <name>\n ...") or of
+// the album ("\nAlbum:\n ...").  With `opus` the gain line also shows the Q7.8 number that
+// goes into R128_TRACK_GAIN / R128_ALBUM_GAIN (tag.cc:442-445).
+extern "C" LG_EXPORT size_t lgb_format_human(const char* name, const lgb_scan_result* r,
+                                             const lgb_clip_info* info, int album_row, int opus,
+                                             const char* unit, char* buf, size_t cap) {
+  const double loud = album_row ? r->album_loudness : r->track_loudness;
+  const double range = album_row ? r->album_loudness_range : r->track_loudness_range;
+  const double peak = album_row ? r->album_peak : r->track_peak;
+  const double gain = album_row ? r->album_gain : r->track_gain;
+  const int fixed = album_row ? info->album_clipped : info->track_clipped;
+  const char* note = fixed ? " (corrected to prevent clipping)" : "";
+  size_t len = 0;
+  auto put = [&](const char* fmt, auto... args) {
+    const int n = snprintf(len < cap ? buf + len : nullptr, len < cap ? cap - len : 0, fmt, args...);
+    if (n > 0) len += (size_t) n;
+  };
+  if (album_row) put("%s", "\nAlbum:\n");
+  else put("\nTrack: %s\n", name);
+  put(" Loudness: %8.2f LUFS\n", loud);
+  put(" Range:    %8.2f %s\n", range, unit);
+  put(" Peak:     %8.6f (%.2f dBTP)\n", peak, 20.0 * log10(peak));
+  if (opus) put(" Gain:     %8.2f %s (%d)%s\n", gain, unit, (int) round(gain * 256.0), note);
+  else put(" Gain:     %8.2f %s%s\n", gain, unit, note);
+  return len;
 }
 
 extern "C" LG_EXPORT size_t lgb_format_tags(const lgb_scan_result* r, int do_album, int extended,

@@ -25,3 +25,10 @@ def product():
     from loudgain_b200 import build, load_library
     build()
     return load_library()
+
+
+@pytest.fixture(scope="session")
+def product_path():
+    """Path of the built product library (building needs no GPU)."""
+    from loudgain_b200 import build
+    return build()

@@ -157,3 +157,33 @@ def test_reference_screenshot_tables(L):
                     if exp is not None:
                         assert got == exp, (name, k, g["columns"][col], got, exp)
                 assert abs(float(cols[9]) - t["new_peak"][k]) <= 2.5e-6, (name, k, cols[9])
+
+
+def test_old_style_and_human_output(L):
+    """loudgain -o (loudgain.c:566-585) and the default human-readable blocks
+    (loudgain.c:613-649), byte for byte."""
+    L.lgb_format_old_row.argtypes = [C.c_char_p, C.POINTER(ScanResult), C.c_int, C.c_char_p, C.c_size_t]
+    L.lgb_format_old_row.restype = C.c_size_t
+    L.lgb_format_human.argtypes = [C.c_char_p, C.POINTER(ScanResult), C.POINTER(ClipInfo), C.c_int, C.c_int,
+                                   C.c_char_p, C.c_char_p, C.c_size_t]
+    L.lgb_format_human.restype = C.c_size_t
+    r, c = _result(-23.0, 0.98, -22.0, 1.02), ClipInfo()
+    assert L.lgb_clip_prevention(r, 1, 1, -1.0, c) == 0
+    buf = C.create_string_buffer(1024)
+    n = L.lgb_format_old_row(b"a.flac", r, 0, buf, 1024)
+    assert buf.value.decode() == "a.flac\t0\t%.2f\t%.6f\t0\t0\n" % (r.track_gain, 0.98 * 32768.0) and n == len(buf.value)
+    L.lgb_format_old_row(b"Album", r, 1, buf, 1024)
+    assert buf.value.decode() == "Album\t0\t%.2f\t%.6f\t0\t0\n" % (r.album_gain, 1.02 * 32768.0)
+    n = L.lgb_format_human(b"a.flac", r, c, 0, 0, b"dB", buf, 1024)
+    note = " (corrected to prevent clipping)" if c.track_clipped else ""
+    want = ("\nTrack: a.flac\n Loudness: %8.2f LUFS\n Range:    %8.2f dB\n Peak:     %8.6f (%.2f dBTP)\n"
+            " Gain:     %8.2f dB%s\n") % (-23.0, 7.5, 0.98, 20.0 * math.log10(0.98), r.track_gain, note)
+    assert buf.value.decode() == want and n == len(want)
+    assert c.track_clipped == 1 and c.album_clipped == 1   # +5 dB on a full-scale peak needs the correction
+    L.lgb_format_human(b"", r, c, 1, 1, b"LU", buf, 1024)
+    note = " (corrected to prevent clipping)" if c.album_clipped else ""
+    want = ("\nAlbum:\n Loudness: %8.2f LUFS\n Range:    %8.2f LU\n Peak:     %8.6f (%.2f dBTP)\n"
+            " Gain:     %8.2f LU (%d)%s\n") % (-22.0, 9.25, 1.02, 20.0 * math.log10(1.02), r.album_gain,
+                                              round(r.album_gain * 256.0), note)
+    assert buf.value.decode() == want
+    assert L.lgb_format_human(b"x", r, c, 0, 0, b"dB", None, 0) > 0          # length query
