@@ -67,11 +67,14 @@ const char* lgb_last_error(void);
 lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t ntracks, uint32_t nalbums,
                             void* cuda_stream);
 
-/* Enqueues the whole measurement (sweep, fix-up, gating, range) on the
- * batch's stream.  Asynchronous; 0 on success. */
+/* Enqueues the whole measurement (sweep, fix-up, gating, range, read-back of the
+ * scalars into pinned memory) on the batch's stream.  Asynchronous; 0 on success.
+ * Up to two runs may be in flight: a caller that repeats a batch can enqueue run
+ * k + 1 before it fetches run k, so that its own turn-around overlaps the GPU. */
 int lgb_batch_run(lgb_batch* b);
 
-/* Waits for the stream and copies results to the host.  Any pointer may be
+/* Waits for the OLDEST run that has not been fetched yet and copies its results to
+ * the host (an error if there is none).  Any pointer may be
  * NULL.  Peaks are linear amplitudes laid out track after track, one value
  * per channel; true_peaks already folds in the sample peak, as
  * ebur128_true_peak does. */
@@ -146,7 +149,8 @@ void lgb_listquery_destroy(lgb_listquery* q);
  * LOUDGAIN_B200_PCM_BUDGET_MB (default 32768) the complete part of every state is
  * measured in one batch, its 100 ms energies and peaks are kept and the PCM is
  * freed (libebur128 itself keeps only block energies per state; scan.c:98-108
- * keeps every state alive until scan_deinit).  Any pointer may be NULL. */
+ * keeps every state alive until scan_deinit).  Any pointer may be NULL.  Reading
+ * restarts the high-water mark at the current value. */
 void lgb_dropin_pcm_bytes(uint64_t* now, uint64_t* peak, uint64_t* releases);
 
 /* ---- albums whose tracks were measured on several GPUs --------------------

@@ -136,19 +136,22 @@ struct lgb_batch {
   cplx* d_xi = nullptr;                // plan.xi_table
   uint32_t* d_runq = nullptr;          // candidate queues of the run-sweep groups (32-bit entries)
   uint32_t* d_runcnt = nullptr;        // [items * 32] candidates queued per sweep lane
-  uint4* d_rundense = nullptr;      // the candidates that passed the final screening, packed
   double* d_eslot = nullptr;
   double* d_zblock = nullptr;
   double* d_zst = nullptr;
-  QueryResult* d_results = nullptr;
-  // pinned host mirrors of the (tiny) results, filled by the step itself
-  QueryResult* h_results = nullptr;
-  uint32_t* h_peaks = nullptr;
-  // A batch that is run repeatedly replays its step as a CUDA graph: the
-  // first run launches directly, the second one captures.
-  cudaGraphExec_t graph = nullptr;
+  QueryResult* d_results = nullptr;    // (inside d_out, in front of the peak cells)
+  uint32_t* d_out = nullptr;           // [results][peak cells][per-group counters]: one read-back per step
+  // Pinned host mirrors of the (tiny) results, filled by the step itself.  Two of
+  // them, used alternately: a second run may be enqueued before the first one's
+  // results are fetched (the host turn-around between steps then overlaps the GPU).
+  unsigned char* h_out[2] = {nullptr, nullptr};
+  size_t out_bytes = 0, peaks_off = 0;
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};
+  // A batch that is run repeatedly replays its step as a CUDA graph (one per
+  // mirror): the first run launches directly, the later ones capture / replay.
+  cudaGraphExec_t graph[2] = {nullptr, nullptr};
   bool graph_off = false;
-  uint32_t runs = 0;
+  uint32_t runs = 0, fetched = 0;
   // The true-peak pass only feeds the peak cells and the fix-up / block / query
   // kernels never read them, so after the sweep the step forks: the small
   // post-processing kernels go to a high-priority side stream and slip in next
@@ -171,6 +174,12 @@ struct lgb_batch {
   // album queries answered together with other ranks (lgb_batch_attach_exchange)
   lgb_exchange* xchg = nullptr;
   uint32_t* d_xstoff = nullptr;
+  cudaStream_t qstream = nullptr;    // the track queries run next to the exchange's three launches
+  cudaEvent_t ev_q0 = nullptr, ev_q1 = nullptr;
+  // LOUDGAIN_B200_STEP_TRACE (tuning): direct launches with a timing event behind every
+  // stage of the step on the stream it runs on; the fetch prints them
+  bool trace = false;
+  std::vector<std::pair<const char*, cudaEvent_t>> marks;
   // optional sweep timing
   bool timing = false, timed_run_pending = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -348,6 +357,7 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
   if (const char* e = getenv("LOUDGAIN_B200_RUN_CHUNKS")) opt.force_run_chunks = atoi(e);   // tuning
   if (const char* e = getenv("LOUDGAIN_B200_RUN_WARPS")) opt.run_warps_per_sm = (uint32_t) atoi(e);   // tuning
   if (const char* e = getenv("LOUDGAIN_B200_PAIR_CTAS")) b->pair_ctas = (uint32_t) atoi(e);   // tuning
+  b->trace = getenv("LOUDGAIN_B200_STEP_TRACE") != nullptr;
   if (const char* e = getenv("LOUDGAIN_B200_TAIL_FRAC")) opt.tail_frac = atof(e);      // tuning
   if (const char* e = getenv("LOUDGAIN_B200_TAIL_DIV")) opt.tail_div = atoi(e);
   build_plan(in.data(), ntracks, nalbums, opt, b->plan);
@@ -364,16 +374,22 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
             upload(p.members, &b->d_members, b->stream) &&
             dalloc(&b->d_recs, p.total_recs, b->stream) &&
             upload(p.items, &b->d_items, b->stream) && upload(p.xi_table, &b->d_xi, b->stream) &&
-            dalloc(&b->d_runq, p.total_queue, b->stream) &&
+            dalloc(&b->d_runq, 2 * p.total_queue, b->stream) &&          // 64-bit entries
             dalloc(&b->d_runcnt, (uint64_t) p.items.size() * 32u, b->stream) &&
-            dalloc(&b->d_rundense, p.total_queue, b->stream) &&
-            dalloc(&b->d_peaks, 2 * p.total_peaks + p.groups.size() + 1, b->stream) &&
+            dalloc(&b->d_out, 16 * (uint64_t) p.queries.size() + 2 * p.total_peaks + p.groups.size() + 1,
+                   b->stream) &&
             dalloc(&b->d_mrec, p.total_mrec, b->stream) &&
             dalloc(&b->d_tpq, 2 * p.total_mrec, b->stream) &&
             dalloc(&b->d_eslot, p.total_slots, b->stream) &&
             dalloc(&b->d_zblock, p.total_blocks, b->stream) &&
-            dalloc(&b->d_zst, p.total_st, b->stream) &&
-            dalloc(&b->d_results, (uint64_t) p.queries.size(), b->stream);
+            dalloc(&b->d_zst, p.total_st, b->stream);
+  static_assert(sizeof(QueryResult) == 64, "results sit in front of the 32-bit peak cells");
+  if (ok) {
+    b->d_results = reinterpret_cast<QueryResult*>(b->d_out);
+    b->d_peaks = b->d_out + 16 * p.queries.size();
+    b->peaks_off = p.queries.size() * sizeof(QueryResult);
+    b->out_bytes = b->peaks_off + 2 * p.total_peaks * sizeof(uint32_t);
+  }
   if (ok) ok = make_tensor_maps(b);
   if (ok) {
     std::vector<BlockList> lists(p.tracks.size());
@@ -384,10 +400,11 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
     ok = upload(lists, &b->d_lists, b->stream);
   }
   if (ok) {
-    cudaError_t e = cudaMallocHost((void**) &b->h_results,
-                                   (p.queries.empty() ? 1 : p.queries.size()) * sizeof(QueryResult));
-    if (e == cudaSuccess)
-      e = cudaMallocHost((void**) &b->h_peaks, (p.total_peaks ? 2 * p.total_peaks : 1) * sizeof(uint32_t));
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+      e = cudaMallocHost((void**) &b->h_out[k], b->out_bytes ? b->out_bytes : 1);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_done[k], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) { set_error("cudaMallocHost(results)", e); ok = false; }
   }
   if (ok) {
@@ -435,7 +452,7 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
   }
   b->sweep_launches = (uint32_t) p.groups.size();
   uint32_t tp_launches = 0;
-  for (const SweepGroup& g : p.groups) tp_launches += g.tpf ? (g.params.packed ? 2u : 1u) : 0u;
+  for (const SweepGroup& g : p.groups) tp_launches += g.tpf ? ((g.params.packed && !g.run) ? 2u : 1u) : 0u;
   b->launches = b->sweep_launches + tp_launches + (p.total_slots ? 1 : 0) +
                 ((p.total_blocks + p.total_st) ? 1 : 0) + (p.queries.empty() ? 0 : 1);
   return b;
@@ -443,7 +460,7 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
 
 // One complete step on the batch's stream: sweep, true-peak pass, FP64
 // fix-up, blocks, queries, and the copy of the scalars into the pinned mirrors.
-static int enqueue_step(lgb_batch* b) {
+static int enqueue_step(lgb_batch* b, int parity) {
   const Plan& p = b->plan;
   const DeviceTables t = b->tables();
   // peak cells, then one true-peak ticket counter per launch group
@@ -451,6 +468,17 @@ static int enqueue_step(lgb_batch* b) {
   cudaError_t e = cudaMemsetAsync(b->d_peaks, 0, (2 * p.total_peaks + p.groups.size() + 1) * sizeof(uint32_t),
                                   b->stream);
   if (e != cudaSuccess) { set_error("cudaMemsetAsync(peaks)", e); return 1; }
+  size_t nmarks = 0;
+  auto mark = [&](const char* name, cudaStream_t s) {
+    if (!b->trace) return;
+    if (nmarks == b->marks.size()) {
+      cudaEvent_t ev;
+      cudaEventCreate(&ev);
+      b->marks.emplace_back(name, ev);
+    }
+    cudaEventRecord(b->marks[nmarks++].second, s);
+  };
+  mark("memset", b->stream);
   if (b->timing) cudaEventRecord(b->ev0, b->stream);
   const bool gfork = p.groups.size() > 1 && b->ngstreams > 0;
   if (gfork) {
@@ -477,7 +505,7 @@ static int enqueue_step(lgb_batch* b) {
       sp.items = b->d_items + g.first_item;
       sp.tp_ticket = b->d_peaks + 2 * p.total_peaks + gidx;
       sp.run_counts = b->d_runcnt + (size_t) g.first_item * 32u;
-      sp.run_queue = b->d_runq + g.queue_base;
+      sp.run_queue = b->d_runq + 2 * g.queue_base;
     }
     ++gidx;
     e = g.run ? launch_sweep_run(sp, g.format, g.tpf, b->sms, gs)
@@ -494,6 +522,7 @@ static int enqueue_step(lgb_batch* b) {
     }
   }
   if (b->timing) { cudaEventRecord(b->ev1, b->stream); b->timed_run_pending = true; }
+  mark("sweep", b->stream);
   // Fork (not in timed runs: those keep everything on the main stream, between
   // the events): fix-up, slot and block kernels go to the high-priority side
   // stream first.  The true-peak evaluation fills every SM for its whole
@@ -506,6 +535,7 @@ static int enqueue_step(lgb_batch* b) {
   auto post_kernels = [&]() -> int {
     e = launch_post(t, z, ps);
     if (e != cudaSuccess) { set_error("launch_post", e); return 1; }
+    mark("fixslot+block", ps);
     if (fork) {
       e = cudaEventRecord(b->ev_post, ps);
       if (e != cudaSuccess) { set_error("cudaEventRecord(post)", e); return 1; }
@@ -539,8 +569,7 @@ static int enqueue_step(lgb_batch* b) {
     if (g.run) {
       sp.items = b->d_items + g.first_item;
       sp.run_counts = b->d_runcnt + (size_t) g.first_item * 32u;
-      sp.run_queue = b->d_runq + g.queue_base;
-      sp.tp_dense = b->d_rundense + g.queue_base;
+      sp.run_queue = b->d_runq + 2 * g.queue_base;
     }
     cudaEvent_t hold = fork ? b->ev_post : nullptr;
     e = g.run ? launch_truepeak_run(sp, g.format, g.tpf, b->sms, b->stream, hold)
@@ -548,6 +577,7 @@ static int enqueue_step(lgb_batch* b) {
                     : launch_truepeak(sp, g.format, g.tpf, b->sms, b->stream, hold);
     if (e != cudaSuccess) { set_error("launch_truepeak", e); return 1; }
   }
+  mark("true-peak pass", b->stream);
   if (b->timing) cudaEventRecord(b->ev2, b->stream);
   if (!fork && post_kernels()) return 1;
   if (b->xchg) {
@@ -561,65 +591,117 @@ static int enqueue_step(lgb_batch* b) {
     for (uint32_t r = 0; r < x->world; ++r) xp.peer[r] = x->peer[r];
     xp.st_off = b->d_xstoff;
     xp.ctl = x->d_ctl;
-    e = launch_exchange_publish(t.lists, t.queries, t.members, b->abs_gate, xp, ps);
+    e = cudaEventRecord(b->ev_q0, ps);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(b->qstream, b->ev_q0, 0);
     if (e == cudaSuccess)
       e = launch_queries(t.lists, t.queries, t.members, (uint32_t) p.tracks.size(), b->abs_gate, t.results,
-                         ps, 1);
+                         b->qstream, 1);
+    if (e == cudaSuccess) e = cudaEventRecord(b->ev_q1, b->qstream);
+    if (e == cudaSuccess) e = launch_exchange_publish(t.lists, t.queries, t.members, b->abs_gate, xp, ps);
     if (e == cudaSuccess)
       e = launch_exchange_finish(t.lists, t.queries, t.members, b->abs_gate, t.results, xp, ps);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ps, b->ev_q1, 0);
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(x->h_ctl, x->d_ctl + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ps);
+  } else if (b->qstream && !b->timing) {
+    // the loudness range (short-term lists, one CTA per query) next to the integrated
+    // loudness (gating lists, a cluster per query): two launches on two streams
+    e = cudaEventRecord(b->ev_q0, ps);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(b->qstream, b->ev_q0, 0);
+    if (e == cudaSuccess)
+      e = launch_queries(t.lists, t.queries, t.members, (uint32_t) p.queries.size(), b->abs_gate, t.results,
+                         b->qstream, 1, 2);
+    if (e == cudaSuccess) e = cudaEventRecord(b->ev_q1, b->qstream);
+    if (e == cudaSuccess)
+      e = launch_queries(t.lists, t.queries, t.members, (uint32_t) p.queries.size(), b->abs_gate, t.results,
+                         ps, b->query_cluster, 1);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ps, b->ev_q1, 0);
   } else {
     e = launch_queries(t.lists, t.queries, t.members, (uint32_t) p.queries.size(), b->abs_gate,
                        t.results, ps, b->query_cluster);
   }
   if (e != cudaSuccess) { set_error("launch_queries", e); return 1; }
+  mark("queries", ps);
   if (fork) {
     e = cudaEventRecord(b->ev_join, b->side);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(b->stream, b->ev_join, 0);
     if (e != cudaSuccess) { set_error("join(post-processing stream)", e); return 1; }
   }
-  if (!p.queries.empty())
-    e = cudaMemcpyAsync(b->h_results, b->d_results, p.queries.size() * sizeof(QueryResult),
-                        cudaMemcpyDeviceToHost, b->stream);
-  if (e == cudaSuccess && p.total_peaks)
-    e = cudaMemcpyAsync(b->h_peaks, b->d_peaks, 2 * p.total_peaks * sizeof(uint32_t),
-                        cudaMemcpyDeviceToHost, b->stream);
+  if (b->out_bytes)
+    e = cudaMemcpyAsync(b->h_out[parity], b->d_out, b->out_bytes, cudaMemcpyDeviceToHost, b->stream);
   if (e != cudaSuccess) { set_error("cudaMemcpyAsync(results)", e); return 1; }
+  mark("read-back", b->stream);
   return 0;
 }
 
 extern "C" LG_EXPORT int lgb_batch_run(lgb_batch* b) {
-  ++b->runs;
-  // timed runs (bench roofline leg) and the first run launch directly
-  if (b->timing || b->graph_off || b->runs < 2) return enqueue_step(b);
-  if (!b->graph) {
+  if (b->runs - b->fetched >= 2u) {
+    set_error("lgb_batch_run: two runs are in flight already (fetch the older one first)");
+    return 1;
+  }
+  const uint32_t k = b->runs++;
+  const int parity = (int) (k & 1u);
+  if (k == 1 && !b->qstream && b->side) {
+    // a batch that is run again gets a third stream: the two halves of its queries run
+    // side by side from now on (a one-shot batch does not pay for the stream)
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&b->qstream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_q0, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_q1, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      if (b->qstream) { cudaStreamDestroy(b->qstream); b->qstream = nullptr; }
+    }
+  }
+  auto done = [&](int rc) {
+    if (rc == 0 && cudaEventRecord(b->ev_done[parity], b->stream) != cudaSuccess) {
+      set_error("lgb_batch_run: cudaEventRecord failed");
+      return 1;
+    }
+    return rc;
+  };
+  // timed runs (bench roofline leg), traced runs and the first run launch directly
+  if (b->timing || b->graph_off || b->trace || k < 1) return done(enqueue_step(b, parity));
+  if (!b->graph[parity]) {
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeRelaxed);
     if (e == cudaSuccess) {
-      const int rc = enqueue_step(b);
+      const int rc = enqueue_step(b, parity);
       e = cudaStreamEndCapture(b->stream, &g);
       if (rc != 0 && e == cudaSuccess) e = cudaErrorUnknown;
     }
-    if (e == cudaSuccess) e = cudaGraphInstantiate(&b->graph, g, 0);
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&b->graph[parity], g, 0);
     if (g) cudaGraphDestroy(g);
     if (e != cudaSuccess) {          // capture not possible on this stream: keep launching directly
       cudaGetLastError();
-      b->graph = nullptr;
+      b->graph[parity] = nullptr;
       b->graph_off = true;
-      return enqueue_step(b);
+      return done(enqueue_step(b, parity));
     }
   }
-  const cudaError_t e = cudaGraphLaunch(b->graph, b->stream);
+  const cudaError_t e = cudaGraphLaunch(b->graph[parity], b->stream);
   if (e != cudaSuccess) { set_error("cudaGraphLaunch", e); return 1; }
-  return 0;
+  return done(0);
 }
 
 extern "C" LG_EXPORT int lgb_batch_fetch(lgb_batch* b, lgb_result* track_results, lgb_result* album_results,
                                double* sample_peaks, double* true_peaks) {
   const Plan& p = b->plan;
-  const cudaError_t e = cudaStreamSynchronize(b->stream);
+  if (b->fetched == b->runs) { set_error("lgb_batch_fetch: no run to fetch"); return 1; }
+  const int parity = (int) (b->fetched++ & 1u);       // the oldest run that has not been fetched
+  const cudaError_t e = cudaEventSynchronize(b->ev_done[parity]);
   if (e != cudaSuccess) { set_error("lgb_batch_fetch", e); return 1; }
+  const QueryResult* h_results = reinterpret_cast<const QueryResult*>(b->h_out[parity]);
+  const uint32_t* h_peaks = reinterpret_cast<const uint32_t*>(b->h_out[parity] + b->peaks_off);
+  if (b->trace && b->marks.size() > 1 && b->runs > 3) {
+    fprintf(stderr, "[lgb step]");
+    for (size_t i = 1; i < b->marks.size(); ++i) {
+      float ms = 0.0f;
+      cudaEventElapsedTime(&ms, b->marks[0].second, b->marks[i].second);
+      fprintf(stderr, " %s +%.1f us;", b->marks[i].first, 1e3f * ms);
+    }
+    fprintf(stderr, "\n");
+  }
   if (b->xchg && *b->xchg->h_ctl) {
     set_error("lgb_batch_fetch: a rank of the album exchange did not arrive (timed out)");
     return 1;
@@ -634,16 +716,16 @@ extern "C" LG_EXPORT int lgb_batch_fetch(lgb_batch* b, lgb_result* track_results
     b->timed_run_pending = false;
   }
   const size_t nt = p.tracks.size();
-  if (track_results) for (size_t i = 0; i < nt; ++i) to_result(b->h_results[i], track_results[i]);
-  if (album_results) for (uint32_t a = 0; a < p.nalbums; ++a) to_result(b->h_results[nt + a], album_results[a]);
+  if (track_results) for (size_t i = 0; i < nt; ++i) to_result(h_results[i], track_results[i]);
+  if (album_results) for (uint32_t a = 0; a < p.nalbums; ++a) to_result(h_results[nt + a], album_results[a]);
   if (sample_peaks || true_peaks) {
     for (size_t i = 0; i < nt; ++i) {
       const Track& tr = p.tracks[i];
       const double scale = tr.format == FMT_S16 ? 32768.0 : 1.0;
       for (uint32_t c = 0; c < tr.channels; ++c) {
         float sp, tp;
-        memcpy(&sp, &b->h_peaks[2 * (tr.peak_base + c)], 4);
-        memcpy(&tp, &b->h_peaks[2 * (tr.peak_base + c) + 1], 4);
+        memcpy(&sp, &h_peaks[2 * (tr.peak_base + c)], 4);
+        memcpy(&tp, &h_peaks[2 * (tr.peak_base + c) + 1], 4);
         const double s = (double) sp / scale, t = (double) tp / scale;
         if (sample_peaks) sample_peaks[tr.peak_base + c] = s;
         if (true_peaks) true_peaks[tr.peak_base + c] = t > s ? t : s;
@@ -682,14 +764,18 @@ extern "C" LG_EXPORT uint64_t lgb_debug_trace(lgb_batch* b, uint64_t* out, uint6
 // True-peak candidates the last run's sweeps queued for evaluation (run-sweep
 // groups; diagnostic: how much of the audio the screening could not rule out).
 extern "C" LG_EXPORT uint64_t lgb_batch_truepeak_candidates(lgb_batch* b) {
-  const size_t n = b->plan.items.size() * 32u;
-  if (!n) return 0;
-  std::vector<uint32_t> h(n);
-  if (cudaStreamSynchronize(b->stream) != cudaSuccess ||
-      cudaMemcpy(h.data(), b->d_runcnt, n * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess)
-    return 0;
+  const Plan& p = b->plan;
+  if (cudaStreamSynchronize(b->stream) != cudaSuccess) return 0;
   uint64_t total = 0;
-  for (uint32_t c : h) total += c;
+  for (const SweepGroup& g : p.groups) {
+    if (!g.run || !g.tpf) continue;
+    const uint32_t grid = g.nitems < b->sms ? g.nitems : b->sms;
+    std::vector<uint32_t> h(grid);
+    if (cudaMemcpy(h.data(), b->d_runcnt + (size_t) g.first_item * 32u, grid * sizeof(uint32_t),
+                   cudaMemcpyDeviceToHost) != cudaSuccess)
+      return 0;
+    for (uint32_t c : h) total += c;
+  }
   return total;
 }
 
@@ -917,7 +1003,18 @@ extern "C" LG_EXPORT int lgb_batch_attach_exchange(lgb_batch* b, lgb_exchange* x
   if (cudaStreamSynchronize(b->stream) != cudaSuccess) { set_error("lgb_batch_attach_exchange: stream error"); return 1; }
   if (b->d_xstoff) cudaFreeAsync(b->d_xstoff, b->stream);
   if (!upload(off, &b->d_xstoff, b->stream) || cudaStreamSynchronize(b->stream) != cudaSuccess) return 1;
-  if (b->graph) { cudaGraphExecDestroy(b->graph); b->graph = nullptr; }
+  for (int k = 0; k < 2; ++k)
+    if (b->graph[k]) { cudaGraphExecDestroy(b->graph[k]); b->graph[k] = nullptr; }
+  if (!b->qstream) {
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&b->qstream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_q0, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_q1, cudaEventDisableTiming) != cudaSuccess) {
+      set_error("lgb_batch_attach_exchange: stream creation failed");
+      return 1;
+    }
+  }
   if (!b->xchg) b->launches += 3u - (nt ? 0u : 1u);      // publish, gate, finish; the query launch stays if there are tracks
   b->xchg = x;
   return 0;
@@ -926,23 +1023,29 @@ extern "C" LG_EXPORT int lgb_batch_attach_exchange(lgb_batch* b, lgb_exchange* x
 extern "C" LG_EXPORT void lgb_batch_destroy(lgb_batch* b) {
   if (!b) return;
   if (b->ev0) { cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); cudaEventDestroy(b->ev2); }
+  for (auto& m : b->marks) cudaEventDestroy(m.second);
   void* const mem[] = {b->d_tracks, b->d_coefs, b->d_work, b->d_queries, b->d_members, b->d_lists,
-                       b->d_recs, b->d_peaks, b->d_mrec, b->d_tpq, b->d_tmaps, b->d_items, b->d_xi, b->d_runq, b->d_runcnt, b->d_rundense, b->d_eslot, b->d_zblock, b->d_zst,
-                       b->d_results, b->d_xstoff};
-  if (b->h_results) cudaStreamSynchronize(b->stream);   // a run may still be writing the mirrors
+                       b->d_recs, b->d_out, b->d_mrec, b->d_tpq, b->d_tmaps, b->d_items, b->d_xi, b->d_runq, b->d_runcnt, b->d_eslot, b->d_zblock, b->d_zst,
+                       b->d_xstoff};
+  cudaStreamSynchronize(b->stream);   // a run may still be writing the mirrors
   for (void* m : mem) if (m) cudaFreeAsync(m, b->stream);
-  if (b->graph) cudaGraphExecDestroy(b->graph);
+  for (int k = 0; k < 2; ++k) {
+    if (b->graph[k]) cudaGraphExecDestroy(b->graph[k]);
+    if (b->ev_done[k]) cudaEventDestroy(b->ev_done[k]);
+    if (b->h_out[k]) cudaFreeHost(b->h_out[k]);
+  }
   if (b->ev_fork) cudaEventDestroy(b->ev_fork);
   if (b->ev_join) cudaEventDestroy(b->ev_join);
   if (b->ev_post) cudaEventDestroy(b->ev_post);
   if (b->ev_blocks) cudaEventDestroy(b->ev_blocks);
   if (b->side) cudaStreamDestroy(b->side);
+  if (b->ev_q0) cudaEventDestroy(b->ev_q0);
+  if (b->ev_q1) cudaEventDestroy(b->ev_q1);
+  if (b->qstream) cudaStreamDestroy(b->qstream);
   if (b->ev_gfork) cudaEventDestroy(b->ev_gfork);
   for (int j = 0; j < lgb_batch::kGroupStreams; ++j) {
     if (b->ev_gjoin[j]) cudaEventDestroy(b->ev_gjoin[j]);
     if (b->gstream[j]) cudaStreamDestroy(b->gstream[j]);
   }
-  if (b->h_results) cudaFreeHost(b->h_results);
-  if (b->h_peaks) cudaFreeHost(b->h_peaks);
   delete b;
 }

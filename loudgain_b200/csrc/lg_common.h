@@ -263,6 +263,7 @@ struct SweepParams {
   float lam_re[kIter], lam_im[kIter];
   float rot_re, rot_im;
   float tp_bound;          // ||taps||_1 bound used for true-peak screening
+  uint32_t tp_taps;        // taps per interpolator phase (12 at 4x, 24 at 2x, 0: no interpolator)
   int32_t W, L, niters, aq;
   uint32_t npairs;         // (niters + 1) / 2: iteration pairs per lane
   uint32_t channels, fb;
@@ -302,10 +303,11 @@ struct SweepParams {
   uint32_t run_stage_frames; // frames per staged piece of a row
   uint32_t run_nstages;      // stages per item = ceil((Wp + Lr) / stage frames)
   uint32_t run_warps_per_sm; // resident one-warp CTAs per SM
-  uint32_t* run_queue;       // true-peak candidates: 32-bit entries, one stretch per (item, lane)
-  void* tp_dense;            // ... that passed the final screening, packed (lg_run.cu: tp_filter_run_kernel)
-  uint32_t* run_counts;      // [nitems * 32] entries a lane queued
-  uint32_t run_lane_stride;  // queue entries reserved per lane = npairs * 2 channels
+  uint32_t* run_queue;       // true-peak candidates: 64-bit entries, one dense stretch per sweep CTA
+  void* tp_dense;            // (unused)
+  uint32_t* run_counts;      // [sweep CTAs] entries a CTA queued
+  uint32_t run_lane_stride;  // most entries one lane can queue = npairs * 2 channels
+  uint32_t run_cta_cap;      // entries reserved per sweep CTA (its items' lanes x run_lane_stride)
   float peak_scale;          // raw sample unit / the sweep's internal unit (16-bit input is scaled by 65536)
 };
 

@@ -247,7 +247,9 @@ bool flush_stage(ebur128_state* st, bool held = false, bool may_release = true) 
   Segment& s = d->segs.back();
   const size_t need = s.fill + sl.fill;
   if (need > s.cap) {
-    const size_t ncap = round_up(std::max<size_t>(std::max<size_t>(s.cap * 2, need), 8u << 20), 1u << 20);
+    // a state that has been released before only keeps a tail: it grows by what it needs
+    const size_t ncap = round_up(s.base ? need : std::max<size_t>(std::max<size_t>(s.cap * 2, need), 8u << 20),
+                                 1u << 20);
     char* np = nullptr;
     if (cudaMallocAsync((void**) &np, ncap, g_ctx.stream) != cudaSuccess) return false;
     if (s.fill &&
@@ -795,6 +797,7 @@ extern "C" LG_EXPORT void lgb_dropin_pcm_bytes(uint64_t* now, uint64_t* peak, ui
   if (now) *now = g_ctx.pcm_bytes;
   if (peak) *peak = g_ctx.pcm_peak_bytes;
   if (releases) *releases = g_ctx.releases;
+  g_ctx.pcm_peak_bytes = g_ctx.pcm_bytes;          // the high-water mark restarts with every reading
 }
 
 extern "C" LG_EXPORT void ebur128_get_version(int* major, int* minor, int* patch) {

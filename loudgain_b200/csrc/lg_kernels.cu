@@ -690,7 +690,19 @@ const double* hist_table() {
 
 // ------------------------------------------------------------- reductions
 
-constexpr int kQueryThreads = 1024;
+constexpr int kQueryThreads = 1024;     // the most a query CTA may have (select_two needs 256 or more)
+// What the query kernels are launched with.  A 1024-thread CTA needs a whole SM's register
+// file (64 per thread), so it waits for any SM that still holds CTAs of the true-peak
+// evaluation; smaller CTAs slip in next to them but have fewer loads in flight.
+constexpr int kQueryLaunchDefault = 1024;
+static int query_launch_threads() {
+  static const int n = [] {
+    const char* e = getenv("LOUDGAIN_B200_QUERY_THREADS");      // tuning: 256, 512 or 1024
+    const int v = e ? atoi(e) : 0;
+    return (v == 256 || v == 512 || v == 1024) ? v : kQueryLaunchDefault;
+  }();
+  return n;
+}
 
 struct SumCount {
   double s;
@@ -823,27 +835,31 @@ __device__ void select_two(const QueryView& v, const double* s_st, uint32_t n_st
       for_each_energy<true>(v, count);
     }
     __syncthreads();
-    // threads 0..255 own the bins of rank 0, 256..511 those of rank 1
-    const bool owner = threadIdx.x < 512;
-    const int which = (threadIdx.x >> 8) & 1, bin = threadIdx.x & 255;
-    const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 7;
-    const unsigned int cnt = owner ? hist[threadIdx.x] : 0u;
-    unsigned int inc = cnt;
+    // a CTA of 512 threads or more: threads 0..255 own the bins of rank 0, 256..511 those
+    // of rank 1; a 256-thread CTA scans the two histograms one after the other
+    const int nscan = blockDim.x >= 512 ? 1 : 2;
+    for (int sc = 0; sc < nscan; ++sc) {
+      const bool owner = threadIdx.x < (nscan == 1 ? 512 : 256);
+      const int which = nscan == 1 ? (threadIdx.x >> 8) & 1 : sc, bin = threadIdx.x & 255;
+      const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 7;
+      const unsigned int cnt = owner ? hist[which * 256 + bin] : 0u;
+      unsigned int inc = cnt;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += u;
-    }
-    if (owner && lane == 31) wsum[which * 8 + w] = inc;
-    __syncthreads();
-    unsigned int base = 0;
-    for (int j = 0; j < w; ++j) base += wsum[which * 8 + j];
-    const unsigned long long excl = (unsigned long long) base + inc - cnt;
-    const unsigned long long kk = st->k[which];
-    __syncthreads();
-    if (owner && cnt && excl <= kk && kk < excl + cnt) {
-      st->k[which] = kk - excl;
-      st->prefix[which] |= (unsigned long long) bin << shift;
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      if (owner && lane == 31) wsum[which * 8 + w] = inc;
+      __syncthreads();
+      unsigned int base = 0;
+      for (int j = 0; j < w; ++j) base += wsum[which * 8 + j];
+      const unsigned long long excl = (unsigned long long) base + inc - cnt;
+      const unsigned long long kk = st->k[which];
+      __syncthreads();
+      if (owner && cnt && excl <= kk && kk < excl + cnt) {
+        st->k[which] = kk - excl;
+        st->prefix[which] |= (unsigned long long) bin << shift;
+      }
     }
     mask |= 0xffull << shift;
     __syncthreads();
@@ -871,6 +887,10 @@ __device__ SumCount cluster_sum_count(cooperative_groups::cluster_group& cluster
   return t;
 }
 
+// PART 0: the whole query; 1: integrated loudness only; 2: loudness range only (the two
+// halves read different lists and write different fields of the result, so a step runs
+// them side by side on two streams: lg_batch.cu).
+template <int PART>
 __global__ void __launch_bounds__(kQueryThreads)
 query_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ queries,
              const uint32_t* __restrict__ members, double abs_gate,
@@ -916,8 +936,10 @@ query_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ quer
   v.stride = R * blockDim.x;
   double s = 0.0;
   unsigned long long n = 0;
+  SumCount a{0.0, 0ull};
+  if (PART != 2) {
   for_each_energy<false>(v, [&](double e, uint32_t) { if (e >= abs_gate) { s += e; ++n; } });
-  SumCount a = cluster_sum_count(cluster, block_sum_count(s, n, scratch), xch[0]);
+  a = cluster_sum_count(cluster, block_sum_count(s, n, scratch), xch[0]);
   res.sum1 = a.s; res.n1 = a.n;
   SumCount b{0.0, 0ull};
   if (a.n) {                                   // cluster-uniform
@@ -932,6 +954,15 @@ query_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ quer
   if (R > 1) {
     cluster.sync();                            // everyone has read rank 0's exchange buffers
     if (rk != 0) return;
+  }
+  }
+  if (PART == 1) {
+    if (threadIdx.x == 0) {
+      QueryResult& o = results[qi];
+      o.loudness = res.loudness; o.rel_thr = res.rel_thr;
+      o.sum1 = res.sum1; o.sum2 = res.sum2; o.n1 = res.n1; o.n2 = res.n2;
+    }
+    return;
   }
 
   // ---- loudness range (rank 0): -20 LU relative gate on short-term energies,
@@ -966,7 +997,10 @@ query_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ quer
       res.range = energy_to_lufs(hi) - energy_to_lufs(lo);
     }
   }
-  if (threadIdx.x == 0) results[qi] = res;
+  if (threadIdx.x == 0) {
+    if (PART == 2) { results[qi].range = res.range; results[qi].nst = res.nst; }
+    else results[qi] = res;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -1215,7 +1249,7 @@ xchg_finish_kernel(double abs_gate, QueryResult* __restrict__ results, const __g
 cudaError_t launch_exchange_publish(const BlockList* lists, const Query* queries, const uint32_t* members,
                                     double abs_gate, const XchgParams& x, cudaStream_t stream) {
   if (!x.nalbums) return cudaSuccess;
-  xchg_publish_kernel<<<x.nalbums, kQueryThreads, 0, stream>>>(lists, queries, members, abs_gate, x);
+  xchg_publish_kernel<<<x.nalbums, query_launch_threads(), 0, stream>>>(lists, queries, members, abs_gate, x);
   return cudaGetLastError();
 }
 
@@ -1223,10 +1257,10 @@ cudaError_t launch_exchange_finish(const BlockList* lists, const Query* queries,
                                    double abs_gate, QueryResult* results, const XchgParams& x,
                                    cudaStream_t stream) {
   if (!x.nalbums) return cudaSuccess;
-  xchg_gate_kernel<<<x.nalbums, kQueryThreads, 0, stream>>>(lists, queries, members, abs_gate, x);
+  xchg_gate_kernel<<<x.nalbums, query_launch_threads(), 0, stream>>>(lists, queries, members, abs_gate, x);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  xchg_finish_kernel<<<x.nalbums, kQueryThreads, 0, stream>>>(abs_gate, results, x);
+  xchg_finish_kernel<<<x.nalbums, query_launch_threads(), 0, stream>>>(abs_gate, results, x);
   return cudaGetLastError();
 }
 
@@ -1317,7 +1351,7 @@ cudaError_t launch_widen_s16(const void* in, void* out, size_t n, cudaStream_t s
 }
 
 uint32_t query_cluster_size(uint64_t max_gating_blocks) {
-  // one more CTA per 4 k gating blocks of the largest query (about seven minutes of audio)
+  // one more CTA (256 threads) per 4 k gating blocks of the largest query (about seven minutes of audio)
   static const uint64_t per_cta = [] {
     const char* e = getenv("LOUDGAIN_B200_QUERY_BLOCKS_PER_CTA");   // tuning
     const long long v = e ? atoll(e) : 0;
@@ -1329,13 +1363,14 @@ uint32_t query_cluster_size(uint64_t max_gating_blocks) {
 
 cudaError_t launch_queries(const BlockList* lists, const Query* queries, const uint32_t* members,
                            uint32_t nqueries, double abs_gate, QueryResult* results,
-                           cudaStream_t stream, uint32_t cluster) {
+                           cudaStream_t stream, uint32_t cluster, int part) {
   if (!nqueries) return cudaSuccess;
+  if (part == 2) cluster = 1;                  // the range is one CTA's work
   if (cluster < 1) cluster = 1;
   if (cluster > (uint32_t) kMaxQueryCluster) cluster = kMaxQueryCluster;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nqueries * cluster);
-  cfg.blockDim = dim3(kQueryThreads);
+  cfg.blockDim = dim3(query_launch_threads());
   cfg.dynamicSmemBytes = 0;
   cfg.stream = stream;
   cudaLaunchAttribute attr;
@@ -1345,7 +1380,9 @@ cudaError_t launch_queries(const BlockList* lists, const Query* queries, const u
   attr.val.clusterDim.z = 1;
   cfg.attrs = &attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, query_kernel, lists, queries, members, abs_gate, results);
+  if (part == 1) return cudaLaunchKernelEx(&cfg, query_kernel<1>, lists, queries, members, abs_gate, results);
+  if (part == 2) return cudaLaunchKernelEx(&cfg, query_kernel<2>, lists, queries, members, abs_gate, results);
+  return cudaLaunchKernelEx(&cfg, query_kernel<0>, lists, queries, members, abs_gate, results);
 }
 
 }  // namespace lg

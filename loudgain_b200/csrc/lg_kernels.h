@@ -64,9 +64,11 @@ const double* hist_table();
 // Gated loudness + range for `nqueries` queries; all pointers are device memory.
 // `cluster` = CTAs per query (thread-block cluster sharing the gating blocks of a
 // query); query_cluster_size() picks it from the largest query's block count.
+// `part`: 0 = the whole query, 1 = integrated loudness only, 2 = loudness range only (the
+// halves touch different lists and different result fields and may run concurrently).
 cudaError_t launch_queries(const BlockList* lists, const Query* queries, const uint32_t* members,
                            uint32_t nqueries, double abs_gate, QueryResult* results,
-                           cudaStream_t stream, uint32_t cluster = 1);
+                           cudaStream_t stream, uint32_t cluster = 1, int part = 0);
 uint32_t query_cluster_size(uint64_t max_gating_blocks);
 // Album queries over tracks sharded across GPUs (lg_common.h: XchgParams): the first
 // launch publishes this rank's share to every peer, the second pair gates against the

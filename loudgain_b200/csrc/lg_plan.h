@@ -301,6 +301,7 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, const Plan
     sp = SweepParams();
     fill_kcoef(cs, sp);
     sp.tp_bound = cs.tpf == 4 ? 1.8645f : 2.3072f;   // > ||taps||_1 (1.8642 / 2.3068)
+    sp.tp_taps = cs.tpf == 4 ? 12u : (cs.tpf == 2 ? 24u : 0u);
     sp.W = cs.W; sp.L = cs.L; sp.niters = (int32_t) t0.niters; sp.aq = (int32_t) t0.aq;
     sp.npairs = (t0.niters + 1u) / 2u;
     sp.channels = t0.channels; sp.fb = t0.fb;
@@ -330,7 +331,14 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, const Plan
       sp.nwarps = g.nitems;
       g.queue_base = p.total_queue;
       sp.run_lane_stride = (sp.npairs * 2u + 3u) & ~3u;        // 16-byte multiples
-      g.queue_cap = cs.tpf ? (uint64_t) g.nitems * 32u * sp.run_lane_stride : 0u;
+      {
+        // one dense stretch per sweep CTA (lg_run.cu launches min(sms, nitems) of them, CTA b
+        // owning the items b, b + grid, ...): room for every pair of every lane of its items
+        const uint32_t grid = g.nitems < opt.sms ? g.nitems : opt.sms;
+        const uint64_t per_cta = grid ? (uint64_t) ((g.nitems + grid - 1) / grid) * 32u * sp.run_lane_stride : 0u;
+        sp.run_cta_cap = (uint32_t) per_cta;
+        g.queue_cap = cs.tpf ? per_cta * grid : 0u;
+      }
       p.total_queue += g.queue_cap;
       if (g.nitems) p.groups.push_back(g);
       continue;

@@ -32,14 +32,18 @@
 // True peak is a maximum: a polyphase output cannot exceed ||c||_1 * max|x|
 // over its window, and the channel's true peak is at least the largest sample
 // seen so far.  The sweep tests every 24-frame pair against the channel's
-// current peak cell and appends the survivors to the lane's own stretch of the
-// candidate queue (no atomics, no votes: the cursor is a register);
-// tp_filter_run_kernel re-tests them against the final sample peak and packs
-// what is left into a dense queue, tp_eval_run_kernel evaluates the FIR on it
-// (identical to evaluating every frame).
+// current peak cell; what survives goes into the CTA's own DENSE stretch of the
+// candidate queue -- once per stage a warp adds up its lanes' survivors, takes
+// that many slots from the CTA's ticket in shared memory and every lane stores
+// its entries behind those of the lanes before it.  tp_eval_run_kernel then
+// spreads all CTAs' candidates over the whole GPU, drops those the channel's
+// FINAL sample peak rules out and evaluates the FIR on the rest: the same
+// maximum as evaluating every frame (a window that is evaluated needlessly
+// cannot raise it above the true value, one that is skipped cannot reach it).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "lg_common.h"
 #include "lg_device.cuh"
@@ -140,21 +144,24 @@ __device__ __forceinline__ void run_iter_warm(RunCtx& c, const SweepParams& k, c
   for (int i = 0; i < kIter; ++i) (void) k_step2(c, x[i], k);
 }
 
-// Queue entry of a true-peak candidate (32 bits, in the lane's own stretch of the
-// item's queue): channel (1) | pair (15) | code of the bound (16; lg_sweep.cuh:
-// peak_code of max |x| in the sweep's unit, rounded up).
+// Queue entry of a true-peak candidate (64 bits): high word = channel (1) | pair (15) |
+// code of the bound (16; lg_sweep.cuh: peak_code of max |x| in the sweep's unit, rounded
+// up), low word = item * 32 + lane.  (Entries that carry the window's address instead,
+// so that the evaluation need not look the item and the track up, made the 16-bit sweep
+// 10 % slower and the evaluation no faster: profiles/r02_tuning.txt.)
 template <int FMT, bool TP>
 __global__ void __launch_bounds__(kRunMaxWarps * 32, 1)
 run_sweep_kernel(const __grid_constant__ SweepParams P) {
   using G = RunGeom<FMT>;
   constexpr uint32_t SF = G::kSF, FB = G::kFB, WPF = FB / 4u;
   constexpr uint32_t kPairsPerStageRun = SF / kPairFrames;
+  static_assert(kPairsPerStageRun <= 2u, "a lane keeps the survivors of at most two pairs per stage");
   extern __shared__ __align__(128) unsigned char smem_all[];
-  __shared__ uint32_t s_ticket;
+  __shared__ uint32_t s_ticket, s_qticket, s_done;
   const uint32_t lane = pin(threadIdx.x & 31u);
   const uint32_t sm_base = (uint32_t) __cvta_generic_to_shared(smem_all) + (threadIdx.x >> 5) * G::kWarpBytes;
   const uint32_t bar0 = sm_base + kRunRing * G::kSlotBytes;
-  if (threadIdx.x == 0) s_ticket = 0u;
+  if (threadIdx.x == 0) { s_ticket = 0u; s_qticket = 0u; s_done = 0u; }
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < kRunRing; ++i) mbar_init(bar0 + 8u * i, 1u);
@@ -179,6 +186,9 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
 #endif
   const uint32_t xi_iters = (uint32_t) P.xi_iters;
   const float thr_scale = 0.999f / (P.tp_bound * P.peak_scale);   // peak cell (raw units) -> |x| threshold
+  // this CTA's dense stretch of the candidate queue (64-bit entries, see tp_eval_run_kernel)
+  unsigned long long* const qcta =
+      reinterpret_cast<unsigned long long*>(P.run_queue) + (size_t) blockIdx.x * P.run_cta_cap;
 
   // this CTA's items: blockIdx.x + k * gridDim.x, k drawn from the CTA's ticket
   uint32_t item = 0;
@@ -242,9 +252,10 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
     cp_async_commit();
     float2 thr = bc2(0.0f);
     uint32_t seen_x = 0, seen_y = 0;               // what this warp last published
-    // this lane's own stretch of the candidate queue, and how much of it is filled
-    uint32_t* const qlane = P.run_queue + ((size_t) item * 32u + lane) * P.run_lane_stride;
-    uint32_t* qp = qlane;
+    // the survivors of the stage being worked on: up to two pairs x two channels per lane
+    // (channel | pair | code of the bound; turned into queue entries when they are stored)
+    uint32_t cand[4];
+    uint32_t cmask = 0;
     if (!active) thr = make_float2(3.0e38f, 3.0e38f);          // lanes past the track's end queue nothing
     // (until the first refresh, at the end of the first stage, every pair of an active lane is queued)
 
@@ -288,20 +299,21 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
 #ifndef LG_RUN_NOCOMP       // (ablation: staging only)
       // sample peak + true-peak screening of one pair: a pair (and the history
       // before it) that cannot beat the channel's peak is done
-      auto screen = [&](const float2 pm, const uint32_t pair) {
+      auto screen = [&](const float2 pm, const uint32_t pair, const uint32_t which /* pair of the stage */) {
         sp.x = fmaxf(sp.x, pm.x);
         sp.y = fmaxf(sp.y, pm.y);
         if (TP) {
-          // no vote, no branch: a predicated store and a predicated bump of the lane's cursor
           const float cx = fmaxf(pm.x, prev_pm.x), cy = fmaxf(pm.y, prev_pm.y);
           prev_pm = pm;
           const uint32_t ex = (pair << 16) | peak_code(cx), ey = 0x80000000u | (pair << 16) | peak_code(cy);
           const bool hx = cx > thr.x, hy = cy > thr.y;
-#ifndef LG_RUN_NOSTORE      // (ablation: screening without the queue)
-          if (hx) *qp = ex;
-          if (hy) qp[hx ? 1 : 0] = ey;
-#endif
-          qp += (hx ? 1 : 0) + (hy ? 1 : 0);
+          if (which == 0u) {
+            cand[0] = ex; cand[1] = ey;
+            cmask |= (hx ? 1u : 0u) | (hy ? 2u : 0u);
+          } else {
+            cand[2] = ex; cand[3] = ey;
+            cmask |= (hx ? 4u : 0u) | (hy ? 8u : 0u);
+          }
         }
       };
       const uint32_t pair0 = s * kPairsPerStageRun;
@@ -359,7 +371,7 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
           }
         }
 #pragma unroll
-        for (uint32_t pr = 0; pr < kPairsPerStageRun; ++pr) screen(pms[pr], pair0 + pr);
+        for (uint32_t pr = 0; pr < kPairsPerStageRun; ++pr) screen(pms[pr], pair0 + pr, pr);
         if (nb == fe) close_chunk();
       } else {
         // ---- a chunk (or the mode sums, or the run) ends inside the stage: one
@@ -396,10 +408,34 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
           if (xi_on) mode_accumulate2(c.yr, c.yi, P, sr, si);
           if (nb == g0 + kIter) close_chunk();
           // screening works on pairs: fold the first iteration's maxima into the second's
-          if (it2 & 1u) screen(make_float2(fmaxf(pm.x, half_pm.x), fmaxf(pm.y, half_pm.y)), iter >> 1);
-          else if (iter + 1u >= niters) screen(pm, iter >> 1);
+          if (it2 & 1u) screen(make_float2(fmaxf(pm.x, half_pm.x), fmaxf(pm.y, half_pm.y)), iter >> 1, it2 >> 1);
+          else if (iter + 1u >= niters) screen(pm, iter >> 1, it2 >> 1);
           else half_pm = pm;
         }
+      }
+      if (TP) {
+        // ---- the stage's survivors -> the CTA's dense queue: one reservation per warp
+        const uint32_t mine = __popc(cmask);
+        const uint32_t total = __reduce_add_sync(0xffffffffu, mine);
+        if (total) {                                   // warp-uniform
+          uint32_t incl = mine;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t) o) incl += v;
+          }
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(&s_qticket, total);
+          base = __shfl_sync(0xffffffffu, base, 0);
+#ifndef LG_RUN_NOSTORE      // (ablation: screening without the queue)
+          unsigned long long* out = qcta + base + (incl - mine);
+          const uint32_t slot_id = item * 32u + lane;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (cmask & (1u << k)) *out++ = ((unsigned long long) cand[k] << 32) | slot_id;
+#endif
+        }
+        cmask = 0;
       }
 #endif
 #ifndef LG_RUN_NOFLOOR        // (ablation: thresholds from the item's start only)
@@ -433,12 +469,16 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
         atomicMax(cell + 2, uy);
       }
     }
-    if (TP) P.run_counts[(size_t) item * 32u + lane] = (uint32_t) (qp - qlane);
     cp_async_wait<0>();                // no cell fetch of this item's track may land in the next item's buffer
     __syncwarp();                      // every lane is done with the ring before the next item refills it
     uint32_t next = 0;
     if (lane == 0) next = atomicAdd(&s_ticket, 1u);
     item = blockIdx.x + __shfl_sync(0xffffffffu, next, 0) * gridDim.x;
+  }
+  if (TP && lane == 0) {
+    // the warp that leaves last tells the evaluation how much this CTA queued
+    __threadfence_block();
+    if (atomicAdd(&s_done, 1u) == (blockDim.x >> 5) - 1u) P.run_counts[blockIdx.x] = atomicAdd(&s_qticket, 0u);
   }
 }
 
@@ -477,107 +517,67 @@ cudaError_t launch_sweep_run(const SweepParams& p, uint32_t format, int tpf, uin
 
 // -------------------------------------------------------------- true peak
 //
-// The candidates the sweep left behind: sweep lane (item, l) queued
-// run_counts[item * 32 + l] entries at run_queue + (item * 32 + l) *
-// run_lane_stride.  tp_filter_run_kernel drops every candidate whose bound does
-// not exceed the channel's FINAL sample peak (so what is evaluated does not
-// depend on how far the peak cells had got when the sweep tested the pair) and
-// packs the rest into one dense queue -- counted first, written second, one
-// reservation per warp; tp_eval_run_kernel evaluates the polyphase FIR on that
-// queue, one candidate per thread, grid-stride: candidates cluster in the loud
-// passages, the dense queue spreads them over the whole GPU.
+// The candidates the sweep left behind: sweep CTA b queued run_counts[b] entries
+// (64 bits each: channel | pair | code, item * 32 + lane) at run_queue + b * run_cta_cap.
+// tp_eval_run_kernel lays the CTAs'
+// stretches end to end (a prefix over at most 148 counts, in shared memory) and
+// deals the candidates out over the whole GPU, one per thread, grid-stride:
+// candidates cluster in the loud passages, so evaluating them where they were
+// found would leave most SMs idle behind a few busy warps.  A candidate whose
+// bound does not exceed the channel's FINAL sample peak is dropped before its
+// window is fetched.
 constexpr int kTpRunThreads = 128;
-
-// Dense queue entry (16 bytes): .x/.y = address of the first frame of the
-// candidate's window (NT frames of history + the pair; 16-byte aligned, bit 0
-// carries the channel), .z = the channel's peak cell, .w = kTpInterior.  A window
-// that touches the track's ends (or its lead-in) carries (item, lane) in .x and
-// (channel, pair) in .w instead and is located again by the evaluation.
-constexpr uint32_t kTpInterior = 0xffffffffu;
-// One CTA of 8 warps per item; warp w reads the stretches of sweep lanes 4w ... 4w + 3,
-// 32 consecutive entries per load (coalesced), so the whole item is in flight at once.
-constexpr int kTpFilterThreads = 256;
-
-template <int FMT, int TPF>
-__global__ void __launch_bounds__(kTpFilterThreads)
-tp_filter_run_kernel(const __grid_constant__ SweepParams P) {
-  constexpr int NT = TpTraits<TPF>::kTaps;
-  __shared__ uint32_t s_warp[kTpFilterThreads / 32 + 1];
-  const uint32_t lane = threadIdx.x & 31u, wic = threadIdx.x >> 5;
-  for (uint32_t item = blockIdx.x; item < P.nitems; item += gridDim.x) {
-    const RunItem it = P.items[item];
-    const Track& tr = P.tracks[it.track];
-    const uint32_t cell0 = (uint32_t) tr.peak_base;
-    const uint32_t* cell = P.peaks + 2 * (size_t) cell0;
-    const float f0 = __uint_as_float(__ldcg(cell)), f1 = __uint_as_float(__ldcg(cell + 2));
-    const long long frames = (long long) tr.frames, lead_in = (long long) tr.lead_in;
-    const unsigned char* pcm = reinterpret_cast<const unsigned char*>(tr.pcm);
-    auto pass = [&](uint32_t e) {
-      return P.tp_bound * (peak_code_value(e & 0xffffu) * P.peak_scale) > ((e >> 31) ? f1 : f0);
-    };
-    // ---- count
-    uint32_t cnt[4], mine = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) cnt[k] = __ldcg(P.run_counts + item * 32u + 4u * wic + k);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t* q = P.run_queue + ((size_t) item * 32u + 4u * wic + k) * P.run_lane_stride;
-      for (uint32_t i = lane; i < cnt[k]; i += 32u) mine += pass(__ldg(q + i)) ? 1u : 0u;
-    }
-    uint32_t incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= (uint32_t) o) incl += v;
-    }
-    __syncthreads();                       // s_warp is free again
-    if (lane == 31) s_warp[wic] = incl;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t total = 0;
-      for (int w = 0; w < kTpFilterThreads / 32; ++w) { const uint32_t c = s_warp[w]; s_warp[w] = total; total += c; }
-      s_warp[kTpFilterThreads / 32] = total ? atomicAdd(P.tp_ticket, total) : 0u;
-    }
-    __syncthreads();
-    // ---- write: this thread's survivors go to base + (warps before) + (lanes before), in the
-    // order it met them
-    uint4* out = reinterpret_cast<uint4*>(P.tp_dense) + s_warp[kTpFilterThreads / 32] + s_warp[wic] + (incl - mine);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t sl = item * 32u + 4u * wic + k;
-      const uint32_t* q = P.run_queue + (size_t) sl * P.run_lane_stride;
-      const long long a = (long long) (it.first_run + 4u * wic + k) * P.Lr - P.Wp;   // track frame of the lane's frame 0
-      for (uint32_t i = lane; i < cnt[k]; i += 32u) {
-        const uint32_t e = __ldg(q + i);
-        if (!pass(e)) continue;
-        const uint32_t ch = e >> 31, pair = (e >> 16) & 0x7fffu;
-        const long long t0 = a + (long long) pair * kPairFrames;
-        if (t0 >= NT && t0 + kPairFrames <= frames && t0 >= lead_in) {
-          const unsigned long long p = (unsigned long long) (pcm + (t0 - NT) * (long long) P.fb) | ch;
-          *out++ = make_uint4((uint32_t) p, (uint32_t) (p >> 32), cell0 + ch, kTpInterior);
-        } else {
-          *out++ = make_uint4(sl, 0u, cell0 + ch, (ch << 15) | pair);
-        }
-      }
-    }
-  }
-}
+constexpr uint32_t kTpMaxCtas = 1024;      // sweep CTAs (one per SM) the prefix has room for
 
 template <int FMT, int TPF>
 __global__ void __launch_bounds__(kTpRunThreads, 4)
-tp_eval_run_kernel(const __grid_constant__ SweepParams P) {
+tp_eval_run_kernel(const __grid_constant__ SweepParams P, const uint32_t nctas) {
   constexpr int NT = TpTraits<TPF>::kTaps;
   constexpr int NW = NT + kPairFrames;
-  const uint32_t count = __ldcg(P.tp_ticket);
+  __shared__ uint32_t s_off[kTpMaxCtas + 1];
+  // exclusive prefix of the CTAs' counts (nctas <= 148 in practice: one warp does it)
+  if (threadIdx.x < 32u) {
+    uint32_t run = 0;
+    for (uint32_t c0 = 0; c0 < nctas; c0 += 32u) {
+      const uint32_t c = c0 + threadIdx.x;
+      const uint32_t v = c < nctas ? __ldcg(P.run_counts + c) : 0u;
+      uint32_t incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (threadIdx.x >= (uint32_t) o) incl += u;
+      }
+      if (c < nctas) s_off[c] = run + incl - v;
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (threadIdx.x == 0) s_off[nctas] = run;
+  }
+  __syncthreads();
+  const uint32_t count = s_off[nctas];
+  const unsigned long long* queue = reinterpret_cast<const unsigned long long*>(P.run_queue);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-    const uint4 e = __ldcs(reinterpret_cast<const uint4*>(P.tp_dense) + i);
-    uint32_t* cell = P.peaks + 2 * (size_t) e.z + 1;
+    uint32_t lo = 0, hi = nctas;                    // the stretch that holds entry i
+    while (hi - lo > 1u) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (s_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    const unsigned long long e = __ldcs(queue + (size_t) lo * P.run_cta_cap + (i - s_off[lo]));
+    const uint32_t slot = (uint32_t) e, w = (uint32_t) (e >> 32);
+    const uint32_t ch = w >> 31, pair = (w >> 16) & 0x7fffu;
+    const RunItem it = P.items[slot >> 5];
+    const Track& tr = P.tracks[it.track];
+    uint32_t* cell = P.peaks + 2 * ((size_t) tr.peak_base + ch);
+    // the bound against the channel's final sample peak
+    if (!(P.tp_bound * (peak_code_value(w & 0xffffu) * P.peak_scale) > __uint_as_float(__ldcg(cell)))) continue;
+    ++cell;                                          // the true-peak cell
+    const long long frames = (long long) tr.frames;
+    const long long t0 = (long long) (it.first_run + (slot & 31u)) * P.Lr - P.Wp + (long long) pair * kPairFrames;
+    const unsigned char* pcm = reinterpret_cast<const unsigned char*>(tr.pcm);
     float win[NW];
     float m = 0.0f;
-    if (e.w == kTpInterior) {
-      const uint32_t ch = e.x & 1u;
-      const unsigned char* q = reinterpret_cast<const unsigned char*>(
-          ((unsigned long long) e.y << 32) | (unsigned long long) (e.x & ~15u));
+    if (t0 >= NT && t0 + kPairFrames <= frames && t0 >= (long long) tr.lead_in) {
+      // the window (NT frames of history + the pair) lies inside the track: 16-byte loads
+      const unsigned char* q = pcm + (t0 - NT) * (long long) P.fb;
       if (FMT == FMT_S16) {
         const uint32_t sel = ch ? 0xBB32u : 0x9910u;
 #pragma unroll
@@ -599,14 +599,8 @@ tp_eval_run_kernel(const __grid_constant__ SweepParams P) {
 #pragma unroll
       for (int k = 0; k < kPairFrames; ++k) m = fmaxf(m, tp_frame<TPF>(win, NT + k));
     } else {
-      // a window at the track's ends or across the lead-in: located through the item
-      const uint32_t slot = e.x, ch = e.w >> 15, pair = e.w & 0x7fffu;
-      const RunItem it = P.items[slot >> 5];
-      const Track& tr = P.tracks[it.track];
-      const long long frames = (long long) tr.frames;
-      const long long t0 = (long long) (it.first_run + (slot & 31u)) * P.Lr - P.Wp + (long long) pair * kPairFrames;
+      // a window at the track's ends or across the lead-in
       if (t0 >= frames || t0 + kPairFrames <= (long long) tr.lead_in) continue;
-      const unsigned char* pcm = reinterpret_cast<const unsigned char*>(tr.pcm);
 #pragma unroll
       for (int k = 0; k < NW; ++k) {
         const long long t = t0 - NT + k;
@@ -630,18 +624,31 @@ tp_eval_run_kernel(const __grid_constant__ SweepParams P) {
 
 template <int FMT, int TPF>
 static cudaError_t launch_tp_run_t(const SweepParams& p, uint32_t sms, cudaStream_t stream, cudaEvent_t hold) {
+  // Resident CTAs per SM of the evaluation, capped at 6 (48 K of the 64 K registers): its
+  // CTAs stay for the whole kernel, and the small post-processing kernels that run next to
+  // it must always find room on an SM.
   static int per_sm = 0;
   if (!per_sm) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tp_eval_run_kernel<FMT, TPF>, kTpRunThreads, 0) !=
             cudaSuccess || per_sm < 1)
       per_sm = 4;
+    int cap = 6;
+    if (const char* e = getenv("LOUDGAIN_B200_TPEVAL_CTAS")) cap = atoi(e) > 0 ? atoi(e) : cap;   // tuning
+    if (per_sm > cap) per_sm = cap;
   }
-  const uint32_t fblocks = p.nitems < sms * 8u ? p.nitems : sms * 8u;          // one CTA per item at a time
-  tp_filter_run_kernel<FMT, TPF><<<fblocks, kTpFilterThreads, 0, stream>>>(p);
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess && hold) e = cudaStreamWaitEvent(stream, hold, 0);
-  if (e != cudaSuccess) return e;
-  tp_eval_run_kernel<FMT, TPF><<<sms * per_sm, kTpRunThreads, 0, stream>>>(p);
+  // `hold`: the evaluation floods the memory system with gathers; started right behind the
+  // sweep it slows the FP64 fix-up next to it down by more than it gains (tuning log)
+  static const bool use_hold = [] {
+    const char* e = getenv("LOUDGAIN_B200_TP_HOLD");      // tuning: 0 = start behind the sweep
+    return e ? atoi(e) != 0 : true;
+  }();
+  if (hold && use_hold) {
+    const cudaError_t e = cudaStreamWaitEvent(stream, hold, 0);
+    if (e != cudaSuccess) return e;
+  }
+  const uint32_t nctas = sms < p.nitems ? sms : p.nitems;       // the sweep's grid (launch_run_k)
+  if (nctas > kTpMaxCtas) return cudaErrorInvalidValue;
+  tp_eval_run_kernel<FMT, TPF><<<sms * per_sm, kTpRunThreads, 0, stream>>>(p, nctas);
   return cudaGetLastError();
 }
 

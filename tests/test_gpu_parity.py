@@ -415,3 +415,46 @@ def test_album_exchange_single_rank(product):
         b.close()
         x.close()
     torch.cuda.synchronize()
+
+
+def _oracle_parallel(oracle, tracks):
+    """The oracle on full-size tracks, one thread per track (ctypes drops the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(t):
+        st = oracle.init(t[0].shape[1], t[1])
+        st.add_frames(t[0], 1024)
+        return st
+
+    with ThreadPoolExecutor(min(len(tracks), 12)) as ex:
+        return list(ex.map(one, tracks))
+
+
+def test_config1_full_size(product, oracle):
+    """cfg1 at BASELINE.json's size: the 3-minute 44.1 kHz stereo S16 track, 1024-frame calls."""
+    spec = synth.config1_spec(180.0)
+    pcm = synth.programme_s16(spec, device="cuda").cpu().numpy()
+    (st,) = _oracle_parallel(oracle, [(pcm, spec.rate)])
+    o = {"loudness": st.loudness_global(), "range": st.loudness_range(),
+         "sample_peak": np.array(st.sample_peaks()), "true_peak": np.array(st.true_peaks())}
+    st.destroy()
+    g = _drive(product, [(pcm, spec.rate)], None, 1024)
+    _check(o, g["tracks"][0])
+
+
+def test_config2_full_size(product, oracle):
+    """cfg2 at BASELINE.json's size: the whole 12-track album (247.6 M samples), per-track and
+    album results, gains at tag precision, clipping prevention inputs (true peaks)."""
+    specs = synth.config2_specs(12)
+    tracks = [(synth.programme_s16(s, device="cuda").cpu().numpy(), s.rate) for s in specs]
+    sts = _oracle_parallel(oracle, tracks)
+    o_tracks = [{"loudness": st.loudness_global(), "range": st.loudness_range(),
+                 "sample_peak": np.array(st.sample_peaks()), "true_peak": np.array(st.true_peaks())}
+                for st in sts]
+    o_album = {"loudness": oracle.loudness_global_multiple(sts), "range": oracle.loudness_range_multiple(sts)}
+    for st in sts:
+        st.destroy()
+    g = _drive(product, tracks, [0] * len(tracks), 1024)
+    for ot, gt in zip(o_tracks, g["tracks"]):
+        _check(ot, gt)
+    _check(o_album, g["albums"][0])
