@@ -5,8 +5,10 @@ loudgain_b200.build from loudgain_b200/csrc.  This package only loads it and
 mirrors the reference scanner's host-side interface:
 
   capi      ctypes binding of include/ebur128.h (what scan.c calls)
-  engine    batch API over HBM-resident PCM (include/ebur128_b200.h)
-  scan      scan.c-shaped host driver (scan_init / scan_file / results)
+  engine    batch API over HBM-resident PCM (include/ebur128_b200.h): Batch, the
+            multi-GPU album exchange and time sharding, and scan_host, the binding of
+            the library's scan.c-shaped driver (lgb_scan_host_mt in csrc/lg_scan.cu)
+  wavio     WAV / RIFF reader with swr-style narrowing to 16 bit
   synth     synthetic PCM for the BASELINE.json configs
 
 There is no CPU measurement path in this package; loading fails loudly if the

@@ -157,7 +157,7 @@ struct lgb_batch {
   // post-processing kernels go to a high-priority side stream and slip in next
   // to the true-peak pass on the main stream; joined before the result copy.
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_post = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_post = nullptr, ev_fix = nullptr;
   // Sweep launch groups after the first go round-robin to these streams, so
   // that the CTAs of the next group fill the SMs while the previous group's
   // last work items run out (the groups touch disjoint tracks).
@@ -174,6 +174,7 @@ struct lgb_batch {
   // album queries answered together with other ranks (lgb_batch_attach_exchange)
   lgb_exchange* xchg = nullptr;
   uint32_t* d_xstoff = nullptr;
+  uint32_t xst_smem = 0;             // short-term energies the exchange's range CTA stages in shared memory
   cudaStream_t qstream = nullptr;    // the track queries run next to the exchange's three launches
   cudaEvent_t ev_q0 = nullptr, ev_q1 = nullptr;
   // LOUDGAIN_B200_STEP_TRACE (tuning): direct launches with a timing event behind every
@@ -422,6 +423,7 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
         cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_post, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_fix, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_blocks, cudaEventDisableTiming) != cudaSuccess) {
       cudaGetLastError();
       if (b->side) { cudaStreamDestroy(b->side); b->side = nullptr; }
@@ -533,7 +535,7 @@ static int enqueue_step(lgb_batch* b, int parity) {
   cudaStream_t ps = fork ? b->side : b->stream;
   PostSizes z{(uint32_t) p.tracks.size(), p.total_recs, p.total_slots, p.total_blocks, p.total_st};
   auto post_kernels = [&]() -> int {
-    e = launch_post(t, z, ps);
+    e = launch_post(t, z, ps, fork ? b->ev_fix : nullptr);
     if (e != cudaSuccess) { set_error("launch_post", e); return 1; }
     mark("fixslot+block", ps);
     if (fork) {
@@ -571,10 +573,18 @@ static int enqueue_step(lgb_batch* b, int parity) {
       sp.run_counts = b->d_runcnt + (size_t) g.first_item * 32u;
       sp.run_queue = b->d_runq + 2 * g.queue_base;
     }
-    cudaEvent_t hold = fork ? b->ev_post : nullptr;
+    // what the true-peak evaluation waits for (tuning, LOUDGAIN_B200_TP_HOLD): 0 nothing,
+    // 1 the block kernel, 2 the fix-up kernel -- the evaluation's gathers slow the FP64 fix-up
+    // down when the two run side by side
+    static const int hold_mode = [] {
+      const char* e = getenv("LOUDGAIN_B200_TP_HOLD");
+      return e ? atoi(e) : 0;
+    }();
+    cudaEvent_t hold = !fork ? nullptr : hold_mode == 1 ? b->ev_post : hold_mode == 2 ? b->ev_fix : nullptr;
+    cudaEvent_t hold_old = fork ? b->ev_post : nullptr;     // the round-1 kernels keep their arrangement
     e = g.run ? launch_truepeak_run(sp, g.format, g.tpf, b->sms, b->stream, hold)
-        : sp.packed ? launch_truepeak_pair(sp, g.format, g.tpf, b->sms, b->stream, hold)
-                    : launch_truepeak(sp, g.format, g.tpf, b->sms, b->stream, hold);
+        : sp.packed ? launch_truepeak_pair(sp, g.format, g.tpf, b->sms, b->stream, hold_old)
+                    : launch_truepeak(sp, g.format, g.tpf, b->sms, b->stream, hold_old);
     if (e != cudaSuccess) { set_error("launch_truepeak", e); return 1; }
   }
   mark("true-peak pass", b->stream);
@@ -599,7 +609,7 @@ static int enqueue_step(lgb_batch* b, int parity) {
     if (e == cudaSuccess) e = cudaEventRecord(b->ev_q1, b->qstream);
     if (e == cudaSuccess) e = launch_exchange_publish(t.lists, t.queries, t.members, b->abs_gate, xp, ps);
     if (e == cudaSuccess)
-      e = launch_exchange_finish(t.lists, t.queries, t.members, b->abs_gate, t.results, xp, ps);
+      e = launch_exchange_finish(t.lists, t.queries, t.members, b->abs_gate, t.results, xp, b->xst_smem, ps);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ps, b->ev_q1, 0);
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(x->h_ctl, x->d_ctl + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ps);
@@ -1000,6 +1010,14 @@ extern "C" LG_EXPORT int lgb_batch_attach_exchange(lgb_batch* b, lgb_exchange* x
     off[a + 1] = off[a] + n;
   }
   if (off[p.nalbums] > x->st_cap) { set_error("lgb_batch_attach_exchange: st_capacity is too small"); return 1; }
+  {
+    // room for the union of an album's short-term energies: the largest local album, as
+    // much again on every other rank and half of that on top; 26 000 doubles at most
+    uint32_t largest = 0;
+    for (uint32_t a = 0; a < p.nalbums; ++a) largest = std::max(largest, off[a + 1] - off[a]);
+    const uint64_t want = (uint64_t) largest * x->world * 3u / 2u + 64u;
+    b->xst_smem = (uint32_t) std::min<uint64_t>(want, 26000u);
+  }
   if (cudaStreamSynchronize(b->stream) != cudaSuccess) { set_error("lgb_batch_attach_exchange: stream error"); return 1; }
   if (b->d_xstoff) cudaFreeAsync(b->d_xstoff, b->stream);
   if (!upload(off, &b->d_xstoff, b->stream) || cudaStreamSynchronize(b->stream) != cudaSuccess) return 1;
@@ -1037,6 +1055,7 @@ extern "C" LG_EXPORT void lgb_batch_destroy(lgb_batch* b) {
   if (b->ev_fork) cudaEventDestroy(b->ev_fork);
   if (b->ev_join) cudaEventDestroy(b->ev_join);
   if (b->ev_post) cudaEventDestroy(b->ev_post);
+  if (b->ev_fix) cudaEventDestroy(b->ev_fix);
   if (b->ev_blocks) cudaEventDestroy(b->ev_blocks);
   if (b->side) cudaStreamDestroy(b->side);
   if (b->ev_q0) cudaEventDestroy(b->ev_q0);

@@ -693,8 +693,9 @@ const double* hist_table() {
 constexpr int kQueryThreads = 1024;     // the most a query CTA may have (select_two needs 256 or more)
 // What the query kernels are launched with.  A 1024-thread CTA needs a whole SM's register
 // file (64 per thread), so it waits for any SM that still holds CTAs of the true-peak
-// evaluation; smaller CTAs slip in next to them but have fewer loads in flight.
-constexpr int kQueryLaunchDefault = 1024;
+// evaluation; smaller CTAs slip in next to them but have fewer loads in flight.  512 was
+// the best of 256 / 512 / 1024 on the album step (profiles/r02_tuning.txt E).
+constexpr int kQueryLaunchDefault = 512;
 static int query_launch_threads() {
   static const int n = [] {
     const char* e = getenv("LOUDGAIN_B200_QUERY_THREADS");      // tuning: 256, 512 or 1024
@@ -1018,10 +1019,10 @@ query_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ quer
 //   xchg_publish_kernel   sums behind the absolute gate (gating and short-term
 //                         blocks) + the rank's short-term energies -> all peers
 //   xchg_gate_kernel      waits for phase 0 of every rank; relative threshold
-//                         from the rank-ordered totals; sums behind it -> all peers
-//   xchg_finish_kernel    waits for phase 1; loudness from the totals; range by
-//                         rank selection over the union of the short-term
-//                         energies every rank received
+//                         from the rank-ordered totals; sums behind it -> all peers.
+//                         A second CTA per album selects the range percentiles over
+//                         the union of the short-term energies every rank received
+//   xchg_finish_kernel    waits for phase 1; loudness from the totals
 // Totals are added in rank order on every rank: all ranks get the same bits.
 // The short-term lists are one value per second of audio, a tenth of the gating
 // blocks, which never leave their GPU.
@@ -1079,12 +1080,12 @@ __device__ __forceinline__ unsigned long long* xchg_flag(const XchgParams& X, ui
 
 // Every thread has fenced its own peer stores; the CTA that finishes last tells
 // every rank that this rank's `phase` of `step` is complete.
-__device__ void xchg_signal(const XchgParams& X, uint32_t phase, unsigned long long step) {
+__device__ void xchg_signal(const XchgParams& X, uint32_t phase, unsigned long long step, uint32_t nctas) {
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned long long done = atomicAdd(X.ctl + 1 + phase, 1ull);
-    if (done == gridDim.x - 1) {
+    if (done == nctas - 1) {
       X.ctl[1 + phase] = 0ull;
       __threadfence_system();
       for (uint32_t p = 0; p < X.world; ++p) st_release_sys(xchg_flag(X, p, phase, X.rank), step);
@@ -1137,7 +1138,7 @@ xchg_publish_kernel(const BlockList* __restrict__ lists, const Query* __restrict
       h->st_off = off; h->st_cnt = cnt;
     }
   }
-  xchg_signal(X, 0, step);
+  xchg_signal(X, 0, step, gridDim.x);
 }
 
 struct XchgTotals {
@@ -1157,51 +1158,50 @@ __device__ XchgTotals xchg_totals(const XchgParams& X, uint32_t parity, uint32_t
   return t;
 }
 
+// Two CTAs per album.  Role 0 gates the rank's own blocks against the relative threshold
+// of the totals and publishes (sum, count).  Role 1 needs nothing of that: the range only
+// depends on what phase 0 brought (every rank's short-term energies and their sums), so it
+// is selected next to the gating instead of behind it.  The union of the short-term
+// energies is staged in (dynamic) shared memory when it fits.
 __global__ void __launch_bounds__(kQueryThreads)
 xchg_gate_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ queries,
-                 const uint32_t* __restrict__ members, double abs_gate, const __grid_constant__ XchgParams X) {
-  __shared__ SumCount scratch[32];
-  __shared__ ViewSmem vs;
-  __shared__ XchgTotals tot;
-  const uint32_t a = blockIdx.x;
-  const unsigned long long step = __ldcg(X.ctl);
-  const uint32_t parity = (uint32_t) (step & 1ull);
-  QueryView v;
-  load_view(v, vs, lists, members, queries[X.first_query + a]);
-  xchg_wait(X, 0, step);
-  if (threadIdx.x == 0) tot = xchg_totals(X, parity, a);
-  __syncthreads();
-  double s = 0.0;
-  unsigned long long n = 0;
-  if (tot.n1) {
-    const double thr = tot.s1 / (double) tot.n1 * 0.1;
-    for_each_energy<false>(v, [&](double e, uint32_t) { if (e >= abs_gate && e >= thr) { s += e; ++n; } });
-  }
-  const SumCount b = block_sum_count(s, n, scratch);
-  if (threadIdx.x == 0) {
-    for (uint32_t p = 0; p < X.world; ++p) {
-      XchgHdr* h = xchg_hdr(X, p, parity, X.rank, a);
-      h->s2 = b.s; h->n2 = b.n;
-    }
-  }
-  xchg_signal(X, 1, step);
-}
-
-__global__ void __launch_bounds__(kQueryThreads)
-xchg_finish_kernel(double abs_gate, QueryResult* __restrict__ results, const __grid_constant__ XchgParams X) {
+                 const uint32_t* __restrict__ members, double abs_gate, QueryResult* __restrict__ results,
+                 uint32_t st_smem_cap, const __grid_constant__ XchgParams X) {
+  extern __shared__ double s_stx[];
   __shared__ SumCount scratch[32];
   __shared__ ViewSmem vs;
   __shared__ XchgTotals tot;
   __shared__ unsigned int hist[512];
   __shared__ unsigned int wsum[16];
   __shared__ SelectState sel;
-  const uint32_t a = blockIdx.x;
+  const uint32_t a = blockIdx.x >> 1, role = blockIdx.x & 1u;
   const unsigned long long step = __ldcg(X.ctl);
   const uint32_t parity = (uint32_t) (step & 1ull);
-  xchg_wait(X, 1, step);
+  QueryView v;
+  if (role == 0) load_view(v, vs, lists, members, queries[X.first_query + a]);
+  xchg_wait(X, 0, step);
+  if (role == 0) {
+    if (threadIdx.x == 0) tot = xchg_totals(X, parity, a);
+    __syncthreads();
+    double s = 0.0;
+    unsigned long long n = 0;
+    if (tot.n1) {
+      const double thr = tot.s1 / (double) tot.n1 * 0.1;
+      for_each_energy<false>(v, [&](double e, uint32_t) { if (e >= abs_gate && e >= thr) { s += e; ++n; } });
+    }
+    const SumCount b = block_sum_count(s, n, scratch);
+    if (threadIdx.x == 0) {
+      for (uint32_t p = 0; p < X.world; ++p) {
+        XchgHdr* h = xchg_hdr(X, p, parity, X.rank, a);
+        h->s2 = b.s; h->n2 = b.n;
+      }
+    }
+    xchg_signal(X, 1, step, X.nalbums);
+    return;
+  }
+  // ---- role 1: loudness range over the union of the short-term energies
   if (threadIdx.x == 0) {
     tot = xchg_totals(X, parity, a);
-    // the union of the short-term energies: one list per rank, in this rank's own region
     uint32_t ast = 0;
     for (uint32_t r = 0; r < X.world; ++r) {
       const XchgHdr* h = xchg_hdr(X, X.rank, parity, r, a);
@@ -1213,33 +1213,50 @@ xchg_finish_kernel(double abs_gate, QueryResult* __restrict__ results, const __g
     vs.zoff[X.world] = 0; vs.stoff[X.world] = ast;
   }
   __syncthreads();
-  QueryView v;
   v.lists = nullptr; v.mem = nullptr; v.count = X.world; v.cached = true;
   v.s_lists = vs.lists; v.s_zoff = vs.zoff; v.s_stoff = vs.stoff;
   v.first = threadIdx.x; v.stride = blockDim.x;
-  QueryResult res;
-  res.loudness = -HUGE_VAL; res.range = 0.0; res.rel_thr = 0.0;
-  res.sum1 = tot.s1; res.n1 = tot.n1; res.sum2 = tot.s2; res.n2 = tot.n2; res.nst = tot.nst;
-  if (tot.n1) {
-    res.rel_thr = tot.s1 / (double) tot.n1 * 0.1;
-    if (tot.n2) res.loudness = energy_to_lufs(tot.s2 / (double) tot.n2);
-  }
+  const uint32_t n_st = vs.stoff[X.world];
+  const bool st_cached = n_st <= st_smem_cap;
+  double range = 0.0;
   if (tot.nst) {
     double floor_e = tot.sst / (double) tot.nst * 0.01;
     if (floor_e < abs_gate) floor_e = abs_gate;
     unsigned long long n = 0;
-    for_each_energy<true>(v, [&](double e, uint32_t) { if (e >= floor_e) ++n; });
-    const SumCount c = block_sum_count(0.0, n, scratch);
+    for_each_energy<true>(v, [&](double e, uint32_t g) {
+      if (st_cached) s_stx[g] = e;
+      if (e >= floor_e) ++n;
+    });
+    const SumCount c = block_sum_count(0.0, n, scratch);      // (its barriers publish s_stx)
     if (c.n) {
       const unsigned long long k_hi = (unsigned long long) ((double) (c.n - 1) * 0.95 + 0.5);
       const unsigned long long k_lo = (unsigned long long) ((double) (c.n - 1) * 0.1 + 0.5);
       double lo, hi;
-      select_two(v, nullptr, 0u, false, floor_e, k_lo, k_hi, hist, wsum, &sel, &lo, &hi);
-      res.range = energy_to_lufs(hi) - energy_to_lufs(lo);
+      select_two(v, s_stx, n_st, st_cached, floor_e, k_lo, k_hi, hist, wsum, &sel, &lo, &hi);
+      range = energy_to_lufs(hi) - energy_to_lufs(lo);
     }
   }
   if (threadIdx.x == 0) {
-    results[X.first_query + a] = res;
+    results[X.first_query + a].range = range;
+    results[X.first_query + a].nst = tot.nst;
+  }
+}
+
+__global__ void __launch_bounds__(64)
+xchg_finish_kernel(QueryResult* __restrict__ results, const __grid_constant__ XchgParams X) {
+  const uint32_t a = blockIdx.x;
+  const unsigned long long step = __ldcg(X.ctl);
+  const uint32_t parity = (uint32_t) (step & 1ull);
+  xchg_wait(X, 1, step);
+  if (threadIdx.x == 0) {
+    const XchgTotals tot = xchg_totals(X, parity, a);
+    QueryResult& o = results[X.first_query + a];
+    o.loudness = -HUGE_VAL; o.rel_thr = 0.0;
+    o.sum1 = tot.s1; o.n1 = tot.n1; o.sum2 = tot.s2; o.n2 = tot.n2;
+    if (tot.n1) {
+      o.rel_thr = tot.s1 / (double) tot.n1 * 0.1;
+      if (tot.n2) o.loudness = energy_to_lufs(tot.s2 / (double) tot.n2);
+    }
     // the step is over on this rank once every album is done
     __threadfence();
     if (atomicAdd(X.ctl + 3, 1ull) == gridDim.x - 1) { X.ctl[3] = 0ull; X.ctl[0] = step + 1ull; }
@@ -1255,20 +1272,33 @@ cudaError_t launch_exchange_publish(const BlockList* lists, const Query* queries
 
 cudaError_t launch_exchange_finish(const BlockList* lists, const Query* queries, const uint32_t* members,
                                    double abs_gate, QueryResult* results, const XchgParams& x,
-                                   cudaStream_t stream) {
+                                   uint32_t st_smem_doubles, cudaStream_t stream) {
   if (!x.nalbums) return cudaSuccess;
-  xchg_gate_kernel<<<x.nalbums, query_launch_threads(), 0, stream>>>(lists, queries, members, abs_gate, x);
+  static size_t smem_limit = 0;
+  const size_t smem = (size_t) st_smem_doubles * sizeof(double);
+  if (smem > 48u * 1024u && smem > smem_limit) {
+    const cudaError_t e = cudaFuncSetAttribute(xchg_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int) smem);
+    if (e != cudaSuccess) return e;
+    smem_limit = smem;
+  }
+  xchg_gate_kernel<<<2 * x.nalbums, query_launch_threads(), smem, stream>>>(lists, queries, members, abs_gate,
+                                                                           results, st_smem_doubles, x);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  xchg_finish_kernel<<<x.nalbums, query_launch_threads(), 0, stream>>>(abs_gate, results, x);
+  xchg_finish_kernel<<<x.nalbums, 64, 0, stream>>>(results, x);
   return cudaGetLastError();
 }
 
-cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t stream) {
+cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t stream, cudaEvent_t fixed) {
   if (z.total_slots) {
     const unsigned blocks = (unsigned) ((z.total_slots + 127) / 128);
     fixslot_kernel<<<blocks, 128, 0, stream>>>(t.tracks, z.ntracks, t.coefs, t.recs, z.total_slots, t.eslot,
                                               t.xi_table);
+  }
+  if (fixed) {
+    const cudaError_t e = cudaEventRecord(fixed, stream);
+    if (e != cudaSuccess) return e;
   }
   if (z.total_blocks + z.total_st) {
     const unsigned blocks = (unsigned) ((z.total_blocks + z.total_st + 255) / 256);

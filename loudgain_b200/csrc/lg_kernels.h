@@ -52,7 +52,9 @@ cudaError_t launch_truepeak_pair(const SweepParams& p, uint32_t format, int tpf,
 cudaError_t launch_sweep_run(const SweepParams& p, uint32_t format, int tpf, uint32_t sms, cudaStream_t stream);
 cudaError_t launch_truepeak_run(const SweepParams& p, uint32_t format, int tpf, uint32_t sms,
                                 cudaStream_t stream, cudaEvent_t hold = nullptr);
-cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t stream);
+// `fixed` (optional): recorded behind the fix-up kernel, before the block kernel.
+cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t stream,
+                        cudaEvent_t fixed = nullptr);
 // 400 ms / 3 s blocks of one stream from its complete 100 ms slot list.
 // hist_tab: hist_table() for EBUR128_MODE_HISTOGRAM semantics, nullptr for exact energies.
 cudaError_t launch_stream_blocks(const double* eslot, int s100, uint64_t nblocks, uint64_t nst,
@@ -76,9 +78,10 @@ uint32_t query_cluster_size(uint64_t max_gating_blocks);
 // early as the block lists allow; whatever runs in between hides the peers' latency.
 cudaError_t launch_exchange_publish(const BlockList* lists, const Query* queries, const uint32_t* members,
                                     double abs_gate, const XchgParams& x, cudaStream_t stream);
+// st_smem_doubles: short-term energies the range CTA may stage in shared memory (0: none).
 cudaError_t launch_exchange_finish(const BlockList* lists, const Query* queries, const uint32_t* members,
                                    double abs_gate, QueryResult* results, const XchgParams& x,
-                                   cudaStream_t stream);
+                                   uint32_t st_smem_doubles, cudaStream_t stream);
 // Sample peak and true peak (float bits, raw sample units) of track frames
 // [first, first + count) per channel into out[2 * channels] (device memory).
 cudaError_t launch_range_peaks(const void* pcm, uint32_t format, uint32_t channels, uint64_t first,

@@ -638,11 +638,7 @@ static cudaError_t launch_tp_run_t(const SweepParams& p, uint32_t sms, cudaStrea
   }
   // `hold`: the evaluation floods the memory system with gathers; started right behind the
   // sweep it slows the FP64 fix-up next to it down by more than it gains (tuning log)
-  static const bool use_hold = [] {
-    const char* e = getenv("LOUDGAIN_B200_TP_HOLD");      // tuning: 0 = start behind the sweep
-    return e ? atoi(e) != 0 : true;
-  }();
-  if (hold && use_hold) {
+  if (hold) {
     const cudaError_t e = cudaStreamWaitEvent(stream, hold, 0);
     if (e != cudaSuccess) return e;
   }
