@@ -175,8 +175,10 @@ struct lgb_batch {
   lgb_exchange* xchg = nullptr;
   uint32_t* d_xstoff = nullptr;
   uint32_t xst_smem = 0;             // short-term energies the exchange's range CTA stages in shared memory
-  cudaStream_t qstream = nullptr;    // the track queries run next to the exchange's three launches
-  cudaEvent_t ev_q0 = nullptr, ev_q1 = nullptr;
+  uint32_t xcluster = 1;             // CTAs that share an album's local gating blocks in the exchange
+  cudaStream_t qstream = nullptr;    // second and third query stream: the halves of the queries (and, with an
+  cudaStream_t q2stream = nullptr;   // exchange, the albums' ranges) run next to each other
+  cudaEvent_t ev_q0 = nullptr, ev_q1 = nullptr, ev_q2 = nullptr;
   // LOUDGAIN_B200_STEP_TRACE (tuning): direct launches with a timing event behind every
   // stage of the step on the stream it runs on; the fetch prints them
   bool trace = false;
@@ -601,16 +603,30 @@ static int enqueue_step(lgb_batch* b, int parity) {
     for (uint32_t r = 0; r < x->world; ++r) xp.peer[r] = x->peer[r];
     xp.st_off = b->d_xstoff;
     xp.ctl = x->d_ctl;
+    // three chains side by side: publish -> gate -> finish | the tracks' ranges | the tracks'
+    // loudness, then the albums' ranges (which need the peers' publish phase only)
+    const uint32_t ntq = (uint32_t) p.tracks.size();
     e = cudaEventRecord(b->ev_q0, ps);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(b->qstream, b->ev_q0, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(b->q2stream, b->ev_q0, 0);
+    if (e == cudaSuccess) e = launch_exchange_publish(t.lists, t.queries, t.members, b->abs_gate, xp, b->xcluster, ps);
+    mark("x-publish", ps);
     if (e == cudaSuccess)
-      e = launch_queries(t.lists, t.queries, t.members, (uint32_t) p.tracks.size(), b->abs_gate, t.results,
-                         b->qstream, 1);
+      e = launch_queries(t.lists, t.queries, t.members, ntq, b->abs_gate, t.results, b->qstream, 1, 2);
+    mark("track ranges", b->qstream);
     if (e == cudaSuccess) e = cudaEventRecord(b->ev_q1, b->qstream);
-    if (e == cudaSuccess) e = launch_exchange_publish(t.lists, t.queries, t.members, b->abs_gate, xp, ps);
     if (e == cudaSuccess)
-      e = launch_exchange_finish(t.lists, t.queries, t.members, b->abs_gate, t.results, xp, b->xst_smem, ps);
+      e = launch_queries(t.lists, t.queries, t.members, ntq, b->abs_gate, t.results, b->q2stream, 1, 1);
+    mark("track loudness", b->q2stream);
+    if (e == cudaSuccess) e = launch_exchange_range(b->abs_gate, t.results, xp, b->xst_smem, b->q2stream);
+    mark("x-range", b->q2stream);
+    if (e == cudaSuccess) e = cudaEventRecord(b->ev_q2, b->q2stream);
+    if (e == cudaSuccess) e = launch_exchange_gate(t.lists, t.queries, t.members, b->abs_gate, xp, b->xcluster, ps);
+    mark("x-gate", ps);
+    if (e == cudaSuccess) e = launch_exchange_finish(t.results, xp, ps);
+    mark("x-finish", ps);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ps, b->ev_q1, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ps, b->ev_q2, 0);
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(x->h_ctl, x->d_ctl + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ps);
   } else if (b->qstream && !b->timing) {
@@ -704,7 +720,7 @@ extern "C" LG_EXPORT int lgb_batch_fetch(lgb_batch* b, lgb_result* track_results
   const QueryResult* h_results = reinterpret_cast<const QueryResult*>(b->h_out[parity]);
   const uint32_t* h_peaks = reinterpret_cast<const uint32_t*>(b->h_out[parity] + b->peaks_off);
   if (b->trace && b->marks.size() > 1 && b->runs > 3) {
-    fprintf(stderr, "[lgb step]");
+    fprintf(stderr, "[lgb step%s%s]", getenv("RANK") ? " rank " : "", getenv("RANK") ? getenv("RANK") : "");
     for (size_t i = 1; i < b->marks.size(); ++i) {
       float ms = 0.0f;
       cudaEventElapsedTime(&ms, b->marks[0].second, b->marks[i].second);
@@ -791,7 +807,10 @@ extern "C" LG_EXPORT uint64_t lgb_batch_truepeak_candidates(lgb_batch* b) {
 
 extern "C" LG_EXPORT uint64_t lgb_batch_total_samples(const lgb_batch* b) { return b->plan.total_samples; }
 extern "C" LG_EXPORT uint64_t lgb_batch_peak_count(const lgb_batch* b) { return b->plan.total_peaks; }
-extern "C" LG_EXPORT uint32_t lgb_batch_kernel_launches(const lgb_batch* b) { return b->launches; }
+extern "C" LG_EXPORT uint32_t lgb_batch_kernel_launches(const lgb_batch* b) {
+  // a repeated batch launches the two halves of its queries separately (lgb_batch_run)
+  return b->launches + ((b->qstream && !b->xchg && !b->plan.queries.empty()) ? 1u : 0u);
+}
 extern "C" LG_EXPORT uint32_t lgb_batch_sweep_launches(const lgb_batch* b) { return b->sweep_launches; }
 
 extern "C" LG_EXPORT uint64_t lgb_batch_blocks(const lgb_batch* b, size_t track, int kind,
@@ -1017,6 +1036,15 @@ extern "C" LG_EXPORT int lgb_batch_attach_exchange(lgb_batch* b, lgb_exchange* x
     for (uint32_t a = 0; a < p.nalbums; ++a) largest = std::max(largest, off[a + 1] - off[a]);
     const uint64_t want = (uint64_t) largest * x->world * 3u / 2u + 64u;
     b->xst_smem = (uint32_t) std::min<uint64_t>(want, 26000u);
+    uint64_t most_blocks = 0;
+    for (uint32_t a = 0; a < p.nalbums; ++a) {
+      const Query& q = p.queries[nt + a];
+      uint64_t nb = 0;
+      for (uint32_t m = 0; m < q.count; ++m) nb += p.tracks[p.members[q.first + m]].nblocks;
+      most_blocks = std::max(most_blocks, nb);
+    }
+    b->xcluster = query_cluster_size(most_blocks);
+    if (const char* e = getenv("LOUDGAIN_B200_XCLUSTER")) b->xcluster = atoi(e) > 0 ? (uint32_t) atoi(e) : b->xcluster;   // tuning
   }
   if (cudaStreamSynchronize(b->stream) != cudaSuccess) { set_error("lgb_batch_attach_exchange: stream error"); return 1; }
   if (b->d_xstoff) cudaFreeAsync(b->d_xstoff, b->stream);
@@ -1033,7 +1061,17 @@ extern "C" LG_EXPORT int lgb_batch_attach_exchange(lgb_batch* b, lgb_exchange* x
       return 1;
     }
   }
-  if (!b->xchg) b->launches += 3u - (nt ? 0u : 1u);      // publish, gate, finish; the query launch stays if there are tracks
+  if (!b->q2stream) {
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&b->q2stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_q2, cudaEventDisableTiming) != cudaSuccess) {
+      set_error("lgb_batch_attach_exchange: stream creation failed");
+      return 1;
+    }
+  }
+  if (!b->xchg) b->launches += 3u + (nt ? 2u : 0u);       // publish, gate, range, finish and the track queries as two
+                                                          // launches, instead of the one query launch
   b->xchg = x;
   return 0;
 }
@@ -1061,6 +1099,8 @@ extern "C" LG_EXPORT void lgb_batch_destroy(lgb_batch* b) {
   if (b->ev_q0) cudaEventDestroy(b->ev_q0);
   if (b->ev_q1) cudaEventDestroy(b->ev_q1);
   if (b->qstream) cudaStreamDestroy(b->qstream);
+  if (b->ev_q2) cudaEventDestroy(b->ev_q2);
+  if (b->q2stream) cudaStreamDestroy(b->q2stream);
   if (b->ev_gfork) cudaEventDestroy(b->ev_gfork);
   for (int j = 0; j < lgb_batch::kGroupStreams; ++j) {
     if (b->ev_gjoin[j]) cudaEventDestroy(b->ev_gjoin[j]);

@@ -569,8 +569,12 @@ __device__ uint32_t find_track_cta(const Track* tracks, uint32_t ntracks, uint64
 }
 
 // FP64 state carry + energy correction + channel weighting, one thread per 100 ms slot
-// (lg_post.cuh: slot_energy_fused).
-__global__ void __launch_bounds__(128)
+// (lg_post.cuh: slot_energy_fused).  (Staging a CTA's stretch of chunk records in shared
+// memory first made it slower, 47 -> 61 us next to the true-peak evaluation:
+// profiles/r02_tuning.txt E.)
+constexpr int kFixThreads = 128;
+
+__global__ void __launch_bounds__(kFixThreads)
 fixslot_kernel(const Track* __restrict__ tracks, uint32_t ntracks, const CoefSet* __restrict__ coefs,
                const ChunkRec* __restrict__ recs, uint64_t total_slots, double* __restrict__ eslot,
                const cplx* __restrict__ xi_table) {
@@ -1013,15 +1017,16 @@ query_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ quer
 // gating blocks and only (sum, count) pairs travel -- written by the kernels
 // themselves into every peer's exchange region over NVLink (peer-mapped memory,
 // lg_common.h: XchgParams), ordered by system-scope release / acquire on one
-// flag per rank and phase.  Three launches per step, each of which waits only
+// flag per rank and phase.  Four launches per step, each of which waits only
 // for the peers' PREVIOUS launch, so nothing depends on how any GPU schedules
 // its CTAs:
 //   xchg_publish_kernel   sums behind the absolute gate (gating and short-term
 //                         blocks) + the rank's short-term energies -> all peers
 //   xchg_gate_kernel      waits for phase 0 of every rank; relative threshold
-//                         from the rank-ordered totals; sums behind it -> all peers.
-//                         A second CTA per album selects the range percentiles over
-//                         the union of the short-term energies every rank received
+//                         from the rank-ordered totals; sums behind it -> all peers
+//   xchg_range_kernel     (on another stream, next to the gating) waits for phase 0;
+//                         range percentiles over the union of the short-term
+//                         energies every rank received
 //   xchg_finish_kernel    waits for phase 1; loudness from the totals
 // Totals are added in rank order on every rank: all ranks get the same bits.
 // The short-term lists are one value per second of audio, a tenth of the gating
@@ -1080,8 +1085,9 @@ __device__ __forceinline__ unsigned long long* xchg_flag(const XchgParams& X, ui
 
 // Every thread has fenced its own peer stores; the CTA that finishes last tells
 // every rank that this rank's `phase` of `step` is complete.
-__device__ void xchg_signal(const XchgParams& X, uint32_t phase, unsigned long long step, uint32_t nctas) {
-  __threadfence_system();
+__device__ void xchg_signal(const XchgParams& X, uint32_t phase, unsigned long long step, uint32_t nctas,
+                            bool wrote) {
+  if (wrote) __threadfence_system();           // only threads that stored into a peer's region
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned long long done = atomicAdd(X.ctl + 1 + phase, 1ull);
@@ -1110,35 +1116,47 @@ __device__ void xchg_wait(const XchgParams& X, uint32_t phase, unsigned long lon
   __syncthreads();
 }
 
+// (A thread-block cluster per album shares the album's local blocks out, like query_kernel.)
 __global__ void __launch_bounds__(kQueryThreads)
 xchg_publish_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ queries,
                     const uint32_t* __restrict__ members, double abs_gate, const __grid_constant__ XchgParams X) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned R = cluster.num_blocks(), rk = cluster.block_rank();
+  if (R > 1) cluster.sync();      // every CTA of the cluster runs before its shared memory is touched
   __shared__ SumCount scratch[32];
+  __shared__ SumCount xch[2][kMaxQueryCluster];
   __shared__ ViewSmem vs;
-  const uint32_t a = blockIdx.x;
+  const uint32_t a = blockIdx.x / R;
   const unsigned long long step = __ldcg(X.ctl);
   const uint32_t parity = (uint32_t) (step & 1ull);
   QueryView v;
   load_view(v, vs, lists, members, queries[X.first_query + a]);
+  v.first = rk * blockDim.x + threadIdx.x;
+  v.stride = R * blockDim.x;
   double s = 0.0;
   unsigned long long n = 0;
   for_each_energy<false>(v, [&](double e, uint32_t) { if (e >= abs_gate) { s += e; ++n; } });
-  const SumCount za = block_sum_count(s, n, scratch);
+  const SumCount za = cluster_sum_count(cluster, block_sum_count(s, n, scratch), xch[0]);
   const uint32_t off = X.st_off[a], cnt = X.st_off[a + 1] - off;
   s = 0.0; n = 0;
+  bool wrote = false;
   for_each_energy<true>(v, [&](double e, uint32_t g) {
     for (uint32_t p = 0; p < X.world; ++p) xchg_st(X, p, parity, X.rank)[off + g] = e;
+    wrote = true;
     if (e >= abs_gate) { s += e; ++n; }
   });
-  const SumCount sa = block_sum_count(s, n, scratch);
-  if (threadIdx.x == 0) {
+  const SumCount sa = cluster_sum_count(cluster, block_sum_count(s, n, scratch), xch[1]);
+  if (rk == 0 && threadIdx.x == 0) {
     for (uint32_t p = 0; p < X.world; ++p) {
       XchgHdr* h = xchg_hdr(X, p, parity, X.rank, a);
       h->s1 = za.s; h->n1 = za.n; h->sst = sa.s; h->nst = sa.n;
       h->st_off = off; h->st_cnt = cnt;
     }
+    wrote = true;
   }
-  xchg_signal(X, 0, step, gridDim.x);
+  xchg_signal(X, 0, step, gridDim.x, wrote);
+  if (R > 1) cluster.sync();      // rank 0's exchange buffers have been read by everyone
 }
 
 struct XchgTotals {
@@ -1158,15 +1176,51 @@ __device__ XchgTotals xchg_totals(const XchgParams& X, uint32_t parity, uint32_t
   return t;
 }
 
-// Two CTAs per album.  Role 0 gates the rank's own blocks against the relative threshold
-// of the totals and publishes (sum, count).  Role 1 needs nothing of that: the range only
-// depends on what phase 0 brought (every rank's short-term energies and their sums), so it
-// is selected next to the gating instead of behind it.  The union of the short-term
-// energies is staged in (dynamic) shared memory when it fits.
 __global__ void __launch_bounds__(kQueryThreads)
 xchg_gate_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ queries,
-                 const uint32_t* __restrict__ members, double abs_gate, QueryResult* __restrict__ results,
-                 uint32_t st_smem_cap, const __grid_constant__ XchgParams X) {
+                 const uint32_t* __restrict__ members, double abs_gate, const __grid_constant__ XchgParams X) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned R = cluster.num_blocks(), rk = cluster.block_rank();
+  if (R > 1) cluster.sync();
+  __shared__ SumCount scratch[32];
+  __shared__ SumCount xch[kMaxQueryCluster];
+  __shared__ ViewSmem vs;
+  __shared__ XchgTotals tot;
+  const uint32_t a = blockIdx.x / R;
+  const unsigned long long step = __ldcg(X.ctl);
+  const uint32_t parity = (uint32_t) (step & 1ull);
+  QueryView v;
+  load_view(v, vs, lists, members, queries[X.first_query + a]);
+  v.first = rk * blockDim.x + threadIdx.x;
+  v.stride = R * blockDim.x;
+  xchg_wait(X, 0, step);
+  if (threadIdx.x == 0) tot = xchg_totals(X, parity, a);
+  __syncthreads();
+  double s = 0.0;
+  unsigned long long n = 0;
+  if (tot.n1) {
+    const double thr = tot.s1 / (double) tot.n1 * 0.1;
+    for_each_energy<false>(v, [&](double e, uint32_t) { if (e >= abs_gate && e >= thr) { s += e; ++n; } });
+  }
+  const SumCount b = cluster_sum_count(cluster, block_sum_count(s, n, scratch), xch);
+  if (rk == 0 && threadIdx.x == 0) {
+    for (uint32_t p = 0; p < X.world; ++p) {
+      XchgHdr* h = xchg_hdr(X, p, parity, X.rank, a);
+      h->s2 = b.s; h->n2 = b.n;
+    }
+  }
+  xchg_signal(X, 1, step, gridDim.x, rk == 0 && threadIdx.x == 0);
+  if (R > 1) cluster.sync();
+}
+
+// The range of an album needs nothing of the relative gate: only what phase 0 brought
+// (every rank's short-term energies and their sums behind the absolute gate).  It is
+// selected by its own launch, next to the gating.  The union of the short-term energies is
+// staged in (dynamic) shared memory when it fits.
+__global__ void __launch_bounds__(kQueryThreads)
+xchg_range_kernel(double abs_gate, QueryResult* __restrict__ results, uint32_t st_smem_cap,
+                  const __grid_constant__ XchgParams X) {
   extern __shared__ double s_stx[];
   __shared__ SumCount scratch[32];
   __shared__ ViewSmem vs;
@@ -1174,32 +1228,10 @@ xchg_gate_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ 
   __shared__ unsigned int hist[512];
   __shared__ unsigned int wsum[16];
   __shared__ SelectState sel;
-  const uint32_t a = blockIdx.x >> 1, role = blockIdx.x & 1u;
+  const uint32_t a = blockIdx.x;
   const unsigned long long step = __ldcg(X.ctl);
   const uint32_t parity = (uint32_t) (step & 1ull);
-  QueryView v;
-  if (role == 0) load_view(v, vs, lists, members, queries[X.first_query + a]);
   xchg_wait(X, 0, step);
-  if (role == 0) {
-    if (threadIdx.x == 0) tot = xchg_totals(X, parity, a);
-    __syncthreads();
-    double s = 0.0;
-    unsigned long long n = 0;
-    if (tot.n1) {
-      const double thr = tot.s1 / (double) tot.n1 * 0.1;
-      for_each_energy<false>(v, [&](double e, uint32_t) { if (e >= abs_gate && e >= thr) { s += e; ++n; } });
-    }
-    const SumCount b = block_sum_count(s, n, scratch);
-    if (threadIdx.x == 0) {
-      for (uint32_t p = 0; p < X.world; ++p) {
-        XchgHdr* h = xchg_hdr(X, p, parity, X.rank, a);
-        h->s2 = b.s; h->n2 = b.n;
-      }
-    }
-    xchg_signal(X, 1, step, X.nalbums);
-    return;
-  }
-  // ---- role 1: loudness range over the union of the short-term energies
   if (threadIdx.x == 0) {
     tot = xchg_totals(X, parity, a);
     uint32_t ast = 0;
@@ -1213,6 +1245,7 @@ xchg_gate_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ 
     vs.zoff[X.world] = 0; vs.stoff[X.world] = ast;
   }
   __syncthreads();
+  QueryView v;
   v.lists = nullptr; v.mem = nullptr; v.count = X.world; v.cached = true;
   v.s_lists = vs.lists; v.s_zoff = vs.zoff; v.s_stoff = vs.stoff;
   v.first = threadIdx.x; v.stride = blockDim.x;
@@ -1263,38 +1296,65 @@ xchg_finish_kernel(QueryResult* __restrict__ results, const __grid_constant__ Xc
   }
 }
 
-cudaError_t launch_exchange_publish(const BlockList* lists, const Query* queries, const uint32_t* members,
-                                    double abs_gate, const XchgParams& x, cudaStream_t stream) {
-  if (!x.nalbums) return cudaSuccess;
-  xchg_publish_kernel<<<x.nalbums, query_launch_threads(), 0, stream>>>(lists, queries, members, abs_gate, x);
-  return cudaGetLastError();
+static cudaError_t launch_clustered(const void* kernel, uint32_t nalbums, uint32_t cluster, cudaStream_t stream,
+                                    void** args) {
+  if (cluster < 1) cluster = 1;
+  if (cluster > (uint32_t) kMaxQueryCluster) cluster = kMaxQueryCluster;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nalbums * cluster);
+  cfg.blockDim = dim3(query_launch_threads());
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = cluster;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelExC(&cfg, kernel, args);
 }
 
-cudaError_t launch_exchange_finish(const BlockList* lists, const Query* queries, const uint32_t* members,
-                                   double abs_gate, QueryResult* results, const XchgParams& x,
-                                   uint32_t st_smem_doubles, cudaStream_t stream) {
+cudaError_t launch_exchange_publish(const BlockList* lists, const Query* queries, const uint32_t* members,
+                                    double abs_gate, const XchgParams& x, uint32_t cluster, cudaStream_t stream) {
+  if (!x.nalbums) return cudaSuccess;
+  void* args[] = {(void*) &lists, (void*) &queries, (void*) &members, (void*) &abs_gate, (void*) &x};
+  return launch_clustered((const void*) xchg_publish_kernel, x.nalbums, cluster, stream, args);
+}
+
+cudaError_t launch_exchange_gate(const BlockList* lists, const Query* queries, const uint32_t* members,
+                                 double abs_gate, const XchgParams& x, uint32_t cluster, cudaStream_t stream) {
+  if (!x.nalbums) return cudaSuccess;
+  void* args[] = {(void*) &lists, (void*) &queries, (void*) &members, (void*) &abs_gate, (void*) &x};
+  return launch_clustered((const void*) xchg_gate_kernel, x.nalbums, cluster, stream, args);
+}
+
+cudaError_t launch_exchange_range(double abs_gate, QueryResult* results, const XchgParams& x,
+                                  uint32_t st_smem_doubles, cudaStream_t stream) {
   if (!x.nalbums) return cudaSuccess;
   static size_t smem_limit = 0;
   const size_t smem = (size_t) st_smem_doubles * sizeof(double);
-  if (smem > 48u * 1024u && smem > smem_limit) {
-    const cudaError_t e = cudaFuncSetAttribute(xchg_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (smem > 32u * 1024u && smem > smem_limit) {       // (the kernel also has ~12 KB of static shared memory)
+    const cudaError_t e = cudaFuncSetAttribute(xchg_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int) smem);
     if (e != cudaSuccess) return e;
     smem_limit = smem;
   }
-  xchg_gate_kernel<<<2 * x.nalbums, query_launch_threads(), smem, stream>>>(lists, queries, members, abs_gate,
-                                                                           results, st_smem_doubles, x);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  xchg_range_kernel<<<x.nalbums, query_launch_threads(), smem, stream>>>(abs_gate, results, st_smem_doubles, x);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_exchange_finish(QueryResult* results, const XchgParams& x, cudaStream_t stream) {
+  if (!x.nalbums) return cudaSuccess;
   xchg_finish_kernel<<<x.nalbums, 64, 0, stream>>>(results, x);
   return cudaGetLastError();
 }
 
 cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t stream, cudaEvent_t fixed) {
   if (z.total_slots) {
-    const unsigned blocks = (unsigned) ((z.total_slots + 127) / 128);
-    fixslot_kernel<<<blocks, 128, 0, stream>>>(t.tracks, z.ntracks, t.coefs, t.recs, z.total_slots, t.eslot,
-                                              t.xi_table);
+    const unsigned blocks = (unsigned) ((z.total_slots + kFixThreads - 1) / kFixThreads);
+    fixslot_kernel<<<blocks, kFixThreads, 0, stream>>>(t.tracks, z.ntracks, t.coefs, t.recs, z.total_slots, t.eslot,
+                                                      t.xi_table);
   }
   if (fixed) {
     const cudaError_t e = cudaEventRecord(fixed, stream);

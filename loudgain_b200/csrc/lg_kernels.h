@@ -72,16 +72,19 @@ cudaError_t launch_queries(const BlockList* lists, const Query* queries, const u
                            uint32_t nqueries, double abs_gate, QueryResult* results,
                            cudaStream_t stream, uint32_t cluster = 1, int part = 0);
 uint32_t query_cluster_size(uint64_t max_gating_blocks);
-// Album queries over tracks sharded across GPUs (lg_common.h: XchgParams): the first
-// launch publishes this rank's share to every peer, the second pair gates against the
-// totals of all ranks and writes results[first_query + album].  Launch the publish as
-// early as the block lists allow; whatever runs in between hides the peers' latency.
+// Album queries over tracks sharded across GPUs (lg_common.h: XchgParams).  publish: this
+// rank's share to every peer; gate: relative threshold from all ranks' totals, this rank's
+// sums behind it to every peer; range: results[first_query + album].range from the union of
+// the short-term energies (needs only the publish phase: run it next to the gate on another
+// stream; st_smem_doubles = energies it may stage in shared memory); finish: the loudness.
+// `cluster` = CTAs that share an album's local gating blocks.
 cudaError_t launch_exchange_publish(const BlockList* lists, const Query* queries, const uint32_t* members,
-                                    double abs_gate, const XchgParams& x, cudaStream_t stream);
-// st_smem_doubles: short-term energies the range CTA may stage in shared memory (0: none).
-cudaError_t launch_exchange_finish(const BlockList* lists, const Query* queries, const uint32_t* members,
-                                   double abs_gate, QueryResult* results, const XchgParams& x,
-                                   uint32_t st_smem_doubles, cudaStream_t stream);
+                                    double abs_gate, const XchgParams& x, uint32_t cluster, cudaStream_t stream);
+cudaError_t launch_exchange_gate(const BlockList* lists, const Query* queries, const uint32_t* members,
+                                 double abs_gate, const XchgParams& x, uint32_t cluster, cudaStream_t stream);
+cudaError_t launch_exchange_range(double abs_gate, QueryResult* results, const XchgParams& x,
+                                  uint32_t st_smem_doubles, cudaStream_t stream);
+cudaError_t launch_exchange_finish(QueryResult* results, const XchgParams& x, cudaStream_t stream);
 // Sample peak and true peak (float bits, raw sample units) of track frames
 // [first, first + count) per channel into out[2 * channels] (device memory).
 cudaError_t launch_range_peaks(const void* pcm, uint32_t format, uint32_t channels, uint64_t first,

@@ -458,3 +458,34 @@ def test_config2_full_size(product, oracle):
     for ot, gt in zip(o_tracks, g["tracks"]):
         _check(ot, gt)
     _check(o_album, g["albums"][0])
+
+
+def test_two_runs_in_flight(product):
+    """lgb_batch_run keeps two result mirrors: run k + 1 may be enqueued before run k is
+    fetched; fetch returns the oldest unfetched run; a third run without a fetch is refused."""
+    import torch
+    from loudgain_b200 import engine
+
+    specs = synth.config2_specs(ntracks=3, scale=0.05)
+    tracks = [(synth.programme_s16(s, device="cuda"), s.rate) for s in specs]
+    want_t, want_a = engine.measure(tracks, [0, 0, 0])
+    b = engine.Batch(tracks, [0, 0, 0])
+    try:
+        with pytest.raises(RuntimeError):
+            b.fetch()                                  # nothing has run yet
+        b.run()
+        b.run()
+        with pytest.raises(RuntimeError):
+            b.run()                                    # two are in flight
+        for _ in range(6):                             # direct launches first, then the two graphs
+            t, a = b.fetch()
+            for w, g in zip(want_t, t):
+                assert g.loudness == w.loudness and g.range == w.range
+                np.testing.assert_array_equal(g.true_peak, w.true_peak)
+            assert a[0].loudness == want_a[0].loudness and a[0].range == want_a[0].range
+            b.run()
+        b.fetch()
+        b.fetch()
+    finally:
+        b.close()
+    torch.cuda.synchronize()

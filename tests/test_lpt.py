@@ -36,3 +36,27 @@ def test_lpt_is_deterministic_and_handles_edges():
     assert engine.lpt_assign([], 4) == ([], 0)
     ranks, worst = engine.lpt_assign([7, 3], 8)    # more ranks than items
     assert sorted(ranks) == [0, 1] and worst == 7
+
+
+def test_bench_union_gating_is_the_oracles(oracle):
+    """bench.py checks the multi-GPU album against a numpy gating of the union of all
+    ranks' block lists (merged_album_check); that restatement must be the oracle's rule."""
+    import numpy as np
+
+    import bench
+    from loudgain_b200 import synth
+    from oracle import blocks as oracle_blocks
+
+    specs = synth.config2_specs(ntracks=3, scale=0.1)
+    sts, z, st = [], [], []
+    for s in specs:
+        state = oracle.init(2, s.rate)
+        state.add_frames(synth.programme_s16(s).numpy(), 4096)
+        sts.append(state)
+        z.append(oracle_blocks(oracle, state, 0))
+        st.append(oracle_blocks(oracle, state, 1))
+    want_l, want_r = oracle.loudness_global_multiple(sts), oracle.loudness_range_multiple(sts)
+    got_l, got_r = bench._numpy_gating(np.concatenate(z), np.concatenate(st))
+    for state in sts:
+        state.destroy()
+    assert abs(got_l - want_l) < 1e-9 and abs(got_r - want_r) < 1e-9

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611"
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "exchange or config2_album or config5" 2>&1 | tail -3
+timeout 300 $TR tools/exchange_check.py 2>&1 | grep exchange_check | cut -c1-200
+for i in 1 2; do timeout 300 $TR bench.py --gpus 2 --quick --steps 20 --warmup 3 2>&1 | grep quick | cut -c30-330; done
+LOUDGAIN_B200_STEP_TRACE=1 timeout 300 $TR bench.py --gpus 2 --quick --steps 6 --warmup 3 2>&1 | grep "lgb step" | tail -2
+timeout 300 python bench.py --quick --steps 20 --warmup 3 2>&1 | tail -1 | cut -c30-330
