@@ -178,7 +178,7 @@ struct lgb_batch {
   uint32_t xcluster = 1;             // CTAs that share an album's local gating blocks in the exchange
   cudaStream_t qstream = nullptr;    // second and third query stream: the halves of the queries (and, with an
   cudaStream_t q2stream = nullptr;   // exchange, the albums' ranges) run next to each other
-  cudaEvent_t ev_q0 = nullptr, ev_q1 = nullptr, ev_q2 = nullptr;
+  cudaEvent_t ev_q0 = nullptr, ev_q1 = nullptr, ev_q2 = nullptr, ev_pub = nullptr;
   // LOUDGAIN_B200_STEP_TRACE (tuning): direct launches with a timing event behind every
   // stage of the step on the stream it runs on; the fetch prints them
   bool trace = false;
@@ -610,6 +610,10 @@ static int enqueue_step(lgb_batch* b, int parity) {
     if (e == cudaSuccess) e = cudaStreamWaitEvent(b->qstream, b->ev_q0, 0);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(b->q2stream, b->ev_q0, 0);
     if (e == cudaSuccess) e = launch_exchange_publish(t.lists, t.queries, t.members, b->abs_gate, xp, b->xcluster, ps);
+    // Every kernel that WAITS for the ranks' flags must be ordered behind this rank's own
+    // publish: with hundreds of albums the waiting CTAs of the range kernel can fill every
+    // SM, and a publish kernel that cannot get an SM never raises the flag they wait for.
+    if (e == cudaSuccess) e = cudaEventRecord(b->ev_pub, ps);
     mark("x-publish", ps);
     if (e == cudaSuccess)
       e = launch_queries(t.lists, t.queries, t.members, ntq, b->abs_gate, t.results, b->qstream, 1, 2);
@@ -618,6 +622,7 @@ static int enqueue_step(lgb_batch* b, int parity) {
     if (e == cudaSuccess)
       e = launch_queries(t.lists, t.queries, t.members, ntq, b->abs_gate, t.results, b->q2stream, 1, 1);
     mark("track loudness", b->q2stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(b->q2stream, b->ev_pub, 0);
     if (e == cudaSuccess) e = launch_exchange_range(b->abs_gate, t.results, xp, b->xst_smem, b->q2stream);
     mark("x-range", b->q2stream);
     if (e == cudaSuccess) e = cudaEventRecord(b->ev_q2, b->q2stream);
@@ -1065,6 +1070,7 @@ extern "C" LG_EXPORT int lgb_batch_attach_exchange(lgb_batch* b, lgb_exchange* x
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithPriority(&b->q2stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_pub, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_q2, cudaEventDisableTiming) != cudaSuccess) {
       set_error("lgb_batch_attach_exchange: stream creation failed");
       return 1;
@@ -1100,6 +1106,7 @@ extern "C" LG_EXPORT void lgb_batch_destroy(lgb_batch* b) {
   if (b->ev_q1) cudaEventDestroy(b->ev_q1);
   if (b->qstream) cudaStreamDestroy(b->qstream);
   if (b->ev_q2) cudaEventDestroy(b->ev_q2);
+  if (b->ev_pub) cudaEventDestroy(b->ev_pub);
   if (b->q2stream) cudaStreamDestroy(b->q2stream);
   if (b->ev_gfork) cudaEventDestroy(b->ev_gfork);
   for (int j = 0; j < lgb_batch::kGroupStreams; ++j) {
