@@ -655,8 +655,7 @@ def gpu_arm(args):
         achieved = samples * 2 / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None
         cpu = cpu_baseline_leg([h.numpy() for h in host], rates) if world == 1 else None
         traffic, traffic_file = _ncu_traffic()
-        cfg = bench_config(world)
-        cfg["scanner_threads_per_gpu"] = threads
+        cfg = bench_config(world)          # (identical to the reference arm's)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,

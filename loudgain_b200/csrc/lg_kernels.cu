@@ -1164,16 +1164,28 @@ struct XchgTotals {
   unsigned long long n1, nst, n2;
 };
 
-// Totals of album `a` over all ranks, added in rank order (thread 0; broadcast by the caller).
-__device__ XchgTotals xchg_totals(const XchgParams& X, uint32_t parity, uint32_t a) {
-  XchgTotals t{0.0, 0.0, 0.0, 0ull, 0ull, 0ull};
-  for (uint32_t r = 0; r < X.world; ++r) {
-    const XchgHdr* h = xchg_hdr(X, X.rank, parity, r, a);
-    t.s1 += __ldcg(&h->s1); t.n1 += __ldcg(&h->n1);
-    t.sst += __ldcg(&h->sst); t.nst += __ldcg(&h->nst);
-    t.s2 += __ldcg(&h->s2); t.n2 += __ldcg(&h->n2);
+// Totals of album `a` over all ranks.  Thread r fetches rank r's header (four 16-byte loads,
+// all ranks at once), thread 0 adds them up in rank order: the same bits on every rank.
+// CTA-collective; the headers stay in s_hdr for the caller.
+__device__ void xchg_totals(const XchgParams& X, uint32_t parity, uint32_t a, XchgHdr* s_hdr /* [kMaxWorld] */,
+                            XchgTotals* out /* shared */) {
+  if (threadIdx.x < X.world) {
+    const uint4* src = reinterpret_cast<const uint4*>(xchg_hdr(X, X.rank, parity, threadIdx.x, a));
+    uint4* dst = reinterpret_cast<uint4*>(s_hdr + threadIdx.x);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dst[k] = __ldcg(src + k);
   }
-  return t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    XchgTotals t{0.0, 0.0, 0.0, 0ull, 0ull, 0ull};
+    for (uint32_t r = 0; r < X.world; ++r) {
+      t.s1 += s_hdr[r].s1; t.n1 += s_hdr[r].n1;
+      t.sst += s_hdr[r].sst; t.nst += s_hdr[r].nst;
+      t.s2 += s_hdr[r].s2; t.n2 += s_hdr[r].n2;
+    }
+    *out = t;
+  }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(kQueryThreads)
@@ -1187,6 +1199,7 @@ xchg_gate_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ 
   __shared__ SumCount xch[kMaxQueryCluster];
   __shared__ ViewSmem vs;
   __shared__ XchgTotals tot;
+  __shared__ XchgHdr s_hdr[kMaxWorld];
   const uint32_t a = blockIdx.x / R;
   const unsigned long long step = __ldcg(X.ctl);
   const uint32_t parity = (uint32_t) (step & 1ull);
@@ -1195,8 +1208,7 @@ xchg_gate_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ 
   v.first = rk * blockDim.x + threadIdx.x;
   v.stride = R * blockDim.x;
   xchg_wait(X, 0, step);
-  if (threadIdx.x == 0) tot = xchg_totals(X, parity, a);
-  __syncthreads();
+  xchg_totals(X, parity, a, s_hdr, &tot);
   double s = 0.0;
   unsigned long long n = 0;
   if (tot.n1) {
@@ -1231,14 +1243,14 @@ xchg_range_kernel(double abs_gate, QueryResult* __restrict__ results, uint32_t s
   const uint32_t a = blockIdx.x;
   const unsigned long long step = __ldcg(X.ctl);
   const uint32_t parity = (uint32_t) (step & 1ull);
+  __shared__ XchgHdr s_hdr[kMaxWorld];
   xchg_wait(X, 0, step);
+  xchg_totals(X, parity, a, s_hdr, &tot);
   if (threadIdx.x == 0) {
-    tot = xchg_totals(X, parity, a);
     uint32_t ast = 0;
     for (uint32_t r = 0; r < X.world; ++r) {
-      const XchgHdr* h = xchg_hdr(X, X.rank, parity, r, a);
-      const uint32_t cnt = __ldcg(&h->st_cnt);
-      vs.lists[r] = BlockList{nullptr, xchg_st(X, X.rank, parity, r) + __ldcg(&h->st_off), 0u, cnt};
+      const uint32_t cnt = s_hdr[r].st_cnt;
+      vs.lists[r] = BlockList{nullptr, xchg_st(X, X.rank, parity, r) + s_hdr[r].st_off, 0u, cnt};
       vs.zoff[r] = 0; vs.stoff[r] = ast;
       ast += cnt;
     }
@@ -1280,9 +1292,11 @@ xchg_finish_kernel(QueryResult* __restrict__ results, const __grid_constant__ Xc
   const uint32_t a = blockIdx.x;
   const unsigned long long step = __ldcg(X.ctl);
   const uint32_t parity = (uint32_t) (step & 1ull);
+  __shared__ XchgHdr s_hdr[kMaxWorld];
+  __shared__ XchgTotals tot;
   xchg_wait(X, 1, step);
+  xchg_totals(X, parity, a, s_hdr, &tot);
   if (threadIdx.x == 0) {
-    const XchgTotals tot = xchg_totals(X, parity, a);
     QueryResult& o = results[X.first_query + a];
     o.loudness = -HUGE_VAL; o.rel_thr = 0.0;
     o.sum1 = tot.s1; o.n1 = tot.n1; o.sum2 = tot.s2; o.n2 = tot.n2;
