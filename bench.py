@@ -228,9 +228,16 @@ def reference_arm(args):
     from oracle import load_oracle
     lib = load_oracle()
     cores = usable_cores()
+    # the same PCM as the GPU arm's rank 0: synthesised on the GPU when there is one (not
+    # timed; bit-identical input for both arms), on the host otherwise
+    try:
+        import torch
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+    except Exception:
+        dev = "cpu"
     pcm, rates = [], []
     for s in album_specs(0):
-        pcm.append(synth.programme_s16(s).numpy())
+        pcm.append(synth.programme_s16(s, device=dev).cpu().numpy())
         rates.append(s.rate)
     samples = sum(p.size for p in pcm)
     threads = scanner_threads(1)            # rank 0 alone runs: it may use every core

@@ -1199,7 +1199,7 @@ xchg_gate_kernel(const BlockList* __restrict__ lists, const Query* __restrict__ 
   __shared__ SumCount xch[kMaxQueryCluster];
   __shared__ ViewSmem vs;
   __shared__ XchgTotals tot;
-  __shared__ XchgHdr s_hdr[kMaxWorld];
+  __shared__ __align__(16) XchgHdr s_hdr[kMaxWorld];
   const uint32_t a = blockIdx.x / R;
   const unsigned long long step = __ldcg(X.ctl);
   const uint32_t parity = (uint32_t) (step & 1ull);
@@ -1243,7 +1243,7 @@ xchg_range_kernel(double abs_gate, QueryResult* __restrict__ results, uint32_t s
   const uint32_t a = blockIdx.x;
   const unsigned long long step = __ldcg(X.ctl);
   const uint32_t parity = (uint32_t) (step & 1ull);
-  __shared__ XchgHdr s_hdr[kMaxWorld];
+  __shared__ __align__(16) XchgHdr s_hdr[kMaxWorld];
   xchg_wait(X, 0, step);
   xchg_totals(X, parity, a, s_hdr, &tot);
   if (threadIdx.x == 0) {
@@ -1292,7 +1292,7 @@ xchg_finish_kernel(QueryResult* __restrict__ results, const __grid_constant__ Xc
   const uint32_t a = blockIdx.x;
   const unsigned long long step = __ldcg(X.ctl);
   const uint32_t parity = (uint32_t) (step & 1ull);
-  __shared__ XchgHdr s_hdr[kMaxWorld];
+  __shared__ __align__(16) XchgHdr s_hdr[kMaxWorld];
   __shared__ XchgTotals tot;
   xchg_wait(X, 1, step);
   xchg_totals(X, parity, a, s_hdr, &tot);
