@@ -315,3 +315,29 @@ def test_more_feeding_threads_than_staging_buffers(product):
     for st in states:
         st.destroy()
     assert got == want
+
+
+def test_histogram_state_released_under_a_budget(product, oracle, monkeypatch):
+    """A histogram-mode state whose PCM is released in spans: its blocks are formed over the
+    kept slot list and quantised there (stream_block_kernel with the histogram table)."""
+    spec = synth.TrackSpec(seed=991, rate=48000, channels=2, seconds=70.0)
+    pcm = synth.programme_s16(spec).numpy()
+    mode = capi.MODE_LOUDGAIN | capi.MODE_HISTOGRAM
+
+    def run(lib):
+        sts = [lib.init(2, 48000, mode) for _ in range(3)]
+        for st in sts:
+            st.add_frames(pcm, 2048)
+        out = _summary(sts[1])
+        out["album_L"] = lib.loudness_global_multiple(sts)
+        for st in sts:
+            st.destroy()
+        return out
+
+    o = run(oracle)
+    rel0 = _pcm_stats(product)[2]
+    monkeypatch.setenv("LOUDGAIN_B200_PCM_BUDGET_MB", "16")
+    g = run(product)
+    assert _pcm_stats(product)[2] > rel0
+    _same(g, o)
+    assert lu_diff(g["album_L"], o["album_L"]) <= TOL_LU
