@@ -253,7 +253,7 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
     float2 thr = bc2(0.0f);
     uint32_t seen_x = 0, seen_y = 0;               // what this warp last published
     // the survivors of the stage being worked on: up to two pairs x two channels per lane
-    // (channel | pair | code of the bound; turned into queue entries when they are stored)
+    // (the bounds as float bits; turned into queue entries when they are stored)
     uint32_t cand[4];
     uint32_t cmask = 0;
     if (!active) thr = make_float2(3.0e38f, 3.0e38f);          // lanes past the track's end queue nothing
@@ -291,6 +291,10 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
 #endif
       phase ^= 1u << slot;
       __syncwarp();                    // the previous stage is consumed by every lane
+      // (Asking for the next but one stage as soon as this stage's last frames are in
+      // registers -- half a stage earlier -- made the kernel slower, 0.145 -> 0.159 ms: the
+      // barrier and the copy's uniform-datapath code in the middle of the stage keep the
+      // compiler from interleaving the two pairs' work.  profiles/r02_tuning.txt C.)
       if (pf_s < nstages) issue();
       // the partial row of a track's last item comes from its own buffer in the main stages
       const uint32_t rowp = sm_base + slot * G::kSlotBytes +
@@ -299,19 +303,20 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
 #ifndef LG_RUN_NOCOMP       // (ablation: staging only)
       // sample peak + true-peak screening of one pair: a pair (and the history
       // before it) that cannot beat the channel's peak is done
-      auto screen = [&](const float2 pm, const uint32_t pair, const uint32_t which /* pair of the stage */) {
+      auto screen = [&](const float2 pm, const uint32_t which /* pair of the stage */) {
         sp.x = fmaxf(sp.x, pm.x);
         sp.y = fmaxf(sp.y, pm.y);
         if (TP) {
+          // (only the bounds are kept here; the queue entries are put together when -- and
+          // if -- they are stored)
           const float cx = fmaxf(pm.x, prev_pm.x), cy = fmaxf(pm.y, prev_pm.y);
           prev_pm = pm;
-          const uint32_t ex = (pair << 16) | peak_code(cx), ey = 0x80000000u | (pair << 16) | peak_code(cy);
           const bool hx = cx > thr.x, hy = cy > thr.y;
           if (which == 0u) {
-            cand[0] = ex; cand[1] = ey;
+            cand[0] = __float_as_uint(cx); cand[1] = __float_as_uint(cy);
             cmask |= (hx ? 1u : 0u) | (hy ? 2u : 0u);
           } else {
-            cand[2] = ex; cand[3] = ey;
+            cand[2] = __float_as_uint(cx); cand[3] = __float_as_uint(cy);
             cmask |= (hx ? 4u : 0u) | (hy ? 8u : 0u);
           }
         }
@@ -371,7 +376,7 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
           }
         }
 #pragma unroll
-        for (uint32_t pr = 0; pr < kPairsPerStageRun; ++pr) screen(pms[pr], pair0 + pr, pr);
+        for (uint32_t pr = 0; pr < kPairsPerStageRun; ++pr) screen(pms[pr], pr);
         if (nb == fe) close_chunk();
       } else {
         // ---- a chunk (or the mode sums, or the run) ends inside the stage: one
@@ -408,8 +413,8 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
           if (xi_on) mode_accumulate2(c.yr, c.yi, P, sr, si);
           if (nb == g0 + kIter) close_chunk();
           // screening works on pairs: fold the first iteration's maxima into the second's
-          if (it2 & 1u) screen(make_float2(fmaxf(pm.x, half_pm.x), fmaxf(pm.y, half_pm.y)), iter >> 1, it2 >> 1);
-          else if (iter + 1u >= niters) screen(pm, iter >> 1, it2 >> 1);
+          if (it2 & 1u) screen(make_float2(fmaxf(pm.x, half_pm.x), fmaxf(pm.y, half_pm.y)), it2 >> 1);
+          else if (iter + 1u >= niters) screen(pm, it2 >> 1);
           else half_pm = pm;
         }
       }
@@ -431,8 +436,13 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
           unsigned long long* out = qcta + base + (incl - mine);
           const uint32_t slot_id = item * 32u + lane;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (cmask & (1u << k)) *out++ = ((unsigned long long) cand[k] << 32) | slot_id;
+          for (int k = 0; k < 4; ++k) {
+            if (!(cmask & (1u << k))) continue;
+            // channel | pair | code of the bound
+            const uint32_t w = ((uint32_t) (k & 1) << 31) | ((pair0 + (uint32_t) (k >> 1)) << 16) |
+                               peak_code(__uint_as_float(cand[k]));
+            *out++ = ((unsigned long long) w << 32) | slot_id;
+          }
 #endif
         }
         cmask = 0;
