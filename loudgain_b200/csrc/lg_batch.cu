@@ -128,7 +128,6 @@ struct lgb_batch {
   uint32_t* d_members = nullptr;
   BlockList* d_lists = nullptr;
   ChunkRec* d_recs = nullptr;
-  uint32_t* d_peaks = nullptr;
   uint32_t* d_mrec = nullptr;
   unsigned char* d_tmaps = nullptr;    // tensor maps of the TMA-staged groups, kTmaMaxM x 128 B per track
   uint64_t* d_tpq = nullptr;           // candidate queue of the packed true-peak pass
@@ -139,8 +138,10 @@ struct lgb_batch {
   double* d_eslot = nullptr;
   double* d_zblock = nullptr;
   double* d_zst = nullptr;
-  QueryResult* d_results = nullptr;    // (inside d_out, in front of the peak cells)
-  uint32_t* d_out = nullptr;           // [results][peak cells][per-group counters]: one read-back per step
+  // [results][peak cells][per-group counters]: read back per step.  Two of them, used by
+  // alternate runs: the sweep of run k + 1 raises its peak cells while the queries of run k
+  // are still filling in their results (pipelined runs, below).
+  uint32_t* d_out2[2] = {nullptr, nullptr};
   // Pinned host mirrors of the (tiny) results, filled by the step itself.  Two of
   // them, used alternately: a second run may be enqueued before the first one's
   // results are fetched (the host turn-around between steps then overlaps the GPU).
@@ -151,6 +152,18 @@ struct lgb_batch {
   // mirror): the first run launches directly, the later ones capture / replay.
   cudaGraphExec_t graph[2] = {nullptr, nullptr};
   bool graph_off = false;
+  // Pipelined runs (a batch that is run again and again): only the sweep and the true-peak
+  // evaluation stay on the caller's stream; the fix-up, the blocks, the queries (with their
+  // album exchange) and the read-back of run k go to `pstream` and finish while the sweep of
+  // run k + 1 is under way -- that sweep waits for nothing of run k but the fix-up kernel,
+  // which reads the chunk records it is about to rewrite.  The small kernels find room on the
+  // SMs the sweep leaves free (lg_common.h: run_grid_ctas).  Everything behind the block
+  // kernel replays as a CUDA graph per mirror.
+  bool pipeline = true, post_in_flight = false, pgraph_off = false;
+  cudaStream_t pstream = nullptr;
+  cudaEvent_t ev_swept = nullptr, ev_pidle = nullptr, ev_mdone[2] = {nullptr, nullptr};
+  cudaGraphExec_t pgraph[2] = {nullptr, nullptr};
+  size_t nmarks = 0;
   uint32_t runs = 0, fetched = 0;
   // The true-peak pass only feeds the peak cells and the fix-up / block / query
   // kernels never read them, so after the sweep the step forks: the small
@@ -189,12 +202,14 @@ struct lgb_batch {
   double sweep_ms_total = 0.0, tp_ms_total = 0.0;
   uint64_t sweep_runs = 0;
 
-  DeviceTables tables() const {
+  QueryResult* d_results(int parity) const { return reinterpret_cast<QueryResult*>(d_out2[parity]); }
+  uint32_t* d_peaks(int parity) const { return d_out2[parity] + 16 * plan.queries.size(); }
+  DeviceTables tables(int parity) const {
     DeviceTables t;
     t.tracks = d_tracks; t.coefs = d_coefs; t.work = d_work;
-    t.queries = d_queries; t.members = d_members; t.lists = d_lists; t.recs = d_recs; t.peaks = d_peaks;
+    t.queries = d_queries; t.members = d_members; t.lists = d_lists; t.recs = d_recs; t.peaks = d_peaks(parity);
     t.eslot = d_eslot; t.zblock = d_zblock; t.zst = d_zst;
-    t.results = d_results; t.xi_table = d_xi; t.hist_tab = hist_tab;
+    t.results = d_results(parity); t.xi_table = d_xi; t.hist_tab = hist_tab;
     return t;
   }
 };
@@ -359,6 +374,8 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
   if (const char* e = getenv("LOUDGAIN_B200_RUN")) opt.use_run = atoi(e) != 0;   // 0: stereo through lg_pair.cu
   if (const char* e = getenv("LOUDGAIN_B200_RUN_CHUNKS")) opt.force_run_chunks = atoi(e);   // tuning
   if (const char* e = getenv("LOUDGAIN_B200_RUN_WARPS")) opt.run_warps_per_sm = (uint32_t) atoi(e);   // tuning
+  if (const char* e = getenv("LOUDGAIN_B200_SPARE_SMS")) opt.spare_sms = atoi(e) != 0;   // 0: the sweep takes every SM
+  if (const char* e = getenv("LOUDGAIN_B200_PIPELINE")) b->pipeline = atoi(e) != 0;      // 0: one run behind the other
   if (const char* e = getenv("LOUDGAIN_B200_PAIR_CTAS")) b->pair_ctas = (uint32_t) atoi(e);   // tuning
   b->trace = getenv("LOUDGAIN_B200_STEP_TRACE") != nullptr;
   if (const char* e = getenv("LOUDGAIN_B200_TAIL_FRAC")) opt.tail_frac = atof(e);      // tuning
@@ -379,7 +396,9 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
             upload(p.items, &b->d_items, b->stream) && upload(p.xi_table, &b->d_xi, b->stream) &&
             dalloc(&b->d_runq, 2 * p.total_queue, b->stream) &&          // 64-bit entries
             dalloc(&b->d_runcnt, (uint64_t) p.items.size() * 32u, b->stream) &&
-            dalloc(&b->d_out, 16 * (uint64_t) p.queries.size() + 2 * p.total_peaks + p.groups.size() + 1,
+            dalloc(&b->d_out2[0], 16 * (uint64_t) p.queries.size() + 2 * p.total_peaks + p.groups.size() + 1,
+                   b->stream) &&
+            dalloc(&b->d_out2[1], 16 * (uint64_t) p.queries.size() + 2 * p.total_peaks + p.groups.size() + 1,
                    b->stream) &&
             dalloc(&b->d_mrec, p.total_mrec, b->stream) &&
             dalloc(&b->d_tpq, 2 * p.total_mrec, b->stream) &&
@@ -388,8 +407,6 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
             dalloc(&b->d_zst, p.total_st, b->stream);
   static_assert(sizeof(QueryResult) == 64, "results sit in front of the 32-bit peak cells");
   if (ok) {
-    b->d_results = reinterpret_cast<QueryResult*>(b->d_out);
-    b->d_peaks = b->d_out + 16 * p.queries.size();
     b->peaks_off = p.queries.size() * sizeof(QueryResult);
     b->out_bytes = b->peaks_off + 2 * p.total_peaks * sizeof(uint32_t);
   }
@@ -462,27 +479,27 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
   return b;
 }
 
-// One complete step on the batch's stream: sweep, true-peak pass, FP64
-// fix-up, blocks, queries, and the copy of the scalars into the pinned mirrors.
-static int enqueue_step(lgb_batch* b, int parity) {
+// ---- the pieces of a step -------------------------------------------------------
+// LOUDGAIN_B200_STEP_TRACE: a timing event behind a stage of the step, on the stream it runs on
+static void step_mark(lgb_batch* b, const char* name, cudaStream_t s) {
+  if (!b->trace) return;
+  if (b->nmarks == b->marks.size()) {
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    b->marks.emplace_back(name, ev);
+  }
+  cudaEventRecord(b->marks[b->nmarks++].second, s);
+}
+
+// Peak cells zeroed, then every sweep launch group (the first on the batch's stream, the
+// others round-robin on the group streams, joined again).
+static int enqueue_sweeps(lgb_batch* b, const DeviceTables& t, int parity) {
   const Plan& p = b->plan;
-  const DeviceTables t = b->tables();
-  // peak cells, then one true-peak ticket counter per launch group
   // peak cells, then per launch group a true-peak queue counter and a work-item ticket
-  cudaError_t e = cudaMemsetAsync(b->d_peaks, 0, (2 * p.total_peaks + p.groups.size() + 1) * sizeof(uint32_t),
-                                  b->stream);
+  cudaError_t e = cudaMemsetAsync(b->d_peaks(parity), 0,
+                                  (2 * p.total_peaks + p.groups.size() + 1) * sizeof(uint32_t), b->stream);
   if (e != cudaSuccess) { set_error("cudaMemsetAsync(peaks)", e); return 1; }
-  size_t nmarks = 0;
-  auto mark = [&](const char* name, cudaStream_t s) {
-    if (!b->trace) return;
-    if (nmarks == b->marks.size()) {
-      cudaEvent_t ev;
-      cudaEventCreate(&ev);
-      b->marks.emplace_back(name, ev);
-    }
-    cudaEventRecord(b->marks[nmarks++].second, s);
-  };
-  mark("memset", b->stream);
+  step_mark(b, "memset", b->stream);
   if (b->timing) cudaEventRecord(b->ev0, b->stream);
   const bool gfork = p.groups.size() > 1 && b->ngstreams > 0;
   if (gfork) {
@@ -507,7 +524,7 @@ static int enqueue_step(lgb_batch* b, int parity) {
     sp.ctas_per_sm = b->pair_ctas;
     if (g.run) {
       sp.items = b->d_items + g.first_item;
-      sp.tp_ticket = b->d_peaks + 2 * p.total_peaks + gidx;
+      sp.tp_ticket = t.peaks + 2 * p.total_peaks + gidx;
       sp.run_counts = b->d_runcnt + (size_t) g.first_item * 32u;
       sp.run_queue = b->d_runq + 2 * g.queue_base;
     }
@@ -526,49 +543,20 @@ static int enqueue_step(lgb_batch* b, int parity) {
     }
   }
   if (b->timing) { cudaEventRecord(b->ev1, b->stream); b->timed_run_pending = true; }
-  mark("sweep", b->stream);
-  // Fork (not in timed runs: those keep everything on the main stream, between
-  // the events): fix-up, slot and block kernels go to the high-priority side
-  // stream first.  The true-peak evaluation fills every SM for its whole
-  // duration, so it is held back until the block kernel is done: then the query
-  // kernel (a handful of large CTAs, high priority) and the evaluation become
-  // ready together and share the GPU, instead of the queries waiting for SMs.
-  const bool fork = !b->timing && b->side != nullptr;
-  cudaStream_t ps = fork ? b->side : b->stream;
-  PostSizes z{(uint32_t) p.tracks.size(), p.total_recs, p.total_slots, p.total_blocks, p.total_st};
-  auto post_kernels = [&]() -> int {
-    e = launch_post(t, z, ps, fork ? b->ev_fix : nullptr);
-    if (e != cudaSuccess) { set_error("launch_post", e); return 1; }
-    mark("fixslot+block", ps);
-    if (fork) {
-      e = cudaEventRecord(b->ev_post, ps);
-      if (e != cudaSuccess) { set_error("cudaEventRecord(post)", e); return 1; }
-    }
-    if (b->ev_blocks) {
-      // while the step is being captured into its graph the record must be an
-      // external event node, so that streams outside the graph can wait for it
-      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-      cudaStreamIsCapturing(ps, &cap);
-      e = cap == cudaStreamCaptureStatusActive
-              ? cudaEventRecordWithFlags(b->ev_blocks, ps, cudaEventRecordExternal)
-              : cudaEventRecord(b->ev_blocks, ps);
-      if (e != cudaSuccess) { set_error("cudaEventRecord(blocks)", e); return 1; }
-    }
-    return 0;
-  };
-  if (fork) {
-    e = cudaEventRecord(b->ev_fork, b->stream);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(b->side, b->ev_fork, 0);
-    if (e != cudaSuccess) { set_error("fork(post-processing stream)", e); return 1; }
-    if (post_kernels()) return 1;
-  }
-  // The true-peak pass needs the final sample peaks of every track of a group.
+  step_mark(b, "sweep", b->stream);
+  return 0;
+}
+
+// The true-peak pass of every group on the batch's stream: it needs the final sample peaks of
+// every track of a group.  `fork`: the post-processing kernels run next to it on the side stream.
+static int enqueue_truepeak(lgb_batch* b, const DeviceTables& t, bool fork) {
+  const Plan& p = b->plan;
   uint32_t gi = 0;
   for (const SweepGroup& g : p.groups) {
     SweepParams sp = g.params;
     sp.tracks = t.tracks; sp.work = t.work + g.first_warp; sp.recs = t.recs; sp.peaks = t.peaks;
     sp.mrec = b->d_mrec + g.mrec_base;
-    sp.tp_ticket = b->d_peaks + 2 * p.total_peaks + gi++;
+    sp.tp_ticket = t.peaks + 2 * p.total_peaks + gi++;
     sp.tp_queue = b->d_tpq + 2 * g.mrec_base;
     if (g.run) {
       sp.items = b->d_items + g.first_item;
@@ -584,14 +572,34 @@ static int enqueue_step(lgb_batch* b, int parity) {
     }();
     cudaEvent_t hold = !fork ? nullptr : hold_mode == 1 ? b->ev_post : hold_mode == 2 ? b->ev_fix : nullptr;
     cudaEvent_t hold_old = fork ? b->ev_post : nullptr;     // the round-1 kernels keep their arrangement
-    e = g.run ? launch_truepeak_run(sp, g.format, g.tpf, b->sms, b->stream, hold)
-        : sp.packed ? launch_truepeak_pair(sp, g.format, g.tpf, b->sms, b->stream, hold_old)
-                    : launch_truepeak(sp, g.format, g.tpf, b->sms, b->stream, hold_old);
+    const cudaError_t e = g.run ? launch_truepeak_run(sp, g.format, g.tpf, b->sms, b->stream, hold)
+                          : sp.packed ? launch_truepeak_pair(sp, g.format, g.tpf, b->sms, b->stream, hold_old)
+                                      : launch_truepeak(sp, g.format, g.tpf, b->sms, b->stream, hold_old);
     if (e != cudaSuccess) { set_error("launch_truepeak", e); return 1; }
   }
-  mark("true-peak pass", b->stream);
+  step_mark(b, "true-peak pass", b->stream);
   if (b->timing) cudaEventRecord(b->ev2, b->stream);
-  if (!fork && post_kernels()) return 1;
+  return 0;
+}
+
+// ev_blocks: the block lists of the run are complete (lgb_batch_wait_blocks).  While the step is
+// being captured into a graph the record must be an external event node, so that streams
+// outside the graph can wait for it.
+static int record_blocks_event(lgb_batch* b, cudaStream_t ps) {
+  if (!b->ev_blocks) return 0;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(ps, &cap);
+  const cudaError_t e = cap == cudaStreamCaptureStatusActive
+                            ? cudaEventRecordWithFlags(b->ev_blocks, ps, cudaEventRecordExternal)
+                            : cudaEventRecord(b->ev_blocks, ps);
+  if (e != cudaSuccess) { set_error("cudaEventRecord(blocks)", e); return 1; }
+  return 0;
+}
+
+// Track and album queries on `ps` (with the second / third query stream next to it).
+static int enqueue_queries(lgb_batch* b, const DeviceTables& t, cudaStream_t ps, int parity) {
+  const Plan& p = b->plan;
+  cudaError_t e = cudaSuccess;
   if (b->xchg) {
     // albums span ranks: this rank's share goes out first, the track queries hide the
     // peers' latency, then the album totals are gated (lg_kernels.cu: xchg_*_kernel)
@@ -614,22 +622,22 @@ static int enqueue_step(lgb_batch* b, int parity) {
     // publish: with hundreds of albums the waiting CTAs of the range kernel can fill every
     // SM, and a publish kernel that cannot get an SM never raises the flag they wait for.
     if (e == cudaSuccess) e = cudaEventRecord(b->ev_pub, ps);
-    mark("x-publish", ps);
+    step_mark(b, "x-publish", ps);
     if (e == cudaSuccess)
       e = launch_queries(t.lists, t.queries, t.members, ntq, b->abs_gate, t.results, b->qstream, 1, 2);
-    mark("track ranges", b->qstream);
+    step_mark(b, "track ranges", b->qstream);
     if (e == cudaSuccess) e = cudaEventRecord(b->ev_q1, b->qstream);
     if (e == cudaSuccess)
       e = launch_queries(t.lists, t.queries, t.members, ntq, b->abs_gate, t.results, b->q2stream, 1, 1);
-    mark("track loudness", b->q2stream);
+    step_mark(b, "track loudness", b->q2stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(b->q2stream, b->ev_pub, 0);
     if (e == cudaSuccess) e = launch_exchange_range(b->abs_gate, t.results, xp, b->xst_smem, b->q2stream);
-    mark("x-range", b->q2stream);
+    step_mark(b, "x-range", b->q2stream);
     if (e == cudaSuccess) e = cudaEventRecord(b->ev_q2, b->q2stream);
     if (e == cudaSuccess) e = launch_exchange_gate(t.lists, t.queries, t.members, b->abs_gate, xp, b->xcluster, ps);
-    mark("x-gate", ps);
+    step_mark(b, "x-gate", ps);
     if (e == cudaSuccess) e = launch_exchange_finish(t.results, xp, ps);
-    mark("x-finish", ps);
+    step_mark(b, "x-finish", ps);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ps, b->ev_q1, 0);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ps, b->ev_q2, 0);
     if (e == cudaSuccess)
@@ -651,17 +659,125 @@ static int enqueue_step(lgb_batch* b, int parity) {
     e = launch_queries(t.lists, t.queries, t.members, (uint32_t) p.queries.size(), b->abs_gate,
                        t.results, ps, b->query_cluster);
   }
+  (void) parity;
   if (e != cudaSuccess) { set_error("launch_queries", e); return 1; }
-  mark("queries", ps);
+  step_mark(b, "queries", ps);
+  return 0;
+}
+
+// One complete step on the batch's stream: sweep, true-peak pass, FP64
+// fix-up, blocks, queries, and the copy of the scalars into the pinned mirrors.
+static int enqueue_step(lgb_batch* b, int parity) {
+  const Plan& p = b->plan;
+  const DeviceTables t = b->tables(parity);
+  cudaError_t e = cudaSuccess;
+  b->nmarks = 0;
+  if (enqueue_sweeps(b, t, parity)) return 1;
+  // Fork (not in timed runs: those keep everything on the main stream, between
+  // the events): fix-up, slot and block kernels go to the high-priority side
+  // stream first.  The true-peak evaluation fills every SM for its whole
+  // duration, so it is held back until the block kernel is done: then the query
+  // kernel (a handful of large CTAs, high priority) and the evaluation become
+  // ready together and share the GPU, instead of the queries waiting for SMs.
+  const bool fork = !b->timing && b->side != nullptr;
+  cudaStream_t ps = fork ? b->side : b->stream;
+  PostSizes z{(uint32_t) p.tracks.size(), p.total_recs, p.total_slots, p.total_blocks, p.total_st};
+  auto post_kernels = [&]() -> int {
+    e = launch_post(t, z, ps, fork ? b->ev_fix : nullptr);
+    if (e != cudaSuccess) { set_error("launch_post", e); return 1; }
+    step_mark(b, "fixslot+block", ps);
+    if (fork) {
+      e = cudaEventRecord(b->ev_post, ps);
+      if (e != cudaSuccess) { set_error("cudaEventRecord(post)", e); return 1; }
+    }
+    return record_blocks_event(b, ps);
+  };
+  if (fork) {
+    e = cudaEventRecord(b->ev_fork, b->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(b->side, b->ev_fork, 0);
+    if (e != cudaSuccess) { set_error("fork(post-processing stream)", e); return 1; }
+    if (post_kernels()) return 1;
+  }
+  if (enqueue_truepeak(b, t, fork)) return 1;
+  if (!fork && post_kernels()) return 1;
+  if (enqueue_queries(b, t, ps, parity)) return 1;
   if (fork) {
     e = cudaEventRecord(b->ev_join, b->side);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(b->stream, b->ev_join, 0);
     if (e != cudaSuccess) { set_error("join(post-processing stream)", e); return 1; }
   }
   if (b->out_bytes)
-    e = cudaMemcpyAsync(b->h_out[parity], b->d_out, b->out_bytes, cudaMemcpyDeviceToHost, b->stream);
+    e = cudaMemcpyAsync(b->h_out[parity], b->d_out2[parity], b->out_bytes, cudaMemcpyDeviceToHost, b->stream);
   if (e != cudaSuccess) { set_error("cudaMemcpyAsync(results)", e); return 1; }
-  mark("read-back", b->stream);
+  step_mark(b, "read-back", b->stream);
+  return 0;
+}
+
+// Everything of a pipelined step behind the fix-up kernel, on `ps` (direct or being captured):
+// blocks, queries, the results' read-back.
+static int enqueue_post_tail(lgb_batch* b, const DeviceTables& t, cudaStream_t ps, int parity) {
+  const Plan& p = b->plan;
+  PostSizes zb{(uint32_t) p.tracks.size(), p.total_recs, 0, p.total_blocks, p.total_st};
+  cudaError_t e = launch_post(t, zb, ps, nullptr);
+  if (e != cudaSuccess) { set_error("launch_post(blocks)", e); return 1; }
+  if (record_blocks_event(b, ps)) return 1;
+  if (enqueue_queries(b, t, ps, parity)) return 1;
+  if (b->peaks_off)
+    e = cudaMemcpyAsync(b->h_out[parity], b->d_out2[parity], b->peaks_off, cudaMemcpyDeviceToHost, ps);
+  if (e != cudaSuccess) { set_error("cudaMemcpyAsync(results)", e); return 1; }
+  return 0;
+}
+
+// A pipelined step (see lgb_batch: pstream).  Caller's stream: peak cells zeroed, sweep,
+// true-peak evaluation -- nothing else, so the next run's sweep follows at once.  pstream:
+// fix-up (direct launch; the caller's stream waits for it before the next sweep), then blocks,
+// queries and the results' read-back as a graph, then the peaks once the evaluation is through.
+static int enqueue_step_pipelined(lgb_batch* b, int parity) {
+  const Plan& p = b->plan;
+  const DeviceTables t = b->tables(parity);
+  b->nmarks = 0;
+  if (enqueue_sweeps(b, t, parity)) return 1;
+  cudaError_t e = cudaEventRecord(b->ev_swept, b->stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(b->pstream, b->ev_swept, 0);
+  if (e != cudaSuccess) { set_error("fork(pipelined post-processing)", e); return 1; }
+  if (enqueue_truepeak(b, t, false)) return 1;
+  e = cudaEventRecord(b->ev_mdone[parity], b->stream);
+  if (e != cudaSuccess) { set_error("cudaEventRecord(main part)", e); return 1; }
+  // fix-up: the only reader of the chunk records
+  PostSizes zf{(uint32_t) p.tracks.size(), p.total_recs, p.total_slots, 0, 0};
+  e = launch_post(t, zf, b->pstream, b->ev_fix);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(b->stream, b->ev_fix, 0);
+  if (e != cudaSuccess) { set_error("launch_post(fix-up)", e); return 1; }
+  if (!b->pgraph[parity] && !b->pgraph_off) {
+    cudaGraph_t g = nullptr;
+    e = cudaStreamBeginCapture(b->pstream, cudaStreamCaptureModeRelaxed);
+    if (e == cudaSuccess) {
+      const int rc = enqueue_post_tail(b, t, b->pstream, parity);
+      e = cudaStreamEndCapture(b->pstream, &g);
+      if (rc != 0 && e == cudaSuccess) e = cudaErrorUnknown;
+    }
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&b->pgraph[parity], g, 0);
+    if (g) cudaGraphDestroy(g);
+    if (e != cudaSuccess) {          // no capture on this stream: keep launching directly
+      cudaGetLastError();
+      b->pgraph[parity] = nullptr;
+      b->pgraph_off = true;
+    }
+  }
+  if (b->pgraph[parity]) {
+    e = cudaGraphLaunch(b->pgraph[parity], b->pstream);
+    if (e != cudaSuccess) { set_error("cudaGraphLaunch(post-processing)", e); return 1; }
+  } else if (enqueue_post_tail(b, t, b->pstream, parity)) {
+    return 1;
+  }
+  // the peak cells are final behind the evaluation
+  e = cudaStreamWaitEvent(b->pstream, b->ev_mdone[parity], 0);
+  if (e == cudaSuccess && b->out_bytes > b->peaks_off)
+    e = cudaMemcpyAsync(b->h_out[parity] + b->peaks_off, b->d_peaks(parity), b->out_bytes - b->peaks_off,
+                        cudaMemcpyDeviceToHost, b->pstream);
+  if (e == cudaSuccess) e = cudaEventRecord(b->ev_done[parity], b->pstream);
+  if (e != cudaSuccess) { set_error("cudaMemcpyAsync(peaks)", e); return 1; }
+  b->post_in_flight = true;
   return 0;
 }
 
@@ -684,6 +800,31 @@ extern "C" LG_EXPORT int lgb_batch_run(lgb_batch* b) {
       if (b->qstream) { cudaStreamDestroy(b->qstream); b->qstream = nullptr; }
     }
   }
+  if (k == 1 && b->pipeline && !b->pstream && b->side && b->qstream) {
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    bool ok = cudaStreamCreateWithPriority(&b->pstream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+              cudaEventCreateWithFlags(&b->ev_swept, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&b->ev_pidle, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i)
+      ok = cudaEventCreateWithFlags(&b->ev_mdone[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      cudaGetLastError();
+      b->pipeline = false;
+    }
+  }
+  // timed runs (bench roofline leg), traced runs and the first run launch directly
+  const bool direct = b->timing || b->graph_off || b->trace || k < 1;
+  if (!direct && b->pipeline && b->pstream) return enqueue_step_pipelined(b, parity);
+  if (b->post_in_flight) {
+    // behind pipelined runs: this run's kernels rewrite what their post-processing reads
+    if (cudaEventRecord(b->ev_pidle, b->pstream) != cudaSuccess ||
+        cudaStreamWaitEvent(b->stream, b->ev_pidle, 0) != cudaSuccess) {
+      set_error("lgb_batch_run: cannot order behind the pipelined runs");
+      return 1;
+    }
+    b->post_in_flight = false;
+  }
   auto done = [&](int rc) {
     if (rc == 0 && cudaEventRecord(b->ev_done[parity], b->stream) != cudaSuccess) {
       set_error("lgb_batch_run: cudaEventRecord failed");
@@ -691,8 +832,7 @@ extern "C" LG_EXPORT int lgb_batch_run(lgb_batch* b) {
     }
     return rc;
   };
-  // timed runs (bench roofline leg), traced runs and the first run launch directly
-  if (b->timing || b->graph_off || b->trace || k < 1) return done(enqueue_step(b, parity));
+  if (direct) return done(enqueue_step(b, parity));
   if (!b->graph[parity]) {
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeRelaxed);
@@ -800,7 +940,7 @@ extern "C" LG_EXPORT uint64_t lgb_batch_truepeak_candidates(lgb_batch* b) {
   uint64_t total = 0;
   for (const SweepGroup& g : p.groups) {
     if (!g.run || !g.tpf) continue;
-    const uint32_t grid = g.nitems < b->sms ? g.nitems : b->sms;
+    const uint32_t grid = run_sweep_grid(g.params, b->sms);
     std::vector<uint32_t> h(grid);
     if (cudaMemcpy(h.data(), b->d_runcnt + (size_t) g.first_item * 32u, grid * sizeof(uint32_t),
                    cudaMemcpyDeviceToHost) != cudaSuccess)
@@ -1051,11 +1191,17 @@ extern "C" LG_EXPORT int lgb_batch_attach_exchange(lgb_batch* b, lgb_exchange* x
     b->xcluster = query_cluster_size(most_blocks);
     if (const char* e = getenv("LOUDGAIN_B200_XCLUSTER")) b->xcluster = atoi(e) > 0 ? (uint32_t) atoi(e) : b->xcluster;   // tuning
   }
-  if (cudaStreamSynchronize(b->stream) != cudaSuccess) { set_error("lgb_batch_attach_exchange: stream error"); return 1; }
+  if (cudaStreamSynchronize(b->stream) != cudaSuccess ||
+      (b->pstream && cudaStreamSynchronize(b->pstream) != cudaSuccess)) {
+    set_error("lgb_batch_attach_exchange: stream error");
+    return 1;
+  }
   if (b->d_xstoff) cudaFreeAsync(b->d_xstoff, b->stream);
   if (!upload(off, &b->d_xstoff, b->stream) || cudaStreamSynchronize(b->stream) != cudaSuccess) return 1;
-  for (int k = 0; k < 2; ++k)
+  for (int k = 0; k < 2; ++k) {
     if (b->graph[k]) { cudaGraphExecDestroy(b->graph[k]); b->graph[k] = nullptr; }
+    if (b->pgraph[k]) { cudaGraphExecDestroy(b->pgraph[k]); b->pgraph[k] = nullptr; }
+  }
   if (!b->qstream) {
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
@@ -1087,12 +1233,15 @@ extern "C" LG_EXPORT void lgb_batch_destroy(lgb_batch* b) {
   if (b->ev0) { cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); cudaEventDestroy(b->ev2); }
   for (auto& m : b->marks) cudaEventDestroy(m.second);
   void* const mem[] = {b->d_tracks, b->d_coefs, b->d_work, b->d_queries, b->d_members, b->d_lists,
-                       b->d_recs, b->d_out, b->d_mrec, b->d_tpq, b->d_tmaps, b->d_items, b->d_xi, b->d_runq, b->d_runcnt, b->d_eslot, b->d_zblock, b->d_zst,
+                       b->d_recs, b->d_out2[0], b->d_out2[1], b->d_mrec, b->d_tpq, b->d_tmaps, b->d_items, b->d_xi, b->d_runq, b->d_runcnt, b->d_eslot, b->d_zblock, b->d_zst,
                        b->d_xstoff};
   cudaStreamSynchronize(b->stream);   // a run may still be writing the mirrors
+  if (b->pstream) cudaStreamSynchronize(b->pstream);
   for (void* m : mem) if (m) cudaFreeAsync(m, b->stream);
   for (int k = 0; k < 2; ++k) {
     if (b->graph[k]) cudaGraphExecDestroy(b->graph[k]);
+    if (b->pgraph[k]) cudaGraphExecDestroy(b->pgraph[k]);
+    if (b->ev_mdone[k]) cudaEventDestroy(b->ev_mdone[k]);
     if (b->ev_done[k]) cudaEventDestroy(b->ev_done[k]);
     if (b->h_out[k]) cudaFreeHost(b->h_out[k]);
   }
@@ -1102,6 +1251,9 @@ extern "C" LG_EXPORT void lgb_batch_destroy(lgb_batch* b) {
   if (b->ev_fix) cudaEventDestroy(b->ev_fix);
   if (b->ev_blocks) cudaEventDestroy(b->ev_blocks);
   if (b->side) cudaStreamDestroy(b->side);
+  if (b->ev_swept) cudaEventDestroy(b->ev_swept);
+  if (b->ev_pidle) cudaEventDestroy(b->ev_pidle);
+  if (b->pstream) cudaStreamDestroy(b->pstream);
   if (b->ev_q0) cudaEventDestroy(b->ev_q0);
   if (b->ev_q1) cudaEventDestroy(b->ev_q1);
   if (b->qstream) cudaStreamDestroy(b->qstream);

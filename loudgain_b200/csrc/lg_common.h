@@ -309,7 +309,24 @@ struct SweepParams {
   uint32_t run_lane_stride;  // most entries one lane can queue = npairs * 2 channels
   uint32_t run_cta_cap;      // entries reserved per sweep CTA (its items' lanes x run_lane_stride)
   float peak_scale;          // raw sample unit / the sweep's internal unit (16-bit input is scaled by 65536)
+  uint32_t run_grid;         // persistent CTAs the sweep is launched with (run_grid_ctas)
 };
+
+// CTAs of the run sweep (one per SM, `warps` autonomous warps each, warp w on sub-partition
+// w % 4).  Several rounds of items: every SM.  One round: the launch lasts as long as the
+// fullest sub-partition, so the SMs that are used are filled up to that level and the others
+// are left free -- the small kernels behind the PREVIOUS run of a repeated batch (fix-up,
+// blocks, queries, the album exchange) run there while this sweep is under way
+// (lg_batch.cu: pipelined runs).  12-track album: 2200 items -> 138 CTAs x 16 warps.
+LG_BOTH uint32_t run_grid_ctas(uint32_t nitems, uint32_t sms, uint32_t warps, bool spare) {
+  const uint32_t grid = nitems < sms ? nitems : sms;
+  if (!spare || nitems <= sms || nitems > sms * warps || warps < 4u) return grid;
+  const uint32_t per_sm = (nitems + sms - 1u) / sms;
+  uint32_t fill = ((per_sm + 3u) / 4u) * 4u;
+  if (fill > warps) fill = warps;
+  const uint32_t g = (nitems + fill - 1u) / fill;
+  return g < grid ? g : grid;
+}
 
 // ---- 2-D TMA view of a track -------------------------------------------------
 // Chunks j = i*m + r of one class r start m*L frames apart, a multiple of 16

@@ -50,6 +50,7 @@ cudaError_t launch_truepeak_pair(const SweepParams& p, uint32_t format, int tpf,
 // The run sweep and its true-peak pass (lg_run.cu: stereo tracks, one lane per
 // run of chunks, persistent one-warp CTAs).
 cudaError_t launch_sweep_run(const SweepParams& p, uint32_t format, int tpf, uint32_t sms, cudaStream_t stream);
+uint32_t run_sweep_grid(const SweepParams& p, uint32_t sms);     // persistent CTAs launch_sweep_run starts
 cudaError_t launch_truepeak_run(const SweepParams& p, uint32_t format, int tpf, uint32_t sms,
                                 cudaStream_t stream, cudaEvent_t hold = nullptr);
 // `fixed` (optional): recorded behind the fix-up kernel, before the block kernel.

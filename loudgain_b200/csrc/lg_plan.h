@@ -85,6 +85,7 @@ struct PlanOptions {
   uint32_t sms = 148;          // SMs of the device (run sweep: one wave of work items when the batch is small)
   uint32_t run_warps_per_sm = 0;   // resident warps per SM of the run sweep (0 = kRunWarpsPerSM)
   int force_run_chunks = 0;    // > 0 pins the chunks per run (tuning / tests)
+  bool spare_sms = true;       // a one-round run sweep leaves the SMs it does not need free (run_grid_ctas)
   // Tail filler (profiles/r01_pair_tuning.txt I/J): the tracks that hold the last
   // `tail_frac` of the batch's lane-frames get chunks `tail_div` times shorter.
   // Their launch group follows the main one on a second stream, and its short
@@ -332,9 +333,10 @@ inline void build_plan(const TrackIn* in, size_t n, uint32_t nalbums, const Plan
       g.queue_base = p.total_queue;
       sp.run_lane_stride = (sp.npairs * 2u + 3u) & ~3u;        // 16-byte multiples
       {
-        // one dense stretch per sweep CTA (lg_run.cu launches min(sms, nitems) of them, CTA b
+        // one dense stretch per sweep CTA (lg_run.cu launches run_grid_ctas() of them, CTA b
         // owning the items b, b + grid, ...): room for every pair of every lane of its items
-        const uint32_t grid = g.nitems < opt.sms ? g.nitems : opt.sms;
+        const uint32_t grid = run_grid_ctas(g.nitems, opt.sms, sp.run_warps_per_sm, opt.spare_sms);
+        sp.run_grid = grid;
         const uint64_t per_cta = grid ? (uint64_t) ((g.nitems + grid - 1) / grid) * 32u * sp.run_lane_stride : 0u;
         sp.run_cta_cap = (uint32_t) per_cta;
         g.queue_cap = cs.tpf ? per_cta * grid : 0u;

@@ -492,6 +492,12 @@ run_sweep_kernel(const __grid_constant__ SweepParams P) {
   }
 }
 
+// CTAs of the sweep (the planner's figure; the evaluation and the host read the counts of as many)
+uint32_t run_sweep_grid(const SweepParams& p, uint32_t sms) {
+  const uint32_t most = sms < p.nitems ? sms : p.nitems;
+  return p.run_grid && p.run_grid < most ? p.run_grid : most;
+}
+
 template <int FMT, bool TP>
 static cudaError_t launch_run_k(const SweepParams& p, uint32_t sms, cudaStream_t stream) {
   using G = RunGeom<FMT>;
@@ -510,7 +516,7 @@ static cudaError_t launch_run_k(const SweepParams& p, uint32_t sms, cudaStream_t
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const uint32_t blocks = sms < p.nitems ? sms : p.nitems;
+  const uint32_t blocks = run_sweep_grid(p, sms);
   run_sweep_kernel<FMT, TP><<<blocks, warps * 32u, smem, stream>>>(p);
   return cudaGetLastError();
 }
@@ -652,7 +658,7 @@ static cudaError_t launch_tp_run_t(const SweepParams& p, uint32_t sms, cudaStrea
     const cudaError_t e = cudaStreamWaitEvent(stream, hold, 0);
     if (e != cudaSuccess) return e;
   }
-  const uint32_t nctas = sms < p.nitems ? sms : p.nitems;       // the sweep's grid (launch_run_k)
+  const uint32_t nctas = run_sweep_grid(p, sms);                // the sweep's grid (launch_run_k)
   if (nctas > kTpMaxCtas) return cudaErrorInvalidValue;
   tp_eval_run_kernel<FMT, TPF><<<sms * per_sm, kTpRunThreads, 0, stream>>>(p, nctas);
   return cudaGetLastError();

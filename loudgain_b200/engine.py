@@ -195,6 +195,10 @@ class Batch:
     def blocks(self, track: int, kind: int = 0) -> np.ndarray:
         """Block energies of one track, copied to the host (0 = 400 ms gating
         blocks, 1 = 3 s short-term blocks, 2 = 100 ms slots).  Diagnostic."""
+        # the block kernel of a repeatedly run batch is on the library's own stream
+        self._L.lgb_batch_wait_blocks.argtypes = [C.c_void_p, C.c_void_p]
+        if self._L.lgb_batch_wait_blocks(self._h, C.c_void_p(self.stream.cuda_stream)):
+            raise RuntimeError("lgb_batch_wait_blocks failed: " + _err(self._L))
         self.stream.synchronize()
         return device_blocks(self, track, kind).cpu().numpy().copy()
 

@@ -489,3 +489,51 @@ def test_two_runs_in_flight(product):
     finally:
         b.close()
     torch.cuda.synchronize()
+
+
+def test_pipelined_runs_see_their_own_pcm(product):
+    """From its second run on a batch is pipelined (lg_batch.cu: the post-processing of run k
+    finishes on the library's own stream while the sweep of run k + 1 is under way).  The
+    audio is REPLACED between runs here (a copy on the batch's stream), two runs in flight:
+    every fetch must return the results of the audio its own run swept, bit for bit what a
+    one-shot measurement of that audio gives -- no stale mirror, no result of the wrong run,
+    no peak cell shared between two runs."""
+    import torch
+    from loudgain_b200 import engine
+
+    specs = synth.config2_specs(ntracks=4, scale=0.06)
+    v0 = [synth.programme_s16(s, device="cuda") for s in specs]
+    v1 = [torch.flip(t, dims=[0]) // 2 if i % 2 else (t // 3) for i, t in enumerate(v0)]
+    rates = [s.rate for s in specs]
+    albums = [0, 0, 1, 1]
+    want = [engine.measure(list(zip(v, rates)), albums) for v in (v0, v1)]
+    bufs = [t.clone() for t in v0]
+    b = engine.Batch(list(zip(bufs, rates)), albums)
+
+    def load(which):
+        for dst, src in zip(bufs, (v0, v1)[which]):
+            dst.copy_(src, non_blocking=True)
+
+    def check(which, got):
+        want_t, want_a = want[which]
+        got_t, got_a = got
+        for w, g in zip(want_t, got_t):
+            assert g.loudness == w.loudness and g.range == w.range
+            np.testing.assert_array_equal(g.true_peak, w.true_peak)
+            np.testing.assert_array_equal(g.sample_peak, w.sample_peak)
+        for w, g in zip(want_a, got_a):
+            assert g.loudness == w.loudness and g.range == w.range
+
+    try:
+        order = [0, 1, 1, 0, 1, 0, 0, 1, 0, 1]
+        load(order[0])
+        b.run()
+        for k in range(1, len(order)):
+            load(order[k])
+            b.run()                       # two in flight
+            check(order[k - 1], b.fetch())
+        check(order[-1], b.fetch())
+        assert want[0][0][0].loudness != want[1][0][0].loudness      # the two variants do differ
+    finally:
+        b.close()
+    torch.cuda.synchronize()
