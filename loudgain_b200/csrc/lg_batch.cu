@@ -128,6 +128,7 @@ struct lgb_batch {
   uint32_t* d_members = nullptr;
   BlockList* d_lists = nullptr;
   ChunkRec* d_recs = nullptr;
+  ChunkRec* d_recs_alt = nullptr;      // pipelined runs: the odd runs' chunk records (allocated with pstream)
   uint32_t* d_mrec = nullptr;
   unsigned char* d_tmaps = nullptr;    // tensor maps of the TMA-staged groups, kTmaMaxM x 128 B per track
   uint64_t* d_tpq = nullptr;           // candidate queue of the packed true-peak pass
@@ -155,8 +156,8 @@ struct lgb_batch {
   // Pipelined runs (a batch that is run again and again): only the sweep and the true-peak
   // evaluation stay on the caller's stream; the fix-up, the blocks, the queries (with their
   // album exchange) and the read-back of run k go to `pstream` and finish while the sweep of
-  // run k + 1 is under way -- that sweep waits for nothing of run k but the fix-up kernel,
-  // which reads the chunk records it is about to rewrite.  The small kernels find room on the
+  // run k + 1 is under way -- that sweep waits for nothing of run k (odd and even runs have
+  // their own chunk records and result areas).  The small kernels find room on the
   // SMs the sweep leaves free (lg_common.h: run_grid_ctas).  Everything behind the block
   // kernel replays as a CUDA graph per mirror.
   bool pipeline = true, post_in_flight = false, pgraph_off = false;
@@ -194,8 +195,9 @@ struct lgb_batch {
   cudaEvent_t ev_q0 = nullptr, ev_q1 = nullptr, ev_q2 = nullptr, ev_pub = nullptr;
   // LOUDGAIN_B200_STEP_TRACE (tuning): direct launches with a timing event behind every
   // stage of the step on the stream it runs on; the fetch prints them
-  bool trace = false;
-  std::vector<std::pair<const char*, cudaEvent_t>> marks;
+  bool trace = false, trace_pipelined = false;
+  std::vector<std::pair<const char*, cudaEvent_t>> marks2[2];    // per mirror
+  int mark_set = 0;
   // optional sweep timing
   bool timing = false, timed_run_pending = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -207,7 +209,7 @@ struct lgb_batch {
   DeviceTables tables(int parity) const {
     DeviceTables t;
     t.tracks = d_tracks; t.coefs = d_coefs; t.work = d_work;
-    t.queries = d_queries; t.members = d_members; t.lists = d_lists; t.recs = d_recs; t.peaks = d_peaks(parity);
+    t.queries = d_queries; t.members = d_members; t.lists = d_lists; t.recs = (parity && d_recs_alt) ? d_recs_alt : d_recs; t.peaks = d_peaks(parity);
     t.eslot = d_eslot; t.zblock = d_zblock; t.zst = d_zst;
     t.results = d_results(parity); t.xi_table = d_xi; t.hist_tab = hist_tab;
     return t;
@@ -377,7 +379,9 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
   if (const char* e = getenv("LOUDGAIN_B200_SPARE_SMS")) opt.spare_sms = atoi(e) != 0;   // 0: the sweep takes every SM
   if (const char* e = getenv("LOUDGAIN_B200_PIPELINE")) b->pipeline = atoi(e) != 0;      // 0: one run behind the other
   if (const char* e = getenv("LOUDGAIN_B200_PAIR_CTAS")) b->pair_ctas = (uint32_t) atoi(e);   // tuning
-  b->trace = getenv("LOUDGAIN_B200_STEP_TRACE") != nullptr;
+  b->trace = getenv("LOUDGAIN_B200_STEP_TRACE") != nullptr;     // =2: the pipelined form of the step
+  b->trace_pipelined = b->trace && atoi(getenv("LOUDGAIN_B200_STEP_TRACE")) == 2;
+  if (b->trace_pipelined) b->pgraph_off = true;                 // (timing events cannot sit inside a graph)
   if (const char* e = getenv("LOUDGAIN_B200_TAIL_FRAC")) opt.tail_frac = atof(e);      // tuning
   if (const char* e = getenv("LOUDGAIN_B200_TAIL_DIV")) opt.tail_div = atoi(e);
   build_plan(in.data(), ntracks, nalbums, opt, b->plan);
@@ -483,12 +487,13 @@ extern "C" LG_EXPORT lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t
 // LOUDGAIN_B200_STEP_TRACE: a timing event behind a stage of the step, on the stream it runs on
 static void step_mark(lgb_batch* b, const char* name, cudaStream_t s) {
   if (!b->trace) return;
-  if (b->nmarks == b->marks.size()) {
+  auto& marks = b->marks2[b->mark_set];
+  if (b->nmarks == marks.size()) {
     cudaEvent_t ev;
     cudaEventCreate(&ev);
-    b->marks.emplace_back(name, ev);
+    marks.emplace_back(name, ev);
   }
-  cudaEventRecord(b->marks[b->nmarks++].second, s);
+  cudaEventRecord(marks[b->nmarks++].second, s);
 }
 
 // Peak cells zeroed, then every sweep launch group (the first on the batch's stream, the
@@ -557,6 +562,7 @@ static int enqueue_truepeak(lgb_batch* b, const DeviceTables& t, bool fork) {
     sp.tracks = t.tracks; sp.work = t.work + g.first_warp; sp.recs = t.recs; sp.peaks = t.peaks;
     sp.mrec = b->d_mrec + g.mrec_base;
     sp.tp_ticket = t.peaks + 2 * p.total_peaks + gi++;
+    sp.npeak_words = (uint32_t) std::min<uint64_t>(2 * p.total_peaks, 0xffffffffu);
     sp.tp_queue = b->d_tpq + 2 * g.mrec_base;
     if (g.run) {
       sp.items = b->d_items + g.first_item;
@@ -672,6 +678,7 @@ static int enqueue_step(lgb_batch* b, int parity) {
   const DeviceTables t = b->tables(parity);
   cudaError_t e = cudaSuccess;
   b->nmarks = 0;
+  b->mark_set = parity;
   if (enqueue_sweeps(b, t, parity)) return 1;
   // Fork (not in timed runs: those keep everything on the main stream, between
   // the events): fix-up, slot and block kernels go to the high-priority side
@@ -730,23 +737,35 @@ static int enqueue_post_tail(lgb_batch* b, const DeviceTables& t, cudaStream_t p
 
 // A pipelined step (see lgb_batch: pstream).  Caller's stream: peak cells zeroed, sweep,
 // true-peak evaluation -- nothing else, so the next run's sweep follows at once.  pstream:
-// fix-up (direct launch; the caller's stream waits for it before the next sweep), then blocks,
-// queries and the results' read-back as a graph, then the peaks once the evaluation is through.
+// fix-up (direct launch), then blocks, queries and the results' read-back as a graph, then the
+// peaks once the evaluation is through.
 static int enqueue_step_pipelined(lgb_batch* b, int parity) {
   const Plan& p = b->plan;
   const DeviceTables t = b->tables(parity);
   b->nmarks = 0;
+  b->mark_set = parity;
   if (enqueue_sweeps(b, t, parity)) return 1;
-  cudaError_t e = cudaEventRecord(b->ev_swept, b->stream);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(b->pstream, b->ev_swept, 0);
-  if (e != cudaSuccess) { set_error("fork(pipelined post-processing)", e); return 1; }
+  // The post-processing starts behind the true-peak evaluation, not next to it: the evaluation's
+  // grid is sized to be resident at once (every thread has its share of the candidates, a CTA
+  // that has to wait for room prolongs the kernel by its whole duration), and nothing waits
+  // for the fix-up any more.  (LOUDGAIN_B200_POST_EARLY=1: behind the sweep, tuning.)
+  static const bool post_early = [] { const char* e = getenv("LOUDGAIN_B200_POST_EARLY"); return e && atoi(e) != 0; }();
+  cudaError_t e = cudaSuccess;
+  if (post_early) {
+    e = cudaEventRecord(b->ev_swept, b->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(b->pstream, b->ev_swept, 0);
+    if (e != cudaSuccess) { set_error("fork(pipelined post-processing)", e); return 1; }
+  }
   if (enqueue_truepeak(b, t, false)) return 1;
   e = cudaEventRecord(b->ev_mdone[parity], b->stream);
+  if (e == cudaSuccess && !post_early) e = cudaStreamWaitEvent(b->pstream, b->ev_mdone[parity], 0);
   if (e != cudaSuccess) { set_error("cudaEventRecord(main part)", e); return 1; }
   // fix-up: the only reader of the chunk records
   PostSizes zf{(uint32_t) p.tracks.size(), p.total_recs, p.total_slots, 0, 0};
+  // (with one set of chunk records the next run's sweep, which rewrites them, has to wait for it)
   e = launch_post(t, zf, b->pstream, b->ev_fix);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(b->stream, b->ev_fix, 0);
+  step_mark(b, "fix-up", b->pstream);
+  if (e == cudaSuccess && !b->d_recs_alt) e = cudaStreamWaitEvent(b->stream, b->ev_fix, 0);
   if (e != cudaSuccess) { set_error("launch_post(fix-up)", e); return 1; }
   if (!b->pgraph[parity] && !b->pgraph_off) {
     cudaGraph_t g = nullptr;
@@ -775,6 +794,7 @@ static int enqueue_step_pipelined(lgb_batch* b, int parity) {
   if (e == cudaSuccess && b->out_bytes > b->peaks_off)
     e = cudaMemcpyAsync(b->h_out[parity] + b->peaks_off, b->d_peaks(parity), b->out_bytes - b->peaks_off,
                         cudaMemcpyDeviceToHost, b->pstream);
+  step_mark(b, "read-back", b->pstream);
   if (e == cudaSuccess) e = cudaEventRecord(b->ev_done[parity], b->pstream);
   if (e != cudaSuccess) { set_error("cudaMemcpyAsync(peaks)", e); return 1; }
   b->post_in_flight = true;
@@ -811,10 +831,13 @@ extern "C" LG_EXPORT int lgb_batch_run(lgb_batch* b) {
     if (!ok) {
       cudaGetLastError();
       b->pipeline = false;
+    } else if (!dalloc(&b->d_recs_alt, b->plan.total_recs, b->stream)) {
+      cudaGetLastError();            // no second set of chunk records: the sweeps wait for the fix-up
+      b->d_recs_alt = nullptr;
     }
   }
   // timed runs (bench roofline leg), traced runs and the first run launch directly
-  const bool direct = b->timing || b->graph_off || b->trace || k < 1;
+  const bool direct = b->timing || b->graph_off || (b->trace && !b->trace_pipelined) || k < 1;
   if (!direct && b->pipeline && b->pstream) return enqueue_step_pipelined(b, parity);
   if (b->post_in_flight) {
     // behind pipelined runs: this run's kernels rewrite what their post-processing reads
@@ -864,12 +887,17 @@ extern "C" LG_EXPORT int lgb_batch_fetch(lgb_batch* b, lgb_result* track_results
   if (e != cudaSuccess) { set_error("lgb_batch_fetch", e); return 1; }
   const QueryResult* h_results = reinterpret_cast<const QueryResult*>(b->h_out[parity]);
   const uint32_t* h_peaks = reinterpret_cast<const uint32_t*>(b->h_out[parity] + b->peaks_off);
-  if (b->trace && b->marks.size() > 1 && b->runs > 3) {
+  if (b->trace && b->marks2[parity].size() > 1 && b->runs > 3) {
+    const auto& marks = b->marks2[parity];
     fprintf(stderr, "[lgb step%s%s]", getenv("RANK") ? " rank " : "", getenv("RANK") ? getenv("RANK") : "");
-    for (size_t i = 1; i < b->marks.size(); ++i) {
-      float ms = 0.0f;
-      cudaEventElapsedTime(&ms, b->marks[0].second, b->marks[i].second);
-      fprintf(stderr, " %s +%.1f us;", b->marks[i].first, 1e3f * ms);
+    float ms = 0.0f;
+    // (two runs in flight: the other mirror's marks belong to the run after this one)
+    if (!b->marks2[1 - parity].empty() &&
+        cudaEventElapsedTime(&ms, marks[0].second, b->marks2[1 - parity][0].second) == cudaSuccess)
+      fprintf(stderr, " next run's start %+.1f us;", 1e3f * ms);
+    for (size_t i = 1; i < marks.size(); ++i) {
+      if (cudaEventElapsedTime(&ms, marks[0].second, marks[i].second) != cudaSuccess) continue;
+      fprintf(stderr, " %s +%.1f us;", marks[i].first, 1e3f * ms);
     }
     fprintf(stderr, "\n");
   }
@@ -1231,9 +1259,9 @@ extern "C" LG_EXPORT int lgb_batch_attach_exchange(lgb_batch* b, lgb_exchange* x
 extern "C" LG_EXPORT void lgb_batch_destroy(lgb_batch* b) {
   if (!b) return;
   if (b->ev0) { cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); cudaEventDestroy(b->ev2); }
-  for (auto& m : b->marks) cudaEventDestroy(m.second);
+  for (auto& ms : b->marks2) for (auto& m : ms) cudaEventDestroy(m.second);
   void* const mem[] = {b->d_tracks, b->d_coefs, b->d_work, b->d_queries, b->d_members, b->d_lists,
-                       b->d_recs, b->d_out2[0], b->d_out2[1], b->d_mrec, b->d_tpq, b->d_tmaps, b->d_items, b->d_xi, b->d_runq, b->d_runcnt, b->d_eslot, b->d_zblock, b->d_zst,
+                       b->d_recs, b->d_recs_alt, b->d_out2[0], b->d_out2[1], b->d_mrec, b->d_tpq, b->d_tmaps, b->d_items, b->d_xi, b->d_runq, b->d_runcnt, b->d_eslot, b->d_zblock, b->d_zst,
                        b->d_xstoff};
   cudaStreamSynchronize(b->stream);   // a run may still be writing the mirrors
   if (b->pstream) cudaStreamSynchronize(b->pstream);

@@ -310,6 +310,7 @@ struct SweepParams {
   uint32_t run_cta_cap;      // entries reserved per sweep CTA (its items' lanes x run_lane_stride)
   float peak_scale;          // raw sample unit / the sweep's internal unit (16-bit input is scaled by 65536)
   uint32_t run_grid;         // persistent CTAs the sweep is launched with (run_grid_ctas)
+  uint32_t npeak_words;      // words of the batch's peak-cell area (two per channel), set per launch
 };
 
 // CTAs of the run sweep (one per SM, `warps` autonomous warps each, warp w on sub-partition

@@ -43,6 +43,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "lg_common.h"
@@ -545,34 +546,84 @@ cudaError_t launch_sweep_run(const SweepParams& p, uint32_t format, int tpf, uin
 constexpr int kTpRunThreads = 128;
 constexpr uint32_t kTpMaxCtas = 1024;      // sweep CTAs (one per SM) the prefix has room for
 
+// One queue entry, looked up: where its window lies and what it has to beat.
+struct TpCand {
+  uint32_t kind;                 // 0: nothing to do, 1: window inside the track (staged), 2: at the track's ends
+  uint32_t ch;
+  uint32_t* cell;                // the channel's true-peak cell
+  uint32_t seen;                 // what the window has to beat (float bits)
+  const unsigned char* q;        // kind 1: first byte of the window (NT frames of history + the pair)
+};
+constexpr int kTpBatch = 4;      // entries a thread looks up together
+constexpr int kTpCellWords = 1024;   // peak-cell words (two per channel) a CTA keeps in shared memory
+
 template <int FMT, int TPF>
-__global__ void __launch_bounds__(kTpRunThreads, 4)
+__global__ void __launch_bounds__(kTpRunThreads, FMT == FMT_S16 ? 6 : 4)
 tp_eval_run_kernel(const __grid_constant__ SweepParams P, const uint32_t nctas) {
   constexpr int NT = TpTraits<TPF>::kTaps;
   constexpr int NW = NT + kPairFrames;
+  constexpr uint32_t FB = FMT == FMT_S16 ? 4u : 8u;            // bytes per stereo frame
+  constexpr uint32_t WB = (uint32_t) NW * FB;                  // bytes of a window: a multiple of 16
+  static_assert(WB % 16u == 0u, "windows are staged in 16-byte copies");
+  // A thread's window is staged in its own stretch of shared memory by cp.async: all its
+  // 16-byte copies are in flight at once (as register loads the compiler spread them over
+  // the FIR, a DRAM round trip each), and the NEXT candidate's window is requested as soon as
+  // this one sits in registers, so that it arrives while the FIR runs.  The entries themselves
+  // are looked up kTpBatch at a time, stage by stage (queue entry -> work item -> track ->
+  // peak cells), so that the four dependent round trips are paid once per batch.
+  extern __shared__ __align__(16) unsigned char tp_stage[];
   __shared__ uint32_t s_off[kTpMaxCtas + 1];
-  // exclusive prefix of the CTAs' counts (nctas <= 148 in practice: one warp does it)
+  // The peak cells of a batch with few channels, per CTA.  An album's dozen tracks share two
+  // cache lines of cells: read from L2 for every candidate (hundreds of thousands of reads of
+  // the same few sectors) they were the slowest link of the look-up.  The sample peaks are
+  // final; the true-peak cells are floors, raised locally by shared-memory atomics (only a
+  // value that beats the CTA's floor goes out to the global cell) and refreshed per batch.
+  __shared__ uint32_t s_cells[kTpCellWords];
+  const bool cells_cached = P.npeak_words <= (uint32_t) kTpCellWords;
+  if (cells_cached)
+    for (uint32_t w = threadIdx.x; w < P.npeak_words; w += blockDim.x) s_cells[w] = __ldcg(P.peaks + w);
+  // exclusive prefix of the CTAs' counts (nctas <= 148 in practice): loaded by all threads,
+  // summed by one warp
+  for (uint32_t c = threadIdx.x; c < nctas; c += blockDim.x) s_off[c + 1] = __ldcg(P.run_counts + c);
+  __syncthreads();
   if (threadIdx.x < 32u) {
     uint32_t run = 0;
     for (uint32_t c0 = 0; c0 < nctas; c0 += 32u) {
       const uint32_t c = c0 + threadIdx.x;
-      const uint32_t v = c < nctas ? __ldcg(P.run_counts + c) : 0u;
+      const uint32_t v = c < nctas ? s_off[c + 1] : 0u;
       uint32_t incl = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
         if (threadIdx.x >= (uint32_t) o) incl += u;
       }
-      if (c < nctas) s_off[c] = run + incl - v;
+      __syncwarp();
+      if (c < nctas) s_off[c + 1] = run + incl;        // inclusive: s_off[c + 1] = entries before stretch c + 1
       run += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (threadIdx.x == 0) s_off[nctas] = run;
+    if (threadIdx.x == 0) s_off[0] = 0u;
   }
   __syncthreads();
   const uint32_t count = s_off[nctas];
   const unsigned long long* queue = reinterpret_cast<const unsigned long long*>(P.run_queue);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-    uint32_t lo = 0, hi = nctas;                    // the stretch that holds entry i
+  const uint32_t stage = (uint32_t) __cvta_generic_to_shared(tp_stage) + threadIdx.x * WB;
+  // ... and its looked-up entries behind all the windows, 16 bytes each: window address, index of
+  // the true-peak cell | channel << 29 | kind << 30, what the window has to beat
+  const uint32_t cands = (uint32_t) __cvta_generic_to_shared(tp_stage) + blockDim.x * WB +
+                         threadIdx.x * (uint32_t) (kTpBatch * 16);
+  const uint32_t stride = gridDim.x * blockDim.x;
+
+  // the window -> the thread's stage
+  auto request = [&](const TpCand& c) {
+    if (c.kind == 1u) {
+#pragma unroll
+      for (uint32_t k = 0; k < WB / 16u; ++k) cp_async16(stage + 16u * k, c.q + 16u * k);
+    }
+    cp_async_commit();
+  };
+  // a window at the track's ends or across the lead-in (rare): everything looked up again
+  auto slow_window = [&](uint32_t i) -> float {
+    uint32_t lo = 0, hi = nctas;
     while (hi - lo > 1u) {
       const uint32_t mid = (lo + hi) >> 1;
       if (s_off[mid] <= i) lo = mid; else hi = mid;
@@ -582,60 +633,172 @@ tp_eval_run_kernel(const __grid_constant__ SweepParams P, const uint32_t nctas) 
     const uint32_t ch = w >> 31, pair = (w >> 16) & 0x7fffu;
     const RunItem it = P.items[slot >> 5];
     const Track& tr = P.tracks[it.track];
-    uint32_t* cell = P.peaks + 2 * ((size_t) tr.peak_base + ch);
-    // the bound against the channel's final sample peak
-    if (!(P.tp_bound * (peak_code_value(w & 0xffffu) * P.peak_scale) > __uint_as_float(__ldcg(cell)))) continue;
-    ++cell;                                          // the true-peak cell
     const long long frames = (long long) tr.frames;
     const long long t0 = (long long) (it.first_run + (slot & 31u)) * P.Lr - P.Wp + (long long) pair * kPairFrames;
     const unsigned char* pcm = reinterpret_cast<const unsigned char*>(tr.pcm);
-    float win[NW];
-    float m = 0.0f;
-    if (t0 >= NT && t0 + kPairFrames <= frames && t0 >= (long long) tr.lead_in) {
-      // the window (NT frames of history + the pair) lies inside the track: 16-byte loads
-      const unsigned char* q = pcm + (t0 - NT) * (long long) P.fb;
-      if (FMT == FMT_S16) {
-        const uint32_t sel = ch ? 0xBB32u : 0x9910u;
-#pragma unroll
-        for (int k = 0; k < NW / 4; ++k) {
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(q) + k);
-          win[4 * k + 0] = (float) sext_half(v.x, sel);
-          win[4 * k + 1] = (float) sext_half(v.y, sel);
-          win[4 * k + 2] = (float) sext_half(v.z, sel);
-          win[4 * k + 3] = (float) sext_half(v.w, sel);
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < NW / 2; ++k) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(q) + k);
-          win[2 * k + 0] = ch ? v.y : v.x;
-          win[2 * k + 1] = ch ? v.w : v.z;
-        }
+    float sw[NW];                                   // (its own array, in local memory: the
+#pragma unroll 1                                    // loop is not unrolled)
+    for (int k = 0; k < NW; ++k) {
+      const long long t = t0 - NT + k;
+      float v = 0.0f;
+      if (t >= 0 && t < frames) {
+        if (FMT == FMT_S16) v = (float) (int) reinterpret_cast<const short*>(pcm)[t * 2 + ch];
+        else v = reinterpret_cast<const float*>(pcm)[t * 2 + ch];
       }
-#pragma unroll
-      for (int k = 0; k < kPairFrames; ++k) m = fmaxf(m, tp_frame<TPF>(win, NT + k));
-    } else {
-      // a window at the track's ends or across the lead-in
-      if (t0 >= frames || t0 + kPairFrames <= (long long) tr.lead_in) continue;
-#pragma unroll
-      for (int k = 0; k < NW; ++k) {
-        const long long t = t0 - NT + k;
-        float v = 0.0f;
-        if (t >= 0 && t < frames) {
-          if (FMT == FMT_S16) v = (float) (int) reinterpret_cast<const short*>(pcm)[t * 2 + ch];
-          else v = reinterpret_cast<const float*>(pcm)[t * 2 + ch];
-        }
-        win[k] = v;
-      }
-      // the reference produces no output beyond the last frame it was given
-      const long long left = frames - t0;
-      const int nvalid = left > kPairFrames ? kPairFrames : (int) left;
-#pragma unroll
-      for (int k = 0; k < kPairFrames; ++k)
-        if (k < nvalid) m = fmaxf(m, tp_frame<TPF>(win, NT + k));
+      sw[k] = v;
     }
-    if (__float_as_uint(m) > __ldcg(cell)) atomicMax(cell, __float_as_uint(m));
+    // the reference produces no output beyond the last frame it was given
+    const long long left = frames - t0;
+    const int nvalid = left > kPairFrames ? kPairFrames : (int) left;
+    float m = 0.0f;
+#pragma unroll 1
+    for (int k = 0; k < nvalid; ++k) m = fmaxf(m, tp_frame<TPF>(sw, NT + k));
+    return m;
+  };
+
+  for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x; base < count; base += (uint32_t) kTpBatch * stride) {
+    TpCand c[kTpBatch];
+    if (cells_cached && base >= (uint32_t) kTpBatch * stride)       // later batches: the floors as they are now
+      for (uint32_t w = 2u * threadIdx.x + 1u; w < P.npeak_words; w += 2u * blockDim.x)
+        atomicMax(&s_cells[w], __ldcg(P.peaks + w));
+    // ---- look the batch's entries up, one stage for all of them at a time
+    unsigned long long e[kTpBatch];
+#pragma unroll
+    for (int j = 0; j < kTpBatch; ++j) {
+      const uint32_t i = base + (uint32_t) j * stride;
+      e[j] = 0ull;
+      c[j].kind = 0u; c[j].ch = 0u; c[j].cell = nullptr; c[j].seen = 0u; c[j].q = nullptr;
+      if (i < count && i >= base) {                 // (i >= base: no wrap-around)
+        uint32_t lo = 0, hi = nctas;                // the stretch that holds entry i
+        while (hi - lo > 1u) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (s_off[mid] <= i) lo = mid; else hi = mid;
+        }
+        e[j] = __ldcs(queue + (size_t) lo * P.run_cta_cap + (i - s_off[lo]));
+        c[j].kind = 3u;                             // (an entry: resolved below)
+      }
+    }
+    uint32_t trk[kTpBatch], run0[kTpBatch];
+#pragma unroll
+    for (int j = 0; j < kTpBatch; ++j) {
+      trk[j] = 0u; run0[j] = 0u;
+      if (c[j].kind) {
+        const RunItem* it = P.items + ((uint32_t) e[j] >> 5);
+        trk[j] = it->track; run0[j] = it->first_run;
+      }
+    }
+    uint32_t pkb[kTpBatch], lead[kTpBatch];
+    unsigned long long frames[kTpBatch];
+    const unsigned char* pcm[kTpBatch];
+#pragma unroll
+    for (int j = 0; j < kTpBatch; ++j) {
+      pkb[j] = 0u; lead[j] = 0u; frames[j] = 0ull; pcm[j] = nullptr;
+      if (c[j].kind) {
+        const Track& tr = P.tracks[trk[j]];
+        pkb[j] = tr.peak_base; lead[j] = (uint32_t) tr.lead_in; frames[j] = tr.frames;
+        pcm[j] = reinterpret_cast<const unsigned char*>(tr.pcm);
+      }
+    }
+    uint32_t spk[kTpBatch];
+#pragma unroll
+    for (int j = 0; j < kTpBatch; ++j) {
+      spk[j] = 0u;
+      if (c[j].kind) {
+        const uint32_t w = (uint32_t) (e[j] >> 32);
+        c[j].ch = w >> 31;
+        const uint32_t ci = 2u * (pkb[j] + c[j].ch);
+        uint32_t* cell = P.peaks + ci;
+        spk[j] = cells_cached ? s_cells[ci] : __ldcg(cell);
+        c[j].seen = cells_cached ? s_cells[ci + 1u] : __ldcg(cell + 1);
+        c[j].cell = cell + 1;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kTpBatch; ++j) {
+      if (!c[j].kind) continue;
+      const uint32_t slot = (uint32_t) e[j], w = (uint32_t) (e[j] >> 32);
+      const uint32_t pair = (w >> 16) & 0x7fffu;
+      // What a window has to beat to matter: the channel's sample peak (final; the true peak
+      // is reported as the larger of the two, lgb_batch_fetch) and the true-peak cell as it
+      // was when the entry was looked up (cells only grow).  Without the first every window
+      // of the first round beats an empty cell, and a hundred thousand atomics queue up on a
+      // few addresses.
+      c[j].seen = max(c[j].seen, spk[j]);
+      // a candidate whose bound does not exceed the channel's FINAL sample peak is dropped
+      // before its window is fetched
+      if (!(P.tp_bound * (peak_code_value(w & 0xffffu) * P.peak_scale) > __uint_as_float(spk[j]))) {
+        c[j].kind = 0u;
+        continue;
+      }
+      const long long fr = (long long) frames[j];
+      const long long t0 = (long long) (run0[j] + (slot & 31u)) * P.Lr - P.Wp + (long long) pair * kPairFrames;
+      if (t0 >= NT && t0 + kPairFrames <= fr && t0 >= (long long) lead[j]) {
+        c[j].kind = 1u;
+        c[j].q = pcm[j] + (t0 - NT) * (long long) FB;
+      } else if (!(t0 >= fr || t0 + kPairFrames <= (long long) lead[j])) {
+        c[j].kind = 2u;
+      } else {
+        c[j].kind = 0u;
+      }
+    }
+    // (kept in shared memory, so that the evaluation below is a loop and not four copies of the FIR)
+#pragma unroll
+    for (int j = 0; j < kTpBatch; ++j) {
+      const unsigned long long qa = (unsigned long long) (uintptr_t) c[j].q;
+      const uint32_t ci = c[j].kind ? (uint32_t) (c[j].cell - P.peaks) | (c[j].ch << 29) | (c[j].kind << 30) : 0u;
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(cands + 16u * j), "r"((uint32_t) qa),
+                   "r"((uint32_t) (qa >> 32)), "r"(ci), "r"(c[j].seen) : "memory");
+    }
+    // ---- evaluate them; candidate j + 1's window travels while j's FIR runs
+    request(c[0]);
+#pragma unroll 1
+    for (int j = 0; j < kTpBatch; ++j) {
+      const uint4 cd = lds128(cands + 16u * j);
+      const uint32_t kind = cd.z >> 30, ch = (cd.z >> 29) & 1u;
+      cp_async_wait<0>();
+      float win[NW];
+      float m = 0.0f;
+      if (kind == 1u) {
+        if (FMT == FMT_S16) {
+          const uint32_t sel = ch ? 0xBB32u : 0x9910u;
+#pragma unroll
+          for (int k = 0; k < NW / 4; ++k) {
+            const uint4 v = lds128(stage + 16u * k);
+            win[4 * k + 0] = (float) sext_half(v.x, sel);
+            win[4 * k + 1] = (float) sext_half(v.y, sel);
+            win[4 * k + 2] = (float) sext_half(v.z, sel);
+            win[4 * k + 3] = (float) sext_half(v.w, sel);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < NW / 2; ++k) {
+            const uint4 v = lds128(stage + 16u * k);
+            win[2 * k + 0] = __uint_as_float(ch ? v.y : v.x);
+            win[2 * k + 1] = __uint_as_float(ch ? v.w : v.z);
+          }
+        }
+      }
+      // (the stage's contents are in registers: the values above depend on every load)
+      if (j + 1 < kTpBatch) {
+        const uint4 nd = lds128(cands + 16u * (j + 1));
+        TpCand nx;
+        nx.kind = nd.z >> 30;
+        nx.q = reinterpret_cast<const unsigned char*>((uintptr_t) (((unsigned long long) nd.y << 32) | nd.x));
+        request(nx);
+      }
+      if (kind == 1u) {
+#pragma unroll
+        for (int k = 0; k < kPairFrames; ++k) m = fmaxf(m, tp_frame<TPF>(win, NT + k));
+      } else if (kind == 2u) {
+        m = slow_window(base + (uint32_t) j * stride);
+      }
+      if (kind && __float_as_uint(m) > cd.w) {
+        const uint32_t ci = cd.z & 0x1fffffffu, mb = __float_as_uint(m);
+        if (!cells_cached || mb > atomicMax(&s_cells[ci], mb)) atomicMax(P.peaks + ci, mb);
+      }
+    }
   }
+  cp_async_wait<0>();
 }
 
 template <int FMT, int TPF>
@@ -643,13 +806,26 @@ static cudaError_t launch_tp_run_t(const SweepParams& p, uint32_t sms, cudaStrea
   // Resident CTAs per SM of the evaluation, capped at 6 (48 K of the 64 K registers): its
   // CTAs stay for the whole kernel, and the small post-processing kernels that run next to
   // it must always find room on an SM.
+  constexpr size_t smem = (size_t) kTpRunThreads * ((TpTraits<TPF>::kTaps + kPairFrames) * (FMT == FMT_S16 ? 4u : 8u) +
+                                                    (size_t) kTpBatch * 16u);
   static int per_sm = 0;
   if (!per_sm) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tp_eval_run_kernel<FMT, TPF>, kTpRunThreads, 0) !=
-            cudaSuccess || per_sm < 1)
-      per_sm = 4;
     int cap = 6;
     if (const char* e = getenv("LOUDGAIN_B200_TPEVAL_CTAS")) cap = atoi(e) > 0 ? atoi(e) : cap;   // tuning
+    // the carve-out of the sweep before it (no reconfiguration of the SMs between the two), which
+    // holds the stages of `cap` CTAs; the default one need not
+    const int carve = 100;
+    cudaError_t e = cudaFuncSetAttribute(tp_eval_run_kernel<FMT, TPF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int) smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tp_eval_run_kernel<FMT, TPF>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    if (e != cudaSuccess) return e;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tp_eval_run_kernel<FMT, TPF>, kTpRunThreads, smem) !=
+            cudaSuccess || per_sm < 1)
+      per_sm = 4;
+    if (getenv("LOUDGAIN_B200_VERBOSE"))
+      fprintf(stderr, "[lgb] tp_eval_run_kernel<%d,%d>: %d CTAs per SM by occupancy, cap %d, %zu B staged per CTA\n",
+              FMT, TPF, per_sm, cap, smem);
     if (per_sm > cap) per_sm = cap;
   }
   // `hold`: the evaluation floods the memory system with gathers; started right behind the
@@ -660,7 +836,7 @@ static cudaError_t launch_tp_run_t(const SweepParams& p, uint32_t sms, cudaStrea
   }
   const uint32_t nctas = run_sweep_grid(p, sms);                // the sweep's grid (launch_run_k)
   if (nctas > kTpMaxCtas) return cudaErrorInvalidValue;
-  tp_eval_run_kernel<FMT, TPF><<<sms * per_sm, kTpRunThreads, 0, stream>>>(p, nctas);
+  tp_eval_run_kernel<FMT, TPF><<<sms * per_sm, kTpRunThreads, smem, stream>>>(p, nctas);
   return cudaGetLastError();
 }
 

@@ -550,6 +550,11 @@ class StreamShard:
         if self.views is None:                   # device views of the slot lists, lead-in dropped
             self.views = [device_blocks(self.batch, i, 2)[lead // self.s100:]
                           for i, (_, lead) in enumerate(self.segments)]
+        # the slot energies come from the fix-up kernel, which a repeatedly run batch keeps on
+        # the library's own stream: order this stream behind the run's block kernel
+        self.batch._L.lgb_batch_wait_blocks.argtypes = [C.c_void_p, C.c_void_p]
+        if self.batch._L.lgb_batch_wait_blocks(self.batch._h, C.c_void_p(self.stream.cuda_stream)):
+            raise RuntimeError("lgb_batch_wait_blocks failed: " + _err(self.batch._L))
         with torch.cuda.stream(self.stream):
             off = 0
             for v in self.views:
