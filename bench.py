@@ -88,8 +88,9 @@ def bench_config(world: int):
             "feed": f"ebur128_add_frames_short, {FEED_FRAMES}-frame calls from host PCM (scan.c:448), one scanner "
                     "thread per track up to the host cores per rank",
             "l2_policy": "input (495 MB per GPU) is larger than L2 (126 MB); no flush",
-            "step_overlap": "timed steps are enqueued two deep (run k + 1 before fetch k); every step's "
-                            "results are read back and fetched inside the timed region",
+            "step_overlap": "timed steps are enqueued three deep (runs k + 1 and k + 2 before fetch k) and "
+                            "pipelined on the GPU (the post-processing of run k finishes under the sweep of "
+                            "run k + 1); every step's results are read back and fetched inside the timed region",
             "clock_sampling": f"{CLOCK_LOAD_STEPS[0]} + {CLOCK_LOAD_STEPS[1]} untimed steps of the same load "
                               "around the timed steps, nvidia-smi every 100 ms",
             "sharding": "by track; one album over all ranks' tracks, gated inside the step over NVLink peer "
@@ -515,6 +516,10 @@ def gpu_arm(args):
         batch.run()
         return batch.fetch()
 
+    # runs in flight in the timed region: run k + DEPTH - 1 is enqueued before run k is fetched
+    DEPTH = 3
+    batch.set_max_in_flight(DEPTH)
+
     # ---- resident-PCM throughput (steps replay the batch's CUDA graph)
     # The timed region is a few milliseconds, far shorter than nvidia-smi's
     # start-up and sampling period.  So the sampler starts first and the same
@@ -526,15 +531,21 @@ def gpu_arm(args):
         for _ in range(args.warmup + CLOCK_LOAD_STEPS[0]):
             step()
         barrier()
-        # The K timed steps run two deep: step k + 1 is enqueued before the results of
-        # step k are fetched (lgb_batch_run keeps two result mirrors), so the host's
-        # turn-around between steps overlaps the GPU; every step's results are read.
+        # The K timed steps run three deep: steps k + 1 and k + 2 are enqueued before the
+        # results of step k are fetched (lgb_batch_run keeps three result mirrors), so the
+        # host's turn-around between steps -- and, with several GPUs, the wait for the slowest
+        # rank of the album exchange -- overlaps the GPU; every step's results are read.
         e0.record(stream)
-        batch.run()
-        for _ in range(args.steps - 1):
+        inflight = 0
+        for _ in range(args.steps):
             batch.run()
+            inflight += 1
+            if inflight == DEPTH:
+                tres, ares = batch.fetch()
+                inflight -= 1
+        while inflight:
             tres, ares = batch.fetch()
-        tres, ares = batch.fetch()
+            inflight -= 1
         e1.record(stream)
         barrier()
         for _ in range(CLOCK_LOAD_STEPS[1]):
@@ -551,11 +562,16 @@ def gpu_arm(args):
         # end -- GPU time per step without the host turn-around between steps
         barrier()
         e0.record(stream)
-        batch.run()
-        for _ in range(args.steps - 1):
+        inflight = 0
+        for _ in range(args.steps):
             batch.run()
+            inflight += 1
+            if inflight == DEPTH:
+                batch.fetch()
+                inflight -= 1
+        while inflight:
             batch.fetch()
-        batch.fetch()
+            inflight -= 1
         e1.record(stream)
         barrier()
         piped_ms = e0.elapsed_time(e1) / args.steps

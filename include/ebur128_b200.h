@@ -80,6 +80,11 @@ lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t ntracks, uint32_t na
  * (LOUDGAIN_B200_PIPELINE=0: every run completely on the batch's stream.) */
 int lgb_batch_run(lgb_batch* b);
 
+/* How many runs may be in flight before the oldest has to be fetched: 1 to 3, 2 by default.
+ * Three keep the GPU fed when the results of a run arrive late -- an album exchange between
+ * several GPUs waits for the slowest rank -- and the host needs its time to turn around. */
+int lgb_batch_set_max_in_flight(lgb_batch* b, uint32_t n);
+
 /* Waits for the OLDEST run that has not been fetched yet and copies its results to
  * the host (an error if there is none).  Any pointer may be
  * NULL.  Peaks are linear amplitudes laid out track after track, one value

@@ -574,7 +574,7 @@ __device__ uint32_t find_track_cta(const Track* tracks, uint32_t ntracks, uint64
 // profiles/r02_tuning.txt E.)
 constexpr int kFixThreads = 128;
 
-__global__ void __launch_bounds__(kFixThreads)
+__global__ void __launch_bounds__(kFixThreads, 5)
 fixslot_kernel(const Track* __restrict__ tracks, uint32_t ntracks, const CoefSet* __restrict__ coefs,
                const ChunkRec* __restrict__ recs, uint64_t total_slots, double* __restrict__ eslot,
                const cplx* __restrict__ xi_table) {

@@ -52,7 +52,7 @@ cudaError_t launch_truepeak_pair(const SweepParams& p, uint32_t format, int tpf,
 cudaError_t launch_sweep_run(const SweepParams& p, uint32_t format, int tpf, uint32_t sms, cudaStream_t stream);
 uint32_t run_sweep_grid(const SweepParams& p, uint32_t sms);     // persistent CTAs launch_sweep_run starts
 cudaError_t launch_truepeak_run(const SweepParams& p, uint32_t format, int tpf, uint32_t sms,
-                                cudaStream_t stream, cudaEvent_t hold = nullptr);
+                                cudaStream_t stream, cudaEvent_t hold = nullptr, uint32_t cta_cap = 0);
 // `fixed` (optional): recorded behind the fix-up kernel, before the block kernel.
 cudaError_t launch_post(const DeviceTables& t, const PostSizes& z, cudaStream_t stream,
                         cudaEvent_t fixed = nullptr);

@@ -83,35 +83,84 @@ LG_HD double weight_of(uint8_t wclass) {
   return wclass == 1 ? 1.0 : (wclass == 2 ? 1.41 : (wclass == 3 ? 2.0 : 0.0));
 }
 
+// The snapshots of a chunk record: what the carry needs of it.
+struct CarryRec { float pd, pw, qd, qw; };
+LG_HD CarryRec carry_rec(const ChunkRec& r) { CarryRec c; c.pd = r.pd; c.pw = r.pw; c.qd = r.qd; c.qw = r.qw; return c; }
+LG_HD void carry_step(const CoefSet& cs, const CarryRec& r, double& td, double& tw) {
+  double mx, my;
+  mat2_vec(cs.ML, td - (double) r.pd, tw - (double) r.pw, mx, my);
+  td = (double) r.qd + mx;
+  tw = (double) r.qw + my;
+}
+
 // Weighted, scaled energy (sum over frames, not yet the mean) of one 100 ms slot,
 // straight from the sweep's records: per channel one pass of the state
 // carry from `horner` chunks before the slot through its k chunks (what the
 // fix-up and slot kernels did in two steps; the carry is shared by the slot's
 // chunks instead of being restarted for each).
+//
+// The carry is a chain -- every step needs the state before it -- but the records it reads are
+// not: one record load per step in the chain's shadow made the kernel a sequence of L2 round
+// trips (15 us on the whole GPU, several times that on the few SMs a pipelined run leaves it).
+// So two channels are carried side by side (independent chains), the look-back records are
+// fetched four steps at a time before the steps are taken, and a slot chunk's record is
+// fetched while the chunk before it is evaluated.  Per channel the arithmetic and its order
+// are what they were.
 LG_HD double slot_energy_fused(const Track& tr, const CoefSet& cs, const ChunkRec* recs, uint32_t slot,
                                const cplx* xi_table, int aq_log2) {
   double total = 0.0;
   const long long j0 = (long long) slot * cs.k;
-  for (uint32_t c = 0; c < tr.channels; ++c) {
-    const double w = weight_of(tr.wclass[c]);
-    if (w == 0.0) continue;
-    const ChunkRec* rc = recs + tr.rec_base + c;
-    const long long stride = tr.channels;
-    double td = 0.0, tw = 0.0;
-    long long i = j0 - cs.horner;
-    if (i < 0) i = 0;
-    for (; i < j0; ++i) carry_step(cs, rc[i * stride], td, tw);
-    double s = 0.0;
+  const long long stride = tr.channels;
+  long long i0 = j0 - cs.horner;
+  if (i0 < 0) i0 = 0;
+  for (uint32_t c0 = 0; c0 < tr.channels; c0 += 2) {
+    const bool two = c0 + 1 < tr.channels;
+    const double wa = weight_of(tr.wclass[c0]), wb = two ? weight_of(tr.wclass[c0 + 1]) : 0.0;
+    if (wa == 0.0 && wb == 0.0) continue;
+    const ChunkRec* ra = recs + tr.rec_base + c0;
+    const ChunkRec* rb = ra + (two ? 1 : 0);
+    double tda = 0.0, twa = 0.0, tdb = 0.0, twb = 0.0;
+    long long i = i0;
+    for (; i + 4 <= j0; i += 4) {
+      CarryRec a[4], b[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int u = 0; u < 4; ++u) {
+        a[u] = carry_rec(ra[(i + u) * stride]);
+        b[u] = carry_rec(rb[(i + u) * stride]);
+      }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int u = 0; u < 4; ++u) {
+        carry_step(cs, a[u], tda, twa);
+        carry_step(cs, b[u], tdb, twb);
+      }
+    }
+    for (; i < j0; ++i) {
+      const CarryRec a = carry_rec(ra[i * stride]), b = carry_rec(rb[i * stride]);
+      carry_step(cs, a, tda, twa);
+      carry_step(cs, b, tdb, twb);
+    }
+    double sa = 0.0, sb = 0.0;
+    ChunkRec na = ra[j0 * stride], nb = rb[j0 * stride];
     for (int q = 0; q < cs.k; ++q) {
       const long long j = j0 + q;
-      const ChunkRec& r = rc[j * stride];
+      const ChunkRec r_a = na, r_b = nb;
+      if (q + 1 < cs.k) { na = ra[(j + 1) * stride]; nb = rb[(j + 1) * stride]; }
       int o = 0;
       if (cs.run_chunks == 0)
         o = lane_geometry((long long) tr.frames, cs.L, cs.W, (int) tr.aq, j).o;
-      s += chunk_energy_at(cs, r, td, tw, j, o, aq_log2, xi_table);
-      carry_step(cs, r, td, tw);
+      sa += chunk_energy_at(cs, r_a, tda, twa, j, o, aq_log2, xi_table);
+      carry_step(cs, r_a, tda, twa);
+      if (two) {
+        sb += chunk_energy_at(cs, r_b, tdb, twb, j, o, aq_log2, xi_table);
+        carry_step(cs, r_b, tdb, twb);
+      }
     }
-    total += w * s;
+    if (wa != 0.0) total += wa * sa;
+    if (two && wb != 0.0) total += wb * sb;
   }
   return total * cs.gain;
 }

@@ -802,7 +802,8 @@ tp_eval_run_kernel(const __grid_constant__ SweepParams P, const uint32_t nctas) 
 }
 
 template <int FMT, int TPF>
-static cudaError_t launch_tp_run_t(const SweepParams& p, uint32_t sms, cudaStream_t stream, cudaEvent_t hold) {
+static cudaError_t launch_tp_run_t(const SweepParams& p, uint32_t sms, cudaStream_t stream, cudaEvent_t hold,
+                                   uint32_t cta_cap) {
   // Resident CTAs per SM of the evaluation, capped at 6 (48 K of the 64 K registers): its
   // CTAs stay for the whole kernel, and the small post-processing kernels that run next to
   // it must always find room on an SM.
@@ -836,16 +837,19 @@ static cudaError_t launch_tp_run_t(const SweepParams& p, uint32_t sms, cudaStrea
   }
   const uint32_t nctas = run_sweep_grid(p, sms);                // the sweep's grid (launch_run_k)
   if (nctas > kTpMaxCtas) return cudaErrorInvalidValue;
-  tp_eval_run_kernel<FMT, TPF><<<sms * per_sm, kTpRunThreads, smem, stream>>>(p, nctas);
+  const uint32_t ctas = cta_cap && cta_cap < (uint32_t) per_sm ? cta_cap : (uint32_t) per_sm;
+  tp_eval_run_kernel<FMT, TPF><<<sms * ctas, kTpRunThreads, smem, stream>>>(p, nctas);
   return cudaGetLastError();
 }
 
 cudaError_t launch_truepeak_run(const SweepParams& p, uint32_t format, int tpf, uint32_t sms,
-                                cudaStream_t stream, cudaEvent_t hold) {
+                                cudaStream_t stream, cudaEvent_t hold, uint32_t cta_cap) {
   if (p.nitems == 0 || tpf == 0) return cudaSuccess;
   if (format == FMT_S16)
-    return tpf == 4 ? launch_tp_run_t<FMT_S16, 4>(p, sms, stream, hold) : launch_tp_run_t<FMT_S16, 2>(p, sms, stream, hold);
-  return tpf == 4 ? launch_tp_run_t<FMT_F32, 4>(p, sms, stream, hold) : launch_tp_run_t<FMT_F32, 2>(p, sms, stream, hold);
+    return tpf == 4 ? launch_tp_run_t<FMT_S16, 4>(p, sms, stream, hold, cta_cap)
+                    : launch_tp_run_t<FMT_S16, 2>(p, sms, stream, hold, cta_cap);
+  return tpf == 4 ? launch_tp_run_t<FMT_F32, 4>(p, sms, stream, hold, cta_cap)
+                  : launch_tp_run_t<FMT_F32, 2>(p, sms, stream, hold, cta_cap);
 }
 
 }  // namespace lg

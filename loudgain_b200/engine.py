@@ -172,6 +172,12 @@ class Batch:
     def sweep_launches(self) -> int:
         return self._L.lgb_batch_sweep_launches(self._h)
 
+    def set_max_in_flight(self, n: int) -> None:
+        """Runs that may be enqueued before the oldest is fetched (1..3, default 2)."""
+        self._L.lgb_batch_set_max_in_flight.argtypes = [C.c_void_p, C.c_uint32]
+        if self._L.lgb_batch_set_max_in_flight(self._h, n):
+            raise RuntimeError("lgb_batch_set_max_in_flight failed: " + _err(self._L))
+
     def run(self) -> None:
         """Enqueue the whole measurement on the batch's stream (asynchronous)."""
         if self._L.lgb_batch_run(self._h):
