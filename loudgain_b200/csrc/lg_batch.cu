@@ -803,10 +803,6 @@ static int enqueue_step_pipelined(lgb_batch* b, int parity) {
   // last CTA.)
   e = cudaEventRecord(b->ev_swept, b->mstream);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(b->fstream, b->ev_swept, 0);
-  // (the slot and block energies are read by the queries of the run before this one, unless
-  // every mirror has its own)
-  if (e == cudaSuccess && !b->blocks_per_mirror)
-    e = cudaStreamWaitEvent(b->fstream, b->ev_done[(parity + kMirrors - 1) % kMirrors], 0);
   if (e != cudaSuccess) { set_error("fork(pipelined post-processing)", e); return 1; }
   if (enqueue_truepeak(b, t, false, 5u)) return 1;
   if (b->mtrace) cudaEventRecord(b->tm1[parity], b->mstream);
@@ -815,8 +811,15 @@ static int enqueue_step_pipelined(lgb_batch* b, int parity) {
   if (e == cudaSuccess) e = cudaStreamWaitEvent(b->stream, b->ev_mdone[parity], 0);
   if (e != cudaSuccess) { set_error("cudaEventRecord(main part)", e); return 1; }
   {
-    PostSizes z{(uint32_t) p.tracks.size(), p.total_recs, p.total_slots, p.total_blocks, p.total_st};
-    e = launch_post(t, z, b->fstream, nullptr);
+    // The block and short-term energies are still being read by the queries of the run before
+    // this one (unless every mirror has its own): only the small block kernel waits for them,
+    // the fix-up does not -- the slot energies have no other reader than the block kernel.
+    PostSizes zf{(uint32_t) p.tracks.size(), p.total_recs, p.total_slots, 0, 0};
+    PostSizes zb{(uint32_t) p.tracks.size(), p.total_recs, 0, p.total_blocks, p.total_st};
+    e = launch_post(t, zf, b->fstream, nullptr);
+    if (e == cudaSuccess && !b->blocks_per_mirror)
+      e = cudaStreamWaitEvent(b->fstream, b->ev_done[(parity + kMirrors - 1) % kMirrors], 0);
+    if (e == cudaSuccess) e = launch_post(t, zb, b->fstream, nullptr);
     step_mark(b, "fix-up+blocks", b->fstream);
     if (e != cudaSuccess) { set_error("launch_post", e); return 1; }
     if (record_blocks_event(b, b->fstream)) return 1;

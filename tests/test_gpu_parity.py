@@ -491,10 +491,12 @@ def test_two_runs_in_flight(product):
     torch.cuda.synchronize()
 
 
-def test_pipelined_runs_see_their_own_pcm(product):
+@pytest.mark.parametrize("depth", [2, 3])
+def test_pipelined_runs_see_their_own_pcm(product, depth):
     """From its second run on a batch is pipelined (lg_batch.cu: the post-processing of run k
     finishes on the library's own stream while the sweep of run k + 1 is under way).  The
-    audio is REPLACED between runs here (a copy on the batch's stream), two runs in flight:
+    audio is REPLACED between runs here (a copy on the batch's stream), two or three runs in
+    flight (lgb_batch_set_max_in_flight):
     every fetch must return the results of the audio its own run swept, bit for bit what a
     one-shot measurement of that audio gives -- no stale mirror, no result of the wrong run,
     no peak cell shared between two runs."""
@@ -525,14 +527,19 @@ def test_pipelined_runs_see_their_own_pcm(product):
             assert g.loudness == w.loudness and g.range == w.range
 
     try:
-        order = [0, 1, 1, 0, 1, 0, 0, 1, 0, 1]
-        load(order[0])
-        b.run()
-        for k in range(1, len(order)):
-            load(order[k])
-            b.run()                       # two in flight
-            check(order[k - 1], b.fetch())
-        check(order[-1], b.fetch())
+        order = [0, 1, 1, 0, 1, 0, 0, 1, 0, 1, 1, 0, 0]
+        b.set_max_in_flight(depth)
+        pending = []
+        for which in order:
+            load(which)
+            b.run()
+            pending.append(which)
+            if len(pending) == depth:
+                with pytest.raises(RuntimeError):
+                    b.run()               # one too many in flight
+                check(pending.pop(0), b.fetch())
+        while pending:
+            check(pending.pop(0), b.fetch())
         assert want[0][0][0].loudness != want[1][0][0].loudness      # the two variants do differ
     finally:
         b.close()
