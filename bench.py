@@ -346,6 +346,31 @@ class Timer:
         self.barrier()
         return self.max_over_ranks(e0.elapsed_time(e1)) / steps, out
 
+    def run_deep(self, batch, steps, warmup, depth):
+        """The same for a repeatedly run batch, `depth` runs in flight (every run's results are
+        fetched inside the timed region)."""
+        torch = self.torch
+        batch.set_max_in_flight(depth)
+        for _ in range(warmup):
+            batch.run()
+            out = batch.fetch()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record(self.stream)
+        inflight = 0
+        for _ in range(steps):
+            batch.run()
+            inflight += 1
+            if inflight == depth:
+                out = batch.fetch()
+                inflight -= 1
+        while inflight:
+            out = batch.fetch()
+            inflight -= 1
+        e1.record(self.stream)
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1)) / steps, out
+
 
 def _timing_api(L):
     L.lgb_batch_enable_timing.argtypes = [C.c_void_p, C.c_int]
@@ -376,8 +401,10 @@ def extra_configs(args, torch, dist, timer, L, dev, rank, world, hbm):
     steps, warmup = max(3, min(args.steps, 10)), 3
     out = {}
 
-    def line(name, desc, batch, step, samples_all, bytes_local, sharding, more=None):
-        ms, res = timer.run(step, steps, warmup)
+    def line(name, desc, batch, step, samples_all, bytes_local, sharding, more=None, deep=True):
+        # (batches: three runs in flight, as in the headline; the time-sharded stream runs its
+        # torch / NCCL tail between the steps, one step at a time)
+        ms, res = timer.run_deep(batch, steps, max(warmup, 4), 3) if deep else timer.run(step, steps, warmup)
         sweep_ms, tp_ms = _sweep_ms(L, batch, step, steps)
         sweep_ms = timer.max_over_ranks(sweep_ms)
         o = {"workload": desc, "value": samples_all / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms,
@@ -452,7 +479,7 @@ def extra_configs(args, torch, dist, timer, L, dev, rank, world, hbm):
          "by time: whole-second segments, 1 s lead-in instead of an IIR state exchange (SURVEY 8e permits a "
          "warm-up halo); 100 ms slot energies all-gathered (NCCL), peaks MAX-all-reduced, blocks / gates / range "
          "over the whole slot list on every rank" if world > 1 else "single GPU",
-         lambda m: {"loudness": m.loudness, "range": m.range})
+         lambda m: {"loudness": m.loudness, "range": m.range}, deep=False)
     shard.close()
     del seg, shard
     torch.cuda.empty_cache()
