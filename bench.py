@@ -162,6 +162,9 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def samples(self) -> int:
+        return len(self.rows)
+
     def __exit__(self, *exc):
         if self.proc:
             self.proc.terminate()
@@ -557,6 +560,14 @@ def gpu_arm(args):
     with ClockSampler(local) as clk:
         for _ in range(args.warmup + CLOCK_LOAD_STEPS[0]):
             step()
+        if world == 1:
+            # nvidia-smi's query (every 100 ms) holds up kernel launches for about a millisecond, a
+            # third of the timed region: keep the load running until a sample has just arrived,
+            # so that the next one is 100 ms away.  (With several ranks the steps are collective
+            # -- the album exchange -- and every rank runs the fixed count above.)
+            seen, t_end = clk.samples(), time.perf_counter() + 0.4
+            while clk.samples() == seen and time.perf_counter() < t_end:
+                step()
         barrier()
         # The K timed steps run three deep: steps k + 1 and k + 2 are enqueued before the
         # results of step k are fetched (lgb_batch_run keeps three result mirrors), so the
