@@ -88,9 +88,14 @@ def bench_config(world: int):
             "feed": f"ebur128_add_frames_short, {FEED_FRAMES}-frame calls from host PCM (scan.c:448), one scanner "
                     "thread per track up to the host cores per rank",
             "l2_policy": "input (495 MB per GPU) is larger than L2 (126 MB); no flush",
-            "step_overlap": "timed steps are enqueued three deep (runs k + 1 and k + 2 before fetch k) and "
-                            "pipelined on the GPU (the post-processing of run k finishes under the sweep of "
-                            "run k + 1); every step's results are read back and fetched inside the timed region",
+            "step_overlap": ("timed steps are enqueued three deep (runs k + 1 and k + 2 before fetch k) and "
+                             "pipelined on the GPU (the post-processing of run k finishes under the sweep of "
+                             "run k + 1); every step's results are read back and fetched inside the timed region"
+                             if world == 1 or os.environ.get("LOUDGAIN_B200_PIPELINE_EXCHANGE", "0") != "0" else
+                             "timed steps are enqueued three deep (runs k + 1 and k + 2 before fetch k), one CUDA "
+                             "graph per step on one stream (with the album exchange attached the runs are not "
+                             "pipelined on the GPU unless LOUDGAIN_B200_PIPELINE_EXCHANGE=1); every step's results "
+                             "are read back and fetched inside the timed region"),
             "clock_sampling": f"{CLOCK_LOAD_STEPS[0]} + {CLOCK_LOAD_STEPS[1]} untimed steps of the same load "
                               "around the timed steps, nvidia-smi every 100 ms",
             "sharding": "by track; one album over all ranks' tracks, gated inside the step over NVLink peer "

@@ -748,7 +748,8 @@ static int enqueue_step(lgb_batch* b, int parity) {
     if (e != cudaSuccess) { set_error("fork(post-processing stream)", e); return 1; }
     if (post_kernels()) return 1;
   }
-  if (enqueue_truepeak(b, t, fork)) return 1;
+  // (next to the forked post-processing the evaluation leaves room for a fix-up CTA per SM)
+  if (enqueue_truepeak(b, t, fork, fork ? 5u : 0u)) return 1;
   if (!fork && post_kernels()) return 1;
   if (enqueue_queries(b, t, ps, parity)) return 1;
   if (fork) {
@@ -918,7 +919,18 @@ extern "C" LG_EXPORT int lgb_batch_run(lgb_batch* b) {
   }
   // timed runs (bench roofline leg), traced runs and the first run launch directly
   const bool direct = b->timing || b->graph_off || (b->trace && !b->trace_pipelined) || k < 1;
-  if (!direct && b->pipeline && b->pstream && b->mstream && b->fstream) return enqueue_step_pipelined(b, parity);
+  // With an album exchange attached the runs are NOT pipelined by default: at two GPUs the
+  // pipelined step ran hundreds of thousands of times (0.190 ms against 0.26 ms, profiles/
+  // r02_bench_n2.json), but one run at two GPUs (with block buffers per mirror) and the one run
+  // at eight ended in an exchange time-out -- a rank that did not arrive within 20 s -- during
+  // the bench's single-step warm-up, and the cause was not found before the round's GPU time
+  // ran out.  LOUDGAIN_B200_PIPELINE_EXCHANGE=1 pipelines them all the same.
+  static const bool pipe_xchg = [] {
+    const char* e = getenv("LOUDGAIN_B200_PIPELINE_EXCHANGE");
+    return e && atoi(e) != 0;
+  }();
+  if (!direct && b->pipeline && b->pstream && b->mstream && b->fstream && (!b->xchg || pipe_xchg))
+    return enqueue_step_pipelined(b, parity);
   if (b->post_in_flight) {
     // behind pipelined runs: this run's kernels rewrite what their post-processing reads
     if (cudaEventRecord(b->ev_pidle, b->pstream) != cudaSuccess ||
