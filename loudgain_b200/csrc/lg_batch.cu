@@ -688,6 +688,8 @@ static int enqueue_queries(lgb_batch* b, const DeviceTables& t, cudaStream_t ps,
     step_mark(b, "x-finish", ps);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ps, b->ev_q1, 0);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ps, b->ev_q2, 0);
+    // behind both chains: the step counter every exchange kernel reads at its start
+    if (e == cudaSuccess) e = launch_exchange_advance(xp, ps);
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(x->h_ctl, x->d_ctl + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ps);
   } else if (qs && !b->timing) {
@@ -1384,8 +1386,8 @@ extern "C" LG_EXPORT int lgb_batch_attach_exchange(lgb_batch* b, lgb_exchange* x
     if (!ok) cudaGetLastError();        // (the fix-up then waits for the run before it)
     b->blocks_per_mirror = ok;
   }
-  if (!b->xchg) b->launches += 3u + (nt ? 2u : 0u);       // publish, gate, range, finish and the track queries as two
-                                                          // launches, instead of the one query launch
+  if (!b->xchg) b->launches += 4u + (nt ? 2u : 0u);       // publish, gate, range, finish, advance and the track
+                                                          // queries as two launches, instead of the one query launch
   b->xchg = x;
   return 0;
 }

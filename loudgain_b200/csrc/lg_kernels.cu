@@ -1304,10 +1304,18 @@ xchg_finish_kernel(QueryResult* __restrict__ results, const __grid_constant__ Xc
       o.rel_thr = tot.s1 / (double) tot.n1 * 0.1;
       if (tot.n2) o.loudness = energy_to_lufs(tot.s2 / (double) tot.n2);
     }
-    // the step is over on this rank once every album is done
-    __threadfence();
-    if (atomicAdd(X.ctl + 3, 1ull) == gridDim.x - 1) { X.ctl[3] = 0ull; X.ctl[0] = step + 1ull; }
   }
+}
+
+// The step is over on this rank: the step counter moves on.  Its own launch, behind BOTH chains of
+// the exchange (gate -> finish, and the albums' ranges on the stream next to it): every kernel
+// of a step reads the counter when it starts, and as long as the finish kernel advanced it, a
+// range kernel that started late -- behind the finish kernel of its own step: it runs on another
+// stream, needs most of an SM's shared memory, and at low priority it can wait for that -- read
+// the NEXT step's number, waited for flags nobody was going to raise before this step was
+// fetched, and the exchange timed out (seen once at two and once at eight GPUs).
+__global__ void xchg_advance_kernel(const __grid_constant__ XchgParams X) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) X.ctl[0] = X.ctl[0] + 1ull;
 }
 
 static cudaError_t launch_clustered(const void* kernel, uint32_t nalbums, uint32_t cluster, cudaStream_t stream,
@@ -1361,6 +1369,12 @@ cudaError_t launch_exchange_range(double abs_gate, QueryResult* results, const X
 cudaError_t launch_exchange_finish(QueryResult* results, const XchgParams& x, cudaStream_t stream) {
   if (!x.nalbums) return cudaSuccess;
   xchg_finish_kernel<<<x.nalbums, 64, 0, stream>>>(results, x);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_exchange_advance(const XchgParams& x, cudaStream_t stream) {
+  if (!x.nalbums) return cudaSuccess;
+  xchg_advance_kernel<<<1, 32, 0, stream>>>(x);
   return cudaGetLastError();
 }
 

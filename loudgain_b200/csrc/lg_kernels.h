@@ -86,6 +86,8 @@ cudaError_t launch_exchange_gate(const BlockList* lists, const Query* queries, c
 cudaError_t launch_exchange_range(double abs_gate, QueryResult* results, const XchgParams& x,
                                   uint32_t st_smem_doubles, cudaStream_t stream);
 cudaError_t launch_exchange_finish(QueryResult* results, const XchgParams& x, cudaStream_t stream);
+// ... and, behind every kernel of the step's exchange, the step counter moves on
+cudaError_t launch_exchange_advance(const XchgParams& x, cudaStream_t stream);
 // Sample peak and true peak (float bits, raw sample units) of track frames
 // [first, first + count) per channel into out[2 * channels] (device memory).
 cudaError_t launch_range_peaks(const void* pcm, uint32_t format, uint32_t channels, uint64_t first,
