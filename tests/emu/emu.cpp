@@ -452,6 +452,11 @@ extern "C" void emu_plan_sizes(const lgb_track* tracks, size_t ntracks, uint64_t
 // row's end), complete / partial rows are classified right, and every chunk of
 // every track is covered by exactly one lane.  Returns the number of items, or
 // -1 - (index of the first bad item).
+// lg_common.h: run_grid_ctas, for the planner's test
+extern "C" uint32_t emu_run_grid(uint32_t nitems, uint32_t sms, uint32_t warps, int spare) {
+  return run_grid_ctas(nitems, sms, warps, spare != 0);
+}
+
 extern "C" long long emu_check_run_view(const lgb_track* tracks, size_t ntracks, uint64_t target_tasks,
                                         long long* full_items) {
   std::vector<TrackIn> in(ntracks);
@@ -493,6 +498,14 @@ extern "C" long long emu_check_run_view(const lgb_track* tracks, size_t ntracks,
             if (c < tr.nchunks) ++covered[it.track][c];
           }
       }
+      // the launch grid and the CTAs' stretches of the candidate queue (lg_common.h: run_grid_ctas;
+      // CTA b owns the items b, b + grid, ...: the fullest CTA's lanes must fit its stretch)
+      const uint32_t grid = sp.run_grid;
+      ok = ok && grid >= 1 && grid <= g.nitems && grid <= opt.sms &&
+           grid == run_grid_ctas(g.nitems, opt.sms, sp.run_warps_per_sm, opt.spare_sms) &&
+           (uint64_t) sp.run_cta_cap >= (uint64_t) ((g.nitems + grid - 1) / grid) * 32u * sp.run_lane_stride &&
+           sp.run_lane_stride >= 2u * sp.npairs &&
+           (cs.tpf == 0 || g.queue_cap == (uint64_t) sp.run_cta_cap * grid);
       if (!ok) return -1 - (long long) (g.first_item + ii);
       ++nitems;
       if (it.tail_rows == 32) ++*full_items;

@@ -234,6 +234,31 @@ def test_run_view_of_a_plan(rate, seconds, dtype, monkeypatch):
         assert full.value <= got
 
 
+def test_run_sweep_grid():
+    """CTAs of the run sweep (lg_common.h: run_grid_ctas).  One round of work items: the SMs that
+    are used are filled up to the fullest sub-partition's level (warp w runs on sub-partition
+    w % 4) and the rest are left to the kernels of the run before (pipelined runs); several
+    rounds, or a tuning switch: every SM."""
+    import ctypes as C
+    from tests.helpers import build_emu
+    lib = C.CDLL(build_emu())
+    lib.emu_run_grid.restype = C.c_uint32
+    grid = lambda n, sms=148, warps=16, spare=1: lib.emu_run_grid(n, sms, warps, spare)
+    assert grid(2200) == 138                 # the 12-track album: 15 items per SM -> 16, ten SMs free
+    assert grid(2200, spare=0) == 148
+    assert grid(2368) == 148 and grid(2369) == 148 and grid(5000) == 148
+    assert grid(100) == 100 and grid(148) == 148 and grid(0) == 0
+    assert grid(1018) == 128                 # 7 per SM -> 8: two per sub-partition either way
+    assert grid(1200) == 100                 # 9 per SM -> 12
+    for n in range(149, 2369, 37):
+        g = grid(n)
+        per_sm = -(-n // 148)
+        fill = min(16, 4 * (-(-per_sm // 4)))
+        assert g <= 148 and g * fill >= n                     # every item has a warp in one round
+        assert -(-(-(-n // g)) // 4) == -(-per_sm // 4)       # no sub-partition fuller than on 148 SMs
+    assert grid(600, sms=4) == 4 and grid(3, sms=4) == 3
+
+
 def test_tail_filler_plan(oracle, monkeypatch):
     """Planner option behind LOUDGAIN_B200_TAIL_FRAC / _TAIL_DIV: the tracks that hold the
     last part of the batch get shorter chunks (their own launch group); results
