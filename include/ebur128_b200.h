@@ -69,15 +69,17 @@ lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t ntracks, uint32_t na
 
 /* Enqueues the whole measurement (sweep, fix-up, gating, range, read-back of the
  * scalars into pinned memory) on the batch's stream.  Asynchronous; 0 on success.
- * Up to two runs may be in flight: a caller that repeats a batch can enqueue run
- * k + 1 before it fetches run k, so that its own turn-around overlaps the GPU.
+ * Up to two runs may be in flight (three: lgb_batch_set_max_in_flight): a caller that repeats
+ * a batch can enqueue run k + 1 before it fetches run k, so that its own turn-around overlaps
+ * the GPU.
  * From the second run of a batch on, the runs are pipelined: only the sweep and the
  * true-peak evaluation (the kernels that read the PCM) stay on the batch's stream; the
  * fix-up, blocks, queries and read-back of run k finish on a stream of the library's own
  * while the sweep of run k + 1 is under way.  Work enqueued on the batch's stream after
  * this call is ordered behind the PCM reads and the slot energies, not behind the
  * results: those are reached through lgb_batch_fetch / lgb_batch_wait_blocks.
- * (LOUDGAIN_B200_PIPELINE=0: every run completely on the batch's stream.) */
+ * (LOUDGAIN_B200_PIPELINE=0: every run completely on the batch's stream; that is also how a
+ * batch with an album exchange attached runs unless LOUDGAIN_B200_PIPELINE_EXCHANGE=1.) */
 int lgb_batch_run(lgb_batch* b);
 
 /* How many runs may be in flight before the oldest has to be fetched: 1 to 3, 2 by default.
