@@ -72,12 +72,13 @@ lgb_batch* lgb_batch_create(const lgb_track* tracks, size_t ntracks, uint32_t na
  * Up to two runs may be in flight (three: lgb_batch_set_max_in_flight): a caller that repeats
  * a batch can enqueue run k + 1 before it fetches run k, so that its own turn-around overlaps
  * the GPU.
- * From the second run of a batch on, the runs are pipelined: only the sweep and the
- * true-peak evaluation (the kernels that read the PCM) stay on the batch's stream; the
- * fix-up, blocks, queries and read-back of run k finish on a stream of the library's own
- * while the sweep of run k + 1 is under way.  Work enqueued on the batch's stream after
- * this call is ordered behind the PCM reads and the slot energies, not behind the
- * results: those are reached through lgb_batch_fetch / lgb_batch_wait_blocks.
+ * From the second run of a batch on, the runs are pipelined: the sweep and the true-peak
+ * evaluation (the kernels that read the PCM) run on a high-priority stream of the library,
+ * ordered behind everything enqueued on the batch's stream so far; the fix-up, blocks,
+ * queries and read-back of run k finish on other streams of the library while the sweep of
+ * run k + 1 is under way.  Work enqueued on the batch's stream after this call is ordered
+ * behind the PCM reads of the run, not behind its slot / block energies or results: those
+ * are reached through lgb_batch_wait_blocks / lgb_batch_fetch.
  * (LOUDGAIN_B200_PIPELINE=0: every run completely on the batch's stream; that is also how a
  * batch with an album exchange attached runs unless LOUDGAIN_B200_PIPELINE_EXCHANGE=1.) */
 int lgb_batch_run(lgb_batch* b);
