@@ -141,3 +141,67 @@ def test_192k_has_no_oversampling(oracle):
     with oracle.init(1, rate) as st:
         st.add_frames(x)
         assert st.true_peak(0) == st.sample_peak(0)
+
+
+def _meter_trace(oracle, pcm, rate, hop_s, query):
+    """Feeds `pcm` in hops of `hop_s` seconds and reads the sliding-window meter after each."""
+    hop = int(round(hop_s * rate))
+    out = []
+    with oracle.init(pcm.shape[1], rate) as st:
+        for a in range(0, len(pcm) - hop + 1, hop):
+            st.add_frames(pcm[a:a + hop], 1024)
+            out.append(((a + hop) / rate, query(st)))
+    return out
+
+
+def test_tech3341_case9_shortterm_constant(oracle):
+    """EBU Tech 3341 case 9: 1.34 s at -20 dBFS then 1.66 s at -30 dBFS, five times -- every 3 s
+    window holds the same mix, so the short-term meter reads -23.0 +-0.1 LUFS from 3 s on."""
+    pcm = cases._stereo([(-20.0, 1.34), (-30.0, 1.66)] * 5)
+    trace = _meter_trace(oracle, pcm, cases.RATE, 0.1, lambda st: st.loudness_shortterm())
+    late = [v for t, v in trace if t >= 3.0]
+    assert len(late) > 100
+    assert max(abs(v + 23.0) for v in late) <= 0.1
+
+
+def test_tech3341_case12_momentary_constant(oracle):
+    """EBU Tech 3341 case 12: 0.18 s at -20 dBFS then 0.22 s at -30 dBFS, repeated -- every
+    400 ms window holds the same mix: the momentary meter reads -23.0 +-0.1 LUFS from 1 s on."""
+    pcm = cases._stereo([(-20.0, 0.18), (-30.0, 0.22)] * 25)
+    trace = _meter_trace(oracle, pcm, cases.RATE, 0.02, lambda st: st.loudness_momentary())
+    late = [v for t, v in trace if t >= 1.0]
+    assert len(late) > 400
+    assert max(abs(v + 23.0) for v in late) <= 0.1
+
+
+@pytest.mark.parametrize("lead_ms", [0, 150, 1000, 2850])
+def test_tech3341_cases10_13_window_maxima(oracle, lead_ms):
+    """EBU Tech 3341 cases 10 and 13: a -23 dBFS tone of exactly one window's length (3 s /
+    0.4 s) behind silences of different lengths and followed by silence -- the maximum of the
+    short-term / momentary meter is -23.0 +-0.1 LUFS wherever the tone starts."""
+    for window_s, query, hop in ((3.0, lambda st: st.loudness_shortterm(), 0.05),
+                                 (0.4, lambda st: st.loudness_momentary(), 0.01)):
+        pcm = cases._stereo([(-200.0, lead_ms / 1000.0 + 1e-9), (-23.0, window_s), (-200.0, 1.0)])
+        trace = _meter_trace(oracle, pcm, cases.RATE, hop, query)
+        best = max(v for _, v in trace)
+        assert abs(best + 23.0) <= 0.1, (window_s, lead_ms, best)
+
+
+def test_tech3341_cases11_14_rising_maxima(oracle):
+    """EBU Tech 3341 cases 11 and 14 (in their structure): tones of one window's length at
+    -38, -36 ... -20 dBFS, each between silences longer than the window -- the meter's maxima
+    within the successive segments step up by the same amounts, +-0.1 LU."""
+    levels = list(range(-38, -18, 2))
+    for window_s, query, hop in ((3.0, lambda st: st.loudness_shortterm(), 0.1),
+                                 (0.4, lambda st: st.loudness_momentary(), 0.02)):
+        gap = window_s + 0.6
+        parts = []
+        for lv in levels:
+            parts += [(-200.0, gap), (float(lv), window_s)]
+        pcm = cases._stereo(parts + [(-200.0, gap)])
+        trace = _meter_trace(oracle, pcm, cases.RATE, hop, query)
+        seg = gap + window_s
+        for i, lv in enumerate(levels):
+            lo, hi = i * seg + gap, (i + 1) * seg + gap - 0.5
+            best = max(v for t, v in trace if lo <= t <= hi)
+            assert abs(best - lv) <= 0.1, (window_s, lv, best)
